@@ -1,0 +1,121 @@
+"""CPU: the oracle restatement vs goldens produced by the reference's own Python
+files (tools/make_goldens.py, stub-loaded in the build container)."""
+import os
+
+import pytest
+import torch
+
+import oracle.mmri as ommri
+import oracle.mmpi as ommpi
+from deepinteraction_b200 import synth
+from tools.make_goldens import small_frame, make_decoder, state_checksum
+from conftest import rel_err
+
+G = os.path.join(os.path.dirname(__file__), 'golden')
+TOL = 5e-5   # fp32 re-association only; the goldens come from the reference's own torch code
+
+
+def load(name):
+    return torch.load(os.path.join(G, name + '.pt'), weights_only=False)
+
+
+@pytest.mark.parametrize('tag', ['i2p_cfg1', 'i2p_cfg1_aug'])
+def test_i2p_config1(tag):
+    g = load(tag)
+    torch.manual_seed(g['seed'])
+    m = ommri.MMRI_I2P(64, 64, 0.1).eval()
+    synth.randomize_norm_stats(m, g['seed'])
+    assert state_checksum(m.state_dict()) == g['checksum']
+    fr = synth.make_frame_batch(g['seed'], batch=2, num_views=1, in_hw=(256, 256), stride=4, c_img=64, c_pts=64,
+                                bev_hw=(32, 32), n_points=20000, aug=g['aug'])
+    pil, coors, npts = synth.pillarize([p.numpy() for p in fr['pts_metas']['pts']], pillar=108.0 / 32)
+    fr['pts_metas'].update(pillars=torch.from_numpy(pil), pillar_coors=torch.from_numpy(coors),
+                           pillars_num_points=torch.from_numpy(npts))
+    with torch.no_grad():
+        out = m(fr['pts_feats'], fr['img_feats'].view(2, 1, 64, 64, 64), fr['img_metas'], fr['pts_metas'])
+    assert rel_err(out, g['out']) < TOL
+    # empty pillars stay exactly zero
+    occupied = torch.zeros(2, 32, 32, dtype=torch.bool)
+    occupied[coors[:, 0], coors[:, 2], coors[:, 3]] = True
+    assert float(out.permute(0, 2, 3, 1)[~occupied].abs().max()) == 0.0
+
+
+def test_lcab():
+    g = load('lcab')
+    torch.manual_seed(g['seed'])
+    m = ommri.LocalContextAttentionBlock(32, 32, 9).eval()
+    synth.randomize_norm_stats(m, g['seed'])
+    assert state_checksum(m.state_dict()) == g['checksum']
+    gen = torch.Generator().manual_seed(g['seed'])
+    tgt, src = torch.randn(2, 32, 13, 21, generator=gen), torch.randn(2, 32, 13, 21, generator=gen)
+    with torch.no_grad():
+        assert rel_err(m(tgt, src), g['out']) < TOL
+
+
+@pytest.mark.parametrize('tag', ['bevwarp', 'bevwarp_aug'])
+def test_bevwarp(tag):
+    g = load(tag)
+    fr = small_frame(g['seed'], aug=g['aug'], views=2, c_img=8, c_pts=8, bev=36)
+    with torch.no_grad():
+        out = ommri.BEVWarp()(fr['pts_feats'], fr['img_feats'].view(1, 2, 8, 28, 50), fr['img_metas'], fr['pts_metas'])
+    assert rel_err(out, g['out']) < TOL
+
+
+@pytest.mark.parametrize('tag', ['encoder_small', 'encoder_small_aug'])
+def test_encoder_small(tag):
+    g = load(tag)
+    torch.manual_seed(g['seed'])
+    m = ommri.DeepInteractionEncoder(2, 16, 24, 32).eval()
+    synth.randomize_norm_stats(m, g['seed'])
+    assert state_checksum(m.state_dict()) == g['checksum']
+    fr = small_frame(g['seed'], aug=g['aug'], views=2, c_img=16, c_pts=24, bev=36, batch=2)
+    with torch.no_grad():
+        img, (p0, p1) = m(fr['img_feats'], fr['pts_feats'], fr['img_metas'], fr['pts_metas'])
+    assert rel_err(img, g['img']) < TOL and rel_err(p0, g['pts_conv']) < TOL and rel_err(p1, g['pts']) < TOL
+
+
+@pytest.mark.parametrize('tag', ['decoder_small', 'decoder_small_aug'])
+def test_decoder_small(tag):
+    g = load(tag)
+    torch.manual_seed(g['seed'])
+    m = make_decoder(ommpi.DeepInteractionDecoder).eval()
+    synth.randomize_norm_stats(m, g['seed'])
+    assert state_checksum(m.state_dict()) == g['checksum']
+    gen = torch.Generator().manual_seed(g['seed'])
+    fr = small_frame(g['seed'], aug=g['aug'], views=2, batch=2)
+    pts_in = [torch.randn(2, 128, 36, 36, generator=gen), torch.randn(2, 128, 36, 36, generator=gen)]
+    img_in = torch.randn(4, 128, 28, 50, generator=gen)
+    with torch.no_grad():
+        out = m(pts_in, img_in, fr['img_metas'])[0][0]
+    for k, ref in g['out'].items():
+        assert rel_err(out[k], ref) < 2e-4, k
+    assert bool((m.query_labels == g['query_labels']).all())
+    for a, b in zip(m.on_the_image_mask, g['on_the_image_mask']):
+        assert bool((a == b).all())
+
+
+def test_depth_completion_numpy_matches_cv2():
+    import numpy as np
+    from oracle import depth_completion as dc
+    rng = np.random.default_rng(3)
+    d = np.zeros((112, 200), np.float32)
+    ys, xs = rng.integers(30, 112, 3000), rng.integers(0, 200, 3000)
+    d[ys, xs] = rng.uniform(1, 70, 3000).astype(np.float32)
+    a, sa = dc.fill_in_multiscale(d, True)
+    b, sb = dc.fill_in_multiscale_numpy(d, True)
+    for k in ('s1', 's2', 's3', 's4', 's5', 's6', 's7m'):
+        assert np.array_equal(sa[k], sb[k]), k       # morphology and medians are exact
+    assert np.abs(a - b).max() < 1e-3                # bilateral: OpenCV LUT/SIMD rounding only
+
+
+def test_roi_align_matches_torchvision():
+    tvo = pytest.importorskip('torchvision.ops')
+    from oracle.geometry import roi_align
+    g = torch.Generator().manual_seed(0)
+    feat = torch.randn(8, 20, 30, generator=g)
+    boxes = torch.tensor([[2.0, 3.0, 17.5, 12.25], [-6.0, -4.0, 5.0, 8.0], [100.0, 60.0, 130.0, 90.0],
+                          [10.0, 10.0, 10.0, 10.0], [110.0, 70.0, 125.0, 85.0]])
+    for scale in (1.0, 0.25):
+        a = roi_align(feat, boxes, 7, scale, 2)
+        b = tvo.roi_align(feat[None], [boxes], 7, scale, 2, aligned=True)
+        assert torch.allclose(a, b, atol=1e-5)

@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.pt from the REFERENCE's own Python files.
+
+Runs only in the build container (needs /root/reference, read-only).  The
+reference package cannot be imported (mmcv/mmdet/mmdet3d/detectron2/spconv are
+absent), so its hot-path files are loaded BY PATH, unmodified, under their real
+dotted names with small ``sys.modules`` stubs for the absent third-party imports
+(SURVEY.md Appendix B).  What each stub assumes is documented next to it.
+
+Every golden stores: the config, the seed, a checksum of the weights, the inputs
+that are not re-creatable from the seed, and the reference outputs.  Weights are
+created by the ORACLE modules under the seed and loaded into the reference
+modules with ``load_state_dict(strict=True)`` -- which also pins state-dict key
+compatibility.  tests/test_oracle_golden.py re-creates them from the seed.
+
+Usage:  python tools/make_goldens.py [--ref /root/reference] [--out tests/golden]
+"""
+import argparse
+import hashlib
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import oracle.geometry as og          # noqa: E402
+import oracle.mmri as ommri            # noqa: E402
+import oracle.mmpi as ommpi            # noqa: E402
+from deepinteraction_b200 import synth  # noqa: E402
+
+PLUGIN = 'projects/mmdet3d_plugin'
+
+
+def _mod(name):
+    m = types.ModuleType(name)
+    sys.modules[name] = m
+    return m
+
+
+def _load(name, path):
+    spec = importlib.util.spec_from_file_location(name, path)
+    m = importlib.util.module_from_spec(spec)
+    sys.modules[name] = m
+    spec.loader.exec_module(m)
+    return m
+
+
+class _Registry:
+    def __init__(self):
+        self.d = {}
+
+    def register_module(self, *a, **k):
+        def deco(cls):
+            self.d[cls.__name__] = cls
+            return cls
+        return deco
+
+    def build(self, cfg):
+        cfg = dict(cfg)
+        return self.d[cfg.pop('type')](**cfg)
+
+
+def install_stubs(ref):
+    np.bool = bool                                    # depth_map_utils.py:209,226 (numpy<1.24 alias)
+    for n in ['projects', 'projects.mmdet3d_plugin', 'projects.mmdet3d_plugin.models',
+              'projects.mmdet3d_plugin.models.utils', 'projects.mmdet3d_plugin.models.utils.ops',
+              'projects.mmdet3d_plugin.models.utils.ip_basic', 'projects.mmdet3d_plugin.models.necks',
+              'projects.mmdet3d_plugin.models.dense_heads', 'projects.mmdet3d_plugin.core',
+              'projects.mmdet3d_plugin.core.bbox', 'projects.mmdet3d_plugin.core.bbox.coders',
+              'mmcv', 'mmcv.cnn', 'mmcv.cnn.bricks', 'mmcv.cnn.bricks.transformer', 'mmcv.runner',
+              'mmdet3d', 'mmdet3d.models', 'mmdet3d.models.fusion_layers', 'mmdet3d.models.builder',
+              'mmdet3d.models.utils', 'mmdet3d.core', 'mmdet3d.ops', 'mmdet3d.ops.iou3d',
+              'mmdet3d.ops.iou3d.iou3d_utils', 'mmdet', 'mmdet.core', 'mmdet.core.bbox', 'mmdet.core.bbox.builder',
+              'detectron2', 'detectron2.modeling', 'detectron2.modeling.poolers', 'detectron2.structures']:
+        _mod(n)
+    sm = sys.modules
+    # mmdet3d 0.17.1 coord transform: restated in oracle.geometry (third party, unpinned)
+    sm['mmdet3d.models.fusion_layers'].apply_3d_transformation = \
+        lambda pcd, coords_type, img_meta, reverse=False: og.apply_3d_transformation(pcd, img_meta, reverse)
+
+    # locatt_ops has no CPU path: semantics of kernels.cuh:4-80 via the oracle's shifted-MAC ops
+    class _LA:
+        similar_forward = staticmethod(lambda q, k, kh, kw: ommri.window_similarity(q, k, kh))
+        weighting_forward = staticmethod(lambda v, w, kh, kw: ommri.window_weighting(v, w, kh))
+    ops = sm['projects.mmdet3d_plugin.models.utils.ops']
+    ops.locatt_ops = types.SimpleNamespace(localattention=_LA)
+
+    # mmcv 1.3.18
+    def build_conv_layer(cfg, *a, **k):
+        k = dict(k)
+        if k.get('bias', True) == 'auto':
+            k['bias'] = True
+        return getattr(nn, cfg['type'])(*a, **k)
+
+    class ConvModule(nn.Module):
+        def __init__(self, cin, cout, kernel_size, stride=1, padding=0, bias='auto', conv_cfg=None, norm_cfg=None,
+                     **kw):
+            super().__init__()
+            with_norm = norm_cfg is not None
+            if bias == 'auto':
+                bias = not with_norm
+            dim = conv_cfg['type'][-2:]
+            self.conv = getattr(nn, 'Conv' + dim)(cin, cout, kernel_size, stride, padding, bias=bias)
+            if with_norm:
+                self.bn = getattr(nn, 'BatchNorm' + dim)(cout)
+            self.activate = nn.ReLU(inplace=True)
+
+        def forward(self, x):
+            x = self.conv(x)
+            if hasattr(self, 'bn'):
+                x = self.bn(x)
+            return self.activate(x)
+    sm['mmcv.cnn'].build_conv_layer = build_conv_layer
+    sm['mmcv.cnn'].ConvModule = ConvModule
+    sm['mmcv.cnn'].kaiming_init = lambda *a, **k: None
+    sm['mmcv.cnn.bricks.transformer'].FFN = object
+    sm['mmcv.runner'].force_fp32 = lambda *a, **k: (lambda f: f)
+    necks, heads, coders = _Registry(), _Registry(), _Registry()
+    sm['mmdet3d.models.builder'].NECKS = necks
+    sm['mmdet3d.models.builder'].HEADS = heads
+    sm['mmdet3d.models.builder'].build_loss = lambda cfg: None
+    sm['mmdet3d.models.utils'].clip_sigmoid = None
+    sm['mmdet3d.ops.iou3d.iou3d_utils'].nms_gpu = None
+    for n in ['circle_nms', 'draw_heatmap_gaussian', 'gaussian_radius', 'xywhr2xyxyr', 'PseudoSampler']:
+        setattr(sm['mmdet3d.core'], n, None)
+
+    class LiDARInstance3DBoxes:                       # mmdet3d 0.17.1 (third party, unpinned)
+        def __init__(self, tensor, box_dim=7):
+            self.tensor = tensor
+
+        @property
+        def corners(self):
+            return og.lidar_box_corners(self.tensor)
+    sm['mmdet3d.core'].LiDARInstance3DBoxes = LiDARInstance3DBoxes
+    sm['mmdet.core.bbox'].BaseBBoxCoder = object
+    sm['mmdet.core.bbox.builder'].BBOX_CODERS = coders
+    sm['mmdet.core'].build_bbox_coder = coders.build
+    for n in ['multi_apply', 'build_assigner', 'build_sampler', 'AssignResult']:
+        setattr(sm['mmdet.core'], n, None)
+
+    # detectron2 ROIPooler(ROIAlignV2, one level) == torchvision roi_align(aligned=True)
+    import torchvision.ops as tvo
+
+    class Boxes:
+        def __init__(self, t):
+            self.tensor = t
+
+    class ROIPooler:
+        def __init__(self, output_size, scales, sampling_ratio, pooler_type):
+            self.o, self.s, self.r = output_size, scales[0], sampling_ratio
+
+        def __call__(self, feats, boxes):
+            return tvo.roi_align(feats[0], [b.tensor for b in boxes], self.o, self.s, self.r, aligned=True)
+    sm['detectron2.modeling.poolers'].ROIPooler = ROIPooler
+    sm['detectron2.structures'].Boxes = Boxes
+
+    P = os.path.join(ref, PLUGIN)
+    _load('projects.mmdet3d_plugin.models.utils.ip_basic.depth_map_utils',
+          os.path.join(P, 'models/utils/ip_basic/depth_map_utils.py'))
+    sm['projects.mmdet3d_plugin.models.utils.ip_basic'].depth_map_utils = \
+        sm['projects.mmdet3d_plugin.models.utils.ip_basic.depth_map_utils']
+    eu = _load('projects.mmdet3d_plugin.models.utils.encoder_utils', os.path.join(P, 'models/utils/encoder_utils.py'))
+    enc = _load('projects.mmdet3d_plugin.models.necks.deepinteraction_encoder',
+                os.path.join(P, 'models/necks/deepinteraction_encoder.py'))
+    _load('projects.mmdet3d_plugin.core.bbox.coders.transfusion_bbox_coder',
+          os.path.join(P, 'core/bbox/coders/transfusion_bbox_coder.py'))
+    du = _load('projects.mmdet3d_plugin.models.utils.decoder_utils', os.path.join(P, 'models/utils/decoder_utils.py'))
+    dec = _load('projects.mmdet3d_plugin.models.dense_heads.deepinteraction_decoder',
+                os.path.join(P, 'models/dense_heads/deepinteraction_decoder.py'))
+    return eu, enc, du, dec
+
+
+def state_checksum(sd):
+    h = hashlib.sha256()
+    for k in sorted(sd):
+        h.update(k.encode())
+        h.update(sd[k].detach().cpu().contiguous().numpy().tobytes())
+    return h.hexdigest()[:16]
+
+
+# ---- golden cases (shared with tests/test_oracle_golden.py through golden_cases()) ----------------
+
+DEC_TEST_CFG = dict(dataset='nuScenes', grid_size=[288, 288, 40], out_size_factor=8, pc_range=[-54.0, -54.0],
+                    voxel_size=[0.375, 0.375], nms_type=None)
+DEC_CODER = dict(type='TransFusionBBoxCoder', pc_range=[-54.0, -54.0], voxel_size=[0.375, 0.375], out_size_factor=8,
+                 post_center_range=[-61.2, -61.2, -10.0, 61.2, 61.2, 10.0], score_threshold=0.0, code_size=10)
+
+
+def small_frame(seed, aug=False, views=2, c_img=16, c_pts=24, bev=36, batch=1, n_points=6000):
+    """Small scene: input images 112x200 (features 28x50), BEV bev x bev over +-54 m."""
+    fr = synth.make_frame_batch(seed, batch=batch, num_views=views, in_hw=(112, 200), stride=4, c_img=c_img,
+                                c_pts=c_pts, bev_hw=(bev, bev), n_points=n_points, cloud='lidar', aug=aug)
+    # re-pillarise at the small BEV resolution
+    pil, coors, npts = synth.pillarize([p.numpy() for p in fr['pts_metas']['pts']], pillar=108.0 / bev)
+    fr['pts_metas'].update(pillars=torch.from_numpy(pil), pillar_coors=torch.from_numpy(coors),
+                           pillars_num_points=torch.from_numpy(npts))
+    return fr
+
+
+def make_decoder(cls, views=2, proposals=24):
+    return cls(num_views=views, out_size_factor_img=4, num_proposals=proposals, auxiliary=True, hidden_channel=128,
+               num_classes=10, num_mmpi=4, num_heads=8, initialize_by_heatmap=True, nms_kernel_size=3,
+               ffn_channel=256, dropout=0.1, bn_momentum=0.1, activation='relu',
+               common_heads=dict(center=(2, 2), height=(1, 2), dim=(3, 2), rot=(2, 2), vel=(2, 2)),
+               loss_cls=dict(type='FocalLoss', use_sigmoid=True, gamma=2, alpha=0.25, reduction='mean',
+                             loss_weight=1.0),
+               bbox_coder=dict(DEC_CODER), test_cfg=dict(DEC_TEST_CFG))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--ref', default='/root/reference')
+    ap.add_argument('--out', default=os.path.join(ROOT, 'tests', 'golden'))
+    args = ap.parse_args()
+    os.makedirs(args.out, exist_ok=True)
+    eu, enc, du, dec = install_stubs(args.ref)
+    torch.set_grad_enabled(False)
+    report = []
+
+    def save(name, obj):
+        torch.save(obj, os.path.join(args.out, name + '.pt'))
+        sz = os.path.getsize(os.path.join(args.out, name + '.pt'))
+        report.append(f'{name}: {sz / 1024:.0f} KiB')
+
+    def cmp(a, b):
+        return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+
+    # --- G1: config 1 of BASELINE.json: single MMRI_I2P, 32x32 BEV C=64, 1 cam 64x64 ---------------
+    for tag, aug in (('i2p_cfg1', False), ('i2p_cfg1_aug', True)):
+        seed = 1235
+        torch.manual_seed(seed)
+        om = ommri.MMRI_I2P(64, 64, 0.1).eval()
+        synth.randomize_norm_stats(om, seed)
+        rm = eu.MMRI_I2P(64, 64, 0.1).eval()
+        rm.load_state_dict(om.state_dict(), strict=True)
+        fr = synth.make_frame_batch(seed, batch=2, num_views=1, in_hw=(256, 256), stride=4, c_img=64, c_pts=64,
+                                    bev_hw=(32, 32), n_points=20000, aug=aug)
+        pil, coors, npts = synth.pillarize([p.numpy() for p in fr['pts_metas']['pts']], pillar=108.0 / 32)
+        fr['pts_metas'].update(pillars=torch.from_numpy(pil), pillar_coors=torch.from_numpy(coors),
+                               pillars_num_points=torch.from_numpy(npts))
+        lidar = fr['pts_feats']
+        img = fr['img_feats'].view(2, 1, 64, 64, 64)
+        ref_out = rm(lidar, img, fr['img_metas'], fr['pts_metas'])
+        ora_out = om(lidar, img, fr['img_metas'], fr['pts_metas'])
+        print(tag, 'oracle vs reference rel err', cmp(ora_out, ref_out), 'pillars', len(npts))
+        save(tag, dict(seed=seed, aug=aug, checksum=state_checksum(om.state_dict()), out=ref_out))
+
+    # --- G2: LocalContextAttentionBlock, cross (target != source) ----------------------------------
+    seed = 1300
+    torch.manual_seed(seed)
+    om = ommri.LocalContextAttentionBlock(32, 32, 9).eval()
+    synth.randomize_norm_stats(om, seed)
+    rm = eu.LocalContextAttentionBlock(32, 32, 9).eval()
+    rm.load_state_dict(om.state_dict(), strict=True)
+    g = torch.Generator().manual_seed(seed)
+    tgt, src = torch.randn(2, 32, 13, 21, generator=g), torch.randn(2, 32, 13, 21, generator=g)
+    ref_out = rm(tgt, src)
+    print('lcab oracle vs reference', cmp(om(tgt, src), ref_out))
+    save('lcab', dict(seed=seed, checksum=state_checksum(om.state_dict()), out=ref_out))
+
+    # --- G3: BEVWarp (incl. cv2 depth completion) ---------------------------------------------------
+    for tag, aug in (('bevwarp', False), ('bevwarp_aug', True)):
+        seed = 1400
+        fr = small_frame(seed, aug=aug, views=2, c_img=8, c_pts=8, bev=36)
+        lidar = fr['pts_feats']
+        img = fr['img_feats'].view(1, 2, 8, 28, 50)
+        ref_out = eu.BEVWarp()(lidar, img, fr['img_metas'], fr['pts_metas'])
+        ora_out = ommri.BEVWarp()(lidar, img, fr['img_metas'], fr['pts_metas'])
+        print(tag, 'oracle vs reference', cmp(ora_out, ref_out), 'nonzero frac', float((ref_out != 0).float().mean()))
+        save(tag, dict(seed=seed, aug=aug, out=ref_out))
+
+    # --- G4: full small encoder ----------------------------------------------------------------------
+    for tag, aug in (('encoder_small', False), ('encoder_small_aug', True)):
+        seed = 1500
+        torch.manual_seed(seed)
+        om = ommri.DeepInteractionEncoder(2, 16, 24, 32).eval()
+        synth.randomize_norm_stats(om, seed)
+        rm = enc.DeepInteractionEncoder(num_layers=2, in_channels_img=16, in_channels_pts=24, hidden_channel=32).eval()
+        rm.load_state_dict(om.state_dict(), strict=True)
+        fr = small_frame(seed, aug=aug, views=2, c_img=16, c_pts=24, bev=36, batch=2)
+        r_img, (r_p0, r_p1) = rm(fr['img_feats'], fr['pts_feats'], fr['img_metas'], fr['pts_metas'])
+        o_img, (o_p0, o_p1) = om(fr['img_feats'], fr['pts_feats'], fr['img_metas'], fr['pts_metas'])
+        print(tag, 'oracle vs reference', cmp(o_img, r_img), cmp(o_p0, r_p0), cmp(o_p1, r_p1))
+        save(tag, dict(seed=seed, aug=aug, checksum=state_checksum(om.state_dict()), img=r_img, pts_conv=r_p0,
+                       pts=r_p1))
+
+    # --- G5: decoder (hidden 128 is hard-coded in DynamicConv) ----------------------------------------
+    for tag, aug in (('decoder_small', False), ('decoder_small_aug', True)):
+        seed = 1600
+        torch.manual_seed(seed)
+        om = make_decoder(ommpi.DeepInteractionDecoder).eval()
+        synth.randomize_norm_stats(om, seed)
+        rm = make_decoder(dec.DeepInteractionDecoder).eval()
+        missing = rm.load_state_dict(om.state_dict(), strict=True)
+        g = torch.Generator().manual_seed(seed)
+        fr = small_frame(seed, aug=aug, views=2, batch=2)
+        pts_in = [torch.randn(2, 128, 36, 36, generator=g), torch.randn(2, 128, 36, 36, generator=g)]
+        img_in = torch.randn(4, 128, 28, 50, generator=g)
+        r = rm(pts_in, img_in, fr['img_metas'])[0][0]
+        o = om(pts_in, img_in, fr['img_metas'])[0][0]
+        for k in r:
+            print(tag, k, tuple(r[k].shape), 'oracle vs reference', cmp(o[k], r[k]))
+        print(tag, 'labels equal', bool((rm.query_labels == om.query_labels).all()),
+              'on-image', [int(m.sum()) for m in rm.on_the_image_mask])
+        save(tag, dict(seed=seed, aug=aug, checksum=state_checksum(om.state_dict()), out=r,
+                       query_labels=rm.query_labels, on_the_image_mask=rm.on_the_image_mask))
+    print('\n'.join(report))
+
+
+if __name__ == '__main__':
+    main()
