@@ -1,0 +1,78 @@
+"""ctypes binding of libdi_b200.so (the C-ABI declared in include/di_b200.h).
+
+There is no fallback: if the library is missing or a call fails, a RuntimeError is raised.
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libdi_b200.so')
+
+_p = ctypes.c_void_p
+_i = ctypes.c_int
+_ll = ctypes.c_longlong
+_f = ctypes.c_float
+_fp = ctypes.POINTER(ctypes.c_float)
+
+# name -> argument ctypes (all functions return int; see include/di_b200.h)
+SIGNATURES = {
+    'di_version': [],
+    'di_built_arch': [],
+    # gemm.cu
+    'di_linear_f32': [_p, _i, _i, _p, _i, _i, _p, _i, _i, _p, _p, _p, _i, _i, _p, _i, _i, _i, _i, _i, _ll, _p],
+    'di_conv3x3_f32': [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
+    # lcab.cu
+    'di_lcab_window_f32': [_p, _i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _p],
+    # geometry.cu
+    'di_gather_rows_f32': [_p, _p, _p, _i, _i, _i, _i, _p],
+    'di_scatter_rows_f32': [_p, _p, _p, _p, _i, _i, _i, _i, _p],
+    'di_i2p_attend_f32': [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
+    'di_depth_scatter': [_p, _i, _i, _p, _p, _i, _i, _i, _i, _i, _p],
+    'di_depth_complete': [_p, _p, _p, _p, _i, _i, _i, _p],
+    'di_lift_grid': [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _fp, _p],
+    'di_bev_sample_f32': [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
+    # decoder.cu
+    'di_heatmap_nms_f32': [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
+    'di_topk_f32': [_p, _p, _i, _i, _i, _p],
+    'di_query_init_f32': [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
+    'di_mha_small_f32': [_p, _i, _p, _i, _p, _i, _p, _i, _p, _p, _i, _i, _i, _i, _p],
+    'di_cross_attn_f32': [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
+    'di_rows_finish_f32': [_p, _i, _ll, _i, _p, _p, _i, _p, _p, _p, _i, _p, _i, _i, _i, _f, _p],
+    'di_pred_finish_f32': [_p, _p, _p, _p, _i, _i, _p],
+    'di_rcnn_rois_f32': [_p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _fp, _p],
+    'di_roi_align_f32': [_p, _p, _p, _i, _i, _i, _i, _f, _p],
+    'di_dynconv_f32': [_p, _p, _p, _p, _p, _p, _p, _i, _f, _p],
+    'di_nchw_to_nhwc_f32': [_p, _p, _i, _i, _i, _p],
+    'di_nhwc_to_nchw_f32': [_p, _p, _i, _i, _i, _p],
+}
+
+_lib = None
+
+
+def lib():
+    """Load the library once; raise loudly when it is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f'{LIB_PATH} not found: build it with `python -m deepinteraction_b200.build` '
+                '(nvcc, sm_100a).  There is no CPU/PyTorch fallback for the MMRI/MMPI kernels.')
+        L = ctypes.CDLL(LIB_PATH)
+        L.di_last_error.restype = ctypes.c_char_p
+        L.di_last_error.argtypes = []
+        for name, args in SIGNATURES.items():
+            fn = getattr(L, name)          # AttributeError if a declared symbol is missing
+            fn.restype = ctypes.c_int
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def last_error():
+    return lib().di_last_error().decode()
+
+
+def check(rc, what=''):
+    if rc < 0:
+        raise RuntimeError(f'libdi_b200 {what}: {last_error()} (status {rc})')
+    return rc

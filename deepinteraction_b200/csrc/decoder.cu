@@ -1,0 +1,836 @@
+// MMPI decoder kernels (forward).  Reference (projects/mmdet3d_plugin/):
+//   models/dense_heads/deepinteraction_decoder.py:223-253  heatmap fusion, 3x3 max-pool NMS, top-k, query init
+//   models/utils/decoder_utils.py:35-113,246-495         transformer decoder layer (self + cross attention)
+//   models/utils/decoder_utils.py:632-841                 Image/Point RCNN blocks (box decode, projection,
+//                                                         RoIAlign 7x7, masked self-attention, DynamicConv)
+//   core/bbox/coders/transfusion_bbox_coder.py:39-76      box decode
+// Queries are stored row-major [B*P, C] ("one query = one row"); feature maps are pixel-major (NHWC).
+#include "common.cuh"
+#include <math.h>
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// Heatmap fusion + NMS  (decoder.py:225-239)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+__global__ void heatmap_nms_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
+                                   int K, int H, int W, int ks, unsigned no_nms_mask, int total) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int x = i % W, y = (i / W) % H, c = (i / (W * H)) % K;
+  const float* pa = a + (i - y * W - x);
+  const float* pb = b + (i - y * W - x);
+  float hc = (sigmoidf_(pa[y * W + x]) + sigmoidf_(pb[y * W + x])) * 0.5f;
+  float res;
+  if ((no_nms_mask >> c) & 1u) {
+    res = hc;
+  } else {
+    int r = ks / 2;
+    if (y < r || y >= H - r || x < r || x >= W - r) {
+      res = 0.f;  // local_max stays 0 on the border ring => never equal to a positive score
+    } else {
+      float m = hc;
+      for (int dy = -r; dy <= r; ++dy)
+        for (int dx = -r; dx <= r; ++dx) {
+          int o = (y + dy) * W + x + dx;
+          m = fmaxf(m, (sigmoidf_(pa[o]) + sigmoidf_(pb[o])) * 0.5f);
+        }
+      res = hc == m ? hc : 0.f;
+    }
+  }
+  out[i] = res;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Top-k of non-negative scores (descending, ties -> smaller index first).  One CTA per batch row.
+// Radix select on the float bit pattern (12 + 12 + 8 bits), then a bitonic sort of the k winners.
+// ------------------------------------------------------------------------------------------------
+constexpr int TOPK_MAX = 1024;
+
+__global__ void __launch_bounds__(1024)
+topk_kernel(const float* __restrict__ scores, int* __restrict__ idx_out, int n, int k) {
+  __shared__ unsigned hist[4096];
+  __shared__ unsigned s_prefix, s_need, s_cnt_gt, s_cnt_eq;
+  __shared__ unsigned long long cand[TOPK_MAX];  // (value bits << 32) | (0xffffffff - index): sort descending
+  __shared__ unsigned eq_idx[TOPK_MAX];
+  const float* s = scores + (size_t)blockIdx.x * n;
+  const int t = threadIdx.x;
+  unsigned prefix = 0, need = (unsigned)k;
+  // pass p examines bits [hi, lo)
+  const int shifts[3] = {20, 8, 0};
+  const int widths[3] = {12, 12, 8};
+  unsigned known_mask = 0;
+  for (int pass = 0; pass < 3; ++pass) {
+    for (int i = t; i < 4096; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    const int sh = shifts[pass];
+    const unsigned wmask = (1u << widths[pass]) - 1u;
+    for (int i = t; i < n; i += blockDim.x) {
+      unsigned u = __float_as_uint(s[i]);
+      if ((u & known_mask) == prefix) atomicAdd(&hist[(u >> sh) & wmask], 1u);
+    }
+    __syncthreads();
+    if (t == 0) {
+      unsigned acc = 0;
+      int bin = (int)wmask;
+      for (; bin > 0; --bin) {
+        if (acc + hist[bin] >= need) break;
+        acc += hist[bin];
+      }
+      s_prefix = prefix | ((unsigned)bin << sh);
+      s_need = need - acc;
+    }
+    __syncthreads();
+    prefix = s_prefix;
+    need = s_need;
+    known_mask |= wmask << sh;
+    __syncthreads();
+  }
+  // prefix == bit pattern of the k-th largest value; `need` of the elements equal to it are taken
+  if (t == 0) {
+    s_cnt_gt = 0;
+    s_cnt_eq = 0;
+  }
+  for (int i = t; i < TOPK_MAX; i += blockDim.x) cand[i] = 0ull;
+  __syncthreads();
+  for (int i = t; i < n; i += blockDim.x) {
+    unsigned u = __float_as_uint(s[i]);
+    if (u > prefix) {
+      unsigned pos = atomicAdd(&s_cnt_gt, 1u);
+      cand[pos] = ((unsigned long long)u << 32) | (unsigned long long)(0xffffffffu - (unsigned)i);
+    } else if (u == prefix) {
+      unsigned pos = atomicAdd(&s_cnt_eq, 1u);
+      if (pos < TOPK_MAX) eq_idx[pos] = (unsigned)i;
+    }
+  }
+  __syncthreads();
+  // ties at the threshold: take the `need` smallest indices (a single thread; ties are measure-zero)
+  if (t == 0) {
+    unsigned ne = min(s_cnt_eq, (unsigned)TOPK_MAX);
+    for (unsigned a = 0; a < need; ++a) {
+      unsigned best = a;
+      for (unsigned b2 = a + 1; b2 < ne; ++b2)
+        if (eq_idx[b2] < eq_idx[best]) best = b2;
+      unsigned tmp = eq_idx[a];
+      eq_idx[a] = eq_idx[best];
+      eq_idx[best] = tmp;
+      cand[s_cnt_gt + a] = ((unsigned long long)prefix << 32) | (unsigned long long)(0xffffffffu - eq_idx[a]);
+    }
+  }
+  __syncthreads();
+  // bitonic sort, descending, over TOPK_MAX slots (empty slots are 0 and sink to the end)
+  for (int size = 2; size <= TOPK_MAX; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = t; i < TOPK_MAX / 2; i += blockDim.x) {
+        int lo = (i / stride) * stride * 2 + (i % stride);
+        int hi = lo + stride;
+        bool desc = ((lo / size) & 1) == 0;
+        unsigned long long a = cand[lo], b2 = cand[hi];
+        if ((a < b2) == desc) {
+          cand[lo] = b2;
+          cand[hi] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = t; i < k; i += blockDim.x)
+    idx_out[(size_t)blockIdx.x * k + i] = (int)(0xffffffffu - (unsigned)(cand[i] & 0xffffffffull));
+}
+
+// query_feat[b,q,:] = feat[b, pix, :] + Wce[cls, :] + bce ; query_pos = (x+.5, y+.5) ; score gather
+__global__ void query_init_kernel(const float* __restrict__ feat, const int* __restrict__ top,
+                                  const float* __restrict__ heat, const float* __restrict__ wce_t,
+                                  const float* __restrict__ bce, float* __restrict__ qfeat, float* __restrict__ qpos,
+                                  int* __restrict__ labels, float* __restrict__ qscore, int HW, int W, int C, int K,
+                                  int P) {
+  int bq = blockIdx.x;  // b*P + q
+  int b = bq / P, qi = bq - b * P;
+  int flat = top[bq];
+  int cls = flat / HW, pix = flat - cls * HW;
+  const float* src = feat + ((size_t)b * HW + pix) * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x)
+    qfeat[(size_t)bq * C + c] = src[c] + wce_t[(size_t)cls * C + c] + bce[c];
+  if (threadIdx.x == 0) {
+    qpos[bq * 2 + 0] = (float)(pix % W) + 0.5f;
+    qpos[bq * 2 + 1] = (float)(pix / W) + 0.5f;
+    labels[bq] = cls;
+  }
+  for (int c = threadIdx.x; c < K; c += blockDim.x)
+    qscore[((size_t)b * K + c) * P + qi] = heat[((size_t)b * K + c) * HW + pix];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Small multi-head attention among the P queries of one sample (self-attention of the transformer
+// layer and of the RCNN blocks).  One warp per (query, head).  Optional group mask: key j is visible to
+// query q iff (onbits[j] >> win[q]) & 1 (queries that project into the same camera view).
+// ------------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256)
+mha_small_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk, const float* __restrict__ v,
+                 int ldv, float* __restrict__ out, int ldo, const int* __restrict__ onbits, const int* __restrict__ win,
+                 int B, int P, int Hh) {
+  int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (wid >= B * P * Hh) return;
+  int head = wid % Hh, bq = wid / Hh;
+  int b = bq / P;
+  int wq = win ? win[bq] : 0;
+  float* o = out + (size_t)bq * ldo + head * D;
+  if (wq < 0) {
+    if (lane < D) o[lane] = 0.f;
+    return;
+  }
+  float qr[D];
+#pragma unroll
+  for (int d = 0; d < D; d += 4) {
+    float4 t4 = ldg4(q + (size_t)bq * ldq + head * D + d);
+    qr[d] = t4.x; qr[d + 1] = t4.y; qr[d + 2] = t4.z; qr[d + 3] = t4.w;
+  }
+  // pass 1: scores of this lane's keys
+  constexpr int MAXK = 16;  // P <= 512
+  float sc[MAXK];
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < MAXK; ++i) {
+    int j = i * 32 + lane;
+    sc[i] = -INFINITY;
+    if (j < P) {
+      int bj = b * P + j;
+      bool vis = onbits ? ((onbits[bj] >> wq) & 1) : true;
+      if (vis) {
+        const float* kr = k + (size_t)bj * ldk + head * D;
+        float s = 0.f;
+#pragma unroll
+        for (int d = 0; d < D; d += 4) {
+          float4 t4 = ldg4(kr + d);
+          s += qr[d] * t4.x + qr[d + 1] * t4.y + qr[d + 2] * t4.z + qr[d + 3] * t4.w;
+        }
+        sc[i] = s;
+        m = fmaxf(m, s);
+      }
+    }
+  }
+  m = warp_max(m);
+  float acc[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) acc[d] = 0.f;
+  float l = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXK; ++i) {
+    int j = i * 32 + lane;
+    if (j < P && sc[i] > -INFINITY) {
+      float p = expf(sc[i] - m);
+      l += p;
+      const float* vr = v + (size_t)(b * P + j) * ldv + head * D;
+#pragma unroll
+      for (int d = 0; d < D; d += 4) {
+        float4 t4 = ldg4(vr + d);
+        acc[d] += p * t4.x; acc[d + 1] += p * t4.y; acc[d + 2] += p * t4.z; acc[d + 3] += p * t4.w;
+      }
+    }
+  }
+  l = warp_sum(l);
+  float inv = l > 0.f ? 1.f / l : 0.f;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    float a = warp_sum(acc[d]);
+    if (lane == d) o[d] = a * inv;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Query x BEV cross attention (decoder_utils.py:101-103,466-488): P queries x HW keys, Hh heads of D=16.
+// kv [B*HW, 2*C]: projected keys (cols [0,C)) and values (cols [C,2C)).  Split over key chunks
+// (flash-decoding): each CTA = (key chunk, head, batch, query tile of 256) keeps a running
+// (max, sum, acc[D]) per query; a second kernel merges the chunks.
+// ------------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256)
+cross_attn_kernel(const float* __restrict__ q, const float* __restrict__ kv, float* __restrict__ part, int P, int HW,
+                  int C, int Hh, int chunk, int nsplit) {
+  constexpr int TK = 128;                        // keys per shared-memory tile
+  __shared__ __align__(16) float ks[TK][D];
+  __shared__ __align__(16) float vs[TK][D];
+  const int split = blockIdx.x % nsplit, qt = blockIdx.x / nsplit;
+  const int head = blockIdx.y, b = blockIdx.z;
+  const int qi = qt * 256 + threadIdx.x;
+  const bool active = qi < P;
+  float qr[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) qr[d] = 0.f;
+  if (active) {
+#pragma unroll
+    for (int d = 0; d < D; d += 4) {
+      float4 t4 = ldg4(q + (size_t)(b * P + qi) * C + head * D + d);
+      qr[d] = t4.x; qr[d + 1] = t4.y; qr[d + 2] = t4.z; qr[d + 3] = t4.w;
+    }
+  }
+  float m = -INFINITY, l = 0.f, acc[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) acc[d] = 0.f;
+  const int k_begin = split * chunk, k_end = min(HW, k_begin + chunk);
+  for (int k0 = k_begin; k0 < k_end; k0 += TK) {
+    int nk = min(TK, k_end - k0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < TK * (D / 4); i += blockDim.x) {
+      int kk = i / (D / 4), d4 = i % (D / 4);
+      float4 kx = make_float4(0, 0, 0, 0), vx = kx;
+      if (kk < nk) {
+        const float* row = kv + (size_t)(b * HW + k0 + kk) * (2 * C) + head * D + d4 * 4;
+        kx = ldg4(row);
+        vx = ldg4(row + C);
+      }
+      *reinterpret_cast<float4*>(&ks[kk][d4 * 4]) = kx;
+      *reinterpret_cast<float4*>(&vs[kk][d4 * 4]) = vx;
+    }
+    __syncthreads();
+    if (active) {
+      for (int kk = 0; kk < nk; kk += 4) {   // 4 keys per rescale
+        float s[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float a = 0.f;
+#pragma unroll
+          for (int d = 0; d < D; d += 4) {
+            float4 t4 = *reinterpret_cast<const float4*>(&ks[kk + u][d]);
+            a += qr[d] * t4.x + qr[d + 1] * t4.y + qr[d + 2] * t4.z + qr[d + 3] * t4.w;
+          }
+          s[u] = (kk + u < nk) ? a : -INFINITY;
+        }
+        float mn = fmaxf(fmaxf(m, fmaxf(s[0], s[1])), fmaxf(s[2], s[3]));
+        float corr = expf(m - mn);
+        l *= corr;
+#pragma unroll
+        for (int d = 0; d < D; ++d) acc[d] *= corr;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float p = expf(s[u] - mn);
+          l += p;
+#pragma unroll
+          for (int d = 0; d < D; d += 4) {
+            float4 t4 = *reinterpret_cast<const float4*>(&vs[kk + u][d]);
+            acc[d] += p * t4.x; acc[d + 1] += p * t4.y; acc[d + 2] += p * t4.z; acc[d + 3] += p * t4.w;
+          }
+        }
+        m = mn;
+      }
+    }
+  }
+  if (active) {
+    float* o = part + ((((size_t)b * Hh + head) * P + qi) * nsplit + split) * (D + 2);
+    o[0] = m;
+    o[1] = l;
+#pragma unroll
+    for (int d = 0; d < D; ++d) o[2 + d] = acc[d];
+  }
+}
+
+template <int D>
+__global__ void cross_attn_combine_kernel(const float* __restrict__ part, float* __restrict__ out, int B, int P, int C,
+                                          int Hh, int nsplit) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;  // (b, head, q)
+  if (i >= B * Hh * P) return;
+  int qi = i % P, head = (i / P) % Hh, b = i / (P * Hh);
+  const float* pp = part + (size_t)i * nsplit * (D + 2);
+  float M = -INFINITY;
+  for (int s = 0; s < nsplit; ++s) M = fmaxf(M, pp[s * (D + 2)]);
+  float L = 0.f, acc[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) acc[d] = 0.f;
+  for (int s = 0; s < nsplit; ++s) {
+    float w = expf(pp[s * (D + 2)] - M);
+    L += w * pp[s * (D + 2) + 1];
+#pragma unroll
+    for (int d = 0; d < D; ++d) acc[d] += w * pp[s * (D + 2) + 2 + d];
+  }
+  float inv = 1.f / L;
+  float* o = out + (size_t)(b * P + qi) * C + head * D;
+#pragma unroll
+  for (int d = 0; d < D; ++d) o[d] = acc[d] * inv;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row-wise finish: x = sum_s part[s][m,:] + bias + res[m,:];  y = act(LayerNorm(x) * gamma + beta)
+// (no LayerNorm when gamma == nullptr); rows with zero_if_neg[m] < 0 are written as 0.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rows_finish_kernel(const float* __restrict__ part, int nsplit, size_t split_stride, int ldp,
+                   const float* __restrict__ bias, const float* __restrict__ res, int ldres,
+                   const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ out, int ldo,
+                   const int* __restrict__ zero_if_neg, int M, int C, int act, float eps) {
+  int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (m >= M) return;
+  constexpr int MAXV = 16;  // C <= 512
+  float x[MAXV];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int c = i * 32 + lane;
+    float a = 0.f;
+    if (c < C) {
+      for (int s = 0; s < nsplit; ++s) a += part[s * split_stride + (size_t)m * ldp + c];
+      if (bias) a += bias[c];
+      if (res) a += res[(size_t)m * ldres + c];
+      sum += a;
+    }
+    x[i] = a;
+  }
+  bool zero = zero_if_neg && zero_if_neg[m] < 0;
+  if (gamma) {
+    float mean = warp_sum(sum) / (float)C;
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      int c = i * 32 + lane;
+      if (c < C) {
+        float d = x[i] - mean;
+        var += d * d;
+      }
+    }
+    var = warp_sum(var) / (float)C;
+    float rstd = 1.f / sqrtf(var + eps);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      int c = i * 32 + lane;
+      if (c < C) x[i] = (x[i] - mean) * rstd * gamma[c] + beta[c];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int c = i * 32 + lane;
+    if (c < C) out[(size_t)m * ldo + c] = zero ? 0.f : di_act(x[i], act);
+  }
+}
+
+// pred [M, NP]: center(0,1) height(2) dim(3..5) rot(6,7) vel(8,9) heatmap(10..).  center += query_pos;
+// rows whose query fell on no image (win < 0) take the first layer's prediction (decoder.py:290-295).
+__global__ void pred_finish_kernel(float* __restrict__ pred, float* __restrict__ qpos, const float* __restrict__ first,
+                                   const int* __restrict__ win, int M, int NP) {
+  int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  float* p = pred + (size_t)m * NP;
+  p[0] += qpos[m * 2];
+  p[1] += qpos[m * 2 + 1];
+  if (win && first && win[m] < 0)
+    for (int c = 0; c < NP; ++c) p[c] = first[(size_t)m * NP + c];
+  qpos[m * 2] = p[0];
+  qpos[m * 2 + 1] = p[1];
+}
+
+// ------------------------------------------------------------------------------------------------
+// RoI generation.  mode 0 (image, decoder_utils.py:660-741): box centre + 8 corners -> every view,
+// on-image test on the centre, views with <= 1 query skipped, later views win.
+// mode 1 (BEV, :788-819): footprint of the box with doubled dims in BEV cells.
+// ------------------------------------------------------------------------------------------------
+struct RoiParams {
+  float sx, sy, ox, oy;        // bbox_coder: out_size_factor*voxel_size[0|1], pc_range[0|1]
+  float csx, cox;              // test_cfg: out_size_factor*voxel_size[0], pc_range[0] (centre path uses index 0 twice)
+  float h_pad, w_pad;          // input_shape
+  float bev_scale, bev_off;    // bbox_coder.voxel_size[0]*out_size_factor, bbox_coder.pc_range[0]
+};
+
+__device__ __forceinline__ void box_corners_xy(float cx, float cy, float dx, float dy, float yaw, float* xs, float* ys) {
+  // mmdet3d 0.17.1 LiDARInstance3DBoxes.corners: (dims * ({0,1}^3 - (.5,.5,0))) @ [[c,-s],[s,c]] + centre
+  float c = cosf(yaw), s = sinf(yaw);
+  int n = 0;
+  for (int ix = 0; ix < 2; ++ix)
+    for (int iy = 0; iy < 2; ++iy) {
+      float lx = dx * ((float)ix - 0.5f), ly = dy * ((float)iy - 0.5f);
+      xs[n] = lx * c + ly * s + cx;
+      ys[n] = -lx * s + ly * c + cy;
+      ++n;
+    }
+}
+
+constexpr int MAXV = 8;
+
+__global__ void __launch_bounds__(1024)
+rcnn_rois_kernel(const float* __restrict__ pred, int NP, const float* __restrict__ proj, const float* __restrict__ aux,
+                 float* __restrict__ rois, int* __restrict__ win, int* __restrict__ onbits, int P, int V, int mode,
+                 RoiParams rp) {
+  __shared__ int cnt[MAXV];
+  const int b = blockIdx.x, qi = threadIdx.x;
+  if (qi < MAXV) cnt[qi] = 0;
+  __syncthreads();
+  const bool act = qi < P;
+  const int bq = b * P + qi;
+  float rect[MAXV][4];
+  int bits = 0;
+  float cxr = 0, cyr = 0, dx = 0, dy = 0, dz = 0, yaw = 0, zc = 0, zb = 0;
+  if (act) {
+    const float* p = pred + (size_t)bq * NP;
+    cxr = p[0] * rp.sx + rp.ox;
+    cyr = p[1] * rp.sy + rp.oy;
+    dx = expf(p[3]); dy = expf(p[4]); dz = expf(p[5]);
+    zc = p[2];
+    zb = zc - dz * 0.5f;
+    yaw = atan2f(p[6], p[7]);
+  }
+  if (mode == 1) {
+    if (act) {
+      float xs[4], ys[4];
+      box_corners_xy(cxr, cyr, dx * 2.f, dy * 2.f, yaw, xs, ys);
+      float x0 = INFINITY, y0 = INFINITY, x1 = -INFINITY, y1 = -INFINITY;
+      for (int i = 0; i < 4; ++i) {
+        float u = (xs[i] - rp.bev_off) / rp.bev_scale, v = (ys[i] - rp.bev_off) / rp.bev_scale;
+        x0 = fminf(x0, u); x1 = fmaxf(x1, u); y0 = fminf(y0, v); y1 = fmaxf(y1, v);
+      }
+      float* r = rois + (size_t)bq * 5;
+      r[0] = (float)b; r[1] = x0; r[2] = y0; r[3] = x1; r[4] = y1;
+      win[bq] = 0;
+      onbits[bq] = 1;
+    }
+    return;
+  }
+  if (act) {
+    // centre used for the on-image test: (centre_real via test_cfg, raw height)
+    float ccx = pred[(size_t)bq * NP] * rp.csx + rp.cox, ccy = pred[(size_t)bq * NP + 1] * rp.csx + rp.cox;
+    float xs[4], ys[4];
+    box_corners_xy(cxr, cyr, dx, dy, yaw, xs, ys);
+    const float* ax = aux + b * 4;  // crop_x, crop_y, flip (0/1), orig_w
+    for (int v = 0; v < V; ++v) {
+      const float* M = proj + ((size_t)b * V + v) * 12;
+      auto prj = [&](float X, float Y, float Z, float& u, float& w) {
+        float a = M[0] * X + M[1] * Y + M[2] * Z + M[3];
+        float bb = M[4] * X + M[5] * Y + M[6] * Z + M[7];
+        float c = fmaxf(M[8] * X + M[9] * Y + M[10] * Z + M[11], 1e-5f);
+        u = a / c - ax[0];
+        w = bb / c - ax[1];
+        if (ax[2] != 0.f) u = ax[3] - u;
+      };
+      float u, w;
+      prj(ccx, ccy, zc, u, w);
+      bool on = (u > 0.f) && (u < rp.w_pad) && (w > 0.f) && (w < rp.h_pad);
+      float x0 = INFINITY, y0 = INFINITY, x1 = -INFINITY, y1 = -INFINITY;
+      for (int i = 0; i < 4; ++i)
+        for (int iz = 0; iz < 2; ++iz) {
+          prj(xs[i], ys[i], zb + (iz ? dz : 0.f), u, w);
+          x0 = fminf(x0, u); x1 = fmaxf(x1, u); y0 = fminf(y0, w); y1 = fmaxf(y1, w);
+        }
+      rect[v][0] = x0; rect[v][1] = y0; rect[v][2] = x1; rect[v][3] = y1;
+      if (on) {
+        bits |= 1 << v;
+        atomicAdd(&cnt[v], 1);
+      }
+    }
+  }
+  __syncthreads();
+  if (act) {
+    int w = -1;
+    for (int v = 0; v < V; ++v)
+      if (((bits >> v) & 1) && cnt[v] > 1) w = v;
+    int live = 0;  // views that were actually processed (count > 1)
+    for (int v = 0; v < V; ++v)
+      if (cnt[v] > 1) live |= 1 << v;
+    float* r = rois + (size_t)bq * 5;
+    r[0] = w >= 0 ? (float)(b * V + w) : -1.f;
+    for (int i = 0; i < 4; ++i) r[1 + i] = w >= 0 ? rect[w][i] : 0.f;
+    win[bq] = w;
+    onbits[bq] = bits & live;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// RoIAlign (detectron2 ROIAlignV2 == aligned=True), 7x7 bins, 2x2 samples per bin, pixel-major map.
+// One warp per (roi, bin).  out [n, 49, C].
+// ------------------------------------------------------------------------------------------------
+template <int NJ>
+__global__ void __launch_bounds__(256)
+roi_align_kernel(const float* __restrict__ maps, const float* __restrict__ rois, float* __restrict__ out, int n, int H,
+                 int W, int C, float scale) {
+  constexpr int R = 7, G = 2;
+  int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (wid >= n * R * R) return;
+  int bin = wid % (R * R), ri = wid / (R * R);
+  int ph = bin / R, pw = bin % R;
+  const float* r = rois + (size_t)ri * 5;
+  int mi = (int)r[0];
+  float4 acc[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) acc[j] = make_float4(0, 0, 0, 0);
+  if (mi >= 0) {
+    const float* map = maps + (size_t)mi * H * W * C;
+    float x0 = r[1] * scale - 0.5f, y0 = r[2] * scale - 0.5f;
+    float x1 = r[3] * scale - 0.5f, y1 = r[4] * scale - 0.5f;
+    float bw = (x1 - x0) / (float)R, bh = (y1 - y0) / (float)R;
+    for (int iy = 0; iy < G; ++iy)
+      for (int ix = 0; ix < G; ++ix) {
+        float y = y0 + (float)ph * bh + ((float)iy + 0.5f) * bh / (float)G;
+        float x = x0 + (float)pw * bw + ((float)ix + 0.5f) * bw / (float)G;
+        if (y < -1.f || y > (float)H || x < -1.f || x > (float)W) continue;
+        if (!(y == y) || !(x == x)) continue;
+        y = fmaxf(y, 0.f);
+        x = fmaxf(x, 0.f);
+        int yl = (int)y, xl = (int)x, yh, xh;
+        if (yl >= H - 1) { yh = yl = H - 1; y = (float)yl; } else yh = yl + 1;
+        if (xl >= W - 1) { xh = xl = W - 1; x = (float)xl; } else xh = xl + 1;
+        float ly = y - (float)yl, lx = x - (float)xl, hy = 1.f - ly, hx = 1.f - lx;
+        float wg[4] = {hy * hx, hy * lx, ly * hx, ly * lx};
+        const float* rows[4] = {map + ((size_t)yl * W + xl) * C, map + ((size_t)yl * W + xh) * C,
+                                map + ((size_t)yh * W + xl) * C, map + ((size_t)yh * W + xh) * C};
+#pragma unroll
+        for (int cnr = 0; cnr < 4; ++cnr)
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) {
+            int c = 4 * lane + 128 * j;
+            if (c < C) {
+              float4 t4 = ldg4(rows[cnr] + c);
+              acc[j].x += wg[cnr] * t4.x; acc[j].y += wg[cnr] * t4.y;
+              acc[j].z += wg[cnr] * t4.z; acc[j].w += wg[cnr] * t4.w;
+            }
+          }
+      }
+  }
+  const float inv = 1.f / (float)(G * G);
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    int c = 4 * lane + 128 * j;
+    if (c < C)
+      *reinterpret_cast<float4*>(out + ((size_t)ri * R * R + bin) * C + c) =
+          make_float4(acc[j].x * inv, acc[j].y * inv, acc[j].z * inv, acc[j].w * inv);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// DynamicConv core (decoder_utils.py:610-624), hidden = dim_dynamic = 128, 49 RoI bins:
+//   f1 = relu(LN1(F @ P1)); f2 = relu(LN2(f1 @ P2)); out = f2 flattened [49*128].  One CTA per query.
+// ------------------------------------------------------------------------------------------------
+constexpr int DC = 128, DR = 49;
+
+__global__ void __launch_bounds__(256)
+dynconv_kernel(const float* __restrict__ roi, const float* __restrict__ params, const float* __restrict__ g1,
+               const float* __restrict__ b1, const float* __restrict__ g2, const float* __restrict__ b2,
+               float* __restrict__ out, float eps) {
+  extern __shared__ __align__(16) float dyn_smem[];
+  float(*F)[DC] = reinterpret_cast<float(*)[DC]>(dyn_smem);
+  float(*T)[DC] = reinterpret_cast<float(*)[DC]>(dyn_smem + DR * DC);
+  const int qn = blockIdx.x, t = threadIdx.x;
+  const float* src = roi + (size_t)qn * DR * DC;
+  for (int i = t; i < DR * DC / 4; i += blockDim.x)
+    reinterpret_cast<float4*>(&F[0][0])[i] = ldg4(src + i * 4);
+  __syncthreads();
+  const int d = t & (DC - 1), half = t >> 7;  // rows half, half+2, ...
+  constexpr int NR = (DR + 1) / 2;            // 25
+  for (int layer = 0; layer < 2; ++layer) {
+    const float* Pm = params + (size_t)qn * 2 * DC * DC + (size_t)layer * DC * DC;  // [c][d]
+    float(*X)[DC] = layer == 0 ? F : T;
+    float acc[NR];
+#pragma unroll
+    for (int i = 0; i < NR; ++i) acc[i] = 0.f;
+    for (int c = 0; c < DC; c += 4) {
+      float p0 = __ldg(Pm + (size_t)(c + 0) * DC + d), p1 = __ldg(Pm + (size_t)(c + 1) * DC + d);
+      float p2 = __ldg(Pm + (size_t)(c + 2) * DC + d), p3 = __ldg(Pm + (size_t)(c + 3) * DC + d);
+#pragma unroll
+      for (int i = 0; i < NR; ++i) {
+        int r = half + 2 * i;
+        if (r < DR) {
+          float4 x = *reinterpret_cast<const float4*>(&X[r][c]);
+          acc[i] = fmaf(x.x, p0, acc[i]);
+          acc[i] = fmaf(x.y, p1, acc[i]);
+          acc[i] = fmaf(x.z, p2, acc[i]);
+          acc[i] = fmaf(x.w, p3, acc[i]);
+        }
+      }
+    }
+    __syncthreads();  // everyone finished reading X before it may be overwritten
+    float(*Y)[DC] = layer == 0 ? T : F;
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+      int r = half + 2 * i;
+      if (r < DR) Y[r][d] = acc[i];
+    }
+    __syncthreads();
+    // LayerNorm over d + ReLU, one warp per row
+    const float* g = layer == 0 ? g1 : g2;
+    const float* bb = layer == 0 ? b1 : b2;
+    for (int r = t >> 5; r < DR; r += (blockDim.x >> 5)) {
+      int lane = t & 31;
+      float4 x = *reinterpret_cast<const float4*>(&Y[r][lane * 4]);
+      float mean = warp_sum(x.x + x.y + x.z + x.w) / (float)DC;
+      float dx0 = x.x - mean, dx1 = x.y - mean, dx2 = x.z - mean, dx3 = x.w - mean;
+      float var = warp_sum(dx0 * dx0 + dx1 * dx1 + dx2 * dx2 + dx3 * dx3) / (float)DC;
+      float rstd = 1.f / sqrtf(var + eps);
+      float4 gg = ldg4(g + lane * 4), be = ldg4(bb + lane * 4);
+      float4 y;
+      y.x = fmaxf(dx0 * rstd * gg.x + be.x, 0.f);
+      y.y = fmaxf(dx1 * rstd * gg.y + be.y, 0.f);
+      y.z = fmaxf(dx2 * rstd * gg.z + be.z, 0.f);
+      y.w = fmaxf(dx3 * rstd * gg.w + be.w, 0.f);
+      *reinterpret_cast<float4*>(&Y[r][lane * 4]) = y;
+    }
+    __syncthreads();
+  }
+  // after layer 1 the result is in F
+  float* dst = out + (size_t)qn * DR * DC;
+  for (int i = t; i < DR * DC / 4; i += blockDim.x)
+    *reinterpret_cast<float4*>(dst + i * 4) = reinterpret_cast<const float4*>(&F[0][0])[i];
+}
+
+// layout converters (drop-in boundary: the reference hands NCHW tensors around)
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int HW) {
+  __shared__ float tile[32][33];
+  int n = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  int tx = threadIdx.x, ty = threadIdx.y;
+  for (int i = ty; i < 32; i += blockDim.y) {
+    int c = c0 + i, p = p0 + tx;
+    tile[i][tx] = (c < C && p < HW) ? in[((size_t)n * C + c) * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += blockDim.y) {
+    int p = p0 + i, c = c0 + tx;
+    if (p < HW && c < C) out[((size_t)n * HW + p) * C + c] = tile[tx][i];
+  }
+}
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int HW) {
+  __shared__ float tile[32][33];
+  int n = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  int tx = threadIdx.x, ty = threadIdx.y;
+  for (int i = ty; i < 32; i += blockDim.y) {
+    int p = p0 + i, c = c0 + tx;
+    tile[i][tx] = (c < C && p < HW) ? in[((size_t)n * HW + p) * C + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += blockDim.y) {
+    int c = c0 + i, p = p0 + tx;
+    if (p < HW && c < C) out[((size_t)n * C + c) * HW + p] = tile[tx][i];
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+// a, b: raw heatmap logits NCHW [B,K,H,W]; out [B,K,H*W] = nms-masked mean of sigmoids.
+int di_heatmap_nms_f32(const float* a, const float* b, float* out, int B, int K, int H, int W, int ks,
+                       int no_nms_class_mask, cudaStream_t stream) {
+  DI_CHECK_ARG(a && b && out && B > 0 && K > 0 && K <= 32 && ks % 2 == 1, "di_heatmap_nms_f32: bad argument");
+  int total = B * K * H * W;
+  heatmap_nms_kernel<<<di_cdiv(total, 256), 256, 0, stream>>>(a, b, out, K, H, W, ks, (unsigned)no_nms_class_mask, total);
+  DI_CHECK_LAUNCH("di_heatmap_nms_f32");
+  return DI_OK;
+}
+
+// scores [B,n] >= 0 -> idx [B,k] (descending score, ties by ascending index); k <= 1024
+int di_topk_f32(const float* scores, int* idx, int B, int n, int k, cudaStream_t stream) {
+  DI_CHECK_ARG(scores && idx && B > 0 && n >= k && k > 0 && k <= TOPK_MAX, "di_topk_f32: bad argument (k=%d n=%d)", k, n);
+  topk_kernel<<<B, 1024, 0, stream>>>(scores, idx, n, k);
+  DI_CHECK_LAUNCH("di_topk_f32");
+  return DI_OK;
+}
+
+int di_query_init_f32(const float* feat, const int* top, const float* heat, const float* wce_t, const float* bce,
+                      float* qfeat, float* qpos, int* labels, float* qscore, int B, int HW, int W, int C, int K, int P,
+                      cudaStream_t stream) {
+  DI_CHECK_ARG(feat && top && heat && wce_t && bce && qfeat && qpos && labels && qscore, "di_query_init_f32: null pointer");
+  query_init_kernel<<<B * P, 128, 0, stream>>>(feat, top, heat, wce_t, bce, qfeat, qpos, labels, qscore, HW, W, C, K, P);
+  DI_CHECK_LAUNCH("di_query_init_f32");
+  return DI_OK;
+}
+
+// q/k/v/out: [B*P, ld*] rows, heads of 16 channels; onbits/win optional (see kernel comment)
+int di_mha_small_f32(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* out, int ldo,
+                     const int* onbits, const int* win, int B, int P, int heads, int head_dim, cudaStream_t stream) {
+  DI_CHECK_ARG(q && k && v && out && head_dim == 16 && P <= 512, "di_mha_small_f32: unsupported shape (head_dim=%d P=%d)", head_dim, P);
+  DI_CHECK_ARG(ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0, "di_mha_small_f32: strides must be multiples of 4");
+  DI_CHECK_ARG((onbits == nullptr) == (win == nullptr), "di_mha_small_f32: onbits and win go together");
+  int warps = B * P * heads;
+  mha_small_kernel<16><<<di_cdiv(warps, 8), 256, 0, stream>>>(q, ldq, k, ldk, v, ldv, out, ldo, onbits, win, B, P, heads);
+  DI_CHECK_LAUNCH("di_mha_small_f32");
+  return DI_OK;
+}
+
+// part: workspace [B, heads, P, nsplit, 18]; out [B*P, C]
+int di_cross_attn_f32(const float* q, const float* kv, float* part, float* out, int B, int P, int HW, int C, int heads,
+                      int nsplit, cudaStream_t stream) {
+  DI_CHECK_ARG(q && kv && part && out && C == heads * 16 && nsplit > 0, "di_cross_attn_f32: bad argument");
+  int chunk = di_cdiv(HW, nsplit);
+  chunk = (chunk + 3) / 4 * 4;
+  int qtiles = di_cdiv(P, 256);
+  dim3 grid(nsplit * qtiles, heads, B);
+  cross_attn_kernel<16><<<grid, 256, 0, stream>>>(q, kv, part, P, HW, C, heads, chunk, nsplit);
+  DI_CHECK_LAUNCH("di_cross_attn_f32");
+  cross_attn_combine_kernel<16><<<di_cdiv(B * heads * P, 128), 128, 0, stream>>>(part, out, B, P, C, heads, nsplit);
+  DI_CHECK_LAUNCH("di_cross_attn_combine");
+  return DI_OK;
+}
+
+int di_rows_finish_f32(const float* part, int nsplit, long long split_stride, int ldp, const float* bias,
+                       const float* res, int ldres, const float* gamma, const float* beta, float* out, int ldo,
+                       const int* zero_if_neg, int M, int C, int act, float eps, cudaStream_t stream) {
+  DI_CHECK_ARG(part && out && M > 0 && C > 0 && C <= 512 && nsplit >= 1, "di_rows_finish_f32: bad argument");
+  DI_CHECK_ARG((gamma == nullptr) == (beta == nullptr), "di_rows_finish_f32: gamma and beta go together");
+  rows_finish_kernel<<<di_cdiv(M, 8), 256, 0, stream>>>(part, nsplit, (size_t)split_stride, ldp, bias, res, ldres, gamma,
+                                                       beta, out, ldo, zero_if_neg, M, C, act, eps);
+  DI_CHECK_LAUNCH("di_rows_finish_f32");
+  return DI_OK;
+}
+
+int di_pred_finish_f32(float* pred, float* qpos, const float* first, const int* win, int M, int NP, cudaStream_t stream) {
+  DI_CHECK_ARG(pred && qpos && M > 0 && NP >= 2, "di_pred_finish_f32: bad argument");
+  pred_finish_kernel<<<di_cdiv(M, 128), 128, 0, stream>>>(pred, qpos, first, win, M, NP);
+  DI_CHECK_LAUNCH("di_pred_finish_f32");
+  return DI_OK;
+}
+
+// params10 (host): sx, sy, ox, oy, csx, cox, h_pad, w_pad, bev_scale, bev_off.  proj [B,V,12] and aux [B,4]
+// (crop_x, crop_y, flip, orig_w) are device pointers used by mode 0 only.
+int di_rcnn_rois_f32(const float* pred, int NP, const float* proj, const float* aux, float* rois, int* win, int* onbits,
+                     int B, int P, int V, int mode, const float* params10, cudaStream_t stream) {
+  DI_CHECK_ARG(pred && rois && win && onbits && params10 && P <= 1024 && V <= MAXV && NP >= 8, "di_rcnn_rois_f32: bad argument");
+  DI_CHECK_ARG(mode == 1 || (proj && aux), "di_rcnn_rois_f32: image mode needs proj and aux");
+  RoiParams rp;
+  rp.sx = params10[0]; rp.sy = params10[1]; rp.ox = params10[2]; rp.oy = params10[3];
+  rp.csx = params10[4]; rp.cox = params10[5]; rp.h_pad = params10[6]; rp.w_pad = params10[7];
+  rp.bev_scale = params10[8]; rp.bev_off = params10[9];
+  int threads = ((P + 31) / 32) * 32;
+  if (threads < 32) threads = 32;
+  rcnn_rois_kernel<<<B, threads, 0, stream>>>(pred, NP, proj, aux, rois, win, onbits, P, V, mode, rp);
+  DI_CHECK_LAUNCH("di_rcnn_rois_f32");
+  return DI_OK;
+}
+
+// maps [n_maps,H,W,C] pixel-major; rois [n,5] = (map index or -1, x0,y0,x1,y1); out [n,49,C]
+int di_roi_align_f32(const float* maps, const float* rois, float* out, int n, int H, int W, int C, float scale,
+                     cudaStream_t stream) {
+  DI_CHECK_ARG(maps && rois && out && n > 0 && C % 4 == 0 && C <= 512, "di_roi_align_f32: bad argument");
+  dim3 grid(di_cdiv(n * 49, 8));
+  if (C <= 128) roi_align_kernel<1><<<grid, 256, 0, stream>>>(maps, rois, out, n, H, W, C, scale);
+  else if (C <= 256) roi_align_kernel<2><<<grid, 256, 0, stream>>>(maps, rois, out, n, H, W, C, scale);
+  else roi_align_kernel<4><<<grid, 256, 0, stream>>>(maps, rois, out, n, H, W, C, scale);
+  DI_CHECK_LAUNCH("di_roi_align_f32");
+  return DI_OK;
+}
+
+// roi [n,49,128]; params [n, 2*128*128]; out [n, 49*128]
+int di_dynconv_f32(const float* roi, const float* params, const float* g1, const float* b1, const float* g2,
+                   const float* b2, float* out, int n, float eps, cudaStream_t stream) {
+  DI_CHECK_ARG(roi && params && g1 && b1 && g2 && b2 && out && n > 0, "di_dynconv_f32: bad argument");
+  const int smem = 2 * DR * DC * (int)sizeof(float);
+  cudaFuncSetAttribute(dynconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  dynconv_kernel<<<n, 256, smem, stream>>>(roi, params, g1, b1, g2, b2, out, eps);
+  DI_CHECK_LAUNCH("di_dynconv_f32");
+  return DI_OK;
+}
+
+int di_nchw_to_nhwc_f32(const float* in, float* out, int N, int C, int HW, cudaStream_t stream) {
+  DI_CHECK_ARG(in && out && N > 0 && C > 0 && HW > 0, "di_nchw_to_nhwc_f32: bad argument");
+  dim3 grid(di_cdiv(HW, 32), di_cdiv(C, 32), N), block(32, 8);
+  nchw_to_nhwc_kernel<<<grid, block, 0, stream>>>(in, out, C, HW);
+  DI_CHECK_LAUNCH("di_nchw_to_nhwc_f32");
+  return DI_OK;
+}
+
+int di_nhwc_to_nchw_f32(const float* in, float* out, int N, int C, int HW, cudaStream_t stream) {
+  DI_CHECK_ARG(in && out && N > 0 && C > 0 && HW > 0, "di_nhwc_to_nchw_f32: bad argument");
+  dim3 grid(di_cdiv(HW, 32), di_cdiv(C, 32), N), block(32, 8);
+  nhwc_to_nchw_kernel<<<grid, block, 0, stream>>>(in, out, C, HW);
+  DI_CHECK_LAUNCH("di_nhwc_to_nchw_f32");
+  return DI_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,137 @@
+/* libdi_b200 -- C ABI of the B200-native (sm_100a) kernels for DeepInteraction's MMRI encoder +
+ * MMPI decoder forward path.
+ *
+ * Conventions (every entry point):
+ *   - plain C types only: device pointers, sizes, a cudaStream_t; no torch / C++ types;
+ *   - returns int: 0 (or a non-negative count where stated) on success, < 0 on error
+ *     (-1 bad argument, -2 launch failure, -3 unsupported configuration); the message is in
+ *     di_last_error() (thread-local);
+ *   - never allocates, never synchronises, never throws: launches on `stream` and returns;
+ *     the caller owns all buffers (inputs are borrowed, outputs/workspaces are caller-provided);
+ *   - stateless and re-entrant; distinct streams may be driven from distinct host threads.
+ *   - fp32 in / fp32 out / fp32 accumulate.  Feature maps are "pixel-major" (NHWC): the C channels
+ *     of one pixel are contiguous; query tensors are row-major [B*P, C].
+ *
+ * The reference has exactly one native boundary on this path, the pybind module `localattention`
+ * (projects/mmdet3d_plugin/models/utils/ops/locatt_ops/localAttention.cpp:61-73; callers
+ * models/utils/encoder_utils.py:43,67).  di_lcab_window_f32 replaces its similar_forward +
+ * softmax + weighting_forward sequence; the other entry points replace the torch / detectron2 / OpenCV
+ * calls of the surrounding Python (cited per function, paths relative to
+ * projects/mmdet3d_plugin/).  INTEGRATION.md shows the reference-side binding.
+ */
+#ifndef DI_B200_H_
+#define DI_B200_H_
+
+#include <cuda_runtime_api.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* di_last_error(void);
+int di_version(void);
+int di_built_arch(void); /* 100 == sm_100a */
+
+/* Activation codes */
+#define DI_ACT_NONE 0
+#define DI_ACT_RELU 1
+#define DI_ACT_GELU 2
+
+/* ---- dense layers (gemm.cu) ------------------------------------------------------------------ */
+
+/* C[M,N] = act([A0|A1|A2][M,K0+K1+K2] * W[N,K0+K1+K2]^T + bias[N] + res[m % res_mod, N]).
+ * Replaces every 1x1 Conv(+folded BN)(+ReLU) of the encoder (models/utils/encoder_utils.py:11-34,92-117),
+ * the cat + 1x1 Conv+BN pairs (models/necks/deepinteraction_encoder.py:26-27,31-32; the K-concatenated
+ * sources make the torch.cat implicit) and every nn.Linear / Conv1d(k=1) of the decoder
+ * (models/utils/decoder_utils.py).  splits > 1 = deterministic split-K: partial s goes to
+ * C + s*split_stride without bias/act; returns the number of partials written (reduce them with
+ * di_rows_finish_f32). */
+int di_linear_f32(const float* A0, int lda0, int K0, const float* A1, int lda1, int K1, const float* A2, int lda2,
+                  int K2, const float* W, const float* bias, const float* res, int ldres, int res_mod, float* C,
+                  int ldc, int M, int N, int act, int splits, long long split_stride, cudaStream_t stream);
+
+/* 3x3 conv, stride 1, pad 1 (models/necks/deepinteraction_encoder.py:47-62,80-81 shared convs;
+ * models/dense_heads/deepinteraction_decoder.py:83-101,223-224 heatmap heads).
+ * x: NCHW (x_nhwc=0) or NHWC (1); w: [Cout][(ky*3+kx)*Cin + ci]; y: NHWC (y_nchw=0) or NCHW (1). */
+int di_conv3x3_f32(const float* x, int x_nhwc, const float* w, const float* bias, float* y, int y_nchw, int N,
+                   int Cin, int H, int W, int Cout, int act, cudaStream_t stream);
+
+/* ---- local-window attention (lcab.cu) ---------------------------------------------------------- */
+
+/* out = weighting(v, softmax(similar(q, k) / sqrt(C))) over a ksize x ksize window, fused
+ * (models/utils/encoder_utils.py:132-134; locatt_ops/kernels.cuh:4-80).  Out-of-image taps: logit 0
+ * (kept in the softmax), value skipped.  q,k,v,out [N,H,W,*] with per-pixel strides ld*. */
+int di_lcab_window_f32(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* out, int ldo,
+                       int N, int H, int W, int C, int ksize, cudaStream_t stream);
+
+/* ---- geometry-driven gathers (geometry.cu) ------------------------------------------------------ */
+
+/* rows[p,:] = map[coors[p] = (b,z,y,x)]  (models/utils/encoder_utils.py:313) */
+int di_gather_rows_f32(const float* map, const int* coors, float* rows, int P, int Y, int X, int C,
+                       cudaStream_t stream);
+/* map[coors[p]] = cnt[p] > 0 ? rows[p,:] : 0  (models/utils/encoder_utils.py:314-318) */
+int di_scatter_rows_f32(const float* rows, const int* cnt, const int* coors, float* map, int P, int Y, int X, int C,
+                        cudaStream_t stream);
+/* Per pillar: project its <=T points to V cameras, strict in-image / z>1e-5 / point<num_points mask,
+ * bilinear gather of the image feature, single-head softmax attention with the folded query qk
+ * (models/utils/encoder_utils.py:270-316; fold: SURVEY.md section 0).  s_out = sum_j a_j k_j, cnt = #valid keys. */
+int di_i2p_attend_f32(const float* qk, const float* pillars, const int* npts, const int* coors, const float* proj,
+                      const float* img, float* s_out, int* cnt_out, int P, int T, int pdim, int V, int h, int w, int C,
+                      int H_in, int W_in, cudaStream_t stream);
+/* Sparse depth maps: keys[v,r,c] = max((point index+1)<<32 | depth bits)  (models/utils/encoder_utils.py:155-174) */
+int di_depth_scatter(const float* pts, int stride, int n, const float* proj, unsigned long long* keys, int V, int h,
+                     int w, int H_in, int W_in, cudaStream_t stream);
+/* ip_basic fill_in_multiscale(extrapolate=False, blur_type='bilateral') on the GPU
+ * (models/utils/ip_basic/depth_map_utils.py:134-287; called at models/utils/encoder_utils.py:175-182).
+ * scratch: 3*n_img*h*w floats. */
+int di_depth_complete(const unsigned long long* keys, float* scratch, float* dense, float* sparse_out, int n_img, int h,
+                      int w, cudaStream_t stream);
+/* Lift feature pixels to LiDAR space and record BEV sampling coordinates (models/utils/encoder_utils.py:183-194). */
+int di_lift_grid(const float* depth, const float* i2l, float* grid_xy, int n_img, int h, int w, int H_in, int W_in,
+                 int Yb, int Xb, const float* pc_range6_host, cudaStream_t stream);
+/* warped = grid_sample(bev, grid) with the lift mask folded into the grid (models/utils/encoder_utils.py:195-196). */
+int di_bev_sample_f32(const float* bev, const float* grid_xy, float* out, int B, int V, int hw, int Yb, int Xb, int C,
+                      cudaStream_t stream);
+
+/* ---- decoder (decoder.cu) ------------------------------------------------------------------------ */
+
+/* models/dense_heads/deepinteraction_decoder.py:225-239 */
+int di_heatmap_nms_f32(const float* a, const float* b, float* out, int B, int K, int H, int W, int ks,
+                       int no_nms_class_mask, cudaStream_t stream);
+/* :242 (argsort descending, first k) */
+int di_topk_f32(const float* scores, int* idx, int B, int n, int k, cudaStream_t stream);
+/* :243-253, :299 */
+int di_query_init_f32(const float* feat, const int* top, const float* heat, const float* wce_t, const float* bce,
+                      float* qfeat, float* qpos, int* labels, float* qscore, int B, int HW, int W, int C, int K, int P,
+                      cudaStream_t stream);
+/* self-attention among the queries of a sample (models/utils/decoder_utils.py:95-99, :745, :826) */
+int di_mha_small_f32(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* out, int ldo,
+                     const int* onbits, const int* win, int B, int P, int heads, int head_dim, cudaStream_t stream);
+/* query x BEV cross attention (models/utils/decoder_utils.py:101-103, 466-488) */
+int di_cross_attn_f32(const float* q, const float* kv, float* part, float* out, int B, int P, int HW, int C, int heads,
+                      int nsplit, cudaStream_t stream);
+/* x = sum_s part[s] + bias + res; y = act(LayerNorm(x)); residual + LayerNorm steps of decoder_utils.py */
+int di_rows_finish_f32(const float* part, int nsplit, long long split_stride, int ldp, const float* bias,
+                       const float* res, int ldres, const float* gamma, const float* beta, float* out, int ldo,
+                       const int* zero_if_neg, int M, int C, int act, float eps, cudaStream_t stream);
+/* models/dense_heads/deepinteraction_decoder.py:265, :290-295 */
+int di_pred_finish_f32(float* pred, float* qpos, const float* first, const int* win, int M, int NP,
+                       cudaStream_t stream);
+/* box decode + RoI rectangles: image mode 0 (models/utils/decoder_utils.py:660-741), BEV mode 1 (:788-819);
+ * core/bbox/coders/transfusion_bbox_coder.py:59-76 */
+int di_rcnn_rois_f32(const float* pred, int NP, const float* proj, const float* aux, float* rois, int* win, int* onbits,
+                     int B, int P, int V, int mode, const float* params10, cudaStream_t stream);
+/* detectron2 ROIAlignV2 7x7, sampling_ratio 2 (models/utils/decoder_utils.py:641-646, 739-741, 769-774, 822-823) */
+int di_roi_align_f32(const float* maps, const float* rois, float* out, int n, int H, int W, int C, float scale,
+                     cudaStream_t stream);
+/* DynamicConv bmm + LayerNorm + ReLU x2 (models/utils/decoder_utils.py:610-624) */
+int di_dynconv_f32(const float* roi, const float* params, const float* g1, const float* b1, const float* g2,
+                   const float* b2, float* out, int n, float eps, cudaStream_t stream);
+/* layout converters for the NCHW drop-in boundary */
+int di_nchw_to_nhwc_f32(const float* in, float* out, int N, int C, int HW, cudaStream_t stream);
+int di_nhwc_to_nchw_f32(const float* in, float* out, int N, int C, int HW, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DI_B200_H_ */
