@@ -148,6 +148,71 @@ lcab_window_kernel(const float* __restrict__ q, int ldq, const float* __restrict
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Unfused NCHW window ops with the exact contract of the reference extension `localattention`
+// (locatt_ops/kernels.cuh: cc2k :4-42, ck2c_ori :44-80, ck2c_loc :82-119; fp32 data, fp64 accumulate
+// as in f_cc2k<float,double>).  They exist for drop-in compatibility (autograd of the unfused path);
+// the product forward uses lcab_window_kernel above.
+// ------------------------------------------------------------------------------------------------
+__global__ void locatt_cc2k_kernel(const float* __restrict__ x_ori, const float* __restrict__ x_loc,
+                                   float* __restrict__ y, int C, int H, int W, int kH, int kW, long long total) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // over N*H*W*patch, w fastest then tap
+  if (i >= total) return;
+  const int patch = kH * kW, hw = H * W;
+  int w = (int)(i % W);
+  int t = (int)((i / W) % patch);
+  int h = (int)((i / ((long long)W * patch)) % H);
+  int n = (int)(i / ((long long)W * patch * H));
+  int hh = h - kH / 2 + t / kW, ww = w - kW / 2 + t % kW;
+  double acc = 0.0;
+  if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
+    const float* a = x_ori + (size_t)n * C * hw + h * W + w;
+    const float* b = x_loc + (size_t)n * C * hw + hh * W + ww;
+    for (int c = 0; c < C; ++c) acc += (double)(__ldg(a + (size_t)c * hw) * __ldg(b + (size_t)c * hw));
+  }
+  y[((size_t)n * hw + h * W + w) * patch + t] = (float)acc;
+}
+
+// y[n,c,h,w] = sum_t x_loc[n,c,h+dy,w+dx] * wgt[n,h,w,t]
+__global__ void locatt_ck2c_ori_kernel(const float* __restrict__ x_loc, const float* __restrict__ wgt,
+                                       float* __restrict__ y, int C, int H, int W, int kH, int kW, long long total) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // over N*C*H*W
+  if (i >= total) return;
+  const int patch = kH * kW, hw = H * W;
+  int w = (int)(i % W), h = (int)((i / W) % H);
+  long long nc = i / hw;
+  int n = (int)(nc / C);
+  const float* src = x_loc + nc * hw;
+  const float* pw = wgt + ((size_t)n * hw + h * W + w) * patch;
+  double acc = 0.0;
+  for (int t = 0; t < patch; ++t) {
+    int hh = h - kH / 2 + t / kW, ww = w - kW / 2 + t % kW;
+    if (hh >= 0 && hh < H && ww >= 0 && ww < W) acc += (double)(__ldg(src + hh * W + ww) * __ldg(pw + t));
+  }
+  y[i] = (float)acc;
+}
+
+// y[n,c,h,w] = sum_t x_ori[n,c,h-dy,w-dx] * wgt[n,h-dy,w-dx,t]
+__global__ void locatt_ck2c_loc_kernel(const float* __restrict__ x_ori, const float* __restrict__ wgt,
+                                       float* __restrict__ y, int C, int H, int W, int kH, int kW, long long total) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int patch = kH * kW, hw = H * W;
+  int w = (int)(i % W), h = (int)((i / W) % H);
+  long long nc = i / hw;
+  int n = (int)(nc / C);
+  const float* src = x_ori + nc * hw;
+  const float* pw = wgt + (size_t)n * hw * patch;
+  double acc = 0.0;
+  for (int t = 0; t < patch; ++t) {
+    int hh = h + kH / 2 - t / kW, ww = w + kW / 2 - t % kW;
+    if (hh >= 0 && hh < H && ww >= 0 && ww < W)
+      acc += (double)(__ldg(src + hh * W + ww) * __ldg(pw + ((size_t)hh * W + ww) * patch + t));
+  }
+  y[i] = (float)acc;
+}
+
 }  // namespace
 
 extern "C" {
@@ -175,6 +240,35 @@ int di_lcab_window_f32(const float* q, int ldq, const float* k, int ldk, const f
     return DI_ERR_UNSUPPORTED;
   }
   DI_CHECK_LAUNCH("di_lcab_window_f32");
+  return DI_OK;
+}
+
+// localattention.similar_forward / weighting_backward_weight  (localAttention.cpp:7-15, 51-59):
+// x_ori, x_loc [N,C,H,W] -> y [N,H,W,kH*kW]
+int di_locatt_cc2k_f32(const float* x_ori, const float* x_loc, float* y, int N, int C, int H, int W, int kH, int kW,
+                       cudaStream_t stream) {
+  DI_CHECK_ARG(x_ori && x_loc && y && N > 0 && C > 0 && H > 0 && W > 0 && kH > 0 && kW > 0, "di_locatt_cc2k_f32: bad argument");
+  long long total = (long long)N * H * W * kH * kW;
+  locatt_cc2k_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(x_ori, x_loc, y, C, H, W, kH, kW, total);
+  DI_CHECK_LAUNCH("di_locatt_cc2k_f32");
+  return DI_OK;
+}
+// localattention.weighting_forward / similar_backward(is_ori=True)  (localAttention.cpp:31-39, 17-28)
+int di_locatt_ck2c_ori_f32(const float* x_loc, const float* wgt, float* y, int N, int C, int H, int W, int kH, int kW,
+                           cudaStream_t stream) {
+  DI_CHECK_ARG(x_loc && wgt && y && N > 0 && C > 0 && H > 0 && W > 0, "di_locatt_ck2c_ori_f32: bad argument");
+  long long total = (long long)N * C * H * W;
+  locatt_ck2c_ori_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(x_loc, wgt, y, C, H, W, kH, kW, total);
+  DI_CHECK_LAUNCH("di_locatt_ck2c_ori_f32");
+  return DI_OK;
+}
+// localattention.similar_backward(is_ori=False) / weighting_backward_ori  (localAttention.cpp:17-28, 41-49)
+int di_locatt_ck2c_loc_f32(const float* x_ori, const float* wgt, float* y, int N, int C, int H, int W, int kH, int kW,
+                           cudaStream_t stream) {
+  DI_CHECK_ARG(x_ori && wgt && y && N > 0 && C > 0 && H > 0 && W > 0, "di_locatt_ck2c_loc_f32: bad argument");
+  long long total = (long long)N * C * H * W;
+  locatt_ck2c_loc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(x_ori, wgt, y, C, H, W, kH, kW, total);
+  DI_CHECK_LAUNCH("di_locatt_ck2c_loc_f32");
   return DI_OK;
 }
 

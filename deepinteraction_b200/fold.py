@@ -1,0 +1,71 @@
+"""Inference-time weight folding (float64 on the host, stored fp32 on the device).
+
+* Conv(no bias)+BatchNorm(eval) -> one affine map                 (reference encoder_utils.py:28-34)
+* P_out_proj + P_integration (two cat + 1x1 Conv+BN with no activation in between,
+  reference deepinteraction_encoder.py:13-14,26-27) -> ONE linear map over [a | b | c]
+* single-head MMRI_I2P attention: K/V projections folded into the query / output side
+  (reference encoder_utils.py:223-224,311-318)
+"""
+import math
+
+import torch
+
+
+def _d(t):
+    return t.detach().double().cpu()
+
+
+def conv_bn(conv, bn=None):
+    """-> (W [Cout, Cin*k*k] float64 in torch layout order, b [Cout])."""
+    W = _d(conv.weight)
+    b = _d(conv.bias) if conv.bias is not None else torch.zeros(W.shape[0], dtype=torch.float64)
+    if bn is not None:
+        g = _d(bn.weight) if bn.weight is not None else torch.ones_like(b)
+        beta = _d(bn.bias) if bn.bias is not None else torch.zeros_like(b)
+        s = g / torch.sqrt(_d(bn.running_var) + bn.eps)
+        W = W * s.view(-1, *([1] * (W.dim() - 1)))
+        b = (b - _d(bn.running_mean)) * s + beta
+    return W, b
+
+
+def pointwise(cb):
+    """ConvBN holder (1x1) -> (W [Cout,Cin], b)."""
+    W, b = conv_bn(cb.conv, getattr(cb, 'bn', None))
+    return W.reshape(W.shape[0], -1), b
+
+
+def pack_conv3x3(W):
+    """[Cout,Cin,3,3] -> [Cout, (ky*3+kx)*Cin + ci]"""
+    return W.permute(0, 2, 3, 1).reshape(W.shape[0], -1)
+
+
+def fuse_pair(out_proj, integration):
+    """new = integration(cat(out_proj(cat(a, b)), c))  ->  Wf [C, 3C], bf with new = Wf @ [a;b;c] + bf."""
+    W1, b1 = pointwise(out_proj)          # [C, 2C]
+    W2, b2 = pointwise(integration)       # [C, 2C]
+    C = W1.shape[0]
+    W2a, W2b = W2[:, :C], W2[:, C:]
+    return torch.cat([W2a @ W1, W2b], 1), W2a @ b1 + b2
+
+
+def i2p_fold(mha):
+    """nn.MultiheadAttention (1 head) -> M1 [Ck, Cq], c1, M2 [Cq, Ck], c2 with
+    qk = M1 q + c1;  out = M2 (sum_j a_j k_j) + c2."""
+    E = mha.embed_dim
+    assert mha.num_heads == 1
+    if mha._qkv_same_embed_dim:
+        Wq, Wk, Wv = _d(mha.in_proj_weight).chunk(3, 0)
+    else:
+        Wq, Wk, Wv = _d(mha.q_proj_weight), _d(mha.k_proj_weight), _d(mha.v_proj_weight)
+    bq, bk, bv = _d(mha.in_proj_bias).chunk(3, 0)
+    Wo, bo = _d(mha.out_proj.weight), _d(mha.out_proj.bias)
+    s = 1.0 / math.sqrt(E)
+    M1 = Wk.T @ Wq * s
+    c1 = Wk.T @ bq * s
+    M2 = Wo @ Wv
+    c2 = Wo @ bv + bo
+    return M1, c1, M2, c2
+
+
+def dev(t, device):
+    return t.to(torch.float32).contiguous().to(device)

@@ -1,0 +1,392 @@
+"""MMPI decoder on libdi_b200: parameter holders with the reference's state_dict schema and the kernel
+schedule of one forward pass.
+
+Reference: projects/mmdet3d_plugin/models/dense_heads/deepinteraction_decoder.py:19-313 (forward
+:201-313) and models/utils/decoder_utils.py (PositionEmbeddingLearned :16-32, TransformerDecoderLayer
+:35-113, MultiheadAttention :116-495, FFN :498-581, DynamicConv :584-629, ImageRCNNBlock :632-761,
+PointRCNNBlock :765-841), core/bbox/coders/transfusion_bbox_coder.py.
+
+B200-first differences from the reference schedule (results unchanged, fp32):
+  * queries are rows [B*P, C]; maps are pixel-major, so the top-k gather, RoIAlign and the cross
+    attention read contiguous 512-byte rows;
+  * the key positional embedding of the query x BEV cross attention depends only on the BEV grid, so
+    its K/V contribution is precomputed once (pack time) and added in the K/V GEMM epilogue;
+  * the per-sample / per-view Python loops of the RCNN blocks become ONE batched pass: every query is
+    pooled from the view that wins it ("later views overwrite", decoder_utils.py:759) and attends to
+    the queries of that view through a group mask -- no data-dependent host control flow, no syncs;
+  * the 324k-element argsort is a radix select + 1024-slot bitonic sort in one CTA.
+"""
+import copy
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import fold, geom, ops
+from .mmri import ConvBN
+
+
+# ------------------------------------------------------------------------------------------------
+# parameter holders
+# ------------------------------------------------------------------------------------------------
+class PositionEmbeddingLearned(nn.Module):
+    def __init__(self, cin, c):
+        super().__init__()
+        self.position_embedding_head = nn.Sequential(nn.Conv1d(cin, c, 1), nn.BatchNorm1d(c), nn.ReLU(inplace=True),
+                                                     nn.Conv1d(c, c, 1))
+
+
+class MultiheadAttention(nn.Module):
+    def __init__(self, embed_dim, num_heads):
+        super().__init__()
+        self.embed_dim, self.num_heads = embed_dim, num_heads
+        self.in_proj_weight = nn.Parameter(torch.empty(3 * embed_dim, embed_dim))
+        self.in_proj_bias = nn.Parameter(torch.zeros(3 * embed_dim))
+        self.out_proj = nn.Linear(embed_dim, embed_dim)
+        nn.init.xavier_uniform_(self.in_proj_weight)
+        nn.init.constant_(self.out_proj.bias, 0.0)
+
+
+class TransformerDecoderLayer(nn.Module):
+    def __init__(self, d_model, nhead, dim_ff):
+        super().__init__()
+        self.self_attn = MultiheadAttention(d_model, nhead)
+        self.multihead_attn = MultiheadAttention(d_model, nhead)
+        self.linear1 = nn.Linear(d_model, dim_ff)
+        self.linear2 = nn.Linear(dim_ff, d_model)
+        self.norm1, self.norm2, self.norm3 = nn.LayerNorm(d_model), nn.LayerNorm(d_model), nn.LayerNorm(d_model)
+        self.self_posembed = PositionEmbeddingLearned(2, d_model)
+        self.cross_posembed = PositionEmbeddingLearned(2, d_model)
+
+
+class FFN(nn.Module):
+    """Prediction heads: per head Sequential(ConvBN1d(in->64), Conv1d(64->k))."""
+
+    def __init__(self, cin, heads, head_conv=64):
+        super().__init__()
+        self.heads = heads
+        for name, (classes, num_conv) in heads.items():
+            layers, c = [], cin
+            for _ in range(num_conv - 1):
+                layers.append(ConvBN(c, head_conv, 1, dims=1))
+                c = head_conv
+            layers.append(nn.Conv1d(c, classes, 1))
+            setattr(self, name, nn.Sequential(*layers))
+
+
+class DynamicConv(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.dynamic_layer = nn.Linear(128, 2 * 128 * 128)
+        self.norm1, self.norm2 = nn.LayerNorm(128), nn.LayerNorm(128)
+        self.out_layer = nn.Linear(128 * 49, 128)
+        self.norm3 = nn.LayerNorm(128)
+
+
+def _rcnn_holder(blk, sfx, c, heads, dropout):
+    setattr(blk, 'dyconv' + sfx, DynamicConv())
+    setattr(blk, 'dyconv_pre_self_attn' + sfx, nn.MultiheadAttention(c, heads, dropout=dropout))
+    for i in (1, 2, 3):
+        setattr(blk, f'norm{i}' + sfx, nn.LayerNorm(c))
+    setattr(blk, 'linear1' + sfx, nn.Linear(c, 4 * c))
+    setattr(blk, 'linear2' + sfx, nn.Linear(4 * c, c))
+
+
+class ImageRCNNBlock(nn.Module):
+    sfx = ''
+
+    def __init__(self, c, heads, dropout):
+        super().__init__()
+        _rcnn_holder(self, '', c, heads, dropout)
+
+
+class PointRCNNBlock(nn.Module):
+    sfx = '_pts'
+
+    def __init__(self, c, heads, dropout):
+        super().__init__()
+        _rcnn_holder(self, '_pts', c, heads, dropout)
+
+
+class TransFusionBBoxCoder:
+    """Box parametrisation constants (core/bbox/coders/transfusion_bbox_coder.py:9-22); decoding itself
+    happens inside di_rcnn_rois_f32."""
+
+    def __init__(self, pc_range, out_size_factor, voxel_size, post_center_range=None, score_threshold=None,
+                 code_size=8, **unused):
+        self.pc_range, self.out_size_factor, self.voxel_size = pc_range, out_size_factor, voxel_size
+        self.post_center_range, self.score_threshold, self.code_size = post_center_range, score_threshold, code_size
+
+
+HEAD_ORDER = ('center', 'height', 'dim', 'rot', 'vel', 'heatmap')
+
+
+class DeepInteractionDecoder(nn.Module):
+    """Drop-in for the reference ``DeepInteractionDecoder`` (HEADS): same constructor kwargs, state_dict
+    and forward contract (``forward(pts_inputs, img_inputs, img_metas) -> [[dict]]``; side attributes
+    ``query_labels`` and ``on_the_image_mask``).  Inference (eval) only."""
+
+    def __init__(self, num_views=0, out_size_factor_img=4, num_proposals=128, auxiliary=True, hidden_channel=128,
+                 num_classes=4, num_mmpi=4, num_decoder_layers=1, num_heads=8, learnable_query_pos=False,
+                 initialize_by_heatmap=False, nms_kernel_size=1, ffn_channel=256, dropout=0.1, bn_momentum=0.1,
+                 activation='relu', common_heads=dict(), num_heatmap_convs=2, conv_cfg=dict(type='Conv1d'),
+                 norm_cfg=dict(type='BN1d'), bias='auto', loss_cls=dict(type='GaussianFocalLoss', reduction='mean'),
+                 loss_bbox=dict(type='L1Loss', reduction='mean'),
+                 loss_heatmap=dict(type='GaussianFocalLoss', reduction='mean'), train_cfg=None, test_cfg=None,
+                 bbox_coder=None, ret_idx=None):
+        super().__init__()
+        if not initialize_by_heatmap:
+            raise NotImplementedError('only initialize_by_heatmap=True (both reference configs) is supported')
+        if hidden_channel != 128:
+            raise NotImplementedError('DynamicConv is hard-coded to 128 channels in the reference (decoder_utils.py:589)')
+        if activation != 'relu' or num_decoder_layers != 1 or num_mmpi % 2 != 0 or num_heatmap_convs != 2:
+            raise NotImplementedError('unsupported decoder configuration for the libdi_b200 path')
+        self.num_classes_heat = num_classes
+        self.num_classes = num_classes + (0 if loss_cls.get('use_sigmoid', False) else 1)
+        self.num_proposals, self.auxiliary, self.num_heads = num_proposals, auxiliary, num_heads
+        self.num_decoder_layers, self.num_mmpi, self.num_views = num_decoder_layers, num_mmpi, num_views
+        self.out_size_factor_img, self.nms_kernel_size = out_size_factor_img, nms_kernel_size
+        self.train_cfg, self.test_cfg = train_cfg, test_cfg
+        self.bbox_coder = TransFusionBBoxCoder(**{k: v for k, v in bbox_coder.items() if k != 'type'})
+        c = hidden_channel
+        self.hidden_channel = c
+        use_bias = True if bias == 'auto' else bool(bias)
+        self.heatmap_head = nn.Sequential(ConvBN(c, c, 3), nn.Conv2d(c, num_classes, 3, padding=1, bias=use_bias))
+        self.heatmap_head_img = copy.deepcopy(self.heatmap_head)
+        self.class_encoding = nn.Conv1d(num_classes, c, 1)
+        self.decoder = nn.ModuleList(TransformerDecoderLayer(c, num_heads, ffn_channel)
+                                     for _ in range(num_decoder_layers))
+        heads = copy.deepcopy(common_heads)
+        heads.update(dict(heatmap=(self.num_classes, num_heatmap_convs)))
+        self.heads = heads
+        self.prediction_heads = nn.ModuleList(FFN(c, heads) for _ in range(num_decoder_layers))
+        self.decode_head, self.pred_head = nn.ModuleList(), nn.ModuleList()
+        for _ in range(num_mmpi // 2):
+            self.decode_head.append(ImageRCNNBlock(c, num_heads, dropout))
+            self.pred_head.append(FFN(2 * c, heads))
+            self.decode_head.append(PointRCNNBlock(c, num_heads, dropout))
+            self.pred_head.append(FFN(2 * c, heads))
+        self.x_size = test_cfg['grid_size'][0] // test_cfg['out_size_factor']
+        self.y_size = test_cfg['grid_size'][1] // test_cfg['out_size_factor']
+        for p in self.decoder.parameters():          # reference :171-175
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+        for m in self.modules():
+            if isinstance(m, (nn.BatchNorm2d, nn.BatchNorm1d)):
+                m.momentum = bn_momentum
+        order = [h for h in HEAD_ORDER if h in heads]
+        assert order[:4] == ['center', 'height', 'dim', 'rot'] and set(order) == set(heads), \
+            'prediction heads must be center, height, dim, rot[, vel], heatmap'
+        self.head_order = order
+        self.head_sizes = [heads[h][0] for h in order]
+        self.NP = sum(self.head_sizes)
+        self.query_labels = None
+        self.on_the_image_mask = []
+        self._pack, self._pack_key = None, None
+
+    # -- packing -----------------------------------------------------------------------------------
+    def _state_key(self):
+        return tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))
+
+    def _pack_pred(self, ffn, d):
+        W1, b1, blocks, b2 = [], [], [], []
+        for h in self.head_order:
+            seq = getattr(ffn, h)
+            w, b = fold.conv_bn(seq[0].conv, seq[0].bn)
+            W1.append(w.reshape(w.shape[0], -1))
+            b1.append(b)
+            blocks.append(fold._d(seq[1].weight).reshape(seq[1].weight.shape[0], -1))
+            b2.append(fold._d(seq[1].bias))
+        return d(torch.cat(W1, 0)), d(torch.cat(b1, 0)), d(torch.block_diag(*blocks)), d(torch.cat(b2, 0))
+
+    def _pack_mha(self, in_w, in_b, out_proj, d, two_source_q=False):
+        C, h = self.hidden_channel, self.num_heads
+        W, b = fold._d(in_w).clone(), fold._d(in_b).clone()
+        s = float(C // h) ** -0.5
+        W[:C] *= s          # q = (Wq x + bq) * head_dim^-0.5  (decoder_utils.py:407; same in nn.MultiheadAttention)
+        b[:C] *= s
+        return W, b, d(fold._d(out_proj.weight)), d(fold._d(out_proj.bias))
+
+    def pack(self, force=False):
+        key = self._state_key()
+        if self._pack is not None and key == self._pack_key and not force:
+            return self._pack
+        device = self.class_encoding.weight.device
+        if device.type != 'cuda':
+            raise RuntimeError('DeepInteractionDecoder (libdi_b200) runs on CUDA only; move the module to a GPU')
+        d = lambda t: fold.dev(t, device)
+        C = self.hidden_channel
+        pk = dict()
+        for name in ('heatmap_head', 'heatmap_head_img'):
+            seq = getattr(self, name)
+            w0, b0 = fold.conv_bn(seq[0].conv, seq[0].bn)
+            w1, b1 = fold.conv_bn(seq[1])
+            pk[name] = (d(fold.pack_conv3x3(w0)), d(b0), d(fold.pack_conv3x3(w1)), d(b1))
+        pk['wce_t'] = d(fold._d(self.class_encoding.weight)[:, :, 0].t())
+        pk['bce'] = d(fold._d(self.class_encoding.bias))
+        layer = self.decoder[0]
+
+        def pe_pack(pe):
+            seq = pe.position_embedding_head
+            w1, b1 = fold.conv_bn(seq[0], seq[1])
+            return d(w1.reshape(w1.shape[0], -1)), d(b1), d(fold._d(seq[3].weight)[:, :, 0]), d(fold._d(seq[3].bias))
+        pk['self_pe'] = pe_pack(layer.self_posembed)
+        cross_pe = pe_pack(layer.cross_posembed)
+        W, b, wo, bo = self._pack_mha(layer.self_attn.in_proj_weight, layer.self_attn.in_proj_bias,
+                                      layer.self_attn.out_proj, d)
+        pk['self_attn'] = (d(torch.cat([W, W], 1)), d(b), wo, bo)           # sources [query | query_pos_embed]
+        W, b, wo, bo = self._pack_mha(layer.multihead_attn.in_proj_weight, layer.multihead_attn.in_proj_bias,
+                                      layer.multihead_attn.out_proj, d)
+        pk['cross_q'] = (d(torch.cat([W[:C], W[:C]], 1)), d(b[:C]))
+        w_kv, b_kv = d(W[C:]), d(b[C:])
+        # constant key positional embedding -> its K/V contribution, with our own kernels (bev grid is fixed)
+        ys, xs = torch.meshgrid(torch.arange(self.y_size, dtype=torch.float32),
+                                torch.arange(self.x_size, dtype=torch.float32), indexing='ij')
+        bev_pos = torch.stack([xs + 0.5, ys + 0.5], -1).view(-1, 2).to(device)       # flatten index = y*X + x (:162-169)
+        kpe = ops.linear([ops.linear([bev_pos], cross_pe[0], cross_pe[1], ops.ACT_RELU)], cross_pe[2], cross_pe[3])
+        pk['cross_kv'] = (w_kv, b_kv, ops.linear([kpe], w_kv))
+        pk['cross_out'] = (wo, bo)
+        lin = lambda m: (d(fold._d(m.weight)), d(fold._d(m.bias)))
+        for i in (1, 2, 3):
+            pk[f'norm{i}'] = lin(getattr(layer, f'norm{i}'))
+        pk['ffn'] = lin(layer.linear1) + lin(layer.linear2)
+        pk['pred0'] = self._pack_pred(self.prediction_heads[0], d)
+        blocks = []
+        for blk, ph in zip(self.decode_head, self.pred_head):
+            g = lambda n: getattr(blk, n + blk.sfx)
+            mha = g('dyconv_pre_self_attn')
+            W, b, wo, bo = self._pack_mha(mha.in_proj_weight, mha.in_proj_bias, mha.out_proj, d)
+            dy = g('dyconv')
+            blocks.append(dict(image=blk.sfx == '', attn=(d(W), d(b), wo, bo), norm1=lin(g('norm1')),
+                               norm2=lin(g('norm2')), norm3=lin(g('norm3')), dyn=lin(dy.dynamic_layer),
+                               dn1=lin(dy.norm1), dn2=lin(dy.norm2), dout=lin(dy.out_layer), dn3=lin(dy.norm3),
+                               ffn=lin(g('linear1')) + lin(g('linear2')), pred=self._pack_pred(ph, d)))
+        pk['blocks'] = blocks
+        self._pack, self._pack_key = pk, key
+        return pk
+
+    # -- forward -----------------------------------------------------------------------------------
+    def _pred(self, pack, srcs):
+        w1, b1, w2, b2 = pack
+        return ops.linear([ops.linear(srcs, w1, b1, ops.ACT_RELU)], w2, b2)
+
+    def _roi_params(self, in_hw):
+        bc, tc = self.bbox_coder, self.test_cfg
+        return [bc.out_size_factor * bc.voxel_size[0], bc.out_size_factor * bc.voxel_size[1], bc.pc_range[0],
+                bc.pc_range[1], tc['out_size_factor'] * tc['voxel_size'][0], tc['pc_range'][0], in_hw[0], in_hw[1],
+                bc.voxel_size[0] * bc.out_size_factor, bc.pc_range[0]]
+
+    def forward_rows(self, pts_conv, new_pts, img, img_metas, debug=None):
+        """pts_conv, new_pts [B,Y,X,C]; img [B*V,h,w,C] (pixel-major) -> list of per-layer pred [B*P, NP], ..."""
+        if self.training:
+            raise NotImplementedError('libdi_b200 DeepInteractionDecoder is forward/eval only (call .eval())')
+        pk = self.pack()
+        B, Y, X, C = pts_conv.shape
+        assert (Y, X) == (self.y_size, self.x_size), 'BEV size must equal test_cfg grid_size // out_size_factor'
+        HW, P, V, K, H = Y * X, self.num_proposals, self.num_views, self.num_classes_heat, self.num_heads
+        dev_ = pts_conv.device
+        # heatmaps, NMS, top-k, query init
+        w0, b0, w1, b1 = pk['heatmap_head']
+        dense_a = ops.conv3x3(ops.conv3x3(pts_conv, w0, b0, C, True, False, ops.ACT_RELU), w1, b1, K, True, True)
+        w0, b0, w1, b1 = pk['heatmap_head_img']
+        dense_b = ops.conv3x3(ops.conv3x3(new_pts, w0, b0, C, True, False, ops.ACT_RELU), w1, b1, K, True, True)
+        ds = self.test_cfg['dataset']
+        no_nms = {'nuScenes': (1 << 8) | (1 << 9), 'Waymo': (1 << 1) | (1 << 2)}.get(ds, 0)
+        heat = ops.heatmap_nms(dense_a, dense_b, self.nms_kernel_size, no_nms)
+        top = ops.topk(heat.view(B, K * HW), P)
+        q, qpos, labels, qscore = ops.query_init(pts_conv.view(B, HW, C), top, heat, pk['wce_t'], pk['bce'], X)
+        self.query_labels = labels.long()
+        if debug is not None:
+            debug.update(top=top, heat=heat, query_feat0=q.clone(), query_pos0=qpos.clone())
+        # transformer decoder layer
+        pw1, pb1, pw2, pb2 = pk['self_pe']
+        qpe = ops.linear([ops.linear([qpos], pw1, pb1, ops.ACT_RELU)], pw2, pb2)
+        w, b, wo, bo = pk['self_attn']
+        qkv = ops.linear([q, qpe], w, b)
+        a = ops.mha_small(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], B, P, H)
+        q = ops.rows_finish(ops.linear([a], wo, bo), res=q, gamma=pk['norm1'][0], beta=pk['norm1'][1])
+        qc = ops.linear([q, qpe], *pk['cross_q'])
+        w_kv, b_kv, ckv = pk['cross_kv']
+        kv = ops.linear([pts_conv.view(B * HW, C)], w_kv, b_kv, res=ckv, res_mod=HW)
+        a = ops.cross_attn(qc, kv, B, P, HW, H)
+        q = ops.rows_finish(ops.linear([a], *pk['cross_out']), res=q, gamma=pk['norm2'][0], beta=pk['norm2'][1])
+        f1w, f1b, f2w, f2b = pk['ffn']
+        f = ops.linear([ops.linear([q], f1w, f1b, ops.ACT_RELU)], f2w, f2b)
+        q = ops.rows_finish(f, res=q, gamma=pk['norm3'][0], beta=pk['norm3'][1])
+        pred = self._pred(pk['pred0'], [q])
+        ops.pred_finish(pred, qpos)
+        first = pred
+        if debug is not None:
+            debug.update(query_feat1=q.clone(), first_res=first.clone())
+        # MMPI layers
+        in_hw = geom.input_hw(img_metas)
+        proj, _ = geom.camera_rows(img_metas, dev_)
+        aux = torch.tensor([[*(np.asarray(m.get('img_crop_offset', (0.0, 0.0)), np.float32).reshape(-1)[:2]),
+                             1.0 if m.get('flip', False) else 0.0,
+                             float(m['img_shape'][0][1]) if m.get('flip', False) else 0.0] for m in img_metas],
+                           dtype=torch.float32).to(dev_, non_blocking=True)
+        prm = self._roi_params(in_hw)
+        preds, wins = [], []
+        for li, bp in enumerate(pk['blocks']):
+            prev = q
+            if bp['image']:
+                rois, win, onbits = ops.rcnn_rois(pred, B, P, V, 0, prm, proj, aux)
+                roi = ops.roi_align(img, rois, 1.0 / self.out_size_factor_img)
+            else:
+                rois, win, onbits = ops.rcnn_rois(pred, B, P, V, 1, prm)
+                roi = ops.roi_align(new_pts, rois, 1.0)
+            w, b, wo, bo = bp['attn']
+            qkv = ops.linear([prev], w, b)
+            a = ops.mha_small(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], B, P, H, onbits, win)
+            q1 = ops.rows_finish(ops.linear([a], wo, bo), res=prev, gamma=bp['norm1'][0], beta=bp['norm1'][1])
+            params = ops.linear([q1], *bp['dyn'])
+            flat = ops.dynconv(roi, params, *bp['dn1'], *bp['dn2'])
+            part = ops.linear([flat], bp['dout'][0], splits=14)
+            t = ops.rows_finish(part, bias=bp['dout'][1], gamma=bp['dn3'][0], beta=bp['dn3'][1], act=ops.ACT_RELU)
+            q2 = ops.rows_finish(t, res=q1, gamma=bp['norm2'][0], beta=bp['norm2'][1])
+            f1w, f1b, f2w, f2b = bp['ffn']
+            f = ops.linear([ops.linear([q2], f1w, f1b, ops.ACT_GELU)], f2w, f2b)
+            q = ops.rows_finish(f, res=q2, gamma=bp['norm3'][0], beta=bp['norm3'][1],
+                                zero_if_neg=win if bp['image'] else None)
+            pred = self._pred(bp['pred'], [q, prev])
+            ops.pred_finish(pred, qpos, first if bp['image'] else None, win if bp['image'] else None)
+            preds.append(pred)
+            if bp['image']:
+                wins.append(win)
+            if debug is not None:
+                debug.setdefault('layer_query', []).append(q.clone())
+                debug.setdefault('rois', []).append(rois)
+        return dict(preds=preds, wins=wins, qscore=qscore, dense_heatmap=dense_b, labels=labels)
+
+    def _to_dict(self, pred, B, P):
+        t = pred.view(B, P, self.NP).permute(0, 2, 1)
+        out, o = {}, 0
+        for h, n in zip(self.head_order, self.head_sizes):
+            out[h] = t[:, o:o + n]
+            o += n
+        return out
+
+    def forward_nhwc(self, pts_conv, new_pts, img, img_metas, debug=None):
+        r = self.forward_rows(pts_conv, new_pts, img, img_metas, debug)
+        B, P = pts_conv.shape[0], self.num_proposals
+        self.on_the_image_mask = [(w.view(B, P) != -1) for w in r['wins']]
+        rets = [self._to_dict(p, B, P) for p in r['preds']]
+        rets[0]['query_heatmap_score'] = r['qscore']
+        rets[0]['dense_heatmap'] = r['dense_heatmap']
+        if not self.auxiliary:
+            return [rets[-1]]
+        merged = {}
+        for key in rets[0]:
+            if key in ('dense_heatmap', 'dense_heatmap_old', 'query_heatmap_score'):
+                merged[key] = rets[0][key]
+            else:
+                merged[key] = torch.cat([r_[key] for r_ in rets], -1)
+        return [[merged]]
+
+    def forward(self, pts_inputs, img_inputs, img_metas):
+        """pts_inputs: [pts_feat_conv, new_pts_feat] (B,C,Y,X); img_inputs (B*V,C,h,w).  NCHW tensors that are
+        channels-last views (what DeepInteractionEncoder returns) are used in place; true NCHW is transposed."""
+        def nhwc(t):
+            p = t.permute(0, 2, 3, 1)
+            return p if p.is_contiguous() else ops.nchw_to_nhwc(t.contiguous())
+        return self.forward_nhwc(nhwc(pts_inputs[0]), nhwc(pts_inputs[1]), nhwc(img_inputs), img_metas)

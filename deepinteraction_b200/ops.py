@@ -1,0 +1,268 @@
+"""Thin torch-tensor wrappers over the C ABI (include/di_b200.h).
+
+torch is used for device memory and the current CUDA stream only; every computation is a
+kernel of libdi_b200.so.  All wrappers require CUDA fp32 contiguous tensors and raise on
+anything else -- there is no fallback path.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
+
+LAUNCHES = [0]   # number of libdi_b200 kernel-launching calls (bench.py reports it)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda, 'libdi_b200 needs CUDA tensors'
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _f32(t, name='tensor'):
+    if not (t.is_cuda and t.dtype == torch.float32):
+        raise TypeError(f'{name}: expected a CUDA float32 tensor, got {t.dtype} on {t.device}')
+    return t
+
+
+def _call(name, *args):
+    LAUNCHES[0] += 1
+    return _lib.check(getattr(_lib.lib(), name)(*args), name)
+
+
+def _rows(t):
+    """(pointer, leading dimension) of a 2-D row-major view whose rows are contiguous."""
+    assert t.dim() == 2 and t.stride(1) == 1, (t.shape, t.stride())
+    return _ptr(t), t.stride(0)
+
+
+def linear(srcs, W, bias=None, act=ACT_NONE, out=None, res=None, res_mod=0, splits=1):
+    """out[M,N] = act(cat(srcs,1) @ W.T + bias + res[m % res_mod]).  srcs: 1..3 2-D row views."""
+    srcs = list(srcs)
+    M = srcs[0].shape[0]
+    N, K = W.shape
+    assert sum(s.shape[1] for s in srcs) == K, (K, [s.shape for s in srcs])
+    a = []
+    for s in srcs:
+        _f32(s)
+        p, ld = _rows(s)
+        a += [p, ld, s.shape[1]]
+    while len(a) < 9:
+        a += [None, 0, 0]
+    assert W.is_contiguous()
+    if splits > 1:
+        assert res is None and bias is None and act == ACT_NONE
+        part = torch.empty(splits, M, N, device=W.device, dtype=torch.float32) if out is None else out
+        n = _call('di_linear_f32', *a, _ptr(W), None, None, 0, 0, _ptr(part), N, M, N, ACT_NONE, splits, M * N,
+                  _stream())
+        return part[:n]
+    if out is None:
+        out = torch.empty(M, N, device=W.device, dtype=torch.float32)
+    po, ldo = _rows(out)
+    pr, ldr = (None, 0) if res is None else _rows(res)
+    _call('di_linear_f32', *a, _ptr(W), _ptr(bias), pr, ldr, res_mod, po, ldo, M, N, act, 1, 0, _stream())
+    return out
+
+
+def conv3x3(x, w_packed, bias, cout, x_nhwc, y_nchw=False, act=ACT_NONE):
+    """x: NCHW (N,Cin,H,W) or NHWC (N,H,W,Cin) contiguous; returns NHWC (N,H,W,cout) or NCHW."""
+    _f32(x)
+    assert x.is_contiguous()
+    if x_nhwc:
+        N, H, W, Cin = x.shape
+    else:
+        N, Cin, H, W = x.shape
+    y = torch.empty((N, cout, H, W) if y_nchw else (N, H, W, cout), device=x.device, dtype=torch.float32)
+    _call('di_conv3x3_f32', _ptr(x), int(x_nhwc), _ptr(w_packed), _ptr(bias), _ptr(y), int(y_nchw), N, Cin, H, W, cout,
+          act, _stream())
+    return y
+
+
+def lcab_window(q, k, v, N, H, W, C, ksize=9, out=None):
+    """q,k,v: 2-D row views [N*H*W, >=C] (pixel-major); returns [N*H*W, C]."""
+    if out is None:
+        out = torch.empty(N * H * W, C, device=q.device, dtype=torch.float32)
+    (pq, lq), (pk, lk), (pv, lv), (po, lo) = _rows(q), _rows(k), _rows(v), _rows(out)
+    _call('di_lcab_window_f32', pq, lq, pk, lk, pv, lv, po, lo, N, H, W, C, ksize, _stream())
+    return out
+
+
+def gather_rows(map_nhwc, coors):
+    B, Y, X, C = map_nhwc.shape
+    P = coors.shape[0]
+    rows = torch.empty(P, C, device=map_nhwc.device, dtype=torch.float32)
+    _call('di_gather_rows_f32', _ptr(map_nhwc), _ptr(coors), _ptr(rows), P, Y, X, C, _stream())
+    return rows
+
+
+def scatter_rows(rows, cnt, coors, map_nhwc):
+    B, Y, X, C = map_nhwc.shape
+    _call('di_scatter_rows_f32', _ptr(rows), _ptr(cnt), _ptr(coors), _ptr(map_nhwc), coors.shape[0], Y, X, C, _stream())
+    return map_nhwc
+
+
+def i2p_attend(qk, pillars, npts, coors, proj, img_nhwc, V, in_hw):
+    P, C = qk.shape
+    _, T, pdim = pillars.shape
+    BV, h, w, Ci = img_nhwc.shape
+    assert Ci == C and pillars.is_contiguous() and img_nhwc.is_contiguous()
+    s = torch.empty(P, C, device=qk.device, dtype=torch.float32)
+    cnt = torch.empty(P, device=qk.device, dtype=torch.int32)
+    _call('di_i2p_attend_f32', _ptr(qk), _ptr(pillars), _ptr(npts), _ptr(coors), _ptr(proj), _ptr(img_nhwc), _ptr(s),
+          _ptr(cnt), P, T, pdim, V, h, w, C, in_hw[0], in_hw[1], _stream())
+    return s, cnt
+
+
+def depth_scatter(pts, proj_b, keys_b, in_hw):
+    """pts (n, >=3) row-major; proj_b (V,12); keys_b (V,h,w) int64 view of zeroed uint64 keys."""
+    V, h, w = keys_b.shape
+    assert pts.stride(1) == 1
+    _call('di_depth_scatter', _ptr(pts), pts.stride(0), pts.shape[0], _ptr(proj_b), _ptr(keys_b), V, h, w, in_hw[0],
+          in_hw[1], _stream())
+
+
+def depth_complete(keys, want_sparse=False):
+    n_img, h, w = keys.shape
+    dev = keys.device
+    scratch = torch.empty(3 * n_img * h * w, device=dev, dtype=torch.float32)
+    dense = torch.empty(n_img, h, w, device=dev, dtype=torch.float32)
+    sparse = torch.empty(n_img, h, w, device=dev, dtype=torch.float32) if want_sparse else None
+    _call('di_depth_complete', _ptr(keys), _ptr(scratch), _ptr(dense), _ptr(sparse), n_img, h, w, _stream())
+    return (dense, sparse) if want_sparse else dense
+
+
+def lift_grid(dense, i2l, in_hw, bev_hw, pc_range):
+    n_img, h, w = dense.shape
+    grid = torch.empty(n_img, h, w, 2, device=dense.device, dtype=torch.float32)
+    rng = (ctypes.c_float * 6)(*[float(v) for v in pc_range])
+    _call('di_lift_grid', _ptr(dense), _ptr(i2l), _ptr(grid), n_img, h, w, in_hw[0], in_hw[1], bev_hw[0], bev_hw[1],
+          rng, _stream())
+    return grid
+
+
+def bev_sample(bev_nhwc, grid, V):
+    B, Yb, Xb, C = bev_nhwc.shape
+    n_img, h, w, _ = grid.shape
+    out = torch.empty(n_img, h, w, C, device=grid.device, dtype=torch.float32)
+    _call('di_bev_sample_f32', _ptr(bev_nhwc), _ptr(grid), _ptr(out), B, V, h * w, Yb, Xb, C, _stream())
+    return out
+
+
+def heatmap_nms(a, b, ks, no_nms_mask):
+    B, K, H, W = a.shape
+    assert a.is_contiguous() and b.is_contiguous()
+    out = torch.empty(B, K, H * W, device=a.device, dtype=torch.float32)
+    _call('di_heatmap_nms_f32', _ptr(a), _ptr(b), _ptr(out), B, K, H, W, ks, no_nms_mask, _stream())
+    return out
+
+
+def topk(scores, k):
+    B, n = scores.shape
+    assert scores.is_contiguous()
+    idx = torch.empty(B, k, device=scores.device, dtype=torch.int32)
+    _call('di_topk_f32', _ptr(scores), _ptr(idx), B, n, k, _stream())
+    return idx
+
+
+def query_init(feat_nhwc, top, heat, wce_t, bce, W):
+    B, HW, C = feat_nhwc.shape
+    K = heat.shape[1]
+    P = top.shape[1]
+    dev = top.device
+    qfeat = torch.empty(B * P, C, device=dev, dtype=torch.float32)
+    qpos = torch.empty(B * P, 2, device=dev, dtype=torch.float32)
+    labels = torch.empty(B, P, device=dev, dtype=torch.int32)
+    qscore = torch.empty(B, K, P, device=dev, dtype=torch.float32)
+    _call('di_query_init_f32', _ptr(feat_nhwc), _ptr(top), _ptr(heat), _ptr(wce_t), _ptr(bce), _ptr(qfeat), _ptr(qpos),
+          _ptr(labels), _ptr(qscore), B, HW, W, C, K, P, _stream())
+    return qfeat, qpos, labels, qscore
+
+
+def mha_small(q, k, v, B, P, heads, onbits=None, win=None):
+    C = q.shape[1]
+    out = torch.empty(B * P, C, device=q.device, dtype=torch.float32)
+    (pq, lq), (pk, lk), (pv, lv) = _rows(q), _rows(k), _rows(v)
+    _call('di_mha_small_f32', pq, lq, pk, lk, pv, lv, _ptr(out), C, _ptr(onbits), _ptr(win), B, P, heads, C // heads,
+          _stream())
+    return out
+
+
+def cross_attn(q, kv, B, P, HW, heads, nsplit=32):
+    C = q.shape[1]
+    assert q.is_contiguous() and kv.is_contiguous() and kv.shape == (B * HW, 2 * C)
+    part = torch.empty(B * heads * P * nsplit * 18, device=q.device, dtype=torch.float32)
+    out = torch.empty(B * P, C, device=q.device, dtype=torch.float32)
+    _call('di_cross_attn_f32', _ptr(q), _ptr(kv), _ptr(part), _ptr(out), B, P, HW, C, heads, nsplit, _stream())
+    return out
+
+
+def rows_finish(x, bias=None, res=None, gamma=None, beta=None, act=ACT_NONE, zero_if_neg=None, eps=1e-5):
+    """x: [M,C] or split-K partials [S,M,C].  y = act(LN(sum_s x[s] + bias + res))."""
+    if x.dim() == 2:
+        S, M, C = 1, x.shape[0], x.shape[1]
+        stride, ldp = 0, x.stride(0)
+    else:
+        S, M, C = x.shape
+        assert x.is_contiguous()
+        stride, ldp = M * C, C
+    out = torch.empty(M, C, device=x.device, dtype=torch.float32)
+    pr, ldr = (None, 0) if res is None else _rows(res)
+    _call('di_rows_finish_f32', _ptr(x), S, stride, ldp, _ptr(bias), pr, ldr, _ptr(gamma), _ptr(beta), _ptr(out), C,
+          _ptr(zero_if_neg), M, C, act, eps, _stream())
+    return out
+
+
+def pred_finish(pred, qpos, first=None, win=None):
+    M, NP = pred.shape
+    _call('di_pred_finish_f32', _ptr(pred), _ptr(qpos), _ptr(first), _ptr(win), M, NP, _stream())
+
+
+def rcnn_rois(pred, B, P, V, mode, params10, proj=None, aux=None):
+    dev = pred.device
+    rois = torch.empty(B * P, 5, device=dev, dtype=torch.float32)
+    win = torch.empty(B * P, device=dev, dtype=torch.int32)
+    onbits = torch.empty(B * P, device=dev, dtype=torch.int32)
+    prm = (ctypes.c_float * 10)(*[float(v) for v in params10])
+    _call('di_rcnn_rois_f32', _ptr(pred), pred.shape[1], _ptr(proj), _ptr(aux), _ptr(rois), _ptr(win), _ptr(onbits), B,
+          P, V, mode, prm, _stream())
+    return rois, win, onbits
+
+
+def roi_align(maps_nhwc, rois, scale):
+    n_maps, H, W, C = maps_nhwc.shape
+    n = rois.shape[0]
+    out = torch.empty(n, 49, C, device=rois.device, dtype=torch.float32)
+    _call('di_roi_align_f32', _ptr(maps_nhwc), _ptr(rois), _ptr(out), n, H, W, C, float(scale), _stream())
+    return out
+
+
+def dynconv(roi, params, g1, b1, g2, b2, eps=1e-5):
+    n = roi.shape[0]
+    assert roi.shape[1:] == (49, 128) and params.shape == (n, 2 * 128 * 128) and params.is_contiguous()
+    out = torch.empty(n, 49 * 128, device=roi.device, dtype=torch.float32)
+    _call('di_dynconv_f32', _ptr(roi), _ptr(params), _ptr(g1), _ptr(b1), _ptr(g2), _ptr(b2), _ptr(out), n, float(eps),
+          _stream())
+    return out
+
+
+def nchw_to_nhwc(x):
+    N, C, H, W = x.shape
+    assert x.is_contiguous()
+    out = torch.empty(N, H, W, C, device=x.device, dtype=torch.float32)
+    _call('di_nchw_to_nhwc_f32', _ptr(_f32(x)), _ptr(out), N, C, H * W, _stream())
+    return out
+
+
+def nhwc_to_nchw(x):
+    N, H, W, C = x.shape
+    assert x.is_contiguous()
+    out = torch.empty(N, C, H, W, device=x.device, dtype=torch.float32)
+    _call('di_nhwc_to_nchw_f32', _ptr(_f32(x)), _ptr(out), N, C, H * W, _stream())
+    return out

@@ -64,6 +64,17 @@ int di_conv3x3_f32(const float* x, int x_nhwc, const float* w, const float* bias
 int di_lcab_window_f32(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* out, int ldo,
                        int N, int H, int W, int C, int ksize, cudaStream_t stream);
 
+/* The reference extension's own five entry points, unfused and NCHW, for drop-in compatibility
+ * (locatt_ops/localAttention.cpp:61-73): similar_forward = cc2k(x_ori, x_loc); weighting_forward =
+ * ck2c_ori(x, weight); similar_backward(is_ori) = ck2c_ori / ck2c_loc(x, grad); weighting_backward_ori =
+ * ck2c_loc(weight-side); weighting_backward_weight = cc2k(x_ori, grad).  fp32 data, fp64 accumulate. */
+int di_locatt_cc2k_f32(const float* x_ori, const float* x_loc, float* y, int N, int C, int H, int W, int kH, int kW,
+                       cudaStream_t stream);
+int di_locatt_ck2c_ori_f32(const float* x_loc, const float* wgt, float* y, int N, int C, int H, int W, int kH, int kW,
+                           cudaStream_t stream);
+int di_locatt_ck2c_loc_f32(const float* x_ori, const float* wgt, float* y, int N, int C, int H, int W, int kH, int kW,
+                           cudaStream_t stream);
+
 /* ---- geometry-driven gathers (geometry.cu) ------------------------------------------------------ */
 
 /* rows[p,:] = map[coors[p] = (b,z,y,x)]  (models/utils/encoder_utils.py:313) */

@@ -129,7 +129,15 @@ def sparse_depth_maps(pts3, proj, in_hw, feat_hw):
         m = mask[v]
         r = (uv[v, m, 1] / H * h).long()
         c = (uv[v, m, 0] / W * w).long()
-        dm[v, r, c] = z[v, m]
+        # dm[v, r, c] = z[v, m] with duplicates resolved as a serial index_put_ does (last wins),
+        # independent of how many CPU threads torch uses
+        lin = r * w + c
+        zz = z[v, m]
+        winner = torch.full((h * w,), -1, dtype=torch.long)
+        winner.scatter_reduce_(0, lin, torch.arange(lin.numel()), 'amax', include_self=True)
+        hit = winner >= 0
+        flat = dm[v].view(-1)
+        flat[hit] = zz[winner[hit]]
     return dm
 
 

@@ -1,0 +1,247 @@
+"""GPU parity: libdi_b200 decoder kernels (through the C ABI) vs the CPU oracle / reference goldens."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+TIGHT = 5e-5
+G = os.path.join(os.path.dirname(__file__), 'golden')
+
+
+def dev():
+    return torch.device('cuda:0')
+
+
+def test_heatmap_nms_and_topk():
+    from deepinteraction_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    B, K, H, W, P = 2, 10, 36, 44, 50
+    a, b = torch.randn(B, K, H, W, generator=g) * 2, torch.randn(B, K, H, W, generator=g) * 2
+    heat = (a.sigmoid() + b.sigmoid()) / 2
+    lm = torch.zeros_like(heat)
+    lm[:, :, 1:-1, 1:-1] = F.max_pool2d(heat, 3, 1, 0)
+    lm[:, 8], lm[:, 9] = heat[:, 8], heat[:, 9]
+    ref = (heat * (heat == lm)).view(B, K, -1)
+    out = ops.heatmap_nms(a.to(dev()), b.to(dev()), 3, (1 << 8) | (1 << 9))
+    # same support; values equal to fp32 rounding of sigmoid
+    assert torch.equal(out.cpu() > 0, ref > 0)
+    assert float((out.cpu() - ref).abs().max()) < 1e-6
+    top = ops.topk(out.view(B, -1), P).cpu().long()
+    ref_top = out.cpu().view(B, -1).argsort(-1, descending=True)[:, :P]       # on the kernel's own scores
+    assert torch.equal(top, ref_top)
+
+
+def test_topk_edge_cases():
+    from deepinteraction_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    # many exact ties at the threshold and lots of zeros; ties resolve to the smaller index
+    s = torch.zeros(1, 5000)
+    s[0, torch.randperm(5000, generator=g)[:300]] = 0.5
+    s[0, 7], s[0, 4000] = 0.9, 0.7
+    top = ops.topk(s.to(dev()), 200).cpu().long()[0]
+    assert top[0] == 7 and top[1] == 4000
+    rest = top[2:]
+    half = (s[0] == 0.5).nonzero().squeeze(1)
+    assert torch.equal(rest, half[:198])
+    # k == n, tiny positive values
+    s2 = torch.rand(3, 64, generator=g) * 1e-6
+    top2 = ops.topk(s2.to(dev()), 64).cpu().long()
+    assert torch.equal(top2, s2.argsort(dim=-1, descending=True, stable=True))
+
+
+def _mha_ref(q, k, v, heads, mask=None):
+    M, C = q.shape
+    d = C // heads
+    qh, kh, vh = (t.view(M, heads, d).transpose(0, 1) for t in (q, k, v))
+    s = qh @ kh.transpose(1, 2)
+    if mask is not None:
+        s = s.masked_fill(~mask[None], float('-inf'))
+    return (s.softmax(-1) @ vh).transpose(0, 1).reshape(M, C)
+
+
+def test_mha_small_with_and_without_group_mask():
+    from deepinteraction_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    B, P, C, H = 2, 200, 128, 8
+    qkv = torch.randn(B * P, 3 * C, generator=g)
+    onbits = torch.randint(0, 64, (B * P,), generator=g, dtype=torch.int32)
+    win = torch.full((B * P,), -1, dtype=torch.int32)
+    for i in range(B * P):
+        bits = [v for v in range(6) if (int(onbits[i]) >> v) & 1]
+        if bits:
+            win[i] = bits[-1]
+    qd = qkv.to(dev())
+    out = ops.mha_small(qd[:, :C], qd[:, C:2 * C], qd[:, 2 * C:], B, P, H).cpu()
+    out_m = ops.mha_small(qd[:, :C], qd[:, C:2 * C], qd[:, 2 * C:], B, P, H, onbits.to(dev()), win.to(dev())).cpu()
+    for b in range(B):
+        sl = slice(b * P, (b + 1) * P)
+        q, k, v = qkv[sl, :C], qkv[sl, C:2 * C], qkv[sl, 2 * C:]
+        assert rel_err(out[sl], _mha_ref(q, k, v, H)) < TIGHT
+        w, ob = win[sl].long(), onbits[sl].long()
+        mask = ((ob[None, :] >> w.clamp(min=0)[:, None]) & 1).bool()
+        ref = _mha_ref(q, k, v, H, mask)
+        live = w >= 0
+        assert rel_err(out_m[sl][live], ref[live]) < TIGHT
+        assert float(out_m[sl][~live].abs().max()) == 0.0
+
+
+def test_cross_attention_matches_dense_softmax():
+    from deepinteraction_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    B, P, HW, C, H = 2, 200, 3000, 128, 8
+    q = torch.randn(B * P, C, generator=g) * 0.5
+    kv = torch.randn(B * HW, 2 * C, generator=g)
+    out = ops.cross_attn(q.to(dev()), kv.to(dev()), B, P, HW, H, nsplit=7).cpu()
+    for b in range(B):
+        qb, kb, vb = q[b * P:(b + 1) * P], kv[b * HW:(b + 1) * HW, :C], kv[b * HW:(b + 1) * HW, C:]
+        d = C // H
+        s = torch.einsum('phd,khd->hpk', qb.view(P, H, d), kb.view(HW, H, d))
+        ref = torch.einsum('hpk,khd->phd', s.softmax(-1), vb.view(HW, H, d)).reshape(P, C)
+        assert rel_err(out[b * P:(b + 1) * P], ref) < TIGHT
+
+
+def test_rows_finish_layernorm():
+    from deepinteraction_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    x, r = torch.randn(333, 128, generator=g), torch.randn(333, 128, generator=g)
+    gm, bt = torch.rand(128, generator=g) + 0.5, torch.randn(128, generator=g)
+    ref = F.relu(F.layer_norm(x + r, (128,), gm, bt))
+    out = ops.rows_finish(x.to(dev()), res=r.to(dev()), gamma=gm.to(dev()), beta=bt.to(dev()), act=ops.ACT_RELU)
+    assert rel_err(out.cpu(), ref) < TIGHT
+
+
+def test_roi_align_matches_oracle():
+    from oracle.geometry import roi_align
+    from deepinteraction_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    maps = torch.randn(3, 128, 28, 50, generator=g)
+    rois = torch.tensor([[0, 8.0, 12.0, 70.0, 49.0], [1, -30.0, -10.0, 20.0, 30.0], [2, 150.0, 60.0, 230.0, 140.0],
+                         [1, 40.0, 40.0, 40.0, 40.0], [-1, 0.0, 0.0, 10.0, 10.0], [0, 190.0, 100.0, 260.0, 150.0]])
+    out = ops.roi_align(maps.permute(0, 2, 3, 1).contiguous().to(dev()), rois.to(dev()), 0.25).cpu()   # [n,49,C]
+    for i, r in enumerate(rois):
+        if r[0] < 0:
+            assert float(out[i].abs().max()) == 0.0
+            continue
+        ref = roi_align(maps[int(r[0])], r[None, 1:], 7, 0.25, 2)[0]            # (C,7,7)
+        assert rel_err(out[i].t().reshape(128, 7, 7), ref) < TIGHT
+
+
+def test_dynconv_matches_oracle():
+    import oracle.mmpi as om
+    from deepinteraction_b200 import ops
+    torch.manual_seed(6)
+    m = om.DynamicConv().eval()
+    g = torch.Generator().manual_seed(6)
+    n = 37
+    pro = torch.randn(1, n, 128, generator=g)
+    roi = torch.randn(49, n, 128, generator=g)
+    with torch.no_grad():
+        params = m.dynamic_layer(pro)[0]                                            # [n, 32768]
+        feats = roi.permute(1, 0, 2)
+        p1 = params[:, :16384].reshape(n, 128, 128)
+        p2 = params[:, 16384:].reshape(n, 128, 128)
+        f = F.relu(m.norm1(torch.bmm(feats, p1)))
+        ref = F.relu(m.norm2(torch.bmm(f, p2))).flatten(1)
+    d = lambda t: t.detach().contiguous().to(dev())
+    out = ops.dynconv(d(feats), d(params), d(m.norm1.weight), d(m.norm1.bias), d(m.norm2.weight), d(m.norm2.bias))
+    assert rel_err(out.cpu(), ref) < TIGHT
+
+
+def _build(tag_seed, views, proposals, test_cfg=None, coder=None):
+    import oracle.mmpi as om
+    from deepinteraction_b200 import mmpi, synth
+    from tools import make_goldens as mg
+    kw = dict(num_views=views, out_size_factor_img=4, num_proposals=proposals, auxiliary=True, hidden_channel=128,
+              num_classes=10, num_mmpi=4, num_heads=8, initialize_by_heatmap=True, nms_kernel_size=3, ffn_channel=256,
+              dropout=0.1, bn_momentum=0.1, activation='relu',
+              common_heads=dict(center=(2, 2), height=(1, 2), dim=(3, 2), rot=(2, 2), vel=(2, 2)),
+              loss_cls=dict(type='FocalLoss', use_sigmoid=True, gamma=2, alpha=0.25, reduction='mean', loss_weight=1.0),
+              bbox_coder=dict(coder or mg.DEC_CODER), test_cfg=dict(test_cfg or mg.DEC_TEST_CFG))
+    torch.manual_seed(tag_seed)
+    o = om.DeepInteractionDecoder(**kw).eval()
+    synth.randomize_norm_stats(o, tag_seed)
+    m = mmpi.DeepInteractionDecoder(**kw)
+    m.load_state_dict(o.state_dict(), strict=True)
+    return o, m.to(dev()).eval()
+
+
+def _compare(out, ref, tol):
+    errs = {k: rel_err(out[k].cpu(), ref[k]) for k in ref}
+    print({k: '%.1e' % v for k, v in errs.items()})
+    for k, e in errs.items():
+        assert e < tol, (k, e)
+
+
+@pytest.mark.parametrize('tag', ['decoder_small', 'decoder_small_aug'])
+def test_decoder_small_matches_reference_golden(tag):
+    from tools.make_goldens import small_frame
+    gold = torch.load(os.path.join(G, tag + '.pt'), weights_only=False)
+    o, m = _build(gold['seed'], 2, 24)
+    gen = torch.Generator().manual_seed(gold['seed'])
+    fr = small_frame(gold['seed'], aug=gold['aug'], views=2, batch=2)
+    pts_in = [torch.randn(2, 128, 36, 36, generator=gen), torch.randn(2, 128, 36, 36, generator=gen)]
+    img_in = torch.randn(4, 128, 28, 50, generator=gen)
+    out = m([p.to(dev()) for p in pts_in], img_in.to(dev()), fr['img_metas'])[0][0]
+    assert torch.equal(m.query_labels.cpu(), gold['query_labels'])
+    for a, b in zip(m.on_the_image_mask, gold['on_the_image_mask']):
+        assert torch.equal(a.cpu(), b)
+    _compare(out, gold['out'], TOL)
+
+
+def test_decoder_stages_match_oracle():
+    """Stage-by-stage (top-k, query init, transformer layer, every MMPI layer) on the small scene."""
+    from tools.make_goldens import small_frame
+    o, m = _build(1600, 2, 24)
+    gen = torch.Generator().manual_seed(1600)
+    fr = small_frame(1600, aug=True, views=2, batch=2)
+    pts_in = [torch.randn(2, 128, 36, 36, generator=gen), torch.randn(2, 128, 36, 36, generator=gen)]
+    img_in = torch.randn(4, 128, 28, 50, generator=gen)
+    with torch.no_grad():
+        ref, aux = o(pts_in, img_in, fr['img_metas'], return_aux=True)
+    dbg = {}
+    nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous().to(dev())
+    m.forward_nhwc(nhwc(pts_in[0]), nhwc(pts_in[1]), nhwc(img_in), fr['img_metas'], debug=dbg)
+    B, P, C = 2, 24, 128
+    assert torch.equal(dbg['top'].cpu().long(), aux['top'])
+    assert rel_err(dbg['heat'].cpu(), aux['heatmap']) < 1e-6
+    rows = lambda t: t.permute(0, 2, 1).reshape(B * P, -1)                       # (B,C,P) -> rows
+    assert rel_err(dbg['query_feat0'].cpu(), rows(aux['query_feat0'])) < TIGHT
+    assert torch.equal(dbg['query_pos0'].cpu(), aux['query_pos0'].reshape(B * P, 2))
+    assert rel_err(dbg['query_feat1'].cpu(), rows(aux['query_feat1'])) < 2e-4
+    first = torch.cat([aux['first_res'][k] for k in m.head_order], 1)
+    assert rel_err(dbg['first_res'].cpu(), rows(first)) < 2e-4
+    for l in range(4):
+        e = rel_err(dbg['layer_query'][l].cpu(), rows(aux['layer_query'][l]))
+        print('layer', l, 'query rel err %.2e' % e)
+        assert e < TOL
+    for a, b in zip(m.on_the_image_mask, aux['on_view']):
+        assert torch.equal(a.cpu(), b != -1)
+
+
+def test_decoder_base_shape_matches_oracle():
+    """Base config shapes (180x180 BEV, 6 x 112x200 image maps, 200 queries), random feature maps."""
+    from deepinteraction_b200 import synth
+    test_cfg = dict(dataset='nuScenes', grid_size=[1440, 1440, 40], out_size_factor=8, pc_range=[-54.0, -54.0],
+                    voxel_size=[0.075, 0.075], nms_type=None)
+    coder = dict(type='TransFusionBBoxCoder', pc_range=[-54.0, -54.0], voxel_size=[0.075, 0.075], out_size_factor=8,
+                 post_center_range=[-61.2, -61.2, -10.0, 61.2, 61.2, 10.0], score_threshold=0.0, code_size=10)
+    o, m = _build(1601, 6, 200, test_cfg, coder)
+    gen = torch.Generator().manual_seed(1601)
+    rig = synth.camera_rig(6, (448, 800))
+    metas = [dict(lidar2img=[r.astype(np.float32) for r in rig], input_shape=(448, 800),
+                  img_shape=[(448, 800, 3)] * 6)]
+    pts_in = [torch.randn(1, 128, 180, 180, generator=gen), torch.randn(1, 128, 180, 180, generator=gen)]
+    img_in = torch.randn(6, 128, 112, 200, generator=gen)
+    with torch.no_grad():
+        ref = o(pts_in, img_in, metas)[0][0]
+    out = m([p.to(dev()) for p in pts_in], img_in.to(dev()), metas)[0][0]
+    assert torch.equal(m.query_labels.cpu(), o.query_labels)
+    for a, b in zip(m.on_the_image_mask, o.on_the_image_mask):
+        assert torch.equal(a.cpu(), b)
+    _compare(out, ref, TOL)
