@@ -13,6 +13,7 @@ from . import _lib
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 
 LAUNCHES = [0]   # number of libdi_b200 kernel-launching calls (bench.py reports it)
+PROFILE = [None]  # bench.py sets PROFILE[0] = [] to record (name, start_event, end_event, bytes, flops) per call
 
 
 def _stream():
@@ -32,9 +33,18 @@ def _f32(t, name='tensor'):
     return t
 
 
-def _call(name, *args):
+def _call(name, *args, nbytes=0, flops=0):
+    """nbytes / flops: ALGORITHMIC traffic and work of the call (inputs read once, outputs written once)."""
     LAUNCHES[0] += 1
-    return _lib.check(getattr(_lib.lib(), name)(*args), name)
+    prof = PROFILE[0]
+    if prof is None:
+        return _lib.check(getattr(_lib.lib(), name)(*args), name)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rc = _lib.check(getattr(_lib.lib(), name)(*args), name)
+    e1.record()
+    prof.append((name, e0, e1, nbytes, flops))
+    return rc
 
 
 def _rows(t):
@@ -61,13 +71,14 @@ def linear(srcs, W, bias=None, act=ACT_NONE, out=None, res=None, res_mod=0, spli
         assert res is None and bias is None and act == ACT_NONE
         part = torch.empty(splits, M, N, device=W.device, dtype=torch.float32) if out is None else out
         n = _call('di_linear_f32', *a, _ptr(W), None, None, 0, 0, _ptr(part), N, M, N, ACT_NONE, splits, M * N,
-                  _stream())
+                  _stream(), nbytes=4 * (M * K + N * K + splits * M * N), flops=2 * M * N * K)
         return part[:n]
     if out is None:
         out = torch.empty(M, N, device=W.device, dtype=torch.float32)
     po, ldo = _rows(out)
     pr, ldr = (None, 0) if res is None else _rows(res)
-    _call('di_linear_f32', *a, _ptr(W), _ptr(bias), pr, ldr, res_mod, po, ldo, M, N, act, 1, 0, _stream())
+    _call('di_linear_f32', *a, _ptr(W), _ptr(bias), pr, ldr, res_mod, po, ldo, M, N, act, 1, 0, _stream(),
+          nbytes=4 * (M * K + N * K + M * N + (0 if res is None else res.numel())), flops=2 * M * N * K)
     return out
 
 
@@ -81,7 +92,7 @@ def conv3x3(x, w_packed, bias, cout, x_nhwc, y_nchw=False, act=ACT_NONE):
         N, Cin, H, W = x.shape
     y = torch.empty((N, cout, H, W) if y_nchw else (N, H, W, cout), device=x.device, dtype=torch.float32)
     _call('di_conv3x3_f32', _ptr(x), int(x_nhwc), _ptr(w_packed), _ptr(bias), _ptr(y), int(y_nchw), N, Cin, H, W, cout,
-          act, _stream())
+          act, _stream(), nbytes=4 * (x.numel() + w_packed.numel() + y.numel()), flops=2 * N * H * W * cout * 9 * Cin)
     return y
 
 
@@ -90,7 +101,8 @@ def lcab_window(q, k, v, N, H, W, C, ksize=9, out=None):
     if out is None:
         out = torch.empty(N * H * W, C, device=q.device, dtype=torch.float32)
     (pq, lq), (pk, lk), (pv, lv), (po, lo) = _rows(q), _rows(k), _rows(v), _rows(out)
-    _call('di_lcab_window_f32', pq, lq, pk, lk, pv, lv, po, lo, N, H, W, C, ksize, _stream())
+    _call('di_lcab_window_f32', pq, lq, pk, lk, pv, lv, po, lo, N, H, W, C, ksize, _stream(),
+          nbytes=4 * 4 * N * H * W * C, flops=2 * 2 * ksize * ksize * N * H * W * C)
     return out
 
 
@@ -116,7 +128,8 @@ def i2p_attend(qk, pillars, npts, coors, proj, img_nhwc, V, in_hw):
     s = torch.empty(P, C, device=qk.device, dtype=torch.float32)
     cnt = torch.empty(P, device=qk.device, dtype=torch.int32)
     _call('di_i2p_attend_f32', _ptr(qk), _ptr(pillars), _ptr(npts), _ptr(coors), _ptr(proj), _ptr(img_nhwc), _ptr(s),
-          _ptr(cnt), P, T, pdim, V, h, w, C, in_hw[0], in_hw[1], _stream())
+          _ptr(cnt), P, T, pdim, V, h, w, C, in_hw[0], in_hw[1], _stream(),
+          nbytes=4 * (2 * P * C + pillars.numel() + img_nhwc.numel()), flops=0)
     return s, cnt
 
 
@@ -151,7 +164,8 @@ def bev_sample(bev_nhwc, grid, V):
     B, Yb, Xb, C = bev_nhwc.shape
     n_img, h, w, _ = grid.shape
     out = torch.empty(n_img, h, w, C, device=grid.device, dtype=torch.float32)
-    _call('di_bev_sample_f32', _ptr(bev_nhwc), _ptr(grid), _ptr(out), B, V, h * w, Yb, Xb, C, _stream())
+    _call('di_bev_sample_f32', _ptr(bev_nhwc), _ptr(grid), _ptr(out), B, V, h * w, Yb, Xb, C, _stream(),
+          nbytes=4 * (bev_nhwc.numel() + grid.numel() + out.numel()))
     return out
 
 
@@ -199,7 +213,8 @@ def cross_attn(q, kv, B, P, HW, heads, nsplit=32):
     assert q.is_contiguous() and kv.is_contiguous() and kv.shape == (B * HW, 2 * C)
     part = torch.empty(B * heads * P * nsplit * 18, device=q.device, dtype=torch.float32)
     out = torch.empty(B * P, C, device=q.device, dtype=torch.float32)
-    _call('di_cross_attn_f32', _ptr(q), _ptr(kv), _ptr(part), _ptr(out), B, P, HW, C, heads, nsplit, _stream())
+    _call('di_cross_attn_f32', _ptr(q), _ptr(kv), _ptr(part), _ptr(out), B, P, HW, C, heads, nsplit, _stream(),
+          nbytes=4 * (kv.numel() + 2 * q.numel()), flops=4 * B * P * HW * C)
     return out
 
 
@@ -239,7 +254,8 @@ def roi_align(maps_nhwc, rois, scale):
     n_maps, H, W, C = maps_nhwc.shape
     n = rois.shape[0]
     out = torch.empty(n, 49, C, device=rois.device, dtype=torch.float32)
-    _call('di_roi_align_f32', _ptr(maps_nhwc), _ptr(rois), _ptr(out), n, H, W, C, float(scale), _stream())
+    _call('di_roi_align_f32', _ptr(maps_nhwc), _ptr(rois), _ptr(out), n, H, W, C, float(scale), _stream(),
+          nbytes=4 * (out.numel() * 5))
     return out
 
 
@@ -248,7 +264,7 @@ def dynconv(roi, params, g1, b1, g2, b2, eps=1e-5):
     assert roi.shape[1:] == (49, 128) and params.shape == (n, 2 * 128 * 128) and params.is_contiguous()
     out = torch.empty(n, 49 * 128, device=roi.device, dtype=torch.float32)
     _call('di_dynconv_f32', _ptr(roi), _ptr(params), _ptr(g1), _ptr(b1), _ptr(g2), _ptr(b2), _ptr(out), n, float(eps),
-          _stream())
+          _stream(), nbytes=4 * (roi.numel() + params.numel() + out.numel()), flops=2 * 2 * n * 49 * 128 * 128)
     return out
 
 
