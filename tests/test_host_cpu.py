@@ -1,0 +1,178 @@
+"""CPU: host-side logic of the product path (weight folding, geometry folding, plug-in registry / config
+loading, state-dict schema, sharding over a 2-rank gloo group).  No kernel launches."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_err
+
+REF_CFG = '/root/reference/projects/configs/nuscenes/Fusion_0075_refactor.py'
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUR_CFG = os.path.join(ROOT, 'projects', 'configs', 'nuscenes', 'di_b200_base_hotpath.py')
+
+
+def test_conv_bn_and_fuse_pair_folding():
+    import oracle.mmri as om
+    from deepinteraction_b200 import fold, synth, mmri
+    torch.manual_seed(0)
+    C = 16
+    a, b = om.ConvBNReLU(2 * C, C, 1, act=False).eval(), om.ConvBNReLU(2 * C, C, 1, act=False).eval()
+    synth.randomize_norm_stats(a, 1)
+    synth.randomize_norm_stats(b, 2)
+    x, y, z = (torch.randn(3, C, 5, 7) for _ in range(3))
+    with torch.no_grad():
+        ref = b(torch.cat((a(torch.cat((x, y), 1)), z), 1))
+    ha, hb = mmri.ConvBN(2 * C, C), mmri.ConvBN(2 * C, C)
+    ha.load_state_dict(a.state_dict())
+    hb.load_state_dict(b.state_dict())
+    W, bias = fold.fuse_pair(ha, hb)
+    rows = torch.cat([t.permute(0, 2, 3, 1).reshape(-1, C) for t in (x, y, z)], 1).double()
+    out = (rows @ W.t() + bias).float().view(3, 5, 7, C).permute(0, 3, 1, 2)
+    assert rel_err(out, ref) < 1e-5
+
+
+def test_i2p_attention_fold_equals_multihead_attention():
+    from deepinteraction_b200 import fold
+    torch.manual_seed(1)
+    C = 32
+    mha = torch.nn.MultiheadAttention(C, 1, kdim=C, vdim=C, batch_first=True).eval()
+    with torch.no_grad():
+        mha.in_proj_bias.normal_(0, 0.1)
+        mha.out_proj.bias.normal_(0, 0.1)
+    q, kv = torch.randn(7, 1, C), torch.randn(7, 11, C)
+    mask = torch.rand(7, 1, 11) > 0.6
+    mask[:, :, 0] = False
+    with torch.no_grad():
+        ref = mha(q, kv, kv, attn_mask=mask)[0][:, 0]
+    M1, c1, M2, c2 = fold.i2p_fold(mha)
+    qk = q[:, 0].double() @ M1.t() + c1
+    logits = torch.einsum('pc,pkc->pk', qk, kv.double()).masked_fill(mask[:, 0], float('-inf'))
+    s = torch.einsum('pk,pkc->pc', logits.softmax(-1), kv.double())
+    out = (s @ M2.t() + c2).float()
+    assert rel_err(out, ref) < 1e-5
+
+
+def test_aug_affine_matches_apply_3d_transformation():
+    from oracle.geometry import apply_3d_transformation
+    from deepinteraction_b200 import geom, synth
+    meta = dict(synth.AUG_META)
+    pts = torch.randn(50, 3, dtype=torch.float64) * 20
+    for reverse in (False, True):
+        ref = apply_3d_transformation(pts, meta, reverse=reverse)
+        A = torch.from_numpy(geom.aug_affine(meta, reverse))
+        out = (torch.cat([pts, torch.ones(50, 1, dtype=torch.float64)], 1) @ A.t())[:, :3]
+        assert float((out - ref).abs().max()) < 1e-9
+    assert np.allclose(geom.aug_affine({}, True), np.eye(4))
+    # vertical flip and an identity flow entry
+    meta2 = dict(pcd_vertical_flip=True, transformation_3d_flow=['VF', 'HF'])
+    ref = apply_3d_transformation(pts, meta2, reverse=False)
+    out = (torch.cat([pts, torch.ones(50, 1, dtype=torch.float64)], 1) @ torch.from_numpy(geom.aug_affine(meta2, False)).t())[:, :3]
+    assert float((out - ref).abs().max()) < 1e-12
+
+
+def test_camera_rows_project_like_the_oracle():
+    import oracle.mmri as om
+    from deepinteraction_b200 import geom, synth
+    fr = synth.make_frame_batch(7, batch=1, num_views=3, in_hw=(112, 200), n_points=500, aug=True, c_img=4, c_pts=4,
+                                bev_hw=(8, 8))
+    proj, i2l = geom.camera_rows(fr['img_metas'], 'cpu')
+    from oracle.geometry import apply_3d_transformation
+    pts = fr['pts_metas']['pts'][0][:, :3]
+    p3 = apply_3d_transformation(pts, fr['img_metas'][0], reverse=True)
+    l2i = torch.from_numpy(np.asarray(fr['img_metas'][0]['lidar2img']))
+    uv, z, mask, _ = om.project_points(p3, l2i, (112, 200))
+    cam = torch.einsum('vrk,nk->vnr', proj[0].view(3, 3, 4), torch.cat([pts, torch.ones(len(pts), 1)], 1))
+    assert float((cam[..., 2] - z).abs().max()) < 1e-3
+    vis = mask
+    u2 = cam[..., 0] / cam[..., 2].clamp_min(1e-5)
+    assert float((u2 - uv[..., 0])[vis].abs().max()) < 2e-2
+
+
+@pytest.mark.parametrize('cfg_path', [OUR_CFG, REF_CFG])
+def test_plugin_builds_from_config_with_reference_state_dict_schema(cfg_path):
+    if not os.path.exists(cfg_path):
+        pytest.skip('reference tree not mounted here')
+    import projects.mmdet3d_plugin  # noqa: F401
+    from projects.mmdet3d_plugin.registry import load_config, build_hot_path, NECKS, HEADS, BBOX_CODERS
+    import oracle.mmri as om
+    import oracle.mmpi as omp
+    cfg = load_config(cfg_path)
+    assert cfg['plugin'] is True and cfg['plugin_dir'] == 'projects/mmdet3d_plugin/'
+    neck, head = build_hot_path(cfg)
+    assert type(neck).__name__ == 'DeepInteractionEncoder' and type(head).__name__ == 'DeepInteractionDecoder'
+    m = cfg['model']
+    o_neck = om.DeepInteractionEncoder(**{k: v for k, v in m['imgpts_neck'].items() if k != 'type'})
+    o_head = omp.DeepInteractionDecoder(test_cfg=m['test_cfg']['pts'],
+                                        **{k: v for k, v in m['pts_bbox_head'].items() if k != 'type'})
+    # the oracle's state_dict was loaded strictly into the REFERENCE classes by tools/make_goldens.py
+    for ours, ref in ((neck, o_neck), (head, o_head)):
+        a, b = ours.state_dict(), ref.state_dict()
+        assert set(a) == set(b), set(a) ^ set(b)
+        for k in a:
+            assert a[k].shape == b[k].shape, k
+        ours.load_state_dict(b, strict=True)
+    assert sum(p.numel() for p in neck.parameters()) == 1780480          # 1.78 M / 21.92 M
+    assert sum(p.numel() for p in head.parameters()) == 21922936
+    for reg, name in ((NECKS, 'DeepInteractionEncoder'), (HEADS, 'DeepInteractionDecoder'),
+                      (BBOX_CODERS, 'TransFusionBBoxCoder')):
+        assert reg.get(name) is not None
+
+
+def test_product_modules_refuse_cpu_and_training():
+    from deepinteraction_b200 import mmri
+    enc = mmri.DeepInteractionEncoder(1, 8, 8, 16).eval()
+    with pytest.raises(RuntimeError, match='CUDA only'):
+        enc.pack()
+
+
+def test_frame_slices_cover_the_batch():
+    from deepinteraction_b200.shard import frame_slice
+    for total in (1, 7, 16, 17):
+        for world in (1, 2, 3, 8):
+            seen = []
+            for r in range(world):
+                s = frame_slice(total, world, r)
+                seen += list(range(s.start, s.stop))
+            assert seen == list(range(total))
+
+
+def _gloo_worker(rank, world, port, ret):
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        import oracle.mmri as om
+        from deepinteraction_b200 import synth
+        from deepinteraction_b200.shard import frame_slice, gather_frames, max_over_ranks
+        torch.manual_seed(5)
+        m = om.LocalContextAttentionBlock(16, 16, 9).eval()
+        synth.randomize_norm_stats(m, 5)
+        g = torch.Generator().manual_seed(6)
+        x = torch.randn(5, 16, 9, 11, generator=g)             # 5 frames over 2 ranks: 3 + 2
+        sl = frame_slice(5, world, rank)
+        with torch.no_grad():
+            local = m(x[sl], x[sl])
+            full = m(x, x)
+        got = gather_frames(local, 5)
+        t = max_over_ranks(10.0 + rank)
+        ret[rank] = (bool(torch.equal(got, full)), t)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sharding_is_bitwise_equal_to_single_rank():
+    import torch.multiprocessing as mp
+    import socket
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_gloo_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert ret[0][0] and ret[1][0], 'sharded frames must equal the single-process result bit for bit'
+    assert ret[0][1] == 11.0 and ret[1][1] == 11.0
