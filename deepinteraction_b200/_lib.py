@@ -21,6 +21,8 @@ SIGNATURES = {
     # gemm.cu
     'di_linear_f32': [_p, _i, _i, _p, _i, _i, _p, _i, _i, _p, _p, _p, _i, _i, _p, _i, _i, _i, _i, _i, _ll, _p],
     'di_conv3x3_f32': [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
+    'di_linear_tc_f32': [_p, _i, _i, _p, _i, _i, _p, _i, _i, _p, _p, _p, _p, _i, _i, _p, _i, _i, _i, _i, _p],
+    'di_conv3x3_tc_f32': [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     # lcab.cu
     'di_lcab_window_f32': [_p, _i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _p],
     'di_locatt_cc2k_f32': [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p],

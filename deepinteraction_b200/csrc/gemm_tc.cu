@@ -1,0 +1,431 @@
+// Blackwell tensor-core path of the dense layers: C[M,N] = act(A[M,K] * W[N,K]^T + bias (+res)), fp32 in/out,
+// computed as an error-compensated 3xTF32 product on tcgen05 (UMMA) with the accumulator in TMEM:
+//
+//     A = A_hi + A_lo,  W = W_hi + W_lo   (hi = value rounded to 10 mantissa bits, lo = exact remainder)
+//     A*W ~= A_hi*W_hi + A_lo*W_hi + A_hi*W_lo                (dropped term ~2^-22 relative)
+//
+// which keeps the result fp32-faithful (the parity bar of this path includes exact top-k indices, so plain
+// TF32/BF16 is not admissible).  Same layers as gemm.cu: every 1x1 Conv(+BN)(+ReLU) / cat+conv pair
+// (reference models/utils/encoder_utils.py:11-34, models/necks/deepinteraction_encoder.py:26-32) and the
+// 3x3 convs as implicit GEMM over pixel-major (NHWC) maps (models/necks/deepinteraction_encoder.py:47-62,
+// models/dense_heads/deepinteraction_decoder.py:83-101).
+//
+// One CTA = one 128 x 128 output tile, 192 threads, warp-specialised:
+//   warp 0      TMA producer: per 32-wide K chunk, box loads of A (2-D [rows,K] map, or a 4-D NHWC map whose
+//               8x16-pixel box shifted by the filter tap gives zero padding for free) and of W_hi / W_lo
+//               into a 3-stage ring of 128B-swizzled K-major tiles (cp.async.bulk.tensor + mbarrier tx-count)
+//   warps 2-5   splitter: rewrite the landed A chunk in place as A_hi and write A_lo beside it
+//               (elementwise, so the swizzle is irrelevant), fence.proxy.async, arrive
+//   warp 1      MMA issuer: 4 k-steps x 3 products of tcgen05.mma.kind::tf32 (M=128,N=128,K=8) per chunk,
+//               tcgen05.commit frees the stage; accumulator = 128 TMEM columns
+//   warps 2-5   epilogue: tcgen05.ld (32 lanes x 32 columns per warp and step) -> bias/res/activation ->
+//               shared-memory transpose -> coalesced 512-byte row stores
+#include "common.cuh"
+#include <cuda.h>
+
+namespace {
+
+constexpr int TM = 128, TN = 128, TK = 32;          // tile; TK fp32 = 128 bytes = one swizzle row
+constexpr int STAGES = 3;
+constexpr int A_BYTES = TM * TK * 4;                // 16 KB
+constexpr int STAGE_BYTES = 4 * A_BYTES;            // A_hi | A_lo | W_hi | W_lo
+constexpr int NTHREADS = 192;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row atoms 1024 bytes apart.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) /*LBO (unused)*/ | (64ull << 32) /*SBO = 1024 B*/ |
+         (1ull << 46) /*version*/ | (2ull << 61) /*SWIZZLE_128B*/;
+}
+// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 128
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(
+          tmem_d),
+      "l"(da), "l"(db), "r"(IDESC), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+struct TcParams {
+  int M, N;                 // logical output size (rows, columns)
+  int nsrc;                 // linear: number of A sources (1..3)
+  int kchunks[3];           // linear: K_s / 32 per source; conv: kchunks[0] = Cin / 32
+  int conv;                 // 1: 3x3 conv over an NHWC map (A map is 4-D)
+  int H, W, tiles_x, tiles_y;  // conv geometry: tile = 8 rows x 16 cols of pixels
+  float* C;
+  int ldc;
+  const float* bias;
+  const float* res;
+  int ldres, res_mod, act;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+               const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapWhi,
+               const __grid_constant__ CUtensorMap mapWlo, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;        // SWIZZLE_128B needs 1024-byte alignment
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bars = base + STAGES * STAGE_BYTES;                   // full[S], split[S], empty[S], tmem_full, tmem_slot
+  auto full = [&](int s) { return bars + 8u * s; };
+  auto split = [&](int s) { return bars + 8u * (STAGES + s); };
+  auto empty = [&](int s) { return bars + 8u * (2 * STAGES + s); };
+  const uint32_t tmem_full = bars + 8u * (3 * STAGES);
+  const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 1);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + STAGES * STAGE_BYTES + 8 * (3 * STAGES + 1));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.y * TN;
+  int m0 = 0, img = 0, y0 = 0, x0 = 0;
+  if (p.conv) {
+    int t = blockIdx.x;
+    img = t / (p.tiles_x * p.tiles_y);
+    t -= img * p.tiles_x * p.tiles_y;
+    y0 = (t / p.tiles_x) * 8;
+    x0 = (t % p.tiles_x) * 16;
+  } else {
+    m0 = blockIdx.x * TM;
+  }
+  int nk = 0;
+  if (p.conv) nk = 9 * p.kchunks[0];
+  else
+    for (int s = 0; s < p.nsrc; ++s) nk += p.kchunks[s];
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full(s), 1);
+      mbar_init(split(s), 4);
+      mbar_init(empty(s), 1);
+    }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM: 128 columns for the 128x128 fp32 accumulator
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(128u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ---------------- TMA producer ----------------
+    if (lane == 0) {
+      for (int it = 0; it < nk; ++it) {
+        const int s = it % STAGES;
+        if (it >= STAGES) mbar_wait(empty(s), ((it / STAGES) - 1) & 1);
+        const uint32_t st = base + s * STAGE_BYTES;
+        mbar_expect_tx(full(s), 3 * A_BYTES);
+        if (p.conv) {
+          const int tap = it / p.kchunks[0], kc = it - tap * p.kchunks[0];
+          tma_load_4d(st, &mapA0, full(s), kc * TK, x0 + tap % 3 - 1, y0 + tap / 3 - 1, img);
+        } else {
+          int src = 0, kc = it;
+          while (kc >= p.kchunks[src]) {
+            kc -= p.kchunks[src];
+            ++src;
+          }
+          const CUtensorMap* mp = src == 0 ? &mapA0 : (src == 1 ? &mapA1 : &mapA2);
+          tma_load_2d(st, mp, full(s), kc * TK, m0);
+        }
+        tma_load_2d(st + 2 * A_BYTES, &mapWhi, full(s), it * TK, n0);
+        tma_load_2d(st + 3 * A_BYTES, &mapWlo, full(s), it * TK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
+    for (int it = 0; it < nk; ++it) {
+      const int s = it % STAGES;
+      mbar_wait(split(s), (it / STAGES) & 1);     // implies the TMA bytes landed and A_hi/A_lo are written
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t st = base + s * STAGE_BYTES;
+#pragma unroll
+        for (int k = 0; k < TK / 8; ++k) {
+          const uint64_t a_hi = umma_desc(st + k * 32), a_lo = umma_desc(st + A_BYTES + k * 32);
+          const uint64_t w_hi = umma_desc(st + 2 * A_BYTES + k * 32), w_lo = umma_desc(st + 3 * A_BYTES + k * 32);
+          umma_tf32(tmem_acc, a_lo, w_hi, (it | k) != 0);   // small terms first
+          umma_tf32(tmem_acc, a_hi, w_lo, 1);
+          umma_tf32(tmem_acc, a_hi, w_hi, 1);
+        }
+        umma_commit(empty(s));                      // stage reusable once these MMAs retire
+        if (it == nk - 1) umma_commit(tmem_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ---------------- splitter, then epilogue (warps 2..5, 128 threads) ----------------
+    const int et = threadIdx.x - 64;                // 0..127
+    for (int it = 0; it < nk; ++it) {
+      const int s = it % STAGES;
+      mbar_wait(full(s), (it / STAGES) & 1);
+      float4* hi = reinterpret_cast<float4*>(base_ptr + s * STAGE_BYTES);
+      float4* lo = reinterpret_cast<float4*>(base_ptr + s * STAGE_BYTES + A_BYTES);
+#pragma unroll
+      for (int j = 0; j < A_BYTES / 16 / 128; ++j) {
+        float4 a = hi[et + j * 128], h, l;
+        h.x = __uint_as_float(__float_as_uint(a.x) & 0xFFFFE000u);
+        h.y = __uint_as_float(__float_as_uint(a.y) & 0xFFFFE000u);
+        h.z = __uint_as_float(__float_as_uint(a.z) & 0xFFFFE000u);
+        h.w = __uint_as_float(__float_as_uint(a.w) & 0xFFFFE000u);
+        l.x = a.x - h.x; l.y = a.y - h.y; l.z = a.z - h.z; l.w = a.w - h.w;
+        hi[et + j * 128] = h;
+        lo[et + j * 128] = l;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
+      __syncwarp();
+      if (lane == 0) mbar_arrive(split(s));
+    }
+    // epilogue
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int q = warp & 3;                          // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;                   // tile row held by this thread
+    float* stage_f = reinterpret_cast<float*>(base_ptr);   // reuse the (now idle) pipeline buffers: [128][132] floats
+    constexpr int SLD = TN + 4;
+#pragma unroll 1
+    for (int c0 = 0; c0 < TN; c0 += 32) {
+      float v[32];
+      tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(&stage_f[row * SLD + c0 + j]) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+    tc_fence_before();
+    asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
+    // coalesced row stores: warp w writes rows w, w+4, ...; lane = 4 consecutive columns
+    const int ew = warp - 2;
+    for (int r = ew; r < TM; r += 4) {
+      long long grow;
+      bool ok;
+      if (p.conv) {
+        const int yy = y0 + r / 16, xx = x0 + r % 16;
+        ok = yy < p.H && xx < p.W;
+        grow = ((long long)img * p.H + yy) * p.W + xx;
+      } else {
+        grow = m0 + r;
+        ok = grow < p.M;
+      }
+      const int col = n0 + lane * 4;
+      if (!ok || col >= p.N) continue;
+      float4 v = *reinterpret_cast<const float4*>(&stage_f[r * SLD + lane * 4]);
+      float o[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (col + j < p.N) {
+          float t = o[j];
+          if (p.bias) t += __ldg(p.bias + col + j);
+          if (p.res) t += __ldg(p.res + (size_t)(grow % p.res_mod) * p.ldres + col + j);
+          o[j] = di_act(t, p.act);
+        }
+      }
+      float* dst = p.C + (size_t)grow * p.ldc + col;
+      if (col + 3 < p.N) *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+      else
+        for (int j = 0; j < 4 && col + j < p.N; ++j) dst[j] = o[j];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(128u) : "memory");
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// 2-D fp32 map over a row-major [rows, cols] matrix with row stride ld (elements); box = 32 cols x 128 rows
+bool make_map_2d(CUtensorMap* m, const float* ptr, long long rows, long long cols, long long ld) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {TK, TM};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// 4-D fp32 map over an NHWC tensor; box = 32 channels x 16 x-pixels x 8 y-pixels x 1 image
+bool make_map_nhwc(CUtensorMap* m, const float* ptr, int N, int H, int W, int C) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+  cuuint32_t box[4] = {TK, 16, 8, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+bool g_attr_set = false;
+
+int launch_tc(const CUtensorMap maps[5], const TcParams& p, dim3 grid, cudaStream_t stream, const char* name) {
+  if (!g_attr_set) {
+    if (cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
+      di_set_error("%s: cannot reserve %d bytes of shared memory", name, SMEM_BYTES);
+      return DI_ERR_LAUNCH;
+    }
+    g_attr_set = true;
+  }
+  gemm_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
+  DI_CHECK_LAUNCH(name);
+  return DI_OK;
+}
+
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+extern "C" {
+
+// Tensor-core (3xTF32, tcgen05 + TMA) version of di_linear_f32.  W_hi / W_lo: the [N, K0+K1+K2] weight split on
+// the host (hi = round-to-tf32, lo = W - hi).  Constraints: every K_s % 32 == 0, lda % 4 == 0, 16-byte aligned
+// pointers, ldc % 4 == 0.  Returns DI_ERR_UNSUPPORTED (-3) when a constraint is not met so the caller can use
+// di_linear_f32.
+int di_linear_tc_f32(const float* A0, int lda0, int K0, const float* A1, int lda1, int K1, const float* A2, int lda2,
+                     int K2, const float* W_hi, const float* W_lo, const float* bias, const float* res, int ldres,
+                     int res_mod, float* C, int ldc, int M, int N, int act, cudaStream_t stream) {
+  DI_CHECK_ARG(A0 && W_hi && W_lo && C && M > 0 && N > 0 && K0 > 0, "di_linear_tc_f32: null pointer or empty shape");
+  const float* As[3] = {A0, A1, A2};
+  const int lds[3] = {lda0, lda1, lda2}, Ks[3] = {K0, K1, K2};
+  int nsrc = 1 + (K1 > 0) + (K2 > 0);
+  int K = K0 + K1 + K2;
+  bool ok = al16(W_hi) && al16(W_lo) && al16(C) && ldc % 4 == 0 && K % 4 == 0 && (K2 == 0 || K1 > 0);
+  for (int s = 0; s < nsrc; ++s) ok = ok && As[s] && Ks[s] % TK == 0 && lds[s] % 4 == 0 && al16(As[s]);
+  if (!ok) {
+    di_set_error("di_linear_tc_f32: shape/alignment not supported by the tensor-core path");
+    return DI_ERR_UNSUPPORTED;
+  }
+  CUtensorMap maps[5];
+  for (int s = 0; s < 3; ++s) {
+    int u = s < nsrc ? s : 0;
+    if (!make_map_2d(&maps[s], As[u], M, Ks[u], lds[u])) {
+      di_set_error("di_linear_tc_f32: cuTensorMapEncodeTiled failed for A%d", s);
+      return DI_ERR_LAUNCH;
+    }
+  }
+  if (!make_map_2d(&maps[3], W_hi, N, K, K) || !make_map_2d(&maps[4], W_lo, N, K, K)) {
+    di_set_error("di_linear_tc_f32: cuTensorMapEncodeTiled failed for W");
+    return DI_ERR_LAUNCH;
+  }
+  TcParams p{};
+  p.M = M; p.N = N; p.nsrc = nsrc;
+  for (int s = 0; s < 3; ++s) p.kchunks[s] = Ks[s] / TK;
+  p.conv = 0; p.C = C; p.ldc = ldc; p.bias = bias; p.res = res; p.ldres = ldres;
+  p.res_mod = res_mod > 0 ? res_mod : M; p.act = act;
+  dim3 grid(di_cdiv(M, TM), di_cdiv(N, TN));
+  return launch_tc(maps, p, grid, stream, "di_linear_tc_f32");
+}
+
+// Tensor-core 3x3 convolution (stride 1, zero pad 1) over a pixel-major map: x [N,H,W,Cin] -> y [N,H,W,Cout],
+// w_hi / w_lo [Cout][(ky*3+kx)*Cin + ci].  Cin % 32 == 0, Cout % 4 == 0.
+int di_conv3x3_tc_f32(const float* x, const float* w_hi, const float* w_lo, const float* bias, float* y, int N, int Cin,
+                      int H, int W, int Cout, int act, cudaStream_t stream) {
+  DI_CHECK_ARG(x && w_hi && w_lo && y && N > 0 && H > 0 && W > 0, "di_conv3x3_tc_f32: bad argument");
+  if (!(Cin % TK == 0 && Cout % 4 == 0 && al16(x) && al16(y) && al16(w_hi) && al16(w_lo))) {
+    di_set_error("di_conv3x3_tc_f32: shape/alignment not supported by the tensor-core path");
+    return DI_ERR_UNSUPPORTED;
+  }
+  CUtensorMap maps[5];
+  if (!make_map_nhwc(&maps[0], x, N, H, W, Cin)) {
+    di_set_error("di_conv3x3_tc_f32: cuTensorMapEncodeTiled failed for x");
+    return DI_ERR_LAUNCH;
+  }
+  maps[1] = maps[0];
+  maps[2] = maps[0];
+  long long K = 9ll * Cin;
+  if (!make_map_2d(&maps[3], w_hi, Cout, K, K) || !make_map_2d(&maps[4], w_lo, Cout, K, K)) {
+    di_set_error("di_conv3x3_tc_f32: cuTensorMapEncodeTiled failed for w");
+    return DI_ERR_LAUNCH;
+  }
+  TcParams p{};
+  p.M = N * H * W; p.N = Cout; p.nsrc = 1; p.kchunks[0] = Cin / TK; p.conv = 1; p.H = H; p.W = W;
+  p.tiles_x = di_cdiv(W, 16); p.tiles_y = di_cdiv(H, 8);
+  p.C = y; p.ldc = Cout; p.bias = bias; p.res = nullptr; p.ldres = 0; p.res_mod = 1; p.act = act;
+  dim3 grid(N * p.tiles_x * p.tiles_y, di_cdiv(Cout, TN));
+  return launch_tc(maps, p, grid, stream, "di_conv3x3_tc_f32");
+}
+
+}  // extern "C"

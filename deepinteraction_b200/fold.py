@@ -69,3 +69,24 @@ def i2p_fold(mha):
 
 def dev(t, device):
     return t.to(torch.float32).contiguous().to(device)
+
+
+def split_tf32(w):
+    """fp32 tensor -> (hi, lo): hi = w rounded (nearest-even) to TF32's 10 mantissa bits, lo = w - hi (exact)."""
+    w = w.to(torch.float32).contiguous()
+    bits = w.view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    rounded = (bits + 0x0FFF + ((bits >> 13) & 1)) & 0xFFFFE000
+    hi = (rounded & 0xFFFFFFFF).to(torch.int64)
+    hi = torch.where(hi >= 2 ** 31, hi - 2 ** 32, hi).to(torch.int32).view(torch.float32)
+    return hi.contiguous(), (w - hi).contiguous()
+
+
+class Weight:
+    """A dense-layer weight [N, K] kept in both forms the kernels consume: plain fp32 (FFMA path) and the
+    TF32 hi/lo split (tcgen05 path)."""
+
+    def __init__(self, w, device):
+        self.w = dev(w, device)
+        hi, lo = split_tf32(w.to(torch.float32))
+        self.hi, self.lo = hi.to(device), lo.to(device)
+        self.shape = self.w.shape

@@ -221,7 +221,7 @@ class DeepInteractionDecoder(nn.Module):
             seq = getattr(self, name)
             w0, b0 = fold.conv_bn(seq[0].conv, seq[0].bn)
             w1, b1 = fold.conv_bn(seq[1])
-            pk[name] = (d(fold.pack_conv3x3(w0)), d(b0), d(fold.pack_conv3x3(w1)), d(b1))
+            pk[name] = (fold.Weight(fold.pack_conv3x3(w0), device), d(b0), d(fold.pack_conv3x3(w1)), d(b1))
         pk['wce_t'] = d(fold._d(self.class_encoding.weight)[:, :, 0].t())
         pk['bce'] = d(fold._d(self.class_encoding.bias))
         layer = self.decoder[0]
@@ -238,7 +238,7 @@ class DeepInteractionDecoder(nn.Module):
         W, b, wo, bo = self._pack_mha(layer.multihead_attn.in_proj_weight, layer.multihead_attn.in_proj_bias,
                                       layer.multihead_attn.out_proj, d)
         pk['cross_q'] = (d(torch.cat([W[:C], W[:C]], 1)), d(b[:C]))
-        w_kv, b_kv = d(W[C:]), d(b[C:])
+        w_kv, b_kv = fold.Weight(W[C:], device), d(b[C:])
         # constant key positional embedding -> its K/V contribution, with our own kernels (bev grid is fixed)
         ys, xs = torch.meshgrid(torch.arange(self.y_size, dtype=torch.float32),
                                 torch.arange(self.x_size, dtype=torch.float32), indexing='ij')
@@ -247,6 +247,7 @@ class DeepInteractionDecoder(nn.Module):
         pk['cross_kv'] = (w_kv, b_kv, ops.linear([kpe], w_kv))
         pk['cross_out'] = (wo, bo)
         lin = lambda m: (d(fold._d(m.weight)), d(fold._d(m.bias)))
+        linw = lambda m: (fold.Weight(fold._d(m.weight), device), d(fold._d(m.bias)))
         for i in (1, 2, 3):
             pk[f'norm{i}'] = lin(getattr(layer, f'norm{i}'))
         pk['ffn'] = lin(layer.linear1) + lin(layer.linear2)
@@ -258,7 +259,7 @@ class DeepInteractionDecoder(nn.Module):
             W, b, wo, bo = self._pack_mha(mha.in_proj_weight, mha.in_proj_bias, mha.out_proj, d)
             dy = g('dyconv')
             blocks.append(dict(image=blk.sfx == '', attn=(d(W), d(b), wo, bo), norm1=lin(g('norm1')),
-                               norm2=lin(g('norm2')), norm3=lin(g('norm3')), dyn=lin(dy.dynamic_layer),
+                               norm2=lin(g('norm2')), norm3=lin(g('norm3')), dyn=linw(dy.dynamic_layer),
                                dn1=lin(dy.norm1), dn2=lin(dy.norm2), dout=lin(dy.out_layer), dn3=lin(dy.norm3),
                                ffn=lin(g('linear1')) + lin(g('linear2')), pred=self._pack_pred(ph, d)))
         pk['blocks'] = blocks

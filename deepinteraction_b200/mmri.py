@@ -90,11 +90,12 @@ def _pack_lcab(blk, device):
     wk2, bk2 = fold.pointwise(blk.key_project[1])
     wv, bv = fold.pointwise(blk.value_project)
     d = lambda t: fold.dev(t, device)
+    Wt = lambda t: fold.Weight(t, device)
     C = wq2.shape[0]
     return dict(C=C, ks=blk.kernel_size,
-                w_self=d(torch.cat([wq1, wk1, wv], 0)), b_self=d(torch.cat([bq1, bk1, bv], 0)),
-                w_q1=d(wq1), b_q1=d(bq1), w_kv1=d(torch.cat([wk1, wv], 0)), b_kv1=d(torch.cat([bk1, bv], 0)),
-                w_q2=d(wq2), b_q2=d(bq2), w_k2=d(wk2), b_k2=d(bk2))
+                w_self=Wt(torch.cat([wq1, wk1, wv], 0)), b_self=d(torch.cat([bq1, bk1, bv], 0)),
+                w_q1=Wt(wq1), b_q1=d(bq1), w_kv1=Wt(torch.cat([wk1, wv], 0)), b_kv1=d(torch.cat([bk1, bv], 0)),
+                w_q2=Wt(wq2), b_q2=d(bq2), w_k2=Wt(wk2), b_k2=d(bk2))
 
 
 def lcab_forward(pk, target, source, N, H, W):
@@ -167,18 +168,19 @@ class DeepInteractionEncoder(nn.Module):
         if device.type != 'cuda':
             raise RuntimeError('DeepInteractionEncoder (libdi_b200) runs on CUDA only; move the module to a GPU')
         d = lambda t: fold.dev(t, device)
+        Wt = lambda t: fold.Weight(t, device)
         pk = dict()
         for name in ('shared_conv_pts', 'shared_conv_img'):
             W, b = fold.conv_bn(getattr(self, name))
-            pk[name] = (d(fold.pack_conv3x3(W)), d(b))
+            pk[name] = (Wt(fold.pack_conv3x3(W)), d(b))
         layers = []
         for blk in self.fusion_blocks:
             M1, c1, M2, c2 = fold.i2p_fold(blk.I2P_block.learnedAlign)
             wp, bp = fold.fuse_pair(blk.P_out_proj, blk.P_integration)
             wi, bi = fold.fuse_pair(blk.I_out_proj, blk.I_integration)
-            layers.append(dict(i2p=(d(M1), d(c1), d(M2), d(c2)), p_iml=_pack_lcab(blk.P_IML, device),
+            layers.append(dict(i2p=(Wt(M1), d(c1), Wt(M2), d(c2)), p_iml=_pack_lcab(blk.P_IML, device),
                                p2i=_pack_lcab(blk.P2I_block.Local, device), i_iml=_pack_lcab(blk.I_IML, device),
-                               p_fuse=(d(wp), d(bp)), i_fuse=(d(wi), d(bi))))
+                               p_fuse=(Wt(wp), d(bp)), i_fuse=(Wt(wi), d(bi))))
         pk['layers'] = layers
         self._pack, self._pack_key = pk, key
         return pk

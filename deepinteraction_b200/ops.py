@@ -5,14 +5,17 @@ kernel of libdi_b200.so.  All wrappers require CUDA fp32 contiguous tensors and 
 anything else -- there is no fallback path.
 """
 import ctypes
+import os
 
 import torch
 
 from . import _lib
+from .fold import Weight
 
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 
 LAUNCHES = [0]   # number of libdi_b200 kernel-launching calls (bench.py reports it)
+USE_TC = [os.environ.get('DI_B200_TC', '1') != '0']   # tcgen05 3xTF32 path for Weight objects (else FFMA)
 PROFILE = [None]  # bench.py sets PROFILE[0] = [] to record (name, start_event, end_event, bytes, flops) per call
 
 
@@ -58,6 +61,11 @@ def linear(srcs, W, bias=None, act=ACT_NONE, out=None, res=None, res_mod=0, spli
     srcs = list(srcs)
     M = srcs[0].shape[0]
     N, K = W.shape
+    if isinstance(W, Weight):
+        if (USE_TC[0] and splits == 1 and M >= 128 and N % 4 == 0
+                and all(s_.shape[1] % 32 == 0 and s_.stride(0) % 4 == 0 and s_.data_ptr() % 16 == 0 for s_ in srcs)):
+            return _linear_tc(srcs, W, bias, act, out, res, res_mod, M, N, K)
+        W = W.w
     assert sum(s.shape[1] for s in srcs) == K, (K, [s.shape for s in srcs])
     a = []
     for s in srcs:
@@ -82,6 +90,23 @@ def linear(srcs, W, bias=None, act=ACT_NONE, out=None, res=None, res_mod=0, spli
     return out
 
 
+def _linear_tc(srcs, W, bias, act, out, res, res_mod, M, N, K):
+    a = []
+    for s in srcs:
+        _f32(s)
+        p, ld = _rows(s)
+        a += [p, ld, s.shape[1]]
+    while len(a) < 9:
+        a += [None, 0, 0]
+    if out is None:
+        out = torch.empty(M, N, device=W.w.device, dtype=torch.float32)
+    po, ldo = _rows(out)
+    pr, ldr = (None, 0) if res is None else _rows(res)
+    _call('di_linear_tc_f32', *a, _ptr(W.hi), _ptr(W.lo), _ptr(bias), pr, ldr, res_mod, po, ldo, M, N, act, _stream(),
+          nbytes=4 * (M * K + N * K + M * N + (0 if res is None else res.numel())), flops=2 * M * N * K)
+    return out
+
+
 def conv3x3(x, w_packed, bias, cout, x_nhwc, y_nchw=False, act=ACT_NONE):
     """x: NCHW (N,Cin,H,W) or NHWC (N,H,W,Cin) contiguous; returns NHWC (N,H,W,cout) or NCHW."""
     _f32(x)
@@ -90,6 +115,15 @@ def conv3x3(x, w_packed, bias, cout, x_nhwc, y_nchw=False, act=ACT_NONE):
         N, H, W, Cin = x.shape
     else:
         N, Cin, H, W = x.shape
+    if isinstance(w_packed, Weight):
+        if USE_TC[0] and not y_nchw and cout % 4 == 0 and Cin % 32 == 0:
+            xin = x if x_nhwc else nchw_to_nhwc(x)       # the TMA box walks a pixel-major map
+            y = torch.empty((N, H, W, cout), device=x.device, dtype=torch.float32)
+            _call('di_conv3x3_tc_f32', _ptr(xin), _ptr(w_packed.hi), _ptr(w_packed.lo), _ptr(bias), _ptr(y), N, Cin, H, W,
+                  cout, act, _stream(), nbytes=4 * (x.numel() + w_packed.w.numel() + y.numel()),
+                  flops=2 * N * H * W * cout * 9 * Cin)
+            return y
+        w_packed = w_packed.w
     y = torch.empty((N, cout, H, W) if y_nchw else (N, H, W, cout), device=x.device, dtype=torch.float32)
     _call('di_conv3x3_f32', _ptr(x), int(x_nhwc), _ptr(w_packed), _ptr(bias), _ptr(y), int(y_nchw), N, Cin, H, W, cout,
           act, _stream(), nbytes=4 * (x.numel() + w_packed.numel() + y.numel()), flops=2 * N * H * W * cout * 9 * Cin)

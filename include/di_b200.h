@@ -56,6 +56,15 @@ int di_linear_f32(const float* A0, int lda0, int K0, const float* A1, int lda1, 
 int di_conv3x3_f32(const float* x, int x_nhwc, const float* w, const float* bias, float* y, int y_nchw, int N,
                    int Cin, int H, int W, int Cout, int act, cudaStream_t stream);
 
+/* Tensor-core versions (gemm_tc.cu): error-compensated 3xTF32 on tcgen05 (accumulator in TMEM), operands
+ * staged by TMA; fp32-faithful results.  W_hi/W_lo = host-side split of the same [N,K] weight.  Return -3
+ * (unsupported) when the shape/alignment constraints are not met; the caller then uses the FFMA entry point. */
+int di_linear_tc_f32(const float* A0, int lda0, int K0, const float* A1, int lda1, int K1, const float* A2, int lda2,
+                     int K2, const float* W_hi, const float* W_lo, const float* bias, const float* res, int ldres,
+                     int res_mod, float* C, int ldc, int M, int N, int act, cudaStream_t stream);
+int di_conv3x3_tc_f32(const float* x, const float* w_hi, const float* w_lo, const float* bias, float* y, int N, int Cin,
+                      int H, int W, int Cout, int act, cudaStream_t stream);
+
 /* ---- local-window attention (lcab.cu) ---------------------------------------------------------- */
 
 /* out = weighting(v, softmax(similar(q, k) / sqrt(C))) over a ksize x ksize window, fused
