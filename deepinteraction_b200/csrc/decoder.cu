@@ -49,14 +49,23 @@ __global__ void heatmap_nms_kernel(const float* __restrict__ a, const float* __r
 // ------------------------------------------------------------------------------------------------
 constexpr int TOPK_MAX = 1024;
 
+// Two levels: level 1 = one CTA per (slice, batch row) keeps the slice's top-k as (value, global index)
+// candidates; level 2 = one CTA per batch row selects the final top-k among the G*k candidates.
 __global__ void __launch_bounds__(1024)
-topk_kernel(const float* __restrict__ scores, int* __restrict__ idx_out, int n, int k) {
+topk_kernel(const float* __restrict__ scores_all, const int* __restrict__ src_idx_all, int n_row, int n_slice, int k,
+            float* __restrict__ val_out, int* __restrict__ idx_out) {
   __shared__ unsigned hist[4096];
   __shared__ unsigned s_prefix, s_need, s_cnt_gt, s_cnt_eq;
   __shared__ unsigned long long cand[TOPK_MAX];  // (value bits << 32) | (0xffffffff - index): sort descending
   __shared__ unsigned eq_idx[TOPK_MAX];
-  const float* s = scores + (size_t)blockIdx.x * n;
+  // blockIdx.y = batch row, blockIdx.x = slice; this CTA looks at elements [off, off + n) of its row
+  const int off = blockIdx.x * n_slice;
+  const int n = min(n_slice, n_row - off);
+  const float* s = scores_all + (size_t)blockIdx.y * n_row + off;
+  const int* sidx = src_idx_all ? src_idx_all + (size_t)blockIdx.y * n_row + off : nullptr;
   const int t = threadIdx.x;
+  const int k_host = k;
+  if (n < k) k = max(n, 0);
   unsigned prefix = 0, need = (unsigned)k;
   // pass p examines bits [hi, lo)
   const int shifts[3] = {20, 8, 0};
@@ -100,7 +109,7 @@ topk_kernel(const float* __restrict__ scores, int* __restrict__ idx_out, int n, 
     if (u > prefix) {
       unsigned pos = atomicAdd(&s_cnt_gt, 1u);
       cand[pos] = ((unsigned long long)u << 32) | (unsigned long long)(0xffffffffu - (unsigned)i);
-    } else if (u == prefix) {
+    } else if (u == prefix && k > 0) {
       unsigned pos = atomicAdd(&s_cnt_eq, 1u);
       if (pos < TOPK_MAX) eq_idx[pos] = (unsigned)i;
     }
@@ -136,8 +145,19 @@ topk_kernel(const float* __restrict__ scores, int* __restrict__ idx_out, int n, 
       __syncthreads();
     }
   }
-  for (int i = t; i < k; i += blockDim.x)
-    idx_out[(size_t)blockIdx.x * k + i] = (int)(0xffffffffu - (unsigned)(cand[i] & 0xffffffffull));
+  // output slot of this CTA: [row][slice][k_out] where k_out = the k passed by the host (before clamping)
+  const size_t obase = ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (size_t)k_host;
+  for (int i = t; i < k_host; i += blockDim.x) {
+    int gi = -1;
+    float gv = 0.f;
+    if (i < k) {
+      int local = (int)(0xffffffffu - (unsigned)(cand[i] & 0xffffffffull));
+      gi = sidx ? sidx[local] : off + local;
+      gv = __uint_as_float((unsigned)(cand[i] >> 32));
+    }
+    idx_out[obase + i] = gi;
+    if (val_out) val_out[obase + i] = gv;
+  }
 }
 
 // query_feat[b,q,:] = feat[b, pix, :] + Wce[cls, :] + bce ; query_pos = (x+.5, y+.5) ; score gather
@@ -715,11 +735,25 @@ int di_heatmap_nms_f32(const float* a, const float* b, float* out, int B, int K,
   return DI_OK;
 }
 
-// scores [B,n] >= 0 -> idx [B,k] (descending score, ties by ascending index); k <= 1024
-int di_topk_f32(const float* scores, int* idx, int B, int n, int k, cudaStream_t stream) {
+// scores [B,n] >= 0 -> idx [B,k] (descending score, ties by ascending index); k <= 1024.
+// work: B * slices * k * 2 ints/floats of scratch (pass nullptr/0 slices for the single-level path).
+int di_topk_f32(const float* scores, int* idx, int B, int n, int k, void* work, int slices, cudaStream_t stream) {
   DI_CHECK_ARG(scores && idx && B > 0 && n >= k && k > 0 && k <= TOPK_MAX, "di_topk_f32: bad argument (k=%d n=%d)", k, n);
-  topk_kernel<<<B, 1024, 0, stream>>>(scores, idx, n, k);
-  DI_CHECK_LAUNCH("di_topk_f32");
+  if (!work || slices <= 1 || slices * k > (1 << 20)) {
+    topk_kernel<<<dim3(1, B), 1024, 0, stream>>>(scores, nullptr, n, n, k, nullptr, idx);
+    DI_CHECK_LAUNCH("di_topk_f32");
+    return DI_OK;
+  }
+  float* cval = reinterpret_cast<float*>(work);
+  int* cidx = reinterpret_cast<int*>(cval + (size_t)B * slices * k);
+  int n_slice = di_cdiv(n, slices);
+  slices = di_cdiv(n, n_slice);
+  topk_kernel<<<dim3(slices, B), 1024, 0, stream>>>(scores, nullptr, n, n_slice, k, cval, cidx);
+  DI_CHECK_LAUNCH("di_topk_f32(level 1)");
+  // level 2: candidates of empty tail slots carry value 0 / index -1 and can only win when fewer than k
+  // positive scores exist in the whole row
+  topk_kernel<<<dim3(1, B), 1024, 0, stream>>>(cval, cidx, slices * k, slices * k, k, nullptr, idx);
+  DI_CHECK_LAUNCH("di_topk_f32(level 2)");
   return DI_OK;
 }
 

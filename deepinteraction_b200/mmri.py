@@ -116,23 +116,41 @@ def lcab_forward(pk, target, source, N, H, W):
 class Geometry:
     """Per-frame geometry shared by both encoder layers (and by the decoder's projections)."""
 
-    def __init__(self, img_metas, pts_metas, feat_hw, bev_hw, device, want_debug=False):
+    def __init__(self, img_metas, pts_metas, feat_hw, bev_hw, device, want_debug=False, side_stream=None):
+        """The depth maps / completion / lifting chain is latency-bound (one CTA per camera) and independent of
+        the feature maps, so it is issued on `side_stream` and overlaps the shared convs and the BEV branch;
+        consumers call wait() before the first BEV sampling."""
         self.in_hw = geom.input_hw(img_metas)
         self.proj, self.i2l = geom.camera_rows(img_metas, device)             # (B,V,12), (B*V,12)
         B, V = self.proj.shape[:2]
         h, w = feat_hw
-        keys = torch.zeros(B * V, h, w, device=device, dtype=torch.int64)
+        main = torch.cuda.current_stream()
+        side = side_stream if side_stream is not None else main
+        pts_list = []
         for b in range(B):
             pts = pts_metas['pts'][b]
-            if pts.device != keys.device or pts.dtype != torch.float32:
+            if pts.device != self.proj.device or pts.dtype != torch.float32:
                 pts = pts.to(device=device, dtype=torch.float32)
-            ops.depth_scatter(pts, self.proj[b], keys[b * V:(b + 1) * V], self.in_hw)
-        if want_debug:
-            self.dense, self.sparse = ops.depth_complete(keys, want_sparse=True)
-        else:
-            self.dense = ops.depth_complete(keys)
-        self.grid = ops.lift_grid(self.dense, self.i2l, self.in_hw, bev_hw, PC_RANGE)
+            pts_list.append(pts)
+        if side is not main:
+            side.wait_stream(main)
+        with torch.cuda.stream(side):
+            keys = torch.zeros(B * V, h, w, device=device, dtype=torch.int64)
+            for b in range(B):
+                ops.depth_scatter(pts_list[b], self.proj[b], keys[b * V:(b + 1) * V], self.in_hw)
+            if want_debug:
+                self.dense, self.sparse = ops.depth_complete(keys, want_sparse=True)
+            else:
+                self.dense = ops.depth_complete(keys)
+            self.grid = ops.lift_grid(self.dense, self.i2l, self.in_hw, bev_hw, PC_RANGE)
+            self.ready = torch.cuda.Event()
+            self.ready.record(side)
+        self._side, self._main = side, main
         self.V = V
+
+    def wait(self):
+        if self._side is not self._main:
+            torch.cuda.current_stream().wait_event(self.ready)
 
 
 class DeepInteractionEncoder(nn.Module):
@@ -155,6 +173,7 @@ class DeepInteractionEncoder(nn.Module):
         self._pack = None
         self._pack_key = None
         self.last_geometry = None
+        self._side_stream = None
 
     # -- packing -----------------------------------------------------------------------------------
     def _state_key(self):
@@ -219,7 +238,10 @@ class DeepInteractionEncoder(nn.Module):
         B, _, Y, X = pts_feats.shape
         V = BV // B
         pm = self._canon_pts_metas(pts_metas, dev_)
-        g = Geometry(img_metas, pm, (h, w), (Y, X), dev_, want_debug=debug is not None)
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(device=dev_)
+        g = Geometry(img_metas, pm, (h, w), (Y, X), dev_, want_debug=debug is not None,
+                     side_stream=self._side_stream)
         self.last_geometry = g
         img = ops.conv3x3(img_feats.contiguous(), *pk['shared_conv_img'], cout=C, x_nhwc=False)
         pts = ops.conv3x3(pts_feats.contiguous(), *pk['shared_conv_pts'], cout=C, x_nhwc=False)
@@ -229,6 +251,8 @@ class DeepInteractionEncoder(nn.Module):
             i2p = self.i2p(lp, pts, img, pm, g)
             p2p = lcab_forward(lp['p_iml'], pts_r, pts_r, B, Y, X)
             new_pts = ops.linear([i2p.view(-1, C), p2p, pts_r], *lp['p_fuse']).view(B, Y, X, C)
+            if li == 0:
+                g.wait()
             warped = ops.bev_sample(pts, g.grid, V)
             p2i = lcab_forward(lp['p2i'], img_r, warped.view(-1, C), BV, h, w)
             i2i = lcab_forward(lp['i_iml'], img_r, img_r, BV, h, w)

@@ -215,7 +215,9 @@ def topk(scores, k):
     B, n = scores.shape
     assert scores.is_contiguous()
     idx = torch.empty(B, k, device=scores.device, dtype=torch.int32)
-    _call('di_topk_f32', _ptr(scores), _ptr(idx), B, n, k, _stream())
+    slices = 64 if n >= 64 * 1024 else 0
+    work = torch.empty(B * slices * k * 2, device=scores.device, dtype=torch.float32) if slices else None
+    _call('di_topk_f32', _ptr(scores), _ptr(idx), B, n, k, _ptr(work), slices, _stream())
     return idx
 
 

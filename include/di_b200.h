@@ -119,7 +119,7 @@ int di_bev_sample_f32(const float* bev, const float* grid_xy, float* out, int B,
 int di_heatmap_nms_f32(const float* a, const float* b, float* out, int B, int K, int H, int W, int ks,
                        int no_nms_class_mask, cudaStream_t stream);
 /* :242 (argsort descending, first k) */
-int di_topk_f32(const float* scores, int* idx, int B, int n, int k, cudaStream_t stream);
+int di_topk_f32(const float* scores, int* idx, int B, int n, int k, void* work, int slices, cudaStream_t stream);
 /* :243-253, :299 */
 int di_query_init_f32(const float* feat, const int* top, const float* heat, const float* wce_t, const float* bce,
                       float* qfeat, float* qpos, int* labels, float* qscore, int B, int HW, int W, int C, int K, int P,

@@ -66,7 +66,7 @@ def test_ctypes_signatures_match_header():
 def test_bad_arguments_are_reported_not_thrown():
     from deepinteraction_b200 import _lib
     L = _lib.lib()
-    rc = L.di_topk_f32(None, None, 1, 10, 5, None)
+    rc = L.di_topk_f32(None, None, 1, 10, 5, None, 0, None)
     assert rc == -1 and 'di_topk_f32' in _lib.last_error()
     with pytest.raises(RuntimeError):
         _lib.check(rc, 'topk')

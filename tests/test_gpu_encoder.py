@@ -189,6 +189,7 @@ def test_bevwarp_stages_match_oracle(aug):
     pm = {k: v for k, v in fr['pts_metas'].items()}
     pm['pts'] = [p.to(dev()) for p in pm['pts']]
     g = mmri.Geometry(fr['img_metas'], pm, (28, 50), (36, 36), dev(), want_debug=True)
+    g.wait()
     sparse = g.sparse.cpu()
     assert torch.equal(sparse > 0, aux[0]['sparse'] > 0), 'sparse depth maps must have identical support'
     if aug:    # the augmentation is folded into the projection matrix: depths agree to fp32 rounding only
