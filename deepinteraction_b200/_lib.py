@@ -37,7 +37,7 @@ SIGNATURES = {
     'di_lift_grid': [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _fp, _p],
     'di_bev_sample_f32': [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     # decoder.cu
-    'di_heatmap_nms_f32': [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
+    'di_heatmap_nms_f32': [_p, _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     'di_topk_f32': [_p, _p, _i, _i, _i, _p, _i, _p],
     'di_query_init_f32': [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     'di_mha_small_f32': [_p, _i, _p, _i, _p, _i, _p, _i, _p, _p, _i, _i, _i, _i, _p],

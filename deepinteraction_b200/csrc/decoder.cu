@@ -15,14 +15,18 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
-__global__ void heatmap_nms_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
-                                   int K, int H, int W, int ks, unsigned no_nms_mask, int total) {
+// a, b: raw logits, pixel-major [B, HW, ld] (first K columns valid).  out [B,K,HW] = NMS-masked mean of
+// sigmoids; dense_b [B,K,H,W] = head-b logits in the NCHW layout the reference returns as `dense_heatmap`.
+__global__ void heatmap_nms_kernel(const float* __restrict__ a, const float* __restrict__ b, int ld,
+                                   float* __restrict__ out, float* __restrict__ dense_b, int K, int H, int W, int ks,
+                                   unsigned no_nms_mask, int total) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  int x = i % W, y = (i / W) % H, c = (i / (W * H)) % K;
-  const float* pa = a + (i - y * W - x);
-  const float* pb = b + (i - y * W - x);
-  float hc = (sigmoidf_(pa[y * W + x]) + sigmoidf_(pb[y * W + x])) * 0.5f;
+  int x = i % W, y = (i / W) % H, c = (i / (W * H)) % K, n = i / (W * H * K);
+  const float* pa = a + (size_t)n * H * W * ld + c;
+  const float* pb = b + (size_t)n * H * W * ld + c;
+  const float lb = pb[(size_t)(y * W + x) * ld];
+  float hc = (sigmoidf_(pa[(size_t)(y * W + x) * ld]) + sigmoidf_(lb)) * 0.5f;
   float res;
   if ((no_nms_mask >> c) & 1u) {
     res = hc;
@@ -34,13 +38,14 @@ __global__ void heatmap_nms_kernel(const float* __restrict__ a, const float* __r
       float m = hc;
       for (int dy = -r; dy <= r; ++dy)
         for (int dx = -r; dx <= r; ++dx) {
-          int o = (y + dy) * W + x + dx;
+          size_t o = (size_t)((y + dy) * W + x + dx) * ld;
           m = fmaxf(m, (sigmoidf_(pa[o]) + sigmoidf_(pb[o])) * 0.5f);
         }
       res = hc == m ? hc : 0.f;
     }
   }
   out[i] = res;
+  if (dense_b) dense_b[i] = lb;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -725,12 +730,14 @@ __global__ void nhwc_to_nchw_kernel(const float* __restrict__ in, float* __restr
 
 extern "C" {
 
-// a, b: raw heatmap logits NCHW [B,K,H,W]; out [B,K,H*W] = nms-masked mean of sigmoids.
-int di_heatmap_nms_f32(const float* a, const float* b, float* out, int B, int K, int H, int W, int ks,
-                       int no_nms_class_mask, cudaStream_t stream) {
-  DI_CHECK_ARG(a && b && out && B > 0 && K > 0 && K <= 32 && ks % 2 == 1, "di_heatmap_nms_f32: bad argument");
+// a, b: raw heatmap logits, pixel-major [B,H*W,ld]; out [B,K,H*W] = nms-masked mean of sigmoids;
+// dense_b (optional) [B,K,H,W] = logits of b in NCHW.
+int di_heatmap_nms_f32(const float* a, const float* b, int ld, float* out, float* dense_b, int B, int K, int H, int W,
+                       int ks, int no_nms_class_mask, cudaStream_t stream) {
+  DI_CHECK_ARG(a && b && out && B > 0 && K > 0 && K <= 32 && ld >= K && ks % 2 == 1, "di_heatmap_nms_f32: bad argument");
   int total = B * K * H * W;
-  heatmap_nms_kernel<<<di_cdiv(total, 256), 256, 0, stream>>>(a, b, out, K, H, W, ks, (unsigned)no_nms_class_mask, total);
+  heatmap_nms_kernel<<<di_cdiv(total, 256), 256, 0, stream>>>(a, b, ld, out, dense_b, K, H, W, ks,
+                                                              (unsigned)no_nms_class_mask, total);
   DI_CHECK_LAUNCH("di_heatmap_nms_f32");
   return DI_OK;
 }

@@ -10,7 +10,7 @@
 // 3x3 convs as implicit GEMM over pixel-major (NHWC) maps (models/necks/deepinteraction_encoder.py:47-62,
 // models/dense_heads/deepinteraction_decoder.py:83-101).
 //
-// One CTA = one 128 x 128 output tile, 192 threads, warp-specialised:
+// Persistent CTAs (one per SM) loop over 128 x 128 output tiles; 320 threads, warp-specialised:
 //   warp 0      TMA producer: per 32-wide K chunk, box loads of A (2-D [rows,K] map, or a 4-D NHWC map whose
 //               8x16-pixel box shifted by the filter tap gives zero padding for free) and of W_hi / W_lo
 //               into a 3-stage ring of 128B-swizzled K-major tiles (cp.async.bulk.tensor + mbarrier tx-count)
@@ -18,8 +18,9 @@
 //               (elementwise, so the swizzle is irrelevant), fence.proxy.async, arrive
 //   warp 1      MMA issuer: 4 k-steps x 3 products of tcgen05.mma.kind::tf32 (M=128,N=128,K=8) per chunk,
 //               tcgen05.commit frees the stage; accumulator = 128 TMEM columns
-//   warps 2-5   epilogue: tcgen05.ld (32 lanes x 32 columns per warp and step) -> bias/res/activation ->
-//               shared-memory transpose -> coalesced 512-byte row stores
+//   warps 6-9   epilogue: tcgen05.ld (32 lanes x 32 columns per warp and step) -> bias/res/activation -> each
+//               thread streams its row as 128-byte runs; overlaps the next tile's main loop through a
+//               double-buffered TMEM accumulator (2 x 128 columns)
 #include "common.cuh"
 #include <cuda.h>
 
@@ -29,8 +30,9 @@ constexpr int TM = 128, TN = 128, TK = 32;          // tile; TK fp32 = 128 bytes
 constexpr int STAGES = 3;
 constexpr int A_BYTES = TM * TK * 4;                // 16 KB
 constexpr int STAGE_BYTES = 4 * A_BYTES;            // A_hi | A_lo | W_hi | W_lo
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 320;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+int g_num_sms = 0;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -115,6 +117,7 @@ struct TcParams {
   int kchunks[3];           // linear: K_s / 32 per source; conv: kchunks[0] = Cin / 32
   int conv;                 // 1: 3x3 conv over an NHWC map (A map is 4-D)
   int H, W, tiles_x, tiles_y;  // conv geometry: tile = 8 rows x 16 cols of pixels
+  int m_tiles, n_tiles;     // tile grid (m_tiles = images * tiles_y * tiles_x for conv)
   float* C;
   int ldc;
   const float* bias;
@@ -122,6 +125,10 @@ struct TcParams {
   int ldres, res_mod, act;
 };
 
+// Persistent, warp-specialised: each CTA loops over output tiles (tile = m_tile * n_tiles + n_tile).  The four
+// pipelines run concurrently on different tiles/chunks:
+//   TMA (warp 0) -> split hi/lo (warps 2-5) -> tcgen05.mma (warp 1) -> epilogue TMEM->regs->global (warps 6-9)
+// with a 3-stage shared-memory ring and a double-buffered TMEM accumulator (2 x 128 columns).
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapWhi,
@@ -129,30 +136,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;        // SWIZZLE_128B needs 1024-byte alignment
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t bars = base + STAGES * STAGE_BYTES;                   // full[S], split[S], empty[S], tmem_full, tmem_slot
+  const uint32_t bars = base + STAGES * STAGE_BYTES;
   auto full = [&](int s) { return bars + 8u * s; };
   auto split = [&](int s) { return bars + 8u * (STAGES + s); };
   auto empty = [&](int s) { return bars + 8u * (2 * STAGES + s); };
-  const uint32_t tmem_full = bars + 8u * (3 * STAGES);
-  const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 1);
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + STAGES * STAGE_BYTES + 8 * (3 * STAGES + 1));
+  auto acc_full = [&](int a) { return bars + 8u * (3 * STAGES + a); };
+  auto acc_empty = [&](int a) { return bars + 8u * (3 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(base_ptr + STAGES * STAGE_BYTES + 8 * (3 * STAGES + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.y * TN;
-  int m0 = 0, img = 0, y0 = 0, x0 = 0;
-  if (p.conv) {
-    int t = blockIdx.x;
-    img = t / (p.tiles_x * p.tiles_y);
-    t -= img * p.tiles_x * p.tiles_y;
-    y0 = (t / p.tiles_x) * 8;
-    x0 = (t % p.tiles_x) * 16;
-  } else {
-    m0 = blockIdx.x * TM;
-  }
   int nk = 0;
   if (p.conv) nk = 9 * p.kchunks[0];
   else
     for (int s = 0; s < p.nsrc; ++s) nk += p.kchunks[s];
+  const int num_tiles = p.m_tiles * p.n_tiles;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -160,140 +159,184 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       mbar_init(split(s), 4);
       mbar_init(empty(s), 1);
     }
-    mbar_init(tmem_full, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(acc_full(a), 1);
+      mbar_init(acc_empty(a), 4);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {  // TMEM: 128 columns for the 128x128 fp32 accumulator
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(128u) : "memory");
+  if (warp == 1) {  // TMEM: 2 x 128 columns (double-buffered 128x128 fp32 accumulator)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(256u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_acc = *tmem_slot_ptr;
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  auto tile_coords = [&](int tile, int& m0, int& n0, int& img, int& y0, int& x0) {
+    const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+    n0 = nt * TN;
+    m0 = mt * TM;
+    img = 0; y0 = 0; x0 = 0;
+    if (p.conv) {
+      int t = mt;
+      img = t / (p.tiles_x * p.tiles_y);
+      t -= img * p.tiles_x * p.tiles_y;
+      y0 = (t / p.tiles_x) * 8;
+      x0 = (t % p.tiles_x) * 16;
+    }
+  };
 
   if (warp == 0) {
     // ---------------- TMA producer ----------------
     if (lane == 0) {
-      for (int it = 0; it < nk; ++it) {
-        const int s = it % STAGES;
-        if (it >= STAGES) mbar_wait(empty(s), ((it / STAGES) - 1) & 1);
-        const uint32_t st = base + s * STAGE_BYTES;
-        mbar_expect_tx(full(s), 3 * A_BYTES);
-        if (p.conv) {
-          const int tap = it / p.kchunks[0], kc = it - tap * p.kchunks[0];
-          tma_load_4d(st, &mapA0, full(s), kc * TK, x0 + tap % 3 - 1, y0 + tap / 3 - 1, img);
-        } else {
-          int src = 0, kc = it;
-          while (kc >= p.kchunks[src]) {
-            kc -= p.kchunks[src];
-            ++src;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int m0, n0, img, y0, x0;
+        tile_coords(tile, m0, n0, img, y0, x0);
+        for (int kc_all = 0; kc_all < nk; ++kc_all, ++it) {
+          const int s = it % STAGES;
+          if (it >= STAGES) mbar_wait(empty(s), ((it / STAGES) - 1) & 1);
+          const uint32_t st = base + s * STAGE_BYTES;
+          mbar_expect_tx(full(s), 3 * A_BYTES);
+          if (p.conv) {
+            const int tap = kc_all / p.kchunks[0], kc = kc_all - tap * p.kchunks[0];
+            tma_load_4d(st, &mapA0, full(s), kc * TK, x0 + tap % 3 - 1, y0 + tap / 3 - 1, img);
+          } else {
+            int src = 0, kc = kc_all;
+            while (kc >= p.kchunks[src]) {
+              kc -= p.kchunks[src];
+              ++src;
+            }
+            const CUtensorMap* mp = src == 0 ? &mapA0 : (src == 1 ? &mapA1 : &mapA2);
+            tma_load_2d(st, mp, full(s), kc * TK, m0);
           }
-          const CUtensorMap* mp = src == 0 ? &mapA0 : (src == 1 ? &mapA1 : &mapA2);
-          tma_load_2d(st, mp, full(s), kc * TK, m0);
+          tma_load_2d(st + 2 * A_BYTES, &mapWhi, full(s), kc_all * TK, n0);
+          tma_load_2d(st + 3 * A_BYTES, &mapWlo, full(s), kc_all * TK, n0);
         }
-        tma_load_2d(st + 2 * A_BYTES, &mapWhi, full(s), it * TK, n0);
-        tma_load_2d(st + 3 * A_BYTES, &mapWlo, full(s), it * TK, n0);
       }
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
-    for (int it = 0; it < nk; ++it) {
-      const int s = it % STAGES;
-      mbar_wait(split(s), (it / STAGES) & 1);     // implies the TMA bytes landed and A_hi/A_lo are written
+    int it = 0, tl = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+      const int a = tl & 1;
+      if (tl >= 2) mbar_wait(acc_empty(a), ((tl >> 1) - 1) & 1);   // epilogue drained this accumulator
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t st = base + s * STAGE_BYTES;
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(a * TN);
+      for (int kc_all = 0; kc_all < nk; ++kc_all, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(split(s), (it / STAGES) & 1);     // implies the TMA bytes landed and A_hi/A_lo are written
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t st = base + s * STAGE_BYTES;
 #pragma unroll
-        for (int k = 0; k < TK / 8; ++k) {
-          const uint64_t a_hi = umma_desc(st + k * 32), a_lo = umma_desc(st + A_BYTES + k * 32);
-          const uint64_t w_hi = umma_desc(st + 2 * A_BYTES + k * 32), w_lo = umma_desc(st + 3 * A_BYTES + k * 32);
-          umma_tf32(tmem_acc, a_lo, w_hi, (it | k) != 0);   // small terms first
-          umma_tf32(tmem_acc, a_hi, w_lo, 1);
-          umma_tf32(tmem_acc, a_hi, w_hi, 1);
+          for (int k = 0; k < TK / 8; ++k) {
+            const uint64_t a_hi = umma_desc(st + k * 32), a_lo = umma_desc(st + A_BYTES + k * 32);
+            const uint64_t w_hi = umma_desc(st + 2 * A_BYTES + k * 32), w_lo = umma_desc(st + 3 * A_BYTES + k * 32);
+            umma_tf32(tmem_acc, a_lo, w_hi, (kc_all | k) != 0);   // small terms first
+            umma_tf32(tmem_acc, a_hi, w_lo, 1);
+            umma_tf32(tmem_acc, a_hi, w_hi, 1);
+          }
+          umma_commit(empty(s));                      // stage reusable once these MMAs retire
+          if (kc_all == nk - 1) umma_commit(acc_full(a));
         }
-        umma_commit(empty(s));                      // stage reusable once these MMAs retire
-        if (it == nk - 1) umma_commit(tmem_full);
+        __syncwarp();
       }
-      __syncwarp();
+    }
+  } else if (warp < 6) {
+    // ---------------- splitter (warps 2..5, 128 threads) ----------------
+    const int et = threadIdx.x - 64;                // 0..127
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int kc_all = 0; kc_all < nk; ++kc_all, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(full(s), (it / STAGES) & 1);
+        float4* hi = reinterpret_cast<float4*>(base_ptr + s * STAGE_BYTES);
+        float4* lo = reinterpret_cast<float4*>(base_ptr + s * STAGE_BYTES + A_BYTES);
+#pragma unroll
+        for (int j = 0; j < A_BYTES / 16 / 128; ++j) {
+          float4 a = hi[et + j * 128], h, l;
+          h.x = __uint_as_float(__float_as_uint(a.x) & 0xFFFFE000u);
+          h.y = __uint_as_float(__float_as_uint(a.y) & 0xFFFFE000u);
+          h.z = __uint_as_float(__float_as_uint(a.z) & 0xFFFFE000u);
+          h.w = __uint_as_float(__float_as_uint(a.w) & 0xFFFFE000u);
+          l.x = a.x - h.x; l.y = a.y - h.y; l.z = a.z - h.z; l.w = a.w - h.w;
+          hi[et + j * 128] = h;
+          lo[et + j * 128] = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
+        __syncwarp();
+        if (lane == 0) mbar_arrive(split(s));
+      }
     }
   } else {
-    // ---------------- splitter, then epilogue (warps 2..5, 128 threads) ----------------
-    const int et = threadIdx.x - 64;                // 0..127
-    for (int it = 0; it < nk; ++it) {
-      const int s = it % STAGES;
-      mbar_wait(full(s), (it / STAGES) & 1);
-      float4* hi = reinterpret_cast<float4*>(base_ptr + s * STAGE_BYTES);
-      float4* lo = reinterpret_cast<float4*>(base_ptr + s * STAGE_BYTES + A_BYTES);
-#pragma unroll
-      for (int j = 0; j < A_BYTES / 16 / 128; ++j) {
-        float4 a = hi[et + j * 128], h, l;
-        h.x = __uint_as_float(__float_as_uint(a.x) & 0xFFFFE000u);
-        h.y = __uint_as_float(__float_as_uint(a.y) & 0xFFFFE000u);
-        h.z = __uint_as_float(__float_as_uint(a.z) & 0xFFFFE000u);
-        h.w = __uint_as_float(__float_as_uint(a.w) & 0xFFFFE000u);
-        l.x = a.x - h.x; l.y = a.y - h.y; l.z = a.z - h.z; l.w = a.w - h.w;
-        hi[et + j * 128] = h;
-        lo[et + j * 128] = l;
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
-      __syncwarp();
-      if (lane == 0) mbar_arrive(split(s));
-    }
-    // epilogue
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
+    // ---------------- epilogue (warps 6..9, 128 threads): TMEM -> registers -> global ----------------
     const int q = warp & 3;                          // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;                   // tile row held by this thread
-    float* stage_f = reinterpret_cast<float*>(base_ptr);   // reuse the (now idle) pipeline buffers: [128][132] floats
-    constexpr int SLD = TN + 4;
-#pragma unroll 1
-    for (int c0 = 0; c0 < TN; c0 += 32) {
-      float v[32];
-      tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-#pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<float4*>(&stage_f[row * SLD + c0 + j]) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-    }
-    tc_fence_before();
-    asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
-    // coalesced row stores: warp w writes rows w, w+4, ...; lane = 4 consecutive columns
-    const int ew = warp - 2;
-    for (int r = ew; r < TM; r += 4) {
+    int tl = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+      int m0, n0, img, y0, x0;
+      tile_coords(tile, m0, n0, img, y0, x0);
+      const int a = tl & 1;
+      mbar_wait(acc_full(a), (tl >> 1) & 1);
+      tc_fence_after();
       long long grow;
       bool ok;
       if (p.conv) {
-        const int yy = y0 + r / 16, xx = x0 + r % 16;
+        const int yy = y0 + row / 16, xx = x0 + row % 16;
         ok = yy < p.H && xx < p.W;
         grow = ((long long)img * p.H + yy) * p.W + xx;
       } else {
-        grow = m0 + r;
+        grow = m0 + row;
         ok = grow < p.M;
       }
-      const int col = n0 + lane * 4;
-      if (!ok || col >= p.N) continue;
-      float4 v = *reinterpret_cast<const float4*>(&stage_f[r * SLD + lane * 4]);
-      float o[4] = {v.x, v.y, v.z, v.w};
+      const float* resrow = (p.res && ok) ? p.res + (size_t)(grow % p.res_mod) * p.ldres : nullptr;
+      float* crow = p.C + (size_t)(ok ? grow : 0) * p.ldc;
+#pragma unroll 1
+      for (int c0 = 0; c0 < TN; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TN + c0), v);   // warp-collective
+        const int col = n0 + c0;
+        if (!ok || col >= p.N) continue;
+        if (col + 32 <= p.N) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (col + j < p.N) {
-          float t = o[j];
-          if (p.bias) t += __ldg(p.bias + col + j);
-          if (p.res) t += __ldg(p.res + (size_t)(grow % p.res_mod) * p.ldres + col + j);
-          o[j] = di_act(t, p.act);
+          for (int j = 0; j < 32; j += 4) {
+            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            if (p.bias) {
+              const float4 b4 = ldg4(p.bias + col + j);
+              o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+            }
+            if (resrow) {
+              const float4 r4 = ldg4(resrow + col + j);
+              o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+            }
+            o.x = di_act(o.x, p.act); o.y = di_act(o.y, p.act); o.z = di_act(o.z, p.act); o.w = di_act(o.w, p.act);
+            *reinterpret_cast<float4*>(crow + col + j) = o;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (col + j < p.N) {
+              float t = v[j];
+              if (p.bias) t += __ldg(p.bias + col + j);
+              if (resrow) t += __ldg(resrow + col + j);
+              crow[col + j] = di_act(t, p.act);
+            }
+          }
         }
       }
-      float* dst = p.C + (size_t)grow * p.ldc + col;
-      if (col + 3 < p.N) *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
-      else
-        for (int j = 0; j < 4 && col + j < p.N; ++j) dst[j] = o[j];
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(a));
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(128u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
   }
 }
 
@@ -341,7 +384,15 @@ bool make_map_nhwc(CUtensorMap* m, const float* ptr, int N, int H, int W, int C)
 
 bool g_attr_set = false;
 
-int launch_tc(const CUtensorMap maps[5], const TcParams& p, dim3 grid, cudaStream_t stream, const char* name) {
+int launch_tc(const CUtensorMap maps[5], const TcParams& p, cudaStream_t stream, const char* name) {
+  if (g_num_sms == 0) {
+    int devid = 0;
+    cudaGetDevice(&devid);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, devid);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  const int tiles = p.m_tiles * p.n_tiles;
+  dim3 grid(tiles < g_num_sms ? tiles : g_num_sms);
   if (!g_attr_set) {
     if (cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
       di_set_error("%s: cannot reserve %d bytes of shared memory", name, SMEM_BYTES);
@@ -372,7 +423,8 @@ int di_linear_tc_f32(const float* A0, int lda0, int K0, const float* A1, int lda
   const int lds[3] = {lda0, lda1, lda2}, Ks[3] = {K0, K1, K2};
   int nsrc = 1 + (K1 > 0) + (K2 > 0);
   int K = K0 + K1 + K2;
-  bool ok = al16(W_hi) && al16(W_lo) && al16(C) && ldc % 4 == 0 && K % 4 == 0 && (K2 == 0 || K1 > 0);
+  bool ok = al16(W_hi) && al16(W_lo) && al16(C) && ldc % 4 == 0 && K % 4 == 0 && (K2 == 0 || K1 > 0) &&
+            (!bias || al16(bias)) && (!res || (al16(res) && ldres % 4 == 0));
   for (int s = 0; s < nsrc; ++s) ok = ok && As[s] && Ks[s] % TK == 0 && lds[s] % 4 == 0 && al16(As[s]);
   if (!ok) {
     di_set_error("di_linear_tc_f32: shape/alignment not supported by the tensor-core path");
@@ -395,8 +447,9 @@ int di_linear_tc_f32(const float* A0, int lda0, int K0, const float* A1, int lda
   for (int s = 0; s < 3; ++s) p.kchunks[s] = Ks[s] / TK;
   p.conv = 0; p.C = C; p.ldc = ldc; p.bias = bias; p.res = res; p.ldres = ldres;
   p.res_mod = res_mod > 0 ? res_mod : M; p.act = act;
-  dim3 grid(di_cdiv(M, TM), di_cdiv(N, TN));
-  return launch_tc(maps, p, grid, stream, "di_linear_tc_f32");
+  p.m_tiles = di_cdiv(M, TM);
+  p.n_tiles = di_cdiv(N, TN);
+  return launch_tc(maps, p, stream, "di_linear_tc_f32");
 }
 
 // Tensor-core 3x3 convolution (stride 1, zero pad 1) over a pixel-major map: x [N,H,W,Cin] -> y [N,H,W,Cout],
@@ -404,7 +457,7 @@ int di_linear_tc_f32(const float* A0, int lda0, int K0, const float* A1, int lda
 int di_conv3x3_tc_f32(const float* x, const float* w_hi, const float* w_lo, const float* bias, float* y, int N, int Cin,
                       int H, int W, int Cout, int act, cudaStream_t stream) {
   DI_CHECK_ARG(x && w_hi && w_lo && y && N > 0 && H > 0 && W > 0, "di_conv3x3_tc_f32: bad argument");
-  if (!(Cin % TK == 0 && Cout % 4 == 0 && al16(x) && al16(y) && al16(w_hi) && al16(w_lo))) {
+  if (!(Cin % TK == 0 && Cout % 4 == 0 && al16(x) && al16(y) && al16(w_hi) && al16(w_lo) && (!bias || al16(bias)))) {
     di_set_error("di_conv3x3_tc_f32: shape/alignment not supported by the tensor-core path");
     return DI_ERR_UNSUPPORTED;
   }
@@ -424,8 +477,9 @@ int di_conv3x3_tc_f32(const float* x, const float* w_hi, const float* w_lo, cons
   p.M = N * H * W; p.N = Cout; p.nsrc = 1; p.kchunks[0] = Cin / TK; p.conv = 1; p.H = H; p.W = W;
   p.tiles_x = di_cdiv(W, 16); p.tiles_y = di_cdiv(H, 8);
   p.C = y; p.ldc = Cout; p.bias = bias; p.res = nullptr; p.ldres = 0; p.res_mod = 1; p.act = act;
-  dim3 grid(N * p.tiles_x * p.tiles_y, di_cdiv(Cout, TN));
-  return launch_tc(maps, p, grid, stream, "di_conv3x3_tc_f32");
+  p.m_tiles = N * p.tiles_x * p.tiles_y;
+  p.n_tiles = di_cdiv(Cout, TN);
+  return launch_tc(maps, p, stream, "di_conv3x3_tc_f32");
 }
 
 }  // extern "C"

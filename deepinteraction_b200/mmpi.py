@@ -197,7 +197,9 @@ class DeepInteractionDecoder(nn.Module):
             b1.append(b)
             blocks.append(fold._d(seq[1].weight).reshape(seq[1].weight.shape[0], -1))
             b2.append(fold._d(seq[1].bias))
-        return d(torch.cat(W1, 0)), d(torch.cat(b1, 0)), d(torch.block_diag(*blocks)), d(torch.cat(b2, 0))
+        dev_ = d(b1[0]).device
+        return (fold.Weight(torch.cat(W1, 0), dev_), d(torch.cat(b1, 0)), fold.Weight(torch.block_diag(*blocks), dev_),
+                d(torch.cat(b2, 0)))
 
     def _pack_mha(self, in_w, in_b, out_proj, d, two_source_q=False):
         C, h = self.hidden_channel, self.num_heads
@@ -205,7 +207,8 @@ class DeepInteractionDecoder(nn.Module):
         s = float(C // h) ** -0.5
         W[:C] *= s          # q = (Wq x + bq) * head_dim^-0.5  (decoder_utils.py:407; same in nn.MultiheadAttention)
         b[:C] *= s
-        return W, b, d(fold._d(out_proj.weight)), d(fold._d(out_proj.bias))
+        dev_ = d(b).device
+        return W, b, fold.Weight(fold._d(out_proj.weight), dev_), d(fold._d(out_proj.bias))
 
     def pack(self, force=False):
         key = self._state_key()
@@ -221,23 +224,30 @@ class DeepInteractionDecoder(nn.Module):
             seq = getattr(self, name)
             w0, b0 = fold.conv_bn(seq[0].conv, seq[0].bn)
             w1, b1 = fold.conv_bn(seq[1])
-            pk[name] = (fold.Weight(fold.pack_conv3x3(w0), device), d(b0), d(fold.pack_conv3x3(w1)), d(b1))
+            # second conv: pad Cout to a multiple of 4 (zero rows) so that it can take the tensor-core path
+            w1p, kpad = fold.pack_conv3x3(w1), (-w1.shape[0]) % 4
+            w1p = torch.cat([w1p, torch.zeros(kpad, w1p.shape[1], dtype=w1p.dtype)], 0)
+            b1p = torch.cat([b1, torch.zeros(kpad, dtype=b1.dtype)], 0)
+            pk[name] = (fold.Weight(fold.pack_conv3x3(w0), device), d(b0), fold.Weight(w1p, device), d(b1p))
         pk['wce_t'] = d(fold._d(self.class_encoding.weight)[:, :, 0].t())
         pk['bce'] = d(fold._d(self.class_encoding.bias))
         layer = self.decoder[0]
+        lin = lambda m: (d(fold._d(m.weight)), d(fold._d(m.bias)))
+        linw = lambda m: (fold.Weight(fold._d(m.weight), device), d(fold._d(m.bias)))
 
         def pe_pack(pe):
             seq = pe.position_embedding_head
             w1, b1 = fold.conv_bn(seq[0], seq[1])
-            return d(w1.reshape(w1.shape[0], -1)), d(b1), d(fold._d(seq[3].weight)[:, :, 0]), d(fold._d(seq[3].bias))
+            return (d(w1.reshape(w1.shape[0], -1)), d(b1), fold.Weight(fold._d(seq[3].weight)[:, :, 0], device),
+                    d(fold._d(seq[3].bias)))
         pk['self_pe'] = pe_pack(layer.self_posembed)
         cross_pe = pe_pack(layer.cross_posembed)
         W, b, wo, bo = self._pack_mha(layer.self_attn.in_proj_weight, layer.self_attn.in_proj_bias,
                                       layer.self_attn.out_proj, d)
-        pk['self_attn'] = (d(torch.cat([W, W], 1)), d(b), wo, bo)           # sources [query | query_pos_embed]
+        pk['self_attn'] = (fold.Weight(torch.cat([W, W], 1), device), d(b), wo, bo)   # sources [query | query_pos_embed]
         W, b, wo, bo = self._pack_mha(layer.multihead_attn.in_proj_weight, layer.multihead_attn.in_proj_bias,
                                       layer.multihead_attn.out_proj, d)
-        pk['cross_q'] = (d(torch.cat([W[:C], W[:C]], 1)), d(b[:C]))
+        pk['cross_q'] = (fold.Weight(torch.cat([W[:C], W[:C]], 1), device), d(b[:C]))
         w_kv, b_kv = fold.Weight(W[C:], device), d(b[C:])
         # constant key positional embedding -> its K/V contribution, with our own kernels (bev grid is fixed)
         ys, xs = torch.meshgrid(torch.arange(self.y_size, dtype=torch.float32),
@@ -246,11 +256,9 @@ class DeepInteractionDecoder(nn.Module):
         kpe = ops.linear([ops.linear([bev_pos], cross_pe[0], cross_pe[1], ops.ACT_RELU)], cross_pe[2], cross_pe[3])
         pk['cross_kv'] = (w_kv, b_kv, ops.linear([kpe], w_kv))
         pk['cross_out'] = (wo, bo)
-        lin = lambda m: (d(fold._d(m.weight)), d(fold._d(m.bias)))
-        linw = lambda m: (fold.Weight(fold._d(m.weight), device), d(fold._d(m.bias)))
         for i in (1, 2, 3):
             pk[f'norm{i}'] = lin(getattr(layer, f'norm{i}'))
-        pk['ffn'] = lin(layer.linear1) + lin(layer.linear2)
+        pk['ffn'] = linw(layer.linear1) + linw(layer.linear2)
         pk['pred0'] = self._pack_pred(self.prediction_heads[0], d)
         blocks = []
         for blk, ph in zip(self.decode_head, self.pred_head):
@@ -258,10 +266,10 @@ class DeepInteractionDecoder(nn.Module):
             mha = g('dyconv_pre_self_attn')
             W, b, wo, bo = self._pack_mha(mha.in_proj_weight, mha.in_proj_bias, mha.out_proj, d)
             dy = g('dyconv')
-            blocks.append(dict(image=blk.sfx == '', attn=(d(W), d(b), wo, bo), norm1=lin(g('norm1')),
+            blocks.append(dict(image=blk.sfx == '', attn=(fold.Weight(W, device), d(b), wo, bo), norm1=lin(g('norm1')),
                                norm2=lin(g('norm2')), norm3=lin(g('norm3')), dyn=linw(dy.dynamic_layer),
                                dn1=lin(dy.norm1), dn2=lin(dy.norm2), dout=lin(dy.out_layer), dn3=lin(dy.norm3),
-                               ffn=lin(g('linear1')) + lin(g('linear2')), pred=self._pack_pred(ph, d)))
+                               ffn=linw(g('linear1')) + linw(g('linear2')), pred=self._pack_pred(ph, d)))
         pk['blocks'] = blocks
         self._pack, self._pack_key = pk, key
         return pk
@@ -288,12 +296,13 @@ class DeepInteractionDecoder(nn.Module):
         dev_ = pts_conv.device
         # heatmaps, NMS, top-k, query init
         w0, b0, w1, b1 = pk['heatmap_head']
-        dense_a = ops.conv3x3(ops.conv3x3(pts_conv, w0, b0, C, True, False, ops.ACT_RELU), w1, b1, K, True, True)
+        Kp = w1.shape[0]
+        logit_a = ops.conv3x3(ops.conv3x3(pts_conv, w0, b0, C, True, False, ops.ACT_RELU), w1, b1, Kp, True, False)
         w0, b0, w1, b1 = pk['heatmap_head_img']
-        dense_b = ops.conv3x3(ops.conv3x3(new_pts, w0, b0, C, True, False, ops.ACT_RELU), w1, b1, K, True, True)
+        logit_b = ops.conv3x3(ops.conv3x3(new_pts, w0, b0, C, True, False, ops.ACT_RELU), w1, b1, Kp, True, False)
         ds = self.test_cfg['dataset']
         no_nms = {'nuScenes': (1 << 8) | (1 << 9), 'Waymo': (1 << 1) | (1 << 2)}.get(ds, 0)
-        heat = ops.heatmap_nms(dense_a, dense_b, self.nms_kernel_size, no_nms)
+        heat, dense_b = ops.heatmap_nms(logit_a, logit_b, K, self.nms_kernel_size, no_nms)
         top = ops.topk(heat.view(B, K * HW), P)
         q, qpos, labels, qscore = ops.query_init(pts_conv.view(B, HW, C), top, heat, pk['wce_t'], pk['bce'], X)
         self.query_labels = labels.long()
@@ -342,7 +351,7 @@ class DeepInteractionDecoder(nn.Module):
             q1 = ops.rows_finish(ops.linear([a], wo, bo), res=prev, gamma=bp['norm1'][0], beta=bp['norm1'][1])
             params = ops.linear([q1], *bp['dyn'])
             flat = ops.dynconv(roi, params, *bp['dn1'], *bp['dn2'])
-            part = ops.linear([flat], bp['dout'][0], splits=14)
+            part = ops.linear([flat], bp['dout'][0], splits=49)
             t = ops.rows_finish(part, bias=bp['dout'][1], gamma=bp['dn3'][0], beta=bp['dn3'][1], act=ops.ACT_RELU)
             q2 = ops.rows_finish(t, res=q1, gamma=bp['norm2'][0], beta=bp['norm2'][1])
             f1w, f1b, f2w, f2b = bp['ffn']

@@ -203,12 +203,14 @@ def bev_sample(bev_nhwc, grid, V):
     return out
 
 
-def heatmap_nms(a, b, ks, no_nms_mask):
-    B, K, H, W = a.shape
-    assert a.is_contiguous() and b.is_contiguous()
+def heatmap_nms(a, b, K, ks, no_nms_mask, want_dense=True):
+    """a, b: pixel-major logits [B,H,W,ld] (ld >= K).  -> masked heat [B,K,H*W], dense_b [B,K,H,W]."""
+    B, H, W, ld = a.shape
+    assert a.is_contiguous() and b.is_contiguous() and b.shape == a.shape
     out = torch.empty(B, K, H * W, device=a.device, dtype=torch.float32)
-    _call('di_heatmap_nms_f32', _ptr(a), _ptr(b), _ptr(out), B, K, H, W, ks, no_nms_mask, _stream())
-    return out
+    dense = torch.empty(B, K, H, W, device=a.device, dtype=torch.float32) if want_dense else None
+    _call('di_heatmap_nms_f32', _ptr(a), _ptr(b), ld, _ptr(out), _ptr(dense), B, K, H, W, ks, no_nms_mask, _stream())
+    return out, dense
 
 
 def topk(scores, k):

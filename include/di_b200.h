@@ -116,8 +116,8 @@ int di_bev_sample_f32(const float* bev, const float* grid_xy, float* out, int B,
 /* ---- decoder (decoder.cu) ------------------------------------------------------------------------ */
 
 /* models/dense_heads/deepinteraction_decoder.py:225-239 */
-int di_heatmap_nms_f32(const float* a, const float* b, float* out, int B, int K, int H, int W, int ks,
-                       int no_nms_class_mask, cudaStream_t stream);
+int di_heatmap_nms_f32(const float* a, const float* b, int ld, float* out, float* dense_b, int B, int K, int H, int W,
+                       int ks, int no_nms_class_mask, cudaStream_t stream);
 /* :242 (argsort descending, first k) */
 int di_topk_f32(const float* scores, int* idx, int B, int n, int k, void* work, int slices, cudaStream_t stream);
 /* :243-253, :299 */

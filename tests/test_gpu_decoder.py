@@ -28,7 +28,9 @@ def test_heatmap_nms_and_topk():
     lm[:, :, 1:-1, 1:-1] = F.max_pool2d(heat, 3, 1, 0)
     lm[:, 8], lm[:, 9] = heat[:, 8], heat[:, 9]
     ref = (heat * (heat == lm)).view(B, K, -1)
-    out = ops.heatmap_nms(a.to(dev()), b.to(dev()), 3, (1 << 8) | (1 << 9))
+    pad = lambda t: F.pad(t.permute(0, 2, 3, 1), (0, 2)).contiguous().to(dev())       # pixel-major, ld = 12
+    out, dense = ops.heatmap_nms(pad(a), pad(b), K, 3, (1 << 8) | (1 << 9))
+    assert torch.equal(dense.cpu(), b)
     # same support; values equal to fp32 rounding of sigmoid
     assert torch.equal(out.cpu() > 0, ref > 0)
     assert float((out.cpu() - ref).abs().max()) < 1e-6
