@@ -86,15 +86,35 @@ topk_kernel(const float* __restrict__ scores_all, const int* __restrict__ src_id
       if ((u & known_mask) == prefix) atomicAdd(&hist[(u >> sh) & wmask], 1u);
     }
     __syncthreads();
-    if (t == 0) {
-      unsigned acc = 0;
-      int bin = (int)wmask;
-      for (; bin > 0; --bin) {
-        if (acc + hist[bin] >= need) break;
-        acc += hist[bin];
+    if (t < 32) {
+      // warp-parallel search of the bin where the count from the top reaches `need`
+      const int nb = (int)wmask + 1, per = (nb + 31) / 32;
+      const int hi_bin = min(nb, (t + 1) * per) - 1, lo_bin = t * per;
+      unsigned mine = 0;
+      for (int bnum = lo_bin; bnum <= hi_bin; ++bnum) mine += hist[bnum];
+      // above[t] = elements in bins owned by lanes > t
+      unsigned above = 0;
+      for (int l = 31; l >= 0; --l) {
+        unsigned v = __shfl_sync(0xffffffffu, mine, l);
+        if (l > t) above += v;
       }
-      s_prefix = prefix | ((unsigned)bin << sh);
-      s_need = need - acc;
+      const bool owner = above < need && above + mine >= need;
+      unsigned vote = __ballot_sync(0xffffffffu, owner);
+      if (vote == 0) {            // cannot happen (the matching count is always >= need); keep the prefix
+        if (t == 0) {
+          s_prefix = prefix;
+          s_need = 0;
+        }
+      } else if (owner) {
+        unsigned acc = above;
+        int bin = hi_bin;
+        for (; bin > lo_bin; --bin) {
+          if (acc + hist[bin] >= need) break;
+          acc += hist[bin];
+        }
+        s_prefix = prefix | ((unsigned)bin << sh);
+        s_need = need - acc;
+      }
     }
     __syncthreads();
     prefix = s_prefix;
