@@ -25,6 +25,7 @@ SIGNATURES = {
     'di_conv3x3_tc_f32': [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     # lcab.cu
     'di_lcab_window_f32': [_p, _i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _p],
+    'di_set_window_ffma': [_i],
     'di_locatt_cc2k_f32': [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     'di_locatt_ck2c_ori_f32': [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     'di_locatt_ck2c_loc_f32': [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p],

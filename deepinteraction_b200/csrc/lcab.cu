@@ -150,6 +150,197 @@ lcab_window_kernel(const float* __restrict__ q, int ldq, const float* __restrict
 
 
 // ------------------------------------------------------------------------------------------------
+// Tensor-core version of the 9x9 window attention (the one the product path launches).
+// One CTA = 8 query rows x 16 query columns; warp w owns the 16 queries of row y0+w.  Both contractions run on
+// mma.sync.m16n8k8 TF32 with error compensation (hi/lo split of both operands, 3 products), so logits and outputs
+// stay fp32-faithful:
+//   S[16 x (9 rows x 24 cols)] = Q K^T   -> 27 key blocks of 8; accumulated over 32-channel chunks
+//   softmax over the 81 in-window keys of each query, entirely in registers (quad shuffles)
+//   O[16 x C] = P V                       -> the S accumulator fragments are re-used as the A operand by pairing
+//                                            k-index t <-> key 2t and t+4 <-> key 2t+1 of each block
+// Band structure: a query uses 9 of the 24 key columns of its row block (2.67x padding, none along rows).
+// The key/value halo tile (16 x 24 pixels x 32 channels) and the query tile stream through shared memory with
+// cp.async double buffering; zero-filled halo pixels give the reference's out-of-image rule (logit 0 kept in the
+// softmax, value skipped).
+// ------------------------------------------------------------------------------------------------
+constexpr int MQ_ROWS = 8, MQ_COLS = 16, MCH = 32, MSTR = MCH + 4;   // padded pixel stride: conflict-free fragments
+constexpr int MT_ROWS = MQ_ROWS + 8, MT_COLS = MQ_COLS + 8;
+constexpr int MKV_FLOATS = MT_ROWS * MT_COLS * MSTR;                  // 13824
+constexpr int MQ_FLOATS = MQ_ROWS * MQ_COLS * MSTR;                   // 4608
+constexpr int MSTAGE_FLOATS = MKV_FLOATS + MQ_FLOATS;
+
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xFFFFE000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
+__global__ void __launch_bounds__(256, 1)
+lcab_window_mma_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk,
+                       const float* __restrict__ v, int ldv, float* __restrict__ out, int ldo, int H, int W, int C,
+                       float scale) {
+  extern __shared__ __align__(16) float smem[];   // [2][MKV_FLOATS + MQ_FLOATS]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int x0 = blockIdx.x * MQ_COLS, y0 = blockIdx.y * MQ_ROWS, n = blockIdx.z;
+  const size_t img_off = (size_t)n * H * W;
+  const int nchunk = C / MCH;
+  const int nstage = 2 * nchunk;
+
+  auto issue = [&](int stage) {
+    const bool is_k = stage < nchunk;
+    const float* src = is_k ? k : v;
+    const int ld = is_k ? ldk : ldv;
+    const int c0 = (is_k ? stage : stage - nchunk) * MCH;
+    float* dst = smem + (stage & 1) * MSTAGE_FLOATS;
+    for (int i = tid; i < MT_ROWS * MT_COLS * (MCH / 4); i += 256) {
+      int px = i / (MCH / 4), c4 = i % (MCH / 4);
+      int gy = y0 - 4 + px / MT_COLS, gx = x0 - 4 + px % MT_COLS;
+      bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
+      const float* gp = ok ? src + (img_off + (size_t)gy * W + gx) * ld + c0 + c4 * 4 : src;
+      cp_async16(dst + px * MSTR + c4 * 4, gp, ok);
+    }
+    if (is_k) {
+      float* qd = dst + MKV_FLOATS;
+      for (int i = tid; i < MQ_ROWS * MQ_COLS * (MCH / 4); i += 256) {
+        int px = i / (MCH / 4), c4 = i % (MCH / 4);
+        int gy = y0 + px / MQ_COLS, gx = x0 + px % MQ_COLS;
+        bool ok = gy < H && gx < W;
+        const float* gp = ok ? q + (img_off + (size_t)gy * W + gx) * ldq + c0 + c4 * 4 : q;
+        cp_async16(qd + px * MSTR + c4 * 4, gp, ok);
+      }
+    }
+    cp_async_commit();
+  };
+
+  float S[27][4];
+#pragma unroll
+  for (int b = 0; b < 27; ++b) S[b][0] = S[b][1] = S[b][2] = S[b][3] = 0.f;
+
+  issue(0);
+  for (int stage = 0; stage < nstage; ++stage) {
+    if (stage + 1 < nstage) {
+      issue(stage + 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const float* kv = smem + (stage & 1) * MSTAGE_FLOATS;
+    if (stage < nchunk) {
+      // ---------------- S += Q[chunk] K[chunk]^T ----------------
+      const float* qs = kv + MKV_FLOATS + (warp * MQ_COLS) * MSTR;
+#pragma unroll
+      for (int ks = 0; ks < MCH / 8; ++ks) {
+        uint32_t ah[4], al[4];
+        split_tf32(qs[g * MSTR + ks * 8 + t], ah[0], al[0]);
+        split_tf32(qs[(g + 8) * MSTR + ks * 8 + t], ah[1], al[1]);
+        split_tf32(qs[g * MSTR + ks * 8 + t + 4], ah[2], al[2]);
+        split_tf32(qs[(g + 8) * MSTR + ks * 8 + t + 4], ah[3], al[3]);
+#pragma unroll
+        for (int r = 0; r < 9; ++r)
+#pragma unroll
+          for (int cb = 0; cb < 3; ++cb) {
+            const float* kp = kv + ((warp + r) * MT_COLS + cb * 8 + g) * MSTR + ks * 8 + t;
+            uint32_t bh0, bl0, bh1, bl1;
+            split_tf32(kp[0], bh0, bl0);
+            split_tf32(kp[4], bh1, bl1);
+            mma_tf32(S[r * 3 + cb], al, bh0, bh1);
+            mma_tf32(S[r * 3 + cb], ah, bl0, bl1);
+            mma_tf32(S[r * 3 + cb], ah, bh0, bh1);
+          }
+      }
+      if (stage == nchunk - 1) {
+        // ---------------- masked softmax over the 81 in-window keys ----------------
+        float m0 = -INFINITY, m1 = -INFINITY;   // rows g and g+8
+#pragma unroll
+        for (int b = 0; b < 27; ++b) {
+          const int cb = b % 3;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int kc = cb * 8 + 2 * t + j;
+            const int d0 = kc - g, d1 = kc - (g + 8);
+            S[b][j] = (d0 >= 0 && d0 <= 8) ? S[b][j] * scale : -INFINITY;
+            S[b][2 + j] = (d1 >= 0 && d1 <= 8) ? S[b][2 + j] * scale : -INFINITY;
+            m0 = fmaxf(m0, S[b][j]);
+            m1 = fmaxf(m1, S[b][2 + j]);
+          }
+        }
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int b = 0; b < 27; ++b)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            S[b][j] = expf(S[b][j] - m0);            // exp(-inf) = 0 for out-of-window entries
+            S[b][2 + j] = expf(S[b][2 + j] - m1);
+            s0 += S[b][j];
+            s1 += S[b][2 + j];
+          }
+        s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
+        s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+        const float i0 = 1.f / s0, i1 = 1.f / s1;
+#pragma unroll
+        for (int b = 0; b < 27; ++b) {
+          S[b][0] *= i0; S[b][1] *= i0; S[b][2] *= i1; S[b][3] *= i1;
+        }
+      }
+    } else {
+      // ---------------- O[chunk] = P V[chunk] ----------------
+      float O[MCH / 8][4];
+#pragma unroll
+      for (int nb = 0; nb < MCH / 8; ++nb) O[nb][0] = O[nb][1] = O[nb][2] = O[nb][3] = 0.f;
+#pragma unroll
+      for (int r = 0; r < 9; ++r)
+#pragma unroll
+        for (int cb = 0; cb < 3; ++cb) {
+          const int b = r * 3 + cb;
+          uint32_t ah[4], al[4];                       // A = P block with k-index t <-> key 2t, t+4 <-> key 2t+1
+          split_tf32(S[b][0], ah[0], al[0]);
+          split_tf32(S[b][2], ah[1], al[1]);
+          split_tf32(S[b][1], ah[2], al[2]);
+          split_tf32(S[b][3], ah[3], al[3]);
+          const float* vp = kv + ((warp + r) * MT_COLS + cb * 8 + 2 * t) * MSTR + g;
+#pragma unroll
+          for (int nb = 0; nb < MCH / 8; ++nb) {
+            uint32_t bh0, bl0, bh1, bl1;
+            split_tf32(vp[nb * 8], bh0, bl0);
+            split_tf32(vp[MSTR + nb * 8], bh1, bl1);
+            mma_tf32(O[nb], al, bh0, bh1);
+            mma_tf32(O[nb], ah, bl0, bl1);
+            mma_tf32(O[nb], ah, bh0, bh1);
+          }
+        }
+      const int qy = y0 + warp, cbase = (stage - nchunk) * MCH;
+      if (qy < H) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int qx = x0 + g + half * 8;
+          if (qx < W) {
+            float* o = out + (img_off + (size_t)qy * W + qx) * ldo + cbase + 2 * t;
+#pragma unroll
+            for (int nb = 0; nb < MCH / 8; ++nb)
+              *reinterpret_cast<float2*>(o + nb * 8) = make_float2(O[nb][half * 2], O[nb][half * 2 + 1]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------
 // Unfused NCHW window ops with the exact contract of the reference extension `localattention`
 // (locatt_ops/kernels.cuh: cc2k :4-42, ck2c_ori :44-80, ck2c_loc :82-119; fp32 data, fp64 accumulate
 // as in f_cc2k<float,double>).  They exist for drop-in compatibility (autograd of the unfused path);
@@ -215,7 +406,15 @@ __global__ void locatt_ck2c_loc_kernel(const float* __restrict__ x_ori, const fl
 
 }  // namespace
 
+static int g_force_ffma_window = 0;
+
 extern "C" {
+
+// test hook: 1 = use the FFMA window kernel even where the tensor-core one applies
+int di_set_window_ffma(int on) {
+  g_force_ffma_window = on;
+  return DI_OK;
+}
 
 // q,k,v,out: [N,H,W,*] pixel-major fp32 with per-pixel strides ldq/ldk/ldv/ldo (>= C, multiples of 4).
 // ksize must be 9 (the only window the reference configs use) or 3 (tests).  C % 16 == 0.
@@ -227,7 +426,12 @@ int di_lcab_window_f32(const float* q, int ldq, const float* k, int ldk, const f
   DI_CHECK_ARG(((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)out) % 16 == 0, "di_lcab_window_f32: pointers must be 16-byte aligned");
   dim3 grid(di_cdiv(W, TQ), di_cdiv(H, TQ), N);
   float scale = 1.0f / sqrtf((float)C);
-  if (ksize == 9) {
+  if (ksize == 9 && C % MCH == 0 && !g_force_ffma_window) {
+    dim3 mgrid(di_cdiv(W, MQ_COLS), di_cdiv(H, MQ_ROWS), N);
+    size_t smem = 2ull * MSTAGE_FLOATS * sizeof(float);
+    cudaFuncSetAttribute(lcab_window_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    lcab_window_mma_kernel<<<mgrid, 256, smem, stream>>>(q, ldq, k, ldk, v, ldv, out, ldo, H, W, C, scale);
+  } else if (ksize == 9) {
     size_t smem = 2ull * (TQ + 8) * (TQ + 8) * PSTR * sizeof(float);
     cudaFuncSetAttribute(lcab_window_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     lcab_window_kernel<9><<<grid, TQ * TQ, smem, stream>>>(q, ldq, k, ldk, v, ldv, out, ldo, H, W, C, scale);

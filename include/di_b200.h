@@ -73,6 +73,10 @@ int di_conv3x3_tc_f32(const float* x, const float* w_hi, const float* w_lo, cons
 int di_lcab_window_f32(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* out, int ldo,
                        int N, int H, int W, int C, int ksize, cudaStream_t stream);
 
+/* test/diagnostic hook: 1 = always use the FFMA window kernel, 0 = tensor-core (mma.sync 3xTF32) kernel when
+ * ksize == 9 and C % 32 == 0 (default) */
+int di_set_window_ffma(int on);
+
 /* The reference extension's own five entry points, unfused and NCHW, for drop-in compatibility
  * (locatt_ops/localAttention.cpp:61-73): similar_forward = cc2k(x_ori, x_loc); weighting_forward =
  * ck2c_ori(x, weight); similar_backward(is_ori) = ck2c_ori / ck2c_loc(x, grad); weighting_backward_ori =

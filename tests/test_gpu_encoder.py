@@ -89,18 +89,24 @@ def test_layout_converters_roundtrip():
     assert torch.equal(ops.nhwc_to_nchw(y), x)
 
 
-@pytest.mark.parametrize('ks,C,H,W', [(9, 32, 13, 21), (9, 128, 40, 33), (3, 16, 7, 5), (9, 64, 16, 16)])
-def test_window_attention_matches_oracle(ks, C, H, W):
+@pytest.mark.parametrize('ffma', [False, True])
+@pytest.mark.parametrize('ks,C,H,W', [(9, 32, 13, 21), (9, 128, 40, 33), (3, 16, 7, 5), (9, 64, 16, 16), (9, 128, 9, 50)])
+def test_window_attention_matches_oracle(ks, C, H, W, ffma):
+    """Both window kernels: mma.sync 3xTF32 (default for ks=9, C%32==0) and the FFMA one."""
     import oracle.mmri as om
-    from deepinteraction_b200 import ops
+    from deepinteraction_b200 import ops, _lib
+    _lib.lib().di_set_window_ffma(1 if ffma else 0)
     g = torch.Generator().manual_seed(3)
     N = 2
     q, k, v = (torch.randn(N, C, H, W, generator=g) for _ in range(3))
     w = F.softmax(om.window_similarity(q, k, ks) / np.sqrt(C), -1)
     ref = om.window_weighting(v, w, ks)
     rows = lambda t: t.permute(0, 2, 3, 1).reshape(-1, C).contiguous().to(dev())
-    out = ops.lcab_window(rows(q), rows(k), rows(v), N, H, W, C, ks)
-    out = out.view(N, H, W, C).permute(0, 3, 1, 2).cpu()
+    try:
+        out = ops.lcab_window(rows(q), rows(k), rows(v), N, H, W, C, ks)
+        out = out.view(N, H, W, C).permute(0, 3, 1, 2).cpu()
+    finally:
+        _lib.lib().di_set_window_ffma(0)
     assert rel_err(out, ref) < TIGHT
 
 
