@@ -74,6 +74,13 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       : "memory");
 }
 
+// L2 prefetch of a future box (no shared-memory footprint): raises the bytes in flight beyond the 3-stage ring
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+
 // K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row atoms 1024 bytes apart.
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) /*LBO (unused)*/ | (64ull << 32) /*SBO = 1024 B*/ |
@@ -192,9 +199,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     // ---------------- TMA producer ----------------
     if (lane == 0) {
       int it = 0;
+      auto prefetch_tile = [&](int tile) {
+        if (p.conv || tile >= num_tiles) return;
+        const int mt = tile / p.n_tiles;
+        if (tile - mt * p.n_tiles != 0 && mt == (tile - 1) / p.n_tiles) return;   // same A rows as the previous n-tile
+        int kc_all = 0;
+        for (int src = 0; src < p.nsrc; ++src)
+          for (int kc = 0; kc < p.kchunks[src]; ++kc, ++kc_all) {
+            const CUtensorMap* mp = src == 0 ? &mapA0 : (src == 1 ? &mapA1 : &mapA2);
+            tma_prefetch_2d(mp, kc * TK, mt * TM);
+          }
+      };
+      constexpr int PF = 2;                                       // prefetch distance in rounds of tiles
+      for (int r = 1; r <= PF; ++r) prefetch_tile(blockIdx.x + r * gridDim.x);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int m0, n0, img, y0, x0;
         tile_coords(tile, m0, n0, img, y0, x0);
+        prefetch_tile(tile + (PF + 1) * gridDim.x);
         for (int kc_all = 0; kc_all < nk; ++kc_all, ++it) {
           const int s = it % STAGES;
           if (it >= STAGES) mbar_wait(empty(s), ((it / STAGES) - 1) & 1);
@@ -297,15 +318,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 #pragma unroll 1
       for (int c0 = 0; c0 < TN; c0 += 32) {
         float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TN + c0), v);   // warp-collective
         const int col = n0 + c0;
+        const bool fullc = col + 32 <= p.N;
+        float4 bv[8];
+        if (p.bias && fullc) {                       // issue the (L1-resident) bias loads before the TMEM wait
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bv[j] = ldg4(p.bias + col + 4 * j);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TN + c0), v);   // warp-collective
         if (!ok || col >= p.N) continue;
-        if (col + 32 <= p.N) {
+        if (fullc) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            if (p.bias) {
-              const float4 b4 = ldg4(p.bias + col + j);
+            {
+              const float4 b4 = bv[j >> 2];
               o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
             }
             if (resrow) {
