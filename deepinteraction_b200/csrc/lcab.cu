@@ -151,14 +151,14 @@ lcab_window_kernel(const float* __restrict__ q, int ldq, const float* __restrict
 
 // ------------------------------------------------------------------------------------------------
 // Tensor-core version of the 9x9 window attention (the one the product path launches).
-// One CTA = 8 query rows x 16 query columns; warp w owns the 16 queries of row y0+w.  Both contractions run on
-// mma.sync.m16n8k8 TF32 with error compensation (hi/lo split of both operands, 3 products), so logits and outputs
-// stay fp32-faithful:
-//   S[16 x (9 rows x 24 cols)] = Q K^T   -> 27 key blocks of 8; accumulated over 32-channel chunks
+// One CTA = 8 query rows x 16 query columns; a warp owns a 2 x 8 patch of queries (M = 16).  Both contractions run
+// on mma.sync.m16n8k8 TF32 with error compensation (hi/lo split of both operands, 3 products), so logits and
+// outputs stay fp32-faithful:
+//   S[16 x (10 rows x 16 cols)] = Q K^T  -> 20 key blocks of 8; accumulated over 32-channel chunks
 //   softmax over the 81 in-window keys of each query, entirely in registers (quad shuffles)
 //   O[16 x C] = P V                       -> the S accumulator fragments are re-used as the A operand by pairing
 //                                            k-index t <-> key 2t and t+4 <-> key 2t+1 of each block
-// Band structure: a query uses 9 of the 24 key columns of its row block (2.67x padding, none along rows).
+// Band structure: a query uses 9 of the 16 key columns and 9 of the 10 key rows of its patch (1.98x padding).
 // The key/value halo tile (16 x 24 pixels x 32 channels) and the query tile stream through shared memory with
 // cp.async double buffering; zero-filled halo pixels give the reference's out-of-image rule (logit 0 kept in the
 // softmax, value skipped).
@@ -218,9 +218,12 @@ lcab_window_mma_kernel(const float* __restrict__ q, int ldq, const float* __rest
     cp_async_commit();
   };
 
-  float S[27][4];
+  // warp -> 2 query rows x 8 query columns (M = 16): fragment rows g = (row wy, col wx+g), g+8 = (row wy+1, col wx+g).
+  // Keys: 10 halo rows (wy .. wy+9 in tile coordinates) x 16 halo columns (wx .. wx+15) = 20 blocks of 8.
+  const int wy = 2 * (warp >> 1), wx = 8 * (warp & 1);
+  float S[20][4];
 #pragma unroll
-  for (int b = 0; b < 27; ++b) S[b][0] = S[b][1] = S[b][2] = S[b][3] = 0.f;
+  for (int b = 0; b < 20; ++b) S[b][0] = S[b][1] = S[b][2] = S[b][3] = 0.f;
 
   issue(0);
   for (int stage = 0; stage < nstage; ++stage) {
@@ -234,39 +237,39 @@ lcab_window_mma_kernel(const float* __restrict__ q, int ldq, const float* __rest
     const float* kv = smem + (stage & 1) * MSTAGE_FLOATS;
     if (stage < nchunk) {
       // ---------------- S += Q[chunk] K[chunk]^T ----------------
-      const float* qs = kv + MKV_FLOATS + (warp * MQ_COLS) * MSTR;
+      const float* qs = kv + MKV_FLOATS + (wy * MQ_COLS + wx) * MSTR;
 #pragma unroll
       for (int ks = 0; ks < MCH / 8; ++ks) {
         uint32_t ah[4], al[4];
         split_tf32(qs[g * MSTR + ks * 8 + t], ah[0], al[0]);
-        split_tf32(qs[(g + 8) * MSTR + ks * 8 + t], ah[1], al[1]);
+        split_tf32(qs[(MQ_COLS + g) * MSTR + ks * 8 + t], ah[1], al[1]);
         split_tf32(qs[g * MSTR + ks * 8 + t + 4], ah[2], al[2]);
-        split_tf32(qs[(g + 8) * MSTR + ks * 8 + t + 4], ah[3], al[3]);
+        split_tf32(qs[(MQ_COLS + g) * MSTR + ks * 8 + t + 4], ah[3], al[3]);
 #pragma unroll
-        for (int r = 0; r < 9; ++r)
+        for (int r = 0; r < 10; ++r)
 #pragma unroll
-          for (int cb = 0; cb < 3; ++cb) {
-            const float* kp = kv + ((warp + r) * MT_COLS + cb * 8 + g) * MSTR + ks * 8 + t;
+          for (int cb = 0; cb < 2; ++cb) {
+            const float* kp = kv + ((wy + r) * MT_COLS + wx + cb * 8 + g) * MSTR + ks * 8 + t;
             uint32_t bh0, bl0, bh1, bl1;
             split_tf32(kp[0], bh0, bl0);
             split_tf32(kp[4], bh1, bl1);
-            mma_tf32(S[r * 3 + cb], al, bh0, bh1);
-            mma_tf32(S[r * 3 + cb], ah, bl0, bl1);
-            mma_tf32(S[r * 3 + cb], ah, bh0, bh1);
+            mma_tf32(S[r * 2 + cb], al, bh0, bh1);
+            mma_tf32(S[r * 2 + cb], ah, bl0, bl1);
+            mma_tf32(S[r * 2 + cb], ah, bh0, bh1);
           }
       }
       if (stage == nchunk - 1) {
         // ---------------- masked softmax over the 81 in-window keys ----------------
-        float m0 = -INFINITY, m1 = -INFINITY;   // rows g and g+8
+        float m0 = -INFINITY, m1 = -INFINITY;   // fragment rows g (query row wy) and g+8 (query row wy+1)
 #pragma unroll
-        for (int b = 0; b < 27; ++b) {
-          const int cb = b % 3;
+        for (int b = 0; b < 20; ++b) {
+          const int r = b >> 1, cb = b & 1;
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
-            const int kc = cb * 8 + 2 * t + j;
-            const int d0 = kc - g, d1 = kc - (g + 8);
-            S[b][j] = (d0 >= 0 && d0 <= 8) ? S[b][j] * scale : -INFINITY;
-            S[b][2 + j] = (d1 >= 0 && d1 <= 8) ? S[b][2 + j] * scale : -INFINITY;
+            const int d = cb * 8 + 2 * t + j - g;               // key column - query column + 4
+            const bool colok = d >= 0 && d <= 8;
+            S[b][j] = (colok && r <= 8) ? S[b][j] * scale : -INFINITY;
+            S[b][2 + j] = (colok && r >= 1) ? S[b][2 + j] * scale : -INFINITY;
             m0 = fmaxf(m0, S[b][j]);
             m1 = fmaxf(m1, S[b][2 + j]);
           }
@@ -277,7 +280,7 @@ lcab_window_mma_kernel(const float* __restrict__ q, int ldq, const float* __rest
         m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
         float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-        for (int b = 0; b < 27; ++b)
+        for (int b = 0; b < 20; ++b)
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
             S[b][j] = expf(S[b][j] - m0);            // exp(-inf) = 0 for out-of-window entries
@@ -291,7 +294,7 @@ lcab_window_mma_kernel(const float* __restrict__ q, int ldq, const float* __rest
         s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
         const float i0 = 1.f / s0, i1 = 1.f / s1;
 #pragma unroll
-        for (int b = 0; b < 27; ++b) {
+        for (int b = 0; b < 20; ++b) {
           S[b][0] *= i0; S[b][1] *= i0; S[b][2] *= i1; S[b][3] *= i1;
         }
       }
@@ -301,16 +304,16 @@ lcab_window_mma_kernel(const float* __restrict__ q, int ldq, const float* __rest
 #pragma unroll
       for (int nb = 0; nb < MCH / 8; ++nb) O[nb][0] = O[nb][1] = O[nb][2] = O[nb][3] = 0.f;
 #pragma unroll
-      for (int r = 0; r < 9; ++r)
+      for (int r = 0; r < 10; ++r)
 #pragma unroll
-        for (int cb = 0; cb < 3; ++cb) {
-          const int b = r * 3 + cb;
+        for (int cb = 0; cb < 2; ++cb) {
+          const int b = r * 2 + cb;
           uint32_t ah[4], al[4];                       // A = P block with k-index t <-> key 2t, t+4 <-> key 2t+1
           split_tf32(S[b][0], ah[0], al[0]);
           split_tf32(S[b][2], ah[1], al[1]);
           split_tf32(S[b][1], ah[2], al[2]);
           split_tf32(S[b][3], ah[3], al[3]);
-          const float* vp = kv + ((warp + r) * MT_COLS + cb * 8 + 2 * t) * MSTR + g;
+          const float* vp = kv + ((wy + r) * MT_COLS + wx + cb * 8 + 2 * t) * MSTR + g;
 #pragma unroll
           for (int nb = 0; nb < MCH / 8; ++nb) {
             uint32_t bh0, bl0, bh1, bl1;
@@ -321,12 +324,13 @@ lcab_window_mma_kernel(const float* __restrict__ q, int ldq, const float* __rest
             mma_tf32(O[nb], ah, bh0, bh1);
           }
         }
-      const int qy = y0 + warp, cbase = (stage - nchunk) * MCH;
-      if (qy < H) {
+      const int cbase = (stage - nchunk) * MCH;
+      const int qx = x0 + wx + g;
+      if (qx < W) {
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-          const int qx = x0 + g + half * 8;
-          if (qx < W) {
+          const int qy = y0 + wy + half;
+          if (qy < H) {
             float* o = out + (img_off + (size_t)qy * W + qx) * ldo + cbase + 2 * t;
 #pragma unroll
             for (int nb = 0; nb < MCH / 8; ++nb)
@@ -338,7 +342,6 @@ lcab_window_mma_kernel(const float* __restrict__ q, int ldq, const float* __rest
     __syncthreads();
   }
 }
-
 
 // ------------------------------------------------------------------------------------------------
 // Unfused NCHW window ops with the exact contract of the reference extension `localattention`
