@@ -118,6 +118,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// optional pipeline trace (CTA 0 only): clock64 stamps per role and chunk, read back with di_tc_debug_read
+constexpr int DBG_SLOTS = 8, DBG_N = 512;
+__device__ long long g_dbg[DBG_SLOTS * DBG_N];
+#define DBG_STAMP(slot, i)                                                            \
+  do {                                                                               \
+    if (p.dbg && blockIdx.x == 0 && (i) < DBG_N) g_dbg[(slot) * DBG_N + (i)] = clock64(); \
+  } while (0)
+
 struct TcParams {
   int M, N;                 // logical output size (rows, columns)
   int nsrc;                 // linear: number of A sources (1..3)
@@ -130,6 +138,7 @@ struct TcParams {
   const float* bias;
   const float* res;
   int ldres, res_mod, act;
+  int dbg;
 };
 
 // Persistent, warp-specialised: each CTA loops over output tiles (tile = m_tile * n_tiles + n_tile).  The four
@@ -219,6 +228,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         for (int kc_all = 0; kc_all < nk; ++kc_all, ++it) {
           const int s = it % STAGES;
           if (it >= STAGES) mbar_wait(empty(s), ((it / STAGES) - 1) & 1);
+          DBG_STAMP(0, it);                          // producer: slot free, issuing TMA
           const uint32_t st = base + s * STAGE_BYTES;
           mbar_expect_tx(full(s), 3 * A_BYTES);
           if (p.conv) {
@@ -251,6 +261,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         mbar_wait(split(s), (it / STAGES) & 1);     // implies the TMA bytes landed and A_hi/A_lo are written
         tc_fence_after();
         if (lane == 0) {
+          DBG_STAMP(3, it);                          // mma: operands ready
           const uint32_t st = base + s * STAGE_BYTES;
 #pragma unroll
           for (int k = 0; k < TK / 8; ++k) {
@@ -262,6 +273,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           }
           umma_commit(empty(s));                      // stage reusable once these MMAs retire
           if (kc_all == nk - 1) umma_commit(acc_full(a));
+          DBG_STAMP(4, it);                          // mma: issued + committed
         }
         __syncwarp();
       }
@@ -274,6 +286,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       for (int kc_all = 0; kc_all < nk; ++kc_all, ++it) {
         const int s = it % STAGES;
         mbar_wait(full(s), (it / STAGES) & 1);
+        if (et == 0) DBG_STAMP(1, it);               // splitter: TMA bytes landed
         float4* hi = reinterpret_cast<float4*>(base_ptr + s * STAGE_BYTES);
         float4* lo = reinterpret_cast<float4*>(base_ptr + s * STAGE_BYTES + A_BYTES);
 #pragma unroll
@@ -290,6 +303,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
         __syncwarp();
         if (lane == 0) mbar_arrive(split(s));
+        if (et == 0) DBG_STAMP(2, it);               // splitter: done
       }
     }
   } else {
@@ -303,6 +317,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       const int a = tl & 1;
       mbar_wait(acc_full(a), (tl >> 1) & 1);
       tc_fence_after();
+      if (threadIdx.x == 192) DBG_STAMP(5, tl);      // epilogue: accumulator ready
       long long grow;
       bool ok;
       if (p.conv) {
@@ -360,6 +375,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty(a));
+      if (threadIdx.x == 192) DBG_STAMP(6, tl);      // epilogue: tile stored
     }
   }
   tc_fence_before();
@@ -413,6 +429,7 @@ bool make_map_nhwc(CUtensorMap* m, const float* ptr, int N, int H, int W, int C)
 }
 
 bool g_attr_set = false;
+int g_tc_debug = 0;
 
 int launch_tc(const CUtensorMap maps[5], const TcParams& p, cudaStream_t stream, const char* name) {
   if (g_num_sms == 0) {
@@ -440,6 +457,21 @@ inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) =
 }  // namespace
 
 extern "C" {
+
+// Pipeline trace of CTA 0 (diagnostics): enable, run ONE tensor-core launch, then read 8 x 512 clock64 stamps
+// (rows: 0 producer issue, 1 bytes landed, 2 split done, 3 mma ready, 4 mma issued, 5 acc ready, 6 tile stored).
+int di_tc_set_debug(int on) {
+  g_tc_debug = on;
+  return DI_OK;
+}
+int di_tc_debug_read(long long* host_buf) {
+  DI_CHECK_ARG(host_buf, "di_tc_debug_read: null buffer");
+  if (cudaMemcpyFromSymbol(host_buf, g_dbg, sizeof(long long) * DBG_SLOTS * DBG_N) != cudaSuccess) {
+    di_set_error("di_tc_debug_read: copy failed");
+    return DI_ERR_LAUNCH;
+  }
+  return DI_OK;
+}
 
 // Tensor-core (3xTF32, tcgen05 + TMA) version of di_linear_f32.  W_hi / W_lo: the [N, K0+K1+K2] weight split on
 // the host (hi = round-to-tf32, lo = W - hi).  Constraints: every K_s % 32 == 0, lda % 4 == 0, 16-byte aligned
@@ -476,7 +508,7 @@ int di_linear_tc_f32(const float* A0, int lda0, int K0, const float* A1, int lda
   p.M = M; p.N = N; p.nsrc = nsrc;
   for (int s = 0; s < 3; ++s) p.kchunks[s] = Ks[s] / TK;
   p.conv = 0; p.C = C; p.ldc = ldc; p.bias = bias; p.res = res; p.ldres = ldres;
-  p.res_mod = res_mod > 0 ? res_mod : M; p.act = act;
+  p.res_mod = res_mod > 0 ? res_mod : M; p.act = act; p.dbg = g_tc_debug;
   p.m_tiles = di_cdiv(M, TM);
   p.n_tiles = di_cdiv(N, TN);
   return launch_tc(maps, p, stream, "di_linear_tc_f32");
@@ -506,7 +538,7 @@ int di_conv3x3_tc_f32(const float* x, const float* w_hi, const float* w_lo, cons
   TcParams p{};
   p.M = N * H * W; p.N = Cout; p.nsrc = 1; p.kchunks[0] = Cin / TK; p.conv = 1; p.H = H; p.W = W;
   p.tiles_x = di_cdiv(W, 16); p.tiles_y = di_cdiv(H, 8);
-  p.C = y; p.ldc = Cout; p.bias = bias; p.res = nullptr; p.ldres = 0; p.res_mod = 1; p.act = act;
+  p.C = y; p.ldc = Cout; p.bias = bias; p.res = nullptr; p.ldres = 0; p.res_mod = 1; p.act = act; p.dbg = g_tc_debug;
   p.m_tiles = N * p.tiles_x * p.tiles_y;
   p.n_tiles = di_cdiv(Cout, TN);
   return launch_tc(maps, p, stream, "di_conv3x3_tc_f32");

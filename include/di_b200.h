@@ -65,6 +65,10 @@ int di_linear_tc_f32(const float* A0, int lda0, int K0, const float* A1, int lda
 int di_conv3x3_tc_f32(const float* x, const float* w_hi, const float* w_lo, const float* bias, float* y, int N, int Cin,
                       int H, int W, int Cout, int act, cudaStream_t stream);
 
+/* diagnostics: clock64 pipeline trace of CTA 0 of the next tensor-core launch (8 x 512 stamps) */
+int di_tc_set_debug(int on);
+int di_tc_debug_read(long long* host_buf);
+
 /* ---- local-window attention (lcab.cu) ---------------------------------------------------------- */
 
 /* out = weighting(v, softmax(similar(q, k) / sqrt(C))) over a ksize x ksize window, fused
