@@ -18,9 +18,9 @@
 //               (elementwise, so the swizzle is irrelevant), fence.proxy.async, arrive
 //   warp 1      MMA issuer: 4 k-steps x 3 products of tcgen05.mma.kind::tf32 (M=128,N=128,K=8) per chunk,
 //               tcgen05.commit frees the stage; accumulator = 128 TMEM columns
-//   warps 6-9   epilogue: tcgen05.ld (32 lanes x 32 columns per warp and step) -> bias/res/activation -> each
-//               thread streams its row as 128-byte runs; overlaps the next tile's main loop through a
-//               double-buffered TMEM accumulator (2 x 128 columns)
+//   warps 6-9   epilogue: tcgen05.ld (32 lanes x 32 columns per warp and step) -> bias/res/activation -> 128B-
+//               swizzled staging tile in shared memory -> cp.async.bulk.tensor store (coalesced, asynchronous);
+//               overlaps the next tile's main loop through a double-buffered TMEM accumulator (2 x 128 columns)
 #include "common.cuh"
 #include <cuda.h>
 
@@ -31,7 +31,8 @@ constexpr int STAGES = 3;
 constexpr int A_BYTES = TM * TK * 4;                // 16 KB
 constexpr int STAGE_BYTES = 4 * A_BYTES;            // A_hi | A_lo | W_hi | W_lo
 constexpr int NTHREADS = 320;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int EP_BYTES = 4 /*warps*/ * 2 /*buffers*/ * 32 * 128;   // epilogue staging: 32 rows x 128 B per buffer
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EP_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 int g_num_sms = 0;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -72,6 +73,19 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
           dst),
       "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
+}
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
 }
 
 // L2 prefetch of a future box (no shared-memory footprint): raises the bytes in flight beyond the 3-stage ring
@@ -148,11 +162,13 @@ struct TcParams {
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapWhi,
-               const __grid_constant__ CUtensorMap mapWlo, const TcParams p) {
+               const __grid_constant__ CUtensorMap mapWlo, const __grid_constant__ CUtensorMap mapC,
+               const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;        // SWIZZLE_128B needs 1024-byte alignment
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t bars = base + STAGES * STAGE_BYTES;
+  const uint32_t ep_base = base + STAGES * STAGE_BYTES;              // epilogue staging (1024-byte aligned)
+  const uint32_t bars = ep_base + EP_BYTES;
   auto full = [&](int s) { return bars + 8u * s; };
   auto split = [&](int s) { return bars + 8u * (STAGES + s); };
   auto empty = [&](int s) { return bars + 8u * (2 * STAGES + s); };
@@ -160,7 +176,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   auto acc_empty = [&](int a) { return bars + 8u * (3 * STAGES + 2 + a); };
   const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 4);
   volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(base_ptr + STAGES * STAGE_BYTES + 8 * (3 * STAGES + 4));
+      reinterpret_cast<volatile uint32_t*>(base_ptr + STAGES * STAGE_BYTES + EP_BYTES + 8 * (3 * STAGES + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int nk = 0;
@@ -307,10 +323,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       }
     }
   } else {
-    // ---------------- epilogue (warps 6..9, 128 threads): TMEM -> registers -> global ----------------
+    // ---------------- epilogue (warps 6..9): TMEM -> registers -> swizzled smem -> TMA store ----------------
     const int q = warp & 3;                          // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;                   // tile row held by this thread
-    int tl = 0;
+    const uint32_t my_ep = ep_base + (uint32_t)((warp - 6) * 2) * 4096u;
+    uint8_t* my_ep_ptr = base_ptr + STAGES * STAGE_BYTES + (warp - 6) * 2 * 4096;
+    int tl = 0, chunk = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
       int m0, n0, img, y0, x0;
       tile_coords(tile, m0, n0, img, y0, x0);
@@ -319,21 +337,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       tc_fence_after();
       if (threadIdx.x == 192) DBG_STAMP(5, tl);      // epilogue: accumulator ready
       long long grow;
-      bool ok;
       if (p.conv) {
-        const int yy = y0 + row / 16, xx = x0 + row % 16;
-        ok = yy < p.H && xx < p.W;
+        const int yy = min(y0 + row / 16, p.H - 1), xx = min(x0 + row % 16, p.W - 1);
         grow = ((long long)img * p.H + yy) * p.W + xx;
       } else {
-        grow = m0 + row;
-        ok = grow < p.M;
+        grow = min((long long)(m0 + row), (long long)p.M - 1);
       }
-      const float* resrow = (p.res && ok) ? p.res + (size_t)(grow % p.res_mod) * p.ldres : nullptr;
-      float* crow = p.C + (size_t)(ok ? grow : 0) * p.ldc;
+      const float* resrow = p.res ? p.res + (size_t)(grow % p.res_mod) * p.ldres : nullptr;
 #pragma unroll 1
-      for (int c0 = 0; c0 < TN; c0 += 32) {
-        float v[32];
+      for (int c0 = 0; c0 < TN; c0 += 32, ++chunk) {
         const int col = n0 + c0;
+        if (col >= p.N) break;                       // warp-uniform: nothing to store in this column block
         const bool fullc = col + 32 <= p.N;
         float4 bv[8];
         if (p.bias && fullc) {                       // issue the (L1-resident) bias loads before the TMEM wait
@@ -341,42 +355,55 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           for (int j = 0; j < 8; ++j) bv[j] = ldg4(p.bias + col + 4 * j);
         } else {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) bv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int j = 0; j < 8; ++j) {
+            bv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias) {
+              if (col + 4 * j + 0 < p.N) bv[j].x = __ldg(p.bias + col + 4 * j + 0);
+              if (col + 4 * j + 1 < p.N) bv[j].y = __ldg(p.bias + col + 4 * j + 1);
+              if (col + 4 * j + 2 < p.N) bv[j].z = __ldg(p.bias + col + 4 * j + 2);
+              if (col + 4 * j + 3 < p.N) bv[j].w = __ldg(p.bias + col + 4 * j + 3);
+            }
+          }
         }
+        float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TN + c0), v);   // warp-collective
-        if (!ok || col >= p.N) continue;
-        if (fullc) {
+        // the staging buffer used two chunks ago must have been read by its TMA store
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
+        const uint32_t buf = (uint32_t)(chunk & 1) * 4096u;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            {
-              const float4 b4 = bv[j >> 2];
-              o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
-            }
-            if (resrow) {
-              const float4 r4 = ldg4(resrow + col + j);
+        for (int j = 0; j < 8; ++j) {
+          float4 o = make_float4(v[4 * j] + bv[j].x, v[4 * j + 1] + bv[j].y, v[4 * j + 2] + bv[j].z,
+                                 v[4 * j + 3] + bv[j].w);
+          if (resrow) {
+            if (fullc) {
+              const float4 r4 = ldg4(resrow + col + 4 * j);
               o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
-            }
-            o.x = di_act(o.x, p.act); o.y = di_act(o.y, p.act); o.z = di_act(o.z, p.act); o.w = di_act(o.w, p.act);
-            *reinterpret_cast<float4*>(crow + col + j) = o;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (col + j < p.N) {
-              float t = v[j];
-              if (p.bias) t += __ldg(p.bias + col + j);
-              if (resrow) t += __ldg(resrow + col + j);
-              crow[col + j] = di_act(t, p.act);
+            } else {
+              if (col + 4 * j + 0 < p.N) o.x += __ldg(resrow + col + 4 * j + 0);
+              if (col + 4 * j + 1 < p.N) o.y += __ldg(resrow + col + 4 * j + 1);
+              if (col + 4 * j + 2 < p.N) o.z += __ldg(resrow + col + 4 * j + 2);
+              if (col + 4 * j + 3 < p.N) o.w += __ldg(resrow + col + 4 * j + 3);
             }
           }
+          o.x = di_act(o.x, p.act); o.y = di_act(o.y, p.act); o.z = di_act(o.z, p.act); o.w = di_act(o.w, p.act);
+          // 128B swizzle of the staging tile: 16-byte unit j of row r lives at unit j ^ (r & 7)
+          *reinterpret_cast<float4*>(my_ep_ptr + buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          if (p.conv) tma_store_4d(&mapC, my_ep + buf, col, x0, y0 + 2 * q, img);
+          else tma_store_2d(&mapC, my_ep + buf, col, m0 + 32 * q);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty(a));
-      if (threadIdx.x == 192) DBG_STAMP(6, tl);      // epilogue: tile stored
+      if (threadIdx.x == 192) DBG_STAMP(6, tl);      // epilogue: tile handed to the TMA store engine
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores retired before exit
   }
   tc_fence_before();
   __syncthreads();
@@ -428,10 +455,32 @@ bool make_map_nhwc(CUtensorMap* m, const float* ptr, int N, int H, int W, int C)
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// store maps: 2-D [rows, cols] box 32 x 32, or 4-D NHWC box 32 ch x 16 x 2 x 1 (one epilogue warp's rows)
+bool make_store_map_2d(CUtensorMap* m, float* ptr, long long rows, long long cols, long long ld) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+bool make_store_map_nhwc(CUtensorMap* m, float* ptr, int N, int H, int W, int C) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+  cuuint32_t box[4] = {32, 16, 2, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 bool g_attr_set = false;
 int g_tc_debug = 0;
 
-int launch_tc(const CUtensorMap maps[5], const TcParams& p, cudaStream_t stream, const char* name) {
+int launch_tc(const CUtensorMap maps[6], const TcParams& p, cudaStream_t stream, const char* name) {
   if (g_num_sms == 0) {
     int devid = 0;
     cudaGetDevice(&devid);
@@ -447,7 +496,7 @@ int launch_tc(const CUtensorMap maps[5], const TcParams& p, cudaStream_t stream,
     }
     g_attr_set = true;
   }
-  gemm_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
+  gemm_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
   DI_CHECK_LAUNCH(name);
   return DI_OK;
 }
@@ -492,7 +541,11 @@ int di_linear_tc_f32(const float* A0, int lda0, int K0, const float* A1, int lda
     di_set_error("di_linear_tc_f32: shape/alignment not supported by the tensor-core path");
     return DI_ERR_UNSUPPORTED;
   }
-  CUtensorMap maps[5];
+  CUtensorMap maps[6];
+  if (!make_store_map_2d(&maps[5], C, M, N, ldc)) {
+    di_set_error("di_linear_tc_f32: cuTensorMapEncodeTiled failed for C");
+    return DI_ERR_LAUNCH;
+  }
   for (int s = 0; s < 3; ++s) {
     int u = s < nsrc ? s : 0;
     if (!make_map_2d(&maps[s], As[u], M, Ks[u], lds[u])) {
@@ -523,7 +576,11 @@ int di_conv3x3_tc_f32(const float* x, const float* w_hi, const float* w_lo, cons
     di_set_error("di_conv3x3_tc_f32: shape/alignment not supported by the tensor-core path");
     return DI_ERR_UNSUPPORTED;
   }
-  CUtensorMap maps[5];
+  CUtensorMap maps[6];
+  if (!make_store_map_nhwc(&maps[5], y, N, H, W, Cout)) {
+    di_set_error("di_conv3x3_tc_f32: cuTensorMapEncodeTiled failed for y");
+    return DI_ERR_LAUNCH;
+  }
   if (!make_map_nhwc(&maps[0], x, N, H, W, Cin)) {
     di_set_error("di_conv3x3_tc_f32: cuTensorMapEncodeTiled failed for x");
     return DI_ERR_LAUNCH;
