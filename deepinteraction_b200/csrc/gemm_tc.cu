@@ -32,7 +32,7 @@ constexpr int A_BYTES = TM * TK * 4;                // 16 KB
 constexpr int STAGE_BYTES = 4 * A_BYTES;            // A_hi | A_lo | W_hi | W_lo
 constexpr int NTHREADS = 320;
 constexpr int EP_BYTES = 4 /*warps*/ * 2 /*buffers*/ * 32 * 128;   // epilogue staging: 32 rows x 128 B per buffer
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EP_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EP_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 512 /*bias*/;
 int g_num_sms = 0;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -328,10 +328,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const int row = q * 32 + lane;                   // tile row held by this thread
     const uint32_t my_ep = ep_base + (uint32_t)((warp - 6) * 2) * 4096u;
     uint8_t* my_ep_ptr = base_ptr + STAGES * STAGE_BYTES + (warp - 6) * 2 * 4096;
-    int tl = 0, chunk = 0;
+    // bias slice of the current column tile lives in shared memory: a global (even L2-resident) load in the
+    // epilogue's dependency chain costs ~2000 cycles per 32-column step under TMA load
+    float* bias_s = reinterpret_cast<float*>(base_ptr + STAGES * STAGE_BYTES + EP_BYTES + 256);
+    int tl = 0, chunk = 0, bias_n0 = -1;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
       int m0, n0, img, y0, x0;
       tile_coords(tile, m0, n0, img, y0, x0);
+      if (n0 != bias_n0) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");          // previous tile's readers are done
+        const int c = n0 + (int)threadIdx.x - 192;
+        bias_s[threadIdx.x - 192] = (p.bias && c < p.N) ? __ldg(p.bias + c) : 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        bias_n0 = n0;
+      }
       const int a = tl & 1;
       mbar_wait(acc_full(a), (tl >> 1) & 1);
       tc_fence_after();
@@ -349,32 +359,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const int col = n0 + c0;
         if (col >= p.N) break;                       // warp-uniform: nothing to store in this column block
         const bool fullc = col + 32 <= p.N;
-        float4 bv[8];
-        if (p.bias && fullc) {                       // issue the (L1-resident) bias loads before the TMEM wait
-#pragma unroll
-          for (int j = 0; j < 8; ++j) bv[j] = ldg4(p.bias + col + 4 * j);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            bv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.bias) {
-              if (col + 4 * j + 0 < p.N) bv[j].x = __ldg(p.bias + col + 4 * j + 0);
-              if (col + 4 * j + 1 < p.N) bv[j].y = __ldg(p.bias + col + 4 * j + 1);
-              if (col + 4 * j + 2 < p.N) bv[j].z = __ldg(p.bias + col + 4 * j + 2);
-              if (col + 4 * j + 3 < p.N) bv[j].w = __ldg(p.bias + col + 4 * j + 3);
-            }
-          }
-        }
         float v[32];
+        if (threadIdx.x == 192) DBG_STAMP(7, chunk * 4 + 0);
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TN + c0), v);   // warp-collective
+        if (threadIdx.x == 192) DBG_STAMP(7, chunk * 4 + 1);
         // the staging buffer used two chunks ago must have been read by its TMA store
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         __syncwarp();
         const uint32_t buf = (uint32_t)(chunk & 1) * 4096u;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          float4 o = make_float4(v[4 * j] + bv[j].x, v[4 * j + 1] + bv[j].y, v[4 * j + 2] + bv[j].z,
-                                 v[4 * j + 3] + bv[j].w);
+          const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + 4 * j);      // broadcast LDS
+          float4 o = make_float4(v[4 * j] + b4.x, v[4 * j + 1] + b4.y, v[4 * j + 2] + b4.z, v[4 * j + 3] + b4.w);
           if (resrow) {
             if (fullc) {
               const float4 r4 = ldg4(resrow + col + 4 * j);
@@ -390,8 +386,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           // 128B swizzle of the staging tile: 16-byte unit j of row r lives at unit j ^ (r & 7)
           *reinterpret_cast<float4*>(my_ep_ptr + buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
         }
+        if (threadIdx.x == 192) DBG_STAMP(7, chunk * 4 + 2);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
+        if (threadIdx.x == 192) DBG_STAMP(7, chunk * 4 + 3);
         if (lane == 0) {
           if (p.conv) tma_store_4d(&mapC, my_ep + buf, col, x0, y0 + 2 * q, img);
           else tma_store_2d(&mapC, my_ep + buf, col, m0 + 32 * q);

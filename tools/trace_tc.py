@@ -7,7 +7,7 @@ from deepinteraction_b200 import ops, fold, _lib
 
 L = _lib.lib()
 dev = torch.device('cuda:0')
-for (M, N, K) in [(134400, 128, 128), (134400, 384, 128), (134400, 128, 384)]:
+for (M, N, K) in [(134400, 128, 128)]:
     A = torch.randn(M, K, device=dev)
     W = fold.Weight(torch.randn(N, K) / 11, dev)
     b = torch.randn(N, device=dev)
@@ -34,5 +34,8 @@ for (M, N, K) in [(134400, 128, 128), (134400, 384, 128), (134400, 128, 384)]:
     names = ['issue', 'landed', 'split', 'mma_rdy', 'mma_iss']
     for it in range(min(nk * ntile, 40)):
         print(it, ' '.join(f'{names[r]}={int(t[r, it] - t0):7d}' for r in range(5)))
+    for ch in range(12):
+        print('epi chunk', ch, 'pre_ld', int(t[7, ch * 4] - t0), 'post_ld', int(t[7, ch * 4 + 1] - t0), 'post_sts',
+              int(t[7, ch * 4 + 2] - t0), 'post_fence', int(t[7, ch * 4 + 3] - t0))
     for tl in range(ntile):
         print('tile', tl, 'acc_ready', int(t[5, tl] - t0), 'stored', int(t[6, tl] - t0))
