@@ -361,8 +361,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const bool fullc = col + 32 <= p.N;
         float v[32];
         if (threadIdx.x == 192) DBG_STAMP(7, chunk * 4 + 0);
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TN + c0), v);   // warp-collective
+        if (p.dbg & 2) {                              // experiment: skip the TMEM read
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 1.f;
+        } else {
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TN + c0), v);   // warp-collective
+        }
         if (threadIdx.x == 192) DBG_STAMP(7, chunk * 4 + 1);
+        if (p.dbg & 4) continue;                      // experiment: skip staging + store
         // the staging buffer used two chunks ago must have been read by its TMA store
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         __syncwarp();
@@ -408,6 +414,291 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// v3: A operand through TENSOR MEMORY.  Shared-memory bandwidth is the limiter of the 3xTF32 scheme (every
+// k-step re-reads A_hi twice, A_lo once and W_hi twice, W_lo once from shared memory, on top of the TMA writes,
+// the splitter's round trip and the epilogue staging -- measured 896 KB of smem traffic per 128x128x128 tile).
+// Here the splitter reads the landed A chunk once, and writes A_hi / A_lo with tcgen05.st into TMEM; the MMA
+// takes A from TMEM ([a_tmem]) and only W from shared memory.  That removes the A_hi/A_lo write-back (128 KB
+// per tile) and the A operand reads (192 KB per tile), and frees room for a 4th pipeline stage.
+//   TMEM columns: [0,128) acc0 | [128,256) acc1 | [256,320) A buffer 0 (hi 32 | lo 32) | [320,384) A buffer 1
+// ------------------------------------------------------------------------------------------------
+constexpr int V3_STAGES = 4;
+constexpr int V3_STAGE_BYTES = 3 * A_BYTES;          // A landing | W_hi | W_lo
+constexpr int V3_SMEM_BYTES = V3_STAGES * V3_STAGE_BYTES + EP_BYTES + 1024 + 256 + 512;
+
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(
+          tmem_d),
+      "r"(tmem_a), "l"(db), "r"(IDESC), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+                  const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapWhi,
+                  const __grid_constant__ CUtensorMap mapWlo, const __grid_constant__ CUtensorMap mapC,
+                  const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  constexpr int S = V3_STAGES;
+  const uint32_t ep_base = base + S * V3_STAGE_BYTES;
+  const uint32_t bars = ep_base + EP_BYTES;
+  auto full = [&](int s) { return bars + 8u * s; };
+  auto empty = [&](int s) { return bars + 8u * (S + s); };
+  auto a_ready = [&](int b) { return bars + 8u * (2 * S + b); };
+  auto a_free = [&](int b) { return bars + 8u * (2 * S + 2 + b); };
+  auto acc_full = [&](int a) { return bars + 8u * (2 * S + 4 + a); };
+  auto acc_empty = [&](int a) { return bars + 8u * (2 * S + 6 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * S + 8);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(base_ptr + S * V3_STAGE_BYTES + EP_BYTES + 8 * (2 * S + 8));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int nk = 0;
+  if (p.conv) nk = 9 * p.kchunks[0];
+  else
+    for (int s = 0; s < p.nsrc; ++s) nk += p.kchunks[s];
+  const int num_tiles = p.m_tiles * p.n_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full(s), 1);
+      mbar_init(empty(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(a_ready(b), 4);
+      mbar_init(a_free(b), 1);
+      mbar_init(acc_full(b), 1);
+      mbar_init(acc_empty(b), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  auto tile_coords = [&](int tile, int& m0, int& n0, int& img, int& y0, int& x0) {
+    const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+    n0 = nt * TN;
+    m0 = mt * TM;
+    img = 0; y0 = 0; x0 = 0;
+    if (p.conv) {
+      int t = mt;
+      img = t / (p.tiles_x * p.tiles_y);
+      t -= img * p.tiles_x * p.tiles_y;
+      y0 = (t / p.tiles_x) * 8;
+      x0 = (t % p.tiles_x) * 16;
+    }
+  };
+
+  if (warp == 0) {
+    // ---------------- TMA producer ----------------
+    if (lane == 0) {
+      int it = 0;
+      auto prefetch_tile = [&](int tile) {
+        if (p.conv || tile >= num_tiles) return;
+        const int mt = tile / p.n_tiles;
+        if (tile - mt * p.n_tiles != 0 && mt == (tile - 1) / p.n_tiles) return;
+        for (int src = 0; src < p.nsrc; ++src)
+          for (int kc = 0; kc < p.kchunks[src]; ++kc) {
+            const CUtensorMap* mp = src == 0 ? &mapA0 : (src == 1 ? &mapA1 : &mapA2);
+            tma_prefetch_2d(mp, kc * TK, mt * TM);
+          }
+      };
+      constexpr int PF = 2;
+      for (int r = 1; r <= PF; ++r) prefetch_tile(blockIdx.x + r * gridDim.x);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int m0, n0, img, y0, x0;
+        tile_coords(tile, m0, n0, img, y0, x0);
+        prefetch_tile(tile + (PF + 1) * gridDim.x);
+        for (int kc_all = 0; kc_all < nk; ++kc_all, ++it) {
+          const int s = it % S;
+          if (it >= S) mbar_wait(empty(s), ((it / S) - 1) & 1);
+          DBG_STAMP(0, it);
+          const uint32_t st = base + s * V3_STAGE_BYTES;
+          mbar_expect_tx(full(s), 3 * A_BYTES);
+          if (p.conv) {
+            const int tap = kc_all / p.kchunks[0], kc = kc_all - tap * p.kchunks[0];
+            tma_load_4d(st, &mapA0, full(s), kc * TK, x0 + tap % 3 - 1, y0 + tap / 3 - 1, img);
+          } else {
+            int src = 0, kc = kc_all;
+            while (kc >= p.kchunks[src]) {
+              kc -= p.kchunks[src];
+              ++src;
+            }
+            const CUtensorMap* mp = src == 0 ? &mapA0 : (src == 1 ? &mapA1 : &mapA2);
+            tma_load_2d(st, mp, full(s), kc * TK, m0);
+          }
+          tma_load_2d(st + A_BYTES, &mapWhi, full(s), kc_all * TK, n0);
+          tma_load_2d(st + 2 * A_BYTES, &mapWlo, full(s), kc_all * TK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer: A from TMEM, W from shared memory ----------------
+    int it = 0, tl = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+      const int a = tl & 1;
+      if (tl >= 2) mbar_wait(acc_empty(a), ((tl >> 1) - 1) & 1);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(a * TN);
+      for (int kc_all = 0; kc_all < nk; ++kc_all, ++it) {
+        const int s = it % S, b = it & 1;
+        mbar_wait(a_ready(b), (it >> 1) & 1);       // A_hi/A_lo of this chunk are in TMEM (implies full[s])
+        tc_fence_after();
+        if (lane == 0) {
+          DBG_STAMP(3, it);
+          const uint32_t st = base + s * V3_STAGE_BYTES;
+          const uint32_t ta = tmem_base + 256u + (uint32_t)(b * 64);
+#pragma unroll
+          for (int k = 0; k < TK / 8; ++k) {
+            const uint64_t w_hi = umma_desc(st + A_BYTES + k * 32), w_lo = umma_desc(st + 2 * A_BYTES + k * 32);
+            umma_tf32_ts(tmem_acc, ta + 32u + (uint32_t)(k * 8), w_hi, (kc_all | k) != 0);   // A_lo * W_hi
+            umma_tf32_ts(tmem_acc, ta + (uint32_t)(k * 8), w_lo, 1);                          // A_hi * W_lo
+            umma_tf32_ts(tmem_acc, ta + (uint32_t)(k * 8), w_hi, 1);                          // A_hi * W_hi
+          }
+          umma_commit(empty(s));
+          umma_commit(a_free(b));
+          if (kc_all == nk - 1) umma_commit(acc_full(a));
+          DBG_STAMP(4, it);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < 6) {
+    // ---------------- splitter (warps 2..5): smem A chunk -> registers -> hi/lo -> TMEM ----------------
+    const int qd = warp & 3;                          // TMEM lane quarter of this warp
+    const int row = qd * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int kc_all = 0; kc_all < nk; ++kc_all, ++it) {
+        const int s = it % S, b = it & 1;
+        mbar_wait(full(s), (it / S) & 1);
+        if (threadIdx.x == 64) DBG_STAMP(1, it);
+        const uint8_t* arow = base_ptr + s * V3_STAGE_BYTES + row * 128;
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 x = *reinterpret_cast<const float4*>(arow + ((j ^ (row & 7)) << 4));   // undo the 128B swizzle
+          const float xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            hi[4 * j + e] = __float_as_uint(xv[e]) & 0xFFFFE000u;
+            lo[4 * j + e] = __float_as_uint(xv[e] - __uint_as_float(hi[4 * j + e]));
+          }
+        }
+        if (it >= 2) mbar_wait(a_free(b), ((it >> 1) - 1) & 1);   // MMAs that read this TMEM A buffer retired
+        tc_fence_after();
+        const uint32_t ta = tmem_base + ((uint32_t)(qd * 32) << 16) + 256u + (uint32_t)(b * 64);
+        tmem_st32(ta, hi);
+        tmem_st32(ta + 32u, lo);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_ready(b));
+        if (threadIdx.x == 64) DBG_STAMP(2, it);
+      }
+    }
+  } else {
+    // ---------------- epilogue (warps 6..9): TMEM -> registers -> swizzled smem -> TMA store ----------------
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t my_ep = ep_base + (uint32_t)((warp - 6) * 2) * 4096u;
+    uint8_t* my_ep_ptr = base_ptr + S * V3_STAGE_BYTES + (warp - 6) * 2 * 4096;
+    float* bias_s = reinterpret_cast<float*>(base_ptr + S * V3_STAGE_BYTES + EP_BYTES + 256);
+    int tl = 0, chunk = 0, bias_n0 = -1;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+      int m0, n0, img, y0, x0;
+      tile_coords(tile, m0, n0, img, y0, x0);
+      if (n0 != bias_n0) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int c = n0 + (int)threadIdx.x - 192;
+        bias_s[threadIdx.x - 192] = (p.bias && c < p.N) ? __ldg(p.bias + c) : 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        bias_n0 = n0;
+      }
+      const int a = tl & 1;
+      mbar_wait(acc_full(a), (tl >> 1) & 1);
+      tc_fence_after();
+      if (threadIdx.x == 192) DBG_STAMP(5, tl);
+      long long grow;
+      if (p.conv) {
+        const int yy = min(y0 + row / 16, p.H - 1), xx = min(x0 + row % 16, p.W - 1);
+        grow = ((long long)img * p.H + yy) * p.W + xx;
+      } else {
+        grow = min((long long)(m0 + row), (long long)p.M - 1);
+      }
+      const float* resrow = p.res ? p.res + (size_t)(grow % p.res_mod) * p.ldres : nullptr;
+#pragma unroll 1
+      for (int c0 = 0; c0 < TN; c0 += 32, ++chunk) {
+        const int col = n0 + c0;
+        if (col >= p.N) break;
+        const bool fullc = col + 32 <= p.N;
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TN + c0), v);
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
+        const uint32_t buf = (uint32_t)(chunk & 1) * 4096u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + 4 * j);
+          float4 o = make_float4(v[4 * j] + b4.x, v[4 * j + 1] + b4.y, v[4 * j + 2] + b4.z, v[4 * j + 3] + b4.w);
+          if (resrow) {
+            if (fullc) {
+              const float4 r4 = ldg4(resrow + col + 4 * j);
+              o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+            } else {
+              if (col + 4 * j + 0 < p.N) o.x += __ldg(resrow + col + 4 * j + 0);
+              if (col + 4 * j + 1 < p.N) o.y += __ldg(resrow + col + 4 * j + 1);
+              if (col + 4 * j + 2 < p.N) o.z += __ldg(resrow + col + 4 * j + 2);
+              if (col + 4 * j + 3 < p.N) o.w += __ldg(resrow + col + 4 * j + 3);
+            }
+          }
+          o.x = di_act(o.x, p.act); o.y = di_act(o.y, p.act); o.z = di_act(o.z, p.act); o.w = di_act(o.w, p.act);
+          *reinterpret_cast<float4*>(my_ep_ptr + buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          if (p.conv) tma_store_4d(&mapC, my_ep + buf, col, x0, y0 + 2 * q, img);
+          else tma_store_2d(&mapC, my_ep + buf, col, m0 + 32 * q);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(a));
+      if (threadIdx.x == 192) DBG_STAMP(6, tl);
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -475,8 +766,9 @@ bool make_store_map_nhwc(CUtensorMap* m, float* ptr, int N, int H, int W, int C)
              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-bool g_attr_set = false;
+bool g_attr_set = false, g_attr_set_v3 = false;
 int g_tc_debug = 0;
+int g_tc_mode = 3;   // 3: A operand through tensor memory (default); 2: A operand through shared memory
 
 int launch_tc(const CUtensorMap maps[6], const TcParams& p, cudaStream_t stream, const char* name) {
   if (g_num_sms == 0) {
@@ -494,7 +786,18 @@ int launch_tc(const CUtensorMap maps[6], const TcParams& p, cudaStream_t stream,
     }
     g_attr_set = true;
   }
-  gemm_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
+  if (g_tc_mode == 3) {
+    if (!g_attr_set_v3) {
+      if (cudaFuncSetAttribute(gemm_tc_kernel_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_BYTES) != cudaSuccess) {
+        di_set_error("%s: cannot reserve %d bytes of shared memory", name, V3_SMEM_BYTES);
+        return DI_ERR_LAUNCH;
+      }
+      g_attr_set_v3 = true;
+    }
+    gemm_tc_kernel_v3<<<grid, NTHREADS, V3_SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
+  } else {
+    gemm_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
+  }
   DI_CHECK_LAUNCH(name);
   return DI_OK;
 }
@@ -509,6 +812,12 @@ extern "C" {
 // (rows: 0 producer issue, 1 bytes landed, 2 split done, 3 mma ready, 4 mma issued, 5 acc ready, 6 tile stored).
 int di_tc_set_debug(int on) {
   g_tc_debug = on;
+  return DI_OK;
+}
+// 3 (default): A operand staged in tensor memory; 2: A operand in shared memory (earlier pipeline, kept for A/B tests)
+int di_tc_set_mode(int mode) {
+  DI_CHECK_ARG(mode == 2 || mode == 3, "di_tc_set_mode: mode must be 2 or 3");
+  g_tc_mode = mode;
   return DI_OK;
 }
 int di_tc_debug_read(long long* host_buf) {

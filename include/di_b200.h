@@ -67,6 +67,7 @@ int di_conv3x3_tc_f32(const float* x, const float* w_hi, const float* w_lo, cons
 
 /* diagnostics: clock64 pipeline trace of CTA 0 of the next tensor-core launch (8 x 512 stamps) */
 int di_tc_set_debug(int on);
+int di_tc_set_mode(int mode); /* 3 = A operand through tensor memory (default), 2 = through shared memory */
 int di_tc_debug_read(long long* host_buf);
 
 /* ---- local-window attention (lcab.cu) ---------------------------------------------------------- */

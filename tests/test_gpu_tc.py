@@ -14,11 +14,20 @@ def dev():
     return torch.device('cuda:0')
 
 
+@pytest.fixture(params=[3, 2], ids=['A-via-TMEM', 'A-via-smem'])
+def tc_mode(request):
+    """Both tensor-core pipelines: v3 stages the A operand in tensor memory, v2 keeps it in shared memory."""
+    from deepinteraction_b200 import _lib
+    _lib.check(_lib.lib().di_tc_set_mode(request.param))
+    yield request.param
+    _lib.lib().di_tc_set_mode(3)
+
+
 @pytest.mark.parametrize('M,N,Ks,act,use_res', [
     (128, 128, [128], 1, False), (1000, 128, [128], 0, False), (32400, 128, [128, 128, 128], 0, False),
     (777, 384, [128], 1, False), (4096, 256, [64, 32], 2, True), (200, 32768, [128], 0, False),
     (300, 20, [384], 0, False), (50001, 128, [256], 1, True)])
-def test_linear_tc_matches_float64(M, N, Ks, act, use_res):
+def test_linear_tc_matches_float64(M, N, Ks, act, use_res, tc_mode):
     from deepinteraction_b200 import ops, fold
     g = torch.Generator().manual_seed(M + N)
     srcs = [torch.randn(M, k, generator=g) * (1 + i) for i, k in enumerate(Ks)]
@@ -59,7 +68,7 @@ def test_linear_tc_strided_sources_and_ffma_agreement():
 @pytest.mark.parametrize('N,Cin,H,W,Cout,nhwc_in,act', [(1, 32, 8, 16, 128, True, 0), (2, 128, 37, 45, 128, True, 1),
                                                           (6, 256, 28, 50, 128, False, 0), (1, 64, 180, 180, 128, False, 0),
                                                           (1, 128, 5, 7, 256, True, 1)])
-def test_conv3x3_tc_matches_float64(N, Cin, H, W, Cout, nhwc_in, act):
+def test_conv3x3_tc_matches_float64(N, Cin, H, W, Cout, nhwc_in, act, tc_mode):
     from deepinteraction_b200 import ops, fold
     g = torch.Generator().manual_seed(N * 100 + Cin)
     x = torch.randn(N, Cin, H, W, generator=g)

@@ -21,6 +21,17 @@ for (M, N, K) in [(134400, 128, 128)]:
     e1.record()
     torch.cuda.synchronize()
     print(f'== M={M} N={N} K={K}: {e0.elapsed_time(e1) / 10 * 1e3:.1f} us per launch')
+    for mode in (3, 5):
+        L.di_tc_set_debug(mode)
+        for _ in range(3):
+            ops.linear([A], W, b, 1)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(10):
+            ops.linear([A], W, b, 1)
+        e1.record()
+        torch.cuda.synchronize()
+        print(f'   debug mode {mode} (2=skip LDTM, 4=skip store): {e0.elapsed_time(e1) / 10 * 1e3:.1f} us per launch')
     L.di_tc_set_debug(1)
     ops.linear([A], W, b, 1)
     torch.cuda.synchronize()
