@@ -658,8 +658,7 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         const bool fullc = col + 32 <= p.N;
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TN + c0), v);
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        __syncwarp();
+        if (p.dbg & 4) continue;                      // experiment: skip staging + store
         const uint32_t buf = (uint32_t)(chunk & 1) * 4096u;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -679,12 +678,25 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           o.x = di_act(o.x, p.act); o.y = di_act(o.y, p.act); o.z = di_act(o.z, p.act); o.w = di_act(o.w, p.act);
           *reinterpret_cast<float4*>(my_ep_ptr + buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
-        if (lane == 0) {
-          if (p.conv) tma_store_4d(&mapC, my_ep + buf, col, x0, y0 + 2 * q, img);
-          else tma_store_2d(&mapC, my_ep + buf, col, m0 + 32 * q);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        // transposed read-back: each store instruction writes 4 rows x 128 contiguous bytes
+        const int unit = lane & 7;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = i * 4 + (lane >> 3);                     // row inside this warp's 32-row slab
+          const float4 o = *reinterpret_cast<const float4*>(my_ep_ptr + buf + r * 128 + ((unit ^ (r & 7)) << 4));
+          long long gr;
+          bool ok;
+          if (p.conv) {
+            const int yy = y0 + 2 * q + (r >> 4), xx = x0 + (r & 15);
+            ok = yy < p.H && xx < p.W;
+            gr = ((long long)img * p.H + yy) * p.W + xx;
+          } else {
+            gr = (long long)m0 + 32 * q + r;
+            ok = gr < p.M;
+          }
+          const int cc = col + unit * 4;
+          if (ok && cc < p.N) *reinterpret_cast<float4*>(p.C + (size_t)gr * p.ldc + cc) = o;
         }
       }
       tc_fence_before();
@@ -692,7 +704,6 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       if (lane == 0) mbar_arrive(acc_empty(a));
       if (threadIdx.x == 192) DBG_STAMP(6, tl);
     }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
