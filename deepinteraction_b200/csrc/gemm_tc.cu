@@ -449,6 +449,10 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
       : "memory");
 }
 
+// WRES: the whole [128, K<=128] weight slice (hi + lo, <= 128 KB) of this CTA's column tile stays resident in
+// shared memory; only A streams.  The SM<->L2 port (~28 B/clk/SM, shared by loads and stores) is what bounds the
+// K=128 layers: per 128x128 tile it moves 64 KB (A) + 64 KB (C) instead of 192 KB + 64 KB.
+template <bool WRES>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                   const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapWhi,
@@ -458,7 +462,11 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
   constexpr int S = V3_STAGES;
-  const uint32_t ep_base = base + S * V3_STAGE_BYTES;
+  constexpr int STG = WRES ? A_BYTES : V3_STAGE_BYTES;            // bytes per pipeline stage
+  constexpr int WRES_BYTES = WRES ? 8 * A_BYTES : 0;              // resident W: hi chunks 0..3 | lo chunks 0..3
+  constexpr int RING_OFF = WRES_BYTES;                            // stage ring starts after the resident weights
+  constexpr int EP_OFF = RING_OFF + S * STG;
+  const uint32_t ep_base = base + EP_OFF;
   const uint32_t bars = ep_base + EP_BYTES;
   auto full = [&](int s) { return bars + 8u * s; };
   auto empty = [&](int s) { return bars + 8u * (S + s); };
@@ -467,8 +475,9 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   auto acc_full = [&](int a) { return bars + 8u * (2 * S + 4 + a); };
   auto acc_empty = [&](int a) { return bars + 8u * (2 * S + 6 + a); };
   const uint32_t tmem_slot = bars + 8u * (2 * S + 8);
+  const uint32_t w_full = bars + 8u * (2 * S + 9);
   volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(base_ptr + S * V3_STAGE_BYTES + EP_BYTES + 8 * (2 * S + 8));
+      reinterpret_cast<volatile uint32_t*>(base_ptr + EP_OFF + EP_BYTES + 8 * (2 * S + 8));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int nk = 0;
@@ -480,8 +489,9 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(full(s), 1);
-      mbar_init(empty(s), 1);
+      mbar_init(empty(s), WRES ? 4 : 1);            // WRES: the splitter frees the A landing buffer
     }
+    mbar_init(w_full, 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(a_ready(b), 4);
       mbar_init(a_free(b), 1);
@@ -528,6 +538,14 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           }
       };
       constexpr int PF = 2;
+      if (WRES) {                                    // gridDim.x % n_tiles == 0  =>  this CTA's column tile is fixed
+        const int n0w = (blockIdx.x % p.n_tiles) * TN;
+        mbar_expect_tx(w_full, 2 * nk * A_BYTES);
+        for (int kc = 0; kc < nk; ++kc) {
+          tma_load_2d(base + kc * A_BYTES, &mapWhi, w_full, kc * TK, n0w);
+          tma_load_2d(base + (4 + kc) * A_BYTES, &mapWlo, w_full, kc * TK, n0w);
+        }
+      }
       for (int r = 1; r <= PF; ++r) prefetch_tile(blockIdx.x + r * gridDim.x);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int m0, n0, img, y0, x0;
@@ -537,8 +555,8 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           const int s = it % S;
           if (it >= S) mbar_wait(empty(s), ((it / S) - 1) & 1);
           DBG_STAMP(0, it);
-          const uint32_t st = base + s * V3_STAGE_BYTES;
-          mbar_expect_tx(full(s), 3 * A_BYTES);
+          const uint32_t st = base + RING_OFF + s * STG;
+          mbar_expect_tx(full(s), WRES ? A_BYTES : 3 * A_BYTES);
           if (p.conv) {
             const int tap = kc_all / p.kchunks[0], kc = kc_all - tap * p.kchunks[0];
             tma_load_4d(st, &mapA0, full(s), kc * TK, x0 + tap % 3 - 1, y0 + tap / 3 - 1, img);
@@ -551,14 +569,17 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
             const CUtensorMap* mp = src == 0 ? &mapA0 : (src == 1 ? &mapA1 : &mapA2);
             tma_load_2d(st, mp, full(s), kc * TK, m0);
           }
-          tma_load_2d(st + A_BYTES, &mapWhi, full(s), kc_all * TK, n0);
-          tma_load_2d(st + 2 * A_BYTES, &mapWlo, full(s), kc_all * TK, n0);
+          if (!WRES) {
+            tma_load_2d(st + A_BYTES, &mapWhi, full(s), kc_all * TK, n0);
+            tma_load_2d(st + 2 * A_BYTES, &mapWlo, full(s), kc_all * TK, n0);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer: A from TMEM, W from shared memory ----------------
     int it = 0, tl = 0;
+    if (WRES) mbar_wait(w_full, 0);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
       const int a = tl & 1;
       if (tl >= 2) mbar_wait(acc_empty(a), ((tl >> 1) - 1) & 1);
@@ -570,16 +591,18 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         tc_fence_after();
         if (lane == 0) {
           DBG_STAMP(3, it);
-          const uint32_t st = base + s * V3_STAGE_BYTES;
+          const uint32_t st = base + RING_OFF + s * STG;
+          const uint32_t whi_base = WRES ? base + kc_all * A_BYTES : st + A_BYTES;
+          const uint32_t wlo_base = WRES ? base + (4 + kc_all) * A_BYTES : st + 2 * A_BYTES;
           const uint32_t ta = tmem_base + 256u + (uint32_t)(b * 64);
 #pragma unroll
           for (int k = 0; k < TK / 8; ++k) {
-            const uint64_t w_hi = umma_desc(st + A_BYTES + k * 32), w_lo = umma_desc(st + 2 * A_BYTES + k * 32);
+            const uint64_t w_hi = umma_desc(whi_base + k * 32), w_lo = umma_desc(wlo_base + k * 32);
             umma_tf32_ts(tmem_acc, ta + 32u + (uint32_t)(k * 8), w_hi, (kc_all | k) != 0);   // A_lo * W_hi
             umma_tf32_ts(tmem_acc, ta + (uint32_t)(k * 8), w_lo, 1);                          // A_hi * W_lo
             umma_tf32_ts(tmem_acc, ta + (uint32_t)(k * 8), w_hi, 1);                          // A_hi * W_hi
           }
-          umma_commit(empty(s));
+          if (!WRES) umma_commit(empty(s));
           umma_commit(a_free(b));
           if (kc_all == nk - 1) umma_commit(acc_full(a));
           DBG_STAMP(4, it);
@@ -597,7 +620,7 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         const int s = it % S, b = it & 1;
         mbar_wait(full(s), (it / S) & 1);
         if (threadIdx.x == 64) DBG_STAMP(1, it);
-        const uint8_t* arow = base_ptr + s * V3_STAGE_BYTES + row * 128;
+        const uint8_t* arow = base_ptr + RING_OFF + s * STG + row * 128;
         uint32_t hi[32], lo[32];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -608,6 +631,10 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
             hi[4 * j + e] = __float_as_uint(xv[e]) & 0xFFFFE000u;
             lo[4 * j + e] = __float_as_uint(xv[e] - __uint_as_float(hi[4 * j + e]));
           }
+        }
+        if (WRES) {                                   // the landing buffer is free as soon as every lane has read it
+          __syncwarp();
+          if (lane == 0) mbar_arrive(empty(s));
         }
         if (it >= 2) mbar_wait(a_free(b), ((it >> 1) - 1) & 1);   // MMAs that read this TMEM A buffer retired
         tc_fence_after();
@@ -626,8 +653,8 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const uint32_t my_ep = ep_base + (uint32_t)((warp - 6) * 2) * 4096u;
-    uint8_t* my_ep_ptr = base_ptr + S * V3_STAGE_BYTES + (warp - 6) * 2 * 4096;
-    float* bias_s = reinterpret_cast<float*>(base_ptr + S * V3_STAGE_BYTES + EP_BYTES + 256);
+    uint8_t* my_ep_ptr = base_ptr + EP_OFF + (warp - 6) * 2 * 4096;
+    float* bias_s = reinterpret_cast<float*>(base_ptr + EP_OFF + EP_BYTES + 256);
     int tl = 0, chunk = 0, bias_n0 = -1;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
       int m0, n0, img, y0, x0;
@@ -779,6 +806,7 @@ bool make_store_map_nhwc(CUtensorMap* m, float* ptr, int N, int H, int W, int C)
 
 bool g_attr_set = false, g_attr_set_v3 = false;
 int g_tc_debug = 0;
+int g_tc_wres = 1;    // keep the weight slice resident in shared memory when K <= 128
 int g_tc_mode = 3;   // 3: A operand through tensor memory (default); 2: A operand through shared memory
 
 int launch_tc(const CUtensorMap maps[6], const TcParams& p, cudaStream_t stream, const char* name) {
@@ -799,13 +827,24 @@ int launch_tc(const CUtensorMap maps[6], const TcParams& p, cudaStream_t stream,
   }
   if (g_tc_mode == 3) {
     if (!g_attr_set_v3) {
-      if (cudaFuncSetAttribute(gemm_tc_kernel_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_BYTES) != cudaSuccess) {
+      if (cudaFuncSetAttribute(gemm_tc_kernel_v3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_BYTES) != cudaSuccess ||
+          cudaFuncSetAttribute(gemm_tc_kernel_v3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_BYTES) != cudaSuccess) {
         di_set_error("%s: cannot reserve %d bytes of shared memory", name, V3_SMEM_BYTES);
         return DI_ERR_LAUNCH;
       }
       g_attr_set_v3 = true;
     }
-    gemm_tc_kernel_v3<<<grid, NTHREADS, V3_SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
+    int nk = 0;
+    for (int s2 = 0; s2 < p.nsrc; ++s2) nk += p.kchunks[s2];
+    const bool wres = !p.conv && nk <= 4 && g_tc_wres;
+    if (wres) {
+      // every CTA keeps one column tile's weights resident: the grid must be a multiple of n_tiles
+      int g2 = tiles < g_num_sms ? tiles : (g_num_sms / p.n_tiles) * p.n_tiles;
+      if (g2 < p.n_tiles) g2 = p.n_tiles;
+      gemm_tc_kernel_v3<true><<<dim3(g2), NTHREADS, V3_SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
+    } else {
+      gemm_tc_kernel_v3<false><<<grid, NTHREADS, V3_SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
+    }
   } else {
     gemm_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
   }
@@ -827,8 +866,9 @@ int di_tc_set_debug(int on) {
 }
 // 3 (default): A operand staged in tensor memory; 2: A operand in shared memory (earlier pipeline, kept for A/B tests)
 int di_tc_set_mode(int mode) {
-  DI_CHECK_ARG(mode == 2 || mode == 3, "di_tc_set_mode: mode must be 2 or 3");
-  g_tc_mode = mode;
+  DI_CHECK_ARG(mode == 2 || mode == 3 || mode == 4, "di_tc_set_mode: mode must be 2, 3 or 4");
+  g_tc_wres = mode != 4;            // 4 = v3 pipeline with streamed weights (A/B tests)
+  g_tc_mode = mode == 2 ? 2 : 3;
   return DI_OK;
 }
 int di_tc_debug_read(long long* host_buf) {

@@ -14,7 +14,7 @@ def dev():
     return torch.device('cuda:0')
 
 
-@pytest.fixture(params=[3, 2], ids=['A-via-TMEM', 'A-via-smem'])
+@pytest.fixture(params=[3, 4, 2], ids=['A-via-TMEM+W-resident', 'A-via-TMEM', 'A-via-smem'])
 def tc_mode(request):
     """Both tensor-core pipelines: v3 stages the A operand in tensor memory, v2 keeps it in shared memory."""
     from deepinteraction_b200 import _lib
