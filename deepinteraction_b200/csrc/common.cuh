@@ -48,6 +48,9 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpre
 // Activation codes shared with the host side.
 enum { DI_ACT_NONE = 0, DI_ACT_RELU = 1, DI_ACT_GELU = 2 };
 
+// NOTE: call sites apply this inside a loop only under a warp-uniform `act`; for register tiles prefer one branch
+// around the whole tile (see act_tile in gemm_tc.cu) so that the GELU polynomial is not if-converted per element.
+__device__ __forceinline__ float di_gelu(float v) { return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f)); }
 __device__ __forceinline__ float di_act(float v, int act) {
   if (act == DI_ACT_RELU) return fmaxf(v, 0.f);
   if (act == DI_ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));

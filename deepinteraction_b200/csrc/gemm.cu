@@ -258,9 +258,17 @@ sgemm_kernel(ALoader la, WLoader lb, Epilogue ep, int M, int N, int K, int ktile
         if (final_ep) {
           if (ep.bias && nb + j < N) s += __ldg(ep.bias + nb + j);
           if (ep.res && nb + j < N) s += __ldg(ep.res + (size_t)(m % ep.res_mod) * ep.ldres + nb + j);
-          s = di_act(s, ep.act);
         }
         v[j] = s;
+      }
+      if (final_ep) {                                  // one uniform branch per 4 values (no per-element if-conversion)
+        if (ep.act == DI_ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
+        } else if (ep.act == DI_ACT_GELU) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[j] = di_gelu(v[j]);
+        }
       }
       if (ep.nchw_hw > 0) {
         int img = m / ep.nchw_hw, pix = m - img * ep.nchw_hw;

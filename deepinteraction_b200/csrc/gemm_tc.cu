@@ -140,6 +140,19 @@ __device__ long long g_dbg[DBG_SLOTS * DBG_N];
     if (p.dbg && blockIdx.x == 0 && (i) < DBG_N) g_dbg[(slot) * DBG_N + (i)] = clock64(); \
   } while (0)
 
+// Activation over a register tile with ONE warp-uniform branch.  (Calling di_act per element made ptxas
+// if-convert the GELU polynomial: every element paid ~60 predicated-off instructions, 3000 cycles per 32-column
+// epilogue step -- found with the clock64 trace.)
+__device__ __forceinline__ void act_tile(float (&v)[32], int act) {
+  if (act == DI_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  } else if (act == DI_ACT_GELU) {
+#pragma unroll 4
+    for (int j = 0; j < 32; ++j) v[j] = 0.5f * v[j] * (1.f + erff(v[j] * 0.70710678118654752440f));
+  }
+}
+
 struct TcParams {
   int M, N;                 // logical output size (rows, columns)
   int nsrc;                 // linear: number of A sources (1..3)
@@ -376,22 +389,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + 4 * j);      // broadcast LDS
-          float4 o = make_float4(v[4 * j] + b4.x, v[4 * j + 1] + b4.y, v[4 * j + 2] + b4.z, v[4 * j + 3] + b4.w);
-          if (resrow) {
+          v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+        }
+        if (resrow) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
             if (fullc) {
               const float4 r4 = ldg4(resrow + col + 4 * j);
-              o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+              v[4 * j] += r4.x; v[4 * j + 1] += r4.y; v[4 * j + 2] += r4.z; v[4 * j + 3] += r4.w;
             } else {
-              if (col + 4 * j + 0 < p.N) o.x += __ldg(resrow + col + 4 * j + 0);
-              if (col + 4 * j + 1 < p.N) o.y += __ldg(resrow + col + 4 * j + 1);
-              if (col + 4 * j + 2 < p.N) o.z += __ldg(resrow + col + 4 * j + 2);
-              if (col + 4 * j + 3 < p.N) o.w += __ldg(resrow + col + 4 * j + 3);
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (col + 4 * j + e < p.N) v[4 * j + e] += __ldg(resrow + col + 4 * j + e);
             }
           }
-          o.x = di_act(o.x, p.act); o.y = di_act(o.y, p.act); o.z = di_act(o.z, p.act); o.w = di_act(o.w, p.act);
-          // 128B swizzle of the staging tile: 16-byte unit j of row r lives at unit j ^ (r & 7)
-          *reinterpret_cast<float4*>(my_ep_ptr + buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
         }
+        act_tile(v, p.act);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(my_ep_ptr + buf + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+              make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         if (threadIdx.x == 192) DBG_STAMP(7, chunk * 4 + 2);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
@@ -689,22 +706,27 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         const uint32_t buf = (uint32_t)(chunk & 1) * 4096u;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + 4 * j);
-          float4 o = make_float4(v[4 * j] + b4.x, v[4 * j + 1] + b4.y, v[4 * j + 2] + b4.z, v[4 * j + 3] + b4.w);
-          if (resrow) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + 4 * j);      // broadcast LDS
+          v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+        }
+        if (resrow) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
             if (fullc) {
               const float4 r4 = ldg4(resrow + col + 4 * j);
-              o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+              v[4 * j] += r4.x; v[4 * j + 1] += r4.y; v[4 * j + 2] += r4.z; v[4 * j + 3] += r4.w;
             } else {
-              if (col + 4 * j + 0 < p.N) o.x += __ldg(resrow + col + 4 * j + 0);
-              if (col + 4 * j + 1 < p.N) o.y += __ldg(resrow + col + 4 * j + 1);
-              if (col + 4 * j + 2 < p.N) o.z += __ldg(resrow + col + 4 * j + 2);
-              if (col + 4 * j + 3 < p.N) o.w += __ldg(resrow + col + 4 * j + 3);
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (col + 4 * j + e < p.N) v[4 * j + e] += __ldg(resrow + col + 4 * j + e);
             }
           }
-          o.x = di_act(o.x, p.act); o.y = di_act(o.y, p.act); o.z = di_act(o.z, p.act); o.w = di_act(o.w, p.act);
-          *reinterpret_cast<float4*>(my_ep_ptr + buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
         }
+        act_tile(v, p.act);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(my_ep_ptr + buf + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+              make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         __syncwarp();
         // transposed read-back: each store instruction writes 4 rows x 128 contiguous bytes
         const int unit = lane & 7;
@@ -721,6 +743,7 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           } else {
             gr = (long long)m0 + 32 * q + r;
             ok = gr < p.M;
+            if (p.dbg & 8) gr = (long long)blockIdx.x * 128 + 32 * q + r;   // experiment: L2-resident destination
           }
           const int cc = col + unit * 4;
           if (ok && cc < p.N) *reinterpret_cast<float4*>(p.C + (size_t)gr * p.ldc + cc) = o;
