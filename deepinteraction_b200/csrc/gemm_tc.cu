@@ -153,6 +153,9 @@ __device__ __forceinline__ void act_tile(float (&v)[32], int act) {
   }
 }
 
+__constant__ int g_direct_store_dev;
+#define g_direct_store (p.dbg & 16)
+
 struct TcParams {
   int M, N;                 // logical output size (rows, columns)
   int nsrc;                 // linear: number of A sources (1..3)
@@ -701,8 +704,10 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         if (col >= p.N) break;
         const bool fullc = col + 32 <= p.N;
         float v[32];
+        if (threadIdx.x == 192) DBG_STAMP(7, chunk * 5 + 0);
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TN + c0), v);
         if (p.dbg & 4) continue;                      // experiment: skip staging + store
+        if (threadIdx.x == 192) DBG_STAMP(7, chunk * 5 + 1);
         const uint32_t buf = (uint32_t)(chunk & 1) * 4096u;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -723,11 +728,34 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           }
         }
         act_tile(v, p.act);
+        if (threadIdx.x == 192) DBG_STAMP(7, chunk * 5 + 2);
+        if (g_direct_store) {                         // registers -> global, no shared-memory staging
+          long long gr2;
+          bool ok2;
+          if (p.conv) {
+            const int yy = y0 + row / 16, xx = x0 + row % 16;
+            ok2 = yy < p.H && xx < p.W;
+            gr2 = ((long long)img * p.H + yy) * p.W + xx;
+          } else {
+            gr2 = (long long)m0 + row;
+            ok2 = gr2 < p.M;
+          }
+          if (ok2) {
+            float* dst = p.C + (size_t)gr2 * p.ldc + col;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (col + 4 * j < p.N)
+                *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+          if (threadIdx.x == 192) DBG_STAMP(7, chunk * 5 + 4);
+          continue;
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           *reinterpret_cast<float4*>(my_ep_ptr + buf + lane * 128 + ((j ^ (lane & 7)) << 4)) =
               make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         __syncwarp();
+        if (threadIdx.x == 192) DBG_STAMP(7, chunk * 5 + 3);
         // transposed read-back: each store instruction writes 4 rows x 128 contiguous bytes
         const int unit = lane & 7;
 #pragma unroll
@@ -748,6 +776,7 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           const int cc = col + unit * 4;
           if (ok && cc < p.N) *reinterpret_cast<float4*>(p.C + (size_t)gr * p.ldc + cc) = o;
         }
+        if (threadIdx.x == 192) DBG_STAMP(7, chunk * 5 + 4);
       }
       tc_fence_before();
       __syncwarp();

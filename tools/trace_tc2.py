@@ -27,5 +27,7 @@ for dbg in (1,):
     names = ['issue', 'landed', 'split', 'mma_rdy', 'mma_iss']
     for it in range(0):
         print(it, ' '.join(f'{names[r]}={int(t[r, it] - t0):7d}' for r in range(5)))
+    for ch in range(8):
+        print('chunk', ch, ' '.join(f'{nm}={int(t[7, ch * 5 + i] - t0)}' for i, nm in enumerate(['pre_ld', 'ld', 'act', 'sts', 'stg'])))
     for tl in range(8):
         print('tile', tl, 'acc_ready', int(t[5, tl] - t0), 'stored', int(t[6, tl] - t0))
