@@ -357,6 +357,10 @@ def main():
     pk = peaks()
 
     # ---- per-kernel device times (separate pass so the event pairs do not perturb the timed regions) -----
+    from deepinteraction_b200 import graph as di_graph
+    di_graph.ENABLED[0] = False                  # event-instrumented pass: launch kernel by kernel
+    neck._graphs.clear()
+    head._graphs.clear()
     ops.PROFILE[0] = []
     for _ in range(max(args.profile_steps, 1)):
         forward(neck, head, fr_dev)
@@ -370,6 +374,7 @@ def main():
         d['bytes'] += nbytes
         d['flops'] += flops
     ops.PROFILE[0] = None
+    di_graph.ENABLED[0] = True
     total_ms = sum(d['ms'] for d in agg.values())
     kernels = []
     for name, d in sorted(agg.items(), key=lambda kv: -kv[1]['ms']):
@@ -419,7 +424,8 @@ def main():
                          d2h_bytes_per_step=int(sum(v.numel() * v.element_size() for v in out.values())),
                          ms_per_step=ms_e2e / K, host_launch_ms_per_step=host_fwd / K * 1e3,
                          overlap='H2D of step i+1 on a copy stream (double-buffered device inputs) while step i computes'),
-                gpu_launches=launches, launches_per_step=launches / K, roofline=roof, cpu_baseline=cpu,
+                gpu_launches=launches, launches_per_step=launches / K, cuda_graph=bool(di_graph.ENABLED[0] and os.environ.get('DI_B200_GRAPH', '1') != '0'),
+                roofline=roof, cpu_baseline=cpu,
                 kernels=kernels[:12])
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -872,7 +872,11 @@ int di_dynconv_f32(const float* roi, const float* params, const float* g1, const
                    const float* b2, float* out, int n, float eps, cudaStream_t stream) {
   DI_CHECK_ARG(roi && params && g1 && b1 && g2 && b2 && out && n > 0, "di_dynconv_f32: bad argument");
   const int smem = 2 * DR * DC * (int)sizeof(float);
-  cudaFuncSetAttribute(dynconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  static bool once = false;
+  if (!once) {
+    cudaFuncSetAttribute(dynconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    once = true;
+  }
   dynconv_kernel<<<n, 256, smem, stream>>>(roi, params, g1, b1, g2, b2, out, eps);
   DI_CHECK_LAUNCH("di_dynconv_f32");
   return DI_OK;

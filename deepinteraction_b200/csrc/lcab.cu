@@ -432,15 +432,27 @@ int di_lcab_window_f32(const float* q, int ldq, const float* k, int ldk, const f
   if (ksize == 9 && C % MCH == 0 && !g_force_ffma_window) {
     dim3 mgrid(di_cdiv(W, MQ_COLS), di_cdiv(H, MQ_ROWS), N);
     size_t smem = 2ull * MSTAGE_FLOATS * sizeof(float);
-    cudaFuncSetAttribute(lcab_window_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static bool once_mma = false;
+    if (!once_mma) {
+      cudaFuncSetAttribute(lcab_window_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      once_mma = true;
+    }
     lcab_window_mma_kernel<<<mgrid, 256, smem, stream>>>(q, ldq, k, ldk, v, ldv, out, ldo, H, W, C, scale);
   } else if (ksize == 9) {
     size_t smem = 2ull * (TQ + 8) * (TQ + 8) * PSTR * sizeof(float);
-    cudaFuncSetAttribute(lcab_window_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static bool once9 = false;
+    if (!once9) {
+      cudaFuncSetAttribute(lcab_window_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      once9 = true;
+    }
     lcab_window_kernel<9><<<grid, TQ * TQ, smem, stream>>>(q, ldq, k, ldk, v, ldv, out, ldo, H, W, C, scale);
   } else if (ksize == 3) {
     size_t smem = 2ull * (TQ + 2) * (TQ + 2) * PSTR * sizeof(float);
-    cudaFuncSetAttribute(lcab_window_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static bool once3 = false;
+    if (!once3) {
+      cudaFuncSetAttribute(lcab_window_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      once3 = true;
+    }
     lcab_window_kernel<3><<<grid, TQ * TQ, smem, stream>>>(q, ldq, k, ldk, v, ldv, out, ldo, H, W, C, scale);
   } else {
     di_set_error("di_lcab_window_f32: unsupported window %d", ksize);

@@ -48,8 +48,8 @@ def lidar2img_array(img_metas):
     return np.asarray([np.asarray(m['lidar2img'], np.float32) for m in img_metas], np.float32)   # (B,V,4,4)
 
 
-def camera_rows(img_metas, device):
-    """-> proj (B,V,12) fp32, i2l (B*V,12) fp32 on `device`."""
+def camera_rows_host(img_metas):
+    """-> proj (B,V,12) fp32, i2l (B*V,12) fp32 as CPU tensors."""
     l2i = lidar2img_array(img_metas)
     B, V = l2i.shape[:2]
     inv = torch.inverse(torch.from_numpy(l2i)).numpy().astype(np.float64)    # fp32 inverse, as the reference (:149)
@@ -60,9 +60,13 @@ def camera_rows(img_metas, device):
         for v in range(V):
             proj[b, v] = (l2i[b, v].astype(np.float64) @ Ar)[:3].reshape(12)
             i2l[b, v] = (Af @ inv[b, v])[:3].reshape(12)
-    proj_t = torch.from_numpy(proj).to(device, non_blocking=True)
-    i2l_t = torch.from_numpy(i2l.reshape(B * V, 12)).to(device, non_blocking=True)
-    return proj_t, i2l_t
+    return torch.from_numpy(proj), torch.from_numpy(i2l.reshape(B * V, 12))
+
+
+def camera_rows(img_metas, device):
+    """-> proj (B,V,12) fp32, i2l (B*V,12) fp32 on `device`."""
+    proj, i2l = camera_rows_host(img_metas)
+    return proj.to(device, non_blocking=True), i2l.to(device, non_blocking=True)
 
 
 def input_hw(img_metas):

@@ -1,0 +1,82 @@
+"""CUDA-graph replay of a fixed kernel schedule.
+
+One forward of the MMRI+MMPI path is ~140 kernel launches; issued from Python they cost ~5 ms of host time per
+frame, as much as the GPU work itself.  The schedule has no data-dependent host control flow, so it can be
+captured once per input signature (shapes incl. pillar / point counts) and replayed: per frame the host only
+copies the small camera constants and calls cudaGraphLaunch.
+
+Policy: a signature is captured the SECOND time it is seen (frames with ever-changing pillar counts therefore stay
+on the eager path and never pay capture cost); at most `max_entries` graphs are kept (LRU).  Outputs are static
+buffers owned by the graph: they are overwritten by the next replay of the same signature.
+"""
+import collections
+import os
+
+import torch
+
+from . import ops
+
+ENABLED = [os.environ.get('DI_B200_GRAPH', '1') != '0']
+
+
+class GraphCache:
+    def __init__(self, max_entries=4):
+        self.entries = collections.OrderedDict()
+        self.seen = collections.OrderedDict()
+        self.max_entries = max_entries
+
+    def clear(self):
+        self.entries.clear()
+        self.seen.clear()
+
+    def run(self, sig, inputs, host_consts, fn):
+        """inputs: list of device tensors; host_consts: list of small CPU tensors; fn(inputs, consts) -> pytree of
+        tensors.  Returns fn's result (eager) or the graph's static outputs (replay)."""
+        ent = self.entries.get(sig)
+        if ent is None:
+            n = self.seen.get(sig, 0) + 1
+            self.seen[sig] = n
+            while len(self.seen) > 64:
+                self.seen.popitem(last=False)
+            if n < 2 or not ENABLED[0]:
+                dev = inputs[0].device
+                return fn(inputs, [c.to(dev, non_blocking=True) for c in host_consts])
+            ent = self._capture(sig, inputs, host_consts, fn)
+        else:
+            self.entries.move_to_end(sig)
+        g, s_in, s_c, pinned, out, launches, flip = ent
+        for dst, src in zip(s_in, inputs):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        k = flip[0] = flip[0] ^ 1
+        for dst, pin, c in zip(s_c, pinned[k], host_consts):
+            pin.copy_(c)
+            dst.copy_(pin, non_blocking=True)
+        g.replay()
+        ops.LAUNCHES[0] += launches
+        return out
+
+    def _capture(self, sig, inputs, host_consts, fn):
+        dev = inputs[0].device
+        s_in = [t.clone() for t in inputs]
+        s_c = [torch.empty(c.shape, dtype=c.dtype, device=dev) for c in host_consts]
+        pinned = [[torch.empty(c.shape, dtype=c.dtype).pin_memory() for c in host_consts] for _ in range(2)]
+        for dst, c in zip(s_c, host_consts):
+            dst.copy_(c)
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):          # warm-up outside capture (lazy module loads, func attributes, packs)
+            fn(s_in, s_c)
+        cur.wait_stream(side)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        n0 = ops.LAUNCHES[0]
+        with torch.cuda.graph(g):
+            out = fn(s_in, s_c)
+        launches = ops.LAUNCHES[0] - n0
+        ent = (g, s_in, s_c, pinned, out, launches, [0])
+        self.entries[sig] = ent
+        while len(self.entries) > self.max_entries:
+            self.entries.popitem(last=False)
+        return ent

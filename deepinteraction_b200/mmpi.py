@@ -23,6 +23,7 @@ import torch
 import torch.nn as nn
 
 from . import fold, geom, ops
+from .graph import GraphCache
 from .mmri import ConvBN
 
 
@@ -183,6 +184,7 @@ class DeepInteractionDecoder(nn.Module):
         self.query_labels = None
         self.on_the_image_mask = []
         self._pack, self._pack_key = None, None
+        self._graphs = GraphCache()
 
     # -- packing -----------------------------------------------------------------------------------
     def _state_key(self):
@@ -272,6 +274,7 @@ class DeepInteractionDecoder(nn.Module):
                                ffn=linw(g('linear1')) + linw(g('linear2')), pred=self._pack_pred(ph, d)))
         pk['blocks'] = blocks
         self._pack, self._pack_key = pk, key
+        self._graphs.clear()                 # captured graphs hold pointers into the previous pack
         return pk
 
     # -- forward -----------------------------------------------------------------------------------
@@ -285,11 +288,35 @@ class DeepInteractionDecoder(nn.Module):
                 bc.pc_range[1], tc['out_size_factor'] * tc['voxel_size'][0], tc['pc_range'][0], in_hw[0], in_hw[1],
                 bc.voxel_size[0] * bc.out_size_factor, bc.pc_range[0]]
 
+    def _camera_consts(self, img_metas):
+        """Host-side constants of one call: camera rows (B,V,12) and per-sample (crop_x, crop_y, flip, orig_w)."""
+        proj, _ = geom.camera_rows_host(img_metas)
+        aux = torch.tensor([[*(np.asarray(m.get('img_crop_offset', (0.0, 0.0)), np.float32).reshape(-1)[:2]),
+                             1.0 if m.get('flip', False) else 0.0,
+                             float(m['img_shape'][0][1]) if m.get('flip', False) else 0.0] for m in img_metas],
+                           dtype=torch.float32)
+        return proj, aux
+
     def forward_rows(self, pts_conv, new_pts, img, img_metas, debug=None):
-        """pts_conv, new_pts [B,Y,X,C]; img [B*V,h,w,C] (pixel-major) -> list of per-layer pred [B*P, NP], ..."""
+        """pts_conv, new_pts [B,Y,X,C]; img [B*V,h,w,C] (pixel-major) -> dict(preds [B*P, NP] per layer, ...).
+        Replayed from a CUDA graph once the input signature repeats (graph.py)."""
         if self.training:
             raise NotImplementedError('libdi_b200 DeepInteractionDecoder is forward/eval only (call .eval())')
-        pk = self.pack()
+        self.pack()
+        proj_h, aux_h = self._camera_consts(img_metas)
+        in_hw = geom.input_hw(img_metas)
+        if debug is not None:
+            dev_ = pts_conv.device
+            return self._schedule(pts_conv, new_pts, img, in_hw, proj_h.to(dev_), aux_h.to(dev_), debug)
+        inputs = [pts_conv, new_pts, img]
+        sig = (tuple(tuple(t.shape) for t in inputs), in_hw, id(self._pack))
+
+        def fn(ins, consts):
+            return self._schedule(ins[0], ins[1], ins[2], in_hw, consts[0], consts[1], None)
+        return self._graphs.run(sig, inputs, [proj_h, aux_h], fn)
+
+    def _schedule(self, pts_conv, new_pts, img, in_hw, proj, aux, debug):
+        pk = self._pack
         B, Y, X, C = pts_conv.shape
         assert (Y, X) == (self.y_size, self.x_size), 'BEV size must equal test_cfg grid_size // out_size_factor'
         HW, P, V, K, H = Y * X, self.num_proposals, self.num_views, self.num_classes_heat, self.num_heads
@@ -305,7 +332,6 @@ class DeepInteractionDecoder(nn.Module):
         heat, dense_b = ops.heatmap_nms(logit_a, logit_b, K, self.nms_kernel_size, no_nms)
         top = ops.topk(heat.view(B, K * HW), P)
         q, qpos, labels, qscore = ops.query_init(pts_conv.view(B, HW, C), top, heat, pk['wce_t'], pk['bce'], X)
-        self.query_labels = labels.long()
         if debug is not None:
             debug.update(top=top, heat=heat, query_feat0=q.clone(), query_pos0=qpos.clone())
         # transformer decoder layer
@@ -329,12 +355,6 @@ class DeepInteractionDecoder(nn.Module):
         if debug is not None:
             debug.update(query_feat1=q.clone(), first_res=first.clone())
         # MMPI layers
-        in_hw = geom.input_hw(img_metas)
-        proj, _ = geom.camera_rows(img_metas, dev_)
-        aux = torch.tensor([[*(np.asarray(m.get('img_crop_offset', (0.0, 0.0)), np.float32).reshape(-1)[:2]),
-                             1.0 if m.get('flip', False) else 0.0,
-                             float(m['img_shape'][0][1]) if m.get('flip', False) else 0.0] for m in img_metas],
-                           dtype=torch.float32).to(dev_, non_blocking=True)
         prm = self._roi_params(in_hw)
         preds, wins = [], []
         for li, bp in enumerate(pk['blocks']):
@@ -379,6 +399,7 @@ class DeepInteractionDecoder(nn.Module):
     def forward_nhwc(self, pts_conv, new_pts, img, img_metas, debug=None):
         r = self.forward_rows(pts_conv, new_pts, img, img_metas, debug)
         B, P = pts_conv.shape[0], self.num_proposals
+        self.query_labels = r['labels'].long()
         self.on_the_image_mask = [(w.view(B, P) != -1) for w in r['wins']]
         rets = [self._to_dict(p, B, P) for p in r['preds']]
         rets[0]['query_heatmap_score'] = r['qscore']

@@ -20,6 +20,7 @@ import torch
 import torch.nn as nn
 
 from . import fold, geom, ops
+from .graph import GraphCache
 
 PC_RANGE = (-54.0, -54.0, -5.0, 54.0, 54.0, 3.0)     # hard-coded in the reference (encoder_utils.py:190)
 
@@ -116,12 +117,14 @@ def lcab_forward(pk, target, source, N, H, W):
 class Geometry:
     """Per-frame geometry shared by both encoder layers (and by the decoder's projections)."""
 
-    def __init__(self, img_metas, pts_metas, feat_hw, bev_hw, device, want_debug=False, side_stream=None):
+    def __init__(self, img_metas, pts_metas, feat_hw, bev_hw, device, want_debug=False, side_stream=None,
+                 cams=None):
         """The depth maps / completion / lifting chain is latency-bound (one CTA per camera) and independent of
         the feature maps, so it is issued on `side_stream` and overlaps the shared convs and the BEV branch;
-        consumers call wait() before the first BEV sampling."""
+        consumers call wait() before the first BEV sampling.  cams = (proj, i2l) device tensors when the caller
+        already uploaded the camera rows (graph replay), else they are derived from img_metas here."""
         self.in_hw = geom.input_hw(img_metas)
-        self.proj, self.i2l = geom.camera_rows(img_metas, device)             # (B,V,12), (B*V,12)
+        self.proj, self.i2l = cams if cams is not None else geom.camera_rows(img_metas, device)   # (B,V,12), (B*V,12)
         B, V = self.proj.shape[:2]
         h, w = feat_hw
         main = torch.cuda.current_stream()
@@ -174,6 +177,7 @@ class DeepInteractionEncoder(nn.Module):
         self._pack_key = None
         self.last_geometry = None
         self._side_stream = None
+        self._graphs = GraphCache()
 
     # -- packing -----------------------------------------------------------------------------------
     def _state_key(self):
@@ -202,6 +206,7 @@ class DeepInteractionEncoder(nn.Module):
                                p_fuse=(Wt(wp), d(bp)), i_fuse=(Wt(wi), d(bi))))
         pk['layers'] = layers
         self._pack, self._pack_key = pk, key
+        self._graphs.clear()                 # captured graphs hold pointers into the previous pack
         return pk
 
     # -- forward -----------------------------------------------------------------------------------
@@ -228,20 +233,39 @@ class DeepInteractionEncoder(nn.Module):
         return pm
 
     def forward_nhwc(self, img_feats, pts_feats, img_metas, pts_metas, debug=None):
-        """-> img [B*V,h,w,C], pts_conv [B,Y,X,C], pts [B,Y,X,C]  (pixel-major, fp32)."""
+        """-> img [B*V,h,w,C], pts_conv [B,Y,X,C], pts [B,Y,X,C]  (pixel-major, fp32).
+        The kernel schedule is replayed from a CUDA graph once an input signature repeats (graph.py)."""
         if self.training:
             raise NotImplementedError('libdi_b200 DeepInteractionEncoder is forward/eval only (call .eval())')
-        pk = self.pack()
+        self.pack()
+        dev_ = img_feats.device
+        pm = self._canon_pts_metas(pts_metas, dev_)
+        pts_list = [p.to(device=dev_, dtype=torch.float32) for p in pm['pts']]
+        if debug is not None:
+            return self._schedule(img_feats, pts_feats, img_metas, pm, pts_list, None, debug)
+        proj_h, i2l_h = geom.camera_rows_host(img_metas)
+        inputs = [img_feats.contiguous(), pts_feats.contiguous(), pm['pillars'], pm['pillar_coors'],
+                  pm['pillars_num_points']] + pts_list
+        sig = (tuple(tuple(t.shape) for t in inputs), geom.input_hw(img_metas), id(self._pack))
+
+        def fn(ins, consts):
+            pmx = dict(pillars=ins[2], pillar_coors=ins[3], pillars_num_points=ins[4], pts=ins[5:])
+            return self._schedule(ins[0], ins[1], img_metas, pmx, ins[5:], (consts[0], consts[1]), None)
+        return self._graphs.run(sig, inputs, [proj_h, i2l_h], fn)
+
+    def _schedule(self, img_feats, pts_feats, img_metas, pm, pts_list, cams, debug):
+        pk = self._pack
         dev_ = img_feats.device
         C = self.hidden_channel
         BV, _, h, w = img_feats.shape
         B, _, Y, X = pts_feats.shape
         V = BV // B
-        pm = self._canon_pts_metas(pts_metas, dev_)
         if self._side_stream is None:
             self._side_stream = torch.cuda.Stream(device=dev_)
+        pm = dict(pm)
+        pm['pts'] = pts_list
         g = Geometry(img_metas, pm, (h, w), (Y, X), dev_, want_debug=debug is not None,
-                     side_stream=self._side_stream)
+                     side_stream=self._side_stream, cams=cams)
         self.last_geometry = g
         img = ops.conv3x3(img_feats.contiguous(), *pk['shared_conv_img'], cout=C, x_nhwc=False)
         pts = ops.conv3x3(pts_feats.contiguous(), *pk['shared_conv_pts'], cout=C, x_nhwc=False)

@@ -1,0 +1,110 @@
+"""GPU: the CUDA-graph replay of the encoder / decoder schedules returns exactly what the eager launches return,
+including after the per-frame constants (camera rows) and the inputs change between replays."""
+import copy
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def dev():
+    return torch.device('cuda:0')
+
+
+def _frames():
+    """Two frames with identical shapes but different features and camera order."""
+    from deepinteraction_b200 import synth
+    from tools.make_goldens import small_frame
+    a = small_frame(77, aug=False, views=2, c_img=16, c_pts=24, bev=36, batch=2)
+    b = copy.deepcopy(a)
+    g = torch.Generator().manual_seed(5)
+    b['img_feats'] = torch.randn(a['img_feats'].shape, generator=g)
+    b['pts_feats'] = torch.randn(a['pts_feats'].shape, generator=g)
+    for m in b['img_metas']:
+        m['lidar2img'] = [m['lidar2img'][1], m['lidar2img'][0]]
+    return synth.to_device(a, dev()), synth.to_device(b, dev())
+
+
+def _encoder(seed=31):
+    from deepinteraction_b200 import mmri, synth
+    import oracle.mmri as om
+    torch.manual_seed(seed)
+    m = om.DeepInteractionEncoder(2, 16, 24, 32).eval()
+    synth.randomize_norm_stats(m, seed)
+    enc = mmri.DeepInteractionEncoder(2, 16, 24, 32)
+    enc.load_state_dict(m.state_dict(), strict=True)
+    return enc.to(dev()).eval()
+
+
+def _run_enc(enc, fr):
+    out = enc.forward_nhwc(fr['img_feats'], fr['pts_feats'], fr['img_metas'], fr['pts_metas'])
+    return [t.clone() for t in out]
+
+
+def test_encoder_graph_replay_equals_eager():
+    from deepinteraction_b200 import graph
+    enc = _encoder()
+    fa, fb = _frames()
+    old = graph.ENABLED[0]
+    try:
+        graph.ENABLED[0] = False
+        ref_a, ref_b = _run_enc(enc, fa), _run_enc(enc, fb)
+        assert not all(torch.equal(x, y) for x, y in zip(ref_a, ref_b))
+        graph.ENABLED[0] = True
+        enc._graphs.clear()
+        seq = [('a', fa, ref_a), ('a', fa, ref_a), ('b', fb, ref_b), ('a', fa, ref_a), ('b', fb, ref_b)]
+        for i, (tag, fr, ref) in enumerate(seq):
+            out = _run_enc(enc, fr)
+            for x, y in zip(out, ref):
+                assert torch.equal(x, y), (i, tag, float((x - y).abs().max()))
+        assert len(enc._graphs.entries) == 1
+    finally:
+        graph.ENABLED[0] = old
+
+
+def _flat(r):
+    out = {}
+    for k, v in r.items():
+        if torch.is_tensor(v):
+            out[k] = v.clone()
+        elif isinstance(v, (list, tuple)):
+            for i, t in enumerate(v):
+                if torch.is_tensor(t):
+                    out['%s%d' % (k, i)] = t.clone()
+    return out
+
+
+def test_decoder_graph_replay_equals_eager():
+    from deepinteraction_b200 import graph
+    from test_gpu_decoder import _build
+    from tools.make_goldens import small_frame
+    _, dec = _build(41, 2, 24)
+    fr = small_frame(41, aug=False, views=2, batch=2)
+    g = torch.Generator().manual_seed(9)
+    mk = lambda *s: torch.randn(*s, generator=g).to(dev())
+    fa = dict(pts_conv=mk(2, 36, 36, 128), new_pts=mk(2, 36, 36, 128), img=mk(4, 28, 50, 128), img_metas=fr['img_metas'])
+    fb = dict(pts_conv=mk(2, 36, 36, 128), new_pts=mk(2, 36, 36, 128), img=mk(4, 28, 50, 128))
+    metas_b = copy.deepcopy(fr['img_metas'])
+    for m in metas_b:
+        m['lidar2img'] = [m['lidar2img'][1], m['lidar2img'][0]]
+    fb['img_metas'] = metas_b
+
+    def run(f):
+        return _flat(dec.forward_rows(f['pts_conv'], f['new_pts'], f['img'], f['img_metas']))
+
+    old = graph.ENABLED[0]
+    try:
+        graph.ENABLED[0] = False
+        ref_a, ref_b = run(fa), run(fb)
+        assert len(ref_a) >= 5
+        graph.ENABLED[0] = True
+        dec._graphs.clear()
+        for i, (f, ref) in enumerate([(fa, ref_a), (fa, ref_a), (fb, ref_b), (fa, ref_a), (fb, ref_b)]):
+            out = run(f)
+            assert out.keys() == ref.keys()
+            for k in ref:
+                assert torch.equal(out[k], ref[k]), (i, k)
+        assert len(dec._graphs.entries) == 1
+    finally:
+        graph.ENABLED[0] = old
