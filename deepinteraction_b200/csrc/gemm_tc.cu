@@ -113,6 +113,11 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -132,6 +137,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// same without the wait: issue several loads, then one tcgen05.wait::ld (asm volatile keeps the order)
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]),
+        "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]), "=f"(v[16]),
+        "=f"(v[17]), "=f"(v[18]), "=f"(v[19]), "=f"(v[20]), "=f"(v[21]), "=f"(v[22]), "=f"(v[23]), "=f"(v[24]),
+        "=f"(v[25]), "=f"(v[26]), "=f"(v[27]), "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+
 // optional pipeline trace (CTA 0 only): clock64 stamps per role and chunk, read back with di_tc_debug_read
 constexpr int DBG_SLOTS = 8, DBG_N = 512;
 __device__ long long g_dbg[DBG_SLOTS * DBG_N];
@@ -148,18 +167,17 @@ __device__ __forceinline__ void act_tile(float (&v)[32], int act) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
   } else if (act == DI_ACT_GELU) {
-#pragma unroll 4
+#pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = 0.5f * v[j] * (1.f + erff(v[j] * 0.70710678118654752440f));
   }
 }
 
-__constant__ int g_direct_store_dev;
-#define g_direct_store (p.dbg & 16)
 
 struct TcParams {
   int M, N;                 // logical output size (rows, columns)
   int nsrc;                 // linear: number of A sources (1..3)
-  int kchunks[3];           // linear: K_s / 32 per source; conv: kchunks[0] = Cin / 32
+  int k0, k1, k2;           // linear: K_s / 32 per source; conv: k0 = Cin / 32.  (Scalars, not an array: a dynamically
+                            // indexed kernel parameter makes ptxas copy the whole struct to LOCAL memory.)
   int conv;                 // 1: 3x3 conv over an NHWC map (A map is 4-D)
   int H, W, tiles_x, tiles_y;  // conv geometry: tile = 8 rows x 16 cols of pixels
   int m_tiles, n_tiles;     // tile grid (m_tiles = images * tiles_y * tiles_x for conv)
@@ -169,7 +187,9 @@ struct TcParams {
   const float* res;
   int ldres, res_mod, act;
   int dbg;
+  int* sched;               // v3: 16 ints of the dynamic tile scheduler (column-group counters [0..13], done [15])
 };
+__host__ __device__ __forceinline__ int tc_kch(const TcParams& p, int s) { return s == 0 ? p.k0 : (s == 1 ? p.k1 : p.k2); }
 
 // Persistent, warp-specialised: each CTA loops over output tiles (tile = m_tile * n_tiles + n_tile).  The four
 // pipelines run concurrently on different tiles/chunks:
@@ -196,9 +216,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int nk = 0;
-  if (p.conv) nk = 9 * p.kchunks[0];
+  if (p.conv) nk = 9 * p.k0;
   else
-    for (int s = 0; s < p.nsrc; ++s) nk += p.kchunks[s];
+    for (int s = 0; s < p.nsrc; ++s) nk += tc_kch(p, s);
   const int num_tiles = p.m_tiles * p.n_tiles;
 
   if (threadIdx.x == 0) {
@@ -246,7 +266,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         if (tile - mt * p.n_tiles != 0 && mt == (tile - 1) / p.n_tiles) return;   // same A rows as the previous n-tile
         int kc_all = 0;
         for (int src = 0; src < p.nsrc; ++src)
-          for (int kc = 0; kc < p.kchunks[src]; ++kc, ++kc_all) {
+          for (int kc = 0; kc < tc_kch(p, src); ++kc, ++kc_all) {
             const CUtensorMap* mp = src == 0 ? &mapA0 : (src == 1 ? &mapA1 : &mapA2);
             tma_prefetch_2d(mp, kc * TK, mt * TM);
           }
@@ -264,12 +284,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           const uint32_t st = base + s * STAGE_BYTES;
           mbar_expect_tx(full(s), 3 * A_BYTES);
           if (p.conv) {
-            const int tap = kc_all / p.kchunks[0], kc = kc_all - tap * p.kchunks[0];
+            const int tap = kc_all / p.k0, kc = kc_all - tap * p.k0;
             tma_load_4d(st, &mapA0, full(s), kc * TK, x0 + tap % 3 - 1, y0 + tap / 3 - 1, img);
           } else {
             int src = 0, kc = kc_all;
-            while (kc >= p.kchunks[src]) {
-              kc -= p.kchunks[src];
+            while (kc >= tc_kch(p, src)) {
+              kc -= tc_kch(p, src);
               ++src;
             }
             const CUtensorMap* mp = src == 0 ? &mapA0 : (src == 1 ? &mapA1 : &mapA2);
@@ -444,11 +464,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 // Here the splitter reads the landed A chunk once, and writes A_hi / A_lo with tcgen05.st into TMEM; the MMA
 // takes A from TMEM ([a_tmem]) and only W from shared memory.  That removes the A_hi/A_lo write-back (128 KB
 // per tile) and the A operand reads (192 KB per tile), and frees room for a 4th pipeline stage.
-//   TMEM columns: [0,128) acc0 | [128,256) acc1 | [256,320) A buffer 0 (hi 32 | lo 32) | [320,384) A buffer 1
+//   TMEM columns: [0,128) acc0 | [128,256) acc1 | [256 + 64 b, +64) A buffer b = 0..3 (hi 32 | lo 32)
 // ------------------------------------------------------------------------------------------------
 constexpr int V3_STAGES = 4;
+constexpr int V3_ABUFS = 4;                          // TMEM columns [256, 512): 4 x (A_hi 32 | A_lo 32)
 constexpr int V3_STAGE_BYTES = 3 * A_BYTES;          // A landing | W_hi | W_lo
-constexpr int V3_SMEM_BYTES = V3_STAGES * V3_STAGE_BYTES + EP_BYTES + 1024 + 256 + 512;
+constexpr int V3_TQ = 8;                             // depth of the in-CTA tile-id queue
+constexpr int V3_BAR_BYTES = 512;
+constexpr int V3_SMEM_BYTES = V3_STAGES * V3_STAGE_BYTES + EP_BYTES + 1024 + V3_BAR_BYTES + 512 /*bias*/ + 64 /*tile queue*/;
+static_assert(V3_SMEM_BYTES <= 232448, "v3 exceeds the 227 KB shared-memory limit");
 
 __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t accumulate) {
   asm volatile(
@@ -490,20 +514,32 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   const uint32_t bars = ep_base + EP_BYTES;
   auto full = [&](int s) { return bars + 8u * s; };
   auto empty = [&](int s) { return bars + 8u * (S + s); };
+  constexpr int NA = V3_ABUFS;                                    // A_hi|A_lo buffers in tensor memory
+  static_assert(V3_ABUFS == V3_STAGES, "a_free(b) doubles as the stage-release barrier: needs NA == S");
   auto a_ready = [&](int b) { return bars + 8u * (2 * S + b); };
-  auto a_free = [&](int b) { return bars + 8u * (2 * S + 2 + b); };
-  auto acc_full = [&](int a) { return bars + 8u * (2 * S + 4 + a); };
-  auto acc_empty = [&](int a) { return bars + 8u * (2 * S + 6 + a); };
-  const uint32_t tmem_slot = bars + 8u * (2 * S + 8);
-  const uint32_t w_full = bars + 8u * (2 * S + 9);
+  auto a_free = [&](int b) { return bars + 8u * (2 * S + NA + b); };
+  auto acc_full = [&](int a) { return bars + 8u * (2 * S + 2 * NA + a); };
+  auto acc_empty = [&](int a) { return bars + 8u * (2 * S + 2 * NA + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * S + 2 * NA + 4);
+  const uint32_t w_full = bars + 8u * (2 * S + 2 * NA + 5);
+  auto tq_full = [&](int i) { return bars + 8u * (2 * S + 2 * NA + 6 + i); };
+  auto tq_empty = [&](int i) { return bars + 8u * (2 * S + 2 * NA + 6 + V3_TQ + i); };
+  static_assert(8 * (2 * S + 2 * NA + 6 + 2 * V3_TQ) <= V3_BAR_BYTES, "barrier block overflow");
+  volatile int* tq = reinterpret_cast<volatile int*>(base_ptr + EP_OFF + EP_BYTES + V3_BAR_BYTES + 512);
   volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(base_ptr + EP_OFF + EP_BYTES + 8 * (2 * S + 8));
+      reinterpret_cast<volatile uint32_t*>(base_ptr + EP_OFF + EP_BYTES + 8 * (2 * S + 2 * NA + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) DBG_STAMP(7, 100);            // kernel entry
+  if (warp == 2 && lane < 6) {                         // pull the six TMA descriptors into the descriptor cache early
+    const CUtensorMap* mp = lane == 0 ? &mapA0 : lane == 1 ? &mapA1 : lane == 2 ? &mapA2 : lane == 3 ? &mapWhi
+                            : lane == 4 ? &mapWlo : &mapC;
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(mp)) : "memory");
+  }
   int nk = 0;
-  if (p.conv) nk = 9 * p.kchunks[0];
+  if (p.conv) nk = 9 * p.k0;
   else
-    for (int s = 0; s < p.nsrc; ++s) nk += p.kchunks[s];
+    for (int s = 0; s < p.nsrc; ++s) nk += tc_kch(p, s);
   const int num_tiles = p.m_tiles * p.n_tiles;
 
   if (threadIdx.x == 0) {
@@ -512,11 +548,17 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       mbar_init(empty(s), WRES ? 4 : 1);            // WRES: the splitter frees the A landing buffer
     }
     mbar_init(w_full, 1);
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < NA; ++b) {
       mbar_init(a_ready(b), 4);
       mbar_init(a_free(b), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
       mbar_init(acc_full(b), 1);
       mbar_init(acc_empty(b), 4);
+    }
+    for (int i = 0; i < V3_TQ; ++i) {
+      mbar_init(tq_full(i), 1);
+      mbar_init(tq_empty(i), 9);                     // MMA warp + 4 splitter warps + 4 epilogue warps
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -528,6 +570,7 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  if (threadIdx.x == 0) DBG_STAMP(7, 101);            // barriers + TMEM ready
 
   auto tile_coords = [&](int tile, int& m0, int& n0, int& img, int& y0, int& x0) {
     const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
@@ -543,47 +586,70 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     }
   };
 
+  // Tiles are handed out by global atomic counters (one per column tile when the weights are resident), NOT by a
+  // static blockIdx stride: when some of the grid's CTAs cannot become resident (another stream holds a few SMs)
+  // the resident CTAs simply take more tiles, instead of the late CTAs running their whole share afterwards.
+  // Warp 0 fetches ids ahead of time and publishes them through a small shared-memory queue.
+  auto take_tile = [&](int tl) -> int {               // consumer side: id of this CTA's tl-th tile, or -1
+    const int i = tl % V3_TQ;
+    mbar_wait(tq_full(i), (tl / V3_TQ) & 1);
+    const int tile = tq[i];
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tq_empty(i));
+    return tile;
+  };
+
   if (warp == 0) {
     // ---------------- TMA producer ----------------
     if (lane == 0) {
       int it = 0;
-      auto prefetch_tile = [&](int tile) {
-        if (p.conv || tile >= num_tiles) return;
-        const int mt = tile / p.n_tiles;
-        if (tile - mt * p.n_tiles != 0 && mt == (tile - 1) / p.n_tiles) return;
-        for (int src = 0; src < p.nsrc; ++src)
-          for (int kc = 0; kc < p.kchunks[src]; ++kc) {
-            const CUtensorMap* mp = src == 0 ? &mapA0 : (src == 1 ? &mapA1 : &mapA2);
-            tma_prefetch_2d(mp, kc * TK, mt * TM);
-          }
-      };
-      constexpr int PF = 2;
-      if (WRES) {                                    // gridDim.x % n_tiles == 0  =>  this CTA's column tile is fixed
-        const int n0w = (blockIdx.x % p.n_tiles) * TN;
-        mbar_expect_tx(w_full, 2 * nk * A_BYTES);
-        for (int kc = 0; kc < nk; ++kc) {
-          tma_load_2d(base + kc * A_BYTES, &mapWhi, w_full, kc * TK, n0w);
-          tma_load_2d(base + (4 + kc) * A_BYTES, &mapWlo, w_full, kc * TK, n0w);
+      const int group = WRES ? (int)(blockIdx.x % p.n_tiles) : 0;
+      int published = 0;
+      bool exhausted = false;
+      auto publish = [&]() {                          // fetch one more tile id, L2-prefetch its A rows, queue it
+        const int i = published % V3_TQ;
+        if (published >= V3_TQ) mbar_wait(tq_empty(i), ((published / V3_TQ) - 1) & 1);
+        int tile;
+        if (WRES) {
+          const int mt = atomicAdd(p.sched + group, 1);
+          tile = mt < p.m_tiles ? mt * p.n_tiles + group : -1;
+        } else {
+          tile = atomicAdd(p.sched, 1);
+          if (tile >= num_tiles) tile = -1;
         }
-      }
-      for (int r = 1; r <= PF; ++r) prefetch_tile(blockIdx.x + r * gridDim.x);
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        if (tile >= 0 && !p.conv) {
+          const int mt = tile / p.n_tiles;
+          for (int src = 0; src < p.nsrc; ++src)
+              for (int kc = 0; kc < tc_kch(p, src); ++kc) {
+                const CUtensorMap* mp = src == 0 ? &mapA0 : (src == 1 ? &mapA1 : &mapA2);
+                tma_prefetch_2d(mp, kc * TK, mt * TM);
+              }
+        }
+        tq[i] = tile;
+        mbar_arrive(tq_full(i));
+        exhausted = tile < 0;
+        ++published;
+      };
+      constexpr int PF = 2;                           // tile ids (and their L2 prefetch) run this far ahead
+      publish();
+      for (int n = 0;; ++n) {
+        const int tile = tq[n % V3_TQ];
+        if (tile < 0) break;
         int m0, n0, img, y0, x0;
         tile_coords(tile, m0, n0, img, y0, x0);
-        prefetch_tile(tile + (PF + 1) * gridDim.x);
         for (int kc_all = 0; kc_all < nk; ++kc_all, ++it) {
           const int s = it % S;
-          if (it >= S) mbar_wait(empty(s), ((it / S) - 1) & 1);
+          if (it >= S) mbar_wait(WRES ? empty(s) : a_free(s), ((it / S) - 1) & 1);
           DBG_STAMP(0, it);
           const uint32_t st = base + RING_OFF + s * STG;
           mbar_expect_tx(full(s), WRES ? A_BYTES : 3 * A_BYTES);
           if (p.conv) {
-            const int tap = kc_all / p.kchunks[0], kc = kc_all - tap * p.kchunks[0];
+            const int tap = kc_all / p.k0, kc = kc_all - tap * p.k0;
             tma_load_4d(st, &mapA0, full(s), kc * TK, x0 + tap % 3 - 1, y0 + tap / 3 - 1, img);
           } else {
             int src = 0, kc = kc_all;
-            while (kc >= p.kchunks[src]) {
-              kc -= p.kchunks[src];
+            while (kc >= tc_kch(p, src)) {
+              kc -= tc_kch(p, src);
               ++src;
             }
             const CUtensorMap* mp = src == 0 ? &mapA0 : (src == 1 ? &mapA1 : &mapA2);
@@ -594,27 +660,42 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
             tma_load_2d(st + 2 * A_BYTES, &mapWlo, full(s), kc_all * TK, n0);
           }
         }
+        if (WRES && n == 0) {
+          // resident weights (gridDim.x % n_tiles == 0 => the column tile of this CTA is fixed).  Issued AFTER the
+          // first tile's A chunks: the splitter needs A first, and 148 CTAs pulling the same 128 KB at once is
+          // the slowest part of the start-up.
+          const int n0w = group * TN;
+          mbar_expect_tx(w_full, 2 * nk * A_BYTES);
+          for (int kc = 0; kc < nk; ++kc) {
+            tma_load_2d(base + kc * A_BYTES, &mapWhi, w_full, kc * TK, n0w);
+            tma_load_2d(base + (4 + kc) * A_BYTES, &mapWlo, w_full, kc * TK, n0w);
+          }
+        }
+        while (!exhausted && published <= n + 1 + PF) publish();   // ids (atomics) + L2 prefetch run ahead of the loads
       }
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer: A from TMEM, W from shared memory ----------------
-    int it = 0, tl = 0;
-    if (WRES) mbar_wait(w_full, 0);
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+    // The whole warp runs the (uniform) control flow; the tcgen05 instructions sit under an elect.sync predicate.
+    // (Under a plain `lane == 0` branch ptxas wraps every UTCMMA in an ELECT / BRA.U.ANY loop over the active
+    // lanes, ~45 cycles per instruction: the issue thread, not the tensor pipe, then sets the pace.)
+    int it = 0;
+    for (int tl = 0;; ++tl) {
+      if (take_tile(tl) < 0) break;
+      if (WRES && tl == 0) mbar_wait(w_full, 0);
       const int a = tl & 1;
       if (tl >= 2) mbar_wait(acc_empty(a), ((tl >> 1) - 1) & 1);
-      tc_fence_after();
       const uint32_t tmem_acc = tmem_base + (uint32_t)(a * TN);
       for (int kc_all = 0; kc_all < nk; ++kc_all, ++it) {
-        const int s = it % S, b = it & 1;
-        mbar_wait(a_ready(b), (it >> 1) & 1);       // A_hi/A_lo of this chunk are in TMEM (implies full[s])
+        const int s = it % S, b = it % NA;
+        mbar_wait(a_ready(b), (it / NA) & 1);       // A_hi/A_lo of this chunk are in TMEM (implies full[s])
         tc_fence_after();
-        if (lane == 0) {
+        const uint32_t st = base + RING_OFF + s * STG;
+        const uint32_t whi_base = WRES ? base + kc_all * A_BYTES : st + A_BYTES;
+        const uint32_t wlo_base = WRES ? base + (4 + kc_all) * A_BYTES : st + 2 * A_BYTES;
+        const uint32_t ta = tmem_base + 256u + (uint32_t)(b * 64);
+        if (elect_one()) {
           DBG_STAMP(3, it);
-          const uint32_t st = base + RING_OFF + s * STG;
-          const uint32_t whi_base = WRES ? base + kc_all * A_BYTES : st + A_BYTES;
-          const uint32_t wlo_base = WRES ? base + (4 + kc_all) * A_BYTES : st + 2 * A_BYTES;
-          const uint32_t ta = tmem_base + 256u + (uint32_t)(b * 64);
 #pragma unroll
           for (int k = 0; k < TK / 8; ++k) {
             const uint64_t w_hi = umma_desc(whi_base + k * 32), w_lo = umma_desc(wlo_base + k * 32);
@@ -622,7 +703,8 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
             umma_tf32_ts(tmem_acc, ta + (uint32_t)(k * 8), w_lo, 1);                          // A_hi * W_lo
             umma_tf32_ts(tmem_acc, ta + (uint32_t)(k * 8), w_hi, 1);                          // A_hi * W_hi
           }
-          if (!WRES) umma_commit(empty(s));
+          // one commit per chunk: a_free(b) releases the TMEM A buffer to the splitter AND (streamed weights,
+          // NA == S so b == s) the shared-memory stage to the TMA producer
           umma_commit(a_free(b));
           if (kc_all == nk - 1) umma_commit(acc_full(a));
           DBG_STAMP(4, it);
@@ -635,9 +717,10 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     const int qd = warp & 3;                          // TMEM lane quarter of this warp
     const int row = qd * 32 + lane;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tl = 0;; ++tl) {
+      if (take_tile(tl) < 0) break;
       for (int kc_all = 0; kc_all < nk; ++kc_all, ++it) {
-        const int s = it % S, b = it & 1;
+        const int s = it % S, b = it % NA;
         mbar_wait(full(s), (it / S) & 1);
         if (threadIdx.x == 64) DBG_STAMP(1, it);
         const uint8_t* arow = base_ptr + RING_OFF + s * STG + row * 128;
@@ -656,7 +739,7 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           __syncwarp();
           if (lane == 0) mbar_arrive(empty(s));
         }
-        if (it >= 2) mbar_wait(a_free(b), ((it >> 1) - 1) & 1);   // MMAs that read this TMEM A buffer retired
+        if (it >= NA) mbar_wait(a_free(b), ((it / NA) - 1) & 1);  // MMAs that read this TMEM A buffer retired
         tc_fence_after();
         const uint32_t ta = tmem_base + ((uint32_t)(qd * 32) << 16) + 256u + (uint32_t)(b * 64);
         tmem_st32(ta, hi);
@@ -670,13 +753,19 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     }
   } else {
     // ---------------- epilogue (warps 6..9): TMEM -> registers -> swizzled smem -> TMA store ----------------
+    // Per tile a warp owns 32 accumulator rows.  It reads them 64 columns at a time (two tcgen05.ld in flight),
+    // applies bias / residual / activation in registers, stages each 32x32 block in a 128B-swizzled 4 KB buffer and
+    // hands it to the TMA store engine (which also clips the M / N edges).  Two staging buffers per warp:
+    // cp.async.bulk.wait_group.read 1 before a buffer is rewritten.  The accumulator is released to the MMA warp
+    // as soon as the last tcgen05.ld of the tile has completed, i.e. before the stores of that tile are issued.
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const uint32_t my_ep = ep_base + (uint32_t)((warp - 6) * 2) * 4096u;
-    uint8_t* my_ep_ptr = base_ptr + EP_OFF + (warp - 6) * 2 * 4096;
-    float* bias_s = reinterpret_cast<float*>(base_ptr + EP_OFF + EP_BYTES + 256);
+    float* bias_s = reinterpret_cast<float*>(base_ptr + EP_OFF + EP_BYTES + V3_BAR_BYTES);
     int tl = 0, chunk = 0, bias_n0 = -1;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+    for (;; ++tl) {
+      const int tile = take_tile(tl);
+      if (tile < 0) break;
       int m0, n0, img, y0, x0;
       tile_coords(tile, m0, n0, img, y0, x0);
       if (n0 != bias_n0) {
@@ -698,94 +787,86 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         grow = min((long long)(m0 + row), (long long)p.M - 1);
       }
       const float* resrow = p.res ? p.res + (size_t)(grow % p.res_mod) * p.ldres : nullptr;
-#pragma unroll 1
-      for (int c0 = 0; c0 < TN; c0 += 32, ++chunk) {
+      const int act = p.act;
+      const int ncols = min(TN, p.N - n0);                       // valid columns of this tile (multiple of 4)
+
+      auto finish_block = [&](float (&v)[32], int c0) {          // bias/res/act -> staging -> TMA store
         const int col = n0 + c0;
-        if (col >= p.N) break;
-        const bool fullc = col + 32 <= p.N;
-        float v[32];
-        if (threadIdx.x == 192) DBG_STAMP(7, chunk * 5 + 0);
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TN + c0), v);
-        if (p.dbg & 4) continue;                      // experiment: skip staging + store
-        if (threadIdx.x == 192) DBG_STAMP(7, chunk * 5 + 1);
-        const uint32_t buf = (uint32_t)(chunk & 1) * 4096u;
+        const bool fullc = c0 + 32 <= ncols;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + 4 * j);      // broadcast LDS
           v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
         }
         if (resrow) {
+          if (fullc) {
+            float4 r4[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if (fullc) {
-              const float4 r4 = ldg4(resrow + col + 4 * j);
-              v[4 * j] += r4.x; v[4 * j + 1] += r4.y; v[4 * j + 2] += r4.z; v[4 * j + 3] += r4.w;
-            } else {
+            for (int j = 0; j < 8; ++j) r4[j] = ldg4(resrow + col + 4 * j);
 #pragma unroll
-              for (int e = 0; e < 4; ++e)
-                if (col + 4 * j + e < p.N) v[4 * j + e] += __ldg(resrow + col + 4 * j + e);
+            for (int j = 0; j < 8; ++j) {
+              v[4 * j] += r4[j].x; v[4 * j + 1] += r4[j].y; v[4 * j + 2] += r4[j].z; v[4 * j + 3] += r4[j].w;
             }
-          }
-        }
-        act_tile(v, p.act);
-        if (threadIdx.x == 192) DBG_STAMP(7, chunk * 5 + 2);
-        if (g_direct_store) {                         // registers -> global, no shared-memory staging
-          long long gr2;
-          bool ok2;
-          if (p.conv) {
-            const int yy = y0 + row / 16, xx = x0 + row % 16;
-            ok2 = yy < p.H && xx < p.W;
-            gr2 = ((long long)img * p.H + yy) * p.W + xx;
           } else {
-            gr2 = (long long)m0 + row;
-            ok2 = gr2 < p.M;
-          }
-          if (ok2) {
-            float* dst = p.C + (size_t)gr2 * p.ldc + col;
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (col + 4 * j < p.N)
-                *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            for (int j = 0; j < 32; ++j)
+              if (c0 + j < ncols) v[j] += __ldg(resrow + col + j);
           }
-          if (threadIdx.x == 192) DBG_STAMP(7, chunk * 5 + 4);
-          continue;
         }
+        act_tile(v, act);
+        const uint32_t buf = my_ep + (uint32_t)(chunk & 1) * 4096u;
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // buffer's previous store done
+        __syncwarp();
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<float4*>(my_ep_ptr + buf + lane * 128 + ((j ^ (lane & 7)) << 4)) =
-              make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(buf + lane * 128 + ((j ^ (lane & 7)) << 4)),
+                       "f"(v[4 * j]), "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
+                       : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
-        if (threadIdx.x == 192) DBG_STAMP(7, chunk * 5 + 3);
-        // transposed read-back: each store instruction writes 4 rows x 128 contiguous bytes
-        const int unit = lane & 7;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = i * 4 + (lane >> 3);                     // row inside this warp's 32-row slab
-          const float4 o = *reinterpret_cast<const float4*>(my_ep_ptr + buf + r * 128 + ((unit ^ (r & 7)) << 4));
-          long long gr;
-          bool ok;
-          if (p.conv) {
-            const int yy = y0 + 2 * q + (r >> 4), xx = x0 + (r & 15);
-            ok = yy < p.H && xx < p.W;
-            gr = ((long long)img * p.H + yy) * p.W + xx;
-          } else {
-            gr = (long long)m0 + 32 * q + r;
-            ok = gr < p.M;
-            if (p.dbg & 8) gr = (long long)blockIdx.x * 128 + 32 * q + r;   // experiment: L2-resident destination
-          }
-          const int cc = col + unit * 4;
-          if (ok && cc < p.N) *reinterpret_cast<float4*>(p.C + (size_t)gr * p.ldc + cc) = o;
+        if (lane == 0 && !(p.dbg & 4)) {
+          if (p.conv) tma_store_4d(&mapC, buf, col, x0, y0 + 2 * q, img);
+          else tma_store_2d(&mapC, buf, col, m0 + 32 * q);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
-        if (threadIdx.x == 192) DBG_STAMP(7, chunk * 5 + 4);
+        ++chunk;
+      };
+
+      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TN);
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        const int c0 = h * 64;
+        if (c0 >= ncols) break;
+        const bool two = c0 + 32 < ncols;
+        float v0[32], v1[32];
+        tmem_ld32_nowait(tacc + (uint32_t)c0, v0);
+        if (two) tmem_ld32_nowait(tacc + (uint32_t)(c0 + 32), v1);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (h == 1 || c0 + 64 >= ncols) {                        // last TMEM read of this tile: release the accumulator
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty(a));
+        }
+        if (threadIdx.x == 192) DBG_STAMP(7, (tl * 2 + h) * 3 + 0);
+        finish_block(v0, c0);
+        if (threadIdx.x == 192) DBG_STAMP(7, (tl * 2 + h) * 3 + 1);
+        if (two) finish_block(v1, c0 + 32);
+        if (threadIdx.x == 192) DBG_STAMP(7, (tl * 2 + h) * 3 + 2);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty(a));
       if (threadIdx.x == 192) DBG_STAMP(6, tl);
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores retired before exit
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) DBG_STAMP(7, 102);            // all roles done
+  if (threadIdx.x == 0) {                              // the last CTA to finish re-arms the scheduler slot
+    __threadfence();
+    if (atomicAdd(p.sched + 15, 1) == (int)gridDim.x - 1) {
+      for (int i = 0; i < 16; ++i) p.sched[i] = 0;
+      __threadfence();
+    }
+  }
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -857,11 +938,19 @@ bool make_store_map_nhwc(CUtensorMap* m, float* ptr, int N, int H, int W, int C)
 }
 
 bool g_attr_set = false, g_attr_set_v3 = false;
+// dynamic tile scheduler state: a ring of 256 zero-initialised slots of 16 ints; launch n uses slot n % 256 and the
+// last CTA of a launch zeroes its slot again, so a slot is clean long before it comes round (also under graph replay,
+// where the slot index is baked into the captured launch).
+constexpr int SCHED_SLOTS = 256;
+__device__ int g_sched[SCHED_SLOTS * 16];
+int* g_sched_ptr = nullptr;
+unsigned g_sched_seq = 0;
 int g_tc_debug = 0;
 int g_tc_wres = 1;    // keep the weight slice resident in shared memory when K <= 128
 int g_tc_mode = 3;   // 3: A operand through tensor memory (default); 2: A operand through shared memory
 
-int launch_tc(const CUtensorMap maps[6], const TcParams& p, cudaStream_t stream, const char* name) {
+int launch_tc(const CUtensorMap maps[6], const TcParams& p_in, cudaStream_t stream, const char* name) {
+  TcParams p = p_in;
   if (g_num_sms == 0) {
     int devid = 0;
     cudaGetDevice(&devid);
@@ -886,9 +975,14 @@ int launch_tc(const CUtensorMap maps[6], const TcParams& p, cudaStream_t stream,
       }
       g_attr_set_v3 = true;
     }
+    if (!g_sched_ptr && cudaGetSymbolAddress(reinterpret_cast<void**>(&g_sched_ptr), g_sched) != cudaSuccess) {
+      di_set_error("%s: cannot resolve the scheduler buffer", name);
+      return DI_ERR_LAUNCH;
+    }
+    p.sched = g_sched_ptr + 16 * (g_sched_seq++ % SCHED_SLOTS);
     int nk = 0;
-    for (int s2 = 0; s2 < p.nsrc; ++s2) nk += p.kchunks[s2];
-    const bool wres = !p.conv && nk <= 4 && g_tc_wres;
+    for (int s2 = 0; s2 < p.nsrc; ++s2) nk += tc_kch(p, s2);
+    const bool wres = !p.conv && nk <= 4 && g_tc_wres && p.n_tiles <= 14;
     if (wres) {
       // every CTA keeps one column tile's weights resident: the grid must be a multiple of n_tiles
       int g2 = tiles < g_num_sms ? tiles : (g_num_sms / p.n_tiles) * p.n_tiles;
@@ -969,7 +1063,7 @@ int di_linear_tc_f32(const float* A0, int lda0, int K0, const float* A1, int lda
   }
   TcParams p{};
   p.M = M; p.N = N; p.nsrc = nsrc;
-  for (int s = 0; s < 3; ++s) p.kchunks[s] = Ks[s] / TK;
+  p.k0 = Ks[0] / TK; p.k1 = Ks[1] / TK; p.k2 = Ks[2] / TK;
   p.conv = 0; p.C = C; p.ldc = ldc; p.bias = bias; p.res = res; p.ldres = ldres;
   p.res_mod = res_mod > 0 ? res_mod : M; p.act = act; p.dbg = g_tc_debug;
   p.m_tiles = di_cdiv(M, TM);
@@ -1003,7 +1097,7 @@ int di_conv3x3_tc_f32(const float* x, const float* w_hi, const float* w_lo, cons
     return DI_ERR_LAUNCH;
   }
   TcParams p{};
-  p.M = N * H * W; p.N = Cout; p.nsrc = 1; p.kchunks[0] = Cin / TK; p.conv = 1; p.H = H; p.W = W;
+  p.M = N * H * W; p.N = Cout; p.nsrc = 1; p.k0 = Cin / TK; p.conv = 1; p.H = H; p.W = W;
   p.tiles_x = di_cdiv(W, 16); p.tiles_y = di_cdiv(H, 8);
   p.C = y; p.ldc = Cout; p.bias = bias; p.res = nullptr; p.ldres = 0; p.res_mod = 1; p.act = act; p.dbg = g_tc_debug;
   p.m_tiles = N * p.tiles_x * p.tiles_y;
