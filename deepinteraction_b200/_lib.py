@@ -22,7 +22,9 @@ SIGNATURES = {
     'di_linear_f32': [_p, _i, _i, _p, _i, _i, _p, _i, _i, _p, _p, _p, _i, _i, _p, _i, _i, _i, _i, _i, _ll, _p],
     'di_conv3x3_f32': [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     'di_linear_tc_f32': [_p, _i, _i, _p, _i, _i, _p, _i, _i, _p, _p, _p, _p, _i, _i, _p, _i, _i, _i, _i, _p],
+    'di_linear_tcb_f32': [_p, _i, _i, _p, _i, _i, _p, _i, _i, _p, _p, _p, _p, _i, _i, _p, _i, _i, _i, _i, _p],
     'di_conv3x3_tc_f32': [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
+    'di_conv3x3_tcb_f32': [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     'di_tc_set_debug': [_i],
     'di_tc_set_mode': [_i],
     'di_tc_debug_read': [ctypes.POINTER(ctypes.c_longlong)],

@@ -1,38 +1,39 @@
 // Blackwell tensor-core path of the dense layers: C[M,N] = act(A[M,K] * W[N,K]^T + bias (+res)), fp32 in/out,
-// computed as an error-compensated 3xTF32 product on tcgen05 (UMMA) with the accumulator in TMEM:
+// computed as an error-compensated SPLIT product on tcgen05 (UMMA) with the accumulator in tensor memory:
 //
-//     A = A_hi + A_lo,  W = W_hi + W_lo   (hi = value rounded to 10 mantissa bits, lo = exact remainder)
-//     A*W ~= A_hi*W_hi + A_lo*W_hi + A_hi*W_lo                (dropped term ~2^-22 relative)
+//     A = A_hi + A_lo,  W = W_hi + W_lo,    A*W ~= A_hi*W_hi + A_lo*W_hi + A_hi*W_lo
 //
-// which keeps the result fp32-faithful (the parity bar of this path includes exact top-k indices, so plain
-// TF32/BF16 is not admissible).  Same layers as gemm.cu: every 1x1 Conv(+BN)(+ReLU) / cat+conv pair
-// (reference models/utils/encoder_utils.py:11-34, models/necks/deepinteraction_encoder.py:26-32) and the
-// 3x3 convs as implicit GEMM over pixel-major (NHWC) maps (models/necks/deepinteraction_encoder.py:47-62,
-// models/dense_heads/deepinteraction_decoder.py:83-101).
+// with either hi = tf32(x) ("3xTF32", dropped term ~2^-22) or hi = bf16(x), lo = bf16(x - hi) ("bf16 split", 16
+// mantissa bits kept, error ~1e-5) -- see the BF template flag below.  A plain TF32/BF16 product is not admissible:
+// the parity bar of this path is 1e-3 end to end over ~40 chained layers and includes exact top-k indices.
+// Same layers as gemm.cu: every 1x1 Conv(+BN)(+ReLU) / cat+conv pair (reference models/utils/encoder_utils.py:11-34,
+// models/necks/deepinteraction_encoder.py:26-32) and the 3x3 convs as implicit GEMM over pixel-major (NHWC) maps
+// (models/necks/deepinteraction_encoder.py:47-62, models/dense_heads/deepinteraction_decoder.py:83-101).
 //
-// Persistent CTAs (one per SM) loop over 128 x 128 output tiles; 320 threads, warp-specialised:
-//   warp 0      TMA producer: per 32-wide K chunk, box loads of A (2-D [rows,K] map, or a 4-D NHWC map whose
-//               8x16-pixel box shifted by the filter tap gives zero padding for free) and of W_hi / W_lo
-//               into a 3-stage ring of 128B-swizzled K-major tiles (cp.async.bulk.tensor + mbarrier tx-count)
-//   warps 2-5   splitter: rewrite the landed A chunk in place as A_hi and write A_lo beside it
-//               (elementwise, so the swizzle is irrelevant), fence.proxy.async, arrive
-//   warp 1      MMA issuer: 4 k-steps x 3 products of tcgen05.mma.kind::tf32 (M=128,N=128,K=8) per chunk,
-//               tcgen05.commit frees the stage; accumulator = 128 TMEM columns
-//   warps 6-9   epilogue: tcgen05.ld (32 lanes x 32 columns per warp and step) -> bias/res/activation -> 128B-
-//               swizzled staging tile in shared memory -> cp.async.bulk.tensor store (coalesced, asynchronous);
-//               overlaps the next tile's main loop through a double-buffered TMEM accumulator (2 x 128 columns)
+// Persistent CTAs (one per SM) take 128 x 128 output tiles from a global atomic counter; 320 threads,
+// warp-specialised, all hand-offs through mbarriers:
+//   warp 0      TMA producer: tile ids (atomics, published through a shared-memory queue, L2 prefetch of the next
+//               tiles' A rows) and, per K chunk, box loads of fp32 A (2-D [rows,K] map, or a 4-D NHWC map whose
+//               8x16-pixel box shifted by the filter tap gives the zero padding for free) and of W_hi / W_lo into a
+//               ring of 128B-swizzled K-major tiles (cp.async.bulk.tensor + mbarrier tx-count).  For K <= 128 the
+//               weight slice is loaded once and stays resident.
+//   warps 2-5   splitter: landed A chunk -> registers -> hi / lo -> tcgen05.st into TENSOR MEMORY (A never goes
+//               back to shared memory)
+//   warp 1      MMA issuer (elect.sync): per chunk 4 k-steps x 3 products of tcgen05.mma (M=128, N=128), A operand
+//               from TMEM, W from shared memory; one tcgen05.commit per chunk releases the A buffer and the stage
+//   warps 6-9   epilogue: tcgen05.ld (two 32-column loads in flight) -> bias / residual / activation -> 128B-
+//               swizzled staging buffer -> cp.async.bulk.tensor store; overlaps the next tile's main loop through
+//               a double-buffered accumulator
+//   TMEM columns: [0,128) acc0 | [128,256) acc1 | [256 + 64 b, +64) A buffer b (hi 32 | lo 32)
 #include "common.cuh"
 #include <cuda.h>
 
 namespace {
 
 constexpr int TM = 128, TN = 128, TK = 32;          // tile; TK fp32 = 128 bytes = one swizzle row
-constexpr int STAGES = 3;
 constexpr int A_BYTES = TM * TK * 4;                // 16 KB
-constexpr int STAGE_BYTES = 4 * A_BYTES;            // A_hi | A_lo | W_hi | W_lo
 constexpr int NTHREADS = 320;
 constexpr int EP_BYTES = 4 /*warps*/ * 2 /*buffers*/ * 32 * 128;   // epilogue staging: 32 rows x 128 B per buffer
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EP_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 512 /*bias*/;
 int g_num_sms = 0;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -103,13 +104,6 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
 // kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 128
 constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(
-          tmem_d),
-      "l"(da), "l"(db), "r"(IDESC), "r"(accumulate)
-      : "memory");
-}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -121,23 +115,7 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// same without the wait: issue several loads, then one tcgen05.wait::ld (asm volatile keeps the order)
+// tcgen05.ld of 32 lanes x 32 columns; the caller issues several, then one tcgen05.wait::ld (asm volatile keeps the order)
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -191,272 +169,6 @@ struct TcParams {
 };
 __host__ __device__ __forceinline__ int tc_kch(const TcParams& p, int s) { return s == 0 ? p.k0 : (s == 1 ? p.k1 : p.k2); }
 
-// Persistent, warp-specialised: each CTA loops over output tiles (tile = m_tile * n_tiles + n_tile).  The four
-// pipelines run concurrently on different tiles/chunks:
-//   TMA (warp 0) -> split hi/lo (warps 2-5) -> tcgen05.mma (warp 1) -> epilogue TMEM->regs->global (warps 6-9)
-// with a 3-stage shared-memory ring and a double-buffered TMEM accumulator (2 x 128 columns).
-__global__ void __launch_bounds__(NTHREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-               const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapWhi,
-               const __grid_constant__ CUtensorMap mapWlo, const __grid_constant__ CUtensorMap mapC,
-               const TcParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;        // SWIZZLE_128B needs 1024-byte alignment
-  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t ep_base = base + STAGES * STAGE_BYTES;              // epilogue staging (1024-byte aligned)
-  const uint32_t bars = ep_base + EP_BYTES;
-  auto full = [&](int s) { return bars + 8u * s; };
-  auto split = [&](int s) { return bars + 8u * (STAGES + s); };
-  auto empty = [&](int s) { return bars + 8u * (2 * STAGES + s); };
-  auto acc_full = [&](int a) { return bars + 8u * (3 * STAGES + a); };
-  auto acc_empty = [&](int a) { return bars + 8u * (3 * STAGES + 2 + a); };
-  const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 4);
-  volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(base_ptr + STAGES * STAGE_BYTES + EP_BYTES + 8 * (3 * STAGES + 4));
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int nk = 0;
-  if (p.conv) nk = 9 * p.k0;
-  else
-    for (int s = 0; s < p.nsrc; ++s) nk += tc_kch(p, s);
-  const int num_tiles = p.m_tiles * p.n_tiles;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full(s), 1);
-      mbar_init(split(s), 4);
-      mbar_init(empty(s), 1);
-    }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(acc_full(a), 1);
-      mbar_init(acc_empty(a), 4);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {  // TMEM: 2 x 128 columns (double-buffered 128x128 fp32 accumulator)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(256u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
-
-  auto tile_coords = [&](int tile, int& m0, int& n0, int& img, int& y0, int& x0) {
-    const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
-    n0 = nt * TN;
-    m0 = mt * TM;
-    img = 0; y0 = 0; x0 = 0;
-    if (p.conv) {
-      int t = mt;
-      img = t / (p.tiles_x * p.tiles_y);
-      t -= img * p.tiles_x * p.tiles_y;
-      y0 = (t / p.tiles_x) * 8;
-      x0 = (t % p.tiles_x) * 16;
-    }
-  };
-
-  if (warp == 0) {
-    // ---------------- TMA producer ----------------
-    if (lane == 0) {
-      int it = 0;
-      auto prefetch_tile = [&](int tile) {
-        if (p.conv || tile >= num_tiles) return;
-        const int mt = tile / p.n_tiles;
-        if (tile - mt * p.n_tiles != 0 && mt == (tile - 1) / p.n_tiles) return;   // same A rows as the previous n-tile
-        int kc_all = 0;
-        for (int src = 0; src < p.nsrc; ++src)
-          for (int kc = 0; kc < tc_kch(p, src); ++kc, ++kc_all) {
-            const CUtensorMap* mp = src == 0 ? &mapA0 : (src == 1 ? &mapA1 : &mapA2);
-            tma_prefetch_2d(mp, kc * TK, mt * TM);
-          }
-      };
-      constexpr int PF = 2;                                       // prefetch distance in rounds of tiles
-      for (int r = 1; r <= PF; ++r) prefetch_tile(blockIdx.x + r * gridDim.x);
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        int m0, n0, img, y0, x0;
-        tile_coords(tile, m0, n0, img, y0, x0);
-        prefetch_tile(tile + (PF + 1) * gridDim.x);
-        for (int kc_all = 0; kc_all < nk; ++kc_all, ++it) {
-          const int s = it % STAGES;
-          if (it >= STAGES) mbar_wait(empty(s), ((it / STAGES) - 1) & 1);
-          DBG_STAMP(0, it);                          // producer: slot free, issuing TMA
-          const uint32_t st = base + s * STAGE_BYTES;
-          mbar_expect_tx(full(s), 3 * A_BYTES);
-          if (p.conv) {
-            const int tap = kc_all / p.k0, kc = kc_all - tap * p.k0;
-            tma_load_4d(st, &mapA0, full(s), kc * TK, x0 + tap % 3 - 1, y0 + tap / 3 - 1, img);
-          } else {
-            int src = 0, kc = kc_all;
-            while (kc >= tc_kch(p, src)) {
-              kc -= tc_kch(p, src);
-              ++src;
-            }
-            const CUtensorMap* mp = src == 0 ? &mapA0 : (src == 1 ? &mapA1 : &mapA2);
-            tma_load_2d(st, mp, full(s), kc * TK, m0);
-          }
-          tma_load_2d(st + 2 * A_BYTES, &mapWhi, full(s), kc_all * TK, n0);
-          tma_load_2d(st + 3 * A_BYTES, &mapWlo, full(s), kc_all * TK, n0);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ---------------- MMA issuer ----------------
-    int it = 0, tl = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
-      const int a = tl & 1;
-      if (tl >= 2) mbar_wait(acc_empty(a), ((tl >> 1) - 1) & 1);   // epilogue drained this accumulator
-      tc_fence_after();
-      const uint32_t tmem_acc = tmem_base + (uint32_t)(a * TN);
-      for (int kc_all = 0; kc_all < nk; ++kc_all, ++it) {
-        const int s = it % STAGES;
-        mbar_wait(split(s), (it / STAGES) & 1);     // implies the TMA bytes landed and A_hi/A_lo are written
-        tc_fence_after();
-        if (lane == 0) {
-          DBG_STAMP(3, it);                          // mma: operands ready
-          const uint32_t st = base + s * STAGE_BYTES;
-#pragma unroll
-          for (int k = 0; k < TK / 8; ++k) {
-            const uint64_t a_hi = umma_desc(st + k * 32), a_lo = umma_desc(st + A_BYTES + k * 32);
-            const uint64_t w_hi = umma_desc(st + 2 * A_BYTES + k * 32), w_lo = umma_desc(st + 3 * A_BYTES + k * 32);
-            umma_tf32(tmem_acc, a_lo, w_hi, (kc_all | k) != 0);   // small terms first
-            umma_tf32(tmem_acc, a_hi, w_lo, 1);
-            umma_tf32(tmem_acc, a_hi, w_hi, 1);
-          }
-          umma_commit(empty(s));                      // stage reusable once these MMAs retire
-          if (kc_all == nk - 1) umma_commit(acc_full(a));
-          DBG_STAMP(4, it);                          // mma: issued + committed
-        }
-        __syncwarp();
-      }
-    }
-  } else if (warp < 6) {
-    // ---------------- splitter (warps 2..5, 128 threads) ----------------
-    const int et = threadIdx.x - 64;                // 0..127
-    int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      for (int kc_all = 0; kc_all < nk; ++kc_all, ++it) {
-        const int s = it % STAGES;
-        mbar_wait(full(s), (it / STAGES) & 1);
-        if (et == 0) DBG_STAMP(1, it);               // splitter: TMA bytes landed
-        float4* hi = reinterpret_cast<float4*>(base_ptr + s * STAGE_BYTES);
-        float4* lo = reinterpret_cast<float4*>(base_ptr + s * STAGE_BYTES + A_BYTES);
-#pragma unroll
-        for (int j = 0; j < A_BYTES / 16 / 128; ++j) {
-          float4 a = hi[et + j * 128], h, l;
-          h.x = __uint_as_float(__float_as_uint(a.x) & 0xFFFFE000u);
-          h.y = __uint_as_float(__float_as_uint(a.y) & 0xFFFFE000u);
-          h.z = __uint_as_float(__float_as_uint(a.z) & 0xFFFFE000u);
-          h.w = __uint_as_float(__float_as_uint(a.w) & 0xFFFFE000u);
-          l.x = a.x - h.x; l.y = a.y - h.y; l.z = a.z - h.z; l.w = a.w - h.w;
-          hi[et + j * 128] = h;
-          lo[et + j * 128] = l;
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
-        __syncwarp();
-        if (lane == 0) mbar_arrive(split(s));
-        if (et == 0) DBG_STAMP(2, it);               // splitter: done
-      }
-    }
-  } else {
-    // ---------------- epilogue (warps 6..9): TMEM -> registers -> swizzled smem -> TMA store ----------------
-    const int q = warp & 3;                          // TMEM lane quarter this warp may access
-    const int row = q * 32 + lane;                   // tile row held by this thread
-    const uint32_t my_ep = ep_base + (uint32_t)((warp - 6) * 2) * 4096u;
-    uint8_t* my_ep_ptr = base_ptr + STAGES * STAGE_BYTES + (warp - 6) * 2 * 4096;
-    // bias slice of the current column tile lives in shared memory: a global (even L2-resident) load in the
-    // epilogue's dependency chain costs ~2000 cycles per 32-column step under TMA load
-    float* bias_s = reinterpret_cast<float*>(base_ptr + STAGES * STAGE_BYTES + EP_BYTES + 256);
-    int tl = 0, chunk = 0, bias_n0 = -1;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
-      int m0, n0, img, y0, x0;
-      tile_coords(tile, m0, n0, img, y0, x0);
-      if (n0 != bias_n0) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");          // previous tile's readers are done
-        const int c = n0 + (int)threadIdx.x - 192;
-        bias_s[threadIdx.x - 192] = (p.bias && c < p.N) ? __ldg(p.bias + c) : 0.f;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        bias_n0 = n0;
-      }
-      const int a = tl & 1;
-      mbar_wait(acc_full(a), (tl >> 1) & 1);
-      tc_fence_after();
-      if (threadIdx.x == 192) DBG_STAMP(5, tl);      // epilogue: accumulator ready
-      long long grow;
-      if (p.conv) {
-        const int yy = min(y0 + row / 16, p.H - 1), xx = min(x0 + row % 16, p.W - 1);
-        grow = ((long long)img * p.H + yy) * p.W + xx;
-      } else {
-        grow = min((long long)(m0 + row), (long long)p.M - 1);
-      }
-      const float* resrow = p.res ? p.res + (size_t)(grow % p.res_mod) * p.ldres : nullptr;
-#pragma unroll 1
-      for (int c0 = 0; c0 < TN; c0 += 32, ++chunk) {
-        const int col = n0 + c0;
-        if (col >= p.N) break;                       // warp-uniform: nothing to store in this column block
-        const bool fullc = col + 32 <= p.N;
-        float v[32];
-        if (threadIdx.x == 192) DBG_STAMP(7, chunk * 4 + 0);
-        if (p.dbg & 2) {                              // experiment: skip the TMEM read
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 1.f;
-        } else {
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TN + c0), v);   // warp-collective
-        }
-        if (threadIdx.x == 192) DBG_STAMP(7, chunk * 4 + 1);
-        if (p.dbg & 4) continue;                      // experiment: skip staging + store
-        // the staging buffer used two chunks ago must have been read by its TMA store
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        __syncwarp();
-        const uint32_t buf = (uint32_t)(chunk & 1) * 4096u;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + 4 * j);      // broadcast LDS
-          v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
-        }
-        if (resrow) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if (fullc) {
-              const float4 r4 = ldg4(resrow + col + 4 * j);
-              v[4 * j] += r4.x; v[4 * j + 1] += r4.y; v[4 * j + 2] += r4.z; v[4 * j + 3] += r4.w;
-            } else {
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                if (col + 4 * j + e < p.N) v[4 * j + e] += __ldg(resrow + col + 4 * j + e);
-            }
-          }
-        }
-        act_tile(v, p.act);
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<float4*>(my_ep_ptr + buf + lane * 128 + ((j ^ (lane & 7)) << 4)) =
-              make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        if (threadIdx.x == 192) DBG_STAMP(7, chunk * 4 + 2);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (threadIdx.x == 192) DBG_STAMP(7, chunk * 4 + 3);
-        if (lane == 0) {
-          if (p.conv) tma_store_4d(&mapC, my_ep + buf, col, x0, y0 + 2 * q, img);
-          else tma_store_2d(&mapC, my_ep + buf, col, m0 + 32 * q);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty(a));
-      if (threadIdx.x == 192) DBG_STAMP(6, tl);      // epilogue: tile handed to the TMA store engine
-    }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores retired before exit
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
 // v3: A operand through TENSOR MEMORY.  Shared-memory bandwidth is the limiter of the 3xTF32 scheme (every
 // k-step re-reads A_hi twice, A_lo once and W_hi twice, W_lo once from shared memory, on top of the TMA writes,
@@ -466,13 +178,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 // per tile) and the A operand reads (192 KB per tile), and frees room for a 4th pipeline stage.
 //   TMEM columns: [0,128) acc0 | [128,256) acc1 | [256 + 64 b, +64) A buffer b = 0..3 (hi 32 | lo 32)
 // ------------------------------------------------------------------------------------------------
-constexpr int V3_STAGES = 4;
-constexpr int V3_ABUFS = 4;                          // TMEM columns [256, 512): 4 x (A_hi 32 | A_lo 32)
-constexpr int V3_STAGE_BYTES = 3 * A_BYTES;          // A landing | W_hi | W_lo
+//
+// Two operand precisions share this kernel (template flag BF):
+//   BF = false  "3xTF32": x = hi + lo with hi = tf32(x); products A_lo W_hi + A_hi W_lo + A_hi W_hi on kind::tf32
+//               (K = 8 per instruction), 32 k-values per pipeline chunk.  Error ~2^-21 per product.
+//   BF = true   "bf16 split": x = hi + mid with hi = bf16(x), mid = bf16(x - hi) (16 mantissa bits kept);
+//               products A_mid W_hi + A_hi W_mid + A_hi W_hi on kind::f16 (K = 16 per instruction), 64 k-values
+//               per chunk.  Error ~3 * 2^-18 per product (1e-5), far inside the 1e-3 budget of the path, for HALF
+//               the tensor-pipe time, half the tensor-memory writes and half the weight bytes per k.
+// Chunk geometry is chosen so that both variants use the same operand tiles: a weight chunk is 128 rows x 128 B
+// (32 tf32 or 64 bf16), an A chunk occupies 32 + 32 TMEM columns, and one chunk is 4 MMA k-steps of 32 bytes.
 constexpr int V3_TQ = 8;                             // depth of the in-CTA tile-id queue
 constexpr int V3_BAR_BYTES = 512;
-constexpr int V3_SMEM_BYTES = V3_STAGES * V3_STAGE_BYTES + EP_BYTES + 1024 + V3_BAR_BYTES + 512 /*bias*/ + 64 /*tile queue*/;
+constexpr int V3_SMEM_BYTES = 192 * 1024 + EP_BYTES + 1024 + V3_BAR_BYTES + 512 /*bias*/ + 64 /*tile queue*/;
 static_assert(V3_SMEM_BYTES <= 232448, "v3 exceeds the 227 KB shared-memory limit");
+// kind::f16, bf16 x bf16 -> fp32, A and B K-major, M = 128, N = 128
+constexpr uint32_t IDESC_BF16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 
 __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t accumulate) {
   asm volatile(
@@ -480,6 +201,19 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
           tmem_d),
       "r"(tmem_a), "l"(db), "r"(IDESC), "r"(accumulate)
       : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(
+          tmem_d),
+      "r"(tmem_a), "l"(db), "r"(IDESC_BF16), "r"(accumulate)
+      : "memory");
+}
+// two fp32 -> packed bf16x2 (round to nearest even): low half = lo_elem, high half = hi_elem
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+  return r;
 }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
@@ -496,7 +230,7 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
 // WRES: the whole [128, K<=128] weight slice (hi + lo, <= 128 KB) of this CTA's column tile stays resident in
 // shared memory; only A streams.  The SM<->L2 port (~28 B/clk/SM, shared by loads and stores) is what bounds the
 // K=128 layers: per 128x128 tile it moves 64 KB (A) + 64 KB (C) instead of 192 KB + 64 KB.
-template <bool WRES>
+template <bool WRES, bool BF>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                   const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapWhi,
@@ -505,17 +239,20 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
-  constexpr int S = V3_STAGES;
-  constexpr int STG = WRES ? A_BYTES : V3_STAGE_BYTES;            // bytes per pipeline stage
-  constexpr int WRES_BYTES = WRES ? 8 * A_BYTES : 0;              // resident W: hi chunks 0..3 | lo chunks 0..3
+  constexpr int KE = BF ? 64 : 32;                                // k-values per chunk
+  constexpr int AL = TM * KE * 4;                                 // fp32 A landing bytes per chunk (BF: two 16 KB boxes)
+  constexpr int S = (BF && !WRES) ? 3 : 4;                        // pipeline stages
+  constexpr int STG = WRES ? AL : AL + 2 * A_BYTES;               // bytes per stage: A landing [| W_hi | W_lo]
+  constexpr int NKW = BF ? 2 : 4;                                 // resident chunks (K <= 128)
+  constexpr int WRES_BYTES = WRES ? 2 * NKW * A_BYTES : 0;        // resident W: hi chunks | lo chunks
   constexpr int RING_OFF = WRES_BYTES;                            // stage ring starts after the resident weights
+  static_assert(RING_OFF + S * STG <= 192 * 1024, "operand ring exceeds its 192 KB");
   constexpr int EP_OFF = RING_OFF + S * STG;
   const uint32_t ep_base = base + EP_OFF;
   const uint32_t bars = ep_base + EP_BYTES;
   auto full = [&](int s) { return bars + 8u * s; };
   auto empty = [&](int s) { return bars + 8u * (S + s); };
-  constexpr int NA = V3_ABUFS;                                    // A_hi|A_lo buffers in tensor memory
-  static_assert(V3_ABUFS == V3_STAGES, "a_free(b) doubles as the stage-release barrier: needs NA == S");
+  constexpr int NA = S;    // A_hi|A_lo buffers in tensor memory; NA == S: a_free(b) doubles as the stage-release barrier
   auto a_ready = [&](int b) { return bars + 8u * (2 * S + b); };
   auto a_free = [&](int b) { return bars + 8u * (2 * S + NA + b); };
   auto acc_full = [&](int a) { return bars + 8u * (2 * S + 2 * NA + a); };
@@ -622,7 +359,8 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           for (int src = 0; src < p.nsrc; ++src)
               for (int kc = 0; kc < tc_kch(p, src); ++kc) {
                 const CUtensorMap* mp = src == 0 ? &mapA0 : (src == 1 ? &mapA1 : &mapA2);
-                tma_prefetch_2d(mp, kc * TK, mt * TM);
+                tma_prefetch_2d(mp, kc * KE, mt * TM);
+                if (BF) tma_prefetch_2d(mp, kc * KE + 32, mt * TM);
               }
         }
         tq[i] = tile;
@@ -642,10 +380,11 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           if (it >= S) mbar_wait(WRES ? empty(s) : a_free(s), ((it / S) - 1) & 1);
           DBG_STAMP(0, it);
           const uint32_t st = base + RING_OFF + s * STG;
-          mbar_expect_tx(full(s), WRES ? A_BYTES : 3 * A_BYTES);
+          mbar_expect_tx(full(s), STG);
           if (p.conv) {
             const int tap = kc_all / p.k0, kc = kc_all - tap * p.k0;
-            tma_load_4d(st, &mapA0, full(s), kc * TK, x0 + tap % 3 - 1, y0 + tap / 3 - 1, img);
+            tma_load_4d(st, &mapA0, full(s), kc * KE, x0 + tap % 3 - 1, y0 + tap / 3 - 1, img);
+            if (BF) tma_load_4d(st + A_BYTES, &mapA0, full(s), kc * KE + 32, x0 + tap % 3 - 1, y0 + tap / 3 - 1, img);
           } else {
             int src = 0, kc = kc_all;
             while (kc >= tc_kch(p, src)) {
@@ -653,11 +392,12 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
               ++src;
             }
             const CUtensorMap* mp = src == 0 ? &mapA0 : (src == 1 ? &mapA1 : &mapA2);
-            tma_load_2d(st, mp, full(s), kc * TK, m0);
+            tma_load_2d(st, mp, full(s), kc * KE, m0);
+            if (BF) tma_load_2d(st + A_BYTES, mp, full(s), kc * KE + 32, m0);
           }
           if (!WRES) {
-            tma_load_2d(st + A_BYTES, &mapWhi, full(s), kc_all * TK, n0);
-            tma_load_2d(st + 2 * A_BYTES, &mapWlo, full(s), kc_all * TK, n0);
+            tma_load_2d(st + AL, &mapWhi, full(s), kc_all * KE, n0);
+            tma_load_2d(st + AL + A_BYTES, &mapWlo, full(s), kc_all * KE, n0);
           }
         }
         if (WRES && n == 0) {
@@ -667,8 +407,8 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           const int n0w = group * TN;
           mbar_expect_tx(w_full, 2 * nk * A_BYTES);
           for (int kc = 0; kc < nk; ++kc) {
-            tma_load_2d(base + kc * A_BYTES, &mapWhi, w_full, kc * TK, n0w);
-            tma_load_2d(base + (4 + kc) * A_BYTES, &mapWlo, w_full, kc * TK, n0w);
+            tma_load_2d(base + kc * A_BYTES, &mapWhi, w_full, kc * KE, n0w);
+            tma_load_2d(base + (NKW + kc) * A_BYTES, &mapWlo, w_full, kc * KE, n0w);
           }
         }
         while (!exhausted && published <= n + 1 + PF) publish();   // ids (atomics) + L2 prefetch run ahead of the loads
@@ -691,17 +431,23 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         mbar_wait(a_ready(b), (it / NA) & 1);       // A_hi/A_lo of this chunk are in TMEM (implies full[s])
         tc_fence_after();
         const uint32_t st = base + RING_OFF + s * STG;
-        const uint32_t whi_base = WRES ? base + kc_all * A_BYTES : st + A_BYTES;
-        const uint32_t wlo_base = WRES ? base + (4 + kc_all) * A_BYTES : st + 2 * A_BYTES;
+        const uint32_t whi_base = WRES ? base + kc_all * A_BYTES : st + AL;
+        const uint32_t wlo_base = WRES ? base + (NKW + kc_all) * A_BYTES : st + AL + A_BYTES;
         const uint32_t ta = tmem_base + 256u + (uint32_t)(b * 64);
         if (elect_one()) {
           DBG_STAMP(3, it);
 #pragma unroll
-          for (int k = 0; k < TK / 8; ++k) {
+          for (int k = 0; k < 4; ++k) {               // 4 k-steps of 32 operand bytes: 8 tf32 or 16 bf16 each
             const uint64_t w_hi = umma_desc(whi_base + k * 32), w_lo = umma_desc(wlo_base + k * 32);
-            umma_tf32_ts(tmem_acc, ta + 32u + (uint32_t)(k * 8), w_hi, (kc_all | k) != 0);   // A_lo * W_hi
-            umma_tf32_ts(tmem_acc, ta + (uint32_t)(k * 8), w_lo, 1);                          // A_hi * W_lo
-            umma_tf32_ts(tmem_acc, ta + (uint32_t)(k * 8), w_hi, 1);                          // A_hi * W_hi
+            if (BF) {
+              umma_bf16_ts(tmem_acc, ta + 32u + (uint32_t)(k * 8), w_hi, (kc_all | k) != 0);  // A_mid * W_hi
+              umma_bf16_ts(tmem_acc, ta + (uint32_t)(k * 8), w_lo, 1);                         // A_hi * W_mid
+              umma_bf16_ts(tmem_acc, ta + (uint32_t)(k * 8), w_hi, 1);                         // A_hi * W_hi
+            } else {
+              umma_tf32_ts(tmem_acc, ta + 32u + (uint32_t)(k * 8), w_hi, (kc_all | k) != 0);  // A_lo * W_hi
+              umma_tf32_ts(tmem_acc, ta + (uint32_t)(k * 8), w_lo, 1);                         // A_hi * W_lo
+              umma_tf32_ts(tmem_acc, ta + (uint32_t)(k * 8), w_hi, 1);                         // A_hi * W_hi
+            }
           }
           // one commit per chunk: a_free(b) releases the TMEM A buffer to the splitter AND (streamed weights,
           // NA == S so b == s) the shared-memory stage to the TMA producer
@@ -725,14 +471,29 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         if (threadIdx.x == 64) DBG_STAMP(1, it);
         const uint8_t* arow = base_ptr + RING_OFF + s * STG + row * 128;
         uint32_t hi[32], lo[32];
+        if (BF) {
+          // 64 k-values (two 128 B rows) -> 32 packed bf16x2 hi + 32 packed mid; column c holds k = 2c, 2c + 1
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 x = *reinterpret_cast<const float4*>(arow + ((j ^ (row & 7)) << 4));   // undo the 128B swizzle
-          const float xv[4] = {x.x, x.y, x.z, x.w};
+          for (int h = 0; h < 2; ++h)
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            hi[4 * j + e] = __float_as_uint(xv[e]) & 0xFFFFE000u;
-            lo[4 * j + e] = __float_as_uint(xv[e] - __uint_as_float(hi[4 * j + e]));
+            for (int j = 0; j < 8; ++j) {
+              const float4 x = *reinterpret_cast<const float4*>(arow + h * A_BYTES + ((j ^ (row & 7)) << 4));
+              const uint32_t h01 = pack_bf16x2(x.x, x.y), h23 = pack_bf16x2(x.z, x.w);
+              hi[h * 16 + 2 * j] = h01;
+              hi[h * 16 + 2 * j + 1] = h23;
+              lo[h * 16 + 2 * j] = pack_bf16x2(x.x - __uint_as_float(h01 << 16), x.y - __uint_as_float(h01 & 0xFFFF0000u));
+              lo[h * 16 + 2 * j + 1] = pack_bf16x2(x.z - __uint_as_float(h23 << 16), x.w - __uint_as_float(h23 & 0xFFFF0000u));
+            }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 x = *reinterpret_cast<const float4*>(arow + ((j ^ (row & 7)) << 4));   // undo the 128B swizzle
+            const float xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              hi[4 * j + e] = __float_as_uint(xv[e]) & 0xFFFFE000u;
+              lo[4 * j + e] = __float_as_uint(xv[e] - __uint_as_float(hi[4 * j + e]));
+            }
           }
         }
         if (WRES) {                                   // the landing buffer is free as soon as every lane has read it
@@ -915,6 +676,19 @@ bool make_map_nhwc(CUtensorMap* m, const float* ptr, int N, int H, int W, int C)
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// 2-D bf16 map over a row-major [rows, cols] weight (cols contiguous); box = 64 cols (128 B) x 128 rows
+bool make_map_2d_bf16(CUtensorMap* m, const void* ptr, long long rows, long long cols) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {64, TM};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // store maps: 2-D [rows, cols] box 32 x 32, or 4-D NHWC box 32 ch x 16 x 2 x 1 (one epilogue warp's rows)
 bool make_store_map_2d(CUtensorMap* m, float* ptr, long long rows, long long cols, long long ld) {
   EncodeTiledFn enc = get_encode();
@@ -937,7 +711,7 @@ bool make_store_map_nhwc(CUtensorMap* m, float* ptr, int N, int H, int W, int C)
              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-bool g_attr_set = false, g_attr_set_v3 = false;
+bool g_attr_set_v3 = false;
 // dynamic tile scheduler state: a ring of 256 zero-initialised slots of 16 ints; launch n uses slot n % 256 and the
 // last CTA of a launch zeroes its slot again, so a slot is clean long before it comes round (also under graph replay,
 // where the slot index is baked into the captured launch).
@@ -947,9 +721,14 @@ int* g_sched_ptr = nullptr;
 unsigned g_sched_seq = 0;
 int g_tc_debug = 0;
 int g_tc_wres = 1;    // keep the weight slice resident in shared memory when K <= 128
-int g_tc_mode = 3;   // 3: A operand through tensor memory (default); 2: A operand through shared memory
 
-int launch_tc(const CUtensorMap maps[6], const TcParams& p_in, cudaStream_t stream, const char* name) {
+template <bool WRES, bool BF>
+void launch_v3(dim3 grid, const CUtensorMap maps[6], const TcParams& p, cudaStream_t stream) {
+  gemm_tc_kernel_v3<WRES, BF><<<grid, NTHREADS, V3_SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
+}
+
+// bf = 1: bf16-split operands (chunks of 64 k-values), 0: 3xTF32 (chunks of 32)
+int launch_tc(const CUtensorMap maps[6], const TcParams& p_in, int bf, cudaStream_t stream, const char* name) {
   TcParams p = p_in;
   if (g_num_sms == 0) {
     int devid = 0;
@@ -957,64 +736,133 @@ int launch_tc(const CUtensorMap maps[6], const TcParams& p_in, cudaStream_t stre
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, devid);
     if (g_num_sms <= 0) g_num_sms = 148;
   }
+  if (!g_attr_set_v3) {
+    if (cudaFuncSetAttribute(gemm_tc_kernel_v3<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(gemm_tc_kernel_v3<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(gemm_tc_kernel_v3<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(gemm_tc_kernel_v3<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_BYTES) != cudaSuccess) {
+      di_set_error("%s: cannot reserve %d bytes of shared memory", name, V3_SMEM_BYTES);
+      return DI_ERR_LAUNCH;
+    }
+    g_attr_set_v3 = true;
+  }
+  if (!g_sched_ptr && cudaGetSymbolAddress(reinterpret_cast<void**>(&g_sched_ptr), g_sched) != cudaSuccess) {
+    di_set_error("%s: cannot resolve the scheduler buffer", name);
+    return DI_ERR_LAUNCH;
+  }
+  p.sched = g_sched_ptr + 16 * (g_sched_seq++ % SCHED_SLOTS);
   const int tiles = p.m_tiles * p.n_tiles;
-  dim3 grid(tiles < g_num_sms ? tiles : g_num_sms);
-  if (!g_attr_set) {
-    if (cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
-      di_set_error("%s: cannot reserve %d bytes of shared memory", name, SMEM_BYTES);
-      return DI_ERR_LAUNCH;
-    }
-    g_attr_set = true;
+  int nk = p.k0 + p.k1 + p.k2;
+  const bool wres = !p.conv && nk <= (bf ? 2 : 4) && g_tc_wres && p.n_tiles <= 14;
+  int g = tiles < g_num_sms ? tiles : g_num_sms;
+  if (wres) {
+    // every CTA keeps one column tile's weights resident: the grid must be a multiple of n_tiles
+    if (tiles >= g_num_sms) g = (g_num_sms / p.n_tiles) * p.n_tiles;
+    if (g < p.n_tiles) g = p.n_tiles;
   }
-  if (g_tc_mode == 3) {
-    if (!g_attr_set_v3) {
-      if (cudaFuncSetAttribute(gemm_tc_kernel_v3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_BYTES) != cudaSuccess ||
-          cudaFuncSetAttribute(gemm_tc_kernel_v3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_BYTES) != cudaSuccess) {
-        di_set_error("%s: cannot reserve %d bytes of shared memory", name, V3_SMEM_BYTES);
-        return DI_ERR_LAUNCH;
-      }
-      g_attr_set_v3 = true;
-    }
-    if (!g_sched_ptr && cudaGetSymbolAddress(reinterpret_cast<void**>(&g_sched_ptr), g_sched) != cudaSuccess) {
-      di_set_error("%s: cannot resolve the scheduler buffer", name);
-      return DI_ERR_LAUNCH;
-    }
-    p.sched = g_sched_ptr + 16 * (g_sched_seq++ % SCHED_SLOTS);
-    int nk = 0;
-    for (int s2 = 0; s2 < p.nsrc; ++s2) nk += tc_kch(p, s2);
-    const bool wres = !p.conv && nk <= 4 && g_tc_wres && p.n_tiles <= 14;
-    if (wres) {
-      // every CTA keeps one column tile's weights resident: the grid must be a multiple of n_tiles
-      int g2 = tiles < g_num_sms ? tiles : (g_num_sms / p.n_tiles) * p.n_tiles;
-      if (g2 < p.n_tiles) g2 = p.n_tiles;
-      gemm_tc_kernel_v3<true><<<dim3(g2), NTHREADS, V3_SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
-    } else {
-      gemm_tc_kernel_v3<false><<<grid, NTHREADS, V3_SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
-    }
-  } else {
-    gemm_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
-  }
+  if (wres && bf) launch_v3<true, true>(dim3(g), maps, p, stream);
+  else if (wres) launch_v3<true, false>(dim3(g), maps, p, stream);
+  else if (bf) launch_v3<false, true>(dim3(g), maps, p, stream);
+  else launch_v3<false, false>(dim3(g), maps, p, stream);
   DI_CHECK_LAUNCH(name);
   return DI_OK;
 }
 
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// shared body of di_linear_tc_f32 (bf = 0) and di_linear_tcb_f32 (bf = 1)
+int linear_tc_impl(const char* name, int bf, const float* A0, int lda0, int K0, const float* A1, int lda1, int K1,
+                   const float* A2, int lda2, int K2, const void* W_hi, const void* W_lo, const float* bias,
+                   const float* res, int ldres, int res_mod, float* C, int ldc, int M, int N, int act,
+                   cudaStream_t stream) {
+  if (!(A0 && W_hi && W_lo && C && M > 0 && N > 0 && K0 > 0)) {
+    di_set_error("%s: null pointer or empty shape", name);
+    return DI_ERR_ARG;
+  }
+  const int KE = bf ? 64 : 32;
+  const float* As[3] = {A0, A1, A2};
+  const int lds[3] = {lda0, lda1, lda2}, Ks[3] = {K0, K1, K2};
+  int nsrc = 1 + (K1 > 0) + (K2 > 0);
+  int K = K0 + K1 + K2;
+  bool ok = al16(W_hi) && al16(W_lo) && al16(C) && ldc % 4 == 0 && (K2 == 0 || K1 > 0) && (!bias || al16(bias)) &&
+            (!res || (al16(res) && ldres % 4 == 0));
+  for (int s = 0; s < nsrc; ++s) ok = ok && As[s] && Ks[s] % KE == 0 && lds[s] % 4 == 0 && al16(As[s]);
+  if (!ok) {
+    di_set_error("%s: shape/alignment not supported by the tensor-core path", name);
+    return DI_ERR_UNSUPPORTED;
+  }
+  CUtensorMap maps[6];
+  bool made = make_store_map_2d(&maps[5], C, M, N, ldc);
+  for (int s = 0; s < 3 && made; ++s) {
+    int u = s < nsrc ? s : 0;
+    made = make_map_2d(&maps[s], As[u], M, Ks[u], lds[u]);
+  }
+  if (made) {
+    if (bf) made = make_map_2d_bf16(&maps[3], W_hi, N, K) && make_map_2d_bf16(&maps[4], W_lo, N, K);
+    else made = make_map_2d(&maps[3], (const float*)W_hi, N, K, K) && make_map_2d(&maps[4], (const float*)W_lo, N, K, K);
+  }
+  if (!made) {
+    di_set_error("%s: cuTensorMapEncodeTiled failed", name);
+    return DI_ERR_LAUNCH;
+  }
+  TcParams p{};
+  p.M = M; p.N = N; p.nsrc = nsrc;
+  p.k0 = Ks[0] / KE; p.k1 = Ks[1] / KE; p.k2 = Ks[2] / KE;
+  p.conv = 0; p.C = C; p.ldc = ldc; p.bias = bias; p.res = res; p.ldres = ldres;
+  p.res_mod = res_mod > 0 ? res_mod : M; p.act = act; p.dbg = g_tc_debug;
+  p.m_tiles = di_cdiv(M, TM);
+  p.n_tiles = di_cdiv(N, TN);
+  return launch_tc(maps, p, bf, stream, name);
+}
+
+int conv3x3_tc_impl(const char* name, int bf, const float* x, const void* w_hi, const void* w_lo, const float* bias,
+                    float* y, int N, int Cin, int H, int W, int Cout, int act, cudaStream_t stream) {
+  if (!(x && w_hi && w_lo && y && N > 0 && H > 0 && W > 0)) {
+    di_set_error("%s: bad argument", name);
+    return DI_ERR_ARG;
+  }
+  const int KE = bf ? 64 : 32;
+  if (!(Cin % KE == 0 && Cout % 4 == 0 && al16(x) && al16(y) && al16(w_hi) && al16(w_lo) && (!bias || al16(bias)))) {
+    di_set_error("%s: shape/alignment not supported by the tensor-core path", name);
+    return DI_ERR_UNSUPPORTED;
+  }
+  CUtensorMap maps[6];
+  long long K = 9ll * Cin;
+  bool made = make_store_map_nhwc(&maps[5], y, N, H, W, Cout) && make_map_nhwc(&maps[0], x, N, H, W, Cin);
+  if (made) {
+    if (bf) made = make_map_2d_bf16(&maps[3], w_hi, Cout, K) && make_map_2d_bf16(&maps[4], w_lo, Cout, K);
+    else made = make_map_2d(&maps[3], (const float*)w_hi, Cout, K, K) && make_map_2d(&maps[4], (const float*)w_lo, Cout, K, K);
+  }
+  if (!made) {
+    di_set_error("%s: cuTensorMapEncodeTiled failed", name);
+    return DI_ERR_LAUNCH;
+  }
+  maps[1] = maps[0];
+  maps[2] = maps[0];
+  TcParams p{};
+  p.M = N * H * W; p.N = Cout; p.nsrc = 1; p.k0 = Cin / KE; p.conv = 1; p.H = H; p.W = W;
+  p.tiles_x = di_cdiv(W, 16); p.tiles_y = di_cdiv(H, 8);
+  p.C = y; p.ldc = Cout; p.bias = bias; p.res = nullptr; p.ldres = 0; p.res_mod = 1; p.act = act; p.dbg = g_tc_debug;
+  p.m_tiles = N * p.tiles_x * p.tiles_y;
+  p.n_tiles = di_cdiv(Cout, TN);
+  return launch_tc(maps, p, bf, stream, name);
+}
+
 }  // namespace
 
 extern "C" {
 
 // Pipeline trace of CTA 0 (diagnostics): enable, run ONE tensor-core launch, then read 8 x 512 clock64 stamps
-// (rows: 0 producer issue, 1 bytes landed, 2 split done, 3 mma ready, 4 mma issued, 5 acc ready, 6 tile stored).
+// (rows: 0 producer issue, 1 bytes landed, 2 split done, 3 mma ready, 4 mma issued, 5 acc ready, 6 tile stored,
+// 7 epilogue phases / kernel entry-exit).
 int di_tc_set_debug(int on) {
   g_tc_debug = on;
   return DI_OK;
 }
-// 3 (default): A operand staged in tensor memory; 2: A operand in shared memory (earlier pipeline, kept for A/B tests)
+// 3 (default): weights resident in shared memory when K <= 128; 4: always streamed (A/B tests)
 int di_tc_set_mode(int mode) {
-  DI_CHECK_ARG(mode == 2 || mode == 3 || mode == 4, "di_tc_set_mode: mode must be 2, 3 or 4");
-  g_tc_wres = mode != 4;            // 4 = v3 pipeline with streamed weights (A/B tests)
-  g_tc_mode = mode == 2 ? 2 : 3;
+  DI_CHECK_ARG(mode == 3 || mode == 4, "di_tc_set_mode: mode must be 3 or 4");
+  g_tc_wres = mode != 4;
   return DI_OK;
 }
 int di_tc_debug_read(long long* host_buf) {
@@ -1026,83 +874,33 @@ int di_tc_debug_read(long long* host_buf) {
   return DI_OK;
 }
 
-// Tensor-core (3xTF32, tcgen05 + TMA) version of di_linear_f32.  W_hi / W_lo: the [N, K0+K1+K2] weight split on
-// the host (hi = round-to-tf32, lo = W - hi).  Constraints: every K_s % 32 == 0, lda % 4 == 0, 16-byte aligned
-// pointers, ldc % 4 == 0.  Returns DI_ERR_UNSUPPORTED (-3) when a constraint is not met so the caller can use
-// di_linear_f32.
+// Tensor-core (tcgen05 + TMA) versions of di_linear_f32: C = act([A0|A1|A2] W^T + bias + res).
+//   di_linear_tc_f32 : 3xTF32.  W_hi / W_lo fp32 [N, K]: hi = tf32(W), lo = W - hi.        every K_s % 32 == 0
+//   di_linear_tcb_f32: bf16 split.  W_hi / W_mid bf16 [N, K]: hi = bf16(W), mid = bf16(W - hi).  every K_s % 64 == 0
+// Common constraints: lda % 4 == 0, ldc % 4 == 0, 16-byte aligned pointers.  Return DI_ERR_UNSUPPORTED (-3) when a
+// constraint is not met so that the caller can fall back (tcb -> tc -> di_linear_f32).
 int di_linear_tc_f32(const float* A0, int lda0, int K0, const float* A1, int lda1, int K1, const float* A2, int lda2,
                      int K2, const float* W_hi, const float* W_lo, const float* bias, const float* res, int ldres,
                      int res_mod, float* C, int ldc, int M, int N, int act, cudaStream_t stream) {
-  DI_CHECK_ARG(A0 && W_hi && W_lo && C && M > 0 && N > 0 && K0 > 0, "di_linear_tc_f32: null pointer or empty shape");
-  const float* As[3] = {A0, A1, A2};
-  const int lds[3] = {lda0, lda1, lda2}, Ks[3] = {K0, K1, K2};
-  int nsrc = 1 + (K1 > 0) + (K2 > 0);
-  int K = K0 + K1 + K2;
-  bool ok = al16(W_hi) && al16(W_lo) && al16(C) && ldc % 4 == 0 && K % 4 == 0 && (K2 == 0 || K1 > 0) &&
-            (!bias || al16(bias)) && (!res || (al16(res) && ldres % 4 == 0));
-  for (int s = 0; s < nsrc; ++s) ok = ok && As[s] && Ks[s] % TK == 0 && lds[s] % 4 == 0 && al16(As[s]);
-  if (!ok) {
-    di_set_error("di_linear_tc_f32: shape/alignment not supported by the tensor-core path");
-    return DI_ERR_UNSUPPORTED;
-  }
-  CUtensorMap maps[6];
-  if (!make_store_map_2d(&maps[5], C, M, N, ldc)) {
-    di_set_error("di_linear_tc_f32: cuTensorMapEncodeTiled failed for C");
-    return DI_ERR_LAUNCH;
-  }
-  for (int s = 0; s < 3; ++s) {
-    int u = s < nsrc ? s : 0;
-    if (!make_map_2d(&maps[s], As[u], M, Ks[u], lds[u])) {
-      di_set_error("di_linear_tc_f32: cuTensorMapEncodeTiled failed for A%d", s);
-      return DI_ERR_LAUNCH;
-    }
-  }
-  if (!make_map_2d(&maps[3], W_hi, N, K, K) || !make_map_2d(&maps[4], W_lo, N, K, K)) {
-    di_set_error("di_linear_tc_f32: cuTensorMapEncodeTiled failed for W");
-    return DI_ERR_LAUNCH;
-  }
-  TcParams p{};
-  p.M = M; p.N = N; p.nsrc = nsrc;
-  p.k0 = Ks[0] / TK; p.k1 = Ks[1] / TK; p.k2 = Ks[2] / TK;
-  p.conv = 0; p.C = C; p.ldc = ldc; p.bias = bias; p.res = res; p.ldres = ldres;
-  p.res_mod = res_mod > 0 ? res_mod : M; p.act = act; p.dbg = g_tc_debug;
-  p.m_tiles = di_cdiv(M, TM);
-  p.n_tiles = di_cdiv(N, TN);
-  return launch_tc(maps, p, stream, "di_linear_tc_f32");
+  return linear_tc_impl("di_linear_tc_f32", 0, A0, lda0, K0, A1, lda1, K1, A2, lda2, K2, W_hi, W_lo, bias, res, ldres,
+                        res_mod, C, ldc, M, N, act, stream);
+}
+int di_linear_tcb_f32(const float* A0, int lda0, int K0, const float* A1, int lda1, int K1, const float* A2, int lda2,
+                      int K2, const void* W_hi, const void* W_mid, const float* bias, const float* res, int ldres,
+                      int res_mod, float* C, int ldc, int M, int N, int act, cudaStream_t stream) {
+  return linear_tc_impl("di_linear_tcb_f32", 1, A0, lda0, K0, A1, lda1, K1, A2, lda2, K2, W_hi, W_mid, bias, res, ldres,
+                        res_mod, C, ldc, M, N, act, stream);
 }
 
 // Tensor-core 3x3 convolution (stride 1, zero pad 1) over a pixel-major map: x [N,H,W,Cin] -> y [N,H,W,Cout],
-// w_hi / w_lo [Cout][(ky*3+kx)*Cin + ci].  Cin % 32 == 0, Cout % 4 == 0.
+// w_hi / w_lo [Cout][(ky*3+kx)*Cin + ci] (fp32 tf32-split, Cin % 32 == 0) or bf16 hi / mid (Cin % 64 == 0).
 int di_conv3x3_tc_f32(const float* x, const float* w_hi, const float* w_lo, const float* bias, float* y, int N, int Cin,
                       int H, int W, int Cout, int act, cudaStream_t stream) {
-  DI_CHECK_ARG(x && w_hi && w_lo && y && N > 0 && H > 0 && W > 0, "di_conv3x3_tc_f32: bad argument");
-  if (!(Cin % TK == 0 && Cout % 4 == 0 && al16(x) && al16(y) && al16(w_hi) && al16(w_lo) && (!bias || al16(bias)))) {
-    di_set_error("di_conv3x3_tc_f32: shape/alignment not supported by the tensor-core path");
-    return DI_ERR_UNSUPPORTED;
-  }
-  CUtensorMap maps[6];
-  if (!make_store_map_nhwc(&maps[5], y, N, H, W, Cout)) {
-    di_set_error("di_conv3x3_tc_f32: cuTensorMapEncodeTiled failed for y");
-    return DI_ERR_LAUNCH;
-  }
-  if (!make_map_nhwc(&maps[0], x, N, H, W, Cin)) {
-    di_set_error("di_conv3x3_tc_f32: cuTensorMapEncodeTiled failed for x");
-    return DI_ERR_LAUNCH;
-  }
-  maps[1] = maps[0];
-  maps[2] = maps[0];
-  long long K = 9ll * Cin;
-  if (!make_map_2d(&maps[3], w_hi, Cout, K, K) || !make_map_2d(&maps[4], w_lo, Cout, K, K)) {
-    di_set_error("di_conv3x3_tc_f32: cuTensorMapEncodeTiled failed for w");
-    return DI_ERR_LAUNCH;
-  }
-  TcParams p{};
-  p.M = N * H * W; p.N = Cout; p.nsrc = 1; p.k0 = Cin / TK; p.conv = 1; p.H = H; p.W = W;
-  p.tiles_x = di_cdiv(W, 16); p.tiles_y = di_cdiv(H, 8);
-  p.C = y; p.ldc = Cout; p.bias = bias; p.res = nullptr; p.ldres = 0; p.res_mod = 1; p.act = act; p.dbg = g_tc_debug;
-  p.m_tiles = N * p.tiles_x * p.tiles_y;
-  p.n_tiles = di_cdiv(Cout, TN);
-  return launch_tc(maps, p, stream, "di_conv3x3_tc_f32");
+  return conv3x3_tc_impl("di_conv3x3_tc_f32", 0, x, w_hi, w_lo, bias, y, N, Cin, H, W, Cout, act, stream);
+}
+int di_conv3x3_tcb_f32(const float* x, const void* w_hi, const void* w_mid, const float* bias, float* y, int N, int Cin,
+                       int H, int W, int Cout, int act, cudaStream_t stream) {
+  return conv3x3_tc_impl("di_conv3x3_tcb_f32", 1, x, w_hi, w_mid, bias, y, N, Cin, H, W, Cout, act, stream);
 }
 
 }  // extern "C"

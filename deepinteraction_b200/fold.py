@@ -81,12 +81,22 @@ def split_tf32(w):
     return hi.contiguous(), (w - hi).contiguous()
 
 
+def split_bf16(w):
+    """fp32 tensor -> (hi, mid) bf16: hi = bf16(w), mid = bf16(w - hi); hi + mid keeps 16 mantissa bits of w."""
+    w = w.to(torch.float32).contiguous()
+    hi = w.to(torch.bfloat16)
+    mid = (w - hi.to(torch.float32)).to(torch.bfloat16)
+    return hi.contiguous(), mid.contiguous()
+
+
 class Weight:
-    """A dense-layer weight [N, K] kept in both forms the kernels consume: plain fp32 (FFMA path) and the
-    TF32 hi/lo split (tcgen05 path)."""
+    """A dense-layer weight [N, K] kept in the forms the kernels consume: plain fp32 (FFMA path), the TF32 hi/lo
+    split and the bf16 hi/mid split (tcgen05 paths)."""
 
     def __init__(self, w, device):
         self.w = dev(w, device)
         hi, lo = split_tf32(w.to(torch.float32))
         self.hi, self.lo = hi.to(device), lo.to(device)
+        bh, bm = split_bf16(w)
+        self.bh, self.bm = bh.to(device), bm.to(device)
         self.shape = self.w.shape

@@ -15,7 +15,8 @@ from .fold import Weight
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 
 LAUNCHES = [0]   # number of libdi_b200 kernel-launching calls (bench.py reports it)
-USE_TC = [os.environ.get('DI_B200_TC', '1') != '0']   # tcgen05 3xTF32 path for Weight objects (else FFMA)
+USE_TC = [os.environ.get('DI_B200_TC', '1') != '0']   # tcgen05 split-product path for Weight objects (else FFMA)
+TC_BF16 = [os.environ.get('DI_B200_TC_BF16', '1') != '0']   # bf16-split operands where K % 64 == 0 (else 3xTF32)
 PROFILE = [None]  # bench.py sets PROFILE[0] = [] to record (name, start_event, end_event, bytes, flops) per call
 
 
@@ -102,7 +103,9 @@ def _linear_tc(srcs, W, bias, act, out, res, res_mod, M, N, K):
         out = torch.empty(M, N, device=W.w.device, dtype=torch.float32)
     po, ldo = _rows(out)
     pr, ldr = (None, 0) if res is None else _rows(res)
-    _call('di_linear_tc_f32', *a, _ptr(W.hi), _ptr(W.lo), _ptr(bias), pr, ldr, res_mod, po, ldo, M, N, act, _stream(),
+    bf = TC_BF16[0] and all(s.shape[1] % 64 == 0 for s in srcs)
+    _call('di_linear_tcb_f32' if bf else 'di_linear_tc_f32', *a, _ptr(W.bh if bf else W.hi), _ptr(W.bm if bf else W.lo),
+          _ptr(bias), pr, ldr, res_mod, po, ldo, M, N, act, _stream(),
           nbytes=4 * (M * K + N * K + M * N + (0 if res is None else res.numel())), flops=2 * M * N * K)
     return out
 
@@ -119,9 +122,10 @@ def conv3x3(x, w_packed, bias, cout, x_nhwc, y_nchw=False, act=ACT_NONE):
         if USE_TC[0] and not y_nchw and cout % 4 == 0 and Cin % 32 == 0:
             xin = x if x_nhwc else nchw_to_nhwc(x)       # the TMA box walks a pixel-major map
             y = torch.empty((N, H, W, cout), device=x.device, dtype=torch.float32)
-            _call('di_conv3x3_tc_f32', _ptr(xin), _ptr(w_packed.hi), _ptr(w_packed.lo), _ptr(bias), _ptr(y), N, Cin, H, W,
-                  cout, act, _stream(), nbytes=4 * (x.numel() + w_packed.w.numel() + y.numel()),
-                  flops=2 * N * H * W * cout * 9 * Cin)
+            bf = TC_BF16[0] and Cin % 64 == 0
+            _call('di_conv3x3_tcb_f32' if bf else 'di_conv3x3_tc_f32', _ptr(xin), _ptr(w_packed.bh if bf else w_packed.hi),
+                  _ptr(w_packed.bm if bf else w_packed.lo), _ptr(bias), _ptr(y), N, Cin, H, W, cout, act, _stream(),
+                  nbytes=4 * (x.numel() + w_packed.w.numel() + y.numel()), flops=2 * N * H * W * cout * 9 * Cin)
             return y
         w_packed = w_packed.w
     y = torch.empty((N, cout, H, W) if y_nchw else (N, H, W, cout), device=x.device, dtype=torch.float32)

@@ -56,18 +56,27 @@ int di_linear_f32(const float* A0, int lda0, int K0, const float* A1, int lda1, 
 int di_conv3x3_f32(const float* x, int x_nhwc, const float* w, const float* bias, float* y, int y_nchw, int N,
                    int Cin, int H, int W, int Cout, int act, cudaStream_t stream);
 
-/* Tensor-core versions (gemm_tc.cu): error-compensated 3xTF32 on tcgen05 (accumulator in TMEM), operands
- * staged by TMA; fp32-faithful results.  W_hi/W_lo = host-side split of the same [N,K] weight.  Return -3
- * (unsupported) when the shape/alignment constraints are not met; the caller then uses the FFMA entry point. */
+/* Tensor-core versions (gemm_tc.cu): error-compensated split products on tcgen05 (accumulator and the A operand
+ * in tensor memory), operands staged by TMA.  Two operand precisions:
+ *   _tc_  : 3xTF32.     W_hi / W_lo  fp32 [N,K]: hi = tf32(W), lo = W - hi.             every K_s % 32 == 0
+ *   _tcb_ : bf16 split. W_hi / W_mid bf16 [N,K]: hi = bf16(W), mid = bf16(W - hi).      every K_s % 64 == 0
+ *           (16 mantissa bits, ~1e-5 per layer; half the tensor-pipe time and weight bytes -- the default)
+ * Return -3 (unsupported) when the shape/alignment constraints are not met; the caller then falls back
+ * (tcb -> tc -> the FFMA entry point). */
 int di_linear_tc_f32(const float* A0, int lda0, int K0, const float* A1, int lda1, int K1, const float* A2, int lda2,
                      int K2, const float* W_hi, const float* W_lo, const float* bias, const float* res, int ldres,
                      int res_mod, float* C, int ldc, int M, int N, int act, cudaStream_t stream);
+int di_linear_tcb_f32(const float* A0, int lda0, int K0, const float* A1, int lda1, int K1, const float* A2, int lda2,
+                      int K2, const void* W_hi, const void* W_mid, const float* bias, const float* res, int ldres,
+                      int res_mod, float* C, int ldc, int M, int N, int act, cudaStream_t stream);
 int di_conv3x3_tc_f32(const float* x, const float* w_hi, const float* w_lo, const float* bias, float* y, int N, int Cin,
                       int H, int W, int Cout, int act, cudaStream_t stream);
+int di_conv3x3_tcb_f32(const float* x, const void* w_hi, const void* w_mid, const float* bias, float* y, int N, int Cin,
+                       int H, int W, int Cout, int act, cudaStream_t stream);
 
 /* diagnostics: clock64 pipeline trace of CTA 0 of the next tensor-core launch (8 x 512 stamps) */
 int di_tc_set_debug(int on);
-int di_tc_set_mode(int mode); /* 3 = A operand through tensor memory (default), 2 = through shared memory */
+int di_tc_set_mode(int mode); /* 3 = weights resident in shared memory when K <= 128 (default), 4 = always streamed */
 int di_tc_debug_read(long long* host_buf);
 
 /* ---- local-window attention (lcab.cu) ---------------------------------------------------------- */

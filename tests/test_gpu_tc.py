@@ -1,4 +1,5 @@
-"""GPU parity of the tcgen05 (3xTF32, TMA-staged) dense kernels vs float64 references, and FFMA/TC agreement."""
+"""GPU parity of the tcgen05 (split-product, TMA-staged) dense kernels vs float64 references, and FFMA/TC agreement.
+Both operand precisions (bf16 split = the default where K % 64 == 0, and 3xTF32) and both weight placements."""
 import numpy as np
 import pytest
 import torch
@@ -14,18 +15,23 @@ def dev():
     return torch.device('cuda:0')
 
 
-@pytest.fixture(params=[3, 4, 2], ids=['A-via-TMEM+W-resident', 'A-via-TMEM', 'A-via-smem'])
+@pytest.fixture(params=[(3, True), (4, True), (3, False), (4, False)],
+                ids=['bf16split+W-resident', 'bf16split+W-streamed', '3xtf32+W-resident', '3xtf32+W-streamed'])
 def tc_mode(request):
-    """Both tensor-core pipelines: v3 stages the A operand in tensor memory, v2 keeps it in shared memory."""
-    from deepinteraction_b200 import _lib
-    _lib.check(_lib.lib().di_tc_set_mode(request.param))
+    from deepinteraction_b200 import _lib, ops
+    mode, bf = request.param
+    _lib.check(_lib.lib().di_tc_set_mode(mode))
+    old = ops.TC_BF16[0]
+    ops.TC_BF16[0] = bf
     yield request.param
+    ops.TC_BF16[0] = old
     _lib.lib().di_tc_set_mode(3)
 
 
 @pytest.mark.parametrize('M,N,Ks,act,use_res', [
     (128, 128, [128], 1, False), (1000, 128, [128], 0, False), (32400, 128, [128, 128, 128], 0, False),
-    (777, 384, [128], 1, False), (4096, 256, [64, 32], 2, True), (200, 32768, [128], 0, False),
+    (777, 384, [128], 1, False), (4096, 256, [64, 32], 2, True), (4096, 256, [64, 128], 2, True),
+    (200, 32768, [128], 0, False),
     (300, 20, [384], 0, False), (50001, 128, [256], 1, True)])
 def test_linear_tc_matches_float64(M, N, Ks, act, use_res, tc_mode):
     from deepinteraction_b200 import ops, fold
@@ -61,8 +67,14 @@ def test_linear_tc_strided_sources_and_ffma_agreement():
         ops.USE_TC[0] = True
     ref = F.relu(big[:, 128:256].cpu().double() @ W.double().t()).float()
     assert rel_err(a.cpu(), ref) < TIGHT and rel_err(b.cpu(), ref) < TIGHT
-    # the compensated product must be at fp32 level, i.e. far better than a single TF32 pass (~5e-4)
+    # the compensated products must be far better than a single TF32 / BF16 pass (~5e-4 / 4e-3)
     assert rel_err(a.cpu(), ref) < 1e-5
+    ops.TC_BF16[0] = False
+    try:
+        c = ops.linear([big[:, 128:256]], Wt, act=ops.ACT_RELU)
+    finally:
+        ops.TC_BF16[0] = True
+    assert rel_err(c.cpu(), ref) < 2e-6
 
 
 @pytest.mark.parametrize('N,Cin,H,W,Cout,nhwc_in,act', [(1, 32, 8, 16, 128, True, 0), (2, 128, 37, 45, 128, True, 1),
@@ -83,6 +95,15 @@ def test_conv3x3_tc_matches_float64(N, Cin, H, W, Cout, nhwc_in, act, tc_mode):
     e = rel_err(y, ref.float())
     print(f'conv_tc N={N} Cin={Cin} {H}x{W}: rel err {e:.2e}')
     assert e < TIGHT
+
+
+def test_bf16_split_keeps_16_bits():
+    from deepinteraction_b200 import fold
+    w = torch.randn(4096) * torch.logspace(-6, 6, 4096)
+    hi, mid = fold.split_bf16(w)
+    assert hi.dtype == torch.bfloat16 and mid.dtype == torch.bfloat16
+    err = (hi.float() + mid.float() - w).abs() / w.abs()
+    assert float(err.max()) <= 2.0 ** -17
 
 
 def test_tf32_split_is_exact():
