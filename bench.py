@@ -372,6 +372,7 @@ def main():
         sd = shapes.setdefault((name, nbytes, flops), [0, 0.0])
         sd[0] += 1
         sd[1] += a.elapsed_time(b)
+        name = name.split(' ')[0]                    # drop the shape tag for the per-kernel totals
         d = agg.setdefault(name, dict(ms=0.0, n=0, bytes=0, flops=0))
         d['ms'] += a.elapsed_time(b)
         d['n'] += 1
@@ -381,7 +382,7 @@ def main():
     di_graph.ENABLED[0] = True
     if os.environ.get('DI_B200_SHAPES'):             # per-shape table (stderr), for kernel work
         for (name, nbytes, flops), (n, t) in sorted(shapes.items(), key=lambda kv: -kv[1][1]):
-            print('%-24s n/step=%5.1f  avg=%8.1f us  total=%7.3f ms/step  %8.2f MB %8.3f GFLOP' % (
+            print('%-44s n/step=%5.1f  avg=%8.1f us  total=%7.3f ms/step  %8.2f MB %8.3f GFLOP' % (
                 name, n / args.profile_steps, t / n * 1e3, t / args.profile_steps, nbytes / 1e6, flops / 1e9),
                 file=sys.stderr)
     total_ms = sum(d['ms'] for d in agg.values())

@@ -253,6 +253,14 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   auto full = [&](int s) { return bars + 8u * s; };
   auto empty = [&](int s) { return bars + 8u * (S + s); };
   constexpr int NA = S;    // A_hi|A_lo buffers in tensor memory; NA == S: a_free(b) doubles as the stage-release barrier
+  // 3xTF32 is the PRECISE mode: the two small cross products accumulate in their own TMEM tile and are added to the
+  // main product in the epilogue.  The tensor core truncates at every accumulate, so the error of a tile grows with
+  // the number of instructions that hit its accumulator (measured ~K * 4e-8 with all three products in one tile);
+  // with the cross terms elsewhere the main tile sees K/8 instead of 3K/8 accumulations.  Accumulators are then
+  // single-buffered (TMEM: main 128 | cross 128 | 4 x 64 A), which costs the epilogue overlap -- acceptable, this
+  // mode only runs the decoder's index-/softmax-critical layers.
+  constexpr int NACC = BF ? 2 : 1;
+  constexpr uint32_t CROSS_COL = 128;                             // precise mode: cross-term accumulator columns
   auto a_ready = [&](int b) { return bars + 8u * (2 * S + b); };
   auto a_free = [&](int b) { return bars + 8u * (2 * S + NA + b); };
   auto acc_full = [&](int a) { return bars + 8u * (2 * S + 2 * NA + a); };
@@ -423,8 +431,8 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     for (int tl = 0;; ++tl) {
       if (take_tile(tl) < 0) break;
       if (WRES && tl == 0) mbar_wait(w_full, 0);
-      const int a = tl & 1;
-      if (tl >= 2) mbar_wait(acc_empty(a), ((tl >> 1) - 1) & 1);
+      const int a = tl % NACC;
+      if (tl >= NACC) mbar_wait(acc_empty(a), ((tl / NACC) - 1) & 1);
       const uint32_t tmem_acc = tmem_base + (uint32_t)(a * TN);
       for (int kc_all = 0; kc_all < nk; ++kc_all, ++it) {
         const int s = it % S, b = it % NA;
@@ -444,9 +452,9 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
               umma_bf16_ts(tmem_acc, ta + (uint32_t)(k * 8), w_lo, 1);                         // A_hi * W_mid
               umma_bf16_ts(tmem_acc, ta + (uint32_t)(k * 8), w_hi, 1);                         // A_hi * W_hi
             } else {
-              umma_tf32_ts(tmem_acc, ta + 32u + (uint32_t)(k * 8), w_hi, (kc_all | k) != 0);  // A_lo * W_hi
-              umma_tf32_ts(tmem_acc, ta + (uint32_t)(k * 8), w_lo, 1);                         // A_hi * W_lo
-              umma_tf32_ts(tmem_acc, ta + (uint32_t)(k * 8), w_hi, 1);                         // A_hi * W_hi
+              umma_tf32_ts(tmem_acc + CROSS_COL, ta + 32u + (uint32_t)(k * 8), w_hi, (kc_all | k) != 0);  // A_lo * W_hi
+              umma_tf32_ts(tmem_acc + CROSS_COL, ta + (uint32_t)(k * 8), w_lo, 1);                         // A_hi * W_lo
+              umma_tf32_ts(tmem_acc, ta + (uint32_t)(k * 8), w_hi, (kc_all | k) != 0);                     // A_hi * W_hi
             }
           }
           // one commit per chunk: a_free(b) releases the TMEM A buffer to the splitter AND (streamed weights,
@@ -491,8 +499,8 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
             const float xv[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              hi[4 * j + e] = __float_as_uint(xv[e]) & 0xFFFFE000u;
-              lo[4 * j + e] = __float_as_uint(xv[e] - __uint_as_float(hi[4 * j + e]));
+              hi[4 * j + e] = (__float_as_uint(xv[e]) + 0x1000u) & 0xFFFFE000u;        // round to nearest tf32
+              lo[4 * j + e] = __float_as_uint(xv[e] - __uint_as_float(hi[4 * j + e]));   // exact remainder
             }
           }
         }
@@ -536,8 +544,8 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         asm volatile("bar.sync 1, 128;" ::: "memory");
         bias_n0 = n0;
       }
-      const int a = tl & 1;
-      mbar_wait(acc_full(a), (tl >> 1) & 1);
+      const int a = tl % NACC;
+      mbar_wait(acc_full(a), (tl / NACC) & 1);
       tc_fence_after();
       if (threadIdx.x == 192) DBG_STAMP(5, tl);
       long long grow;
@@ -602,6 +610,19 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         float v0[32], v1[32];
         tmem_ld32_nowait(tacc + (uint32_t)c0, v0);
         if (two) tmem_ld32_nowait(tacc + (uint32_t)(c0 + 32), v1);
+        if (!BF) {                                               // precise mode: add the cross-term tile
+          float x[32];
+          tmem_ld32_nowait(tacc + CROSS_COL + (uint32_t)c0, x);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v0[j] += x[j];
+          if (two) {
+            tmem_ld32_nowait(tacc + CROSS_COL + (uint32_t)(c0 + 32), x);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v1[j] += x[j];
+          }
+        }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (h == 1 || c0 + 64 >= ncols) {                        // last TMEM read of this tile: release the accumulator
           tc_fence_before();

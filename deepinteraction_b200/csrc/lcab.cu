@@ -344,6 +344,233 @@ lcab_window_mma_kernel(const float* __restrict__ q, int ldq, const float* __rest
 }
 
 // ------------------------------------------------------------------------------------------------
+// bf16-split version of the kernel above (the default): same tiling, same fragment algebra, but every operand is
+// split ONCE per shared-memory stage into hi = bf16(x), mid = bf16(x - hi) (16 mantissa bits kept, product error
+// ~1e-5) instead of per fragment load, and the contractions run on mma.sync.m16n8k16 bf16 (3 products per k16
+// instead of 3 per k8: half the tensor instructions, ~1/4 of the splitting arithmetic).
+//   K / Q chunk: cp.async lands fp32 [pixel][32 ch]; a conversion pass rewrites each channel pair IN PLACE as the
+//                64-bit word (hi bf16x2, mid bf16x2)  -> B / A fragments are single LDS.64, conflict-free with a
+//                pixel stride of 40 words
+//   V chunk:     the k index of P V is the key, so V is re-laid as [key pair along x][channel] -> (hi, mid) words in
+//                a separate buffer (pair stride 72 words)
+//   P:           after the softmax the 20 S accumulator fragments ARE the A fragments of P V (k16 = the 16 halo
+//                columns of one halo row); they are packed to hi / mid once and reused for every V chunk
+// ------------------------------------------------------------------------------------------------
+constexpr int BSTR = 40;                                             // words per pixel of the K / Q landing rows
+constexpr int BKV_WORDS = MT_ROWS * MT_COLS * BSTR;                  // 15360
+constexpr int BQ_WORDS = MQ_ROWS * MQ_COLS * BSTR;                   // 5120
+constexpr int BSTAGE_WORDS = BKV_WORDS + BQ_WORDS;                   // 20480 (80 KB)
+constexpr int VPSTR = 72;                                            // words per key pair of the packed V chunk
+constexpr int VPK_WORDS = MT_ROWS * (MT_COLS / 2) * VPSTR;           // 13824 (54 KB)
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+  return r;
+}
+// (x0, x1) -> hi = bf16x2(x0, x1), mid = bf16x2(x0 - hi0, x1 - hi1)
+__device__ __forceinline__ uint2 split_bf16x2(float x0, float x1) {
+  const uint32_t h = pack_bf16x2(x0, x1);
+  return make_uint2(h, pack_bf16x2(x0 - __uint_as_float(h << 16), x1 - __uint_as_float(h & 0xFFFF0000u)));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(256, 1)
+lcab_window_bf16_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk,
+                        const float* __restrict__ v, int ldv, float* __restrict__ out, int ldo, int H, int W, int C,
+                        float scale) {
+  extern __shared__ __align__(16) float smem[];   // [2][BSTAGE_WORDS] landing / converted K,Q | [VPK_WORDS] packed V
+  uint32_t* vpk = reinterpret_cast<uint32_t*>(smem + 2 * BSTAGE_WORDS);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int x0 = blockIdx.x * MQ_COLS, y0 = blockIdx.y * MQ_ROWS, n = blockIdx.z;
+  const size_t img_off = (size_t)n * H * W;
+  const int nchunk = C / MCH;
+  const int nstage = 2 * nchunk;
+
+  auto issue = [&](int stage) {
+    const bool is_k = stage < nchunk;
+    const float* src = is_k ? k : v;
+    const int ld = is_k ? ldk : ldv;
+    const int c0 = (is_k ? stage : stage - nchunk) * MCH;
+    float* dst = smem + (stage & 1) * BSTAGE_WORDS;
+    for (int i = tid; i < MT_ROWS * MT_COLS * (MCH / 4); i += 256) {
+      int px = i / (MCH / 4), c4 = i % (MCH / 4);
+      int gy = y0 - 4 + px / MT_COLS, gx = x0 - 4 + px % MT_COLS;
+      bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
+      const float* gp = ok ? src + (img_off + (size_t)gy * W + gx) * ld + c0 + c4 * 4 : src;
+      cp_async16(dst + px * BSTR + c4 * 4, gp, ok);
+    }
+    if (is_k) {
+      float* qd = dst + BKV_WORDS;
+      for (int i = tid; i < MQ_ROWS * MQ_COLS * (MCH / 4); i += 256) {
+        int px = i / (MCH / 4), c4 = i % (MCH / 4);
+        int gy = y0 + px / MQ_COLS, gx = x0 + px % MQ_COLS;
+        bool ok = gy < H && gx < W;
+        const float* gp = ok ? q + (img_off + (size_t)gy * W + gx) * ldq + c0 + c4 * 4 : q;
+        cp_async16(qd + px * BSTR + c4 * 4, gp, ok);
+      }
+    }
+    cp_async_commit();
+  };
+
+  const int wy = 2 * (warp >> 1), wx = 8 * (warp & 1);
+  float S[20][4];
+#pragma unroll
+  for (int b = 0; b < 20; ++b) S[b][0] = S[b][1] = S[b][2] = S[b][3] = 0.f;
+  uint32_t Ph[10][4], Pm[10][4];                     // P = softmax(S) as packed bf16 hi / mid A fragments
+
+  issue(0);
+  for (int stage = 0; stage < nstage; ++stage) {
+    if (stage + 1 < nstage) {
+      issue(stage + 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    float* buf = smem + (stage & 1) * BSTAGE_WORDS;
+    if (stage < nchunk) {
+      // ---- split K and Q in place: channel pair (2j, 2j+1) of a pixel -> (hi, mid) ----
+      for (int i = tid; i < (MT_ROWS * MT_COLS + MQ_ROWS * MQ_COLS) * (MCH / 2); i += 256) {
+        float* pp = buf + (i >> 4) * BSTR + (i & 15) * 2;
+        const float2 x = *reinterpret_cast<const float2*>(pp);
+        *reinterpret_cast<uint2*>(pp) = split_bf16x2(x.x, x.y);
+      }
+      __syncthreads();
+      // ---------------- S += Q[chunk] K[chunk]^T ----------------
+      const uint32_t* kw = reinterpret_cast<const uint32_t*>(buf);
+      const uint32_t* qw = kw + BKV_WORDS + (wy * MQ_COLS + wx) * BSTR;
+#pragma unroll
+      for (int ks = 0; ks < MCH / 16; ++ks) {
+        uint32_t ah[4], am[4];
+        {
+          const uint2 a0 = *reinterpret_cast<const uint2*>(qw + g * BSTR + (ks * 8 + t) * 2);
+          const uint2 a1 = *reinterpret_cast<const uint2*>(qw + (MQ_COLS + g) * BSTR + (ks * 8 + t) * 2);
+          const uint2 a2 = *reinterpret_cast<const uint2*>(qw + g * BSTR + (ks * 8 + t + 4) * 2);
+          const uint2 a3 = *reinterpret_cast<const uint2*>(qw + (MQ_COLS + g) * BSTR + (ks * 8 + t + 4) * 2);
+          ah[0] = a0.x; am[0] = a0.y; ah[1] = a1.x; am[1] = a1.y;
+          ah[2] = a2.x; am[2] = a2.y; ah[3] = a3.x; am[3] = a3.y;
+        }
+        // 4 key blocks at a time, product-major: consecutive mma.sync never share an accumulator (the legacy
+        // tensor path has a long issue-to-result latency; 3 back-to-back products into one fragment serialise on it)
+#pragma unroll
+        for (int r2 = 0; r2 < 5; ++r2) {
+          uint2 b0[4], b1[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint32_t* kp = kw + ((wy + 2 * r2 + (u >> 1)) * MT_COLS + wx + (u & 1) * 8 + g) * BSTR + (ks * 8 + t) * 2;
+            b0[u] = *reinterpret_cast<const uint2*>(kp);
+            b1[u] = *reinterpret_cast<const uint2*>(kp + 8);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) mma_bf16(S[r2 * 4 + u], am, b0[u].x, b1[u].x);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) mma_bf16(S[r2 * 4 + u], ah, b0[u].y, b1[u].y);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) mma_bf16(S[r2 * 4 + u], ah, b0[u].x, b1[u].x);
+        }
+      }
+      if (stage == nchunk - 1) {
+        // ---------------- masked softmax over the 81 in-window keys ----------------
+        float m0 = -INFINITY, m1 = -INFINITY;   // fragment rows g (query row wy) and g+8 (query row wy+1)
+#pragma unroll
+        for (int b = 0; b < 20; ++b) {
+          const int r = b >> 1, cb = b & 1;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int d = cb * 8 + 2 * t + j - g;               // key column - query column + 4
+            const bool colok = d >= 0 && d <= 8;
+            S[b][j] = (colok && r <= 8) ? S[b][j] * scale : -INFINITY;
+            S[b][2 + j] = (colok && r >= 1) ? S[b][2 + j] * scale : -INFINITY;
+            m0 = fmaxf(m0, S[b][j]);
+            m1 = fmaxf(m1, S[b][2 + j]);
+          }
+        }
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int b = 0; b < 20; ++b)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            S[b][j] = expf(S[b][j] - m0);            // exp(-inf) = 0 for out-of-window entries
+            S[b][2 + j] = expf(S[b][2 + j] - m1);
+            s0 += S[b][j];
+            s1 += S[b][2 + j];
+          }
+        s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
+        s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+        const float i0 = 1.f / s0, i1 = 1.f / s1;
+        // A fragments of P V for halo row r: k = the 16 halo columns wx .. wx+15 (block cb=0 -> k 0..7, cb=1 -> 8..15)
+#pragma unroll
+        for (int r = 0; r < 10; ++r)
+#pragma unroll
+          for (int cb = 0; cb < 2; ++cb) {
+            const uint2 lo = split_bf16x2(S[r * 2 + cb][0] * i0, S[r * 2 + cb][1] * i0);   // row g
+            const uint2 hi = split_bf16x2(S[r * 2 + cb][2] * i1, S[r * 2 + cb][3] * i1);   // row g + 8
+            Ph[r][cb * 2] = lo.x; Pm[r][cb * 2] = lo.y;
+            Ph[r][cb * 2 + 1] = hi.x; Pm[r][cb * 2 + 1] = hi.y;
+          }
+      }
+    } else {
+      // ---- re-lay the V chunk: (key 2i, key 2i+1 of a halo row) x channel -> (hi, mid) ----
+      for (int i = tid; i < MT_ROWS * (MT_COLS / 2) * MCH; i += 256) {
+        const int c = i & (MCH - 1), pr = i >> 5;               // pr = row * 12 + pair
+        const int px = (pr / (MT_COLS / 2)) * MT_COLS + (pr % (MT_COLS / 2)) * 2;
+        const float v0 = buf[px * BSTR + c], v1 = buf[(px + 1) * BSTR + c];
+        *reinterpret_cast<uint2*>(vpk + pr * VPSTR + 2 * c) = split_bf16x2(v0, v1);
+      }
+      __syncthreads();
+      // ---------------- O[chunk] = P V[chunk] ----------------
+      float O[MCH / 8][4];
+#pragma unroll
+      for (int nb = 0; nb < MCH / 8; ++nb) O[nb][0] = O[nb][1] = O[nb][2] = O[nb][3] = 0.f;
+#pragma unroll
+      for (int r = 0; r < 10; ++r) {
+        const uint32_t* vp = vpk + ((wy + r) * (MT_COLS / 2) + wx / 2 + t) * VPSTR + 2 * g;
+        uint2 b0[MCH / 8], b1[MCH / 8];
+#pragma unroll
+        for (int nb = 0; nb < MCH / 8; ++nb) {
+          b0[nb] = *reinterpret_cast<const uint2*>(vp + nb * 16);
+          b1[nb] = *reinterpret_cast<const uint2*>(vp + 4 * VPSTR + nb * 16);
+        }
+#pragma unroll
+        for (int nb = 0; nb < MCH / 8; ++nb) mma_bf16(O[nb], Pm[r], b0[nb].x, b1[nb].x);
+#pragma unroll
+        for (int nb = 0; nb < MCH / 8; ++nb) mma_bf16(O[nb], Ph[r], b0[nb].y, b1[nb].y);
+#pragma unroll
+        for (int nb = 0; nb < MCH / 8; ++nb) mma_bf16(O[nb], Ph[r], b0[nb].x, b1[nb].x);
+      }
+      const int cbase = (stage - nchunk) * MCH;
+      const int qx = x0 + wx + g;
+      if (qx < W) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int qy = y0 + wy + half;
+          if (qy < H) {
+            float* o = out + (img_off + (size_t)qy * W + qx) * ldo + cbase + 2 * t;
+#pragma unroll
+            for (int nb = 0; nb < MCH / 8; ++nb)
+              *reinterpret_cast<float2*>(o + nb * 8) = make_float2(O[nb][half * 2], O[nb][half * 2 + 1]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Unfused NCHW window ops with the exact contract of the reference extension `localattention`
 // (locatt_ops/kernels.cuh: cc2k :4-42, ck2c_ori :44-80, ck2c_loc :82-119; fp32 data, fp64 accumulate
 // as in f_cc2k<float,double>).  They exist for drop-in compatibility (autograd of the unfused path);
@@ -409,11 +636,11 @@ __global__ void locatt_ck2c_loc_kernel(const float* __restrict__ x_ori, const fl
 
 }  // namespace
 
-static int g_force_ffma_window = 0;
+static int g_force_ffma_window = 0;   // 1: FFMA kernel, 2: 3xTF32 mma.sync kernel, 0: bf16-split mma.sync kernel
 
 extern "C" {
 
-// test hook: 1 = use the FFMA window kernel even where the tensor-core one applies
+// test hook: 0 = bf16-split tensor-core kernel (default), 1 = FFMA kernel, 2 = 3xTF32 tensor-core kernel
 int di_set_window_ffma(int on) {
   g_force_ffma_window = on;
   return DI_OK;
@@ -429,7 +656,16 @@ int di_lcab_window_f32(const float* q, int ldq, const float* k, int ldk, const f
   DI_CHECK_ARG(((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)out) % 16 == 0, "di_lcab_window_f32: pointers must be 16-byte aligned");
   dim3 grid(di_cdiv(W, TQ), di_cdiv(H, TQ), N);
   float scale = 1.0f / sqrtf((float)C);
-  if (ksize == 9 && C % MCH == 0 && !g_force_ffma_window) {
+  if (ksize == 9 && C % MCH == 0 && g_force_ffma_window == 0) {
+    dim3 mgrid(di_cdiv(W, MQ_COLS), di_cdiv(H, MQ_ROWS), N);
+    size_t smem = (2ull * BSTAGE_WORDS + VPK_WORDS) * sizeof(float);
+    static bool once_bf = false;
+    if (!once_bf) {
+      cudaFuncSetAttribute(lcab_window_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      once_bf = true;
+    }
+    lcab_window_bf16_kernel<<<mgrid, 256, smem, stream>>>(q, ldq, k, ldk, v, ldv, out, ldo, H, W, C, scale);
+  } else if (ksize == 9 && C % MCH == 0 && g_force_ffma_window == 2) {
     dim3 mgrid(di_cdiv(W, MQ_COLS), di_cdiv(H, MQ_ROWS), N);
     size_t smem = 2ull * MSTAGE_FLOATS * sizeof(float);
     static bool once_mma = false;

@@ -16,7 +16,10 @@ ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 
 LAUNCHES = [0]   # number of libdi_b200 kernel-launching calls (bench.py reports it)
 USE_TC = [os.environ.get('DI_B200_TC', '1') != '0']   # tcgen05 split-product path for Weight objects (else FFMA)
+TC_CONV = [os.environ.get('DI_B200_TC_CONV', '1') != '0']
+TC_MIN_M = [int(os.environ.get('DI_B200_TC_MIN_M', '128'))]   # smaller row counts go to the fp32 FFMA kernels
 TC_BF16 = [os.environ.get('DI_B200_TC_BF16', '1') != '0']   # bf16-split operands where K % 64 == 0 (else 3xTF32)
+_TAG = ['']        # optional shape tag for the next profiled call (bench.py --shapes table)
 PROFILE = [None]  # bench.py sets PROFILE[0] = [] to record (name, start_event, end_event, bytes, flops) per call
 
 
@@ -47,7 +50,8 @@ def _call(name, *args, nbytes=0, flops=0):
     e0.record()
     rc = _lib.check(getattr(_lib.lib(), name)(*args), name)
     e1.record()
-    prof.append((name, e0, e1, nbytes, flops))
+    prof.append((name + _TAG[0], e0, e1, nbytes, flops))
+    _TAG[0] = ''
     return rc
 
 
@@ -63,7 +67,7 @@ def linear(srcs, W, bias=None, act=ACT_NONE, out=None, res=None, res_mod=0, spli
     M = srcs[0].shape[0]
     N, K = W.shape
     if isinstance(W, Weight):
-        if (USE_TC[0] and splits == 1 and M >= 128 and N % 4 == 0
+        if (USE_TC[0] and splits == 1 and (M >= TC_MIN_M[0] or N > 2048) and N % 4 == 0
                 and all(s_.shape[1] % 32 == 0 and s_.stride(0) % 4 == 0 and s_.data_ptr() % 16 == 0 for s_ in srcs)):
             return _linear_tc(srcs, W, bias, act, out, res, res_mod, M, N, K)
         W = W.w
@@ -86,6 +90,8 @@ def linear(srcs, W, bias=None, act=ACT_NONE, out=None, res=None, res_mod=0, spli
         out = torch.empty(M, N, device=W.device, dtype=torch.float32)
     po, ldo = _rows(out)
     pr, ldr = (None, 0) if res is None else _rows(res)
+    if PROFILE[0] is not None:
+        _TAG[0] = ' M%d N%d K%d' % (M, N, K)
     _call('di_linear_f32', *a, _ptr(W), _ptr(bias), pr, ldr, res_mod, po, ldo, M, N, act, 1, 0, _stream(),
           nbytes=4 * (M * K + N * K + M * N + (0 if res is None else res.numel())), flops=2 * M * N * K)
     return out
@@ -104,6 +110,8 @@ def _linear_tc(srcs, W, bias, act, out, res, res_mod, M, N, K):
     po, ldo = _rows(out)
     pr, ldr = (None, 0) if res is None else _rows(res)
     bf = TC_BF16[0] and all(s.shape[1] % 64 == 0 for s in srcs)
+    if PROFILE[0] is not None:
+        _TAG[0] = ' M%d N%d K%s' % (M, N, '+'.join(str(s.shape[1]) for s in srcs))
     _call('di_linear_tcb_f32' if bf else 'di_linear_tc_f32', *a, _ptr(W.bh if bf else W.hi), _ptr(W.bm if bf else W.lo),
           _ptr(bias), pr, ldr, res_mod, po, ldo, M, N, act, _stream(),
           nbytes=4 * (M * K + N * K + M * N + (0 if res is None else res.numel())), flops=2 * M * N * K)
@@ -119,7 +127,7 @@ def conv3x3(x, w_packed, bias, cout, x_nhwc, y_nchw=False, act=ACT_NONE):
     else:
         N, Cin, H, W = x.shape
     if isinstance(w_packed, Weight):
-        if USE_TC[0] and not y_nchw and cout % 4 == 0 and Cin % 32 == 0:
+        if USE_TC[0] and TC_CONV[0] and not y_nchw and cout % 4 == 0 and Cin % 32 == 0:
             xin = x if x_nhwc else nchw_to_nhwc(x)       # the TMA box walks a pixel-major map
             y = torch.empty((N, H, W, cout), device=x.device, dtype=torch.float32)
             bf = TC_BF16[0] and Cin % 64 == 0

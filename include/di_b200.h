@@ -89,7 +89,7 @@ int di_lcab_window_f32(const float* q, int ldq, const float* k, int ldk, const f
 
 /* test/diagnostic hook: 1 = always use the FFMA window kernel, 0 = tensor-core (mma.sync 3xTF32) kernel when
  * ksize == 9 and C % 32 == 0 (default) */
-int di_set_window_ffma(int on);
+int di_set_window_ffma(int on); /* test hook: 0 = bf16-split mma.sync kernel (default), 1 = FFMA, 2 = 3xTF32 mma.sync */
 
 /* The reference extension's own five entry points, unfused and NCHW, for drop-in compatibility
  * (locatt_ops/localAttention.cpp:61-73): similar_forward = cc2k(x_ori, x_loc); weighting_forward =

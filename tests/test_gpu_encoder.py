@@ -89,13 +89,13 @@ def test_layout_converters_roundtrip():
     assert torch.equal(ops.nhwc_to_nchw(y), x)
 
 
-@pytest.mark.parametrize('ffma', [False, True])
+@pytest.mark.parametrize('kernel', [0, 2, 1], ids=['mma-bf16split', 'mma-3xtf32', 'ffma'])
 @pytest.mark.parametrize('ks,C,H,W', [(9, 32, 13, 21), (9, 128, 40, 33), (3, 16, 7, 5), (9, 64, 16, 16), (9, 128, 9, 50)])
-def test_window_attention_matches_oracle(ks, C, H, W, ffma):
-    """Both window kernels: mma.sync 3xTF32 (default for ks=9, C%32==0) and the FFMA one."""
+def test_window_attention_matches_oracle(ks, C, H, W, kernel):
+    """All three window kernels: mma.sync bf16-split (default for ks=9, C%32==0), mma.sync 3xTF32, FFMA."""
     import oracle.mmri as om
     from deepinteraction_b200 import ops, _lib
-    _lib.lib().di_set_window_ffma(1 if ffma else 0)
+    _lib.lib().di_set_window_ffma(kernel)
     g = torch.Generator().manual_seed(3)
     N = 2
     q, k, v = (torch.randn(N, C, H, W, generator=g) for _ in range(3))
