@@ -356,6 +356,23 @@ def main():
     e2e_value = frames / (ms_e2e * 1e-3)
     pk = peaks()
 
+    # ---- encoder / decoder split of the step (graph replay, device-resident inputs) -----
+    def stage_ms(fn, n=10):
+        fn(); fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+    enc_out = neck(fr_dev['img_feats'], fr_dev['pts_feats'], fr_dev['img_metas'], fr_dev['pts_metas'])
+    enc_out = (enc_out[0].clone(), [t.clone() for t in enc_out[1]])
+    stages = dict(encoder_ms=stage_ms(lambda: neck(fr_dev['img_feats'], fr_dev['pts_feats'], fr_dev['img_metas'],
+                                                   fr_dev['pts_metas'])),
+                  decoder_ms=stage_ms(lambda: head(enc_out[1], enc_out[0], fr_dev['img_metas'])))
+
     # ---- per-kernel device times (separate pass so the event pairs do not perturb the timed regions) -----
     from deepinteraction_b200 import graph as di_graph
     di_graph.ENABLED[0] = False                  # event-instrumented pass: launch kernel by kernel
@@ -434,7 +451,7 @@ def main():
                          d2h_bytes_per_step=int(sum(v.numel() * v.element_size() for v in out.values())),
                          ms_per_step=ms_e2e / K, host_launch_ms_per_step=host_fwd / K * 1e3,
                          overlap='H2D of step i+1 on a copy stream (double-buffered device inputs) while step i computes'),
-                gpu_launches=launches, launches_per_step=launches / K, cuda_graph=bool(di_graph.ENABLED[0] and os.environ.get('DI_B200_GRAPH', '1') != '0'),
+                gpu_launches=launches, launches_per_step=launches / K, stages=stages, cuda_graph=bool(di_graph.ENABLED[0] and os.environ.get('DI_B200_GRAPH', '1') != '0'),
                 roofline=roof, cpu_baseline=cpu,
                 kernels=kernels[:12])
     print(json.dumps(line), flush=True)

@@ -302,6 +302,99 @@ int launch(const ALoader& la, const WLoader& lb, const Epilogue& ep, int M, int 
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+
+// ------------------------------------------------------------------------------------------------
+// Query-level dense layers of the decoder: M = batch * num_proposals (200..600 rows), K <= 512, N <= 512.
+// These are latency-bound, not throughput-bound: a 32 x 64 output tile per CTA of 128 threads (4 x 4 per thread)
+// gives 14..56 CTAs, the K loop runs on 32-wide chunks with the next chunk's global loads in flight during the
+// FMAs.  Plain fp32 FFMA with round-to-nearest in k order: these layers feed softmax logits and LayerNorms of a
+// badly conditioned stack, so they stay exact-fp32 rather than tensor-core split products.
+// ------------------------------------------------------------------------------------------------
+constexpr int SBM = 32, SBN = 64, SBK = 32;
+
+struct SmallSrc {          // scalars, not arrays: dynamically indexed kernel parameters end up in local memory
+  const float *p0, *p1, *p2;
+  int ld0, ld1, ld2;
+  int kend0, kend1;        // cumulative K boundaries of sources 0 and 1
+};
+
+__global__ void __launch_bounds__(128)
+linear_small_kernel(SmallSrc a, const float* __restrict__ W, const float* __restrict__ bias,
+                    const float* __restrict__ res, int ldres, int res_mod, float* __restrict__ C, int ldc, int M,
+                    int N, int K, int act) {
+  __shared__ float As[SBK][SBM + 1];               // k-major: As[k][row]
+  __shared__ float Ws[SBK][SBN + 1];               // Ws[k][col]
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * SBM, n0 = blockIdx.x * SBN;
+  // loader roles: A tile 32 rows x 32 k = 1024 floats -> 8 per thread (row = tid / 4, k = (tid % 4) * 8 .. +7)
+  //               W tile 64 cols x 32 k = 2048 floats -> 16 per thread (col = tid / 2, k = (tid % 2) * 16 .. +15)
+  const int ar = tid >> 2, ak = (tid & 3) * 8;
+  const int wc = tid >> 1, wk = (tid & 1) * 16;
+  float ra[8], rw[16];
+  auto load = [&](int k0) {
+    const int row = m0 + ar;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = k0 + ak + j;
+      float v = 0.f;
+      if (row < M && k < K) {
+        const float* src = k < a.kend0 ? a.p0 : (k < a.kend1 ? a.p1 : a.p2);
+        const int ld = k < a.kend0 ? a.ld0 : (k < a.kend1 ? a.ld1 : a.ld2);
+        const int kb = k < a.kend0 ? 0 : (k < a.kend1 ? a.kend0 : a.kend1);
+        v = __ldg(src + (size_t)row * ld + (k - kb));
+      }
+      ra[j] = v;
+    }
+    const int col = n0 + wc;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int k = k0 + wk + j;
+      rw[j] = (col < N && k < K) ? __ldg(W + (size_t)col * K + k) : 0.f;
+    }
+  };
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  load(0);
+  for (int k0 = 0; k0 < K; k0 += SBK) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) As[ak + j][ar] = ra[j];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) Ws[wk + j][wc] = rw[j];
+    __syncthreads();
+    if (k0 + SBK < K) load(k0 + SBK);              // next chunk's loads overlap the FMAs below
+#pragma unroll
+    for (int k = 0; k < SBK; ++k) {
+      float av[4], wv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) av[i] = As[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) wv[j] = Ws[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = m0 + ty * 4 + i;
+    if (row >= M) continue;
+    const float* rr = res ? res + (size_t)(row % res_mod) * ldres : nullptr;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = n0 + tx * 4 + j;
+      if (col >= N) continue;
+      float v = acc[i][j] + (bias ? __ldg(bias + col) : 0.f);
+      if (rr) v += __ldg(rr + col);
+      C[(size_t)row * ldc + col] = di_act(v, act);
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -317,6 +410,17 @@ int di_linear_f32(const float* A0, int lda0, int K0, const float* A1, int lda1, 
   DI_CHECK_ARG(A0 && W && C && M > 0 && N > 0 && K0 > 0, "di_linear_f32: null pointer or empty shape");
   DI_CHECK_ARG((K1 == 0 || A1) && (K2 == 0 || A2), "di_linear_f32: missing source");
   DI_CHECK_ARG(K2 == 0 || K1 > 0, "di_linear_f32: source 2 without source 1");
+  if (M <= 640 && splits == 1 && N <= 2048) {        // query-level layers: latency-optimised small-tile kernel
+    SmallSrc sa;
+    sa.p0 = A0; sa.p1 = A1 ? A1 : A0; sa.p2 = A2 ? A2 : A0;
+    sa.ld0 = lda0; sa.ld1 = lda1; sa.ld2 = lda2;
+    sa.kend0 = K0; sa.kend1 = K0 + K1;
+    dim3 grid(di_cdiv(N, SBN), di_cdiv(M, SBM));
+    linear_small_kernel<<<grid, 128, 0, stream>>>(sa, W, bias, res, ldres, res_mod > 0 ? res_mod : M, C, ldc, M, N,
+                                                  K0 + K1 + K2, act);
+    DI_CHECK_LAUNCH("di_linear_f32(small)");
+    return 1;
+  }
   RowsLoader la;
   la.p[0] = A0; la.p[1] = A1 ? A1 : A0; la.p[2] = A2 ? A2 : A0;
   la.ld[0] = lda0; la.ld[1] = lda1; la.ld[2] = lda2;

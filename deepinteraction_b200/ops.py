@@ -17,7 +17,7 @@ ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 LAUNCHES = [0]   # number of libdi_b200 kernel-launching calls (bench.py reports it)
 USE_TC = [os.environ.get('DI_B200_TC', '1') != '0']   # tcgen05 split-product path for Weight objects (else FFMA)
 TC_CONV = [os.environ.get('DI_B200_TC_CONV', '1') != '0']
-TC_MIN_M = [int(os.environ.get('DI_B200_TC_MIN_M', '128'))]   # smaller row counts go to the fp32 FFMA kernels
+TC_MIN_M = [int(os.environ.get('DI_B200_TC_MIN_M', '128'))]   # fewer rows: fp32 FFMA kernels of gemm.cu (measured: the tensor-core kernel is faster from 128 rows up)
 TC_BF16 = [os.environ.get('DI_B200_TC_BF16', '1') != '0']   # bf16-split operands where K % 64 == 0 (else 3xTF32)
 _TAG = ['']        # optional shape tag for the next profiled call (bench.py --shapes table)
 PROFILE = [None]  # bench.py sets PROFILE[0] = [] to record (name, start_event, end_event, bytes, flops) per call
