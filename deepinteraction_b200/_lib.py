@@ -23,6 +23,7 @@ SIGNATURES = {
     'di_conv3x3_f32': [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     'di_linear_tc_f32': [_p, _i, _i, _p, _i, _i, _p, _i, _i, _p, _p, _p, _p, _i, _i, _p, _i, _i, _i, _i, _p],
     'di_linear_tcb_f32': [_p, _i, _i, _p, _i, _i, _p, _i, _i, _p, _p, _p, _p, _i, _i, _p, _i, _i, _i, _i, _p],
+    'di_linear_tcb_split_f32': [_p, _i, _i, _p, _i, _i, _p, _i, _i, _p, _p, _p, _p, _i, _i, _p, _i, _i, _i, _i, _i, _i, _p],
     'di_conv3x3_tc_f32': [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     'di_conv3x3_tcb_f32': [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     'di_tc_set_debug': [_i],
@@ -30,6 +31,7 @@ SIGNATURES = {
     'di_tc_debug_read': [ctypes.POINTER(ctypes.c_longlong)],
     # lcab.cu
     'di_lcab_window_f32': [_p, _i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _p],
+    'di_lcab_window_pre_f32': [_p, _i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _p],
     'di_set_window_ffma': [_i],
     'di_locatt_cc2k_f32': [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     'di_locatt_ck2c_ori_f32': [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p],

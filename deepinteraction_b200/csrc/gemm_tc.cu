@@ -166,6 +166,7 @@ struct TcParams {
   int ldres, res_mod, act;
   int dbg;
   int* sched;               // v3: 16 ints of the dynamic tile scheduler (column-group counters [0..13], done [15])
+  int split_col0, split_kind;  // output columns >= split_col0 are emitted as bf16 (hi, mid) words (0 = off), see below
 };
 __host__ __device__ __forceinline__ int tc_kch(const TcParams& p, int s) { return s == 0 ? p.k0 : (s == 1 ? p.k1 : p.k2); }
 
@@ -225,6 +226,40 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
       "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
       "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
+}
+
+// Pre-split outputs for the window-attention kernel (lcab.cu), same 4 bytes per value, same position of each
+// 32-channel block: the consumer then needs no conversion pass.  hi = bf16(x), mid = bf16(x - hi), packed bf16x2
+// with the lower channel in the low half.
+//   kind 1 (Q, K): channel pair (2j, 2j+1) -> words 2j = hi pair, 2j+1 = mid pair          (one LDS.64 per fragment)
+//   kind 2 (V):    channel group of 8      -> words 8g..8g+3 = hi pairs, 8g+4..8g+7 = mid pairs  (16-byte rows for
+//                                             ldmatrix.trans: the k index of P V is the key, not the channel)
+__device__ __forceinline__ void split_block(float (&v)[32], int kind) {
+  if (kind == 1) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const uint32_t h = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+      const uint32_t m = pack_bf16x2(v[2 * j] - __uint_as_float(h << 16), v[2 * j + 1] - __uint_as_float(h & 0xFFFF0000u));
+      v[2 * j] = __uint_as_float(h);
+      v[2 * j + 1] = __uint_as_float(m);
+    }
+  } else {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      uint32_t h[4], m[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float a = v[8 * g + 2 * q], b = v[8 * g + 2 * q + 1];
+        h[q] = pack_bf16x2(a, b);
+        m[q] = pack_bf16x2(a - __uint_as_float(h[q] << 16), b - __uint_as_float(h[q] & 0xFFFF0000u));
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        v[8 * g + q] = __uint_as_float(h[q]);
+        v[8 * g + 4 + q] = __uint_as_float(m[q]);
+      }
+    }
+  }
 }
 
 // WRES: the whole [128, K<=128] weight slice (hi + lo, <= 128 KB) of this CTA's column tile stays resident in
@@ -583,6 +618,7 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           }
         }
         act_tile(v, act);
+        if (p.split_kind && col >= p.split_col0) split_block(v, p.split_kind);
         const uint32_t buf = my_ep + (uint32_t)(chunk & 1) * 4096u;
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // buffer's previous store done
         __syncwarp();
@@ -795,7 +831,7 @@ inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) =
 int linear_tc_impl(const char* name, int bf, const float* A0, int lda0, int K0, const float* A1, int lda1, int K1,
                    const float* A2, int lda2, int K2, const void* W_hi, const void* W_lo, const float* bias,
                    const float* res, int ldres, int res_mod, float* C, int ldc, int M, int N, int act,
-                   cudaStream_t stream) {
+                   int split_col0, int split_kind, cudaStream_t stream) {
   if (!(A0 && W_hi && W_lo && C && M > 0 && N > 0 && K0 > 0)) {
     di_set_error("%s: null pointer or empty shape", name);
     return DI_ERR_ARG;
@@ -833,6 +869,14 @@ int linear_tc_impl(const char* name, int bf, const float* A0, int lda0, int K0, 
   p.res_mod = res_mod > 0 ? res_mod : M; p.act = act; p.dbg = g_tc_debug;
   p.m_tiles = di_cdiv(M, TM);
   p.n_tiles = di_cdiv(N, TN);
+  if (split_kind) {
+    if (!((split_kind == 1 || split_kind == 2) && split_col0 >= 0 && split_col0 % 32 == 0 && N % 32 == 0)) {
+      di_set_error("%s: split output needs kind 1|2, split_col0 %% 32 == 0 and N %% 32 == 0", name);
+      return DI_ERR_ARG;
+    }
+    p.split_col0 = split_col0;
+    p.split_kind = split_kind;
+  }
   return launch_tc(maps, p, bf, stream, name);
 }
 
@@ -904,13 +948,22 @@ int di_linear_tc_f32(const float* A0, int lda0, int K0, const float* A1, int lda
                      int K2, const float* W_hi, const float* W_lo, const float* bias, const float* res, int ldres,
                      int res_mod, float* C, int ldc, int M, int N, int act, cudaStream_t stream) {
   return linear_tc_impl("di_linear_tc_f32", 0, A0, lda0, K0, A1, lda1, K1, A2, lda2, K2, W_hi, W_lo, bias, res, ldres,
-                        res_mod, C, ldc, M, N, act, stream);
+                        res_mod, C, ldc, M, N, act, 0, 0, stream);
 }
 int di_linear_tcb_f32(const float* A0, int lda0, int K0, const float* A1, int lda1, int K1, const float* A2, int lda2,
                       int K2, const void* W_hi, const void* W_mid, const float* bias, const float* res, int ldres,
                       int res_mod, float* C, int ldc, int M, int N, int act, cudaStream_t stream) {
   return linear_tc_impl("di_linear_tcb_f32", 1, A0, lda0, K0, A1, lda1, K1, A2, lda2, K2, W_hi, W_mid, bias, res, ldres,
-                        res_mod, C, ldc, M, N, act, stream);
+                        res_mod, C, ldc, M, N, act, 0, 0, stream);
+}
+// di_linear_tcb_f32 whose output columns >= split_col0 are written pre-split for di_lcab_window_pre_f32
+// (split_kind 1 = Q / K layout, 2 = V layout; see split_block above).  split_col0 % 32 == 0, N % 32 == 0.
+int di_linear_tcb_split_f32(const float* A0, int lda0, int K0, const float* A1, int lda1, int K1, const float* A2,
+                            int lda2, int K2, const void* W_hi, const void* W_mid, const float* bias, const float* res,
+                            int ldres, int res_mod, float* C, int ldc, int M, int N, int act, int split_col0,
+                            int split_kind, cudaStream_t stream) {
+  return linear_tc_impl("di_linear_tcb_split_f32", 1, A0, lda0, K0, A1, lda1, K1, A2, lda2, K2, W_hi, W_mid, bias, res,
+                        ldres, res_mod, C, ldc, M, N, act, split_col0, split_kind, stream);
 }
 
 // Tensor-core 3x3 convolution (stride 1, zero pad 1) over a pixel-major map: x [N,H,W,Cin] -> y [N,H,W,Cout],

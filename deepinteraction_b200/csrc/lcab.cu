@@ -571,6 +571,192 @@ lcab_window_bf16_kernel(const float* __restrict__ q, int ldq, const float* __res
 }
 
 // ------------------------------------------------------------------------------------------------
+// Same kernel for PRE-SPLIT operands: q, k (kind 1) and v (kind 2) were written by the producing dense layer's
+// epilogue already as bf16 (hi, mid) words (gemm_tc.cu split_block), 4 bytes per value at the value's own position.
+// The two conversion passes, one barrier per stage and the packed-V buffer disappear: stages go straight from
+// cp.async to fragments (LDS.64 for Q/K, ldmatrix.x4.trans for V).
+// ------------------------------------------------------------------------------------------------
+constexpr int VSTR2 = 36;                                            // V chunk pixel stride: 8 ldmatrix rows -> 32 distinct banks
+
+__global__ void __launch_bounds__(256, 1)
+lcab_window_pre_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk,
+                        const float* __restrict__ v, int ldv, float* __restrict__ out, int ldo, int H, int W, int C,
+                        float scale) {
+  extern __shared__ __align__(16) float smem[];   // [2][BSTAGE_WORDS]: K,Q chunk (pixel stride 40 words) or V chunk (36)
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int x0 = blockIdx.x * MQ_COLS, y0 = blockIdx.y * MQ_ROWS, n = blockIdx.z;
+  const size_t img_off = (size_t)n * H * W;
+  const int nchunk = C / MCH;
+  const int nstage = 2 * nchunk;
+
+  auto issue = [&](int stage) {
+    const bool is_k = stage < nchunk;
+    const float* src = is_k ? k : v;
+    const int ld = is_k ? ldk : ldv;
+    const int c0 = (is_k ? stage : stage - nchunk) * MCH;
+    float* dst = smem + (stage & 1) * BSTAGE_WORDS;
+    const int pstr = is_k ? BSTR : VSTR2;
+    for (int i = tid; i < MT_ROWS * MT_COLS * (MCH / 4); i += 256) {
+      int px = i / (MCH / 4), c4 = i % (MCH / 4);
+      int gy = y0 - 4 + px / MT_COLS, gx = x0 - 4 + px % MT_COLS;
+      bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
+      const float* gp = ok ? src + (img_off + (size_t)gy * W + gx) * ld + c0 + c4 * 4 : src;
+      cp_async16(dst + px * pstr + c4 * 4, gp, ok);
+    }
+    if (is_k) {
+      float* qd = dst + BKV_WORDS;
+      for (int i = tid; i < MQ_ROWS * MQ_COLS * (MCH / 4); i += 256) {
+        int px = i / (MCH / 4), c4 = i % (MCH / 4);
+        int gy = y0 + px / MQ_COLS, gx = x0 + px % MQ_COLS;
+        bool ok = gy < H && gx < W;
+        const float* gp = ok ? q + (img_off + (size_t)gy * W + gx) * ldq + c0 + c4 * 4 : q;
+        cp_async16(qd + px * BSTR + c4 * 4, gp, ok);
+      }
+    }
+    cp_async_commit();
+  };
+
+  const int wy = 2 * (warp >> 1), wx = 8 * (warp & 1);
+  float S[20][4];
+#pragma unroll
+  for (int b = 0; b < 20; ++b) S[b][0] = S[b][1] = S[b][2] = S[b][3] = 0.f;
+  uint32_t Ph[10][4], Pm[10][4];                     // P = softmax(S) as packed bf16 hi / mid A fragments
+
+  issue(0);
+  for (int stage = 0; stage < nstage; ++stage) {
+    if (stage + 1 < nstage) {
+      issue(stage + 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    float* buf = smem + (stage & 1) * BSTAGE_WORDS;
+    if (stage < nchunk) {
+      // ---------------- S += Q[chunk] K[chunk]^T ----------------
+      const uint32_t* kw = reinterpret_cast<const uint32_t*>(buf);
+      const uint32_t* qw = kw + BKV_WORDS + (wy * MQ_COLS + wx) * BSTR;
+#pragma unroll
+      for (int ks = 0; ks < MCH / 16; ++ks) {
+        uint32_t ah[4], am[4];
+        {
+          const uint2 a0 = *reinterpret_cast<const uint2*>(qw + g * BSTR + (ks * 8 + t) * 2);
+          const uint2 a1 = *reinterpret_cast<const uint2*>(qw + (MQ_COLS + g) * BSTR + (ks * 8 + t) * 2);
+          const uint2 a2 = *reinterpret_cast<const uint2*>(qw + g * BSTR + (ks * 8 + t + 4) * 2);
+          const uint2 a3 = *reinterpret_cast<const uint2*>(qw + (MQ_COLS + g) * BSTR + (ks * 8 + t + 4) * 2);
+          ah[0] = a0.x; am[0] = a0.y; ah[1] = a1.x; am[1] = a1.y;
+          ah[2] = a2.x; am[2] = a2.y; ah[3] = a3.x; am[3] = a3.y;
+        }
+        // 4 key blocks at a time, product-major: consecutive mma.sync never share an accumulator (the legacy
+        // tensor path has a long issue-to-result latency; 3 back-to-back products into one fragment serialise on it)
+#pragma unroll
+        for (int r2 = 0; r2 < 5; ++r2) {
+          uint2 b0[4], b1[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint32_t* kp = kw + ((wy + 2 * r2 + (u >> 1)) * MT_COLS + wx + (u & 1) * 8 + g) * BSTR + (ks * 8 + t) * 2;
+            b0[u] = *reinterpret_cast<const uint2*>(kp);
+            b1[u] = *reinterpret_cast<const uint2*>(kp + 8);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) mma_bf16(S[r2 * 4 + u], am, b0[u].x, b1[u].x);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) mma_bf16(S[r2 * 4 + u], ah, b0[u].y, b1[u].y);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) mma_bf16(S[r2 * 4 + u], ah, b0[u].x, b1[u].x);
+        }
+      }
+      if (stage == nchunk - 1) {
+        // ---------------- masked softmax over the 81 in-window keys ----------------
+        float m0 = -INFINITY, m1 = -INFINITY;   // fragment rows g (query row wy) and g+8 (query row wy+1)
+#pragma unroll
+        for (int b = 0; b < 20; ++b) {
+          const int r = b >> 1, cb = b & 1;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int d = cb * 8 + 2 * t + j - g;               // key column - query column + 4
+            const bool colok = d >= 0 && d <= 8;
+            S[b][j] = (colok && r <= 8) ? S[b][j] * scale : -INFINITY;
+            S[b][2 + j] = (colok && r >= 1) ? S[b][2 + j] * scale : -INFINITY;
+            m0 = fmaxf(m0, S[b][j]);
+            m1 = fmaxf(m1, S[b][2 + j]);
+          }
+        }
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int b = 0; b < 20; ++b)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            S[b][j] = expf(S[b][j] - m0);            // exp(-inf) = 0 for out-of-window entries
+            S[b][2 + j] = expf(S[b][2 + j] - m1);
+            s0 += S[b][j];
+            s1 += S[b][2 + j];
+          }
+        s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
+        s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+        const float i0 = 1.f / s0, i1 = 1.f / s1;
+        // A fragments of P V for halo row r: k = the 16 halo columns wx .. wx+15 (block cb=0 -> k 0..7, cb=1 -> 8..15)
+#pragma unroll
+        for (int r = 0; r < 10; ++r)
+#pragma unroll
+          for (int cb = 0; cb < 2; ++cb) {
+            const uint2 lo = split_bf16x2(S[r * 2 + cb][0] * i0, S[r * 2 + cb][1] * i0);   // row g
+            const uint2 hi = split_bf16x2(S[r * 2 + cb][2] * i1, S[r * 2 + cb][3] * i1);   // row g + 8
+            Ph[r][cb * 2] = lo.x; Pm[r][cb * 2] = lo.y;
+            Ph[r][cb * 2 + 1] = hi.x; Pm[r][cb * 2 + 1] = hi.y;
+          }
+      }
+    } else {
+      // ---------------- O[chunk] = P V[chunk] ----------------
+      // V arrives pre-split in 8-channel groups [4 hi words | 4 mid words]; ldmatrix.trans turns the [key][channel]
+      // rows into the (k = key pair, n = channel) B fragments: matrices 0/1 = keys 0-7 / 8-15 hi, 2/3 = the mid parts.
+      float O[MCH / 8][4];
+#pragma unroll
+      for (int nb = 0; nb < MCH / 8; ++nb) O[nb][0] = O[nb][1] = O[nb][2] = O[nb][3] = 0.f;
+      const uint32_t vbase = (uint32_t)__cvta_generic_to_shared(buf) +
+                             (uint32_t)(((wy * MT_COLS + wx + (lane & 7) + ((lane >> 3) & 1) * 8) * VSTR2 + (lane >> 4) * 4) * 4);
+#pragma unroll
+      for (int r = 0; r < 10; ++r) {
+        uint32_t bh0[MCH / 8], bh1[MCH / 8], bm0[MCH / 8], bm1[MCH / 8];
+#pragma unroll
+        for (int nb = 0; nb < MCH / 8; ++nb)
+          asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(bh0[nb]), "=r"(bh1[nb]), "=r"(bm0[nb]), "=r"(bm1[nb])
+                       : "r"(vbase + (uint32_t)((r * MT_COLS * VSTR2 + nb * 8) * 4)));
+#pragma unroll
+        for (int nb = 0; nb < MCH / 8; ++nb) mma_bf16(O[nb], Pm[r], bh0[nb], bh1[nb]);
+#pragma unroll
+        for (int nb = 0; nb < MCH / 8; ++nb) mma_bf16(O[nb], Ph[r], bm0[nb], bm1[nb]);
+#pragma unroll
+        for (int nb = 0; nb < MCH / 8; ++nb) mma_bf16(O[nb], Ph[r], bh0[nb], bh1[nb]);
+      }
+      const int cbase = (stage - nchunk) * MCH;
+      const int qx = x0 + wx + g;
+      if (qx < W) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int qy = y0 + wy + half;
+          if (qy < H) {
+            float* o = out + (img_off + (size_t)qy * W + qx) * ldo + cbase + 2 * t;
+#pragma unroll
+            for (int nb = 0; nb < MCH / 8; ++nb)
+              *reinterpret_cast<float2*>(o + nb * 8) = make_float2(O[nb][half * 2], O[nb][half * 2 + 1]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Unfused NCHW window ops with the exact contract of the reference extension `localattention`
 // (locatt_ops/kernels.cuh: cc2k :4-42, ck2c_ori :44-80, ck2c_loc :82-119; fp32 data, fp64 accumulate
 // as in f_cc2k<float,double>).  They exist for drop-in compatibility (autograd of the unfused path);
@@ -643,6 +829,26 @@ extern "C" {
 // test hook: 0 = bf16-split tensor-core kernel (default), 1 = FFMA kernel, 2 = 3xTF32 tensor-core kernel
 int di_set_window_ffma(int on) {
   g_force_ffma_window = on;
+  return DI_OK;
+}
+
+// di_lcab_window_f32 for operands that the producing layers emitted pre-split (di_linear_tcb_split_f32: q, k kind 1,
+// v kind 2).  9x9 window, C % 32 == 0.
+int di_lcab_window_pre_f32(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* out, int ldo,
+                           int N, int H, int W, int C, cudaStream_t stream) {
+  DI_CHECK_ARG(q && k && v && out && N > 0 && H > 0 && W > 0, "di_lcab_window_pre_f32: bad argument");
+  DI_CHECK_ARG(C > 0 && C % MCH == 0, "di_lcab_window_pre_f32: C must be a multiple of 32 (got %d)", C);
+  DI_CHECK_ARG(ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0 && ldo % 4 == 0, "di_lcab_window_pre_f32: strides must be multiples of 4");
+  DI_CHECK_ARG(((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)out) % 16 == 0, "di_lcab_window_pre_f32: pointers must be 16-byte aligned");
+  dim3 mgrid(di_cdiv(W, MQ_COLS), di_cdiv(H, MQ_ROWS), N);
+  size_t smem = 2ull * BSTAGE_WORDS * sizeof(float);
+  static bool once = false;
+  if (!once) {
+    cudaFuncSetAttribute(lcab_window_pre_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    once = true;
+  }
+  lcab_window_pre_kernel<<<mgrid, 256, smem, stream>>>(q, ldq, k, ldk, v, ldv, out, ldo, H, W, C, 1.0f / sqrtf((float)C));
+  DI_CHECK_LAUNCH("di_lcab_window_pre_f32");
   return DI_OK;
 }
 

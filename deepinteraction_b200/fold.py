@@ -89,6 +89,26 @@ def split_bf16(w):
     return hi.contiguous(), mid.contiguous()
 
 
+def split_rows(x, kind):
+    """Host model of the pre-split operand format of the window kernel (gemm_tc.cu split_block): x [M, C] fp32 ->
+    [M, C] fp32-typed tensor whose 32-bit words are packed bf16x2 (hi = bf16(x), mid = bf16(x - hi), lower channel in
+    the low half).  kind 1: channel pair j -> words 2j (hi), 2j+1 (mid); kind 2: channel group of 8 -> 4 hi | 4 mid."""
+    x = x.to(torch.float32)
+    hi = x.to(torch.bfloat16)
+    mid = (x - hi.to(torch.float32)).to(torch.bfloat16)
+    bits = lambda t: t.view(torch.int16).to(torch.int32) & 0xFFFF
+    pack = lambda b: (b[:, 0::2] | (b[:, 1::2] << 16))                  # [M, C/2] words
+    wh, wm = pack(bits(hi)), pack(bits(mid))
+    M, C = x.shape
+    out = torch.empty(M, C, dtype=torch.int32, device=x.device)
+    if kind == 1:
+        out[:, 0::2], out[:, 1::2] = wh, wm
+    else:
+        o = out.view(M, C // 8, 8)
+        o[:, :, :4], o[:, :, 4:] = wh.view(M, C // 8, 4), wm.view(M, C // 8, 4)
+    return out.view(torch.float32)
+
+
 class Weight:
     """A dense-layer weight [N, K] kept in the forms the kernels consume: plain fp32 (FFMA path), the TF32 hi/lo
     split and the bf16 hi/mid split (tcgen05 paths)."""

@@ -100,15 +100,28 @@ def _pack_lcab(blk, device):
 
 
 def lcab_forward(pk, target, source, N, H, W):
-    """target/source: [N*H*W, C] pixel-major rows (same tensor object => self attention)."""
+    """target/source: [N*H*W, C] pixel-major rows (same tensor object => self attention).
+    Where the tensor-core path applies, the projections that feed the window kernel write its operand format
+    directly (bf16 hi/mid words, ops.linear_split), so the window kernel has no conversion work."""
     C = pk['C']
+    pre = ops.can_presplit(N * H * W, C, pk['ks'])
     if target is source:
-        t = ops.linear([source], pk['w_self'], pk['b_self'], ops.ACT_RELU)            # [M, 3C] = q1 | k1 | v
+        if pre:
+            t = ops.linear_split([source], pk['w_self'], pk['b_self'], ops.ACT_RELU, 2 * C, 2)    # q1 | k1 | v(split)
+        else:
+            t = ops.linear([source], pk['w_self'], pk['b_self'], ops.ACT_RELU)        # [M, 3C] = q1 | k1 | v
         q1, k1, v = t[:, :C], t[:, C:2 * C], t[:, 2 * C:]
     else:
         q1 = ops.linear([target], pk['w_q1'], pk['b_q1'], ops.ACT_RELU)
-        t = ops.linear([source], pk['w_kv1'], pk['b_kv1'], ops.ACT_RELU)              # [M, 2C] = k1 | v
+        if pre:
+            t = ops.linear_split([source], pk['w_kv1'], pk['b_kv1'], ops.ACT_RELU, C, 2)          # k1 | v(split)
+        else:
+            t = ops.linear([source], pk['w_kv1'], pk['b_kv1'], ops.ACT_RELU)          # [M, 2C] = k1 | v
         k1, v = t[:, :C], t[:, C:]
+    if pre:
+        q = ops.linear_split([q1], pk['w_q2'], pk['b_q2'], ops.ACT_RELU, 0, 1)
+        k = ops.linear_split([k1], pk['w_k2'], pk['b_k2'], ops.ACT_RELU, 0, 1)
+        return ops.lcab_window_pre(q, k, v, N, H, W, C)
     q = ops.linear([q1], pk['w_q2'], pk['b_q2'], ops.ACT_RELU)
     k = ops.linear([k1], pk['w_k2'], pk['b_k2'], ops.ACT_RELU)
     return ops.lcab_window(q, k, v, N, H, W, C, pk['ks'])

@@ -118,6 +118,45 @@ def _linear_tc(srcs, W, bias, act, out, res, res_mod, M, N, K):
     return out
 
 
+PRESPLIT = [os.environ.get('DI_B200_PRESPLIT', '1') != '0']   # q/k/v projections emit bf16 (hi, mid) words for the window kernel
+
+
+def can_presplit(M, C, ksize):
+    """True when the k/q/v projections may write the window kernel's operand format directly."""
+    return bool(PRESPLIT[0] and USE_TC[0] and TC_BF16[0] and ksize == 9 and C % 64 == 0 and M >= TC_MIN_M[0])
+
+
+def linear_split(srcs, W, bias, act, split_col0, split_kind):
+    """linear() on the bf16-split tensor-core path whose output columns >= split_col0 are pre-split (kind 1: Q/K
+    layout, 2: V layout) for lcab_window_pre.  Only valid where can_presplit() holds."""
+    M, N = srcs[0].shape[0], W.shape[0]
+    assert isinstance(W, Weight) and all(s.shape[1] % 64 == 0 for s in srcs) and N % 32 == 0 and split_col0 % 32 == 0
+    a = []
+    for s in srcs:
+        _f32(s)
+        p, ld = _rows(s)
+        a += [p, ld, s.shape[1]]
+    while len(a) < 9:
+        a += [None, 0, 0]
+    out = torch.empty(M, N, device=W.w.device, dtype=torch.float32)
+    K = sum(s.shape[1] for s in srcs)
+    if PROFILE[0] is not None:
+        _TAG[0] = ' M%d N%d K%d split' % (M, N, K)
+    _call('di_linear_tcb_split_f32', *a, _ptr(W.bh), _ptr(W.bm), _ptr(bias), None, 0, 0, _ptr(out), N, M, N, act,
+          split_col0, split_kind, _stream(), nbytes=4 * (M * K + N * K + M * N), flops=2 * M * N * K)
+    return out
+
+
+def lcab_window_pre(q, k, v, N, H, W, C, out=None):
+    """lcab_window for pre-split q, k (kind 1) and v (kind 2) row views."""
+    if out is None:
+        out = torch.empty(N * H * W, C, device=q.device, dtype=torch.float32)
+    (pq, lq), (pk, lk), (pv, lv), (po, lo) = _rows(q), _rows(k), _rows(v), _rows(out)
+    _call('di_lcab_window_pre_f32', pq, lq, pk, lk, pv, lv, po, lo, N, H, W, C, _stream(),
+          nbytes=4 * 4 * N * H * W * C, flops=2 * 2 * 81 * N * H * W * C)
+    return out
+
+
 def conv3x3(x, w_packed, bias, cout, x_nhwc, y_nchw=False, act=ACT_NONE):
     """x: NCHW (N,Cin,H,W) or NHWC (N,H,W,Cin) contiguous; returns NHWC (N,H,W,cout) or NCHW."""
     _f32(x)

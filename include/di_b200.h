@@ -69,6 +69,15 @@ int di_linear_tc_f32(const float* A0, int lda0, int K0, const float* A1, int lda
 int di_linear_tcb_f32(const float* A0, int lda0, int K0, const float* A1, int lda1, int K1, const float* A2, int lda2,
                       int K2, const void* W_hi, const void* W_mid, const float* bias, const float* res, int ldres,
                       int res_mod, float* C, int ldc, int M, int N, int act, cudaStream_t stream);
+/* di_linear_tcb_f32 whose output columns >= split_col0 (a multiple of 32; N % 32 == 0) are written PRE-SPLIT for
+ * di_lcab_window_pre_f32: each value keeps its 4 bytes and its position, but holds packed bf16x2 words
+ * (hi = bf16(x), mid = bf16(x - hi)); split_kind 1 = Q/K layout (channel pair 2j,2j+1 -> words 2j = hi, 2j+1 = mid),
+ * 2 = V layout (channel group of 8 -> 4 hi words | 4 mid words).  Replaces the k/q/v projections of
+ * LocalContextAttentionBlock (models/utils/encoder_utils.py:95-131) when their consumer is the window kernel. */
+int di_linear_tcb_split_f32(const float* A0, int lda0, int K0, const float* A1, int lda1, int K1, const float* A2,
+                            int lda2, int K2, const void* W_hi, const void* W_mid, const float* bias, const float* res,
+                            int ldres, int res_mod, float* C, int ldc, int M, int N, int act, int split_col0,
+                            int split_kind, cudaStream_t stream);
 int di_conv3x3_tc_f32(const float* x, const float* w_hi, const float* w_lo, const float* bias, float* y, int N, int Cin,
                       int H, int W, int Cout, int act, cudaStream_t stream);
 int di_conv3x3_tcb_f32(const float* x, const void* w_hi, const void* w_mid, const float* bias, float* y, int N, int Cin,
@@ -86,6 +95,10 @@ int di_tc_debug_read(long long* host_buf);
  * (kept in the softmax), value skipped.  q,k,v,out [N,H,W,*] with per-pixel strides ld*. */
 int di_lcab_window_f32(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* out, int ldo,
                        int N, int H, int W, int C, int ksize, cudaStream_t stream);
+
+/* Same op for q, k (kind 1) and v (kind 2) emitted pre-split by di_linear_tcb_split_f32: no conversion passes. */
+int di_lcab_window_pre_f32(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* out, int ldo,
+                           int N, int H, int W, int C, cudaStream_t stream);
 
 /* test/diagnostic hook: 1 = always use the FFMA window kernel, 0 = tensor-core (mma.sync 3xTF32) kernel when
  * ksize == 9 and C % 32 == 0 (default) */

@@ -110,6 +110,35 @@ def test_window_attention_matches_oracle(ks, C, H, W, kernel):
     assert rel_err(out, ref) < TIGHT
 
 
+@pytest.mark.parametrize('C,H,W', [(64, 16, 16), (128, 40, 33), (128, 9, 50)])
+def test_window_attention_presplit_operands(C, H, W):
+    """The pre-split operand path: host-side model of the format -> di_lcab_window_pre_f32 vs the oracle, and
+    di_linear_tcb_split_f32 emits exactly that format."""
+    import oracle.mmri as om
+    from deepinteraction_b200 import ops, fold
+    g = torch.Generator().manual_seed(11)
+    N = 2
+    q, k, v = (torch.randn(N, C, H, W, generator=g) for _ in range(3))
+    w = F.softmax(om.window_similarity(q, k, 9) / np.sqrt(C), -1)
+    ref = om.window_weighting(v, w, 9)
+    rows = lambda t: t.permute(0, 2, 3, 1).reshape(-1, C).contiguous().to(dev())
+    out = ops.lcab_window_pre(fold.split_rows(rows(q), 1), fold.split_rows(rows(k), 1), fold.split_rows(rows(v), 2),
+                              N, H, W, C)
+    assert rel_err(out.view(N, H, W, C).permute(0, 3, 1, 2).cpu(), ref) < TIGHT
+    # the dense layer's split epilogue == split_rows(plain output), bit for bit
+    M = 1000
+    x = torch.randn(M, 128, generator=g).to(dev())
+    Wt = fold.Weight(torch.randn(3 * C, 128, generator=g) / 11, dev())
+    b = torch.randn(3 * C, generator=g).to(dev())
+    plain = ops.linear([x], Wt, b, ops.ACT_RELU)
+    mixed = ops.linear_split([x], Wt, b, ops.ACT_RELU, 2 * C, 2)
+    assert torch.equal(mixed[:, :2 * C], plain[:, :2 * C])
+    assert torch.equal(mixed[:, 2 * C:].contiguous().view(torch.int32),
+                       fold.split_rows(plain[:, 2 * C:].contiguous(), 2).view(torch.int32))
+    k1 = ops.linear_split([x], Wt, b, ops.ACT_RELU, 0, 1)
+    assert torch.equal(k1.view(torch.int32), fold.split_rows(plain, 1).view(torch.int32))
+
+
 def _mk_lcab(C, seed):
     import oracle.mmri as om
     from deepinteraction_b200 import synth
