@@ -57,6 +57,9 @@ SIGNATURES = {
     'di_dynconv_f32': [_p, _p, _p, _p, _p, _p, _p, _i, _f, _p],
     'di_nchw_to_nhwc_f32': [_p, _p, _i, _i, _i, _p],
     'di_nhwc_to_nchw_f32': [_p, _p, _i, _i, _i, _p],
+    'di_bbox_decode_f32': [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _f, _f, _f, _fp, _f, _i, _p, _p, _p, _p, _p],
+    'di_bbox_encode_f32': [_p, _i, _p, _i, _i, _f, _f, _f, _f, _p],
+    'di_circle_nms_f32': [_p, _i, _p, _p, _p, _i, _i, ctypes.c_uint, _f, _i, _p],
 }
 
 _lib = None

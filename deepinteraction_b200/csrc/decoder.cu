@@ -746,6 +746,143 @@ __global__ void nhwc_to_nchw_kernel(const float* __restrict__ in, float* __restr
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Box coder (core/bbox/coders/transfusion_bbox_coder.py) and the post-processing of get_bboxes
+// (models/dense_heads/deepinteraction_decoder.py:549-638).
+// ------------------------------------------------------------------------------------------------
+struct CoderParams {
+  float sx, sy, ox, oy;          // centre: feature cell -> metres (out_size_factor * voxel_size, pc_range)
+  float rng[6];                  // post_center_range
+  int use_range, use_thr;
+  float thr;
+};
+
+// One thread per (sample, proposal).  score_c = heat_c, or sigmoid(heat_c) * qscore_c * [c == qlabel] when qscore
+// is given (decoder.py:561-563); class = first arg-max over c (torch.max).  Box = transfusion_bbox_coder.py:61-75.
+__global__ void bbox_decode_kernel(const float* __restrict__ heat, const float* __restrict__ qscore,
+                                   const int* __restrict__ qlabel, const float* __restrict__ rot,
+                                   const float* __restrict__ dim, const float* __restrict__ center,
+                                   const float* __restrict__ height, const float* __restrict__ vel, int B, int K, int P,
+                                   CoderParams cp, float* __restrict__ boxes, float* __restrict__ scores,
+                                   int* __restrict__ labels, unsigned char* __restrict__ keep) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * P) return;
+  const int b = i / P, p = i - b * P;
+  float best = -INFINITY;
+  int arg = 0;
+  for (int c = 0; c < K; ++c) {
+    float v = heat[((size_t)b * K + c) * P + p];
+    if (qscore) {
+      v = 1.f / (1.f + expf(-v));
+      v = v * qscore[((size_t)b * K + c) * P + p] * (qlabel[i] == c ? 1.f : 0.f);
+    }
+    if (v > best) { best = v; arg = c; }
+  }
+  const int nb = vel ? 9 : 7;
+  float* o = boxes + (size_t)i * nb;
+  const float cx = center[((size_t)b * 2 + 0) * P + p] * cp.sx + cp.ox;
+  const float cy = center[((size_t)b * 2 + 1) * P + p] * cp.sy + cp.oy;
+  const float dx = expf(dim[((size_t)b * 3 + 0) * P + p]);
+  const float dy = expf(dim[((size_t)b * 3 + 1) * P + p]);
+  const float dz = expf(dim[((size_t)b * 3 + 2) * P + p]);
+  const float z = height[(size_t)b * P + p] - dz * 0.5f;                 // gravity centre -> bottom centre
+  o[0] = cx; o[1] = cy; o[2] = z; o[3] = dx; o[4] = dy; o[5] = dz;
+  o[6] = atan2f(rot[((size_t)b * 2 + 0) * P + p], rot[((size_t)b * 2 + 1) * P + p]);
+  if (vel) {
+    o[7] = vel[((size_t)b * 2 + 0) * P + p];
+    o[8] = vel[((size_t)b * 2 + 1) * P + p];
+  }
+  scores[i] = best;
+  labels[i] = arg;
+  bool k = true;
+  if (cp.use_range)
+    k = cx >= cp.rng[0] && cy >= cp.rng[1] && z >= cp.rng[2] && cx <= cp.rng[3] && cy <= cp.rng[4] && z <= cp.rng[5];
+  if (cp.use_thr) k = k && best > cp.thr;
+  keep[i] = k ? 1 : 0;
+}
+
+// transfusion_bbox_coder.py:24-38
+__global__ void bbox_encode_kernel(const float* __restrict__ boxes, int nb, float* __restrict__ t, int code, int n,
+                                   CoderParams cp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* s = boxes + (size_t)i * nb;
+  float* o = t + (size_t)i * code;
+  for (int c = 0; c < code; ++c) o[c] = 0.f;
+  o[0] = (s[0] - cp.ox) / cp.sx;
+  o[1] = (s[1] - cp.oy) / cp.sy;
+  o[3] = logf(s[3]); o[4] = logf(s[4]); o[5] = logf(s[5]);
+  o[2] = s[2] + s[5] * 0.5f;
+  o[6] = sinf(s[6]);
+  o[7] = cosf(s[6]);
+  if (code == 10) { o[8] = s[7]; o[9] = s[8]; }
+}
+
+// Circle NMS of one task (a set of classes, squared-distance threshold) for one sample per CTA, greedy in descending
+// score order (ties: lower index first), at most post_max kept (mmdet3d circle_nms as called at decoder.py:603-609).
+// keep_io: in = candidates that survived the coder's filter, out = survivors of this task are left set, the
+// suppressed candidates of this task are cleared; other classes are untouched.
+constexpr int NMS_MAX = 1024;
+__global__ void __launch_bounds__(256)
+circle_nms_kernel(const float* __restrict__ boxes, int nb, const float* __restrict__ scores, const int* __restrict__ labels,
+                  unsigned char* __restrict__ keep_io, int P, unsigned class_mask, float thresh, int post_max) {
+  __shared__ float sk[NMS_MAX];        // sort key: score (descending)
+  __shared__ int si[NMS_MAX];          // proposal index, -1 = padding
+  __shared__ unsigned char sup[NMS_MAX];
+  __shared__ int kept;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float* bx = boxes + (size_t)b * P * nb;
+  for (int i = tid; i < NMS_MAX; i += 256) {
+    bool cand = i < P && keep_io[(size_t)b * P + i] && ((class_mask >> labels[(size_t)b * P + i]) & 1u);
+    sk[i] = cand ? scores[(size_t)b * P + i] : -INFINITY;
+    si[i] = cand ? i : -1;
+    sup[i] = 0;
+  }
+  if (tid == 0) kept = 0;
+  __syncthreads();
+  // bitonic sort, descending score, ascending index among equal scores, padding last
+  for (int k = 2; k <= NMS_MAX; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < NMS_MAX; i += 256) {
+        const int l = i ^ j;
+        if (l > i) {
+          const bool up = (i & k) == 0;
+          const bool a_first = (si[i] >= 0) && (si[l] < 0 || sk[i] > sk[l] || (sk[i] == sk[l] && si[i] < si[l]));
+          if (up ? !a_first : a_first) {
+            const float tk = sk[i]; sk[i] = sk[l]; sk[l] = tk;
+            const int ti = si[i]; si[i] = si[l]; si[l] = ti;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  for (int a = 0; a < NMS_MAX; ++a) {
+    const int ia = si[a];
+    if (ia < 0) break;                                   // uniform: shared value
+    if (!sup[a]) {
+      const bool over = kept >= post_max;
+      __syncthreads();
+      if (over) {
+        if (tid == 0) sup[a] = 1;                        // beyond post_max_size: dropped
+      } else {
+        if (tid == 0) ++kept;
+        const float xa = bx[(size_t)ia * nb], ya = bx[(size_t)ia * nb + 1];
+        for (int c = a + 1 + tid; c < NMS_MAX; c += 256) {
+          const int ic = si[c];
+          if (ic >= 0 && !sup[c]) {
+            const float dx = xa - bx[(size_t)ic * nb], dy = ya - bx[(size_t)ic * nb + 1];
+            if (dx * dx + dy * dy <= thresh) sup[c] = 1;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  for (int a = tid; a < NMS_MAX; a += 256)
+    if (si[a] >= 0 && sup[a]) keep_io[(size_t)b * P + si[a]] = 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -895,6 +1032,48 @@ int di_nhwc_to_nchw_f32(const float* in, float* out, int N, int C, int HW, cudaS
   dim3 grid(di_cdiv(HW, 32), di_cdiv(C, 32), N), block(32, 8);
   nhwc_to_nchw_kernel<<<grid, block, 0, stream>>>(in, out, C, HW);
   DI_CHECK_LAUNCH("di_nhwc_to_nchw_f32");
+  return DI_OK;
+}
+
+// TransFusionBBoxCoder.decode (+ the score composition of get_bboxes when qscore/qlabel are given).  All inputs
+// contiguous [B, k, P]; range6 = post_center_range or NULL; boxes [B,P,7|9] (9 iff vel), scores [B,P], labels [B,P]
+// (int32), keep [B,P] (uint8: centre inside range and score > thr when use_thr).
+int di_bbox_decode_f32(const float* heat, const float* qscore, const int* qlabel, const float* rot, const float* dim,
+                       const float* center, const float* height, const float* vel, int B, int K, int P, float sx, float sy,
+                       float ox, float oy, const float* range6, float score_thr, int use_thr, float* boxes, float* scores,
+                       int* labels, unsigned char* keep, cudaStream_t stream) {
+  DI_CHECK_ARG(heat && rot && dim && center && height && boxes && scores && labels && keep && B > 0 && K > 0 && P > 0,
+               "di_bbox_decode_f32: bad argument");
+  DI_CHECK_ARG((qscore == nullptr) == (qlabel == nullptr), "di_bbox_decode_f32: qscore and qlabel go together");
+  CoderParams cp{};
+  cp.sx = sx; cp.sy = sy; cp.ox = ox; cp.oy = oy; cp.use_range = range6 != nullptr; cp.use_thr = use_thr; cp.thr = score_thr;
+  if (range6) memcpy(cp.rng, range6, sizeof(cp.rng));               // host pointer
+  bbox_decode_kernel<<<di_cdiv((long long)B * P, 128), 128, 0, stream>>>(heat, qscore, qlabel, rot, dim, center, height, vel,
+                                                                        B, K, P, cp, boxes, scores, labels, keep);
+  DI_CHECK_LAUNCH("di_bbox_decode_f32");
+  return DI_OK;
+}
+
+// TransFusionBBoxCoder.encode: boxes [n, nb = 7|9] -> targets [n, code = 8|10]
+int di_bbox_encode_f32(const float* boxes, int nb, float* targets, int code, int n, float sx, float sy, float ox, float oy,
+                       cudaStream_t stream) {
+  DI_CHECK_ARG(boxes && targets && n > 0 && (nb == 7 || nb == 9) && (code == 8 || code == 10) && (code != 10 || nb == 9),
+               "di_bbox_encode_f32: bad argument");
+  CoderParams cp{};
+  cp.sx = sx; cp.sy = sy; cp.ox = ox; cp.oy = oy;
+  bbox_encode_kernel<<<di_cdiv(n, 128), 128, 0, stream>>>(boxes, nb, targets, code, n, cp);
+  DI_CHECK_LAUNCH("di_bbox_encode_f32");
+  return DI_OK;
+}
+
+// Circle NMS of one task over B samples (get_bboxes, nms_type == 'circle'): classes in class_mask, squared-distance
+// threshold `thresh`, at most post_max survivors; keep_io [B,P] is updated in place.  P <= 1024.
+int di_circle_nms_f32(const float* boxes, int nb, const float* scores, const int* labels, unsigned char* keep_io, int B,
+                      int P, unsigned class_mask, float thresh, int post_max, cudaStream_t stream) {
+  DI_CHECK_ARG(boxes && scores && labels && keep_io && B > 0 && P > 0 && P <= NMS_MAX && nb >= 2,
+               "di_circle_nms_f32: bad argument (P must be <= 1024)");
+  circle_nms_kernel<<<B, 256, 0, stream>>>(boxes, nb, scores, labels, keep_io, P, class_mask, thresh, post_max);
+  DI_CHECK_LAUNCH("di_circle_nms_f32");
   return DI_OK;
 }
 

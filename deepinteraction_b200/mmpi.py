@@ -19,6 +19,8 @@ B200-first differences from the reference schedule (results unchanged, fp32):
 import copy
 
 import numpy as np
+import os
+
 import torch
 import torch.nn as nn
 
@@ -110,16 +112,51 @@ class PointRCNNBlock(nn.Module):
 
 
 class TransFusionBBoxCoder:
-    """Box parametrisation constants (core/bbox/coders/transfusion_bbox_coder.py:9-22); decoding itself
-    happens inside di_rcnn_rois_f32."""
+    """Drop-in for core/bbox/coders/transfusion_bbox_coder.py:8-126: same constructor, ``decode`` and ``encode``
+    (CUDA tensors; kernels di_bbox_decode_f32 / di_bbox_encode_f32).  Unlike the reference, ``decode`` does not
+    write into its ``center`` / ``dim`` arguments.  Inside the forward the RCNN blocks decode in di_rcnn_rois_f32."""
 
     def __init__(self, pc_range, out_size_factor, voxel_size, post_center_range=None, score_threshold=None,
                  code_size=8, **unused):
         self.pc_range, self.out_size_factor, self.voxel_size = pc_range, out_size_factor, voxel_size
         self.post_center_range, self.score_threshold, self.code_size = post_center_range, score_threshold, code_size
 
+    def _scale(self):
+        return (self.out_size_factor * self.voxel_size[0], self.out_size_factor * self.voxel_size[1],
+                self.pc_range[0], self.pc_range[1])
+
+    def encode(self, dst_boxes):
+        return ops.bbox_encode(dst_boxes, self.code_size, *self._scale())
+
+    def _decode_all(self, heatmap, rot, dim, center, height, vel, filter, qscore=None, qlabel=None):
+        if filter and self.post_center_range is None:
+            raise NotImplementedError('Need to reorganize output as a batch, only support post_center_range is not None for now!')
+        rng = None if not filter else [float(v) for v in (self.post_center_range.tolist() if torch.is_tensor(
+            self.post_center_range) else self.post_center_range)]
+        return ops.bbox_decode(heatmap, rot, dim, center, height, vel, *self._scale(), post_range=rng,
+                               score_thr=self.score_threshold if filter else None, qscore=qscore, qlabel=qlabel)
+
+    def decode(self, heatmap, rot, dim, center, height, vel, filter=False):
+        boxes, scores, labels, keep = self._decode_all(heatmap, rot, dim, center, height, vel, filter)
+        labels = labels.long()
+        if not filter:
+            return [dict(bboxes=boxes[i], scores=scores[i], labels=labels[i]) for i in range(boxes.shape[0])]
+        return [dict(bboxes=boxes[i, keep[i]], scores=scores[i, keep[i]], labels=labels[i, keep[i]])
+                for i in range(boxes.shape[0])]
+
+
+NMS_TASKS = {   # deepinteraction_decoder.py:575-586: (class indices, radius)
+    'nuScenes': [((0, 1, 2, 3, 4, 5, 6, 7), -1.0), ((8,), 0.175), ((9,), 0.175)],
+    'Waymo': [((0,), 0.7), ((1,), 0.7), ((2,), 0.7)],
+}
+
 
 HEAD_ORDER = ('center', 'height', 'dim', 'rot', 'vel', 'heatmap')
+
+
+# The DynamicConv parameter generator streams a 32768 x 128 weight per MMPI layer; its output only feeds the
+# (LayerNorm-ed) dynamic convolution, no index or softmax decision, so it may run the cheaper bf16 split.
+_DYN_BF16 = os.environ.get('DI_B200_DYN_BF16', '0') != '0'
 
 
 class DeepInteractionDecoder(nn.Module):
@@ -384,7 +421,9 @@ class DeepInteractionDecoder(nn.Module):
             qkv = ops.linear([prev], w, b)
             a = ops.mha_small(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], B, P, H, onbits, win)
             q1 = ops.rows_finish(ops.linear([a], wo, bo), res=prev, gamma=bp['norm1'][0], beta=bp['norm1'][1])
+            ops.TC_BF16[0] = _DYN_BF16                       # parameter generator (M=P, N=32768): see _DYN_BF16
             params = ops.linear([q1], *bp['dyn'])
+            ops.TC_BF16[0] = False
             flat = ops.dynconv(roi, params, *bp['dn1'], *bp['dn2'])
             part = ops.linear([flat], bp['dout'][0], splits=49)
             t = ops.rows_finish(part, bias=bp['dout'][1], gamma=bp['dn3'][0], beta=bp['dn3'][1], act=ops.ACT_RELU)
@@ -428,6 +467,33 @@ class DeepInteractionDecoder(nn.Module):
             else:
                 merged[key] = torch.cat([r_[key] for r_ in rets], -1)
         return [[merged]]
+
+    def get_bboxes(self, preds_dicts, img_metas, img=None, rescale=False, for_roi=False):
+        """deepinteraction_decoder.py:549-638 on the forward's output: last-layer score composition + box decode +
+        range/score filter in one kernel, optional per-task circle NMS (nms_type 'circle'), one boolean compaction at
+        the end (the only host synchronisation: the result length is data dependent).  Batch size 1 and a single
+        layer, as the reference asserts (:631-632).  -> [[boxes, scores, labels.int()]]."""
+        assert len(preds_dicts) == 1, 'get_bboxes expects the single merged layer the forward returns'
+        p0, P = preds_dicts[0][0], self.num_proposals
+        assert p0['heatmap'].shape[0] == 1, 'the reference get_bboxes supports batch size 1 (:632)'
+        last = lambda k: p0[k][..., -P:]
+        coder = self.bbox_coder
+        boxes, scores, labels, keep = coder._decode_all(last('heatmap'), last('rot'), last('dim'), last('center'),
+                                                        last('height'), last('vel') if 'vel' in p0 else None, True,
+                                                        qscore=p0['query_heatmap_score'], qlabel=self.query_labels)
+        nms = self.test_cfg['nms_type']
+        if nms is not None:
+            if nms != 'circle':
+                raise NotImplementedError("nms_type %r: only None and 'circle' are provided (rotated NMS is mmdet3d's nms_gpu)" % nms)
+            for classes, radius in NMS_TASKS[self.test_cfg['dataset']]:
+                if radius > 0:
+                    keep = ops.circle_nms(boxes, scores, labels, keep, sum(1 << c for c in classes), radius)
+        k = keep[0]
+        boxes, scores, labels = boxes[0, k], scores[0, k], labels[0, k]
+        wrap = img_metas[0].get('box_type_3d') if isinstance(img_metas[0], dict) else None
+        if wrap is not None:
+            boxes = wrap(boxes, box_dim=boxes.shape[-1])
+        return [[boxes, scores, labels.int()]]
 
     def forward(self, pts_inputs, img_inputs, img_metas):
         """pts_inputs: [pts_feat_conv, new_pts_feat] (B,C,Y,X); img_inputs (B*V,C,h,w).  NCHW tensors that are

@@ -371,3 +371,45 @@ def nhwc_to_nchw(x):
     out = torch.empty(N, C, H, W, device=x.device, dtype=torch.float32)
     _call('di_nhwc_to_nchw_f32', _ptr(_f32(x)), _ptr(out), N, C, H * W, _stream())
     return out
+
+
+def bbox_decode(heat, rot, dim, center, height, vel, sx, sy, ox, oy, post_range=None, score_thr=None, qscore=None,
+                qlabel=None):
+    """TransFusionBBoxCoder.decode on [B,k,P] tensors -> boxes [B,P,7|9], scores [B,P], labels [B,P] int32,
+    keep [B,P] bool (range + score filter).  With qscore/qlabel the get_bboxes score composition is applied first."""
+    B, K, P = heat.shape
+    heat, rot, dim, center, height = (t.contiguous() for t in (heat, rot, dim, center, height))
+    vel = None if vel is None else vel.contiguous()
+    qscore = None if qscore is None else qscore.contiguous()
+    qlabel = None if qlabel is None else qlabel.to(torch.int32).contiguous()
+    dev = heat.device
+    boxes = torch.empty(B, P, 9 if vel is not None else 7, device=dev, dtype=torch.float32)
+    scores = torch.empty(B, P, device=dev, dtype=torch.float32)
+    labels = torch.empty(B, P, device=dev, dtype=torch.int32)
+    keep = torch.empty(B, P, device=dev, dtype=torch.uint8)
+    rng = None if post_range is None else (ctypes.c_float * 6)(*[float(v) for v in post_range])
+    use_thr = bool(score_thr)                       # the reference tests `if self.score_threshold:` (coder :110)
+    _call('di_bbox_decode_f32', _ptr(heat), _ptr(qscore), _ptr(qlabel), _ptr(rot), _ptr(dim), _ptr(center), _ptr(height),
+          _ptr(vel), B, K, P, float(sx), float(sy), float(ox), float(oy), rng, float(score_thr or 0.0), int(use_thr),
+          _ptr(boxes), _ptr(scores), _ptr(labels), _ptr(keep), _stream())
+    return boxes, scores, labels, keep.bool()
+
+
+def bbox_encode(boxes, code_size, sx, sy, ox, oy):
+    boxes = boxes.contiguous()
+    _f32(boxes)
+    n, nb = boxes.shape
+    out = torch.empty(n, code_size, device=boxes.device, dtype=torch.float32)
+    if n:
+        _call('di_bbox_encode_f32', _ptr(boxes), nb, _ptr(out), code_size, n, float(sx), float(sy), float(ox), float(oy),
+              _stream())
+    return out
+
+
+def circle_nms(boxes, scores, labels, keep, class_mask, thresh, post_max=83):
+    """In-place per-task circle NMS on keep [B,P] (bool)."""
+    B, P, nb = boxes.shape
+    k8 = keep.to(torch.uint8).contiguous()
+    _call('di_circle_nms_f32', _ptr(boxes), nb, _ptr(scores), _ptr(labels), _ptr(k8), B, P, int(class_mask), float(thresh),
+          int(post_max), _stream())
+    return k8.bool()

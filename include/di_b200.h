@@ -182,6 +182,25 @@ int di_dynconv_f32(const float* roi, const float* params, const float* g1, const
 int di_nchw_to_nhwc_f32(const float* in, float* out, int N, int C, int HW, cudaStream_t stream);
 int di_nhwc_to_nchw_f32(const float* in, float* out, int N, int C, int HW, cudaStream_t stream);
 
+/* ---- box coder and get_bboxes post-processing (decoder.cu) ------------------------------------- */
+
+/* TransFusionBBoxCoder.decode (core/bbox/coders/transfusion_bbox_coder.py:40-126): class = first arg-max of the
+ * score over K, box = (x, y, z_bottom, dx, dy, dz, yaw[, vx, vy]); keep = centre inside range6 (host pointer to
+ * post_center_range, or NULL) and, when use_thr, score > score_thr.  With qscore/qlabel the score is composed as in
+ * DeepInteractionDecoder.get_bboxes (models/dense_heads/deepinteraction_decoder.py:561-563):
+ * sigmoid(heat) * query_heatmap_score * one_hot(query_label).  Inputs contiguous [B,k,P]. */
+int di_bbox_decode_f32(const float* heat, const float* qscore, const int* qlabel, const float* rot, const float* dim,
+                       const float* center, const float* height, const float* vel, int B, int K, int P, float sx, float sy,
+                       float ox, float oy, const float* range6, float score_thr, int use_thr, float* boxes, float* scores,
+                       int* labels, unsigned char* keep, cudaStream_t stream);
+/* TransFusionBBoxCoder.encode (transfusion_bbox_coder.py:24-38): boxes [n,7|9] -> targets [n,8|10]. */
+int di_bbox_encode_f32(const float* boxes, int nb, float* targets, int code, int n, float sx, float sy, float ox, float oy,
+                       cudaStream_t stream);
+/* Per-task circle NMS of get_bboxes (deepinteraction_decoder.py:594-625; mmdet3d circle_nms semantics: greedy in
+ * descending score, squared centre distance <= thresh suppresses, at most post_max kept).  keep_io [B,P] in place. */
+int di_circle_nms_f32(const float* boxes, int nb, const float* scores, const int* labels, unsigned char* keep_io, int B,
+                      int P, unsigned class_mask, float thresh, int post_max, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

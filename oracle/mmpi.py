@@ -156,6 +156,65 @@ class TransFusionBBoxCoder:
         parts = [cx, cy, height, dim, yaw] + ([vel] if vel is not None else [])
         return torch.cat(parts, 1).permute(0, 2, 1)
 
+    def encode(self, dst_boxes):
+        """transfusion_bbox_coder.py:24-38: (n, 7|9) boxes (x, y, z_bottom, dx, dy, dz, yaw[, vx, vy]) -> (n, code_size)."""
+        t = torch.zeros(dst_boxes.shape[0], self.code_size)
+        t[:, 0] = (dst_boxes[:, 0] - self.pc_range[0]) / (self.out_size_factor * self.voxel_size[0])
+        t[:, 1] = (dst_boxes[:, 1] - self.pc_range[1]) / (self.out_size_factor * self.voxel_size[1])
+        t[:, 3:6] = dst_boxes[:, 3:6].log()
+        t[:, 2] = dst_boxes[:, 2] + dst_boxes[:, 5] * 0.5
+        t[:, 6], t[:, 7] = torch.sin(dst_boxes[:, 6]), torch.cos(dst_boxes[:, 6])
+        if self.code_size == 10:
+            t[:, 8:10] = dst_boxes[:, 7:]
+        return t
+
+    def decode(self, heatmap, rot, dim, center, height, vel, filter=False):
+        """transfusion_bbox_coder.py:40-126 (without the reference's in-place writes into `center` / `dim`).
+        -> list over samples of dict(bboxes (n, 7|9), scores (n,), labels (n,) int64); filter=True keeps
+        score > score_threshold (when it is truthy, :110) and centres inside post_center_range (:101-105)."""
+        scores, labels = heatmap.max(1)
+        boxes = self.decode_boxes(rot, dim, center, height, vel)
+        if not filter:
+            return [dict(bboxes=boxes[i], scores=scores[i], labels=labels[i]) for i in range(heatmap.shape[0])]
+        if self.post_center_range is None:
+            raise NotImplementedError('Need to reorganize output as a batch, only support post_center_range is not None for now!')
+        rng = torch.tensor(self.post_center_range, dtype=boxes.dtype)
+        mask = (boxes[..., :3] >= rng[:3]).all(2) & (boxes[..., :3] <= rng[3:]).all(2)
+        out = []
+        for i in range(heatmap.shape[0]):
+            m = mask[i]
+            if self.score_threshold:
+                m = m & (scores[i] > self.score_threshold)
+            out.append(dict(bboxes=boxes[i, m], scores=scores[i, m], labels=labels[i, m]))
+        return out
+
+
+def circle_nms(dets, thresh, post_max_size=83):
+    """mmdet3d v0.17.1 mmdet3d/core/post_processing/box3d_nms.py::circle_nms (third party, NOT in the reference
+    tree: parity unpinned).  dets (n, 3) = x, y, score; `thresh` is compared with the SQUARED centre distance;
+    returns the kept indices in descending score order, at most post_max_size."""
+    x, y, sc = dets[:, 0], dets[:, 1], dets[:, 2]
+    order = np.argsort(-sc, kind='stable')
+    suppressed = np.zeros(len(sc), bool)
+    keep = []
+    for a in range(len(order)):
+        i = order[a]
+        if suppressed[i]:
+            continue
+        keep.append(int(i))
+        for b in range(a + 1, len(order)):
+            j = order[b]
+            if not suppressed[j] and (x[i] - x[j]) ** 2 + (y[i] - y[j]) ** 2 <= thresh:
+                suppressed[j] = True
+    return keep[:post_max_size]
+
+
+NMS_TASKS = {   # deepinteraction_decoder.py:575-586
+    'nuScenes': [dict(indices=[0, 1, 2, 3, 4, 5, 6, 7], radius=-1), dict(indices=[8], radius=0.175),
+                 dict(indices=[9], radius=0.175)],
+    'Waymo': [dict(indices=[0], radius=0.7), dict(indices=[1], radius=0.7), dict(indices=[2], radius=0.7)],
+}
+
 
 class DynamicConv(nn.Module):
     """decoder_utils.py:584-629."""
@@ -415,3 +474,41 @@ class DeepInteractionDecoder(nn.Module):
                     merged[key] = torch.cat([r[key] for r in rets], -1)
             out = [[merged]]
         return (out, aux) if return_aux else out
+
+    def get_bboxes(self, preds_dicts, img_metas, img=None, rescale=False, for_roi=False):
+        """deepinteraction_decoder.py:549-638: last-layer scores = sigmoid(heatmap) * query_heatmap_score * one-hot
+        of the query label, decode(filter=True), optional per-task circle NMS; one layer, batch size 1 (:631-632).
+        -> [[boxes, scores, labels.int()]] (boxes wrapped by img_metas[0]['box_type_3d'] when that key exists)."""
+        rets = []
+        for preds in preds_dicts:
+            p0, P = preds[0], self.num_proposals
+            score = p0['heatmap'][..., -P:].sigmoid()
+            one_hot = F.one_hot(self.query_labels, num_classes=self.num_classes).permute(0, 2, 1)
+            score = score * p0['query_heatmap_score'] * one_hot
+            vel = p0['vel'][..., -P:] if 'vel' in p0 else None
+            temp = self.bbox_coder.decode(score, p0['rot'][..., -P:], p0['dim'][..., -P:], p0['center'][..., -P:],
+                                          p0['height'][..., -P:], vel, filter=True)
+            layer = []
+            for t in temp:
+                boxes, scores, labels = t['bboxes'], t['scores'], t['labels']
+                if self.test_cfg['nms_type'] is not None:
+                    if self.test_cfg['nms_type'] != 'circle':
+                        raise NotImplementedError('only nms_type None / circle are restated (rotated NMS = mmdet3d nms_gpu)')
+                    keep = torch.zeros_like(scores, dtype=torch.bool)
+                    for task in NMS_TASKS[self.test_cfg['dataset']]:
+                        tm = torch.zeros_like(keep)
+                        for c in task['indices']:
+                            tm |= labels == c
+                        idx = torch.where(tm)[0]
+                        if task['radius'] > 0:
+                            dets = torch.cat([boxes[tm][:, :2], scores[tm][:, None]], 1).detach().numpy()
+                            idx = idx[torch.tensor(circle_nms(dets, task['radius']), dtype=torch.long)]
+                        keep[idx] = True
+                    boxes, scores, labels = boxes[keep], scores[keep], labels[keep]
+                layer.append(dict(bboxes=boxes, scores=scores, labels=labels))
+            rets.append(layer)
+        assert len(rets) == 1 and len(rets[0]) == 1
+        r = rets[0][0]
+        wrap = img_metas[0].get('box_type_3d') if isinstance(img_metas[0], dict) else None
+        boxes = wrap(r['bboxes'], box_dim=r['bboxes'].shape[-1]) if wrap is not None else r['bboxes']
+        return [[boxes, r['scores'], r['labels'].int()]]

@@ -28,6 +28,8 @@ def kind(arg):
         return 'll'
     if re.match(r'(const\s+)?float\b', arg):
         return 'float'
+    if re.match(r'(const\s+)?unsigned\b', arg):
+        return 'uint'
     assert re.match(r'(const\s+)?int\b', arg), arg
     return 'int'
 
@@ -35,7 +37,7 @@ def kind(arg):
 def ctype_kind(t):
     if t in (ctypes.c_void_p,) or (isinstance(t, type) and issubclass(t, ctypes._Pointer)):
         return 'ptr'
-    return {ctypes.c_int: 'int', ctypes.c_longlong: 'll', ctypes.c_float: 'float'}[t]
+    return {ctypes.c_int: 'int', ctypes.c_uint: 'uint', ctypes.c_longlong: 'll', ctypes.c_float: 'float'}[t]
 
 
 def test_library_is_built_and_exports_header():

@@ -247,3 +247,54 @@ def test_decoder_base_shape_matches_oracle():
     for a, b in zip(m.on_the_image_mask, o.on_the_image_mask):
         assert torch.equal(a.cpu(), b)
     _compare(out, ref, TOL)
+
+
+def test_get_bboxes_and_coder_match_reference_golden():
+    """get_bboxes (decoder.py:549-638) and TransFusionBBoxCoder.decode/encode on the GPU vs the reference golden."""
+    from tools.make_goldens import small_frame
+    gold = torch.load(os.path.join(G, 'decoder_bboxes.pt'), weights_only=False)
+    o, m = _build(gold['seed'], 2, 24)
+    m.bbox_coder.score_threshold = gold['score_threshold']
+    preds = {k: v.to(dev()) for k, v in gold['preds'].items()}
+    m.query_labels = gold['query_labels'].to(dev())
+    boxes, scores, labels = m.get_bboxes([[preds]], [dict()])[0]
+    assert boxes.shape == gold['boxes'].shape and labels.dtype == torch.int32
+    assert torch.equal(labels.cpu(), gold['labels'])
+    assert rel_err(boxes.cpu(), gold['boxes']) < TIGHT and rel_err(scores.cpu(), gold['scores']) < TIGHT
+    assert rel_err(m.bbox_coder.encode(gold['boxes'].to(dev())).cpu(), gold['encoded']) < TIGHT
+    # end to end: forward on the GPU then get_bboxes == the reference's boxes for the same inputs
+    gen = torch.Generator().manual_seed(gold['seed'])
+    fr = small_frame(gold['seed'], aug=False, views=2, batch=1)
+    pts_in = [torch.randn(1, 128, 36, 36, generator=gen), torch.randn(1, 128, 36, 36, generator=gen)]
+    img_in = torch.randn(2, 128, 28, 50, generator=gen)
+    out = m([p.to(dev()) for p in pts_in], img_in.to(dev()), fr['img_metas'])
+    b2, s2, l2 = m.get_bboxes(out, fr['img_metas'])[0]
+    assert torch.equal(l2.cpu(), gold['labels']) and rel_err(b2.cpu(), gold['boxes']) < TOL
+    # box_type_3d wrapper and the unfiltered decode
+    class Boxes:
+        def __init__(self, t, box_dim=9):
+            self.tensor, self.box_dim = t, box_dim
+    b3 = m.get_bboxes(out, [dict(box_type_3d=Boxes)])[0][0]
+    assert isinstance(b3, Boxes) and b3.box_dim == 9 and torch.equal(b3.tensor, b2)
+    full = m.bbox_coder.decode(*(preds[k][..., -24:] for k in ('heatmap', 'rot', 'dim', 'center', 'height', 'vel')))
+    ref = o.bbox_coder.decode(*(gold['preds'][k][..., -24:] for k in ('heatmap', 'rot', 'dim', 'center', 'height', 'vel')))
+    assert torch.equal(full[0]['labels'].cpu(), ref[0]['labels']) and rel_err(full[0]['bboxes'].cpu(), ref[0]['bboxes']) < TIGHT
+
+
+def test_get_bboxes_circle_nms_matches_oracle():
+    """nms_type='circle' (per-task greedy circle NMS) vs the oracle restatement, crowded random proposals."""
+    import oracle.mmpi as om
+    from tools import make_goldens as mg
+    P = 300
+    o, m = _build(5, 2, P, test_cfg=dict(mg.DEC_TEST_CFG, nms_type='circle'))
+    g = torch.Generator().manual_seed(3)
+    preds = dict(center=torch.rand(1, 2, P, generator=g) * 6 + 15, height=torch.randn(1, 1, P, generator=g),
+                 dim=torch.randn(1, 3, P, generator=g) * 0.2, rot=torch.randn(1, 2, P, generator=g),
+                 vel=torch.randn(1, 2, P, generator=g), heatmap=torch.randn(1, 10, P, generator=g),
+                 query_heatmap_score=torch.rand(1, 10, P, generator=g))
+    labels = torch.randint(6, 10, (1, P), generator=g)               # classes 8 and 9 have radius 0.175
+    o.query_labels, m.query_labels = labels, labels.to(dev())
+    rb, rs, rl = o.get_bboxes([[preds]], [dict()])[0]
+    b, s_, l = m.get_bboxes([[{k: v.to(dev()) for k, v in preds.items()}]], [dict()])[0]
+    assert 0 < rb.shape[0] < P and b.shape == rb.shape
+    assert torch.equal(l.cpu(), rl) and rel_err(b.cpu(), rb) < TIGHT and rel_err(s_.cpu(), rs) < TIGHT

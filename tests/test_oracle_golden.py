@@ -2,6 +2,8 @@
 files (tools/make_goldens.py, stub-loaded in the build container)."""
 import os
 
+import numpy as np
+
 import pytest
 import torch
 
@@ -119,3 +121,31 @@ def test_roi_align_matches_torchvision():
         a = roi_align(feat, boxes, 7, scale, 2)
         b = tvo.roi_align(feat[None], [boxes], 7, scale, 2, aligned=True)
         assert torch.allclose(a, b, atol=1e-5)
+
+
+def test_oracle_get_bboxes_and_coder_match_reference_golden():
+    """A16 + get_bboxes: oracle restatement vs the stub-loaded reference (decoder.py:549-638,
+    transfusion_bbox_coder.py:24-126), golden made by tools/make_goldens.py (G6)."""
+    import oracle.mmpi as om
+    from tools.make_goldens import make_decoder
+    gold = torch.load(os.path.join(G, 'decoder_bboxes.pt'), weights_only=False)
+    torch.manual_seed(gold['seed'])
+    m = make_decoder(om.DeepInteractionDecoder).eval()
+    m.bbox_coder.score_threshold = gold['score_threshold']
+    m.query_labels = gold['query_labels']
+    boxes, scores, labels = m.get_bboxes([[gold['preds']]], [dict()])[0]
+    assert boxes.shape == gold['boxes'].shape and 0 < boxes.shape[0] < m.num_proposals      # the filter did filter
+    assert torch.equal(labels, gold['labels'])
+    assert rel_err(boxes, gold['boxes']) < 1e-6 and rel_err(scores, gold['scores']) < 1e-6
+    assert rel_err(m.bbox_coder.encode(gold['boxes']), gold['encoded']) < 1e-6
+    # encode(decode(x)) returns the regression targets (sin/cos normalised)
+    full = m.bbox_coder.decode(torch.rand(1, 10, 24), *(gold['preds'][k][..., -24:] for k in ('rot', 'dim', 'center', 'height', 'vel')))
+    enc = m.bbox_coder.encode(full[0]['bboxes'])
+    assert rel_err(enc[:, :2], gold['preds']['center'][0, :, -24:].t()) < 1e-5
+
+
+def test_oracle_circle_nms_semantics():
+    import oracle.mmpi as om
+    dets = np.array([[0, 0, .9], [.1, 0, .8], [1, 0, .7], [1, .05, .95], [5, 5, .1]], np.float32)
+    assert om.circle_nms(dets, 0.05) == [3, 0, 4]            # 2 suppressed by 3, 1 by 0 (squared distance <= thresh)
+    assert om.circle_nms(dets, 0.05, post_max_size=2) == [3, 0]

@@ -18,6 +18,7 @@ Usage:  python tools/make_goldens.py [--ref /root/reference] [--out tests/golden
 import argparse
 import hashlib
 import importlib.util
+import copy
 import os
 import sys
 import types
@@ -310,6 +311,35 @@ def main():
               'on-image', [int(m.sum()) for m in rm.on_the_image_mask])
         save(tag, dict(seed=seed, aug=aug, checksum=state_checksum(om.state_dict()), out=r,
                        query_labels=rm.query_labels, on_the_image_mask=rm.on_the_image_mask))
+    # --- G6: get_bboxes + bbox coder (A16): batch 1 (the reference asserts it, :631-632), nms_type None ---
+    class Boxes:                                    # stands in for img_metas['box_type_3d'] (mmdet3d LiDARInstance3DBoxes)
+        def __init__(self, tensor, box_dim=9):
+            self.tensor, self.box_dim = tensor, box_dim
+    seed = 1610
+    torch.manual_seed(seed)
+    om = make_decoder(ommpi.DeepInteractionDecoder).eval()
+    synth.randomize_norm_stats(om, seed)
+    rm = make_decoder(dec.DeepInteractionDecoder).eval()
+    rm.load_state_dict(om.state_dict(), strict=True)
+    rm.bbox_coder.score_threshold = om.bbox_coder.score_threshold = 0.27       # filters about half of the proposals
+    g = torch.Generator().manual_seed(seed)
+    fr = small_frame(seed, aug=False, views=2, batch=1)
+    pts_in = [torch.randn(1, 128, 36, 36, generator=g), torch.randn(1, 128, 36, 36, generator=g)]
+    img_in = torch.randn(2, 128, 28, 50, generator=g)
+    metas = [dict(m, box_type_3d=Boxes) for m in fr['img_metas']]
+    r_out = rm(pts_in, img_in, metas)
+    o_out = om(pts_in, img_in, metas)
+    preds = copy.deepcopy(r_out)                                      # the reference decode() writes into its inputs
+    rb = rm.get_bboxes(copy.deepcopy(r_out), metas)
+    ob = om.get_bboxes(o_out, metas)
+    print('get_bboxes kept', tuple(rb[0][0].tensor.shape), 'oracle vs reference', cmp(ob[0][0].tensor, rb[0][0].tensor),
+          cmp(ob[0][1], rb[0][1]), 'labels equal', bool((ob[0][2] == rb[0][2]).all()))
+    enc_r = rm.bbox_coder.encode(rb[0][0].tensor)
+    enc_o = om.bbox_coder.encode(ob[0][0].tensor)
+    print('encode oracle vs reference', cmp(enc_o, enc_r))
+    save('decoder_bboxes', dict(seed=seed, checksum=state_checksum(om.state_dict()), preds=preds[0][0],
+                                query_labels=rm.query_labels, boxes=rb[0][0].tensor, scores=rb[0][1], labels=rb[0][2],
+                                encoded=enc_r, score_threshold=0.27))
     print('\n'.join(report))
 
 
