@@ -242,6 +242,7 @@ def main():
     ap.add_argument('--cloud', default='lidar', choices=['lidar', 'dense'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--profile-steps', type=int, default=3)
+    ap.add_argument('--inflight', type=int, default=3, help='independent frames in flight per GPU (CUDA streams)')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -265,8 +266,13 @@ def main():
     fr_dev = h2d(fr_host, device)
     torch.cuda.synchronize()
     W, K = max(args.warmup, 3), args.steps
+    from deepinteraction_b200.pipeline import FramePipeline
+    pipe = FramePipeline(neck, head, depth=max(args.inflight, 1), device=device)
+    out = forward(neck, head, fr_dev)                   # one plain call (default stream), then per-stream graph capture
+    pipe.warm(fr_dev, rounds=3)
     for _ in range(W):
-        out = forward(neck, head, fr_dev)
+        out = pipe.submit(fr_dev)[0]
+    pipe.join()
     torch.cuda.synchronize()
 
     def barrier():
@@ -288,60 +294,62 @@ def main():
         l0 = ops.LAUNCHES[0]
         e0.record()
         for _ in range(K):
-            out = forward(neck, head, fr_dev)
+            out = pipe.submit(fr_dev)[0]
+        pipe.join()
         e1.record()
         barrier()
         launches = ops.LAUNCHES[0] - l0
         ms = max_over_ranks(e0.elapsed_time(e1))
         # ---- timed region 2: end to end through the plug-in API, host buffers ------------------------------
-        # Two device input sets; the host->device copy of step i+1 runs on a copy stream while step i computes.
-        outs_host = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items()}
+        # NSETS device input sets; the host->device copy of a later step runs on a copy stream while earlier steps
+        # compute on the pipeline's streams; every step's result goes back to pinned host memory on its own stream.
+        NSETS = pipe.depth + 1
+        outs_host = [{k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items()} for _ in range(pipe.depth)]
         copy_stream = torch.cuda.Stream()
-        main_stream = torch.cuda.current_stream()
 
         def flat(fr):
             pm = fr['pts_metas']
             return [fr['img_feats'], fr['pts_feats'], pm['pillars'], pm['pillar_coors'], pm['pillars_num_points']] + \
                 list(pm['pts'])
-        sets = [h2d(fr_host, device), h2d(fr_host, device)]
+        sets = [h2d(fr_host, device) for _ in range(NSETS)]
         torch.cuda.synchronize()
-        done = [torch.cuda.Event(), torch.cuda.Event()]
-        ready = [torch.cuda.Event(), torch.cuda.Event()]
-        used = [False, False]
+        done = [None] * NSETS
+        ready = [torch.cuda.Event() for _ in range(NSETS)]
 
         def issue_copy(i):
-            bi = i % 2
+            bi = i % NSETS
             with torch.cuda.stream(copy_stream):
-                if used[bi]:
+                if done[bi] is not None:
                     copy_stream.wait_event(done[bi])          # the forward that read this set has finished
                 for dst, src in zip(flat(sets[bi]), flat(fr_host)):
                     dst.copy_(src, non_blocking=True)
                 ready[bi].record(copy_stream)
 
-        for i in range(2):                                       # warm the copy path
-            issue_copy(i)
-            main_stream.wait_event(ready[i % 2])
-            o = forward(neck, head, sets[i % 2])
-            done[i % 2].record(main_stream)
-            used[i % 2] = True
+        def step(i):
+            bi = i % NSETS
+            o, ev, s = pipe.submit(sets[bi], wait_event=ready[bi], stream_index=i % pipe.depth)
+            done[bi] = ev
+            with torch.cuda.stream(s):
+                for k_, v in o.items():
+                    outs_host[i % pipe.depth][k_].copy_(v, non_blocking=True)
+
+        for r in range(3):                                       # every (input set, stream) pair owns its graphs
+            for i in range(NSETS * pipe.depth):
+                issue_copy(i)
+                step(i)
+        pipe.join()
         barrier()
         e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        host_t0 = time.perf_counter()
         e2.record()
         issue_copy(0)
         host_fwd = 0.0
         for i in range(K):
-            bi = i % 2
             if i + 1 < K:
                 issue_copy(i + 1)
-            main_stream.wait_event(ready[bi])
             t_h = time.perf_counter()
-            o = forward(neck, head, sets[bi])
+            step(i)
             host_fwd += time.perf_counter() - t_h
-            done[bi].record(main_stream)
-            used[bi] = True
-            for k_, v in o.items():
-                outs_host[k_].copy_(v, non_blocking=True)
+        pipe.join()
         e3.record()
         barrier()
         ms_e2e = max_over_ranks(e2.elapsed_time(e3))
@@ -445,12 +453,13 @@ def main():
                 higher_is_better=True, scaling='weak', vs_baseline=None, dtype='fp32', data='synthetic',
                 config=dict(workload=WORKLOAD, global_batch=args.batch * world, cloud=args.cloud,
                             parallelism=f'dp{world} (independent frames, no data-path collective)',
+                            frames_in_flight=pipe.depth,
                             l2='inputs (204 MB/frame) larger than L2; no flush'),
                 clocks=clocks,
                 e2e=dict(value=e2e_value, unit='frames/s', h2d_bytes_per_step=h2d_bytes(fr_host),
                          d2h_bytes_per_step=int(sum(v.numel() * v.element_size() for v in out.values())),
                          ms_per_step=ms_e2e / K, host_launch_ms_per_step=host_fwd / K * 1e3,
-                         overlap='H2D of step i+1 on a copy stream (double-buffered device inputs) while step i computes'),
+                         overlap='H2D of step i+1 on a copy stream (depth+1 device input sets) while earlier steps compute'),
                 gpu_launches=launches, launches_per_step=launches / K, stages=stages, cuda_graph=bool(di_graph.ENABLED[0] and os.environ.get('DI_B200_GRAPH', '1') != '0'),
                 roofline=roof, cpu_baseline=cpu,
                 kernels=kernels[:12])

@@ -28,6 +28,7 @@ SIGNATURES = {
     'di_conv3x3_tcb_f32': [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     'di_tc_set_debug': [_i],
     'di_tc_set_mode': [_i],
+    'di_tc_set_sm_limit': [_i],
     'di_tc_debug_read': [ctypes.POINTER(ctypes.c_longlong)],
     # lcab.cu
     'di_lcab_window_f32': [_p, _i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _p],

@@ -778,6 +778,7 @@ int* g_sched_ptr = nullptr;
 unsigned g_sched_seq = 0;
 int g_tc_debug = 0;
 int g_tc_wres = 1;    // keep the weight slice resident in shared memory when K <= 128
+int g_tc_sm_limit = 0; // > 0: persistent grids use at most this many CTAs (leaves SMs to kernels of other streams)
 
 template <bool WRES, bool BF>
 void launch_v3(dim3 grid, const CUtensorMap maps[6], const TcParams& p, cudaStream_t stream) {
@@ -809,12 +810,13 @@ int launch_tc(const CUtensorMap maps[6], const TcParams& p_in, int bf, cudaStrea
   }
   p.sched = g_sched_ptr + 16 * (g_sched_seq++ % SCHED_SLOTS);
   const int tiles = p.m_tiles * p.n_tiles;
+  const int sms = (g_tc_sm_limit > 0 && g_tc_sm_limit < g_num_sms) ? g_tc_sm_limit : g_num_sms;
   int nk = p.k0 + p.k1 + p.k2;
   const bool wres = !p.conv && nk <= (bf ? 2 : 4) && g_tc_wres && p.n_tiles <= 14;
-  int g = tiles < g_num_sms ? tiles : g_num_sms;
+  int g = tiles < sms ? tiles : sms;
   if (wres) {
     // every CTA keeps one column tile's weights resident: the grid must be a multiple of n_tiles
-    if (tiles >= g_num_sms) g = (g_num_sms / p.n_tiles) * p.n_tiles;
+    if (tiles >= sms) g = (sms / p.n_tiles) * p.n_tiles;
     if (g < p.n_tiles) g = p.n_tiles;
   }
   if (wres && bf) launch_v3<true, true>(dim3(g), maps, p, stream);
@@ -928,6 +930,13 @@ int di_tc_set_debug(int on) {
 int di_tc_set_mode(int mode) {
   DI_CHECK_ARG(mode == 3 || mode == 4, "di_tc_set_mode: mode must be 3 or 4");
   g_tc_wres = mode != 4;
+  return DI_OK;
+}
+// Persistent tensor-core grids use at most n CTAs (0 = all SMs): with several frames in flight the other streams'
+// small kernels then always find a free SM.  The dynamic tile scheduler makes any grid size correct.
+int di_tc_set_sm_limit(int n) {
+  DI_CHECK_ARG(n >= 0, "di_tc_set_sm_limit: n must be >= 0");
+  g_tc_sm_limit = n;
   return DI_OK;
 }
 int di_tc_debug_read(long long* host_buf) {

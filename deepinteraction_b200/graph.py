@@ -7,7 +7,13 @@ copies the small camera constants and calls cudaGraphLaunch.
 
 Policy: a signature is captured the SECOND time it is seen (frames with ever-changing pillar counts therefore stay
 on the eager path and never pay capture cost); at most `max_entries` graphs are kept (LRU).  Outputs are static
-buffers owned by the graph: they are overwritten by the next replay of the same signature.
+buffers owned by the graph: they are overwritten by the next replay of the same graph.
+
+A graph is bound to (signature, CUDA stream, input buffer addresses): the captured kernels read the caller's input
+tensors in place (no staging copy of the 200 MB of feature maps), and frames submitted on different streams
+(pipeline.FramePipeline) get their own graph and output buffers, so independent frames can be in flight together.
+A caller that passes fresh tensors every frame simply stays on the eager path; one that cycles through a few input
+sets (double / triple buffering) gets one graph per set.
 """
 import collections
 import os
@@ -20,7 +26,7 @@ ENABLED = [os.environ.get('DI_B200_GRAPH', '1') != '0']
 
 
 class GraphCache:
-    def __init__(self, max_entries=4):
+    def __init__(self, max_entries=16):
         self.entries = collections.OrderedDict()
         self.seen = collections.OrderedDict()
         self.max_entries = max_entries
@@ -32,6 +38,7 @@ class GraphCache:
     def run(self, sig, inputs, host_consts, fn):
         """inputs: list of device tensors; host_consts: list of small CPU tensors; fn(inputs, consts) -> pytree of
         tensors.  Returns fn's result (eager) or the graph's static outputs (replay)."""
+        sig = (sig, torch.cuda.current_stream().cuda_stream, tuple(t.data_ptr() for t in inputs))
         ent = self.entries.get(sig)
         if ent is None:
             n = self.seen.get(sig, 0) + 1
@@ -45,20 +52,22 @@ class GraphCache:
         else:
             self.entries.move_to_end(sig)
         g, s_in, s_c, pinned, out, launches, flip = ent
-        for dst, src in zip(s_in, inputs):
-            if dst.data_ptr() != src.data_ptr():
-                dst.copy_(src, non_blocking=True)
         k = flip[0] = flip[0] ^ 1
+        if flip[1 + k] is not None:
+            flip[1 + k].synchronize()          # the H2D copy that last read this pinned set has run (host may be ahead)
         for dst, pin, c in zip(s_c, pinned[k], host_consts):
             pin.copy_(c)
             dst.copy_(pin, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        flip[1 + k] = ev
         g.replay()
         ops.LAUNCHES[0] += launches
         return out
 
     def _capture(self, sig, inputs, host_consts, fn):
         dev = inputs[0].device
-        s_in = [t.clone() for t in inputs]
+        s_in = list(inputs)                    # bound to the caller's buffers (kept alive by the entry)
         s_c = [torch.empty(c.shape, dtype=c.dtype, device=dev) for c in host_consts]
         pinned = [[torch.empty(c.shape, dtype=c.dtype).pin_memory() for c in host_consts] for _ in range(2)]
         for dst, c in zip(s_c, host_consts):
@@ -75,7 +84,7 @@ class GraphCache:
         with torch.cuda.graph(g):
             out = fn(s_in, s_c)
         launches = ops.LAUNCHES[0] - n0
-        ent = (g, s_in, s_c, pinned, out, launches, [0])
+        ent = (g, s_in, s_c, pinned, out, launches, [0, None, None])
         self.entries[sig] = ent
         while len(self.entries) > self.max_entries:
             self.entries.popitem(last=False)

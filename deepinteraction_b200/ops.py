@@ -118,6 +118,9 @@ def _linear_tc(srcs, W, bias, act, out, res, res_mod, M, N, K):
     return out
 
 
+if os.environ.get('DI_B200_TC_SMS'):
+    _lib.check(_lib.lib().di_tc_set_sm_limit(int(os.environ['DI_B200_TC_SMS'])), 'di_tc_set_sm_limit')
+
 PRESPLIT = [os.environ.get('DI_B200_PRESPLIT', '1') != '0']   # q/k/v projections emit bf16 (hi, mid) words for the window kernel
 
 

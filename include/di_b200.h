@@ -86,6 +86,7 @@ int di_conv3x3_tcb_f32(const float* x, const void* w_hi, const void* w_mid, cons
 /* diagnostics: clock64 pipeline trace of CTA 0 of the next tensor-core launch (8 x 512 stamps) */
 int di_tc_set_debug(int on);
 int di_tc_set_mode(int mode); /* 3 = weights resident in shared memory when K <= 128 (default), 4 = always streamed */
+int di_tc_set_sm_limit(int n); /* persistent tensor-core grids use at most n CTAs (0 = one per SM) */
 int di_tc_debug_read(long long* host_buf);
 
 /* ---- local-window attention (lcab.cu) ---------------------------------------------------------- */

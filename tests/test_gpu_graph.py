@@ -1,5 +1,6 @@
 """GPU: the CUDA-graph replay of the encoder / decoder schedules returns exactly what the eager launches return,
-including after the per-frame constants (camera rows) and the inputs change between replays."""
+including after the per-frame constants (camera rows) change and after the bound input buffers are refilled in place;
+frames in flight on several streams (pipeline.FramePipeline) give the single-stream results."""
 import copy
 
 import pytest
@@ -58,7 +59,14 @@ def test_encoder_graph_replay_equals_eager():
             out = _run_enc(enc, fr)
             for x, y in zip(out, ref):
                 assert torch.equal(x, y), (i, tag, float((x - y).abs().max()))
-        assert len(enc._graphs.entries) == 1
+        assert len(enc._graphs.entries) == 2              # one graph per set of input buffers
+        # graphs read the caller's buffers in place: refill frame a's tensors with frame b's data and replay
+        for k in ('img_feats', 'pts_feats'):
+            fa[k].copy_(fb[k])
+        fa['img_metas'] = fb['img_metas']
+        out = _run_enc(enc, fa)
+        for x, y in zip(out, ref_b):
+            assert torch.equal(x, y)
     finally:
         graph.ENABLED[0] = old
 
@@ -105,6 +113,47 @@ def test_decoder_graph_replay_equals_eager():
             assert out.keys() == ref.keys()
             for k in ref:
                 assert torch.equal(out[k], ref[k]), (i, k)
-        assert len(dec._graphs.entries) == 1
+        assert len(dec._graphs.entries) == 2
+    finally:
+        graph.ENABLED[0] = old
+
+
+def test_frames_in_flight_equal_single_stream():
+    """Two streams, alternating frames: every result equals the single-stream eager result of that frame."""
+    from deepinteraction_b200 import graph, mmpi, synth
+    from deepinteraction_b200.pipeline import FramePipeline
+    from test_gpu_decoder import _build
+    from tools.make_goldens import small_frame
+    import oracle.mmri as om
+    torch.manual_seed(2)
+    o = om.DeepInteractionEncoder(2, 16, 24, 128).eval()
+    synth.randomize_norm_stats(o, 2)
+    from deepinteraction_b200 import mmri
+    enc = mmri.DeepInteractionEncoder(2, 16, 24, 128)
+    enc.load_state_dict(o.state_dict(), strict=True)
+    enc = enc.to(dev()).eval()
+    _, dec = _build(43, 2, 24)
+    frames = [synth.to_device(small_frame(90 + i, aug=False, views=2, c_img=16, c_pts=24, bev=36, batch=1), dev())
+              for i in range(2)]
+    old = graph.ENABLED[0]
+    try:
+        graph.ENABLED[0] = False
+        refs = []
+        for fr in frames:
+            img, pts = enc(fr['img_feats'], fr['pts_feats'], fr['img_metas'], fr['pts_metas'])
+            refs.append({k: v.clone() for k, v in dec(pts, img, fr['img_metas'])[0][0].items()})
+        graph.ENABLED[0] = True
+        pipe = FramePipeline(enc, dec, depth=2, device=dev())
+        for rnd in range(5):
+            got = []
+            for i, fr in enumerate(frames):
+                out, ev, s = pipe.submit(fr, stream_index=i)
+                with torch.cuda.stream(s):
+                    got.append({k: v.clone() for k, v in out.items()})
+            pipe.join()
+            torch.cuda.synchronize()
+            for g_, r in zip(got, refs):
+                for k in r:
+                    assert torch.equal(g_[k], r[k]), (rnd, k)
     finally:
         graph.ENABLED[0] = old
