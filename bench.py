@@ -136,6 +136,11 @@ def h2d_bytes(fr):
     return int(sum(t.numel() * t.element_size() for t in ts))
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the launches of one forward, from the ncu
+# --set full captures summarised under profiles/ (r1_ncu_window_pre.md: 4 image launches 256.6 MB, 2 BEV 51.2 MB).
+NCU_TRAFFIC = {'di_lcab_window_pre_f32': (4 * 256.57e6 + 2 * 51.23e6) / 6}
+
+
 def forward(neck, head, fr):
     img, pts = neck(fr['img_feats'], fr['pts_feats'], fr['img_metas'], fr['pts_metas'])
     return head(pts, img, fr['img_metas'])[0][0]
@@ -424,7 +429,7 @@ def main():
         roof = dict(bound='tensor', achieved=top['tflops'], peak=pk['tf'], unit='TFLOP/s', frac=top['tflops'] / pk['tf'])
     else:
         roof = dict(bound='hbm', achieved=top['gbs'], peak=pk['hbm'], unit='GB/s', frac=top['gbs'] / pk['hbm'])
-    roof.update(kernel=top['name'], traffic=None, peak_source=pk['src'], share_of_step=top['share'],
+    roof.update(kernel=top['name'], traffic=NCU_TRAFFIC.get(top['name']), peak_source=pk['src'], share_of_step=top['share'],
                 avg_launch_us=top['avg_us'])
 
     cpu = None
