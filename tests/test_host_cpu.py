@@ -176,3 +176,20 @@ def test_two_rank_gloo_sharding_is_bitwise_equal_to_single_rank():
     mp.spawn(_gloo_worker, args=(2, port, ret), nprocs=2, join=True)
     assert ret[0][0] and ret[1][0], 'sharded frames must equal the single-process result bit for bit'
     assert ret[0][1] == 11.0 and ret[1][1] == 11.0
+
+
+def test_presplit_operand_format_roundtrip():
+    """fold.split_rows = host model of the window kernel's pre-split operand format (gemm_tc.cu split_block)."""
+    from deepinteraction_b200 import fold
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(37, 64, generator=g) * torch.logspace(-3, 3, 64)
+    for kind in (1, 2):
+        w = fold.split_rows(x, kind).view(torch.int32)
+        if kind == 1:
+            wh, wm = w[:, 0::2], w[:, 1::2]
+        else:
+            v = w.view(37, 8, 8)
+            wh, wm = v[:, :, :4].reshape(37, 32), v[:, :, 4:].reshape(37, 32)
+        unpack = lambda t: torch.stack([(t << 16), (t & -65536)], -1).view(torch.float32).reshape(37, 64)
+        rec = unpack(wh) + unpack(wm)
+        assert float(((rec - x).abs() / x.abs()).max()) <= 2.0 ** -16
