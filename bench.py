@@ -459,6 +459,9 @@ def main():
                 config=dict(workload=WORKLOAD, global_batch=args.batch * world, cloud=args.cloud,
                             parallelism=f'dp{world} (independent frames, no data-path collective)',
                             frames_in_flight=pipe.depth,
+                            arithmetic='fp32 in/out and accumulate; dense products as error-compensated splits on tcgen05 '
+                                       '(bf16 hi+mid x3 in the encoder, 3xTF32 in the decoder), mma.sync bf16 split in the '
+                                       'window attention; measured vs the fp32 oracle: see cpu_baseline.max_rel_err_vs_gpu',
                             l2='inputs (204 MB/frame) larger than L2; no flush'),
                 clocks=clocks,
                 e2e=dict(value=e2e_value, unit='frames/s', h2d_bytes_per_step=h2d_bytes(fr_host),
