@@ -224,6 +224,8 @@ def i2p_attend(qk, pillars, npts, coors, proj, img_nhwc, V, in_hw):
 def depth_scatter(pts, proj_b, keys_b, in_hw):
     """pts (n, >=3) row-major; proj_b (V,12); keys_b (V,h,w) int64 view of zeroed uint64 keys."""
     V, h, w = keys_b.shape
+    if pts.shape[0] == 0:                 # a sample without lidar points: its depth maps stay empty
+        return
     assert pts.stride(1) == 1
     _call('di_depth_scatter', _ptr(pts), pts.stride(0), pts.shape[0], _ptr(proj_b), _ptr(keys_b), V, h, w, in_hw[0],
           in_hw[1], _stream())

@@ -276,6 +276,11 @@ def test_get_bboxes_and_coder_match_reference_golden():
             self.tensor, self.box_dim = t, box_dim
     b3 = m.get_bboxes(out, [dict(box_type_3d=Boxes)])[0][0]
     assert isinstance(b3, Boxes) and b3.box_dim == 9 and torch.equal(b3.tensor, b2)
+    m.bbox_coder.score_threshold = 0.999                                  # nothing survives: empty, well-typed result
+    b0, s0, l0 = m.get_bboxes(out, fr['img_metas'])[0]
+    assert b0.shape == (0, 9) and s0.shape == (0,) and l0.shape == (0,) and l0.dtype == torch.int32
+    assert m.bbox_coder.encode(b0).shape == (0, 10)
+    m.bbox_coder.score_threshold = gold['score_threshold']
     full = m.bbox_coder.decode(*(preds[k][..., -24:] for k in ('heatmap', 'rot', 'dim', 'center', 'height', 'vel')))
     ref = o.bbox_coder.decode(*(gold['preds'][k][..., -24:] for k in ('heatmap', 'rot', 'dim', 'center', 'height', 'vel')))
     assert torch.equal(full[0]['labels'].cpu(), ref[0]['labels']) and rel_err(full[0]['bboxes'].cpu(), ref[0]['bboxes']) < TIGHT

@@ -316,3 +316,63 @@ def test_encoder_refuses_training_mode_and_cpu():
     enc = enc.to(dev()).train()
     with pytest.raises(NotImplementedError):
         enc.forward_nhwc(torch.zeros(1, 8, 8, 8, device=dev()), torch.zeros(1, 8, 8, 8, device=dev()), [], {})
+
+
+def _edge_models(seed=5):
+    from deepinteraction_b200 import mmri, synth
+    import oracle.mmri as om
+    torch.manual_seed(seed)
+    m = om.DeepInteractionEncoder(1, 16, 24, 32).eval()
+    synth.randomize_norm_stats(m, seed)
+    enc = mmri.DeepInteractionEncoder(1, 16, 24, 32)
+    enc.load_state_dict(m.state_dict(), strict=True)
+    return m, enc.to(dev()).eval()
+
+
+@pytest.mark.parametrize('case', ['empty_cloud', 'three_points', 'no_valid_keys', 'max_points_per_pillar'])
+def test_encoder_edge_inputs_match_oracle(case):
+    """Degenerate geometry the reference tolerates: a sample without lidar points (all-zero depth maps -> nothing
+    lifted), a 3-point cloud, pillars whose points project into no camera (0 valid keys -> zero row, eu.py:314-316),
+    pillars filled to the 20-point cap."""
+    from deepinteraction_b200 import synth
+    from tools.make_goldens import small_frame
+    m, enc = _edge_models()
+    fr = small_frame(21, aug=False, views=2, c_img=16, c_pts=24, bev=36, batch=2)
+    pm = dict(fr['pts_metas'])
+    if case == 'empty_cloud':
+        pm['pts'] = [pm['pts'][0], pm['pts'][1][:0]]
+    elif case == 'three_points':
+        pm['pts'] = [pm['pts'][0], pm['pts'][1][:3]]
+    elif case == 'no_valid_keys':
+        pil = pm['pillars'].clone()
+        pil[pm['pillar_coors'][:, 0] == 1, :, 2] = -500.0
+        pm['pillars'] = pil
+    else:
+        pm['pillars_num_points'] = torch.full_like(pm['pillars_num_points'], 20)
+        pm['pillars'] = pm['pillars'] + (pm['pillars'] == 0) * pm['pillars'][:, :1]      # padded slots become real points
+    with torch.no_grad():
+        r_img, (r_p0, r_p1) = m(fr['img_feats'], fr['pts_feats'], fr['img_metas'], pm)
+    frd = synth.to_device(dict(fr, pts_metas=pm), dev())
+    img, (p0, p1) = enc(frd['img_feats'], frd['pts_feats'], frd['img_metas'], frd['pts_metas'])
+    e = (rel_err(img.cpu(), r_img), rel_err(p0.cpu(), r_p0), rel_err(p1.cpu(), r_p1))
+    print(case, 'rel err img %.2e pts_conv %.2e pts %.2e' % e)
+    assert max(e) < TOL
+
+
+def test_encoder_without_pillars_is_defined():
+    """No pillars at all: the reference crashes on the empty reshape (eu.py:313); this path defines the I2P term as
+    zero, i.e. the result equals the one obtained from pillars that see no camera."""
+    from deepinteraction_b200 import synth
+    from tools.make_goldens import small_frame
+    m, enc = _edge_models()
+    fr = small_frame(21, aug=False, views=2, c_img=16, c_pts=24, bev=36, batch=2)
+    pm = dict(fr['pts_metas'])
+    blind = pm['pillars'].clone()
+    blind[:, :, 2] = -500.0
+    with torch.no_grad():
+        r_img, (r_p0, r_p1) = m(fr['img_feats'], fr['pts_feats'], fr['img_metas'], dict(pm, pillars=blind))
+    pm0 = dict(pm, pillars=pm['pillars'][:0], pillar_coors=pm['pillar_coors'][:0],
+               pillars_num_points=pm['pillars_num_points'][:0])
+    frd = synth.to_device(dict(fr, pts_metas=pm0), dev())
+    img, (p0, p1) = enc(frd['img_feats'], frd['pts_feats'], frd['img_metas'], frd['pts_metas'])
+    assert rel_err(img.cpu(), r_img) < TOL and rel_err(p1.cpu(), r_p1) < TOL
