@@ -345,11 +345,13 @@ cross_attn_kernel(const float* __restrict__ q, const float* __restrict__ kv, flo
           }
           s[u] = (kk + u < nk) ? a : -INFINITY;
         }
-        float mn = fmaxf(fmaxf(m, fmaxf(s[0], s[1])), fmaxf(s[2], s[3]));
-        float corr = expf(m - mn);
-        l *= corr;
+        const float mn = fmaxf(fmaxf(m, fmaxf(s[0], s[1])), fmaxf(s[2], s[3]));
+        if (mn > m) {                              // the running maximum rarely moves after the first keys
+          const float corr = expf(m - mn);
+          l *= corr;
 #pragma unroll
-        for (int d = 0; d < D; ++d) acc[d] *= corr;
+          for (int d = 0; d < D; ++d) acc[d] *= corr;
+        }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           float p = expf(s[u] - mn);
@@ -365,11 +367,12 @@ cross_attn_kernel(const float* __restrict__ q, const float* __restrict__ kv, flo
     }
   }
   if (active) {
-    float* o = part + ((((size_t)b * Hh + head) * P + qi) * nsplit + split) * (D + 2);
+    // partials as [b, head, split, field, q]: the threads of a warp (consecutive q) write / read consecutive floats
+    float* o = part + ((((size_t)b * Hh + head) * nsplit + split) * (D + 2)) * P + qi;
     o[0] = m;
-    o[1] = l;
+    o[P] = l;
 #pragma unroll
-    for (int d = 0; d < D; ++d) o[2 + d] = acc[d];
+    for (int d = 0; d < D; ++d) o[(size_t)(2 + d) * P] = acc[d];
   }
 }
 
@@ -379,17 +382,18 @@ __global__ void cross_attn_combine_kernel(const float* __restrict__ part, float*
   int i = blockIdx.x * blockDim.x + threadIdx.x;  // (b, head, q)
   if (i >= B * Hh * P) return;
   int qi = i % P, head = (i / P) % Hh, b = i / (P * Hh);
-  const float* pp = part + (size_t)i * nsplit * (D + 2);
+  const float* pp = part + (size_t)(b * Hh + head) * nsplit * (D + 2) * P + qi;   // [split][field][q]
+  const size_t ss = (size_t)(D + 2) * P;
   float M = -INFINITY;
-  for (int s = 0; s < nsplit; ++s) M = fmaxf(M, pp[s * (D + 2)]);
+  for (int s = 0; s < nsplit; ++s) M = fmaxf(M, pp[s * ss]);
   float L = 0.f, acc[D];
 #pragma unroll
   for (int d = 0; d < D; ++d) acc[d] = 0.f;
   for (int s = 0; s < nsplit; ++s) {
-    float w = expf(pp[s * (D + 2)] - M);
-    L += w * pp[s * (D + 2) + 1];
+    float w = expf(pp[s * ss] - M);
+    L += w * pp[s * ss + P];
 #pragma unroll
-    for (int d = 0; d < D; ++d) acc[d] += w * pp[s * (D + 2) + 2 + d];
+    for (int d = 0; d < D; ++d) acc[d] += w * pp[s * ss + (size_t)(2 + d) * P];
   }
   float inv = 1.f / L;
   float* o = out + (size_t)(b * P + qi) * C + head * D;
