@@ -196,18 +196,20 @@ static_assert(V3_SMEM_BYTES <= 232448, "v3 exceeds the 227 KB shared-memory limi
 // kind::f16, bf16 x bf16 -> fp32, A and B K-major, M = 128, N = 128
 constexpr uint32_t IDESC_BF16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 
-__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t accumulate) {
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc,
+                                             uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(
           tmem_d),
-      "r"(tmem_a), "l"(db), "r"(IDESC), "r"(accumulate)
+      "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t accumulate) {
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc,
+                                             uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(
           tmem_d),
-      "r"(tmem_a), "l"(db), "r"(IDESC_BF16), "r"(accumulate)
+      "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // two fp32 -> packed bf16x2 (round to nearest even): low half = lo_elem, high half = hi_elem
@@ -464,8 +466,13 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     // lanes, ~45 cycles per instruction: the issue thread, not the tensor pipe, then sets the pace.)
     int it = 0;
     for (int tl = 0;; ++tl) {
-      if (take_tile(tl) < 0) break;
+      const int tile = take_tile(tl);
+      if (tile < 0) break;
       if (WRES && tl == 0) mbar_wait(w_full, 0);
+      // MMA width = the valid columns of this tile rounded up to 16: a 10-class heat-map conv issues N = 16
+      // instructions (8 cycles) instead of N = 128 (64 cycles) and reads 1/8 of the weight tile
+      const int ncols = min(TN, p.N - (tile % p.n_tiles) * TN);
+      const uint32_t idesc = ((BF ? IDESC_BF16 : IDESC) & ~(0x3Fu << 17)) | ((uint32_t)(((ncols + 15) & ~15) >> 3) << 17);
       const int a = tl % NACC;
       if (tl >= NACC) mbar_wait(acc_empty(a), ((tl / NACC) - 1) & 1);
       const uint32_t tmem_acc = tmem_base + (uint32_t)(a * TN);
@@ -483,13 +490,13 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           for (int k = 0; k < 4; ++k) {               // 4 k-steps of 32 operand bytes: 8 tf32 or 16 bf16 each
             const uint64_t w_hi = umma_desc(whi_base + k * 32), w_lo = umma_desc(wlo_base + k * 32);
             if (BF) {
-              umma_bf16_ts(tmem_acc, ta + 32u + (uint32_t)(k * 8), w_hi, (kc_all | k) != 0);  // A_mid * W_hi
-              umma_bf16_ts(tmem_acc, ta + (uint32_t)(k * 8), w_lo, 1);                         // A_hi * W_mid
-              umma_bf16_ts(tmem_acc, ta + (uint32_t)(k * 8), w_hi, 1);                         // A_hi * W_hi
+              umma_bf16_ts(tmem_acc, ta + 32u + (uint32_t)(k * 8), w_hi, idesc, (kc_all | k) != 0);  // A_mid * W_hi
+              umma_bf16_ts(tmem_acc, ta + (uint32_t)(k * 8), w_lo, idesc, 1);                         // A_hi * W_mid
+              umma_bf16_ts(tmem_acc, ta + (uint32_t)(k * 8), w_hi, idesc, 1);                         // A_hi * W_hi
             } else {
-              umma_tf32_ts(tmem_acc + CROSS_COL, ta + 32u + (uint32_t)(k * 8), w_hi, (kc_all | k) != 0);  // A_lo * W_hi
-              umma_tf32_ts(tmem_acc + CROSS_COL, ta + (uint32_t)(k * 8), w_lo, 1);                         // A_hi * W_lo
-              umma_tf32_ts(tmem_acc, ta + (uint32_t)(k * 8), w_hi, (kc_all | k) != 0);                     // A_hi * W_hi
+              umma_tf32_ts(tmem_acc + CROSS_COL, ta + 32u + (uint32_t)(k * 8), w_hi, idesc, (kc_all | k) != 0);  // A_lo * W_hi
+              umma_tf32_ts(tmem_acc + CROSS_COL, ta + (uint32_t)(k * 8), w_lo, idesc, 1);                         // A_hi * W_lo
+              umma_tf32_ts(tmem_acc, ta + (uint32_t)(k * 8), w_hi, idesc, (kc_all | k) != 0);                     // A_hi * W_hi
             }
           }
           // one commit per chunk: a_free(b) releases the TMEM A buffer to the splitter AND (streamed weights,
