@@ -26,6 +26,8 @@ SIGNATURES = {
     'di_linear_tcb_split_f32': [_p, _i, _i, _p, _i, _i, _p, _i, _i, _p, _p, _p, _p, _i, _i, _p, _i, _i, _i, _i, _i, _i, _p],
     'di_conv3x3_tc_f32': [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     'di_conv3x3_tcb_f32': [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
+    'di_conv3x3_tc_nchw_f32': [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
+    'di_conv3x3_tcb_nchw_f32': [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     'di_tc_set_debug': [_i],
     'di_tc_set_mode': [_i],
     'di_tc_set_sm_limit': [_i],

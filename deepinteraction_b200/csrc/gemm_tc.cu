@@ -167,6 +167,7 @@ struct TcParams {
   int dbg;
   int* sched;               // v3: 16 ints of the dynamic tile scheduler (column-group counters [0..13], done [15])
   int split_col0, split_kind;  // output columns >= split_col0 are emitted as bf16 (hi, mid) words (0 = off), see below
+  int a_nchw;               // conv: the input map is NCHW (kernel variant ANCHW)
 };
 __host__ __device__ __forceinline__ int tc_kch(const TcParams& p, int s) { return s == 0 ? p.k0 : (s == 1 ? p.k1 : p.k2); }
 
@@ -267,7 +268,13 @@ __device__ __forceinline__ void split_block(float (&v)[32], int kind) {
 // WRES: the whole [128, K<=128] weight slice (hi + lo, <= 128 KB) of this CTA's column tile stays resident in
 // shared memory; only A streams.  The SM<->L2 port (~28 B/clk/SM, shared by loads and stores) is what bounds the
 // K=128 layers: per 128x128 tile it moves 64 KB (A) + 64 KB (C) instead of 192 KB + 64 KB.
-template <bool WRES, bool BF>
+// ANCHW (convolution only): the input map is NCHW.  A TMA box must start on a 16-byte boundary in the innermost
+// dimension, so single-pixel tap shifts along x cannot be expressed as box coordinates of a channel-major map (probed:
+// tools/tma_nchw_probe.cu).  Instead ONE box [KE channels][8 rows][24 pixels] starting at x0 - 4 is loaded per (tap
+// row, channel chunk) into a 2-deep ring and serves the three taps of that row: the splitter reads column k of pixel
+// (y, x + 3 + dx) -- conflict-light LDS.32, lanes = pixels -- so no transposition pass is needed and the A traffic per
+// tap halves.  Weights stream through their own ring (one 32 KB hi|lo stage per tap and channel chunk).
+template <bool WRES, bool BF, bool ANCHW>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                   const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapWhi,
@@ -278,11 +285,13 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
   constexpr int KE = BF ? 64 : 32;                                // k-values per chunk
   constexpr int AL = TM * KE * 4;                                 // fp32 A landing bytes per chunk (BF: two 16 KB boxes)
+  static_assert(!(ANCHW && WRES), "the NCHW conv variant streams its weights");
+  constexpr int AB = 24 * 8 * KE * 4;                             // ANCHW: bytes of one [KE][8][24] A box
   constexpr int S = (BF && !WRES) ? 3 : 4;                        // pipeline stages
-  constexpr int STG = WRES ? AL : AL + 2 * A_BYTES;               // bytes per stage: A landing [| W_hi | W_lo]
+  constexpr int STG = ANCHW ? 2 * A_BYTES : (WRES ? AL : AL + 2 * A_BYTES);   // stage: [A landing |] W_hi | W_lo
   constexpr int NKW = BF ? 2 : 4;                                 // resident chunks (K <= 128)
   constexpr int WRES_BYTES = WRES ? 2 * NKW * A_BYTES : 0;        // resident W: hi chunks | lo chunks
-  constexpr int RING_OFF = WRES_BYTES;                            // stage ring starts after the resident weights
+  constexpr int RING_OFF = ANCHW ? 2 * AB : WRES_BYTES;           // stage ring starts after the resident weights / A ring
   static_assert(RING_OFF + S * STG <= 192 * 1024, "operand ring exceeds its 192 KB");
   constexpr int EP_OFF = RING_OFF + S * STG;
   const uint32_t ep_base = base + EP_OFF;
@@ -306,7 +315,9 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   const uint32_t w_full = bars + 8u * (2 * S + 2 * NA + 5);
   auto tq_full = [&](int i) { return bars + 8u * (2 * S + 2 * NA + 6 + i); };
   auto tq_empty = [&](int i) { return bars + 8u * (2 * S + 2 * NA + 6 + V3_TQ + i); };
-  static_assert(8 * (2 * S + 2 * NA + 6 + 2 * V3_TQ) <= V3_BAR_BYTES, "barrier block overflow");
+  auto a2_full = [&](int i) { return bars + 8u * (2 * S + 2 * NA + 6 + 2 * V3_TQ + i); };       // ANCHW A-box ring
+  auto a2_empty = [&](int i) { return bars + 8u * (2 * S + 2 * NA + 6 + 2 * V3_TQ + 2 + i); };
+  static_assert(8 * (2 * S + 2 * NA + 6 + 2 * V3_TQ + 4) <= V3_BAR_BYTES, "barrier block overflow");
   volatile int* tq = reinterpret_cast<volatile int*>(base_ptr + EP_OFF + EP_BYTES + V3_BAR_BYTES + 512);
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(base_ptr + EP_OFF + EP_BYTES + 8 * (2 * S + 2 * NA + 4));
@@ -341,6 +352,10 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     for (int i = 0; i < V3_TQ; ++i) {
       mbar_init(tq_full(i), 1);
       mbar_init(tq_empty(i), 9);                     // MMA warp + 4 splitter warps + 4 epilogue warps
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(a2_full(i), 1);
+      mbar_init(a2_empty(i), 4);                     // the four splitter warps
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -384,7 +399,7 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   if (warp == 0) {
     // ---------------- TMA producer ----------------
     if (lane == 0) {
-      int it = 0;
+      int it = 0, t3 = 0;
       const int group = WRES ? (int)(blockIdx.x % p.n_tiles) : 0;
       int published = 0;
       bool exhausted = false;
@@ -420,6 +435,25 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         if (tile < 0) break;
         int m0, n0, img, y0, x0;
         tile_coords(tile, m0, n0, img, y0, x0);
+        if (ANCHW) {
+          for (int dy = 0; dy < 3; ++dy)
+            for (int kc = 0; kc < p.k0; ++kc, ++t3) {
+              const int ab = t3 & 1;
+              if (t3 >= 2) mbar_wait(a2_empty(ab), ((t3 >> 1) - 1) & 1);
+              mbar_expect_tx(a2_full(ab), AB);
+              tma_load_4d(base + ab * AB, &mapA0, a2_full(ab), x0 - 4, y0 + dy - 1, kc * KE, img);
+              for (int dx = 0; dx < 3; ++dx, ++it) {
+                const int s = it % S;
+                if (it >= S) mbar_wait(a_free(s), ((it / S) - 1) & 1);
+                DBG_STAMP(0, it);
+                const uint32_t st = base + RING_OFF + s * STG;
+                const int kw = ((dy * 3 + dx) * p.k0 + kc) * KE;
+                mbar_expect_tx(full(s), STG);
+                tma_load_2d(st, &mapWhi, full(s), kw, n0);
+                tma_load_2d(st + A_BYTES, &mapWlo, full(s), kw, n0);
+              }
+            }
+        } else
         for (int kc_all = 0; kc_all < nk; ++kc_all, ++it) {
           const int s = it % S;
           if (it >= S) mbar_wait(WRES ? empty(s) : a_free(s), ((it / S) - 1) & 1);
@@ -479,10 +513,11 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       for (int kc_all = 0; kc_all < nk; ++kc_all, ++it) {
         const int s = it % S, b = it % NA;
         mbar_wait(a_ready(b), (it / NA) & 1);       // A_hi/A_lo of this chunk are in TMEM (implies full[s])
+        if (ANCHW) mbar_wait(full(s), (it / S) & 1);    // ... except here: the weights land on their own barrier
         tc_fence_after();
         const uint32_t st = base + RING_OFF + s * STG;
-        const uint32_t whi_base = WRES ? base + kc_all * A_BYTES : st + AL;
-        const uint32_t wlo_base = WRES ? base + (NKW + kc_all) * A_BYTES : st + AL + A_BYTES;
+        const uint32_t whi_base = ANCHW ? st : (WRES ? base + kc_all * A_BYTES : st + AL);
+        const uint32_t wlo_base = ANCHW ? st + A_BYTES : (WRES ? base + (NKW + kc_all) * A_BYTES : st + AL + A_BYTES);
         const uint32_t ta = tmem_base + 256u + (uint32_t)(b * 64);
         if (elect_one()) {
           DBG_STAMP(3, it);
@@ -517,10 +552,37 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       if (take_tile(tl) < 0) break;
       for (int kc_all = 0; kc_all < nk; ++kc_all, ++it) {
         const int s = it % S, b = it % NA;
+        uint32_t hi[32], lo[32];
+        if (ANCHW) {
+          const int t3 = it / 3, dx = it - 3 * t3, ab = t3 & 1;
+          if (dx == 0) mbar_wait(a2_full(ab), (t3 >> 1) & 1);
+          if (threadIdx.x == 64) DBG_STAMP(1, it);
+          // box [KE][8][24]: channel k of pixel (y, x) shifted by the tap = float k * 192 + y * 24 + x + 3 + dx
+          const float* acol = reinterpret_cast<const float*>(base_ptr + ab * AB) + ((row >> 4) * 24 + (row & 15) + 3 + dx);
+          if (BF) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float a0 = acol[(2 * j) * 192], a1 = acol[(2 * j + 1) * 192];
+              const uint32_t h = pack_bf16x2(a0, a1);
+              hi[j] = h;
+              lo[j] = pack_bf16x2(a0 - __uint_as_float(h << 16), a1 - __uint_as_float(h & 0xFFFF0000u));
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float a0 = acol[j * 192];
+              hi[j] = (__float_as_uint(a0) + 0x1000u) & 0xFFFFE000u;
+              lo[j] = __float_as_uint(a0 - __uint_as_float(hi[j]));
+            }
+          }
+          if (dx == 2) {                               // last tap of this box: hand the buffer back
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a2_empty(ab));
+          }
+        } else {
         mbar_wait(full(s), (it / S) & 1);
         if (threadIdx.x == 64) DBG_STAMP(1, it);
         const uint8_t* arow = base_ptr + RING_OFF + s * STG + row * 128;
-        uint32_t hi[32], lo[32];
         if (BF) {
           // 64 k-values (two 128 B rows) -> 32 packed bf16x2 hi + 32 packed mid; column c holds k = 2c, 2c + 1
 #pragma unroll
@@ -546,6 +608,7 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
             }
           }
         }
+        }   // !ANCHW
         if (WRES) {                                   // the landing buffer is free as soon as every lane has read it
           __syncwarp();
           if (lane == 0) mbar_arrive(empty(s));
@@ -753,6 +816,20 @@ bool make_map_2d_bf16(CUtensorMap* m, const void* ptr, long long rows, long long
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// 4-D fp32 map over an NCHW tensor (dims W, H, C, N); box = 24 x-pixels x 8 y-pixels x ke channels, no swizzle.
+// Boxes must start on 16-byte boundaries in x: the kernel loads from x0 - 4 (x0 % 16 == 0).
+bool make_map_nchw(CUtensorMap* m, const float* ptr, int N, int H, int W, int C, int ke) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)C * H * W * 4};
+  cuuint32_t box[4] = {24, 8, (cuuint32_t)ke, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // store maps: 2-D [rows, cols] box 32 x 32, or 4-D NHWC box 32 ch x 16 x 2 x 1 (one epilogue warp's rows)
 bool make_store_map_2d(CUtensorMap* m, float* ptr, long long rows, long long cols, long long ld) {
   EncodeTiledFn enc = get_encode();
@@ -787,9 +864,9 @@ int g_tc_debug = 0;
 int g_tc_wres = 1;    // keep the weight slice resident in shared memory when K <= 128
 int g_tc_sm_limit = 0; // > 0: persistent grids use at most this many CTAs (leaves SMs to kernels of other streams)
 
-template <bool WRES, bool BF>
+template <bool WRES, bool BF, bool ANCHW = false>
 void launch_v3(dim3 grid, const CUtensorMap maps[6], const TcParams& p, cudaStream_t stream) {
-  gemm_tc_kernel_v3<WRES, BF><<<grid, NTHREADS, V3_SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
+  gemm_tc_kernel_v3<WRES, BF, ANCHW><<<grid, NTHREADS, V3_SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
 }
 
 // bf = 1: bf16-split operands (chunks of 64 k-values), 0: 3xTF32 (chunks of 32)
@@ -802,10 +879,12 @@ int launch_tc(const CUtensorMap maps[6], const TcParams& p_in, int bf, cudaStrea
     if (g_num_sms <= 0) g_num_sms = 148;
   }
   if (!g_attr_set_v3) {
-    if (cudaFuncSetAttribute(gemm_tc_kernel_v3<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(gemm_tc_kernel_v3<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(gemm_tc_kernel_v3<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(gemm_tc_kernel_v3<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_BYTES) != cudaSuccess) {
+    if (cudaFuncSetAttribute(gemm_tc_kernel_v3<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(gemm_tc_kernel_v3<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(gemm_tc_kernel_v3<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(gemm_tc_kernel_v3<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(gemm_tc_kernel_v3<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(gemm_tc_kernel_v3<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_BYTES) != cudaSuccess) {
       di_set_error("%s: cannot reserve %d bytes of shared memory", name, V3_SMEM_BYTES);
       return DI_ERR_LAUNCH;
     }
@@ -826,7 +905,9 @@ int launch_tc(const CUtensorMap maps[6], const TcParams& p_in, int bf, cudaStrea
     if (tiles >= sms) g = (sms / p.n_tiles) * p.n_tiles;
     if (g < p.n_tiles) g = p.n_tiles;
   }
-  if (wres && bf) launch_v3<true, true>(dim3(g), maps, p, stream);
+  if (p.a_nchw && bf) launch_v3<false, true, true>(dim3(g), maps, p, stream);
+  else if (p.a_nchw) launch_v3<false, false, true>(dim3(g), maps, p, stream);
+  else if (wres && bf) launch_v3<true, true>(dim3(g), maps, p, stream);
   else if (wres) launch_v3<true, false>(dim3(g), maps, p, stream);
   else if (bf) launch_v3<false, true>(dim3(g), maps, p, stream);
   else launch_v3<false, false>(dim3(g), maps, p, stream);
@@ -889,20 +970,22 @@ int linear_tc_impl(const char* name, int bf, const float* A0, int lda0, int K0, 
   return launch_tc(maps, p, bf, stream, name);
 }
 
-int conv3x3_tc_impl(const char* name, int bf, const float* x, const void* w_hi, const void* w_lo, const float* bias,
-                    float* y, int N, int Cin, int H, int W, int Cout, int act, cudaStream_t stream) {
+int conv3x3_tc_impl(const char* name, int bf, int x_nchw, const float* x, const void* w_hi, const void* w_lo,
+                    const float* bias, float* y, int N, int Cin, int H, int W, int Cout, int act, cudaStream_t stream) {
   if (!(x && w_hi && w_lo && y && N > 0 && H > 0 && W > 0)) {
     di_set_error("%s: bad argument", name);
     return DI_ERR_ARG;
   }
   const int KE = bf ? 64 : 32;
-  if (!(Cin % KE == 0 && Cout % 4 == 0 && al16(x) && al16(y) && al16(w_hi) && al16(w_lo) && (!bias || al16(bias)))) {
+  if (!(Cin % KE == 0 && Cout % 4 == 0 && al16(x) && al16(y) && al16(w_hi) && al16(w_lo) && (!bias || al16(bias)) &&
+        (!x_nchw || W % 4 == 0))) {
     di_set_error("%s: shape/alignment not supported by the tensor-core path", name);
     return DI_ERR_UNSUPPORTED;
   }
   CUtensorMap maps[6];
   long long K = 9ll * Cin;
-  bool made = make_store_map_nhwc(&maps[5], y, N, H, W, Cout) && make_map_nhwc(&maps[0], x, N, H, W, Cin);
+  bool made = make_store_map_nhwc(&maps[5], y, N, H, W, Cout) &&
+              (x_nchw ? make_map_nchw(&maps[0], x, N, H, W, Cin, KE) : make_map_nhwc(&maps[0], x, N, H, W, Cin));
   if (made) {
     if (bf) made = make_map_2d_bf16(&maps[3], w_hi, Cout, K) && make_map_2d_bf16(&maps[4], w_lo, Cout, K);
     else made = make_map_2d(&maps[3], (const float*)w_hi, Cout, K, K) && make_map_2d(&maps[4], (const float*)w_lo, Cout, K, K);
@@ -914,7 +997,7 @@ int conv3x3_tc_impl(const char* name, int bf, const float* x, const void* w_hi, 
   maps[1] = maps[0];
   maps[2] = maps[0];
   TcParams p{};
-  p.M = N * H * W; p.N = Cout; p.nsrc = 1; p.k0 = Cin / KE; p.conv = 1; p.H = H; p.W = W;
+  p.M = N * H * W; p.N = Cout; p.nsrc = 1; p.k0 = Cin / KE; p.conv = 1; p.a_nchw = x_nchw; p.H = H; p.W = W;
   p.tiles_x = di_cdiv(W, 16); p.tiles_y = di_cdiv(H, 8);
   p.C = y; p.ldc = Cout; p.bias = bias; p.res = nullptr; p.ldres = 0; p.res_mod = 1; p.act = act; p.dbg = g_tc_debug;
   p.m_tiles = N * p.tiles_x * p.tiles_y;
@@ -986,11 +1069,21 @@ int di_linear_tcb_split_f32(const float* A0, int lda0, int K0, const float* A1, 
 // w_hi / w_lo [Cout][(ky*3+kx)*Cin + ci] (fp32 tf32-split, Cin % 32 == 0) or bf16 hi / mid (Cin % 64 == 0).
 int di_conv3x3_tc_f32(const float* x, const float* w_hi, const float* w_lo, const float* bias, float* y, int N, int Cin,
                       int H, int W, int Cout, int act, cudaStream_t stream) {
-  return conv3x3_tc_impl("di_conv3x3_tc_f32", 0, x, w_hi, w_lo, bias, y, N, Cin, H, W, Cout, act, stream);
+  return conv3x3_tc_impl("di_conv3x3_tc_f32", 0, 0, x, w_hi, w_lo, bias, y, N, Cin, H, W, Cout, act, stream);
 }
 int di_conv3x3_tcb_f32(const float* x, const void* w_hi, const void* w_mid, const float* bias, float* y, int N, int Cin,
                        int H, int W, int Cout, int act, cudaStream_t stream) {
-  return conv3x3_tc_impl("di_conv3x3_tcb_f32", 1, x, w_hi, w_mid, bias, y, N, Cin, H, W, Cout, act, stream);
+  return conv3x3_tc_impl("di_conv3x3_tcb_f32", 1, 0, x, w_hi, w_mid, bias, y, N, Cin, H, W, Cout, act, stream);
+}
+// Same convolutions reading an NCHW input x [N,Cin,H,W] directly (W % 4 == 0); y stays pixel-major [N,H,W,Cout].
+// The boundary tensors of the path are NCHW (deepinteraction_encoder.py:47-62): no transposition pass is needed.
+int di_conv3x3_tc_nchw_f32(const float* x, const float* w_hi, const float* w_lo, const float* bias, float* y, int N,
+                           int Cin, int H, int W, int Cout, int act, cudaStream_t stream) {
+  return conv3x3_tc_impl("di_conv3x3_tc_nchw_f32", 0, 1, x, w_hi, w_lo, bias, y, N, Cin, H, W, Cout, act, stream);
+}
+int di_conv3x3_tcb_nchw_f32(const float* x, const void* w_hi, const void* w_mid, const float* bias, float* y, int N,
+                            int Cin, int H, int W, int Cout, int act, cudaStream_t stream) {
+  return conv3x3_tc_impl("di_conv3x3_tcb_nchw_f32", 1, 1, x, w_hi, w_mid, bias, y, N, Cin, H, W, Cout, act, stream);
 }
 
 }  // extern "C"

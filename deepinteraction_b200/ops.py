@@ -121,6 +121,9 @@ def _linear_tc(srcs, W, bias, act, out, res, res_mod, M, N, K):
 if os.environ.get('DI_B200_TC_SMS'):
     _lib.check(_lib.lib().di_tc_set_sm_limit(int(os.environ['DI_B200_TC_SMS'])), 'di_tc_set_sm_limit')
 
+# shared convs read the NCHW boundary tensors in place (no transposition pass).  Measured on B200: image conv
+# 251 us vs 208 + 65 us (transposition), BEV conv 204 us vs 111 + 39 us -> a wash overall, off by default.
+NCHW_DIRECT = [os.environ.get('DI_B200_NCHW_DIRECT', '0') != '0']
 PRESPLIT = [os.environ.get('DI_B200_PRESPLIT', '1') != '0']   # q/k/v projections emit bf16 (hi, mid) words for the window kernel
 
 
@@ -170,11 +173,13 @@ def conv3x3(x, w_packed, bias, cout, x_nhwc, y_nchw=False, act=ACT_NONE):
         N, Cin, H, W = x.shape
     if isinstance(w_packed, Weight):
         if USE_TC[0] and TC_CONV[0] and not y_nchw and cout % 4 == 0 and Cin % 32 == 0:
-            xin = x if x_nhwc else nchw_to_nhwc(x)       # the TMA box walks a pixel-major map
-            y = torch.empty((N, H, W, cout), device=x.device, dtype=torch.float32)
             bf = TC_BF16[0] and Cin % 64 == 0
-            _call('di_conv3x3_tcb_f32' if bf else 'di_conv3x3_tc_f32', _ptr(xin), _ptr(w_packed.bh if bf else w_packed.hi),
-                  _ptr(w_packed.bm if bf else w_packed.lo), _ptr(bias), _ptr(y), N, Cin, H, W, cout, act, _stream(),
+            direct = NCHW_DIRECT[0] and not x_nhwc and W % 4 == 0     # NCHW input read in place (channel-major TMA boxes)
+            xin = x if (x_nhwc or direct) else nchw_to_nhwc(x)
+            y = torch.empty((N, H, W, cout), device=x.device, dtype=torch.float32)
+            name = 'di_conv3x3_tc%s%s_f32' % ('b' if bf else '', '_nchw' if direct else '')
+            _call(name, _ptr(xin), _ptr(w_packed.bh if bf else w_packed.hi), _ptr(w_packed.bm if bf else w_packed.lo),
+                  _ptr(bias), _ptr(y), N, Cin, H, W, cout, act, _stream(),
                   nbytes=4 * (x.numel() + w_packed.w.numel() + y.numel()), flops=2 * N * H * W * cout * 9 * Cin)
             return y
         w_packed = w_packed.w

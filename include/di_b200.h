@@ -82,6 +82,12 @@ int di_conv3x3_tc_f32(const float* x, const float* w_hi, const float* w_lo, cons
                       int H, int W, int Cout, int act, cudaStream_t stream);
 int di_conv3x3_tcb_f32(const float* x, const void* w_hi, const void* w_mid, const float* bias, float* y, int N, int Cin,
                        int H, int W, int Cout, int act, cudaStream_t stream);
+/* the same two convolutions over an NCHW input x [N,Cin,H,W] (W % 4 == 0), output pixel-major: the encoder's
+ * boundary tensors (deepinteraction_encoder.py:47-62) are consumed without a transposition pass */
+int di_conv3x3_tc_nchw_f32(const float* x, const float* w_hi, const float* w_lo, const float* bias, float* y, int N,
+                           int Cin, int H, int W, int Cout, int act, cudaStream_t stream);
+int di_conv3x3_tcb_nchw_f32(const float* x, const void* w_hi, const void* w_mid, const float* bias, float* y, int N,
+                            int Cin, int H, int W, int Cout, int act, cudaStream_t stream);
 
 /* diagnostics: clock64 pipeline trace of CTA 0 of the next tensor-core launch (8 x 512 stamps) */
 int di_tc_set_debug(int on);

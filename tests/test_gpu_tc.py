@@ -79,7 +79,8 @@ def test_linear_tc_strided_sources_and_ffma_agreement():
 
 @pytest.mark.parametrize('N,Cin,H,W,Cout,nhwc_in,act', [(1, 32, 8, 16, 128, True, 0), (2, 128, 37, 45, 128, True, 1),
                                                           (6, 256, 28, 50, 128, False, 0), (1, 64, 180, 180, 128, False, 0),
-                                                          (1, 128, 5, 7, 256, True, 1)])
+                                                          (1, 128, 5, 7, 256, True, 1), (2, 128, 37, 44, 128, False, 1),
+                                                          (1, 64, 9, 200, 20, False, 0)])
 def test_conv3x3_tc_matches_float64(N, Cin, H, W, Cout, nhwc_in, act, tc_mode):
     from deepinteraction_b200 import ops, fold
     g = torch.Generator().manual_seed(N * 100 + Cin)
@@ -91,10 +92,16 @@ def test_conv3x3_tc_matches_float64(N, Cin, H, W, Cout, nhwc_in, act, tc_mode):
         ref = F.relu(ref)
     xin = x.permute(0, 2, 3, 1).contiguous() if nhwc_in else x
     Wt = fold.Weight(fold.pack_conv3x3(w), dev())
-    y = ops.conv3x3(xin.to(dev()), Wt, b.to(dev()), Cout, nhwc_in, False, act).cpu().permute(0, 3, 1, 2)
-    e = rel_err(y, ref.float())
-    print(f'conv_tc N={N} Cin={Cin} {H}x{W}: rel err {e:.2e}')
-    assert e < TIGHT
+    for direct in ((False,) if nhwc_in else (False, True)):     # NCHW inputs: via transposition, and read in place
+        old = ops.NCHW_DIRECT[0]
+        ops.NCHW_DIRECT[0] = direct
+        try:
+            y = ops.conv3x3(xin.to(dev()), Wt, b.to(dev()), Cout, nhwc_in, False, act).cpu().permute(0, 3, 1, 2)
+        finally:
+            ops.NCHW_DIRECT[0] = old
+        e = rel_err(y, ref.float())
+        print(f'conv_tc N={N} Cin={Cin} {H}x{W} direct={direct}: rel err {e:.2e}')
+        assert e < TIGHT
 
 
 def test_bf16_split_keeps_16_bits():
