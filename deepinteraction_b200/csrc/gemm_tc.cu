@@ -25,8 +25,43 @@
 //               swizzled staging buffer -> cp.async.bulk.tensor store; overlaps the next tile's main loop through
 //               a double-buffered accumulator
 //   TMEM columns: [0,128) acc0 | [128,256) acc1 | [256 + 64 b, +64) A buffer b (hi 32 | lo 32)
-#include "common.cuh"
-#include <cuda.h>
+#include "tc_common.cuh"
+#include <mutex>
+#include <vector>
+
+// ------------------------------------------------------------------------------------------------
+// Dynamic tile-scheduler state of the persistent tensor-core kernels (this file and lcab_tc.cu): every launch gets
+// a 16-int slot (tile counters + a done counter); the last CTA of a launch zeroes its slot again.  Slots come from a
+// ring that belongs to the (device, stream) pair of the launch: launches of one stream are serialised, so a slot can
+// only ever be shared by launches that cannot overlap -- also under graph replay, where the slot address is baked
+// into the captured launch and the graph is replayed on the stream it was captured on (graph.GraphCache keys on the
+// stream).  Launches of different streams (frames in flight, pipeline.FramePipeline) never share a slot.
+// ------------------------------------------------------------------------------------------------
+namespace tc {
+constexpr int SCHED_RINGS = 64, SCHED_RING_SLOTS = 64;
+__device__ int g_sched_pool[SCHED_RINGS * SCHED_RING_SLOTS * 16];
+struct Ring { int dev; cudaStream_t stream; unsigned seq; };
+static std::mutex g_sched_mu;
+static std::vector<Ring> g_rings;
+static int* g_pool_ptr[64] = {nullptr};
+
+int* sched_slot(cudaStream_t stream) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lock(g_sched_mu);
+  if (!g_pool_ptr[dev] && cudaGetSymbolAddress(reinterpret_cast<void**>(&g_pool_ptr[dev]), g_sched_pool) != cudaSuccess)
+    return nullptr;
+  size_t r = 0;
+  for (; r < g_rings.size(); ++r)
+    if (g_rings[r].dev == dev && g_rings[r].stream == stream) break;
+  if (r == g_rings.size()) g_rings.push_back(Ring{dev, stream, 0u});
+  // more than SCHED_RINGS (device, stream) pairs: rings are reused modulo SCHED_RINGS (documented limit)
+  const size_t ring = r % SCHED_RINGS;
+  const unsigned slot = g_rings[r].seq++ % SCHED_RING_SLOTS;
+  return g_pool_ptr[dev] + (ring * SCHED_RING_SLOTS + slot) * 16;
+}
+}  // namespace tc
 
 namespace {
 
@@ -34,100 +69,12 @@ constexpr int TM = 128, TN = 128, TK = 32;          // tile; TK fp32 = 128 bytes
 constexpr int A_BYTES = TM * TK * 4;                // 16 KB
 constexpr int NTHREADS = 320;
 constexpr int EP_BYTES = 4 /*warps*/ * 2 /*buffers*/ * 32 * 128;   // epilogue staging: 32 rows x 128 B per buffer
-int g_num_sms = 0;
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+using namespace tc;
 
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {
-  }
-}
-
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
-                                            int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
-          dst),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                   reinterpret_cast<uint64_t>(map)),
-               "r"(src), "r"(c0), "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
-                   reinterpret_cast<uint64_t>(map)),
-               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-               : "memory");
-}
-
-// L2 prefetch of a future box (no shared-memory footprint): raises the bytes in flight beyond the 3-stage ring
-__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)),
-               "r"(c0), "r"(c1)
-               : "memory");
-}
-
-// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row atoms 1024 bytes apart.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) /*LBO (unused)*/ | (64ull << 32) /*SBO = 1024 B*/ |
-         (1ull << 46) /*version*/ | (2ull << 61) /*SWIZZLE_128B*/;
-}
 // kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 128
 constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// tcgen05.ld of 32 lanes x 32 columns; the caller issues several, then one tcgen05.wait::ld (asm volatile keeps the order)
-__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]),
-        "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]), "=f"(v[16]),
-        "=f"(v[17]), "=f"(v[18]), "=f"(v[19]), "=f"(v[20]), "=f"(v[21]), "=f"(v[22]), "=f"(v[23]), "=f"(v[24]),
-        "=f"(v[25]), "=f"(v[26]), "=f"(v[27]), "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])
-      : "r"(taddr)
-      : "memory");
-}
 
 // optional pipeline trace (CTA 0 only): clock64 stamps per role and chunk, read back with di_tc_debug_read
 constexpr int DBG_SLOTS = 8, DBG_N = 512;
@@ -197,39 +144,6 @@ static_assert(V3_SMEM_BYTES <= 232448, "v3 exceeds the 227 KB shared-memory limi
 // kind::f16, bf16 x bf16 -> fp32, A and B K-major, M = 128, N = 128
 constexpr uint32_t IDESC_BF16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 
-__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc,
-                                             uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(
-          tmem_d),
-      "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc,
-                                             uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(
-          tmem_d),
-      "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// two fp32 -> packed bf16x2 (round to nearest even): low half = lo_elem, high half = hi_elem
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
-  uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
-  return r;
-}
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
-      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
-      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
-      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-      : "memory");
-}
 
 // Pre-split outputs for the window-attention kernel (lcab.cu), same 4 bytes per value, same position of each
 // 32-channel block: the consumer then needs no conversion pass.  hi = bf16(x), mid = bf16(x - hi), packed bf16x2
@@ -237,6 +151,7 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
 //   kind 1 (Q, K): channel pair (2j, 2j+1) -> words 2j = hi pair, 2j+1 = mid pair          (one LDS.64 per fragment)
 //   kind 2 (V):    channel group of 8      -> words 8g..8g+3 = hi pairs, 8g+4..8g+7 = mid pairs  (16-byte rows for
 //                                             ldmatrix.trans: the k index of P V is the key, not the channel)
+//   kind 3 (planar, tcgen05 window kernel): group of 128 channels -> 64 hi words | 64 mid words (finish_pair_planar)
 __device__ __forceinline__ void split_block(float (&v)[32], int kind) {
   if (kind == 1) {
 #pragma unroll
@@ -664,7 +579,7 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       const int act = p.act;
       const int ncols = min(TN, p.N - n0);                       // valid columns of this tile (multiple of 4)
 
-      auto finish_block = [&](float (&v)[32], int c0) {          // bias/res/act -> staging -> TMA store
+      auto prep_block = [&](float (&v)[32], int c0) {            // bias / residual / activation in registers
         const int col = n0 + c0;
         const bool fullc = c0 + 32 <= ncols;
 #pragma unroll
@@ -688,7 +603,8 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           }
         }
         act_tile(v, act);
-        if (p.split_kind && col >= p.split_col0) split_block(v, p.split_kind);
+      };
+      auto store_block = [&](float (&v)[32], int col) {          // 32 words per row -> staging -> TMA store at word column col
         const uint32_t buf = my_ep + (uint32_t)(chunk & 1) * 4096u;
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // buffer's previous store done
         __syncwarp();
@@ -705,6 +621,36 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
         ++chunk;
+      };
+      auto finish_block = [&](float (&v)[32], int c0) {          // bias/res/act -> staging -> TMA store
+        const int col = n0 + c0;
+        prep_block(v, c0);
+        if (p.split_kind && col >= p.split_col0) split_block(v, p.split_kind);
+        store_block(v, col);
+      };
+      // split kind 3 ("planar", the operand format of the tcgen05 window kernel, lcab_tc.cu): every group of 128
+      // output channels becomes 64 words of bf16 hi followed by 64 words of bf16 mid; one call handles 64 channels
+      // (v0 = channels c0..c0+31, v1 = c0+32..c0+63) = 32 hi words + 32 mid words.
+      auto finish_pair_planar = [&](float (&v0)[32], float (&v1)[32], int c0) {
+        prep_block(v0, c0);
+        prep_block(v1, c0 + 32);
+        uint32_t h[32], m[32];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          h[j] = pack_bf16x2(v0[2 * j], v0[2 * j + 1]);
+          m[j] = pack_bf16x2(v0[2 * j] - __uint_as_float(h[j] << 16), v0[2 * j + 1] - __uint_as_float(h[j] & 0xFFFF0000u));
+          h[16 + j] = pack_bf16x2(v1[2 * j], v1[2 * j + 1]);
+          m[16 + j] = pack_bf16x2(v1[2 * j] - __uint_as_float(h[16 + j] << 16), v1[2 * j + 1] - __uint_as_float(h[16 + j] & 0xFFFF0000u));
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          v0[j] = __uint_as_float(h[j]);
+          v1[j] = __uint_as_float(m[j]);
+        }
+        const int rel = n0 + c0 - p.split_col0;
+        const int wcol = p.split_col0 + (rel & ~127) + ((rel & 127) >> 1);
+        store_block(v0, wcol);
+        store_block(v1, wcol + 64);
       };
 
       const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TN);
@@ -736,9 +682,13 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           if (lane == 0) mbar_arrive(acc_empty(a));
         }
         if (threadIdx.x == 192) DBG_STAMP(7, (tl * 2 + h) * 3 + 0);
-        finish_block(v0, c0);
-        if (threadIdx.x == 192) DBG_STAMP(7, (tl * 2 + h) * 3 + 1);
-        if (two) finish_block(v1, c0 + 32);
+        if (p.split_kind == 3 && n0 + c0 >= p.split_col0) {
+          finish_pair_planar(v0, v1, c0);
+        } else {
+          finish_block(v0, c0);
+          if (threadIdx.x == 192) DBG_STAMP(7, (tl * 2 + h) * 3 + 1);
+          if (two) finish_block(v1, c0 + 32);
+        }
         if (threadIdx.x == 192) DBG_STAMP(7, (tl * 2 + h) * 3 + 2);
       }
       if (threadIdx.x == 192) DBG_STAMP(6, tl);
@@ -762,21 +712,6 @@ gemm_tc_kernel_v3(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
 }
 
 // ---- host side ----------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(ptr);
-  }
-  return fn;
-}
 
 // 2-D fp32 map over a row-major [rows, cols] matrix with row stride ld (elements); box = 32 cols x 128 rows
 bool make_map_2d(CUtensorMap* m, const float* ptr, long long rows, long long cols, long long ld) {
@@ -852,14 +787,14 @@ bool make_store_map_nhwc(CUtensorMap* m, float* ptr, int N, int H, int W, int C)
              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-bool g_attr_set_v3 = false;
-// dynamic tile scheduler state: a ring of 256 zero-initialised slots of 16 ints; launch n uses slot n % 256 and the
-// last CTA of a launch zeroes its slot again, so a slot is clean long before it comes round (also under graph replay,
-// where the slot index is baked into the captured launch).
-constexpr int SCHED_SLOTS = 256;
-__device__ int g_sched[SCHED_SLOTS * 16];
-int* g_sched_ptr = nullptr;
-unsigned g_sched_seq = 0;
+// Per-device launch state (one process may drive several GPUs): SM count, the one-time shared-memory attribute and
+// the address of this device's copy of the scheduler pool.
+constexpr int MAX_DEV = 64;
+struct DevState {
+  int num_sms = 0;
+  bool attr_set = false;
+};
+DevState g_dev[MAX_DEV];
 int g_tc_debug = 0;
 int g_tc_wres = 1;    // keep the weight slice resident in shared memory when K <= 128
 int g_tc_sm_limit = 0; // > 0: persistent grids use at most this many CTAs (leaves SMs to kernels of other streams)
@@ -872,13 +807,19 @@ void launch_v3(dim3 grid, const CUtensorMap maps[6], const TcParams& p, cudaStre
 // bf = 1: bf16-split operands (chunks of 64 k-values), 0: 3xTF32 (chunks of 32)
 int launch_tc(const CUtensorMap maps[6], const TcParams& p_in, int bf, cudaStream_t stream, const char* name) {
   TcParams p = p_in;
-  if (g_num_sms == 0) {
-    int devid = 0;
-    cudaGetDevice(&devid);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, devid);
-    if (g_num_sms <= 0) g_num_sms = 148;
+  int devid = 0;
+  cudaGetDevice(&devid);
+  if (devid < 0 || devid >= MAX_DEV) {
+    di_set_error("%s: device ordinal %d not supported", name, devid);
+    return DI_ERR_UNSUPPORTED;
   }
-  if (!g_attr_set_v3) {
+  DevState& ds = g_dev[devid];
+  if (ds.num_sms == 0) {
+    cudaDeviceGetAttribute(&ds.num_sms, cudaDevAttrMultiProcessorCount, devid);
+    if (ds.num_sms <= 0) ds.num_sms = 148;
+  }
+  const int g_num_sms = ds.num_sms;
+  if (!ds.attr_set) {
     if (cudaFuncSetAttribute(gemm_tc_kernel_v3<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(gemm_tc_kernel_v3<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(gemm_tc_kernel_v3<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_BYTES) != cudaSuccess ||
@@ -888,13 +829,13 @@ int launch_tc(const CUtensorMap maps[6], const TcParams& p_in, int bf, cudaStrea
       di_set_error("%s: cannot reserve %d bytes of shared memory", name, V3_SMEM_BYTES);
       return DI_ERR_LAUNCH;
     }
-    g_attr_set_v3 = true;
+    ds.attr_set = true;
   }
-  if (!g_sched_ptr && cudaGetSymbolAddress(reinterpret_cast<void**>(&g_sched_ptr), g_sched) != cudaSuccess) {
+  p.sched = tc::sched_slot(stream);
+  if (!p.sched) {
     di_set_error("%s: cannot resolve the scheduler buffer", name);
     return DI_ERR_LAUNCH;
   }
-  p.sched = g_sched_ptr + 16 * (g_sched_seq++ % SCHED_SLOTS);
   const int tiles = p.m_tiles * p.n_tiles;
   const int sms = (g_tc_sm_limit > 0 && g_tc_sm_limit < g_num_sms) ? g_tc_sm_limit : g_num_sms;
   int nk = p.k0 + p.k1 + p.k2;
@@ -960,8 +901,10 @@ int linear_tc_impl(const char* name, int bf, const float* A0, int lda0, int K0, 
   p.m_tiles = di_cdiv(M, TM);
   p.n_tiles = di_cdiv(N, TN);
   if (split_kind) {
-    if (!((split_kind == 1 || split_kind == 2) && split_col0 >= 0 && split_col0 % 32 == 0 && N % 32 == 0)) {
-      di_set_error("%s: split output needs kind 1|2, split_col0 %% 32 == 0 and N %% 32 == 0", name);
+    const bool ok12 = (split_kind == 1 || split_kind == 2) && split_col0 >= 0 && split_col0 % 32 == 0 && N % 32 == 0;
+    const bool ok3 = split_kind == 3 && split_col0 >= 0 && split_col0 % 128 == 0 && N % 128 == 0;
+    if (!(ok12 || ok3)) {
+      di_set_error("%s: split output needs kind 1|2 (split_col0 %% 32 == 0, N %% 32 == 0) or kind 3 (both %% 128 == 0)", name);
       return DI_ERR_ARG;
     }
     p.split_col0 = split_col0;
@@ -1056,7 +999,9 @@ int di_linear_tcb_f32(const float* A0, int lda0, int K0, const float* A1, int ld
                         res_mod, C, ldc, M, N, act, 0, 0, stream);
 }
 // di_linear_tcb_f32 whose output columns >= split_col0 are written pre-split for di_lcab_window_pre_f32
-// (split_kind 1 = Q / K layout, 2 = V layout; see split_block above).  split_col0 % 32 == 0, N % 32 == 0.
+// (split_kind 1 = Q / K layout, 2 = V layout; see split_block above; split_col0 % 32 == 0, N % 32 == 0) or for
+// di_lcab_window_tc_f32 (split_kind 3 = planar: per 128 channels 64 words of bf16 hi, then 64 words of bf16 mid;
+// split_col0 % 128 == 0, N % 128 == 0).
 int di_linear_tcb_split_f32(const float* A0, int lda0, int K0, const float* A1, int lda1, int K1, const float* A2,
                             int lda2, int K2, const void* W_hi, const void* W_mid, const float* bias, const float* res,
                             int ldres, int res_mod, float* C, int ldc, int M, int N, int act, int split_col0,

@@ -92,7 +92,8 @@ def split_bf16(w):
 def split_rows(x, kind):
     """Host model of the pre-split operand format of the window kernel (gemm_tc.cu split_block): x [M, C] fp32 ->
     [M, C] fp32-typed tensor whose 32-bit words are packed bf16x2 (hi = bf16(x), mid = bf16(x - hi), lower channel in
-    the low half).  kind 1: channel pair j -> words 2j (hi), 2j+1 (mid); kind 2: channel group of 8 -> 4 hi | 4 mid."""
+    the low half).  kind 1: channel pair j -> words 2j (hi), 2j+1 (mid); kind 2: channel group of 8 -> 4 hi | 4 mid;
+    kind 3 (planar, tcgen05 window kernel): channel group of 128 -> 64 hi words | 64 mid words."""
     x = x.to(torch.float32)
     hi = x.to(torch.bfloat16)
     mid = (x - hi.to(torch.float32)).to(torch.bfloat16)
@@ -103,6 +104,10 @@ def split_rows(x, kind):
     out = torch.empty(M, C, dtype=torch.int32, device=x.device)
     if kind == 1:
         out[:, 0::2], out[:, 1::2] = wh, wm
+    elif kind == 3:
+        assert C % 128 == 0
+        o = out.view(M, C // 128, 128)
+        o[:, :, :64], o[:, :, 64:] = wh.view(M, C // 128, 64), wm.view(M, C // 128, 64)
     else:
         o = out.view(M, C // 8, 8)
         o[:, :, :4], o[:, :, 4:] = wh.view(M, C // 8, 4), wm.view(M, C // 8, 4)

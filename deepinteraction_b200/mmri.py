@@ -105,19 +105,24 @@ def lcab_forward(pk, target, source, N, H, W):
     directly (bf16 hi/mid words, ops.linear_split), so the window kernel has no conversion work."""
     C = pk['C']
     pre = ops.can_presplit(N * H * W, C, pk['ks'])
+    tc = ops.can_window_tc(N * H * W, C, pk['ks'])       # tcgen05 window kernel: planar operands (split kind 3)
     if target is source:
         if pre:
-            t = ops.linear_split([source], pk['w_self'], pk['b_self'], ops.ACT_RELU, 2 * C, 2)    # q1 | k1 | v(split)
+            t = ops.linear_split([source], pk['w_self'], pk['b_self'], ops.ACT_RELU, 2 * C, 3 if tc else 2)    # q1 | k1 | v(split)
         else:
             t = ops.linear([source], pk['w_self'], pk['b_self'], ops.ACT_RELU)        # [M, 3C] = q1 | k1 | v
         q1, k1, v = t[:, :C], t[:, C:2 * C], t[:, 2 * C:]
     else:
         q1 = ops.linear([target], pk['w_q1'], pk['b_q1'], ops.ACT_RELU)
         if pre:
-            t = ops.linear_split([source], pk['w_kv1'], pk['b_kv1'], ops.ACT_RELU, C, 2)          # k1 | v(split)
+            t = ops.linear_split([source], pk['w_kv1'], pk['b_kv1'], ops.ACT_RELU, C, 3 if tc else 2)          # k1 | v(split)
         else:
             t = ops.linear([source], pk['w_kv1'], pk['b_kv1'], ops.ACT_RELU)          # [M, 2C] = k1 | v
         k1, v = t[:, :C], t[:, C:]
+    if tc:
+        q = ops.linear_split([q1], pk['w_q2'], pk['b_q2'], ops.ACT_RELU, 0, 3)
+        k = ops.linear_split([k1], pk['w_k2'], pk['b_k2'], ops.ACT_RELU, 0, 3)
+        return ops.lcab_window_tc(q, k, v, N, H, W, C)
     if pre:
         q = ops.linear_split([q1], pk['w_q2'], pk['b_q2'], ops.ACT_RELU, 0, 1)
         k = ops.linear_split([k1], pk['w_k2'], pk['b_k2'], ops.ACT_RELU, 0, 1)

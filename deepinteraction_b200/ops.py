@@ -137,6 +137,7 @@ def linear_split(srcs, W, bias, act, split_col0, split_kind):
     layout, 2: V layout) for lcab_window_pre.  Only valid where can_presplit() holds."""
     M, N = srcs[0].shape[0], W.shape[0]
     assert isinstance(W, Weight) and all(s.shape[1] % 64 == 0 for s in srcs) and N % 32 == 0 and split_col0 % 32 == 0
+    assert split_kind != 3 or (N % 128 == 0 and split_col0 % 128 == 0)
     a = []
     for s in srcs:
         _f32(s)
@@ -150,6 +151,24 @@ def linear_split(srcs, W, bias, act, split_col0, split_kind):
         _TAG[0] = ' M%d N%d K%d split' % (M, N, K)
     _call('di_linear_tcb_split_f32', *a, _ptr(W.bh), _ptr(W.bm), _ptr(bias), None, 0, 0, _ptr(out), N, M, N, act,
           split_col0, split_kind, _stream(), nbytes=4 * (M * K + N * K + M * N), flops=2 * M * N * K)
+    return out
+
+
+WINDOW_TC = [os.environ.get('DI_B200_WINDOW_TC', '1') != '0']   # tcgen05 window kernel (C == 128) instead of mma.sync
+
+
+def can_window_tc(M, C, ksize):
+    """True when the LCAB projections may emit planar operands for the tcgen05 window kernel (lcab_tc.cu)."""
+    return bool(WINDOW_TC[0] and can_presplit(M, C, ksize) and C == 128)
+
+
+def lcab_window_tc(q, k, v, N, H, W, C, out=None):
+    """9x9 window attention on tcgen05 for planar pre-split q, k, v row views (linear_split kind 3)."""
+    if out is None:
+        out = torch.empty(N * H * W, C, device=q.device, dtype=torch.float32)
+    (pq, lq), (pk, lk), (pv, lv), (po, lo) = _rows(q), _rows(k), _rows(v), _rows(out)
+    _call('di_lcab_window_tc_f32', pq, lq, pk, lk, pv, lv, po, lo, N, H, W, C, _stream(),
+          nbytes=4 * 4 * N * H * W * C, flops=2 * 2 * 81 * N * H * W * C)
     return out
 
 

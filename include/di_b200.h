@@ -72,8 +72,11 @@ int di_linear_tcb_f32(const float* A0, int lda0, int K0, const float* A1, int ld
 /* di_linear_tcb_f32 whose output columns >= split_col0 (a multiple of 32; N % 32 == 0) are written PRE-SPLIT for
  * di_lcab_window_pre_f32: each value keeps its 4 bytes and its position, but holds packed bf16x2 words
  * (hi = bf16(x), mid = bf16(x - hi)); split_kind 1 = Q/K layout (channel pair 2j,2j+1 -> words 2j = hi, 2j+1 = mid),
- * 2 = V layout (channel group of 8 -> 4 hi words | 4 mid words).  Replaces the k/q/v projections of
- * LocalContextAttentionBlock (models/utils/encoder_utils.py:95-131) when their consumer is the window kernel. */
+ * 2 = V layout (channel group of 8 -> 4 hi words | 4 mid words); split_kind 3 = PLANAR layout for
+ * di_lcab_window_tc_f32 (split_col0 % 128 == 0, N % 128 == 0): every group of 128 channels becomes 64 words of bf16
+ * hi followed by 64 words of bf16 mid, i.e. two K-major bf16 planes that TMA can drop into tcgen05 operand tiles.
+ * Replaces the k/q/v projections of LocalContextAttentionBlock (models/utils/encoder_utils.py:95-131) when their
+ * consumer is the window kernel. */
 int di_linear_tcb_split_f32(const float* A0, int lda0, int K0, const float* A1, int lda1, int K1, const float* A2,
                             int lda2, int K2, const void* W_hi, const void* W_mid, const float* bias, const float* res,
                             int ldres, int res_mod, float* C, int ldc, int M, int N, int act, int split_col0,
@@ -106,6 +109,15 @@ int di_lcab_window_f32(const float* q, int ldq, const float* k, int ldk, const f
 /* Same op for q, k (kind 1) and v (kind 2) emitted pre-split by di_linear_tcb_split_f32: no conversion passes. */
 int di_lcab_window_pre_f32(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* out, int ldo,
                            int N, int H, int W, int C, cudaStream_t stream);
+
+/* The same op on the Blackwell tensor cores (lcab_tc.cu: tcgen05.mma with S = Q K^T and O = P V accumulated in
+ * tensor memory, TMA-staged halo tiles, softmax by lane = query warps).  q, k, v: PLANAR pre-split operands
+ * (split_kind 3 above) -- [N*H*W] pixels with a stride of ld* 32-bit words, 128 bf16 hi | 128 bf16 mid per pixel;
+ * out fp32 [N,H,W,ldo].  C must be 128 (returns -3 otherwise: use di_lcab_window_pre_f32 / di_lcab_window_f32).
+ * Replaces similar_forward + softmax + weighting_forward (encoder_utils.py:132-134, localAttention.cpp:7-15,31-39). */
+int di_lcab_window_tc_f32(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, float* out, int ldo,
+                          int N, int H, int W, int C, cudaStream_t stream);
+int di_lcab_window_tc_set_sm_limit(int n); /* persistent grid of the kernel above uses at most n CTAs (0 = all) */
 
 /* test/diagnostic hook: 1 = always use the FFMA window kernel, 0 = tensor-core (mma.sync 3xTF32) kernel when
  * ksize == 9 and C % 32 == 0 (default) */

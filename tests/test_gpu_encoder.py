@@ -139,6 +139,47 @@ def test_window_attention_presplit_operands(C, H, W):
     assert torch.equal(k1.view(torch.int32), fold.split_rows(plain, 1).view(torch.int32))
 
 
+@pytest.mark.parametrize('N,H,W', [(2, 16, 8), (1, 40, 33), (2, 9, 50), (3, 37, 21), (1, 112, 200)])
+def test_window_attention_tcgen05_planar_operands(N, H, W):
+    """tcgen05 window kernel (lcab_tc.cu, C = 128): host-side model of the planar operand format ->
+    di_lcab_window_tc_f32 vs the oracle (edge tiles, several images, the base image-map shape), and
+    di_linear_tcb_split_f32 kind 3 emits exactly that format."""
+    import oracle.mmri as om
+    from deepinteraction_b200 import ops, fold
+    C = 128
+    g = torch.Generator().manual_seed(17 + H)
+    q, k, v = (torch.randn(N, C, H, W, generator=g) for _ in range(3))
+    q = q * 1.7                                         # logits with a spread of a few units after the 1/sqrt(C) scale
+    w = F.softmax(om.window_similarity(q, k, 9) / np.sqrt(C), -1)
+    ref = om.window_weighting(v, w, 9)
+    rows = lambda t: t.permute(0, 2, 3, 1).reshape(-1, C).contiguous().to(dev())
+    out = ops.lcab_window_tc(fold.split_rows(rows(q), 3), fold.split_rows(rows(k), 3), fold.split_rows(rows(v), 3),
+                             N, H, W, C)
+    assert rel_err(out.view(N, H, W, C).permute(0, 3, 1, 2).cpu(), ref) < TIGHT
+    # second launch on the same stream (scheduler slot re-armed, TMEM re-allocated) must reproduce the result bit for bit
+    out2 = ops.lcab_window_tc(fold.split_rows(rows(q), 3), fold.split_rows(rows(k), 3), fold.split_rows(rows(v), 3),
+                              N, H, W, C)
+    assert torch.equal(out, out2)
+
+
+def test_linear_split_planar_format():
+    """The dense layer's planar split epilogue (kind 3) == fold.split_rows(plain output, 3), bit for bit, also when
+    only the trailing 128 columns of a wider output are split (q1 | k1 | v)."""
+    from deepinteraction_b200 import ops, fold
+    g = torch.Generator().manual_seed(23)
+    M, C = 1000, 128
+    x = torch.randn(M, 128, generator=g).to(dev())
+    Wt = fold.Weight(torch.randn(3 * C, 128, generator=g) / 11, dev())
+    b = torch.randn(3 * C, generator=g).to(dev())
+    plain = ops.linear([x], Wt, b, ops.ACT_RELU)
+    mixed = ops.linear_split([x], Wt, b, ops.ACT_RELU, 2 * C, 3)
+    assert torch.equal(mixed[:, :2 * C], plain[:, :2 * C])
+    assert torch.equal(mixed[:, 2 * C:].contiguous().view(torch.int32),
+                       fold.split_rows(plain[:, 2 * C:].contiguous(), 3).view(torch.int32))
+    allp = ops.linear_split([x], Wt, b, ops.ACT_RELU, 0, 3)
+    assert torch.equal(allp.view(torch.int32), fold.split_rows(plain, 3).view(torch.int32))
+
+
 def _mk_lcab(C, seed):
     import oracle.mmri as om
     from deepinteraction_b200 import synth

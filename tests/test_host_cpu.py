@@ -193,3 +193,9 @@ def test_presplit_operand_format_roundtrip():
         unpack = lambda t: torch.stack([(t << 16), (t & -65536)], -1).view(torch.float32).reshape(37, 64)
         rec = unpack(wh) + unpack(wm)
         assert float(((rec - x).abs() / x.abs()).max()) <= 2.0 ** -16
+    # kind 3 (planar, tcgen05 window kernel): 128 channels -> 64 hi words | 64 mid words
+    x3 = torch.randn(37, 256, generator=g) * torch.logspace(-3, 3, 256)
+    w = fold.split_rows(x3, 3).view(torch.int32).view(37, 2, 128)
+    wh, wm = w[:, :, :64].reshape(37, 128), w[:, :, 64:].reshape(37, 128)
+    unpack = lambda t: torch.stack([(t << 16), (t & -65536)], -1).view(torch.float32).reshape(37, 256)
+    assert float((((unpack(wh) + unpack(wm)) - x3).abs() / x3.abs()).max()) <= 2.0 ** -16
