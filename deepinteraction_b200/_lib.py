@@ -37,6 +37,8 @@ SIGNATURES = {
     'di_lcab_window_pre_f32': [_p, _i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _p],
     'di_lcab_window_tc_f32': [_p, _i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _p],
     'di_lcab_window_tc_set_sm_limit': [_i],
+    'di_lcab_window_tc_set_debug': [_i],
+    'di_lcab_window_tc_debug_read': [ctypes.POINTER(ctypes.c_longlong)],
     'di_set_window_ffma': [_i],
     'di_locatt_cc2k_f32': [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     'di_locatt_ck2c_ori_f32': [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p],

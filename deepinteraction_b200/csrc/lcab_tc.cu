@@ -22,10 +22,13 @@
 //                                     accumulator in TMEM columns [384, 512)
 //   out = O / sum                     tcgen05.ld -> registers -> swizzled staging -> TMA store (clips the image edge)
 //
-// Warp roles (192 threads): warp 0 = tile scheduler + TMA producer (Q tile, then K and V stages through one 3-deep
-// ring of 48 KB stages), warp 1 = MMA issuer (elect.sync), warps 2..5 = softmax + epilogue.  All hand-offs through
-// mbarriers; the S product of tile i+1 overlaps the epilogue of tile i, the first softmax pass overlaps the S product
-// group by group, and the P V product starts as soon as the first 6 halo rows of P are written.
+// Warp roles (576 threads): warp 0 = tile scheduler + TMA producer (Q tile, then K and V stages through one 3-deep
+// ring of 48 KB stages; the next tile's Q is loaded and its first K stages are prefetched into L2 while the current
+// tile is in its softmax / P V phase), warp 1 = MMA issuer (elect.sync), warps 2..13 = softmax (three warps per TMEM
+// lane quarter, each takes two of the quarter's six halo row pairs -- interleaved so that every key group of P is
+// complete after at most two exp passes; maxima / sums exchanged through shared memory), warps 14..17 = epilogue.  All hand-offs through mbarriers; the S product of tile i+1 overlaps the epilogue of tile i, the first
+// softmax pass overlaps the S product group by group, and the P V product starts as soon as the first 6 halo rows of
+// P are written.
 #include "tc_common.cuh"
 
 namespace {
@@ -42,10 +45,12 @@ constexpr int QBOX = 128 * 128;                // 128 queries x 128 B
 constexpr int Q_BYTES = 4 * QBOX;
 constexpr int EP_BYTES_W = 4096;               // epilogue staging per warp: 32 rows x 128 B
 constexpr int Q_OFF = 0, RING_OFF = Q_BYTES, EP_OFF = RING_OFF + RING * STAGE_BYTES, BAR_OFF = EP_OFF + 4 * EP_BYTES_W;
+constexpr int NSW = 3;                         // softmax warps per TMEM lane quarter
+constexpr int MX_OFF = BAR_OFF + 512;          // float [NSW][128 queries]: pass-1 maxima, then the partial softmax sums
 constexpr int TQD = 4;                         // tile-id queue depth
-constexpr int WT_SMEM_BYTES = BAR_OFF + 512 + 1024;
+constexpr int WT_SMEM_BYTES = MX_OFF + NSW * 512;  // the dynamic shared-memory window is 1024-byte aligned (checked at run time)
 static_assert(WT_SMEM_BYTES <= 232448, "window kernel exceeds the 227 KB shared-memory limit");
-constexpr int WT_THREADS = 192;
+constexpr int WT_THREADS = (2 + 4 * NSW + 4) * 32;
 constexpr uint32_t O_COL = 384;
 
 // kind::f16: bf16 x bf16 -> fp32, M = 128.  S: N = 96, A and B K-major.  PV: N = 128, B MN-major (bit 16).
@@ -75,15 +80,25 @@ struct WtParams {
   int H, W, tiles_x, tiles_y, num_tiles;
   float c_log2;        // log2(e) / sqrt(C)
   int* sched;
+  int dbg;
 };
+
+// optional pipeline trace of CTA 0 (di_lcab_window_tc_set_debug): clock64 stamps per role, 16 per tile
+constexpr int WDBG_SLOTS = 6, WDBG_N = 256;
+__device__ long long g_wdbg[WDBG_SLOTS * WDBG_N];
+#define WSTAMP(slot, i)                                                                          \
+  do {                                                                                          \
+    if (p.dbg && blockIdx.x == 0 && (i) < WDBG_N) g_wdbg[(slot) * WDBG_N + (i)] = clock64();     \
+  } while (0)
 
 __global__ void __launch_bounds__(WT_THREADS, 1)
 lcab_window_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                       const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapO,
                       const WtParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = smem_u32(smem_raw);
+  uint8_t* base_ptr = smem_raw;
+  if ((base & 1023u) != 0u) __trap();                 // 128B-swizzled operand tiles need 1024-byte alignment
   const uint32_t bars = base + BAR_OFF;
   const uint32_t q_full = bars, q_empty = bars + 8, o_full = bars + 16, o_empty = bars + 24;
   auto full = [&](int s) { return bars + 32u + 8u * s; };
@@ -95,6 +110,8 @@ lcab_window_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
   const uint32_t tmem_slot = bars + 208;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + BAR_OFF + 208);
   volatile int* tq = reinterpret_cast<volatile int*>(base_ptr + BAR_OFF + 224);
+  const uint32_t sum_full = bars + 240, sum_empty = bars + 248;
+  volatile float* mx = reinterpret_cast<volatile float*>(base_ptr + MX_OFF);   // maxima (pass 1) / partial sums (after pass 2)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane < 4) {
@@ -112,11 +129,13 @@ lcab_window_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
     }
     for (int g = 0; g < NG; ++g) {
       mbar_init(s_full(g), 1);
-      mbar_init(p_full(g), 4);
+      mbar_init(p_full(g), 4 * NSW);
     }
+    mbar_init(sum_full, 4 * NSW);
+    mbar_init(sum_empty, 4);
     for (int i = 0; i < TQD; ++i) {
       mbar_init(tq_full(i), 1);
-      mbar_init(tq_empty(i), 5);                       // MMA warp + 4 softmax warps
+      mbar_init(tq_empty(i), 1 + 4 * NSW + 4);         // MMA warp + softmax warps + 4 epilogue warps
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -161,19 +180,45 @@ lcab_window_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
         ++published;
       };
       publish();
+      publish();
+      auto load_q = [&](int tile) {
+        int img, y0, x0;
+        tile_coords(tile, img, y0, x0);
+        mbar_expect_tx(q_full, Q_BYTES);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) tma_load_4d(base + Q_OFF + b * QBOX, &mapQ, q_full, b * 64, x0, y0, img);
+      };
+      if (tq[0] >= 0) load_q(tq[0]);
       for (int n = 0;; ++n) {
         const int tile = tq[n % TQD];
         if (tile < 0) break;
         int img, y0, x0;
         tile_coords(tile, img, y0, x0);
-        if (n > 0) mbar_wait(q_empty, (n - 1) & 1);     // the S product of the previous tile has read Q
-        mbar_expect_tx(q_full, Q_BYTES);
-#pragma unroll
-        for (int b = 0; b < 4; ++b) tma_load_4d(base + Q_OFF + b * QBOX, &mapQ, q_full, b * 64, x0, y0, img);
         for (int op = 0; op < 2; ++op)
           for (int g = 0; g < NG; ++g, ++it) {
+            if (op == 1 && g == 2) {
+              // Between V1 and V2 of this tile (both wait for the end of this tile's S product anyway): the next
+              // tile's Q tile, and an L2 prefetch of its first two K stages (their ring slots free up much later).
+              const int nxt = tq[(n + 1) % TQD];
+              if (nxt >= 0) {
+                mbar_wait(q_empty, n & 1);              // the S product of this tile has read Q
+                WSTAMP(4, n * 16 + 8);
+                load_q(nxt);
+                int img2, y2, x2;
+                tile_coords(nxt, img2, y2, x2);
+#pragma unroll
+                for (int g2 = 0; g2 < 2; ++g2)
+#pragma unroll
+                  for (int b = 0; b < 4; ++b)
+                    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(
+                                     reinterpret_cast<uint64_t>(&mapK)),
+                                 "r"(b * 64), "r"(x2 - 4), "r"(y2 - 4 + g2 * SG), "r"(img2)
+                                 : "memory");
+              }
+            }
             const int s = it % RING;
             if (it >= RING) mbar_wait(empty(s), ((it / RING) - 1) & 1);
+            WSTAMP(4, n * 16 + op * 4 + g);
             const uint32_t st = base + RING_OFF + s * STAGE_BYTES;
             mbar_expect_tx(full(s), STAGE_BYTES);
 #pragma unroll
@@ -189,12 +234,15 @@ lcab_window_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
     const uint32_t qb = base + Q_OFF;
     for (int tl = 0;; ++tl) {
       if (take_tile(tl) < 0) break;
+      if (lane == 0) WSTAMP(0, tl * 16);
       mbar_wait(q_full, tl & 1);
+      if (lane == 0) WSTAMP(0, tl * 16 + 1);
       // S = Q K^T, one key group (6 halo rows = 96 keys) per stage
       for (int g = 0; g < NG; ++g, ++it) {
         const int s = it % RING;
         mbar_wait(full(s), (it / RING) & 1);
         tc_fence_after();
+        if (lane == 0) WSTAMP(0, tl * 16 + 2 + g);
         if (elect_one()) {
           const uint32_t kb = base + RING_OFF + s * STAGE_BYTES;
           const uint32_t d = tmem_base + (uint32_t)(g * SG * HC);
@@ -215,12 +263,16 @@ lcab_window_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
         __syncwarp();
       }
       // O = P V, one halo row (16 keys) per k-step
+      if (lane == 0) WSTAMP(0, tl * 16 + 6);
       if (tl > 0) mbar_wait(o_empty, (tl - 1) & 1);      // the epilogue of the previous tile has drained O
+      if (lane == 0) WSTAMP(0, tl * 16 + 7);
       for (int g = 0; g < NG; ++g, ++it) {
         const int s = it % RING;
         mbar_wait(full(s), (it / RING) & 1);
+        if (lane == 0 && g == 0) WSTAMP(0, tl * 16 + 13);
         mbar_wait(p_full(g), tl & 1);
         tc_fence_after();
+        if (lane == 0) WSTAMP(0, tl * 16 + 8 + g);
         if (elect_one()) {
           const uint32_t vb = base + RING_OFF + s * STAGE_BYTES;
           const uint32_t d = tmem_base + O_COL;
@@ -237,26 +289,29 @@ lcab_window_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
         }
         __syncwarp();
       }
+      if (lane == 0) WSTAMP(0, tl * 16 + 12);
     }
-  } else {
-    // ---------------- softmax + epilogue (warps 2..5): thread = query = TMEM lane ----------------
+  } else if (warp < 2 + 4 * NSW) {
+    // ---------------- softmax (warps 2..13): thread = query = TMEM lane; NSW warps per lane quarter ----------------
     const int qd = warp & 3;                              // TMEM lane quarter = query rows 4 qd .. 4 qd + 3 of the tile
+    const int sub = (warp - 2) >> 2;                      // this warp's index among the quarter's softmax warps
+    const int qrow = qd * 32 + lane;                      // query index in the tile
     const int qyl = 4 * qd + (lane >> 3), qx = lane & 7;
     const uint32_t colmask = 0x1FFu << qx;                // halo columns qx .. qx + 8 are inside the window
     const uint32_t tlane = tmem_base + ((uint32_t)(qd * 32) << 16);
-    const uint32_t my_ep = base + EP_OFF + (uint32_t)(warp - 2) * EP_BYTES_W;
     const float c = p.c_log2;
+    const int r2_a = 2 * qd + sub, r2_b = r2_a + NSW;     // this warp's two heavy row pairs (rows 2 r2, 2 r2 + 1)
     for (int tl = 0;; ++tl) {
-      const int tile = take_tile(tl);
-      if (tile < 0) break;
-      int img, y0, x0;
-      tile_coords(tile, img, y0, x0);
-      // ---- pass 1: exact maximum over the 81 in-window logits (halo rows 4 qd .. 4 qd + 11, two rows per load)
+      if (take_tile(tl) < 0) break;
+      const int ds = warp == 2 ? 1 : (warp == 13 ? 2 : -1);
+      if (lane == 0 && ds > 0) WSTAMP(ds, tl * 16);
+      // ---- pass 1: exact maximum over the in-window logits of this warp's 4 halo rows (two rows per load)
       float m = -INFINITY;
       int waited = -1;
 #pragma unroll 1
-      for (int r2 = 0; r2 < 6; ++r2) {
-        const int hr = 4 * qd + 2 * r2;
+      for (int u = 0; u < 2; ++u) {
+        const int r2 = u == 0 ? r2_a : r2_b;
+        const int hr = 2 * r2;
         const int g = hr / SG;
         if (g > waited) {
           mbar_wait(s_full(g), tl & 1);
@@ -274,52 +329,90 @@ lcab_window_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
           if (rb && cok) m = fmaxf(m, v[16 + j]);
         }
       }
+      if (lane == 0 && ds > 0) WSTAMP(ds, tl * 16 + 1);
+      if (tl > 0) mbar_wait(sum_empty, (tl - 1) & 1);      // the epilogue has read the previous tile's sums (same buffer)
+      mx[sub * 128 + qrow] = m;                            // exchange with the other warps of this lane quarter
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + qd), "r"(32 * NSW) : "memory");
+#pragma unroll
+      for (int o = 0; o < NSW; ++o) m = fmaxf(m, mx[o * 128 + qrow]);
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + qd), "r"(32 * NSW) : "memory");   // all have read before anyone writes a sum
       for (int g = waited + 1; g < NG; ++g) mbar_wait(s_full(g), tl & 1);   // pass 2 writes into every key group
       tc_fence_after();
+      if (lane == 0 && ds > 0) WSTAMP(ds, tl * 16 + 2);
       const float mc = m * c;
-      // ---- pass 2: p = exp((s - m) / sqrt(C)); P (bf16 hi | mid) written over S, zeros outside the window
+      // ---- pass 2: p = exp((s - m) / sqrt(C)); P (bf16 hi | mid) written over S, zeros outside the window.  Row pairs
+      // outside the quarter's 12 rows (zero fill) are dealt round robin.
       float sum = 0.f;
 #pragma unroll 1
       for (int r2 = 0; r2 < 12; ++r2) {
         const int hr = 2 * r2;
-        uint32_t w[32];
-        if (hr >= 4 * qd && hr < 4 * qd + 12) {
-          float v[32];
-          tmem_ld32_nowait(tlane + (uint32_t)(hr * HC), v);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          const bool ra = (unsigned)(hr - qyl) <= 8u, rb = (unsigned)(hr + 1 - qyl) <= 8u;
+        const bool heavy = r2 == r2_a || r2 == r2_b;
+        const bool in_quarter = r2 >= 2 * qd && r2 < 2 * qd + 6;
+        if (heavy || (!in_quarter && r2 % NSW == sub)) {
+          uint32_t w[32];
+          if (heavy) {
+            float v[32];
+            tmem_ld32_nowait(tlane + (uint32_t)(hr * HC), v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const bool ra = (unsigned)(hr - qyl) <= 8u, rb = (unsigned)(hr + 1 - qyl) <= 8u;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const bool cok = (colmask >> j) & 1u;
-            v[j] = (ra && cok) ? ex2_approx(fmaf(v[j], c, -mc)) : 0.f;
-            v[16 + j] = (rb && cok) ? ex2_approx(fmaf(v[16 + j], c, -mc)) : 0.f;
-            sum += v[j] + v[16 + j];
-          }
-#pragma unroll
-          for (int h = 0; h < 2; ++h)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float a = v[16 * h + 2 * j], b = v[16 * h + 2 * j + 1];
-              const uint32_t hi = pack_bf16x2(a, b);
-              w[16 * h + j] = hi;
-              w[16 * h + 8 + j] = pack_bf16x2(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xFFFF0000u));
+            for (int j = 0; j < 16; ++j) {
+              const bool cok = (colmask >> j) & 1u;
+              v[j] = (ra && cok) ? ex2_approx(fmaf(v[j], c, -mc)) : 0.f;
+              v[16 + j] = (rb && cok) ? ex2_approx(fmaf(v[16 + j], c, -mc)) : 0.f;
+              sum += v[j] + v[16 + j];
             }
-        } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) w[j] = 0u;
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float a = v[16 * h + 2 * j], b = v[16 * h + 2 * j + 1];
+                const uint32_t hi = pack_bf16x2(a, b);
+                w[16 * h + j] = hi;
+                w[16 * h + 8 + j] = pack_bf16x2(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xFFFF0000u));
+              }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) w[j] = 0u;
+          }
+          tmem_st32(tlane + (uint32_t)(hr * HC), w);
         }
-        tmem_st32(tlane + (uint32_t)(hr * HC), w);
-        if (r2 % 3 == 2) {                                 // the 6 halo rows of key group r2 / 3 are complete
+        if (r2 % 3 == 2) {                                 // this warp's share of key group r2 / 3 is complete
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(p_full(r2 / 3));
+          if (lane == 0 && ds > 0) WSTAMP(ds, tl * 16 + 3 + r2 / 3);
         }
       }
-      const float inv = 1.f / sum;
-      // ---- epilogue: O / sum -> swizzled staging -> TMA store of this warp's 4 x 8 query patch
+      // ---- partial sum of this warp's rows -> epilogue warp of the quarter
+      mx[sub * 128 + qrow] = sum;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sum_full);
+    }
+  } else {
+    // ---------------- epilogue (warps 14..17): O / sum -> swizzled staging -> TMA store of a 4 x 8 query patch ----
+    const int qd = warp & 3;
+    const int qrow = qd * 32 + lane;
+    const uint32_t tlane = tmem_base + ((uint32_t)(qd * 32) << 16);
+    const uint32_t my_ep = base + EP_OFF + (uint32_t)(warp - (2 + 4 * NSW)) * EP_BYTES_W;
+    for (int tl = 0;; ++tl) {
+      const int tile = take_tile(tl);
+      if (tile < 0) break;
+      int img, y0, x0;
+      tile_coords(tile, img, y0, x0);
+      if (lane == 0 && warp == 2 + 4 * NSW) WSTAMP(3, tl * 16);
+      mbar_wait(sum_full, tl & 1);
+      float tot = 0.f;
+#pragma unroll
+      for (int o = 0; o < NSW; ++o) tot += mx[o * 128 + qrow];
+      const float inv = 1.f / tot;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sum_empty);
+      if (lane == 0 && warp == 2 + 4 * NSW) WSTAMP(3, tl * 16 + 1);
       mbar_wait(o_full, tl & 1);
       tc_fence_after();
+      if (lane == 0 && warp == 2 + 4 * NSW) WSTAMP(3, tl * 16 + 2);
 #pragma unroll 1
       for (int cq = 0; cq < 4; ++cq) {
         float v[32];
@@ -329,6 +422,7 @@ lcab_window_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(o_empty);
+          if (lane == 0 && warp == 2 + 4 * NSW) WSTAMP(3, tl * 16 + 3);
         }
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging buffer free again
         __syncwarp();
@@ -392,6 +486,7 @@ struct WtDev {
 };
 WtDev g_wt_dev[64];
 int g_wt_sm_limit = 0;
+int g_wt_debug = 0;
 
 }  // namespace
 
@@ -401,6 +496,21 @@ extern "C" {
 int di_lcab_window_tc_set_sm_limit(int n) {
   DI_CHECK_ARG(n >= 0, "di_lcab_window_tc_set_sm_limit: n must be >= 0");
   g_wt_sm_limit = n;
+  return DI_OK;
+}
+
+// Pipeline trace of CTA 0 (diagnostics, tools/trace_window.py): enable, run ONE launch, read 6 x 256 clock64 stamps
+// (rows: 0 MMA issuer, 1 / 2 softmax warps 2 / 9, 3 epilogue warp 10, 4 producer; 16 stamps per tile).
+int di_lcab_window_tc_set_debug(int on) {
+  g_wt_debug = on;
+  return DI_OK;
+}
+int di_lcab_window_tc_debug_read(long long* host_buf) {
+  DI_CHECK_ARG(host_buf, "di_lcab_window_tc_debug_read: null buffer");
+  if (cudaMemcpyFromSymbol(host_buf, g_wdbg, sizeof(long long) * WDBG_SLOTS * WDBG_N) != cudaSuccess) {
+    di_set_error("di_lcab_window_tc_debug_read: copy failed");
+    return DI_ERR_LAUNCH;
+  }
   return DI_OK;
 }
 
@@ -448,6 +558,7 @@ int di_lcab_window_tc_f32(const void* q, int ldq, const void* k, int ldk, const 
   p.tiles_y = di_cdiv(H, QR);
   p.num_tiles = N * p.tiles_x * p.tiles_y;
   p.c_log2 = 1.4426950408889634f / sqrtf((float)C);
+  p.dbg = g_wt_debug;
   p.sched = tc::sched_slot(stream);
   if (!p.sched) {
     di_set_error("di_lcab_window_tc_f32: cannot resolve the scheduler buffer");

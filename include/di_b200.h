@@ -118,6 +118,8 @@ int di_lcab_window_pre_f32(const float* q, int ldq, const float* k, int ldk, con
 int di_lcab_window_tc_f32(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, float* out, int ldo,
                           int N, int H, int W, int C, cudaStream_t stream);
 int di_lcab_window_tc_set_sm_limit(int n); /* persistent grid of the kernel above uses at most n CTAs (0 = all) */
+int di_lcab_window_tc_set_debug(int on);    /* diagnostics: clock64 pipeline trace of CTA 0 ... */
+int di_lcab_window_tc_debug_read(long long* host_buf); /* ... 6 x 256 stamps (tools/trace_window.py) */
 
 /* test/diagnostic hook: 1 = always use the FFMA window kernel, 0 = tensor-core (mma.sync 3xTF32) kernel when
  * ksize == 9 and C % 32 == 0 (default) */
