@@ -109,9 +109,9 @@ def build_oracle(neck_sd=None, head_sd=None):
     return neck, head
 
 
-def host_frame(batch, cloud, seed):
+def host_frame(batch, cloud, seed, n_points=250000):
     from deepinteraction_b200 import synth
-    fr = synth.make_frame_batch(seed, batch=batch, cloud=cloud)
+    fr = synth.make_frame_batch(seed, batch=batch, cloud=cloud, n_points=n_points)
     pin = lambda t: t.contiguous().pin_memory() if torch.cuda.is_available() else t
     pm = fr['pts_metas']
     fr['img_feats'], fr['pts_feats'] = pin(fr['img_feats']), pin(fr['pts_feats'])
@@ -136,9 +136,13 @@ def h2d_bytes(fr):
     return int(sum(t.numel() * t.element_size() for t in ts))
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the launches of one forward, from the ncu
-# --set full captures summarised under profiles/ (r1_ncu_window_pre.md: 4 image launches 256.6 MB, 2 BEV 51.2 MB).
-NCU_TRAFFIC = {'di_lcab_window_pre_f32': (4 * 256.57e6 + 2 * 51.23e6) / 6}
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernels, measured by `ncu --set full`
+    on the bench command of this build and written by tools/ncu_traffic.py (kernel -> average bytes per launch)."""
+    p = os.path.join(ROOT, 'profiles', 'r2_traffic.json')
+    if os.path.exists(p):
+        return json.load(open(p)), 'profiles/r2_traffic.json'
+    return {}, None
 
 
 def forward(neck, head, fr):
@@ -248,6 +252,8 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--profile-steps', type=int, default=3)
     ap.add_argument('--inflight', type=int, default=3, help='independent frames in flight per GPU (CUDA streams)')
+    ap.add_argument('--frames', type=int, default=9, help='distinct synthetic frames (different point / pillar counts) cycled '
+                    'through the timed regions, each in its own device buffers')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -267,16 +273,27 @@ def main():
     from deepinteraction_b200 import ops
 
     neck, head = build_models(device)
-    fr_host = host_frame(args.batch, args.cloud, SEED + rank)
-    fr_dev = h2d(fr_host, device)
-    torch.cuda.synchronize()
     W, K = max(args.warmup, 3), args.steps
     from deepinteraction_b200.pipeline import FramePipeline
-    pipe = FramePipeline(neck, head, depth=max(args.inflight, 1), device=device)
+    depth = max(args.inflight, 1)
+    pipe = FramePipeline(neck, head, depth=depth, device=device)
+    # NF distinct frames (different seeds, point counts and therefore pillar counts), each in its own device buffers;
+    # NF is a multiple of the pipeline depth so that a frame always runs on the same stream (one graph per frame set).
+    NF = max(1, args.frames // depth) * depth if args.frames >= depth else args.frames
+    frames_host = [host_frame(args.batch, args.cloud, SEED + 1000 * rank + i, n_points=int(250000 * (0.86 + 0.035 * i)))
+                   for i in range(NF)]
+    frames_dev = [h2d(f, device) for f in frames_host]
+    fr_host, fr_dev = frames_host[0], frames_dev[0]
+    n_pillars = [int(f['pts_metas']['pillars'].shape[0]) for f in frames_host]
+    n_points = [int(sum(p.shape[0] for p in f['pts_metas']['pts'])) for f in frames_host]
+    torch.cuda.synchronize()
     out = forward(neck, head, fr_dev)                   # one plain call (default stream), then per-stream graph capture
-    pipe.warm(fr_dev, rounds=3)
-    for _ in range(W):
-        out = pipe.submit(fr_dev)[0]
+    for _ in range(3):                                  # every (frame set, stream) pair captures its graphs
+        for i in range(NF):
+            pipe.submit(frames_dev[i], stream_index=i % depth)
+    pipe.join()
+    for i in range(W):
+        out = pipe.submit(frames_dev[i % NF], stream_index=i % depth)[0]
     pipe.join()
     torch.cuda.synchronize()
 
@@ -292,14 +309,14 @@ def main():
             return float(t.item())
         return ms
 
-    # ---- timed region 1: inputs resident in HBM --------------------------------------------------------
+    # ---- timed region 1: inputs resident in HBM (NF distinct frames cycled) ------------------------------
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
         barrier()
         l0 = ops.LAUNCHES[0]
         e0.record()
-        for _ in range(K):
-            out = pipe.submit(fr_dev)[0]
+        for i in range(K):
+            out = pipe.submit(frames_dev[i % NF], stream_index=i % depth)[0]
         pipe.join()
         e1.record()
         barrier()
@@ -308,38 +325,53 @@ def main():
         # ---- timed region 2: end to end through the plug-in API, host buffers ------------------------------
         # NSETS device input sets; the host->device copy of a later step runs on a copy stream while earlier steps
         # compute on the pipeline's streams; every step's result goes back to pinned host memory on its own stream.
-        NSETS = pipe.depth + 1
-        outs_host = [{k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items()} for _ in range(pipe.depth)]
+        # The feature maps land in persistent per-set buffers; the per-frame pillar / point arrays (their sizes change
+        # from frame to frame) land in the leading rows of per-set capacity buffers and are passed as exact-size views.
+        NSETS = depth + 1
+        outs_host = [{k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items()} for _ in range(depth)]
         copy_stream = torch.cuda.Stream()
-
-        def flat(fr):
-            pm = fr['pts_metas']
-            return [fr['img_feats'], fr['pts_feats'], pm['pillars'], pm['pillar_coors'], pm['pillars_num_points']] + \
-                list(pm['pts'])
-        sets = [h2d(fr_host, device) for _ in range(NSETS)]
+        cap_p, cap_n = max(n_pillars), max(max(int(p.shape[0]) for p in f['pts_metas']['pts']) for f in frames_host)
+        pm0 = fr_host['pts_metas']
+        mk = lambda t, n: torch.empty((n,) + tuple(t.shape[1:]), dtype=t.dtype, device=device)
+        sets = [dict(img_feats=torch.empty_like(fr_dev['img_feats']), pts_feats=torch.empty_like(fr_dev['pts_feats']),
+                     pillars=mk(pm0['pillars'], cap_p), pillar_coors=mk(pm0['pillar_coors'], cap_p),
+                     pillars_num_points=mk(pm0['pillars_num_points'], cap_p),
+                     pts=[mk(p, cap_n) for p in pm0['pts']]) for _ in range(NSETS)]
         torch.cuda.synchronize()
         done = [None] * NSETS
         ready = [torch.cuda.Event() for _ in range(NSETS)]
+        views = [None] * NSETS
 
         def issue_copy(i):
-            bi = i % NSETS
+            bi, fh = i % NSETS, frames_host[i % NF]
+            st, pm = sets[bi], fh['pts_metas']
             with torch.cuda.stream(copy_stream):
                 if done[bi] is not None:
                     copy_stream.wait_event(done[bi])          # the forward that read this set has finished
-                for dst, src in zip(flat(sets[bi]), flat(fr_host)):
-                    dst.copy_(src, non_blocking=True)
+                st['img_feats'].copy_(fh['img_feats'], non_blocking=True)
+                st['pts_feats'].copy_(fh['pts_feats'], non_blocking=True)
+                npl = pm['pillars'].shape[0]
+                v = dict(pillars=st['pillars'][:npl], pillar_coors=st['pillar_coors'][:npl],
+                         pillars_num_points=st['pillars_num_points'][:npl], pts=[])
+                for k_ in ('pillars', 'pillar_coors', 'pillars_num_points'):
+                    v[k_].copy_(pm[k_], non_blocking=True)
+                for dst, src in zip(st['pts'], pm['pts']):
+                    d = dst[:src.shape[0]]
+                    d.copy_(src, non_blocking=True)
+                    v['pts'].append(d)
+                views[bi] = dict(img_feats=st['img_feats'], pts_feats=st['pts_feats'], img_metas=fh['img_metas'], pts_metas=v)
                 ready[bi].record(copy_stream)
 
         def step(i):
             bi = i % NSETS
-            o, ev, s = pipe.submit(sets[bi], wait_event=ready[bi], stream_index=i % pipe.depth)
+            o, ev, s_ = pipe.submit(views[bi], wait_event=ready[bi], stream_index=i % depth)
             done[bi] = ev
-            with torch.cuda.stream(s):
+            with torch.cuda.stream(s_):
                 for k_, v in o.items():
-                    outs_host[i % pipe.depth][k_].copy_(v, non_blocking=True)
+                    outs_host[i % depth][k_].copy_(v, non_blocking=True)
 
         for r in range(3):                                       # every (input set, stream) pair owns its graphs
-            for i in range(NSETS * pipe.depth):
+            for i in range(NSETS * depth):
                 issue_copy(i)
                 step(i)
         pipe.join()
@@ -398,7 +430,13 @@ def main():
     torch.cuda.synchronize()
     agg = {}
     shapes = {}
-    for name, a, b, nbytes, flops in ops.PROFILE[0]:
+    mods = {}
+    for name, a, b, nbytes, flops, mod in ops.PROFILE[0]:
+        if mod is not None:
+            md = mods.setdefault(mod[0], dict(ms=0.0, bytes=0, flops=0, launches=0, seen=set()))
+            md['ms'] += a.elapsed_time(b)
+            md['launches'] += 1
+            md['bytes'], md['flops'] = mod[1], mod[2]
         sd = shapes.setdefault((name, nbytes, flops), [0, 0.0])
         sd[0] += 1
         sd[1] += a.elapsed_time(b)
@@ -429,8 +467,23 @@ def main():
         roof = dict(bound='tensor', achieved=top['tflops'], peak=pk['tf'], unit='TFLOP/s', frac=top['tflops'] / pk['tf'])
     else:
         roof = dict(bound='hbm', achieved=top['gbs'], peak=pk['hbm'], unit='GB/s', frac=top['gbs'] / pk['hbm'])
-    roof.update(kernel=top['name'], traffic=NCU_TRAFFIC.get(top['name']), peak_source=pk['src'], share_of_step=top['share'],
-                avg_launch_us=top['avg_us'])
+    traffic, traffic_src = ncu_traffic()
+    roof.update(kernel=top['name'], traffic=traffic.get(top['name']), traffic_source=traffic_src, peak_source=pk['src'],
+                share_of_step=top['share'], avg_launch_us=top['avg_us'])
+    # per-MODULE roofline with the module-boundary numerators of SURVEY.md 8(d): time = sum of the module's kernel
+    # durations (eager, serialised pass), calls = instances per frame
+    calls = {'MMRI_I2P': 2, 'LCAB_self_bev': 2, 'P_out_proj+P_integration': 2, 'MMRI_P2I': 2, 'LCAB_self_img': 2,
+             'I_out_proj+I_integration': 2, 'ImageRCNNBlock': 2, 'PointRCNNBlock': 2, 'prediction_heads': 5}
+    modules = []
+    for name, md in mods.items():
+        n = calls.get(name, 1) * args.profile_steps
+        us = md['ms'] / n * 1e3
+        gbs = md['bytes'] / (us * 1e-6) / 1e9 if us > 0 else 0.0
+        tfl = md['flops'] / (us * 1e-6) / 1e12 if us > 0 else 0.0
+        modules.append(dict(module=name, calls_per_frame=calls.get(name, 1), us_per_call=us, launches_per_call=md['launches'] / n,
+                            bytes_mb=md['bytes'] / 1e6, gflop=md['flops'] / 1e9, gbs=gbs, frac_of_hbm_peak=gbs / pk['hbm'],
+                            tflops=tfl, frac_of_bf16_peak=tfl / pk['tf']))
+    modules.sort(key=lambda m: -m['us_per_call'] * m['calls_per_frame'])
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
@@ -460,16 +513,20 @@ def main():
                             parallelism=f'dp{world} (independent frames, no data-path collective)',
                             frames_in_flight=pipe.depth,
                             arithmetic='fp32 in/out and accumulate; dense products as error-compensated splits on tcgen05 '
-                                       '(bf16 hi+mid x3 in the encoder, 3xTF32 in the decoder), mma.sync bf16 split in the '
+                                       '(bf16 hi+mid x3 in the encoder, 3xTF32 in the decoder), tcgen05 bf16 hi+mid x3 in the '
                                        'window attention; measured vs the fp32 oracle: see cpu_baseline.max_rel_err_vs_gpu',
-                            l2='inputs (204 MB/frame) larger than L2; no flush'),
+                            l2='inputs (204 MB/frame, %d distinct frames in their own buffers) larger than L2; no flush' % NF,
+                            frames=dict(distinct=NF, pillars=n_pillars, points=n_points,
+                                        note='frames differ in seed, point and pillar counts; CUDA graphs are keyed on '
+                                             'bucketed capacities, live counts are read from device memory')),
                 clocks=clocks,
-                e2e=dict(value=e2e_value, unit='frames/s', h2d_bytes_per_step=h2d_bytes(fr_host),
+                e2e=dict(value=e2e_value, unit='frames/s', h2d_bytes_per_step=int(np.mean([h2d_bytes(f) for f in frames_host])),
+                         bound='PCIe host->device copies (%.0f MB/frame of fp32 feature maps)' % (h2d_bytes(fr_host) / 1e6),
                          d2h_bytes_per_step=int(sum(v.numel() * v.element_size() for v in out.values())),
                          ms_per_step=ms_e2e / K, host_launch_ms_per_step=host_fwd / K * 1e3,
                          overlap='H2D of step i+1 on a copy stream (depth+1 device input sets) while earlier steps compute'),
                 gpu_launches=launches, launches_per_step=launches / K, stages=stages, cuda_graph=bool(di_graph.ENABLED[0] and os.environ.get('DI_B200_GRAPH', '1') != '0'),
-                roofline=roof, cpu_baseline=cpu,
+                roofline=roof, modules=modules, cpu_baseline=cpu,
                 kernels=kernels[:12])
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -44,10 +44,10 @@ SIGNATURES = {
     'di_locatt_ck2c_ori_f32': [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     'di_locatt_ck2c_loc_f32': [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     # geometry.cu
-    'di_gather_rows_f32': [_p, _p, _p, _i, _i, _i, _i, _p],
-    'di_scatter_rows_f32': [_p, _p, _p, _p, _i, _i, _i, _i, _p],
-    'di_i2p_attend_f32': [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
-    'di_depth_scatter': [_p, _i, _i, _p, _p, _i, _i, _i, _i, _i, _p],
+    'di_gather_rows_f32': [_p, _p, _p, _i, _i, _i, _i, _p, _p],
+    'di_scatter_rows_f32': [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p],
+    'di_i2p_attend_f32': [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p],
+    'di_depth_scatter': [_p, _i, _i, _p, _p, _i, _i, _i, _i, _i, _p, _p],
     'di_depth_complete': [_p, _p, _p, _p, _i, _i, _i, _p],
     'di_lift_grid': [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _fp, _p],
     'di_bev_sample_f32': [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p],

@@ -65,9 +65,10 @@ __global__ void __launch_bounds__(256)
 i2p_attend_kernel(const float* __restrict__ qk, const float* __restrict__ pillars, const int* __restrict__ npts,
                   const int* __restrict__ coors, const float* __restrict__ proj, const float* __restrict__ img,
                   float* __restrict__ s_out, int* __restrict__ cnt_out, int P, int T, int pdim, int V, int h, int w,
-                  int C, float H_in, float W_in) {
+                  int C, float H_in, float W_in, const int* __restrict__ n_dev) {
   const int lane = threadIdx.x & 31;
   const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n_dev) P = min(P, __ldg(n_dev));          // capacity-sized arrays: the live count sits in device memory
   if (p >= P) return;
   const int b = coors[p * 4];
   const int np = min(npts[p], T);
@@ -149,9 +150,10 @@ i2p_attend_kernel(const float* __restrict__ qk, const float* __restrict__ pillar
 
 // rows[p,:] = map[b, y, x, :]   (coors = [b, z, y, x])
 __global__ void gather_rows_kernel(const float* __restrict__ map, const int* __restrict__ coors, float* __restrict__ rows,
-                                   int P, int Y, int X, int C) {
+                                   int P, int Y, int X, int C, const int* __restrict__ n_dev) {
   int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
+  if (n_dev) P = min(P, __ldg(n_dev));
   if (p >= P) return;
   const int* c4 = coors + p * 4;
   const float* src = map + (((size_t)c4[0] * Y + c4[2]) * X + c4[3]) * C;
@@ -160,9 +162,11 @@ __global__ void gather_rows_kernel(const float* __restrict__ map, const int* __r
 
 // map[b, y, x, :] = cnt[p] > 0 ? rows[p,:] : 0
 __global__ void scatter_rows_kernel(const float* __restrict__ rows, const int* __restrict__ cnt,
-                                    const int* __restrict__ coors, float* __restrict__ map, int P, int Y, int X, int C) {
+                                    const int* __restrict__ coors, float* __restrict__ map, int P, int Y, int X, int C,
+                                    const int* __restrict__ n_dev) {
   int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
+  if (n_dev) P = min(P, __ldg(n_dev));
   if (p >= P) return;
   const int* c4 = coors + p * 4;
   float* dst = map + (((size_t)c4[0] * Y + c4[2]) * X + c4[3]) * C;
@@ -176,8 +180,10 @@ __global__ void scatter_rows_kernel(const float* __restrict__ rows, const int* _
 // LAST point in order for duplicate pixels (the CPU index_put_ rule the oracle follows).
 // ------------------------------------------------------------------------------------------------
 __global__ void depth_scatter_kernel(const float* __restrict__ pts, int stride, int n, const float* __restrict__ proj,
-                                     unsigned long long* __restrict__ keys, int V, int h, int w, float H_in, float W_in) {
+                                     unsigned long long* __restrict__ keys, int V, int h, int w, float H_in, float W_in,
+                                     const int* __restrict__ n_dev) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_dev) n = min(n, __ldg(n_dev));
   if (i >= n) return;
   float x = pts[(size_t)i * stride], y = pts[(size_t)i * stride + 1], z = pts[(size_t)i * stride + 2];
   for (int v = 0; v < V; ++v) {
@@ -482,20 +488,23 @@ bev_sample_kernel(const float* __restrict__ bev, const float2* __restrict__ grid
 
 extern "C" {
 
-int di_gather_rows_f32(const float* map, const int* coors, float* rows, int P, int Y, int X, int C,
+// n_dev (all four entry points below; may be NULL): device pointer to the LIVE element count when the arrays are
+// allocated at capacity P / n -- the kernels then process min(capacity, *n_dev) elements.  This keeps launch
+// configurations and buffer addresses independent of the per-frame pillar / point counts (CUDA-graph replay).
+int di_gather_rows_f32(const float* map, const int* coors, float* rows, int P, int Y, int X, int C, const int* n_dev,
                        cudaStream_t stream) {
   DI_CHECK_ARG(map && coors && rows && P >= 0 && C % 4 == 0, "di_gather_rows_f32: bad argument");
   if (P == 0) return DI_OK;
-  gather_rows_kernel<<<di_cdiv(P, 8), 256, 0, stream>>>(map, coors, rows, P, Y, X, C);
+  gather_rows_kernel<<<di_cdiv(P, 8), 256, 0, stream>>>(map, coors, rows, P, Y, X, C, n_dev);
   DI_CHECK_LAUNCH("di_gather_rows_f32");
   return DI_OK;
 }
 
 int di_scatter_rows_f32(const float* rows, const int* cnt, const int* coors, float* map, int P, int Y, int X, int C,
-                        cudaStream_t stream) {
+                        const int* n_dev, cudaStream_t stream) {
   DI_CHECK_ARG(map && coors && rows && cnt && P >= 0 && C % 4 == 0, "di_scatter_rows_f32: bad argument");
   if (P == 0) return DI_OK;
-  scatter_rows_kernel<<<di_cdiv(P, 8), 256, 0, stream>>>(rows, cnt, coors, map, P, Y, X, C);
+  scatter_rows_kernel<<<di_cdiv(P, 8), 256, 0, stream>>>(rows, cnt, coors, map, P, Y, X, C, n_dev);
   DI_CHECK_LAUNCH("di_scatter_rows_f32");
   return DI_OK;
 }
@@ -505,27 +514,27 @@ int di_scatter_rows_f32(const float* rows, const int* cnt, const int* coors, flo
 // proj [B,V,12]: rows 0..2 of lidar2img[b,v] @ undo-augmentation; img [B*V,h,w,C] pixel-major.
 int di_i2p_attend_f32(const float* qk, const float* pillars, const int* npts, const int* coors, const float* proj,
                       const float* img, float* s_out, int* cnt_out, int P, int T, int pdim, int V, int h, int w, int C,
-                      int H_in, int W_in, cudaStream_t stream) {
+                      int H_in, int W_in, const int* n_dev, cudaStream_t stream) {
   DI_CHECK_ARG(qk && pillars && npts && coors && proj && img && s_out && cnt_out, "di_i2p_attend_f32: null pointer");
   DI_CHECK_ARG(C % 4 == 0 && C <= 512 && pdim >= 3 && T * V <= 256, "di_i2p_attend_f32: unsupported shape (C=%d T=%d V=%d)", C, T, V);
   if (P == 0) return DI_OK;
   dim3 grid(di_cdiv(P, 8));
   if (C <= 128)
-    i2p_attend_kernel<1><<<grid, 256, 0, stream>>>(qk, pillars, npts, coors, proj, img, s_out, cnt_out, P, T, pdim, V, h, w, C, (float)H_in, (float)W_in);
+    i2p_attend_kernel<1><<<grid, 256, 0, stream>>>(qk, pillars, npts, coors, proj, img, s_out, cnt_out, P, T, pdim, V, h, w, C, (float)H_in, (float)W_in, n_dev);
   else if (C <= 256)
-    i2p_attend_kernel<2><<<grid, 256, 0, stream>>>(qk, pillars, npts, coors, proj, img, s_out, cnt_out, P, T, pdim, V, h, w, C, (float)H_in, (float)W_in);
+    i2p_attend_kernel<2><<<grid, 256, 0, stream>>>(qk, pillars, npts, coors, proj, img, s_out, cnt_out, P, T, pdim, V, h, w, C, (float)H_in, (float)W_in, n_dev);
   else
-    i2p_attend_kernel<4><<<grid, 256, 0, stream>>>(qk, pillars, npts, coors, proj, img, s_out, cnt_out, P, T, pdim, V, h, w, C, (float)H_in, (float)W_in);
+    i2p_attend_kernel<4><<<grid, 256, 0, stream>>>(qk, pillars, npts, coors, proj, img, s_out, cnt_out, P, T, pdim, V, h, w, C, (float)H_in, (float)W_in, n_dev);
   DI_CHECK_LAUNCH("di_i2p_attend_f32");
   return DI_OK;
 }
 
 // keys [V,h,w] uint64 must be zeroed by the caller; one call per sample (its points + its V projections).
 int di_depth_scatter(const float* pts, int stride, int n, const float* proj, unsigned long long* keys, int V, int h,
-                     int w, int H_in, int W_in, cudaStream_t stream) {
+                     int w, int H_in, int W_in, const int* n_dev, cudaStream_t stream) {
   DI_CHECK_ARG(pts && proj && keys && stride >= 3 && n >= 0, "di_depth_scatter: bad argument");
   if (n == 0) return DI_OK;
-  depth_scatter_kernel<<<di_cdiv(n, 256), 256, 0, stream>>>(pts, stride, n, proj, keys, V, h, w, (float)H_in, (float)W_in);
+  depth_scatter_kernel<<<di_cdiv(n, 256), 256, 0, stream>>>(pts, stride, n, proj, keys, V, h, w, (float)H_in, (float)W_in, n_dev);
   DI_CHECK_LAUNCH("di_depth_scatter");
   return DI_OK;
 }

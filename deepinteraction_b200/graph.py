@@ -14,6 +14,12 @@ tensors in place (no staging copy of the 200 MB of feature maps), and frames sub
 (pipeline.FramePipeline) get their own graph and output buffers, so independent frames can be in flight together.
 A caller that passes fresh tensors every frame simply stays on the eager path; one that cycles through a few input
 sets (double / triple buffering) gets one graph per set.
+
+SHAPE INDEPENDENCE.  The per-frame pillar / point arrays change their row counts every frame.  They are `staged`:
+the graph owns buffers at a bucketed CAPACITY, every replay copies the live rows in (device-to-device, ~10 MB) and
+uploads the live counts with the other host constants; the kernels read the counts from device memory (`n_dev`
+arguments of the C ABI).  The signature therefore holds capacities, not counts, and one graph serves every frame
+whose counts fit its buckets.
 """
 import collections
 import os
@@ -26,7 +32,7 @@ ENABLED = [os.environ.get('DI_B200_GRAPH', '1') != '0']
 
 
 class GraphCache:
-    def __init__(self, max_entries=16):
+    def __init__(self, max_entries=64):
         self.entries = collections.OrderedDict()
         self.seen = collections.OrderedDict()
         self.max_entries = max_entries
@@ -35,23 +41,30 @@ class GraphCache:
         self.entries.clear()
         self.seen.clear()
 
-    def run(self, sig, inputs, host_consts, fn):
-        """inputs: list of device tensors; host_consts: list of small CPU tensors; fn(inputs, consts) -> pytree of
-        tensors.  Returns fn's result (eager) or the graph's static outputs (replay)."""
-        sig = (sig, torch.cuda.current_stream().cuda_stream, tuple(t.data_ptr() for t in inputs))
+    def run(self, sig, inputs, host_consts, fn, staged=(), caps=()):
+        """inputs: list of device tensors bound by address; host_consts: list of small CPU tensors; staged: device
+        tensors whose leading dimension varies per frame, caps[i] >= staged[i].shape[0] their bucketed capacities
+        (part of the signature).  fn(inputs, consts, staged_bufs) -> pytree of tensors; staged_bufs are ALWAYS capacity
+        buffers (also on the eager path, so that eager and replayed frames run the very same kernels on the very same
+        shapes and agree bit for bit); the live counts travel through `consts`.
+        Returns fn's result (eager) or the graph's static outputs (replay)."""
+        sig = (sig, tuple(caps), torch.cuda.current_stream().cuda_stream, tuple(t.data_ptr() for t in inputs))
         ent = self.entries.get(sig)
         if ent is None:
             n = self.seen.get(sig, 0) + 1
             self.seen[sig] = n
-            while len(self.seen) > 64:
+            while len(self.seen) > 256:
                 self.seen.popitem(last=False)
             if n < 2 or not ENABLED[0]:
                 dev = inputs[0].device
-                return fn(inputs, [c.to(dev, non_blocking=True) for c in host_consts])
-            ent = self._capture(sig, inputs, host_consts, fn)
+                return fn(inputs, [c.to(dev, non_blocking=True) for c in host_consts], self._pad(staged, caps, dev))
+            ent = self._capture(sig, inputs, host_consts, fn, staged, caps)
         else:
             self.entries.move_to_end(sig)
-        g, s_in, s_c, pinned, out, launches, flip = ent
+        g, s_in, s_c, pinned, out, launches, flip, s_st = ent
+        for buf, t in zip(s_st, staged):       # live rows of the per-frame arrays into the graph's capacity buffers
+            if t.shape[0]:
+                buf[:t.shape[0]].copy_(t, non_blocking=True)
         k = flip[0] = flip[0] ^ 1
         if flip[1 + k] is not None:
             flip[1 + k].synchronize()          # the H2D copy that last read this pinned set has run (host may be ahead)
@@ -65,9 +78,20 @@ class GraphCache:
         ops.LAUNCHES[0] += launches
         return out
 
-    def _capture(self, sig, inputs, host_consts, fn):
+    @staticmethod
+    def _pad(staged, caps, dev):
+        out = []
+        for t, cap in zip(staged, caps):
+            buf = torch.zeros((cap,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+            if t.shape[0]:
+                buf[:t.shape[0]].copy_(t, non_blocking=True)
+            out.append(buf)
+        return out
+
+    def _capture(self, sig, inputs, host_consts, fn, staged=(), caps=()):
         dev = inputs[0].device
         s_in = list(inputs)                    # bound to the caller's buffers (kept alive by the entry)
+        s_st = self._pad(staged, caps, dev)
         s_c = [torch.empty(c.shape, dtype=c.dtype, device=dev) for c in host_consts]
         pinned = [[torch.empty(c.shape, dtype=c.dtype).pin_memory() for c in host_consts] for _ in range(2)]
         for dst, c in zip(s_c, host_consts):
@@ -76,15 +100,15 @@ class GraphCache:
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(cur)
         with torch.cuda.stream(side):          # warm-up outside capture (lazy module loads, func attributes, packs)
-            fn(s_in, s_c)
+            fn(s_in, s_c, s_st)
         cur.wait_stream(side)
         torch.cuda.synchronize(dev)
         g = torch.cuda.CUDAGraph()
         n0 = ops.LAUNCHES[0]
         with torch.cuda.graph(g):
-            out = fn(s_in, s_c)
+            out = fn(s_in, s_c, s_st)
         launches = ops.LAUNCHES[0] - n0
-        ent = (g, s_in, s_c, pinned, out, launches, [0, None, None])
+        ent = (g, s_in, s_c, pinned, out, launches, [0, None, None], s_st)
         self.entries[sig] = ent
         while len(self.entries) > self.max_entries:
             self.entries.popitem(last=False)

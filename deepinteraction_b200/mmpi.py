@@ -351,7 +351,7 @@ class DeepInteractionDecoder(nn.Module):
         inputs = [pts_conv, new_pts, img]
         sig = (tuple(tuple(t.shape) for t in inputs), in_hw, id(self._pack))
 
-        def fn(ins, consts):
+        def fn(ins, consts, staged):
             return self._schedule(ins[0], ins[1], ins[2], in_hw, consts[0], consts[1], None)
         return self._graphs.run(sig, inputs, [proj_h, aux_h], fn)
 
@@ -373,6 +373,9 @@ class DeepInteractionDecoder(nn.Module):
         assert (Y, X) == (self.y_size, self.x_size), 'BEV size must equal test_cfg grid_size // out_size_factor'
         HW, P, V, K, H = Y * X, self.num_proposals, self.num_views, self.num_classes_heat, self.num_heads
         dev_ = pts_conv.device
+        # module tags + module-boundary bytes for bench.py's roofline table; no effect otherwise
+        F_b, F_i = 4 * B * HW * C, 4 * img.numel()
+        ops._MODULE[0] = ('heatmap_heads+nms+topk+query_init', 2 * F_b + 2 * 4 * K * B * HW, 2 * 2 * B * HW * 9 * C * (C + K))
         # heatmaps, NMS, top-k, query init
         w0, b0, w1, b1 = pk['heatmap_head']
         Kp = w1.shape[0]
@@ -387,6 +390,8 @@ class DeepInteractionDecoder(nn.Module):
         if debug is not None:
             debug.update(top=top, heat=heat, query_feat0=q.clone(), query_pos0=qpos.clone())
         # transformer decoder layer
+        ops._MODULE[0] = ('TransformerDecoderLayer (query x BEV cross-attn)', F_b + 4 * (2 * C * C + 2 * HW * C),
+                          2 * B * HW * C * 2 * C + 4 * B * P * HW * C)
         pw1, pb1, pw2, pb2 = pk['self_pe']
         qpe = ops.linear([ops.linear([qpos], pw1, pb1, ops.ACT_RELU)], pw2, pb2)
         w, b, wo, bo = pk['self_attn']
@@ -401,6 +406,7 @@ class DeepInteractionDecoder(nn.Module):
         f1w, f1b, f2w, f2b = pk['ffn']
         f = ops.linear([ops.linear([q], f1w, f1b, ops.ACT_RELU)], f2w, f2b)
         q = ops.rows_finish(f, res=q, gamma=pk['norm3'][0], beta=pk['norm3'][1])
+        ops._MODULE[0] = ('prediction_heads', 0, 0)
         pred = self._pred(pk['pred0'], [q])
         ops.pred_finish(pred, qpos)
         first = pred
@@ -411,6 +417,9 @@ class DeepInteractionDecoder(nn.Module):
         preds, wins = [], []
         for li, bp in enumerate(pk['blocks']):
             prev = q
+            # RoI reads <= one map; DynamicConv parameter generator weights 128 x 32768 (+ out_layer 6272 x 128) read once
+            ops._MODULE[0] = ('ImageRCNNBlock' if bp['image'] else 'PointRCNNBlock',
+                              4 * (B * P * 49 * C) + 4 * (C * 2 * C * C + 49 * C * C), 2 * B * P * (C * 2 * C * C + 2 * 49 * C * C + 49 * C * C))
             if bp['image']:
                 rois, win, onbits = ops.rcnn_rois(pred, B, P, V, 0, prm, proj, aux)
                 roi = ops.roi_align(img, rois, 1.0 / self.out_size_factor_img)
@@ -432,6 +441,7 @@ class DeepInteractionDecoder(nn.Module):
             f = ops.linear([ops.linear([q2], f1w, f1b, ops.ACT_GELU)], f2w, f2b)
             q = ops.rows_finish(f, res=q2, gamma=bp['norm3'][0], beta=bp['norm3'][1],
                                 zero_if_neg=win if bp['image'] else None)
+            ops._MODULE[0] = ('prediction_heads', 0, 0)
             pred = self._pred(bp['pred'], [q, prev])
             ops.pred_finish(pred, qpos, first if bp['image'] else None, win if bp['image'] else None)
             preds.append(pred)
@@ -440,6 +450,7 @@ class DeepInteractionDecoder(nn.Module):
             if debug is not None:
                 debug.setdefault('layer_query', []).append(q.clone())
                 debug.setdefault('rois', []).append(rois)
+        ops._MODULE[0] = None
         return dict(preds=preds, wins=wins, qscore=qscore, dense_heatmap=dense_b, labels=labels)
 
     def _to_dict(self, pred, B, P):

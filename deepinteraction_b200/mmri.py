@@ -23,6 +23,11 @@ from . import fold, geom, ops
 from .graph import GraphCache
 
 PC_RANGE = (-54.0, -54.0, -5.0, 54.0, 54.0, 3.0)     # hard-coded in the reference (encoder_utils.py:190)
+PILLAR_BUCKET, POINT_BUCKET = 4096, 32768            # capacity granularity of the staged per-frame arrays (graph.py)
+
+
+def _bucket(n, step):
+    return max(step, -(-int(n) // step) * step)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -136,11 +141,12 @@ class Geometry:
     """Per-frame geometry shared by both encoder layers (and by the decoder's projections)."""
 
     def __init__(self, img_metas, pts_metas, feat_hw, bev_hw, device, want_debug=False, side_stream=None,
-                 cams=None):
+                 cams=None, counts=None):
         """The depth maps / completion / lifting chain is latency-bound (one CTA per camera) and independent of
         the feature maps, so it is issued on `side_stream` and overlaps the shared convs and the BEV branch;
         consumers call wait() before the first BEV sampling.  cams = (proj, i2l) device tensors when the caller
-        already uploaded the camera rows (graph replay), else they are derived from img_metas here."""
+        already uploaded the camera rows (graph replay), else they are derived from img_metas here.  counts: device
+        int32 [1 + B] (live pillar count, live point count per sample) when the point arrays are capacity buffers."""
         self.in_hw = geom.input_hw(img_metas)
         self.proj, self.i2l = cams if cams is not None else geom.camera_rows(img_metas, device)   # (B,V,12), (B*V,12)
         B, V = self.proj.shape[:2]
@@ -155,10 +161,12 @@ class Geometry:
             pts_list.append(pts)
         if side is not main:
             side.wait_stream(main)
-        with torch.cuda.stream(side):
+        with torch.cuda.stream(side), ops.module('BEVWarp_geometry (once per frame, side stream)',
+                                                 12 * sum(int(p.shape[0]) for p in pts_list) + 3 * 4 * B * V * h * w):
             keys = torch.zeros(B * V, h, w, device=device, dtype=torch.int64)
             for b in range(B):
-                ops.depth_scatter(pts_list[b], self.proj[b], keys[b * V:(b + 1) * V], self.in_hw)
+                ops.depth_scatter(pts_list[b], self.proj[b], keys[b * V:(b + 1) * V], self.in_hw,
+                                  None if counts is None else counts[1 + b:2 + b])
             if want_debug:
                 self.dense, self.sparse = ops.depth_complete(keys, want_sparse=True)
             else:
@@ -166,6 +174,13 @@ class Geometry:
             self.grid = ops.lift_grid(self.dense, self.i2l, self.in_hw, bev_hw, PC_RANGE)
             self.ready = torch.cuda.Event()
             self.ready.record(side)
+        if side is not main and not torch.cuda.is_current_stream_capturing():
+            # The buffers were allocated under the side stream but are read by kernels of the consumer stream: tell
+            # the caching allocator, or a later frame's geometry could reuse a block while bev_sample of this frame is
+            # still queued (eager path with several frames in flight).  Captured graphs own a private pool instead.
+            for t in (keys, self.dense, self.grid, getattr(self, 'sparse', None)):
+                if t is not None:
+                    t.record_stream(main)
         self._side, self._main = side, main
         self.V = V
 
@@ -194,7 +209,7 @@ class DeepInteractionEncoder(nn.Module):
         self._pack = None
         self._pack_key = None
         self.last_geometry = None
-        self._side_stream = None
+        self._side_streams = {}              # one geometry side stream per consumer stream (frames in flight)
         self._graphs = GraphCache()
 
     # -- packing -----------------------------------------------------------------------------------
@@ -228,19 +243,20 @@ class DeepInteractionEncoder(nn.Module):
         return pk
 
     # -- forward -----------------------------------------------------------------------------------
-    def i2p(self, lp, pts_nhwc, img_nhwc, pts_metas, g):
+    def i2p(self, lp, pts_nhwc, img_nhwc, pts_metas, g, n_dev=None):
+        """n_dev: device int32 [1] with the live pillar count when the pillar arrays are capacity buffers."""
         B, Y, X, C = pts_nhwc.shape
         coors = pts_metas['pillar_coors']
         out = torch.zeros_like(pts_nhwc)
         if coors.shape[0] == 0:
             return out
         M1, c1, M2, c2 = lp['i2p']
-        rows = ops.gather_rows(pts_nhwc, coors)
+        rows = ops.gather_rows(pts_nhwc, coors, n_dev)
         qk = ops.linear([rows], M1, c1)
         s, cnt = ops.i2p_attend(qk, pts_metas['pillars'], pts_metas['pillars_num_points'], coors, g.proj, img_nhwc,
-                                g.V, g.in_hw)
+                                g.V, g.in_hw, n_dev)
         o = ops.linear([s], M2, c2)
-        return ops.scatter_rows(o, cnt, coors, out)
+        return ops.scatter_rows(o, cnt, coors, out, n_dev)
 
     @staticmethod
     def _canon_pts_metas(pts_metas, device):
@@ -262,43 +278,60 @@ class DeepInteractionEncoder(nn.Module):
         if debug is not None:
             return self._schedule(img_feats, pts_feats, img_metas, pm, pts_list, None, debug)
         proj_h, i2l_h = geom.camera_rows_host(img_metas)
-        inputs = [img_feats.contiguous(), pts_feats.contiguous(), pm['pillars'], pm['pillar_coors'],
-                  pm['pillars_num_points']] + pts_list
-        sig = (tuple(tuple(t.shape) for t in inputs), geom.input_hw(img_metas), id(self._pack))
+        inputs = [img_feats.contiguous(), pts_feats.contiguous()]
+        # per-frame arrays (row counts change every frame): staged at bucketed capacities, live counts via `consts`
+        staged = [pm['pillars'], pm['pillar_coors'], pm['pillars_num_points']] + pts_list
+        caps = [_bucket(pm['pillars'].shape[0], PILLAR_BUCKET)] * 3 + [_bucket(p.shape[0], POINT_BUCKET) for p in pts_list]
+        counts_h = torch.tensor([pm['pillars'].shape[0]] + [p.shape[0] for p in pts_list], dtype=torch.int32)
+        sig = (tuple(tuple(t.shape) for t in inputs), tuple(tuple(t.shape[1:]) for t in staged),
+               geom.input_hw(img_metas), id(self._pack))
 
-        def fn(ins, consts):
-            pmx = dict(pillars=ins[2], pillar_coors=ins[3], pillars_num_points=ins[4], pts=ins[5:])
-            return self._schedule(ins[0], ins[1], img_metas, pmx, ins[5:], (consts[0], consts[1]), None)
-        return self._graphs.run(sig, inputs, [proj_h, i2l_h], fn)
+        def fn(ins, consts, st):
+            pmx = dict(pillars=st[0], pillar_coors=st[1], pillars_num_points=st[2], pts=st[3:])
+            return self._schedule(ins[0], ins[1], img_metas, pmx, st[3:], (consts[0], consts[1]), None, counts=consts[2])
+        return self._graphs.run(sig, inputs, [proj_h, i2l_h, counts_h], fn, staged=staged, caps=caps)
 
-    def _schedule(self, img_feats, pts_feats, img_metas, pm, pts_list, cams, debug):
+    def _schedule(self, img_feats, pts_feats, img_metas, pm, pts_list, cams, debug, counts=None):
         pk = self._pack
         dev_ = img_feats.device
         C = self.hidden_channel
         BV, _, h, w = img_feats.shape
         B, _, Y, X = pts_feats.shape
         V = BV // B
-        if self._side_stream is None:
-            self._side_stream = torch.cuda.Stream(device=dev_)
+        cur_id = torch.cuda.current_stream().cuda_stream
+        if cur_id not in self._side_streams:
+            self._side_streams[cur_id] = torch.cuda.Stream(device=dev_)
         pm = dict(pm)
         pm['pts'] = pts_list
         g = Geometry(img_metas, pm, (h, w), (Y, X), dev_, want_debug=debug is not None,
-                     side_stream=self._side_stream, cams=cams)
+                     side_stream=self._side_streams[cur_id], cams=cams, counts=counts)
         self.last_geometry = g
-        img = ops.conv3x3(img_feats.contiguous(), *pk['shared_conv_img'], cout=C, x_nhwc=False)
-        pts = ops.conv3x3(pts_feats.contiguous(), *pk['shared_conv_pts'], cout=C, x_nhwc=False)
+        # module-boundary bytes of SURVEY.md 8(d) (fp32 maps: F_i image side, F_b BEV side) for bench.py's roofline table
+        F_i, F_b = 4 * BV * h * w * C, 4 * B * Y * X * C
+        n_pil, n_pts = pm['pillars'].shape[0], sum(int(p.shape[0]) for p in pts_list)
+        with ops.module('shared_conv_img+pts', 4 * (img_feats.numel() + pts_feats.numel()) + F_i + F_b,
+                        2 * 9 * C * (img_feats.numel() + pts_feats.numel())):
+            img = ops.conv3x3(img_feats.contiguous(), *pk['shared_conv_img'], cout=C, x_nhwc=False)
+            pts = ops.conv3x3(pts_feats.contiguous(), *pk['shared_conv_pts'], cout=C, x_nhwc=False)
         pts_conv = pts
+        lcab_flops = lambda npx: 2 * npx * C * (5 * C + 2 * 81)
         for li, lp in enumerate(pk['layers']):
             img_r, pts_r = img.view(BV * h * w, C), pts.view(B * Y * X, C)
-            i2p = self.i2p(lp, pts, img, pm, g)
-            p2p = lcab_forward(lp['p_iml'], pts_r, pts_r, B, Y, X)
-            new_pts = ops.linear([i2p.view(-1, C), p2p, pts_r], *lp['p_fuse']).view(B, Y, X, C)
+            with ops.module('MMRI_I2P', n_pil * (C * 4 + 20 * 12 + 16) + F_i + F_b):
+                i2p = self.i2p(lp, pts, img, pm, g, None if counts is None else counts[0:1])
+            with ops.module('LCAB_self_bev', 2 * F_b, lcab_flops(B * Y * X)):
+                p2p = lcab_forward(lp['p_iml'], pts_r, pts_r, B, Y, X)
+            with ops.module('P_out_proj+P_integration', 4 * F_b, 2 * B * Y * X * C * 3 * C):
+                new_pts = ops.linear([i2p.view(-1, C), p2p, pts_r], *lp['p_fuse']).view(B, Y, X, C)
             if li == 0:
                 g.wait()
-            warped = ops.bev_sample(pts, g.grid, V)
-            p2i = lcab_forward(lp['p2i'], img_r, warped.view(-1, C), BV, h, w)
-            i2i = lcab_forward(lp['i_iml'], img_r, img_r, BV, h, w)
-            new_img = ops.linear([p2i, i2i, img_r], *lp['i_fuse']).view(BV, h, w, C)
+            with ops.module('MMRI_P2I', 2 * F_i + F_b + 12 * n_pts, lcab_flops(BV * h * w)):
+                warped = ops.bev_sample(pts, g.grid, V)
+                p2i = lcab_forward(lp['p2i'], img_r, warped.view(-1, C), BV, h, w)
+            with ops.module('LCAB_self_img', 2 * F_i, lcab_flops(BV * h * w)):
+                i2i = lcab_forward(lp['i_iml'], img_r, img_r, BV, h, w)
+            with ops.module('I_out_proj+I_integration', 4 * F_i, 2 * BV * h * w * C * 3 * C):
+                new_img = ops.linear([p2i, i2i, img_r], *lp['i_fuse']).view(BV, h, w, C)
             if debug is not None:
                 debug.append(dict(i2p=i2p, p2p=p2p.view(B, Y, X, C), warped=warped, p2i=p2i.view(BV, h, w, C),
                                   i2i=i2i.view(BV, h, w, C)))

@@ -20,7 +20,24 @@ TC_CONV = [os.environ.get('DI_B200_TC_CONV', '1') != '0']
 TC_MIN_M = [int(os.environ.get('DI_B200_TC_MIN_M', '128'))]   # fewer rows: fp32 FFMA kernels of gemm.cu (measured: the tensor-core kernel is faster from 128 rows up)
 TC_BF16 = [os.environ.get('DI_B200_TC_BF16', '1') != '0']   # bf16-split operands where K % 64 == 0 (else 3xTF32)
 _TAG = ['']        # optional shape tag for the next profiled call (bench.py --shapes table)
-PROFILE = [None]  # bench.py sets PROFILE[0] = [] to record (name, start_event, end_event, bytes, flops) per call
+PROFILE = [None]  # bench.py sets PROFILE[0] = [] to record (name, start_event, end_event, bytes, flops, module) per call
+_MODULE = [None]  # (name, module-boundary bytes, flops) of the nn.Module whose kernels are being issued (bench.py roofline table)
+
+
+class module:
+    """`with ops.module('lcab_img_self', nbytes, flops):` tags the calls issued inside with the reference nn.Module
+    they belong to and that module's ALGORITHMIC bytes (every distinct input map read once, the
+    output written once).  Only bench.py's profile pass reads the tags; zero cost otherwise."""
+
+    def __init__(self, name, nbytes=0, flops=0):
+        self.tag = (name, int(nbytes), int(flops))
+
+    def __enter__(self):
+        self.prev, _MODULE[0] = _MODULE[0], self.tag
+
+    def __exit__(self, *a):
+        _MODULE[0] = self.prev
+        return False
 
 
 def _stream():
@@ -50,7 +67,7 @@ def _call(name, *args, nbytes=0, flops=0):
     e0.record()
     rc = _lib.check(getattr(_lib.lib(), name)(*args), name)
     e1.record()
-    prof.append((name + _TAG[0], e0, e1, nbytes, flops))
+    prof.append((name + _TAG[0], e0, e1, nbytes, flops, _MODULE[0]))
     _TAG[0] = ''
     return rc
 
@@ -218,41 +235,47 @@ def lcab_window(q, k, v, N, H, W, C, ksize=9, out=None):
     return out
 
 
-def gather_rows(map_nhwc, coors):
+def gather_rows(map_nhwc, coors, n_dev=None):
+    """n_dev (here and in scatter_rows / i2p_attend / depth_scatter): int32 device tensor holding the live count when
+    the arrays are allocated at capacity (shape-independent graph replay); None = all rows."""
     B, Y, X, C = map_nhwc.shape
     P = coors.shape[0]
-    rows = torch.empty(P, C, device=map_nhwc.device, dtype=torch.float32)
-    _call('di_gather_rows_f32', _ptr(map_nhwc), _ptr(coors), _ptr(rows), P, Y, X, C, _stream())
+    rows = torch.zeros(P, C, device=map_nhwc.device, dtype=torch.float32) if n_dev is not None else \
+        torch.empty(P, C, device=map_nhwc.device, dtype=torch.float32)
+    _call('di_gather_rows_f32', _ptr(map_nhwc), _ptr(coors), _ptr(rows), P, Y, X, C, _ptr(n_dev), _stream())
     return rows
 
 
-def scatter_rows(rows, cnt, coors, map_nhwc):
+def scatter_rows(rows, cnt, coors, map_nhwc, n_dev=None):
     B, Y, X, C = map_nhwc.shape
-    _call('di_scatter_rows_f32', _ptr(rows), _ptr(cnt), _ptr(coors), _ptr(map_nhwc), coors.shape[0], Y, X, C, _stream())
+    _call('di_scatter_rows_f32', _ptr(rows), _ptr(cnt), _ptr(coors), _ptr(map_nhwc), coors.shape[0], Y, X, C,
+          _ptr(n_dev), _stream())
     return map_nhwc
 
 
-def i2p_attend(qk, pillars, npts, coors, proj, img_nhwc, V, in_hw):
+def i2p_attend(qk, pillars, npts, coors, proj, img_nhwc, V, in_hw, n_dev=None):
     P, C = qk.shape
     _, T, pdim = pillars.shape
     BV, h, w, Ci = img_nhwc.shape
     assert Ci == C and pillars.is_contiguous() and img_nhwc.is_contiguous()
     s = torch.empty(P, C, device=qk.device, dtype=torch.float32)
     cnt = torch.empty(P, device=qk.device, dtype=torch.int32)
+    if n_dev is not None:
+        s.zero_()                       # rows beyond the live count feed a dense layer: keep them finite
     _call('di_i2p_attend_f32', _ptr(qk), _ptr(pillars), _ptr(npts), _ptr(coors), _ptr(proj), _ptr(img_nhwc), _ptr(s),
-          _ptr(cnt), P, T, pdim, V, h, w, C, in_hw[0], in_hw[1], _stream(),
+          _ptr(cnt), P, T, pdim, V, h, w, C, in_hw[0], in_hw[1], _ptr(n_dev), _stream(),
           nbytes=4 * (2 * P * C + pillars.numel() + img_nhwc.numel()), flops=0)
     return s, cnt
 
 
-def depth_scatter(pts, proj_b, keys_b, in_hw):
+def depth_scatter(pts, proj_b, keys_b, in_hw, n_dev=None):
     """pts (n, >=3) row-major; proj_b (V,12); keys_b (V,h,w) int64 view of zeroed uint64 keys."""
     V, h, w = keys_b.shape
     if pts.shape[0] == 0:                 # a sample without lidar points: its depth maps stay empty
         return
     assert pts.stride(1) == 1
     _call('di_depth_scatter', _ptr(pts), pts.stride(0), pts.shape[0], _ptr(proj_b), _ptr(keys_b), V, h, w, in_hw[0],
-          in_hw[1], _stream())
+          in_hw[1], _ptr(n_dev), _stream())
 
 
 def depth_complete(keys, want_sparse=False):

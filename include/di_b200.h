@@ -139,20 +139,23 @@ int di_locatt_ck2c_loc_f32(const float* x_ori, const float* wgt, float* y, int N
 /* ---- geometry-driven gathers (geometry.cu) ------------------------------------------------------ */
 
 /* rows[p,:] = map[coors[p] = (b,z,y,x)]  (models/utils/encoder_utils.py:313) */
-int di_gather_rows_f32(const float* map, const int* coors, float* rows, int P, int Y, int X, int C,
+/* n_dev (this and the next three entry points; may be NULL): device pointer to the LIVE element count when the arrays
+ * are allocated at a capacity P / n -- min(capacity, *n_dev) elements are processed.  Launch configurations and
+ * buffer addresses then do not depend on the per-frame pillar / point counts (shape-independent CUDA-graph replay). */
+int di_gather_rows_f32(const float* map, const int* coors, float* rows, int P, int Y, int X, int C, const int* n_dev,
                        cudaStream_t stream);
 /* map[coors[p]] = cnt[p] > 0 ? rows[p,:] : 0  (models/utils/encoder_utils.py:314-318) */
 int di_scatter_rows_f32(const float* rows, const int* cnt, const int* coors, float* map, int P, int Y, int X, int C,
-                        cudaStream_t stream);
+                        const int* n_dev, cudaStream_t stream);
 /* Per pillar: project its <=T points to V cameras, strict in-image / z>1e-5 / point<num_points mask,
  * bilinear gather of the image feature, single-head softmax attention with the folded query qk
  * (models/utils/encoder_utils.py:270-316; fold: SURVEY.md section 0).  s_out = sum_j a_j k_j, cnt = #valid keys. */
 int di_i2p_attend_f32(const float* qk, const float* pillars, const int* npts, const int* coors, const float* proj,
                       const float* img, float* s_out, int* cnt_out, int P, int T, int pdim, int V, int h, int w, int C,
-                      int H_in, int W_in, cudaStream_t stream);
+                      int H_in, int W_in, const int* n_dev, cudaStream_t stream);
 /* Sparse depth maps: keys[v,r,c] = max((point index+1)<<32 | depth bits)  (models/utils/encoder_utils.py:155-174) */
 int di_depth_scatter(const float* pts, int stride, int n, const float* proj, unsigned long long* keys, int V, int h,
-                     int w, int H_in, int W_in, cudaStream_t stream);
+                     int w, int H_in, int W_in, const int* n_dev, cudaStream_t stream);
 /* ip_basic fill_in_multiscale(extrapolate=False, blur_type='bilateral') on the GPU
  * (models/utils/ip_basic/depth_map_utils.py:134-287; called at models/utils/encoder_utils.py:175-182).
  * scratch: 3*n_img*h*w floats. */

@@ -18,10 +18,22 @@ def _chk(*ts):
             raise RuntimeError('localattention is fp32-only')
 
 
+def _chk_same(a, b, what):
+    if a.dim() != 4 or a.shape != b.shape:
+        raise RuntimeError(f'{what}: expected two [N,C,H,W] tensors of equal shape, got {tuple(a.shape)} and {tuple(b.shape)}')
+
+
+def _chk_weight(x, w, kH, kW, what):
+    if x.dim() != 4 or w.dim() != 4 or tuple(w.shape) != (x.shape[0], x.shape[2], x.shape[3], kH * kW):
+        raise RuntimeError(f'{what}: weight must be [N,H,W,kH*kW] = {(x.shape[0], x.shape[2], x.shape[3], kH * kW)}, '
+                           f'got {tuple(w.shape)}')
+
+
 class localattention:
     @staticmethod
     def similar_forward(x_ori, x_loc, kH, kW):
         _chk(x_ori, x_loc)
+        _chk_same(x_ori, x_loc, 'similar_forward')
         x_ori, x_loc = x_ori.contiguous(), x_loc.contiguous()
         N, C, H, W = x_ori.shape
         y = torch.empty(N, H, W, kH * kW, device=x_ori.device, dtype=torch.float32)
@@ -31,6 +43,7 @@ class localattention:
     @staticmethod
     def similar_backward(x, grad_out, kH, kW, is_ori):
         _chk(x, grad_out)
+        _chk_weight(x, grad_out, kH, kW, 'similar_backward')
         x, grad_out = x.contiguous(), grad_out.contiguous()
         N, C, H, W = x.shape
         y = torch.empty_like(x)
@@ -41,6 +54,7 @@ class localattention:
     @staticmethod
     def weighting_forward(x_ori, x_weight, kH, kW):
         _chk(x_ori, x_weight)
+        _chk_weight(x_ori, x_weight, kH, kW, 'weighting_forward')
         x_ori, x_weight = x_ori.contiguous(), x_weight.contiguous()
         N, C, H, W = x_ori.shape
         y = torch.empty_like(x_ori)
@@ -50,6 +64,7 @@ class localattention:
     @staticmethod
     def weighting_backward_ori(x_weight, grad_out, kH, kW):
         _chk(x_weight, grad_out)
+        _chk_weight(grad_out, x_weight, kH, kW, 'weighting_backward_ori')
         x_weight, grad_out = x_weight.contiguous(), grad_out.contiguous()
         N, C, H, W = grad_out.shape
         y = torch.empty_like(grad_out)
@@ -59,6 +74,7 @@ class localattention:
     @staticmethod
     def weighting_backward_weight(x_ori, grad_out, kH, kW):
         _chk(x_ori, grad_out)
+        _chk_same(x_ori, grad_out, 'weighting_backward_weight')
         x_ori, grad_out = x_ori.contiguous(), grad_out.contiguous()
         N, C, H, W = x_ori.shape
         y = torch.empty(N, H, W, kH * kW, device=x_ori.device, dtype=torch.float32)

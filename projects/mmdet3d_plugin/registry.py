@@ -65,5 +65,7 @@ def build_hot_path(cfg):
     neck = NECKS.build(model['imgpts_neck'])
     head_cfg = dict(model['pts_bbox_head'])
     test_cfg = model.get('test_cfg') or {}
-    head = HEADS.build(head_cfg, train_cfg=None, test_cfg=test_cfg.get('pts'))
+    # folded into the cfg like MVXTwoStageDetector does (mmcv's Registry.build takes the cfg only)
+    head_cfg.update(train_cfg=None, test_cfg=test_cfg.get('pts'))
+    head = HEADS.build(head_cfg)
     return neck, head

@@ -324,6 +324,25 @@ def test_encoder_small_matches_reference_golden(tag):
     print(tag, 'rel err img %.2e pts %.2e' % (rel_err(img.cpu(), gold['img']), rel_err(p1.cpu(), gold['pts'])))
 
 
+def test_encoder_c128_matches_reference_golden():
+    """C = 128 (tcgen05 window kernel, planar operands) against a golden produced by the reference's own files."""
+    from deepinteraction_b200 import mmri, synth
+    from tools.make_goldens import small_frame
+    import oracle.mmri as om
+    gold = torch.load(os.path.join(G, 'encoder_c128.pt'), weights_only=False)
+    torch.manual_seed(gold['seed'])
+    m = om.DeepInteractionEncoder(2, 16, 24, 128).eval()
+    synth.randomize_norm_stats(m, gold['seed'])
+    enc = mmri.DeepInteractionEncoder(2, 16, 24, 128)
+    enc.load_state_dict(m.state_dict(), strict=True)
+    enc = enc.to(dev()).eval()
+    fr = synth.to_device(small_frame(gold['seed'], aug=gold['aug'], views=2, c_img=16, c_pts=24, bev=36, batch=1), dev())
+    img, (p0, p1) = enc(fr['img_feats'], fr['pts_feats'], fr['img_metas'], fr['pts_metas'])
+    assert rel_err(p0.cpu(), gold['pts_conv']) < TIGHT
+    assert rel_err(p1.cpu(), gold['pts']) < TOL
+    assert rel_err(img.cpu(), gold['img']) < TOL
+
+
 def test_encoder_medium_c128_matches_oracle():
     """C=128 (the production width), 3 cameras 56x100, 90x90 BEV, dense cloud: every module vs the oracle."""
     from deepinteraction_b200 import mmri, synth

@@ -71,6 +71,41 @@ def test_encoder_graph_replay_equals_eager():
         graph.ENABLED[0] = old
 
 
+def test_encoder_graph_replay_is_shape_independent():
+    """Frames with DIFFERENT pillar and point counts replay through ONE captured graph (the per-frame arrays are staged
+    at bucketed capacities, the live counts are read from device memory) and reproduce the eager results bit for bit."""
+    from deepinteraction_b200 import graph, synth
+    from tools.make_goldens import small_frame
+    enc = _encoder(33)
+    frames = [synth.to_device(small_frame(300 + i, aug=bool(i & 1), views=2, c_img=16, c_pts=24, bev=36, batch=2,
+                                          n_points=n), dev())
+              for i, n in enumerate((6000, 2500, 9000, 40))]
+    counts = [(f['pts_metas']['pillars'].shape[0], tuple(p.shape[0] for p in f['pts_metas']['pts'])) for f in frames]
+    assert len(set(c[0] for c in counts)) == len(frames), counts      # the pillar counts really differ
+    buf_img = torch.empty_like(frames[0]['img_feats'])
+    buf_pts = torch.empty_like(frames[0]['pts_feats'])
+
+    def run(fr):
+        buf_img.copy_(fr['img_feats'])
+        buf_pts.copy_(fr['pts_feats'])
+        return [t.clone() for t in enc.forward_nhwc(buf_img, buf_pts, fr['img_metas'], fr['pts_metas'])]
+
+    old = graph.ENABLED[0]
+    try:
+        graph.ENABLED[0] = False
+        refs = [run(f) for f in frames]
+        graph.ENABLED[0] = True
+        enc._graphs.clear()
+        order = [0, 1, 2, 3, 0, 3, 2, 1, 1, 0]
+        for step, i in enumerate(order):
+            out = run(frames[i])
+            for x, y in zip(out, refs[i]):
+                assert torch.equal(x, y), (step, i, float((x - y).abs().max()))
+        assert len(enc._graphs.entries) == 1, list(enc._graphs.entries)
+    finally:
+        graph.ENABLED[0] = old
+
+
 def _flat(r):
     out = {}
     for k, v in r.items():

@@ -76,6 +76,19 @@ def test_encoder_small(tag):
     assert rel_err(img, g['img']) < TOL and rel_err(p0, g['pts_conv']) < TOL and rel_err(p1, g['pts']) < TOL
 
 
+def test_encoder_c128():
+    """Reference-generated golden at the base model's hidden width (C = 128), augmented frame."""
+    g = load('encoder_c128')
+    torch.manual_seed(g['seed'])
+    m = ommri.DeepInteractionEncoder(2, 16, 24, 128).eval()
+    synth.randomize_norm_stats(m, g['seed'])
+    assert state_checksum(m.state_dict()) == g['checksum']
+    fr = small_frame(g['seed'], aug=g['aug'], views=2, c_img=16, c_pts=24, bev=36, batch=1)
+    with torch.no_grad():
+        img, (p0, p1) = m(fr['img_feats'], fr['pts_feats'], fr['img_metas'], fr['pts_metas'])
+    assert rel_err(img, g['img']) < TOL and rel_err(p0, g['pts_conv']) < TOL and rel_err(p1, g['pts']) < TOL
+
+
 @pytest.mark.parametrize('tag', ['decoder_small', 'decoder_small_aug'])
 def test_decoder_small(tag):
     g = load(tag)

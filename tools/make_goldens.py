@@ -218,13 +218,17 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--ref', default='/root/reference')
     ap.add_argument('--out', default=os.path.join(ROOT, 'tests', 'golden'))
+    ap.add_argument('--only', default='', help='comma-separated golden names to (re)generate; default: all')
     args = ap.parse_args()
+    only = set(x for x in args.only.split(',') if x)
     os.makedirs(args.out, exist_ok=True)
     eu, enc, du, dec = install_stubs(args.ref)
     torch.set_grad_enabled(False)
     report = []
 
     def save(name, obj):
+        if only and name not in only:
+            return
         torch.save(obj, os.path.join(args.out, name + '.pt'))
         sz = os.path.getsize(os.path.join(args.out, name + '.pt'))
         report.append(f'{name}: {sz / 1024:.0f} KiB')
@@ -290,6 +294,21 @@ def main():
         print(tag, 'oracle vs reference', cmp(o_img, r_img), cmp(o_p0, r_p0), cmp(o_p1, r_p1))
         save(tag, dict(seed=seed, aug=aug, checksum=state_checksum(om.state_dict()), img=r_img, pts_conv=r_p0,
                        pts=r_p1))
+
+    # --- G4b: encoder at the base model's hidden width (C = 128: the tcgen05 window kernel's only width) -------------
+    if not only or 'encoder_c128' in only:
+        seed = 1550
+        torch.manual_seed(seed)
+        om = ommri.DeepInteractionEncoder(2, 16, 24, 128).eval()
+        synth.randomize_norm_stats(om, seed)
+        rm = enc.DeepInteractionEncoder(num_layers=2, in_channels_img=16, in_channels_pts=24, hidden_channel=128).eval()
+        rm.load_state_dict(om.state_dict(), strict=True)
+        fr = small_frame(seed, aug=True, views=2, c_img=16, c_pts=24, bev=36, batch=1)
+        r_img, (r_p0, r_p1) = rm(fr['img_feats'], fr['pts_feats'], fr['img_metas'], fr['pts_metas'])
+        o_img, (o_p0, o_p1) = om(fr['img_feats'], fr['pts_feats'], fr['img_metas'], fr['pts_metas'])
+        print('encoder_c128 oracle vs reference', cmp(o_img, r_img), cmp(o_p0, r_p0), cmp(o_p1, r_p1))
+        save('encoder_c128', dict(seed=seed, aug=True, checksum=state_checksum(om.state_dict()), img=r_img, pts_conv=r_p0,
+                                  pts=r_p1))
 
     # --- G5: decoder (hidden 128 is hard-coded in DynamicConv) ----------------------------------------
     for tag, aug in (('decoder_small', False), ('decoder_small_aug', True)):
