@@ -41,6 +41,24 @@ def camera_rig(num_views, in_hw, radius=1.0, height=1.5, focal_frac=0.79):
     return np.stack(mats)
 
 
+def camera_extras(num_views, in_hw, radius=1.0, height=1.5, focal_frac=0.79):
+    """cam2lidar (V,4,4) and cam_intrinsic (V,3,3) of the same rig (img_metas keys read by the ++ polar block,
+    reference fusion_transformerv4.py:521-531)."""
+    H, W = in_hw
+    base = np.array([[0.0, 0.0, 1.0], [-1.0, 0.0, 0.0], [0.0, -1.0, 0.0]])
+    c2l, Ks = [], []
+    for k in range(num_views):
+        yaw = 2.0 * math.pi * k / num_views
+        c, s = math.cos(yaw), math.sin(yaw)
+        Rz = np.array([[c, -s, 0.0], [s, c, 0.0], [0.0, 0.0, 1.0]])
+        M = np.eye(4)
+        M[:3, :3] = Rz @ base
+        M[:3, 3] = Rz @ np.array([radius, 0.0, height])
+        c2l.append(M)
+        Ks.append(np.array([[focal_frac * W, 0.0, W / 2.0], [0.0, focal_frac * W, H / 2.0], [0.0, 0.0, 1.0]]))
+    return np.stack(c2l), np.stack(Ks)
+
+
 def make_points(n, rng, mode='lidar', rmax=76.0):
     theta = rng.uniform(0.0, 2.0 * math.pi, n)
     if mode == 'lidar':
@@ -119,6 +137,7 @@ def make_frame_batch(seed, batch=1, num_views=6, in_hw=(448, 800), stride=4, c_i
     g = torch.Generator().manual_seed(seed)
     h, w = in_hw[0] // stride, in_hw[1] // stride
     rig = camera_rig(num_views, in_hw)
+    c2l, intr = camera_extras(num_views, in_hw)
     img_metas, pts = [], []
     for b in range(batch):
         p = make_points(n_points, rng, cloud)
@@ -126,7 +145,8 @@ def make_frame_batch(seed, batch=1, num_views=6, in_hw=(448, 800), stride=4, c_i
             p = sanitize(p, rig, in_hw, (h, w))
         pts.append(p)
         meta = dict(lidar2img=[m.astype(np.float32) for m in rig], input_shape=in_hw,
-                    img_shape=[(in_hw[0], in_hw[1], 3)] * num_views, box_type_3d=None)
+                    img_shape=[(in_hw[0], in_hw[1], 3)] * num_views, box_type_3d=None,
+                    cam2lidar=[m.astype(np.float32) for m in c2l], cam_intrinsic=[m.astype(np.float32) for m in intr])
         if aug:
             meta.update(AUG_META)
         img_metas.append(meta)

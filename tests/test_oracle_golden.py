@@ -1,6 +1,7 @@
 """CPU: the oracle restatement vs goldens produced by the reference's own Python
 files (tools/make_goldens.py, stub-loaded in the build container)."""
 import os
+import sys
 
 import numpy as np
 
@@ -13,7 +14,8 @@ from deepinteraction_b200 import synth
 from tools.make_goldens import small_frame, make_decoder, state_checksum
 from conftest import rel_err
 
-G = os.path.join(os.path.dirname(__file__), 'golden')
+G = os.path.join(os.path.dirname(__file__), "golden")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TOL = 5e-5   # fp32 re-association only; the goldens come from the reference's own torch code
 
 
@@ -87,6 +89,29 @@ def test_encoder_c128():
     with torch.no_grad():
         img, (p0, p1) = m(fr['img_feats'], fr['pts_feats'], fr['img_metas'], fr['pts_metas'])
     assert rel_err(img, g['img']) < TOL and rel_err(p0, g['pts_conv']) < TOL and rel_err(p1, g['pts']) < TOL
+
+
+@pytest.mark.parametrize('tag', ['encoder_pp_small', 'encoder_pp_nopolar'])
+def test_encoder_plusplus(tag):
+    """++ ("deformable") encoder, BASELINE config 4: oracle/mmri_pp.py vs the golden produced by the reference's own
+    fusion_transformerv4.py (tools/make_goldens_pp.py).  The polar block runs flash-attn in fp16 in the reference
+    (emulated in the golden); the oracle evaluates it in fp32, hence the looser bound on that case."""
+    import oracle.mmri_pp as opp
+    sys.path.insert(0, os.path.join(ROOT, 'tools'))
+    import make_goldens_pp as mgp
+    g = load(tag)
+    img_l, pts_l = mgp.pp_layers(g['polar'])
+    torch.manual_seed(g['seed'])
+    m = opp.FusionTransformerv4(2, 2, 16, 24, 128, img_transformerlayers=img_l, pts_transformerlayers=pts_l).eval()
+    mgp.randomize_pp(m, g['seed'])
+    assert state_checksum(m.state_dict()) == g['checksum']
+    fr = mgp.pp_frame(g['seed'], g['aug'])
+    with torch.no_grad():
+        img, (p0, p1) = m(list(fr['img_levels']), list(fr['pts_levels']), fr['img_metas'], fr['pts_metas'])
+    st = g['channel_step']
+    tol = 2e-4 if g['polar'] else 1e-5
+    assert rel_err(img[:, ::st], g['img']) < tol and rel_err(p0[:, ::st], g['pts_conv']) < 1e-6
+    assert rel_err(p1[:, ::st], g['pts']) < tol
 
 
 @pytest.mark.parametrize('tag', ['decoder_small', 'decoder_small_aug'])
