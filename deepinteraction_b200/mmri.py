@@ -23,11 +23,16 @@ from . import fold, geom, ops
 from .graph import GraphCache
 
 PC_RANGE = (-54.0, -54.0, -5.0, 54.0, 54.0, 3.0)     # hard-coded in the reference (encoder_utils.py:190)
-PILLAR_BUCKET, POINT_BUCKET = 4096, 32768            # capacity granularity of the staged per-frame arrays (graph.py)
+POINT_CAP_MIN = 1 << 19      # staged point arrays: capacity = max(2^19, next power of two) rows per sample (graph.py)
 
 
-def _bucket(n, step):
-    return max(step, -(-int(n) // step) * step)
+def _pow2_cap(n, floor):
+    """Capacity of a staged per-frame array: a power of two >= floor, so that ordinary frame-to-frame variation never
+    crosses a capacity boundary (every boundary costs a graph re-capture)."""
+    c = floor
+    while c < n:
+        c *= 2
+    return c
 
 
 # ------------------------------------------------------------------------------------------------
@@ -281,7 +286,9 @@ class DeepInteractionEncoder(nn.Module):
         inputs = [img_feats.contiguous(), pts_feats.contiguous()]
         # per-frame arrays (row counts change every frame): staged at bucketed capacities, live counts via `consts`
         staged = [pm['pillars'], pm['pillar_coors'], pm['pillars_num_points']] + pts_list
-        caps = [_bucket(pm['pillars'].shape[0], PILLAR_BUCKET)] * 3 + [_bucket(p.shape[0], POINT_BUCKET) for p in pts_list]
+        # pillars: at most one per BEV cell (the physical maximum) -> a capacity that never changes for a given map size
+        B_, _, Y_, X_ = pts_feats.shape
+        caps = [_pow2_cap(pm['pillars'].shape[0], B_ * Y_ * X_)] * 3 + [_pow2_cap(p.shape[0], POINT_CAP_MIN) for p in pts_list]
         counts_h = torch.tensor([pm['pillars'].shape[0]] + [p.shape[0] for p in pts_list], dtype=torch.int32)
         sig = (tuple(tuple(t.shape) for t in inputs), tuple(tuple(t.shape[1:]) for t in staged),
                geom.input_hw(img_metas), id(self._pack))
