@@ -51,6 +51,14 @@ SIGNATURES = {
     'di_depth_complete': [_p, _p, _p, _p, _i, _i, _i, _p],
     'di_lift_grid': [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _fp, _p],
     'di_bev_sample_f32': [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
+    # deform.cu
+    'di_msdeform_f32': [_p, _p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, ctypes.POINTER(ctypes.c_int), _p],
+    'di_axpy_f32': [_p, _p, _p, _p, _ll, _p],
+    'di_polar_grid_f32': [_p, _p, _i, _i, _i, _i, _f, _f, _f, _fp, _i, _i, _p],
+    'di_add_rows_mod_f32': [_p, _p, _p, _ll, _i, _ll, _p],
+    'di_seq_attn_f32': [_p, _i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p],
+    'di_polar_gather_f32': [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _fp, _f, _f, _p],
+    'di_scatter_rows_add_f32': [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p],
     # decoder.cu
     'di_heatmap_nms_f32': [_p, _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     'di_topk_f32': [_p, _p, _i, _i, _i, _p, _i, _p],

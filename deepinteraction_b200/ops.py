@@ -253,6 +253,75 @@ def scatter_rows(rows, cnt, coors, map_nhwc, n_dev=None):
     return map_nhwc
 
 
+def scatter_rows_add(rows, cnt, coors, map_nhwc, n_dev=None):
+    """map[coors[p]] += rows[p] where cnt[p] > 0 (in place)."""
+    B, Y, X, C = map_nhwc.shape
+    _call('di_scatter_rows_add_f32', _ptr(rows), _ptr(cnt), _ptr(coors), _ptr(map_nhwc), coors.shape[0], Y, X, C,
+          _ptr(n_dev), _stream())
+    return map_nhwc
+
+
+def msdeform(values, raw, B, hq, wq, heads=8, points=4):
+    """values: list of 1 or 2 projected value maps [B, H_l, W_l, C]; raw [B*hq*wq, heads*L*P*3] (offsets | logits)
+    -> [B*hq*wq, C]."""
+    L = len(values)
+    C = values[0].shape[-1]
+    assert all(v.is_contiguous() and v.shape[0] == B for v in values) and raw.shape[0] == B * hq * wq
+    out = torch.empty(B * hq * wq, C, device=raw.device, dtype=torch.float32)
+    sh = (ctypes.c_int * (2 * L))(*[d for v in values for d in v.shape[1:3]])
+    pr, ldr = _rows(raw)
+    _call('di_msdeform_f32', _ptr(values[0]), _ptr(values[1]) if L > 1 else None, pr, ldr, _ptr(out), C, B, hq * wq, hq, wq,
+          heads, C // heads, L, points, sh, _stream(),
+          nbytes=4 * (sum(v.numel() for v in values) + raw.numel() + out.numel()),
+          flops=2 * 4 * heads * L * points * (C // heads) * B * hq * wq)
+    return out
+
+
+def polar_grid(cam, BV, R, W, h_feat, im_scale, r0, r_step, pc_range, bev_hw):
+    grid = torch.empty(BV, R, W, 2, device=cam.device, dtype=torch.float32)
+    rng = (ctypes.c_float * 6)(*[float(v) for v in pc_range])
+    _call('di_polar_grid_f32', _ptr(cam), _ptr(grid), BV, R, W, h_feat, float(im_scale), float(r0), float(r_step), rng,
+          bev_hw[0], bev_hw[1], _stream())
+    return grid
+
+
+def add_rows_mod(x, pos):
+    """x [M, C] + pos[m % mod] (pos [mod, C])."""
+    assert x.is_contiguous() and pos.is_contiguous() and x.shape[1] == pos.shape[1]
+    out = torch.empty_like(x)
+    _call('di_add_rows_mod_f32', _ptr(x), _ptr(pos), _ptr(out), x.shape[0], x.shape[1], pos.shape[0], _stream(),
+          nbytes=8 * x.numel())
+    return out
+
+
+def seq_attn(q, k, v, G, Wn, Lq, Lk, heads):
+    """Attention over column sequences: q [G*Lq*Wn, C] row views, k / v [G*Lk*Wn, C] row views -> [G*Lq*Wn, C]."""
+    C = q.shape[1]
+    out = torch.empty(G * Lq * Wn, C, device=q.device, dtype=torch.float32)
+    (pq, lq), (pk, lk), (pv, lv) = _rows(q), _rows(k), _rows(v)
+    _call('di_seq_attn_f32', pq, lq, pk, lk, pv, lv, _ptr(out), C, G, Wn, Lq, Lk, heads, C // heads, _stream(),
+          flops=4 * G * Wn * Lq * Lk * C)
+    return out
+
+
+def polar_gather(rays, lidar, proj, undo, camc, V, in_hw, pc_range, r0, r_count):
+    BV, R, W, C = rays.shape
+    B, Y, X, _ = lidar.shape
+    out = torch.empty_like(lidar)
+    rng = (ctypes.c_float * 6)(*[float(v) for v in pc_range])
+    _call('di_polar_gather_f32', _ptr(rays), _ptr(lidar), _ptr(proj), _ptr(undo), _ptr(camc), _ptr(out), B, V, R, W, Y, X,
+          C, in_hw[0], in_hw[1], rng, float(r0), float(r_count), _stream(), nbytes=4 * (rays.numel() + 2 * lidar.numel()))
+    return out
+
+
+def axpy(a, b, scale):
+    """a + scale[0] * b; scale: 1-element device tensor."""
+    assert a.is_contiguous() and b.is_contiguous() and a.shape == b.shape
+    out = torch.empty_like(a)
+    _call('di_axpy_f32', _ptr(a), _ptr(b), _ptr(scale), _ptr(out), a.numel(), _stream(), nbytes=12 * a.numel())
+    return out
+
+
 def i2p_attend(qk, pillars, npts, coors, proj, img_nhwc, V, in_hw, n_dev=None):
     P, C = qk.shape
     _, T, pdim = pillars.shape

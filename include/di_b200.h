@@ -168,6 +168,43 @@ int di_lift_grid(const float* depth, const float* i2l, float* grid_xy, int n_img
 int di_bev_sample_f32(const float* bev, const float* grid_xy, float* out, int B, int V, int hw, int Yb, int Xb, int C,
                       cudaStream_t stream);
 
+/* ---- ++ ("deformable") encoder, DeepInteraction++ (deform.cu) ------------------------------------------ */
+
+/* Core of mmcv 1.3.18 MultiScaleDeformableAttention as the reference uses it (models/necks/fusion_transformerv4.py:
+ * 169-177 self attention over the multi-scale maps, :226-238 MMRI_P2I over the warped BEV map): per query and head,
+ * softmax over the L*P logits, sampling location = reference point (pixel centre of the Hq x Wq query grid, :129-138)
+ * + offset / (W_l, H_l), bilinear zero-padded sampling of the projected value map, weighted sum.
+ * value0 / value1 [B, H_l, W_l, 128]: projected value map of level 0 / 1 (shapes[2l], shapes[2l+1] = H_l, W_l);
+ * raw [B*NQ, ld_raw]: 8*L*P*2 offsets (head, level, point, xy) then 8*L*P logits (= the outputs of the
+ * sampling_offsets / attention_weights Linear layers, one fused GEMM); out [B*NQ, ldo].
+ * Supported: 8 heads x 16 channels, P = 4, L in {1, 2} (the ++ config); -3 otherwise.  shapes: HOST array. */
+int di_msdeform_f32(const float* value0, const float* value1, const float* raw, int ld_raw, float* out, int ldo, int B,
+                    int NQ, int Hq, int Wq, int heads, int dim, int L, int P, const int* shapes, cudaStream_t stream);
+/* out = a + scale[0] * b (DeepInteractionLayer's `self_feat + self.scale * query`, fusion_transformerv4.py:217);
+ * scale is a device pointer (learned parameter); n % 4 == 0. */
+int di_axpy_f32(const float* a, const float* b, const float* scale, float* out, long long n, cudaStream_t stream);
+/* map[coors[p]] += rows[p,:] where cnt[p] > 0 (++ MMRI_I2P returns decorated + lidar_feat, fusion_transformerv4.py:364) */
+int di_scatter_rows_add_f32(const float* rows, const int* cnt, const int* coors, float* map, int P, int Y, int X, int C,
+                            const int* n_dev, cudaStream_t stream);
+
+/* MMRI_I2P_Polar (models/necks/fusion_transformerv4.py:487-640).
+ * di_polar_grid_f32: BEV pixel coordinates [BV,R,W,2] (input of di_bev_sample_f32) at which the ray queries are
+ *   sampled (:551-577); cam [BV,26] = rows 0-1 of inverse(lidar2img) (8), camera centre xy (2), rows 0-1 of the forward
+ *   augmentation affine (8), 8 unused; pc_range: host float[6].
+ * di_add_rows_mod_f32: out[m] = x[m] + pos[m % mod] (sine position tables, :537-548,576,579).
+ * di_seq_attn_f32: multi-head softmax attention over column sequences -- token t of sequence (g, w) is row
+ *   (g*L + t)*Wn + w -- replacing the flash-attn calls of the polar decoder layer (:651-759), in fp32.
+ * di_polar_gather_f32: decoded rays [B*V,R,W,128] -> BEV (:579-636): per cell and camera the mean over 10 heights of
+ *   (projected pixel x, clamped radius), any-height visibility, bilinear gather, mean over the seeing cameras, + lidar. */
+int di_polar_grid_f32(const float* cam, float* grid, int BV, int R, int W, int h_feat, float im_scale, float r0,
+                      float r_step, const float* pc_range, int Yb, int Xb, cudaStream_t stream);
+int di_add_rows_mod_f32(const float* x, const float* pos, float* out, long long M, int C, long long mod, cudaStream_t stream);
+int di_seq_attn_f32(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* out, int ldo, int G,
+                    int Wn, int Lq, int Lk, int heads, int dim, cudaStream_t stream);
+int di_polar_gather_f32(const float* rays, const float* lidar, const float* proj, const float* undo, const float* camc,
+                        float* out, int B, int V, int R, int W, int Y, int X, int C, int H_in, int W_in,
+                        const float* pc_range, float r0, float r_count, cudaStream_t stream);
+
 /* ---- decoder (decoder.cu) ------------------------------------------------------------------------ */
 
 /* models/dense_heads/deepinteraction_decoder.py:225-239 */

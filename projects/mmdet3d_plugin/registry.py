@@ -48,6 +48,8 @@ HAVE_MMDET3D = _real('mmdet3d.models.builder', 'NECKS') is not None
 NECKS = _real('mmdet3d.models.builder', 'NECKS') or Registry('neck')
 HEADS = _real('mmdet3d.models.builder', 'HEADS') or Registry('head')
 BBOX_CODERS = _real('mmdet.core.bbox.builder', 'BBOX_CODERS') or Registry('bbox_coder')
+TRANSFORMER_LAYER = _real('mmcv.cnn.bricks.registry', 'TRANSFORMER_LAYER') or Registry('transformer layer')
+ATTENTION = _real('mmcv.cnn.bricks.registry', 'ATTENTION') or Registry('attention')
 
 
 def load_config(path):
@@ -56,6 +58,12 @@ def load_config(path):
     with open(path) as f:
         exec(compile(f.read(), path, 'exec'), ns)
     return {k: v for k, v in ns.items() if not k.startswith('__')}
+
+
+def build_neck(cfg):
+    """Build cfg.model.imgpts_neck alone (e.g. the ++ config, whose decoder variant is outside this repository)."""
+    model = cfg['model'] if 'model' in cfg else cfg
+    return NECKS.build(model['imgpts_neck'])
 
 
 def build_hot_path(cfg):

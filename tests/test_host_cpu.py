@@ -121,6 +121,31 @@ def test_plugin_builds_from_config_with_reference_state_dict_schema(cfg_path):
         assert reg.get(name) is not None
 
 
+def test_plusplus_config_builds_its_neck_with_the_reference_schema():
+    """The reference's UNCHANGED Fusion_0075_plusplus.py builds `imgpts_neck` (FusionTransformerv4 + DeepInteractionLayer
+    + MMRI_P2I / MMRI_I2P / MMRI_I2P_Polar) through the plug-in registries; state_dict keys and shapes equal the
+    oracle's, whose state_dict tools/make_goldens_pp.py loads strictly into the reference classes."""
+    ref_cfg = '/root/reference/projects/configs/nuscenes/Fusion_0075_plusplus.py'
+    if not os.path.exists(ref_cfg):
+        pytest.skip('reference tree not mounted here')
+    import projects.mmdet3d_plugin  # noqa: F401
+    from projects.mmdet3d_plugin.registry import load_config, build_neck, NECKS, TRANSFORMER_LAYER, ATTENTION
+    import oracle.mmri_pp as opp
+    cfg = load_config(ref_cfg)
+    neck = build_neck(cfg)
+    assert type(neck).__name__ == 'FusionTransformerv4'
+    o = opp.FusionTransformerv4(**{k: v for k, v in cfg['model']['imgpts_neck'].items() if k != 'type'})
+    a, b = neck.state_dict(), o.state_dict()
+    assert set(a) == set(b), sorted(set(a) ^ set(b))[:8]
+    for k in a:
+        assert a[k].shape == b[k].shape, k
+    neck.load_state_dict(b, strict=True)
+    for reg, names in ((NECKS, ['FusionTransformerv4']), (TRANSFORMER_LAYER, ['DeepInteractionLayer']),
+                       (ATTENTION, ['MMRI_P2I', 'MMRI_I2P', 'MMRI_I2P_Polar'])):
+        for n in names:
+            assert reg.get(n) is not None, n
+
+
 def test_product_modules_refuse_cpu_and_training():
     from deepinteraction_b200 import mmri
     enc = mmri.DeepInteractionEncoder(1, 8, 8, 16).eval()
