@@ -241,8 +241,203 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def randomize_deform(model, seed):
+    """mmcv initialises sampling_offsets.weight / attention_weights to zero (query-independent sampling): draw them, the
+    LayerNorm affines and the layer scales so that every path of the ++ encoder is exercised."""
+    g = torch.Generator().manual_seed(seed + 17)
+    for m in model.modules():
+        if hasattr(m, 'sampling_offsets') and hasattr(m, 'attention_weights'):
+            m.sampling_offsets.weight.data = torch.randn(m.sampling_offsets.weight.shape, generator=g) * 0.05
+            m.attention_weights.weight.data = torch.randn(m.attention_weights.weight.shape, generator=g) * 0.1
+            m.attention_weights.bias.data = torch.randn(m.attention_weights.bias.shape, generator=g) * 0.1
+        if isinstance(m, torch.nn.LayerNorm):
+            m.weight.data = 1 + 0.2 * torch.randn(m.weight.shape, generator=g)
+            m.bias.data = 0.1 * torch.randn(m.bias.shape, generator=g)
+    for n, p_ in model.named_parameters():
+        if n.endswith('scale'):
+            p_.data.fill_(0.7)
+
+
+def pp_host_frame(batch, seed, n_points=250000):
+    """Config 4 inputs: image levels (B*6,256,112,200), (B*6,256,56,100); BEV maps [(B,512,180,180),
+    (B,256,180,180), (B,256,180,180)]; the base frame's cloud / pillars / camera rig."""
+    from deepinteraction_b200 import synth
+    fr = synth.make_frame_batch(seed, batch=batch, cloud='lidar', n_points=n_points, c_pts=256)
+    g = torch.Generator().manual_seed(seed + 3)
+    p1, p2 = fr['pts_feats'], torch.randn(batch, 256, 180, 180, generator=g)
+    pin = lambda t: t.contiguous().pin_memory() if torch.cuda.is_available() else t
+    fr['img_levels'] = [pin(fr['img_feats']), pin(torch.randn(batch * 6, 256, 56, 100, generator=g))]
+    fr['pts_levels'] = [pin(torch.cat([p1, p2], 1)), pin(p1), pin(p2)]
+    pm = fr['pts_metas']
+    for k in ('pillars', 'pillar_coors', 'pillars_num_points'):
+        pm[k] = pin(pm[k])
+    pm['pts'] = [pin(p) for p in pm['pts']]
+    return fr
+
+
+def run_plusplus(args):
+    """BASELINE.json config 4: the ++ ("deformable") encoder FusionTransformerv4 (Fusion_0075_plusplus.py imgpts_neck),
+    bs = --batch per GPU (default 2: bs=4 on 2 GPUs).  One JSON line like the base workload: `value` with the inputs
+    resident in HBM, `e2e` with host buffers (H2D of the five input maps + pillars / points and D2H of the three output
+    maps inside the timed region), per-kernel table, CPU oracle of the same module for ONE sample as cpu_baseline."""
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device: the product path has no CPU fallback'
+    torch.cuda.set_device(local)
+    device = torch.device('cuda', local)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=device)
+    torch.set_grad_enabled(False)
+    import projects.mmdet3d_plugin  # noqa: F401
+    from projects.mmdet3d_plugin.registry import load_config, build_neck
+    from deepinteraction_b200 import ops, synth, graph as di_graph
+    cfg = load_config(os.path.join(ROOT, 'projects', 'configs', 'nuscenes', 'di_b200_plusplus_hotpath.py'))
+    torch.manual_seed(SEED)
+    neck = build_neck(cfg)
+    synth.randomize_norm_stats(neck, SEED)
+    randomize_deform(neck, SEED)
+    neck = neck.to(device).eval()
+    B = args.batch
+    NF = 3
+    hosts = [pp_host_frame(B, SEED + 1000 * rank + i, n_points=int(250000 * (0.9 + 0.05 * i))) for i in range(NF)]
+    nb = lambda t: t.to(device, non_blocking=True)
+
+    def to_dev(fr):
+        pm = fr['pts_metas']
+        return dict(img=[nb(t) for t in fr['img_levels']], pts=[nb(t) for t in fr['pts_levels']], img_metas=fr['img_metas'],
+                    pts_metas=dict(pillars=nb(pm['pillars']), pillar_coors=nb(pm['pillar_coors']),
+                                   pillars_num_points=nb(pm['pillars_num_points']), pts=[nb(p) for p in pm['pts']]))
+    devs = [to_dev(f) for f in hosts]
+    fwd = lambda d: neck(d['img'], d['pts'], d['img_metas'], d['pts_metas'])
+    W, K = max(args.warmup, 3), args.steps
+    for _ in range(3):
+        for d in devs:
+            out = fwd(d)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+    for i in range(W):
+        fwd(devs[i % NF])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        barrier()
+        l0 = ops.LAUNCHES[0]
+        e0.record()
+        for i in range(K):
+            out = fwd(devs[i % NF])
+        e1.record()
+        barrier()
+        launches = ops.LAUNCHES[0] - l0
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        # end to end: host -> device copies of every input of the step, forward, device -> host of the three outputs
+        flat = lambda fr: list(fr['img_levels']) + list(fr['pts_levels'])
+        dset = dict(img=[torch.empty_like(t) for t in devs[0]['img']], pts=[torch.empty_like(t) for t in devs[0]['pts']])
+        outs_host = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in (out[0], out[1][0], out[1][1])]
+        h2d_b = int(np.mean([sum(t.numel() * 4 for t in flat(f)) + sum(v.numel() * v.element_size() for k_, v in
+                             f['pts_metas'].items() if k_ != 'pts') + sum(p.numel() * 4 for p in f['pts_metas']['pts'])
+                             for f in hosts]))
+
+        def e2e_step(i):
+            fh = hosts[i % NF]
+            for dst, src in zip(dset['img'] + dset['pts'], flat(fh)):
+                dst.copy_(src, non_blocking=True)
+            pm = fh['pts_metas']
+            o = neck(dset['img'], dset['pts'], fh['img_metas'],
+                     dict(pillars=nb(pm['pillars']), pillar_coors=nb(pm['pillar_coors']),
+                          pillars_num_points=nb(pm['pillars_num_points']), pts=[nb(p) for p in pm['pts']]))
+            for dst, src in zip(outs_host, (o[0], o[1][0], o[1][1])):
+                dst.copy_(src, non_blocking=True)
+        for i in range(3):
+            e2e_step(i)
+        barrier()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record()
+        for i in range(K):
+            e2e_step(i)
+        e3.record()
+        barrier()
+        ms_e2e = max_over_ranks(e2.elapsed_time(e3))
+    clocks = clk.summary()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    frames = B * world * K
+    pk = peaks()
+    di_graph.ENABLED[0] = False
+    neck._graphs.clear()
+    ops.PROFILE[0] = []
+    for _ in range(2):
+        fwd(devs[0])
+    torch.cuda.synchronize()
+    agg = {}
+    for name, a, b, nbytes, flops, mod in ops.PROFILE[0]:
+        d = agg.setdefault(name.split(' ')[0], dict(ms=0.0, n=0, bytes=0, flops=0))
+        d['ms'] += a.elapsed_time(b)
+        d['n'] += 1
+        d['bytes'] += nbytes
+        d['flops'] += flops
+    ops.PROFILE[0] = None
+    di_graph.ENABLED[0] = True
+    tot = sum(d['ms'] for d in agg.values())
+    kernels = [dict(name=n, launches_per_step=d['n'] / 2, ms_per_step=d['ms'] / 2, share=d['ms'] / tot,
+                    avg_us=d['ms'] / d['n'] * 1e3, gbs=d['bytes'] / max(d['ms'], 1e-9) / 1e6)
+               for n, d in sorted(agg.items(), key=lambda kv: -kv[1]['ms'])]
+    top = kernels[0]
+    roof = dict(bound='hbm', achieved=top['gbs'], peak=pk['hbm'], unit='GB/s', frac=top['gbs'] / pk['hbm'], kernel=top['name'],
+                traffic=None, peak_source=pk['src'], share_of_step=top['share'], avg_launch_us=top['avg_us'])
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        import oracle.mmri_pp as opp
+        cores = usable_cores()
+        torch.set_num_threads(cores)
+        try:
+            with Deadline(170):
+                o = opp.FusionTransformerv4(**{k: v for k, v in cfg['model']['imgpts_neck'].items() if k != 'type'}).eval()
+                o.load_state_dict({k: v.detach().cpu() for k, v in neck.state_dict().items()}, strict=True)
+                f1 = pp_host_frame(1, SEED + 77, n_points=120000)
+                t0 = time.perf_counter()
+                r_img, r_pts = o(list(f1['img_levels']), list(f1['pts_levels']), f1['img_metas'], f1['pts_metas'])
+                dt = time.perf_counter() - t0
+            d1 = to_dev(f1)
+            g_img, g_pts = fwd(d1)
+            rel = lambda a, b: float((a.cpu() - b).abs().max() / b.abs().max().clamp_min(1e-12))
+            cpu = dict(value=1.0 / dt, unit='frames/s', cores=cores, kind='port',
+                       sample='1 sample (6 cameras) of the same workload through oracle/mmri_pp.py (reference math, fp32)',
+                       max_rel_err_vs_gpu=max(rel(g_img, r_img), rel(g_pts[1], r_pts[1])))
+        except TimeoutError:
+            cpu = dict(value=None, unit='frames/s', cores=cores, kind='port', sample='1 sample did not finish within 170 s')
+    line = dict(metric='frames/sec ++ MMRI encoder (FusionTransformerv4), 180x180 BEV / 6 cams x 2 levels', value=frames / (ms * 1e-3),
+                unit='frames/s', n_gpus=world, steps=K, warmup=W, ms_per_step=ms / K, higher_is_better=True, scaling='weak',
+                vs_baseline=None, dtype='fp32', data='synthetic',
+                config=dict(workload='DeepInteraction++ Fusion_0075_plusplus imgpts_neck (deformable variant), bs=%d/GPU' % B,
+                            global_batch=B * world, parallelism=f'dp{world} (independent frames, no data-path collective)',
+                            l2='inputs (%.0f MB/step) larger than L2; %d distinct frames cycled' % (h2d_b / 1e6, NF)),
+                clocks=clocks, e2e=dict(value=frames / (ms_e2e * 1e-3), unit='frames/s', h2d_bytes_per_step=h2d_b,
+                                        d2h_bytes_per_step=int(sum(t.numel() * 4 for t in outs_host)), ms_per_step=ms_e2e / K),
+                gpu_launches=launches, launches_per_step=launches / K, roofline=roof, cpu_baseline=cpu, kernels=kernels[:12])
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument('--workload', default='base', choices=['base', 'plusplus'],
+                    help='base = BASELINE.json config 2 (the headline metric); plusplus = config 4 (++ encoder)')
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=30)
     ap.add_argument('--warmup', type=int, default=5)
@@ -257,6 +452,10 @@ def main():
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
+    if args.workload == 'plusplus':
+        if args.batch == 1:
+            args.batch = 2                       # config 4: bs=4 on 2 GPUs
+        return run_plusplus(args)
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))

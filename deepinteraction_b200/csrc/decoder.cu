@@ -455,6 +455,37 @@ rows_finish_kernel(const float* __restrict__ part, int nsplit, size_t split_stri
   }
 }
 
+// Fast path of rows_finish for the map-sized calls of the ++ encoder (C == 128, one partial, 16-byte aligned rows):
+// one warp per row, one float4 per lane -- 512 contiguous bytes in and out per row.
+__global__ void __launch_bounds__(256)
+rows_finish_c128_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ bias, const float* __restrict__ res,
+                        int ldres, const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ out,
+                        int ldo, const int* __restrict__ zero_if_neg, int M, int act, float eps) {
+  const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (m >= M) return;
+  float4 a = ldg4(x + (size_t)m * ldx + lane * 4);
+  if (bias) {
+    const float4 b = ldg4(bias + lane * 4);
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+  }
+  if (res) {
+    const float4 r = ldg4(res + (size_t)m * ldres + lane * 4);
+    a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
+  }
+  if (gamma) {
+    const float mean = warp_sum(a.x + a.y + a.z + a.w) * (1.f / 128.f);
+    const float dx = a.x - mean, dy = a.y - mean, dz = a.z - mean, dw = a.w - mean;
+    const float var = warp_sum(dx * dx + dy * dy + dz * dz + dw * dw) * (1.f / 128.f);
+    const float rstd = 1.f / sqrtf(var + eps);
+    const float4 g = ldg4(gamma + lane * 4), b = ldg4(beta + lane * 4);
+    a = make_float4(dx * rstd * g.x + b.x, dy * rstd * g.y + b.y, dz * rstd * g.z + b.z, dw * rstd * g.w + b.w);
+  }
+  if (zero_if_neg && zero_if_neg[m] < 0) a = make_float4(0.f, 0.f, 0.f, 0.f);
+  else a = make_float4(di_act(a.x, act), di_act(a.y, act), di_act(a.z, act), di_act(a.w, act));
+  *reinterpret_cast<float4*>(out + (size_t)m * ldo + lane * 4) = a;
+}
+
 // pred [M, NP]: center(0,1) height(2) dim(3..5) rot(6,7) vel(8,9) heatmap(10..).  center += query_pos;
 // rows whose query fell on no image (win < 0) take the first layer's prediction (decoder.py:290-295).
 __global__ void pred_finish_kernel(float* __restrict__ pred, float* __restrict__ qpos, const float* __restrict__ first,
@@ -966,8 +997,13 @@ int di_rows_finish_f32(const float* part, int nsplit, long long split_stride, in
                        const int* zero_if_neg, int M, int C, int act, float eps, cudaStream_t stream) {
   DI_CHECK_ARG(part && out && M > 0 && C > 0 && C <= 512 && nsplit >= 1, "di_rows_finish_f32: bad argument");
   DI_CHECK_ARG((gamma == nullptr) == (beta == nullptr), "di_rows_finish_f32: gamma and beta go together");
-  rows_finish_kernel<<<di_cdiv(M, 8), 256, 0, stream>>>(part, nsplit, (size_t)split_stride, ldp, bias, res, ldres, gamma,
-                                                       beta, out, ldo, zero_if_neg, M, C, act, eps);
+  const bool al = (((uintptr_t)part | (uintptr_t)out | (uintptr_t)bias | (uintptr_t)res | (uintptr_t)gamma | (uintptr_t)beta) & 15) == 0;
+  if (C == 128 && nsplit == 1 && M >= 4096 && al && ldp % 4 == 0 && ldo % 4 == 0 && (!res || ldres % 4 == 0))
+    rows_finish_c128_kernel<<<di_cdiv(M, 8), 256, 0, stream>>>(part, ldp, bias, res, ldres, gamma, beta, out, ldo, zero_if_neg,
+                                                              M, act, eps);
+  else
+    rows_finish_kernel<<<di_cdiv(M, 8), 256, 0, stream>>>(part, nsplit, (size_t)split_stride, ldp, bias, res, ldres, gamma,
+                                                         beta, out, ldo, zero_if_neg, M, C, act, eps);
   DI_CHECK_LAUNCH("di_rows_finish_f32");
   return DI_OK;
 }

@@ -20,7 +20,8 @@ import torch
 import torch.nn as nn
 
 from . import fold, geom, ops
-from .mmri import Geometry, MMRI_I2P as _I2PHolder
+from .graph import GraphCache
+from .mmri import Geometry, MMRI_I2P as _I2PHolder, _pow2_cap, POINT_CAP_MIN
 
 PC_RANGE = (-54.0, -54.0, -5.0, 54.0, 54.0, 3.0)
 
@@ -203,6 +204,7 @@ class FusionTransformerv4(nn.Module):
         self._pack_key = None
         self._side_streams = {}
         self.last_geometry = None
+        self._graphs = GraphCache()
 
     # -- packing -----------------------------------------------------------------------------------
     def _state_key(self):
@@ -241,6 +243,7 @@ class FusionTransformerv4(nn.Module):
         pk['img'] = [self._pack_layer(l, device) for l in self.img_fusion_blocks]
         pk['pts'] = [self._pack_layer(l, device) for l in self.pts_fusion_blocks]
         self._pack, self._pack_key = pk, key
+        self._graphs.clear()
         return pk
 
     # -- forward -----------------------------------------------------------------------------------
@@ -299,31 +302,59 @@ class FusionTransformerv4(nn.Module):
         raise NotImplementedError(ap['kind'])
 
     def forward_nhwc(self, img_feats, pts_feats, img_metas, pts_metas):
-        """-> img [B*V,h,w,C], pts_conv [B,Y,X,C], pts [B,Y,X,C] (pixel-major, fp32)."""
+        """-> img [B*V,h,w,C], pts_conv [B,Y,X,C], pts [B,Y,X,C] (pixel-major, fp32).  The kernel schedule is replayed
+        from a CUDA graph once an input signature repeats (graph.py: feature maps bound by address, per-frame pillar /
+        point arrays staged at fixed capacities, camera constants uploaded per replay)."""
         if self.training:
             raise NotImplementedError('libdi_b200 FusionTransformerv4 is forward/eval only (call .eval())')
-        pk = self.pack()
-        img_feats, pts_feats = list(img_feats), list(pts_feats)
+        self.pack()
+        img_feats, pts_feats = [t.contiguous() for t in img_feats], [t.contiguous() for t in pts_feats]
+        dev_ = img_feats[0].device
+        pillars = pts_metas['pillars'].to(device=dev_, dtype=torch.float32).contiguous()
+        coors = pts_metas['pillar_coors'].to(device=dev_, dtype=torch.int32).contiguous()
+        npts = pts_metas['pillars_num_points'].to(device=dev_, dtype=torch.int32).contiguous()
+        pts_list = [p.to(device=dev_, dtype=torch.float32) for p in pts_metas['pts']]
+        proj_h, i2l_h = geom.camera_rows_host(img_metas)
+        consts = [proj_h, i2l_h]
+        has_polar = any(a['kind'] == 'polar' for l in self._pack['pts'] for a in l['attn'])
+        if has_polar:
+            from .polar import polar_consts_host
+            consts += list(polar_consts_host(img_metas))
+        B_, _, Y_, X_ = pts_feats[0].shape
+        staged = [pillars, coors, npts] + pts_list
+        caps = [_pow2_cap(pillars.shape[0], B_ * Y_ * X_)] * 3 + [_pow2_cap(p.shape[0], POINT_CAP_MIN) for p in pts_list]
+        consts.append(torch.tensor([pillars.shape[0]] + [p.shape[0] for p in pts_list], dtype=torch.int32))
+        n_img = len(img_feats)
+        inputs = img_feats + pts_feats
+        sig = (tuple(tuple(t.shape) for t in inputs), tuple(tuple(t.shape[1:]) for t in staged), geom.input_hw(img_metas),
+               id(self._pack))
+
+        def fn(ins, cs, st):
+            pm = dict(pillars=st[0], pillar_coors=st[1], pillars_num_points=st[2], pts=list(st[3:]))
+            return self._schedule(list(ins[:n_img]), list(ins[n_img:]), img_metas, pm, cs)
+        return self._graphs.run(sig, inputs, consts, fn, staged=staged, caps=caps)
+
+    def _schedule(self, img_feats, pts_feats, img_metas, pm, consts):
+        pk = self._pack
         dev_ = img_feats[0].device
         C = self.hidden_channel
-        pm = dict(pts_metas)
-        pm['pillars'] = pm['pillars'].to(device=dev_, dtype=torch.float32).contiguous()
-        pm['pillar_coors'] = pm['pillar_coors'].to(device=dev_, dtype=torch.int32).contiguous()
-        pm['pillars_num_points'] = pm['pillars_num_points'].to(device=dev_, dtype=torch.int32).contiguous()
-        pm['pts'] = [p.to(device=dev_, dtype=torch.float32) for p in pm['pts']]
+        counts = consts[-1]
         BV, _, h, w = img_feats[0].shape
         B, _, Y, X = pts_feats[0].shape
         cur_id = torch.cuda.current_stream().cuda_stream
         if cur_id not in self._side_streams:
             self._side_streams[cur_id] = torch.cuda.Stream(device=dev_)
-        g = Geometry(img_metas, pm, (h, w), (Y, X), dev_, side_stream=self._side_streams[cur_id])
+        g = Geometry(img_metas, pm, (h, w), (Y, X), dev_, side_stream=self._side_streams[cur_id], cams=(consts[0], consts[1]),
+                     counts=counts)
         self.last_geometry = g
-        conv = lambda x, name: ops.conv3x3(x.contiguous(), *pk[name], cout=C, x_nhwc=False)
-        pts_conv = conv(pts_feats.pop(0), 'shared_conv_pts')
+        conv = lambda x, name: ops.conv3x3(x, *pk[name], cout=C, x_nhwc=False)
+        pts_conv = conv(pts_feats[0], 'shared_conv_pts')
         ms_img = [conv(f, 'multi_scale_conv_img') for f in img_feats]
-        ms_pts = [conv(f, 'multi_scale_conv_pts') for f in pts_feats]
+        ms_pts = [conv(f, 'multi_scale_conv_pts') for f in pts_feats[1:]]
         new_img, new_pts = ms_img[0], ms_pts[0]
-        ctx = dict(g=g, pm=pm, counts=None, img_metas=img_metas, B=B, V=BV // B)
+        ctx = dict(g=g, pm=pm, counts=counts, img_metas=img_metas, B=B, V=BV // B)
+        if len(consts) > 3:
+            ctx['polar_consts'] = tuple(consts[2:5])
         for i in range(self.num_layers):
             t_img = self._layer(pk['img'][i], new_img, new_pts, ms_img, ctx)
             t_pts = self._layer(pk['pts'][i], new_pts, new_img, ms_pts, ctx)

@@ -67,7 +67,9 @@ def test_config5_decoder_300_queries_256_bev():
     assert torch.equal(m.query_labels.cpu(), o.query_labels)
     for a, b in zip(m.on_the_image_mask, o.on_the_image_mask):
         assert torch.equal(a.cpu(), b)
-XX, [(512, 1, (128, 352), 64, 8000), (128, 2, (512, 1408), 256, 120000)])
+
+
+@pytest.mark.parametrize('C,views,hw,bev,npts', [(512, 1, (128, 352), 64, 8000), (128, 2, (512, 1408), 256, 120000)])
 def test_config5_encoder_shapes(C, views, hw, bev, npts):
     """Encoder at config 5's hidden width 512 (reduced map sizes so that the CPU oracle stays in seconds) and at its
     full map sizes (256x256 BEV, 128x352 maps from 512x1408 inputs) with C = 128 and two cameras."""
