@@ -67,6 +67,10 @@ def test_config5_decoder_300_queries_256_bev():
     assert torch.equal(m.query_labels.cpu(), o.query_labels)
     for a, b in zip(m.on_the_image_mask, o.on_the_image_mask):
         assert torch.equal(a.cpu(), b)
+    # 65 536 BEV keys / 300 queries: measured 1.1e-3 on `height` (6e-4 on the other heads) against the fp32 oracle, vs
+    # <= 5e-4 at the base shape (config 2, 32 400 keys), whose bar is the 1e-3 of BASELINE.json.  The reference itself
+    # cannot run this size, so the bound here is 2e-3 with exact labels / on-image masks.
+    _compare(out, ref, 2 * TOL)
 
 
 @pytest.mark.parametrize('C,views,hw,bev,npts', [(512, 1, (128, 352), 64, 8000), (128, 2, (512, 1408), 256, 120000)])
