@@ -39,6 +39,8 @@ SIGNATURES = {
     'di_lcab_window_tc_set_sm_limit': [_i],
     'di_lcab_window_tc_set_debug': [_i],
     'di_lcab_window_tc_debug_read': [ctypes.POINTER(ctypes.c_longlong)],
+    'di_lcab_proj_f32': [_p, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p],
+    'di_lcab_proj_set_sm_limit': [_i],
     'di_set_window_ffma': [_i],
     'di_locatt_cc2k_f32': [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     'di_locatt_ck2c_ori_f32': [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
@@ -51,6 +53,8 @@ SIGNATURES = {
     'di_depth_complete': [_p, _p, _p, _p, _i, _i, _i, _p],
     'di_lift_grid': [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _fp, _p],
     'di_bev_sample_f32': [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
+    # pillar.cu
+    'di_pillarize_f32': [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int), _p, _i, _i, _i, _i, _i, _i, _fp, _p, _p, _p, _p, _p, _i, _p],
     # deform.cu
     'di_msdeform_f32': [_p, _p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, ctypes.POINTER(ctypes.c_int), _p],
     'di_axpy_f32': [_p, _p, _p, _p, _ll, _p],

@@ -106,7 +106,8 @@ def _pack_lcab(blk, device):
     return dict(C=C, ks=blk.kernel_size,
                 w_self=Wt(torch.cat([wq1, wk1, wv], 0)), b_self=d(torch.cat([bq1, bk1, bv], 0)),
                 w_q1=Wt(wq1), b_q1=d(bq1), w_kv1=Wt(torch.cat([wk1, wv], 0)), b_kv1=d(torch.cat([bk1, bv], 0)),
-                w_q2=Wt(wq2), b_q2=d(bq2), w_k2=Wt(wk2), b_k2=d(bk2))
+                w_q2=Wt(wq2), b_q2=d(bq2), w_k2=Wt(wk2), b_k2=d(bk2),
+                w_2=Wt(torch.cat([wq2, wk2], 0)), b_2=d(torch.cat([bq2, bk2], 0)))
 
 
 def lcab_forward(pk, target, source, N, H, W):
@@ -116,6 +117,10 @@ def lcab_forward(pk, target, source, N, H, W):
     C = pk['C']
     pre = ops.can_presplit(N * H * W, C, pk['ks'])
     tc = ops.can_window_tc(N * H * W, C, pk['ks'])       # tcgen05 window kernel: planar operands (split kind 3)
+    if tc and ops.LCAB_PROJ[0] and target.is_contiguous() and source.is_contiguous():
+        # all five projections in one launch, q1 / k1 stay on chip (lcab_proj.cu)
+        q, k, v = ops.lcab_proj(target, source, pk['w_self'], pk['b_self'], pk['w_2'], pk['b_2'])
+        return ops.lcab_window_tc(q, k, v, N, H, W, C)
     if target is source:
         if pre:
             t = ops.linear_split([source], pk['w_self'], pk['b_self'], ops.ACT_RELU, 2 * C, 3 if tc else 2)    # q1 | k1 | v(split)
@@ -265,7 +270,12 @@ class DeepInteractionEncoder(nn.Module):
 
     @staticmethod
     def _canon_pts_metas(pts_metas, device):
+        """pts_metas without 'pillars' (or pillars=None): the pillars are generated on the GPU from pts_metas['pts']
+        inside the schedule (ops.pillarize: the reference's 'pillar' voxelisation, detectors/deepinteraction.py:132-139)."""
         pm = dict(pts_metas)
+        if pm.get('pillars') is None:
+            pm['pillars'] = pm['pillar_coors'] = pm['pillars_num_points'] = None
+            return pm
         pm['pillars'] = pm['pillars'].to(device=device, dtype=torch.float32).contiguous()
         pm['pillar_coors'] = pm['pillar_coors'].to(device=device, dtype=torch.int32).contiguous()
         pm['pillars_num_points'] = pm['pillars_num_points'].to(device=device, dtype=torch.int32).contiguous()
@@ -285,17 +295,21 @@ class DeepInteractionEncoder(nn.Module):
         proj_h, i2l_h = geom.camera_rows_host(img_metas)
         inputs = [img_feats.contiguous(), pts_feats.contiguous()]
         # per-frame arrays (row counts change every frame): staged at bucketed capacities, live counts via `consts`
-        staged = [pm['pillars'], pm['pillar_coors'], pm['pillars_num_points']] + pts_list
+        auto = pm['pillars'] is None                # generate the pillars on the GPU inside the schedule
+        staged = ([] if auto else [pm['pillars'], pm['pillar_coors'], pm['pillars_num_points']]) + pts_list
         # pillars: at most one per BEV cell (the physical maximum) -> a capacity that never changes for a given map size
         B_, _, Y_, X_ = pts_feats.shape
-        caps = [_pow2_cap(pm['pillars'].shape[0], B_ * Y_ * X_)] * 3 + [_pow2_cap(p.shape[0], POINT_CAP_MIN) for p in pts_list]
-        counts_h = torch.tensor([pm['pillars'].shape[0]] + [p.shape[0] for p in pts_list], dtype=torch.int32)
-        sig = (tuple(tuple(t.shape) for t in inputs), tuple(tuple(t.shape[1:]) for t in staged),
+        caps = ([] if auto else [_pow2_cap(pm['pillars'].shape[0], B_ * Y_ * X_)] * 3) + \
+            [_pow2_cap(p.shape[0], POINT_CAP_MIN) for p in pts_list]
+        counts_h = torch.tensor([0 if auto else pm['pillars'].shape[0]] + [p.shape[0] for p in pts_list], dtype=torch.int32)
+        sig = (tuple(tuple(t.shape) for t in inputs), tuple(tuple(t.shape[1:]) for t in staged), auto,
                geom.input_hw(img_metas), id(self._pack))
+        k0 = 0 if auto else 3
 
         def fn(ins, consts, st):
-            pmx = dict(pillars=st[0], pillar_coors=st[1], pillars_num_points=st[2], pts=st[3:])
-            return self._schedule(ins[0], ins[1], img_metas, pmx, st[3:], (consts[0], consts[1]), None, counts=consts[2])
+            pmx = dict(pillars=None, pillar_coors=None, pillars_num_points=None) if auto else \
+                dict(pillars=st[0], pillar_coors=st[1], pillars_num_points=st[2])
+            return self._schedule(ins[0], ins[1], img_metas, pmx, st[k0:], (consts[0], consts[1]), None, counts=consts[2])
         return self._graphs.run(sig, inputs, [proj_h, i2l_h, counts_h], fn, staged=staged, caps=caps)
 
     def _schedule(self, img_feats, pts_feats, img_metas, pm, pts_list, cams, debug, counts=None):
@@ -310,6 +324,11 @@ class DeepInteractionEncoder(nn.Module):
             self._side_streams[cur_id] = torch.cuda.Stream(device=dev_)
         pm = dict(pm)
         pm['pts'] = pts_list
+        n_pil_dev = None if counts is None else counts[0:1]
+        if pm['pillars'] is None:                   # (f1) pillars from the raw points, live count stays on the device
+            pts_c = [p.contiguous() for p in pts_list]
+            pm['pillars'], pm['pillar_coors'], pm['pillars_num_points'], n_pil_dev = ops.pillarize(
+                pts_c, (Y, X), PC_RANGE, 20, None if counts is None else counts[1:1 + B])
         g = Geometry(img_metas, pm, (h, w), (Y, X), dev_, want_debug=debug is not None,
                      side_stream=self._side_streams[cur_id], cams=cams, counts=counts)
         self.last_geometry = g
@@ -325,7 +344,7 @@ class DeepInteractionEncoder(nn.Module):
         for li, lp in enumerate(pk['layers']):
             img_r, pts_r = img.view(BV * h * w, C), pts.view(B * Y * X, C)
             with ops.module('MMRI_I2P', n_pil * (C * 4 + 20 * 12 + 16) + F_i + F_b):
-                i2p = self.i2p(lp, pts, img, pm, g, None if counts is None else counts[0:1])
+                i2p = self.i2p(lp, pts, img, pm, g, n_pil_dev)
             with ops.module('LCAB_self_bev', 2 * F_b, lcab_flops(B * Y * X)):
                 p2p = lcab_forward(lp['p_iml'], pts_r, pts_r, B, Y, X)
             with ops.module('P_out_proj+P_integration', 4 * F_b, 2 * B * Y * X * C * 3 * C):

@@ -189,6 +189,22 @@ def lcab_window_tc(q, k, v, N, H, W, C, out=None):
     return out
 
 
+LCAB_PROJ = [os.environ.get('DI_B200_LCAB_PROJ', '1') != '0']   # fused projection chain (lcab_proj.cu) in front of the tcgen05 window kernel
+
+
+def lcab_proj(x_t, x_s, w1, b1, w2, b2):
+    """q, k, v (planar operands of lcab_window_tc) from the target / source rows in ONE launch: w1 = Weight of
+    [q1 | k1 | v] (384 x 128), w2 = Weight of [q2 | k2] (256 x 128), BN folded."""
+    M = x_t.shape[0]
+    assert x_t.shape[1] == 128 and x_s.shape == x_t.shape and w1.shape == (384, 128) and w2.shape == (256, 128)
+    out = torch.empty(3, M, 128, device=x_t.device, dtype=torch.float32)
+    (pt, lt), (ps, ls) = _rows(x_t), _rows(x_s)
+    _call('di_lcab_proj_f32', pt, lt, ps, ls, _ptr(w1.bh), _ptr(w1.bm), _ptr(b1), _ptr(w2.bh), _ptr(w2.bm), _ptr(b2),
+          _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), M, _stream(),
+          nbytes=4 * M * 128 * (4 if x_t is x_s else 5), flops=2 * 5 * M * 128 * 128)
+    return out[0], out[1], out[2]
+
+
 def lcab_window_pre(q, k, v, N, H, W, C, out=None):
     """lcab_window for pre-split q, k (kind 1) and v (kind 2) row views."""
     if out is None:
@@ -251,6 +267,30 @@ def scatter_rows(rows, cnt, coors, map_nhwc, n_dev=None):
     _call('di_scatter_rows_f32', _ptr(rows), _ptr(cnt), _ptr(coors), _ptr(map_nhwc), coors.shape[0], Y, X, C,
           _ptr(n_dev), _stream())
     return map_nhwc
+
+
+def pillarize(pts_list, bev_hw, pc_range, max_pts=20, n_dev=None, cap=None):
+    """GPU pillar generation.  pts_list: B device tensors [n_b, >=3] (capacity rows when n_dev [B] int32 holds the live
+    counts).  -> pillars [cap, max_pts, pdim], coors [cap, 4] int32, npts [cap] int32, n_pillars [1] int32 (device)."""
+    B = len(pts_list)
+    Y, X = bev_hw
+    dev = pts_list[0].device
+    pdim = pts_list[0].shape[1]
+    assert all(p.dtype == torch.float32 and p.stride(1) == 1 and p.shape[1] == pdim and p.stride(0) == pts_list[0].stride(0)
+               for p in pts_list)
+    caps = [int(p.shape[0]) for p in pts_list]
+    cap = B * Y * X if cap is None else cap
+    work = torch.empty(4 * B * Y * X + 1 + B * max(caps + [1]) + sum(caps) + 1, device=dev, dtype=torch.int32)
+    pillars = torch.empty(cap, max_pts, pdim, device=dev, dtype=torch.float32)
+    coors = torch.zeros(cap, 4, device=dev, dtype=torch.int32)
+    npts = torch.zeros(cap, device=dev, dtype=torch.int32)
+    n_out = torch.empty(1, device=dev, dtype=torch.int32)
+    ptrs = (ctypes.c_void_p * B)(*[p.data_ptr() if p.shape[0] else None for p in pts_list])
+    ncap = (ctypes.c_int * B)(*caps)
+    rng = (ctypes.c_float * 6)(*[float(v) for v in pc_range])
+    _call('di_pillarize_f32', ptrs, ncap, _ptr(n_dev), B, pts_list[0].stride(0), pdim, Y, X, max_pts, rng, _ptr(work),
+          _ptr(pillars), _ptr(coors), _ptr(npts), _ptr(n_out), cap, _stream())
+    return pillars, coors, npts, n_out
 
 
 def scatter_rows_add(rows, cnt, coors, map_nhwc, n_dev=None):

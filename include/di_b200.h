@@ -121,6 +121,17 @@ int di_lcab_window_tc_set_sm_limit(int n); /* persistent grid of the kernel abov
 int di_lcab_window_tc_set_debug(int on);    /* diagnostics: clock64 pipeline trace of CTA 0 ... */
 int di_lcab_window_tc_debug_read(long long* host_buf); /* ... 6 x 256 stamps (tools/trace_window.py) */
 
+/* The five 1x1 Conv(+folded BN)+ReLU projections of LocalContextAttentionBlock (models/utils/encoder_utils.py:92-131:
+ * query_project 2 layers on the target map x_t, key_project 2 layers and value_project 1 layer on the source map x_s)
+ * as ONE tcgen05 launch writing q, k, v in the planar operand format of di_lcab_window_tc_f32; the first-stage
+ * activations stay in tensor memory (lcab_proj.cu).  x_t / x_s [M,128] fp32 rows (x_s == x_t: self attention);
+ * W1_hi / W1_mid [384,128] bf16 rows (q1 | k1 | v), b1 [384]; W2_hi / W2_mid [256,128] rows (q2 | k2), b2 [256];
+ * q, k, v [M,128] words each (contiguous).  Results equal the unfused di_linear_tcb_split_f32 chain bit for bit. */
+int di_lcab_proj_f32(const float* x_t, int ld_t, const float* x_s, int ld_s, const void* W1_hi, const void* W1_mid,
+                     const float* b1, const void* W2_hi, const void* W2_mid, const float* b2, float* q, float* k, float* v,
+                     int M, cudaStream_t stream);
+int di_lcab_proj_set_sm_limit(int n); /* persistent grid of the kernel above uses at most n CTAs (0 = all) */
+
 /* test/diagnostic hook: 1 = always use the FFMA window kernel, 0 = tensor-core (mma.sync 3xTF32) kernel when
  * ksize == 9 and C % 32 == 0 (default) */
 int di_set_window_ffma(int on); /* test hook: 0 = bf16-split mma.sync kernel (default), 1 = FFMA, 2 = 3xTF32 mma.sync */
@@ -167,6 +178,20 @@ int di_lift_grid(const float* depth, const float* i2l, float* grid_xy, int n_img
 /* warped = grid_sample(bev, grid) with the lift mask folded into the grid (models/utils/encoder_utils.py:195-196). */
 int di_bev_sample_f32(const float* bev, const float* grid_xy, float* out, int B, int V, int hw, int Yb, int Xb, int C,
                       cudaStream_t stream);
+
+/* ---- pillar generation (pillar.cu) ------------------------------------------------------------------- */
+
+/* Raw points -> pts_metas {pillars, pillar_coors, pillars_num_points} on the GPU, the live pillar count left in device
+ * memory: replaces the spconv 2.1.21 PointToVoxel wrapper of the reference for the 'pillar' voxelisation
+ * (models/updated_modules/sparse_voxelize.py:9-60; models/detectors/deepinteraction.py:132-139,151-171).
+ * cell = floor((xy - range_min) / cell_size) on a Y x X grid over range[0..1]..range[3..4], z strictly inside
+ * (range[2], range[5]); a pillar keeps its T lowest-index points in index order, pillars are emitted sorted by
+ * (b, y, x), coors = (b, 0, y, x) -- deterministic where spconv's hash insertion order is not.
+ * pts_ptrs / n_caps / range: HOST arrays (B device pointers, B capacities, 6 floats); n_dev: device int32 [B] live point
+ * counts or NULL; work: device int32 [4*B*Y*X + 1 + B*max(n_caps) + sum(n_caps)]; outputs at capacity `cap` rows. */
+int di_pillarize_f32(const float* const* pts_ptrs, const int* n_caps, const int* n_dev, int B, int stride, int pdim,
+                     int Y, int X, int T, const float* range, int* work, float* pillars, int* coors, int* npts,
+                     int* n_pillars, int cap, cudaStream_t stream);
 
 /* ---- ++ ("deformable") encoder, DeepInteraction++ (deform.cu) ------------------------------------------ */
 

@@ -22,6 +22,15 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip)
 
 
+@pytest.fixture(autouse=True)
+def _restore_grad_mode():
+    """Tests that switch autograd off globally (torch.set_grad_enabled(False)) must not leak it into the next test."""
+    import torch
+    prev = torch.is_grad_enabled()
+    yield
+    torch.set_grad_enabled(prev)
+
+
 def rel_err(a, b):
     """max|a-b| / max|b|  -- the tolerance metric of SURVEY.md 8(d)."""
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))

@@ -162,6 +162,29 @@ def test_window_attention_tcgen05_planar_operands(N, H, W):
     assert torch.equal(out, out2)
 
 
+@pytest.mark.parametrize('M,self_attn', [(1000, True), (134400, False), (128, True), (32400, True)])
+def test_lcab_projection_chain_equals_unfused_layers(M, self_attn):
+    """di_lcab_proj_f32 (q1 / k1 kept in tensor memory) == the unfused di_linear_tcb_split_f32 chain, bit for bit."""
+    from deepinteraction_b200 import ops, fold
+    g = torch.Generator().manual_seed(29)
+    C = 128
+    xt = torch.randn(M, C, generator=g).to(dev())
+    xs = xt if self_attn else torch.randn(M, C, generator=g).to(dev())
+    w1 = fold.Weight(torch.randn(3 * C, C, generator=g) / 11, dev())
+    w2 = fold.Weight(torch.randn(2 * C, C, generator=g) / 11, dev())
+    b1, b2 = torch.randn(3 * C, generator=g).to(dev()), torch.randn(2 * C, generator=g).to(dev())
+    q, k, v = ops.lcab_proj(xt, xs, w1, b1, w2, b2)
+    wq1, wk1, wv = (fold.Weight(w1.w[i * C:(i + 1) * C].cpu().double(), dev()) for i in range(3))
+    wq2, wk2 = (fold.Weight(w2.w[i * C:(i + 1) * C].cpu().double(), dev()) for i in range(2))
+    q1 = ops.linear([xt], wq1, b1[:C].contiguous(), ops.ACT_RELU)
+    k1 = ops.linear([xs], wk1, b1[C:2 * C].contiguous(), ops.ACT_RELU)
+    want_q = ops.linear_split([q1], wq2, b2[:C].contiguous(), ops.ACT_RELU, 0, 3)
+    want_k = ops.linear_split([k1], wk2, b2[C:].contiguous(), ops.ACT_RELU, 0, 3)
+    want_v = ops.linear_split([xs], wv, b1[2 * C:].contiguous(), ops.ACT_RELU, 0, 3)
+    i32 = lambda t: t.contiguous().view(torch.int32)
+    assert torch.equal(i32(q), i32(want_q)) and torch.equal(i32(k), i32(want_k)) and torch.equal(i32(v), i32(want_v))
+
+
 def test_linear_split_planar_format():
     """The dense layer's planar split epilogue (kind 3) == fold.split_rows(plain output, 3), bit for bit, also when
     only the trailing 128 columns of a wider output are split (q1 | k1 | v)."""
@@ -322,6 +345,54 @@ def test_encoder_small_matches_reference_golden(tag):
     assert rel_err(p1.cpu(), gold['pts']) < TOL
     assert rel_err(img.cpu(), gold['img']) < TOL
     print(tag, 'rel err img %.2e pts %.2e' % (rel_err(img.cpu(), gold['img']), rel_err(p1.cpu(), gold['pts'])))
+
+
+@pytest.mark.parametrize('cloud,n', [('lidar', 60000), ('dense', 9000)])
+def test_gpu_pillarisation_is_bit_exact(cloud, n):
+    """(f1) di_pillarize_f32 == synth.pillarize (lowest-index points first, pillars sorted by (b, y, x)), bit for bit,
+    for exact-size inputs and for capacity buffers with device-side counts; points on cell borders included."""
+    from deepinteraction_b200 import ops, synth
+    rng = np.random.default_rng(77)
+    pts = [synth.make_points(n, rng, cloud), synth.make_points(n // 3, rng, cloud)]
+    for p in pts:                                   # plant points exactly on pillar borders and on the range limits
+        p[:50, 0] = np.round(p[:50, 0] / 0.6) * 0.6
+        p[50:60, 2] = -5.0
+        p[60:70, 0] = 54.0
+    Y = X = 180
+    pil, coors, cnt = synth.pillarize(pts, pillar=108.0 / X)
+    dpts = [torch.from_numpy(p).to(dev()) for p in pts]
+    g_pil, g_coors, g_cnt, g_n = ops.pillarize(dpts, (Y, X), synth.PC_RANGE, 20)
+    P = int(g_n.item())
+    assert P == len(cnt)
+    assert torch.equal(g_coors[:P].cpu(), torch.from_numpy(coors)) and torch.equal(g_cnt[:P].cpu(), torch.from_numpy(cnt))
+    assert torch.equal(g_pil[:P].cpu(), torch.from_numpy(pil))
+    # capacity buffers (stale rows behind the live count) + device-side counts
+    cap = 1 << 17
+    bufs = [torch.randn(cap, 5, device=dev()) for _ in pts]
+    for b, p in zip(bufs, dpts):
+        b[:p.shape[0]] = p
+    n_dev = torch.tensor([p.shape[0] for p in dpts], dtype=torch.int32, device=dev())
+    c_pil, c_coors, c_cnt, c_n = ops.pillarize(bufs, (Y, X), synth.PC_RANGE, 20, n_dev=n_dev)
+    assert int(c_n.item()) == P and torch.equal(c_pil[:P], g_pil[:P]) and torch.equal(c_coors[:P], g_coors[:P])
+
+
+def test_encoder_generates_pillars_when_not_given():
+    """pts_metas without 'pillars': the encoder pillarises on the GPU and reproduces the run with host-built pillars."""
+    from deepinteraction_b200 import mmri, synth
+    import oracle.mmri as om
+    seed = 1950
+    torch.manual_seed(seed)
+    m = om.DeepInteractionEncoder(2, 16, 24, 128).eval()
+    synth.randomize_norm_stats(m, seed)
+    enc = mmri.DeepInteractionEncoder(2, 16, 24, 128)
+    enc.load_state_dict(m.state_dict(), strict=True)
+    enc = enc.to(dev()).eval()
+    from tools.make_goldens import small_frame
+    fr = synth.to_device(small_frame(seed, aug=True, views=2, c_img=16, c_pts=24, bev=36, batch=2), dev())
+    want = [t.clone() for t in enc.forward_nhwc(fr['img_feats'], fr['pts_feats'], fr['img_metas'], fr['pts_metas'])]
+    got = enc.forward_nhwc(fr['img_feats'], fr['pts_feats'], fr['img_metas'], dict(pts=fr['pts_metas']['pts']))
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
 
 
 def test_encoder_c128_matches_reference_golden():

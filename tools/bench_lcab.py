@@ -43,8 +43,9 @@ def main():
         M = N * H * W
         x = torch.randn(M, C, device=dev)
         y = x if self_attn else torch.randn(M, C, device=dev)
-        for path in ('tcgen05', 'mma.sync'):
-            ops.WINDOW_TC[0] = path == 'tcgen05'
+        for path in ('tcgen05+proj', 'tcgen05', 'mma.sync'):
+            ops.WINDOW_TC[0] = path != 'mma.sync'
+            ops.LCAB_PROJ[0] = path == 'tcgen05+proj'
             for _ in range(3):
                 out = mmri.lcab_forward(pk, x, y, N, H, W)
             torch.cuda.synchronize()
@@ -60,7 +61,7 @@ def main():
                 tot += a.elapsed_time(b)
             prof, ops.PROFILE[0] = ops.PROFILE[0], None
             per = {}
-            for name, e0, e1, nb, fl in prof:
+            for name, e0, e1, nb, fl, _mod in prof:
                 d = per.setdefault(name, [0, 0.0])
                 d[0] += 1
                 d[1] += e0.elapsed_time(e1)
@@ -78,6 +79,7 @@ def main():
                                   kernels={k: round(v[1] / v[0] * 1e3, 1) for k, v in per.items()},
                                   out_checksum=float(out.double().abs().sum()))), flush=True)
     ops.WINDOW_TC[0] = True
+    ops.LCAB_PROJ[0] = True
 
 
 if __name__ == '__main__':
