@@ -5,7 +5,7 @@
 //     q = relu(W_q2 relu(W_q1 x_t + b_q1) + b_q2)      k = relu(W_k2 relu(W_k1 x_s + b_k1) + b_k2)      v = relu(W_v x_s + b_v)
 //
 // written directly in the planar bf16 hi|mid operand format of the tcgen05 window kernel (lcab_tc.cu).  The first-stage
-// activations q1 / k1 never leave the SM: a persistent CTA owns one ROLE (q chain, k chain or v; blockIdx % 3) and keeps
+// activations q1 / k1 never leave the SM: a persistent CTA owns one ROLE (q chain, k chain or v; CTAs dealt 2 : 2 : 1) and keeps
 // that role's weights resident in shared memory (W1 slice + W2 slice, bf16 hi + mid, 128 KB); per 128-row tile
 //   x tile (TMA, fp32) -> splitter warps: bf16 hi/mid -> TENSOR MEMORY -> GEMM 1 (tcgen05.mma, A from TMEM)
 //   -> epilogue warps: bias + ReLU + hi/mid split, written back to tensor memory as the A operand of
@@ -43,6 +43,7 @@ struct PjParams {
   const float* bias1;         // [384]
   const float* bias2;         // [256]
   int* sched;                 // 16 ints: [role] tile counters, [15] done counter
+  int n_chain;                // CTAs per chain role (q, k); the rest of the grid serves v
 };
 
 __global__ void __launch_bounds__(PJ_THREADS, 1)
@@ -71,7 +72,8 @@ lcab_proj_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_constan
   float* bias_s = reinterpret_cast<float*>(base_ptr + BIAS_OFF);   // [0,128) stage-1 bias slice, [128,256) stage-2
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int role = blockIdx.x % 3;
+  // CTAs are dealt 2 : 2 : 1 to the roles: a chain role (two GEMMs + two epilogues per tile) costs twice the v role
+  const int role = (int)blockIdx.x < p.n_chain ? 0 : ((int)blockIdx.x < 2 * p.n_chain ? 1 : 2);
   const bool chain = role < 2;
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
@@ -443,8 +445,10 @@ int di_lcab_proj_f32(const float* x_t, int ld_t, const float* x_s, int ld_s, con
     return DI_ERR_LAUNCH;
   }
   const int sms = (g_pj_sm_limit > 0 && g_pj_sm_limit < ds.num_sms) ? g_pj_sm_limit : ds.num_sms;
-  int grid = (sms / 3) * 3;
-  if (grid > 3 * p.m_tiles) grid = 3 * p.m_tiles;
+  int grid = sms < 5 ? 5 : sms;
+  if (grid > 3 * p.m_tiles) grid = 3 * p.m_tiles < 5 ? 5 : 3 * p.m_tiles;
+  p.n_chain = (2 * grid) / 5;
+  if (p.n_chain < 1) p.n_chain = 1;
   lcab_proj_kernel<<<grid, PJ_THREADS, PJ_SMEM_BYTES, stream>>>(mx0, mx1, w1h, w1m, w2h, w2m, mq, mk, mv, p);
   DI_CHECK_LAUNCH("di_lcab_proj_f32");
   return DI_OK;

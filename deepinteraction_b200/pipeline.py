@@ -20,7 +20,10 @@ class FramePipeline:
         self.streams = [torch.cuda.Stream(device=device) for _ in range(depth)]
         self.count = 0
         if depth > 1 and tc_sms:
-            _lib.check(_lib.lib().di_tc_set_sm_limit(int(tc_sms)), 'di_tc_set_sm_limit')
+            L = _lib.lib()
+            _lib.check(L.di_tc_set_sm_limit(int(tc_sms)), 'di_tc_set_sm_limit')
+            _lib.check(L.di_lcab_window_tc_set_sm_limit(int(tc_sms)), 'di_lcab_window_tc_set_sm_limit')
+            _lib.check(L.di_lcab_proj_set_sm_limit(int(tc_sms)), 'di_lcab_proj_set_sm_limit')
 
     def submit(self, frame, wait_event=None, stream_index=None):
         """frame: dict(img_feats, pts_feats, img_metas, pts_metas) of device tensors.  Returns (out, done_event,
