@@ -486,6 +486,116 @@ rows_finish_c128_kernel(const float* __restrict__ x, int ldx, const float* __res
   *reinterpret_cast<float4*>(out + (size_t)m * ldo + lane * 4) = a;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Query-row MLP: the decoder runs dozens of dense layers on B*P = 200..600 query rows.  On the tcgen05 path each is a
+// 20 us launch dominated by start-up (TMEM allocation, tensor maps, barrier set-up); here one CTA takes 4 rows through
+// up to TWO chained dense layers, a residual, a LayerNorm and an activation without leaving shared memory:
+//     H = act1([X0 | X1] W1^T + b1)            Y = H W2^T + b2   (or Y = H)
+//     Y = act_out(LN(Y + res))                 rows with zero_if_neg[m] < 0 are written as 0
+// -> nn.Linear / Conv1d(k=1) chains of decoder_utils.py: pos-embed MLPs :16-32, attention in/out projections + norm
+// :73-113, FFNs :104-109,754-757, prediction heads :498-581.  fp32 FFMA, sequential accumulation over k.
+// Weights are passed TRANSPOSED ([K, N], so that lanes read consecutive output columns).
+// ------------------------------------------------------------------------------------------------
+constexpr int MLP_R = 4;   // rows per CTA: small, so that 200 query rows already spread over 50 SMs
+__global__ void __launch_bounds__(256)
+rows_mlp_kernel(const float* __restrict__ X0, int ld0, int K0, const float* __restrict__ X1, int ld1, int K1,
+                const float* __restrict__ W1t, const float* __restrict__ b1, int N1, int act1,
+                const float* __restrict__ W2t, const float* __restrict__ b2, int N2, const float* __restrict__ res, int ldres,
+                const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int act_out,
+                const int* __restrict__ zero_if_neg, float* __restrict__ Y, int ldy, int M) {
+  extern __shared__ float sm[];
+  const int K = K0 + K1;
+  float* xs = sm;                         // [R][K]
+  float* hs = xs + MLP_R * K;             // [R][N1]
+  float* ys = hs + MLP_R * N1;            // [R][N2] (only with a second layer)
+  const int m0 = blockIdx.x * MLP_R, tid = threadIdx.x;
+  for (int i = tid; i < MLP_R * K; i += 256) {
+    const int r = i / K, k = i - r * K, m = m0 + r;
+    float v = 0.f;
+    if (m < M) v = k < K0 ? X0[(size_t)m * ld0 + k] : X1[(size_t)m * ld1 + (k - K0)];
+    xs[i] = v;
+  }
+  __syncthreads();
+  for (int n = tid; n < N1; n += 256) {
+    float acc[MLP_R];
+    const float bb = b1 ? b1[n] : 0.f;
+#pragma unroll
+    for (int r = 0; r < MLP_R; ++r) acc[r] = bb;
+#pragma unroll 16
+    for (int k = 0; k < K; ++k) {                       // 16 independent weight loads in flight per thread (latency-bound otherwise)
+      const float w = __ldg(W1t + (size_t)k * N1 + n);
+#pragma unroll
+      for (int r = 0; r < MLP_R; ++r) acc[r] = fmaf(xs[r * K + k], w, acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < MLP_R; ++r) hs[r * N1 + n] = di_act(acc[r], act1);
+  }
+  __syncthreads();
+  const float* outs = hs;
+  int N = N1;
+  if (W2t) {
+    for (int n = tid; n < N2; n += 256) {
+      float acc[MLP_R];
+      const float bb = b2 ? b2[n] : 0.f;
+#pragma unroll
+      for (int r = 0; r < MLP_R; ++r) acc[r] = bb;
+#pragma unroll 16
+      for (int k = 0; k < N1; ++k) {
+        const float w = __ldg(W2t + (size_t)k * N2 + n);
+#pragma unroll
+        for (int r = 0; r < MLP_R; ++r) acc[r] = fmaf(hs[r * N1 + k], w, acc[r]);
+      }
+#pragma unroll
+      for (int r = 0; r < MLP_R; ++r) ys[r * N2 + n] = acc[r];
+    }
+    __syncthreads();
+    outs = ys;
+    N = N2;
+  }
+  // finish: warp r owns row r (N <= 512 -> up to 16 values per lane)
+  const int r = tid >> 5, lane = tid & 31, m = m0 + r;
+  if (r >= MLP_R || m >= M) return;
+  float x[16];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int c = i * 32 + lane;
+    float a = 0.f;
+    if (c < N) {
+      a = outs[r * N + c];
+      if (res) a += res[(size_t)m * ldres + c];
+      sum += a;
+    }
+    x[i] = a;
+  }
+  if (gamma) {
+    const float mean = warp_sum(sum) / (float)N;
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int c = i * 32 + lane;
+      if (c < N) {
+        const float d = x[i] - mean;
+        var += d * d;
+      }
+    }
+    var = warp_sum(var) / (float)N;
+    const float rstd = 1.f / sqrtf(var + eps);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int c = i * 32 + lane;
+      if (c < N) x[i] = (x[i] - mean) * rstd * gamma[c] + beta[c];
+    }
+  }
+  const bool zero = zero_if_neg && zero_if_neg[m] < 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int c = i * 32 + lane;
+    if (c < N) Y[(size_t)m * ldy + c] = zero ? 0.f : di_act(x[i], act_out);
+  }
+}
+
 // pred [M, NP]: center(0,1) height(2) dim(3..5) rot(6,7) vel(8,9) heatmap(10..).  center += query_pos;
 // rows whose query fell on no image (win < 0) take the first layer's prediction (decoder.py:290-295).
 __global__ void pred_finish_kernel(float* __restrict__ pred, float* __restrict__ qpos, const float* __restrict__ first,
@@ -1005,6 +1115,28 @@ int di_rows_finish_f32(const float* part, int nsplit, long long split_stride, in
     rows_finish_kernel<<<di_cdiv(M, 8), 256, 0, stream>>>(part, nsplit, (size_t)split_stride, ldp, bias, res, ldres, gamma,
                                                          beta, out, ldo, zero_if_neg, M, C, act, eps);
   DI_CHECK_LAUNCH("di_rows_finish_f32");
+  return DI_OK;
+}
+
+// Query-row MLP (see rows_mlp_kernel): Y[M, N] = act_out(LN(act1([X0|X1] W1t + b1) [W2t + b2] + res)).
+// W1t [K0+K1, N1] and W2t [N1, N2] are TRANSPOSED weights (row = input channel); W2t / b1 / b2 / res / gamma may be NULL.
+// K0 + K1 <= 1024, N1, N2 <= 512.
+int di_rows_mlp_f32(const float* X0, int ld0, int K0, const float* X1, int ld1, int K1, const float* W1t, const float* b1,
+                    int N1, int act1, const float* W2t, const float* b2, int N2, const float* res, int ldres,
+                    const float* gamma, const float* beta, float eps, int act_out, const int* zero_if_neg, float* Y, int ldy,
+                    int M, cudaStream_t stream) {
+  DI_CHECK_ARG(X0 && W1t && Y && M > 0 && K0 > 0 && K1 >= 0 && (K1 == 0 || X1) && N1 > 0, "di_rows_mlp_f32: bad argument");
+  DI_CHECK_ARG(K0 + K1 <= 1024 && N1 <= 512 && (!W2t || (N2 > 0 && N2 <= 512)), "di_rows_mlp_f32: K <= 1024, N <= 512");
+  DI_CHECK_ARG((gamma == nullptr) == (beta == nullptr), "di_rows_mlp_f32: gamma and beta go together");
+  const size_t smem = sizeof(float) * MLP_R * (size_t)(K0 + K1 + N1 + (W2t ? N2 : 0));
+  static bool once = false;
+  if (!once) {
+    cudaFuncSetAttribute(rows_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    once = true;
+  }
+  rows_mlp_kernel<<<di_cdiv(M, MLP_R), 256, smem, stream>>>(X0, ld0, K0, X1, ld1, K1, W1t, b1, N1, act1, W2t, b2, N2, res,
+                                                           ldres, gamma, beta, eps, act_out, zero_if_neg, Y, ldy, M);
+  DI_CHECK_LAUNCH("di_rows_mlp_f32");
   return DI_OK;
 }
 

@@ -125,3 +125,11 @@ class Weight:
         bh, bm = split_bf16(w)
         self.bh, self.bm = bh.to(device), bm.to(device)
         self.shape = self.w.shape
+        self._wt = None
+
+    @property
+    def wt(self):
+        """fp32 weight transposed to [K, N] (input channel major) for the query-row MLP kernel (di_rows_mlp_f32)."""
+        if self._wt is None:
+            self._wt = self.w.t().contiguous()
+        return self._wt

@@ -277,8 +277,8 @@ class DeepInteractionDecoder(nn.Module):
         def pe_pack(pe):
             seq = pe.position_embedding_head
             w1, b1 = fold.conv_bn(seq[0], seq[1])
-            return (d(w1.reshape(w1.shape[0], -1)), d(b1), fold.Weight(fold._d(seq[3].weight)[:, :, 0], device),
-                    d(fold._d(seq[3].bias)))
+            return (fold.Weight(w1.reshape(w1.shape[0], -1), device), d(b1),
+                    fold.Weight(fold._d(seq[3].weight)[:, :, 0], device), d(fold._d(seq[3].bias)))
         pk['self_pe'] = pe_pack(layer.self_posembed)
         W, b, wo, bo = self._pack_mha(layer.self_attn.in_proj_weight, layer.self_attn.in_proj_bias,
                                       layer.self_attn.out_proj, d)
@@ -320,7 +320,23 @@ class DeepInteractionDecoder(nn.Module):
     # -- forward -----------------------------------------------------------------------------------
     def _pred(self, pack, srcs):
         w1, b1, w2, b2 = pack
-        return ops.linear([ops.linear(srcs, w1, b1, ops.ACT_RELU)], w2, b2)
+        return self._mlp(srcs, w1, b1, ops.ACT_RELU, w2, b2)
+
+    @staticmethod
+    def _mlp(srcs, W1, b1, act1=ops.ACT_NONE, W2=None, b2=None, res=None, ln=None, act_out=ops.ACT_NONE, zero_if_neg=None):
+        """act_out(LN(act1(cat(srcs) W1^T + b1) [W2^T + b2] + res)): ONE launch of the query-row MLP kernel when the
+        shapes fit it (a few hundred query rows), otherwise the general dense-layer + rows_finish kernels."""
+        M, K = srcs[0].shape[0], sum(t.shape[1] for t in srcs)
+        if ops.can_rows_mlp(M, K, W1.shape[0], 0 if W2 is None else W2.shape[0]) and len(srcs) <= 2:
+            return ops.rows_mlp(srcs, W1, b1, act1, W2, b2, res, None if ln is None else ln[0], None if ln is None else ln[1],
+                                act_out, zero_if_neg)
+        y = ops.linear(srcs, W1, b1, act1)
+        if W2 is not None:
+            y = ops.linear([y], W2, b2)
+        if res is None and ln is None and act_out == ops.ACT_NONE and zero_if_neg is None:
+            return y
+        return ops.rows_finish(y, res=res, gamma=None if ln is None else ln[0], beta=None if ln is None else ln[1],
+                               act=act_out, zero_if_neg=zero_if_neg)
 
     def _roi_params(self, in_hw):
         bc, tc = self.bbox_coder, self.test_cfg
@@ -393,19 +409,18 @@ class DeepInteractionDecoder(nn.Module):
         ops._MODULE[0] = ('TransformerDecoderLayer (query x BEV cross-attn)', F_b + 4 * (2 * C * C + 2 * HW * C),
                           2 * B * HW * C * 2 * C + 4 * B * P * HW * C)
         pw1, pb1, pw2, pb2 = pk['self_pe']
-        qpe = ops.linear([ops.linear([qpos], pw1, pb1, ops.ACT_RELU)], pw2, pb2)
+        qpe = self._mlp([qpos], pw1, pb1, ops.ACT_RELU, pw2, pb2)
         w, b, wo, bo = pk['self_attn']
-        qkv = ops.linear([q, qpe], w, b)
+        qkv = self._mlp([q, qpe], w, b)
         a = ops.mha_small(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], B, P, H)
-        q = ops.rows_finish(ops.linear([a], wo, bo), res=q, gamma=pk['norm1'][0], beta=pk['norm1'][1])
-        qc = ops.linear([q, qpe], *pk['cross_q'])
+        q = self._mlp([a], wo, bo, res=q, ln=pk['norm1'])
+        qc = self._mlp([q, qpe], *pk['cross_q'])
         w_kv, b_kv, ckv = pk['cross_kv']
         kv = ops.linear([pts_conv.view(B * HW, C)], w_kv, b_kv, res=ckv, res_mod=HW)
         a = ops.cross_attn(qc, kv, B, P, HW, H)
-        q = ops.rows_finish(ops.linear([a], *pk['cross_out']), res=q, gamma=pk['norm2'][0], beta=pk['norm2'][1])
+        q = self._mlp([a], *pk['cross_out'], res=q, ln=pk['norm2'])
         f1w, f1b, f2w, f2b = pk['ffn']
-        f = ops.linear([ops.linear([q], f1w, f1b, ops.ACT_RELU)], f2w, f2b)
-        q = ops.rows_finish(f, res=q, gamma=pk['norm3'][0], beta=pk['norm3'][1])
+        q = self._mlp([q], f1w, f1b, ops.ACT_RELU, f2w, f2b, res=q, ln=pk['norm3'])
         ops._MODULE[0] = ('prediction_heads', 0, 0)
         pred = self._pred(pk['pred0'], [q])
         ops.pred_finish(pred, qpos)
@@ -427,9 +442,9 @@ class DeepInteractionDecoder(nn.Module):
                 rois, win, onbits = ops.rcnn_rois(pred, B, P, V, 1, prm)
                 roi = ops.roi_align(new_pts, rois, 1.0)
             w, b, wo, bo = bp['attn']
-            qkv = ops.linear([prev], w, b)
+            qkv = self._mlp([prev], w, b)
             a = ops.mha_small(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], B, P, H, onbits, win)
-            q1 = ops.rows_finish(ops.linear([a], wo, bo), res=prev, gamma=bp['norm1'][0], beta=bp['norm1'][1])
+            q1 = self._mlp([a], wo, bo, res=prev, ln=bp['norm1'])
             ops.TC_BF16[0] = _DYN_BF16                       # parameter generator (M=P, N=32768): see _DYN_BF16
             params = ops.linear([q1], *bp['dyn'])
             ops.TC_BF16[0] = False
@@ -438,9 +453,8 @@ class DeepInteractionDecoder(nn.Module):
             t = ops.rows_finish(part, bias=bp['dout'][1], gamma=bp['dn3'][0], beta=bp['dn3'][1], act=ops.ACT_RELU)
             q2 = ops.rows_finish(t, res=q1, gamma=bp['norm2'][0], beta=bp['norm2'][1])
             f1w, f1b, f2w, f2b = bp['ffn']
-            f = ops.linear([ops.linear([q2], f1w, f1b, ops.ACT_GELU)], f2w, f2b)
-            q = ops.rows_finish(f, res=q2, gamma=bp['norm3'][0], beta=bp['norm3'][1],
-                                zero_if_neg=win if bp['image'] else None)
+            q = self._mlp([q2], f1w, f1b, ops.ACT_GELU, f2w, f2b, res=q2, ln=bp['norm3'],
+                          zero_if_neg=win if bp['image'] else None)
             ops._MODULE[0] = ('prediction_heads', 0, 0)
             pred = self._pred(bp['pred'], [q, prev])
             ops.pred_finish(pred, qpos, first if bp['image'] else None, win if bp['image'] else None)

@@ -484,6 +484,32 @@ def rows_finish(x, bias=None, res=None, gamma=None, beta=None, act=ACT_NONE, zer
     return out
 
 
+ROWS_MLP = [os.environ.get('DI_B200_ROWS_MLP', '1') != '0']   # query-row dense layers on the fused FFMA kernel (M <= 2048)
+
+
+def can_rows_mlp(M, K, N1, N2=0):
+    return bool(ROWS_MLP[0] and M <= 2048 and K <= 1024 and N1 <= 512 and N2 <= 512)
+
+
+def rows_mlp(srcs, W1, b1=None, act1=ACT_NONE, W2=None, b2=None, res=None, gamma=None, beta=None, act_out=ACT_NONE,
+             zero_if_neg=None, eps=1e-5):
+    """act_out(LN(act1(cat(srcs) W1^T + b1) [W2^T + b2] + res)) on a few hundred rows in one launch (W*: fold.Weight)."""
+    srcs = list(srcs)
+    M = srcs[0].shape[0]
+    N1 = W1.shape[0]
+    N2 = W2.shape[0] if W2 is not None else 0
+    assert len(srcs) <= 2 and sum(s.shape[1] for s in srcs) == W1.shape[1]
+    (p0, l0) = _rows(srcs[0])
+    (p1, l1) = _rows(srcs[1]) if len(srcs) > 1 else (None, 0)
+    K1 = srcs[1].shape[1] if len(srcs) > 1 else 0
+    out = torch.empty(M, N2 or N1, device=srcs[0].device, dtype=torch.float32)
+    pr, ldr = (None, 0) if res is None else _rows(res)
+    _call('di_rows_mlp_f32', p0, l0, srcs[0].shape[1], p1, l1, K1, _ptr(W1.wt), _ptr(b1), N1, act1,
+          _ptr(W2.wt) if W2 is not None else None, _ptr(b2), N2, pr, ldr, _ptr(gamma), _ptr(beta), float(eps), act_out,
+          _ptr(zero_if_neg), _ptr(out), out.shape[1], M, _stream())
+    return out
+
+
 def pred_finish(pred, qpos, first=None, win=None):
     M, NP = pred.shape
     _call('di_pred_finish_f32', _ptr(pred), _ptr(qpos), _ptr(first), _ptr(win), M, NP, _stream())

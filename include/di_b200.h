@@ -268,6 +268,16 @@ int di_dynconv_f32(const float* roi, const float* params, const float* g1, const
 int di_nchw_to_nhwc_f32(const float* in, float* out, int N, int C, int HW, cudaStream_t stream);
 int di_nhwc_to_nchw_f32(const float* in, float* out, int N, int C, int HW, cudaStream_t stream);
 
+/* Query-row MLP: up to two chained dense layers, residual, LayerNorm and activation on M <= a few hundred rows in ONE
+ * launch (4 rows per CTA, fp32 FFMA): Y = act_out(LN(act1([X0|X1] W1t + b1) [W2t + b2] + res)); rows with
+ * zero_if_neg[m] < 0 are written as 0.  Replaces the nn.Linear / Conv1d(k=1) chains of models/utils/decoder_utils.py
+ * (pos-embed MLPs :16-32, attention projections + norms :73-113, FFNs :104-109,754-757, prediction heads :498-581).
+ * W1t [K0+K1, N1], W2t [N1, N2]: TRANSPOSED weights; W2t / b1 / b2 / res / gamma+beta / zero_if_neg may be NULL. */
+int di_rows_mlp_f32(const float* X0, int ld0, int K0, const float* X1, int ld1, int K1, const float* W1t, const float* b1,
+                    int N1, int act1, const float* W2t, const float* b2, int N2, const float* res, int ldres,
+                    const float* gamma, const float* beta, float eps, int act_out, const int* zero_if_neg, float* Y, int ldy,
+                    int M, cudaStream_t stream);
+
 /* ---- box coder and get_bboxes post-processing (decoder.cu) ------------------------------------- */
 
 /* TransFusionBBoxCoder.decode (core/bbox/coders/transfusion_bbox_coder.py:40-126): class = first arg-max of the

@@ -108,6 +108,34 @@ def test_cross_attention_matches_dense_softmax():
         assert rel_err(out[b * P:(b + 1) * P], ref) < TIGHT
 
 
+@pytest.mark.parametrize('M,Ks,N1,N2', [(200, (128,), 384, 0), (200, (128, 128), 384, 20), (37, (2,), 128, 128),
+                                        (600, (128,), 512, 128), (5, (256,), 64, 0)])
+def test_rows_mlp_matches_float64(M, Ks, N1, N2):
+    """Query-row MLP kernel: two chained dense layers + residual + LayerNorm + activation + row masking in one launch."""
+    from deepinteraction_b200 import ops, fold
+    g = torch.Generator().manual_seed(M + N1)
+    xs = [torch.randn(M, k, generator=g) for k in Ks]
+    K = sum(Ks)
+    W1, b1 = torch.randn(N1, K, generator=g) / K ** 0.5, torch.randn(N1, generator=g)
+    N = N2 or N1
+    res, gam, bet = torch.randn(M, N, generator=g), torch.rand(N, generator=g) + 0.5, torch.randn(N, generator=g)
+    zin = torch.where(torch.rand(M, generator=g) < 0.2, -1, 3).to(torch.int32)
+    x64 = torch.cat(xs, 1).double()
+    h = F.gelu(x64 @ W1.double().t() + b1.double())
+    if N2:
+        W2, b2 = torch.randn(N2, N1, generator=g) / N1 ** 0.5, torch.randn(N2, generator=g)
+        h = h @ W2.double().t() + b2.double()
+    want = F.relu(F.layer_norm(h + res.double(), (N,), gam.double(), bet.double()))
+    want[zin < 0] = 0
+    d = dev()
+    got = ops.rows_mlp([x.to(d) for x in xs], fold.Weight(W1, d), b1.to(d), ops.ACT_GELU,
+                       fold.Weight(W2, d) if N2 else None, b2.to(d) if N2 else None, res.to(d), gam.to(d), bet.to(d),
+                       ops.ACT_RELU, zin.to(d))
+    assert rel_err(got.cpu().double(), want) < 2e-6
+    plain = ops.rows_mlp([x.to(d) for x in xs], fold.Weight(W1, d), b1.to(d))          # single layer, nothing else
+    assert rel_err(plain.cpu().double(), x64 @ W1.double().t() + b1.double()) < 2e-6
+
+
 def test_rows_finish_layernorm():
     from deepinteraction_b200 import ops
     g = torch.Generator().manual_seed(4)
