@@ -292,14 +292,16 @@ def run_plusplus(args):
         dist.init_process_group('nccl', device_id=device)
     torch.set_grad_enabled(False)
     import projects.mmdet3d_plugin  # noqa: F401
-    from projects.mmdet3d_plugin.registry import load_config, build_neck
+    from projects.mmdet3d_plugin.registry import load_config, build_hot_path
     from deepinteraction_b200 import ops, synth, graph as di_graph
     cfg = load_config(os.path.join(ROOT, 'projects', 'configs', 'nuscenes', 'di_b200_plusplus_hotpath.py'))
     torch.manual_seed(SEED)
-    neck = build_neck(cfg)
+    neck, head = build_hot_path(cfg)
     synth.randomize_norm_stats(neck, SEED)
     randomize_deform(neck, SEED)
+    synth.randomize_norm_stats(head, SEED + 1)
     neck = neck.to(device).eval()
+    head = head.to(device).eval() if args.with_decoder else None      # --with-decoder: + DeepInteractionPlusPlusDecoder
     B = args.batch
     NF = 3
     hosts = [pp_host_frame(B, SEED + 1000 * rank + i, n_points=int(250000 * (0.9 + 0.05 * i))) for i in range(NF)]
@@ -311,7 +313,12 @@ def run_plusplus(args):
                     pts_metas=dict(pillars=nb(pm['pillars']), pillar_coors=nb(pm['pillar_coors']),
                                    pillars_num_points=nb(pm['pillars_num_points']), pts=[nb(p) for p in pm['pts']]))
     devs = [to_dev(f) for f in hosts]
-    fwd = lambda d: neck(d['img'], d['pts'], d['img_metas'], d['pts_metas'])
+    enc = lambda d: neck(d['img'], d['pts'], d['img_metas'], d['pts_metas'])
+
+    def fwd(d):
+        o = enc(d)
+        return o if head is None else head(o[1], o[0], d['img_metas'])
+    results = lambda o: (o[0], o[1][0], o[1][1]) if head is None else tuple(o[0][0].values())
     W, K = max(args.warmup, 3), args.steps
     for _ in range(3):
         for d in devs:
@@ -345,7 +352,7 @@ def run_plusplus(args):
         # end to end: host -> device copies of every input of the step, forward, device -> host of the three outputs
         flat = lambda fr: list(fr['img_levels']) + list(fr['pts_levels'])
         dset = dict(img=[torch.empty_like(t) for t in devs[0]['img']], pts=[torch.empty_like(t) for t in devs[0]['pts']])
-        outs_host = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in (out[0], out[1][0], out[1][1])]
+        outs_host = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in results(out)]
         h2d_b = int(np.mean([sum(t.numel() * 4 for t in flat(f)) + sum(v.numel() * v.element_size() for k_, v in
                              f['pts_metas'].items() if k_ != 'pts') + sum(p.numel() * 4 for p in f['pts_metas']['pts'])
                              for f in hosts]))
@@ -355,10 +362,10 @@ def run_plusplus(args):
             for dst, src in zip(dset['img'] + dset['pts'], flat(fh)):
                 dst.copy_(src, non_blocking=True)
             pm = fh['pts_metas']
-            o = neck(dset['img'], dset['pts'], fh['img_metas'],
-                     dict(pillars=nb(pm['pillars']), pillar_coors=nb(pm['pillar_coors']),
-                          pillars_num_points=nb(pm['pillars_num_points']), pts=[nb(p) for p in pm['pts']]))
-            for dst, src in zip(outs_host, (o[0], o[1][0], o[1][1])):
+            o = fwd(dict(img=dset['img'], pts=dset['pts'], img_metas=fh['img_metas'],
+                         pts_metas=dict(pillars=nb(pm['pillars']), pillar_coors=nb(pm['pillar_coors']),
+                                        pillars_num_points=nb(pm['pillars_num_points']), pts=[nb(p) for p in pm['pts']])))
+            for dst, src in zip(outs_host, results(o)):
                 dst.copy_(src, non_blocking=True)
         for i in range(3):
             e2e_step(i)
@@ -379,6 +386,8 @@ def run_plusplus(args):
     pk = peaks()
     di_graph.ENABLED[0] = False
     neck._graphs.clear()
+    if head is not None:
+        head._graphs.clear()
     ops.PROFILE[0] = []
     for _ in range(2):
         fwd(devs[0])
@@ -413,17 +422,19 @@ def run_plusplus(args):
                 r_img, r_pts = o(list(f1['img_levels']), list(f1['pts_levels']), f1['img_metas'], f1['pts_metas'])
                 dt = time.perf_counter() - t0
             d1 = to_dev(f1)
-            g_img, g_pts = fwd(d1)
+            g_img, g_pts = enc(d1)
             rel = lambda a, b: float((a.cpu() - b).abs().max() / b.abs().max().clamp_min(1e-12))
             cpu = dict(value=1.0 / dt, unit='frames/s', cores=cores, kind='port',
                        sample='1 sample (6 cameras) of the same workload through oracle/mmri_pp.py (reference math, fp32)',
                        max_rel_err_vs_gpu=max(rel(g_img, r_img), rel(g_pts[1], r_pts[1])))
         except TimeoutError:
             cpu = dict(value=None, unit='frames/s', cores=cores, kind='port', sample='1 sample did not finish within 170 s')
-    line = dict(metric='frames/sec ++ MMRI encoder (FusionTransformerv4), 180x180 BEV / 6 cams x 2 levels', value=frames / (ms * 1e-3),
+    what = '++ MMRI encoder (FusionTransformerv4)' + (' + ++ MMPI decoder' if head is not None else '')
+    line = dict(metric='frames/sec %s, 180x180 BEV / 6 cams x 2 levels' % what, value=frames / (ms * 1e-3),
                 unit='frames/s', n_gpus=world, steps=K, warmup=W, ms_per_step=ms / K, higher_is_better=True, scaling='weak',
                 vs_baseline=None, dtype='fp32', data='synthetic',
-                config=dict(workload='DeepInteraction++ Fusion_0075_plusplus imgpts_neck (deformable variant), bs=%d/GPU' % B,
+                config=dict(workload='DeepInteraction++ Fusion_0075_plusplus imgpts_neck%s (deformable variant), bs=%d/GPU'
+                            % (' + pts_bbox_head' if head is not None else '', B),
                             global_batch=B * world, parallelism=f'dp{world} (independent frames, no data-path collective)',
                             l2='inputs (%.0f MB/step) larger than L2; %d distinct frames cycled' % (h2d_b / 1e6, NF)),
                 clocks=clocks, e2e=dict(value=frames / (ms_e2e * 1e-3), unit='frames/s', h2d_bytes_per_step=h2d_b,
@@ -445,6 +456,9 @@ def main():
     ap.add_argument('--batch', type=int, default=1, help='frames per GPU per step')
     ap.add_argument('--cloud', default='lidar', choices=['lidar', 'dense'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--with-decoder', action='store_true',
+                    help='plusplus workload: run DeepInteractionPlusPlusDecoder after the ++ encoder (default: encoder only, '
+                         'as BASELINE.json config 4 is quoted)')
     ap.add_argument('--profile-steps', type=int, default=3)
     ap.add_argument('--inflight', type=int, default=3, help='independent frames in flight per GPU (CUDA streams)')
     ap.add_argument('--frames', type=int, default=9, help='distinct synthetic frames (different point / pillar counts) cycled '

@@ -72,6 +72,11 @@ SIGNATURES = {
     'di_rows_finish_f32': [_p, _i, _ll, _i, _p, _p, _i, _p, _p, _p, _i, _p, _i, _i, _i, _f, _p],
     'di_rows_mlp_f32': [_p, _i, _i, _p, _i, _i, _p, _p, _i, _i, _p, _p, _i, _p, _i, _p, _p, _f, _i, _p, _p, _i, _i, _p],
     'di_pred_finish_f32': [_p, _p, _p, _p, _i, _i, _p],
+    'di_pred_finish_pp_f32': [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
+    'di_rcnn_leaders': [_p, _p, _p, _i, _i, _i, _p],
+    'di_mha_small_rows_f32': [_p, _i, _p, _i, _p, _i, _p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
+    'di_take_rows_f32': [_p, _i, _p, _p, _i, _i, _p],
+    'di_branch_mix_f32': [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     'di_rcnn_rois_f32': [_p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _fp, _p],
     'di_roi_align_f32': [_p, _p, _p, _i, _i, _i, _i, _f, _p],
     'di_dynconv_f32': [_p, _p, _p, _p, _p, _p, _p, _i, _f, _p],

@@ -216,14 +216,21 @@ template <int D>
 __global__ void __launch_bounds__(256)
 mha_small_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk, const float* __restrict__ v,
                  int ldv, float* __restrict__ out, int ldo, const int* __restrict__ onbits, const int* __restrict__ win,
-                 int B, int P, int Hh) {
+                 int B, int P, int Hh, const int* __restrict__ rows, int R, int rows_per_b) {
   int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
-  if (wid >= B * P * Hh) return;
+  if (wid >= (rows ? R : B * P) * Hh) return;
   int head = wid % Hh, bq = wid / Hh;
   int b = bq / P;
   int wq = win ? win[bq] : 0;
   float* o = out + (size_t)bq * ldo + head * D;
+  if (rows) {
+    // row-map form (V2 blocks): output row r = query rows[r] seen from group win[r] (= the r-th (sample, view) pair)
+    b = bq / rows_per_b;
+    const int r = bq;
+    bq = rows[r];
+    if (bq < 0) wq = -1;
+  }
   if (wq < 0) {
     if (lane < D) o[lane] = 0.f;
     return;
@@ -609,6 +616,57 @@ __global__ void pred_finish_kernel(float* __restrict__ pred, float* __restrict__
     for (int c = 0; c < NP; ++c) p[c] = first[(size_t)m * NP + c];
   qpos[m * 2] = p[0];
   qpos[m * 2 + 1] = p[1];
+}
+
+__global__ void pred_finish_pp_kernel(float* __restrict__ pred, float* __restrict__ qpos, float* __restrict__ look,
+                                      const float* __restrict__ first, const int* __restrict__ win,
+                                      int* __restrict__ keep, int first_layer, int M, int NP) {
+  int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  float* p = pred + (size_t)m * NP;
+  const float d0 = p[0], d1 = p[1];
+  p[0] = d0 + look[m * 2];
+  p[1] = d1 + look[m * 2 + 1];
+  look[m * 2] = d0 + qpos[m * 2];
+  look[m * 2 + 1] = d1 + qpos[m * 2 + 1];
+  int k = first_layer ? 1 : keep[m];
+  if (win) k = k && (win[m] >= 0);
+  keep[m] = k;
+  if (!k)
+    for (int c = 0; c < NP; ++c) p[c] = first[(size_t)m * NP + c];
+  qpos[m * 2] = p[0];
+  qpos[m * 2 + 1] = p[1];
+}
+
+__global__ void rcnn_leaders_kernel(const int* __restrict__ onbits, int* __restrict__ lead_row, int* __restrict__ lead_win,
+                                    int P, int V) {
+  const int b = blockIdx.x / V, v = blockIdx.x % V, lane = threadIdx.x;
+  int best = 0x7fffffff;
+  for (int i = lane; i < P; i += 32)
+    if ((onbits[b * P + i] >> v) & 1) best = min(best, i);
+  for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+  if (lane == 0) {
+    lead_row[blockIdx.x] = best < P ? b * P + best : -1;
+    lead_win[blockIdx.x] = best < P ? v : -1;
+  }
+}
+
+__global__ void take_rows_kernel(const float* __restrict__ src, int ld, const int* __restrict__ idx, float* __restrict__ out,
+                                 int C) {
+  const int r = blockIdx.x, i = idx[r];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) out[(size_t)r * C + c] = i >= 0 ? src[(size_t)i * ld + c] : 0.f;
+}
+
+__global__ void branch_mix_kernel(const float* __restrict__ a, const float* __restrict__ lead, const int* __restrict__ win,
+                                  const float* __restrict__ scale, const float* __restrict__ self_scale,
+                                  float* __restrict__ out, int C, int P, int V, int zero_off) {
+  const int m = blockIdx.x, w = win[m];
+  const float s = scale[0], t = self_scale[0];
+  const float* l = lead + (size_t)((m / P) * V + (w < 0 ? 0 : w)) * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float y = __fadd_rn(__fmul_rn(a[(size_t)m * C + c], s), __fmul_rn(l[c], t));
+    out[(size_t)m * C + c] = (w < 0 && zero_off) ? 0.f : y;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1082,8 +1140,63 @@ int di_mha_small_f32(const float* q, int ldq, const float* k, int ldk, const flo
   DI_CHECK_ARG(ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0, "di_mha_small_f32: strides must be multiples of 4");
   DI_CHECK_ARG((onbits == nullptr) == (win == nullptr), "di_mha_small_f32: onbits and win go together");
   int warps = B * P * heads;
-  mha_small_kernel<16><<<di_cdiv(warps, 8), 256, 0, stream>>>(q, ldq, k, ldk, v, ldv, out, ldo, onbits, win, B, P, heads);
+  mha_small_kernel<16><<<di_cdiv(warps, 8), 256, 0, stream>>>(q, ldq, k, ldk, v, ldv, out, ldo, onbits, win, B, P, heads,
+                                                              nullptr, 0, 1);
   DI_CHECK_LAUNCH("di_mha_small_f32");
+  return DI_OK;
+}
+
+// Row-map form: out row r (of R = B * rows_per_b) = attention of query rows[r] (a global row b*P+i, or -1 -> zero row)
+// over the keys of its sample whose onbits have bit rwin[r].  Used for the "view leader" rows of the V2 RCNN blocks.
+int di_mha_small_rows_f32(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* out, int ldo,
+                          const int* onbits, const int* rows, const int* rwin, int R, int rows_per_b, int B, int P,
+                          int heads, int head_dim, cudaStream_t stream) {
+  DI_CHECK_ARG(q && k && v && out && onbits && rows && rwin && head_dim == 16 && P <= 512 && R == B * rows_per_b,
+               "di_mha_small_rows_f32: unsupported shape (head_dim=%d P=%d R=%d)", head_dim, P, R);
+  DI_CHECK_ARG(ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0, "di_mha_small_rows_f32: strides must be multiples of 4");
+  mha_small_kernel<16><<<di_cdiv(R * heads, 8), 256, 0, stream>>>(q, ldq, k, ldk, v, ldv, out, ldo, onbits, rwin, B, P, heads,
+                                                                  rows, R, rows_per_b);
+  DI_CHECK_LAUNCH("di_mha_small_rows_f32");
+  return DI_OK;
+}
+
+// lead_row [B*V]: global row (b*P + i) of the FIRST query of sample b whose onbits have bit v, or -1; lead_win [B*V] = v
+// or -1.  (decoder_utils.py:987 / :1085: the self-branch feature every query of a view receives is the one of the
+// view's first query -- see oracle/mmpi_pp.py.)
+int di_rcnn_leaders(const int* onbits, int* lead_row, int* lead_win, int B, int P, int V, cudaStream_t stream) {
+  DI_CHECK_ARG(onbits && lead_row && lead_win && B > 0 && P > 0 && V > 0 && V <= MAXV, "di_rcnn_leaders: bad argument");
+  rcnn_leaders_kernel<<<B * V, 32, 0, stream>>>(onbits, lead_row, lead_win, P, V);
+  DI_CHECK_LAUNCH("di_rcnn_leaders");
+  return DI_OK;
+}
+
+// out[r, :C] = idx[r] >= 0 ? src[idx[r], :C] : 0
+int di_take_rows_f32(const float* src, int ld, const int* idx, float* out, int R, int C, cudaStream_t stream) {
+  DI_CHECK_ARG(src && idx && out && R > 0 && C > 0, "di_take_rows_f32: bad argument");
+  take_rows_kernel<<<R, 128, 0, stream>>>(src, ld, idx, out, C);
+  DI_CHECK_LAUNCH("di_take_rows_f32");
+  return DI_OK;
+}
+
+// out[m] = a[m] * scale[0] + lead[(m / P) * V + win[m]] * self_scale[0]  (two rounded products, one rounded sum, as
+// torch evaluates decoder_utils.py:987); rows with win[m] < 0 are zero when zero_off != 0 (queries on no image).
+int di_branch_mix_f32(const float* a, const float* lead, const int* win, const float* scale, const float* self_scale,
+                      float* out, int M, int C, int P, int V, int zero_off, cudaStream_t stream) {
+  DI_CHECK_ARG(a && lead && win && scale && self_scale && out && M > 0 && C > 0 && P > 0 && V > 0, "di_branch_mix_f32: bad argument");
+  branch_mix_kernel<<<M, 128, 0, stream>>>(a, lead, win, scale, self_scale, out, C, P, V, zero_off);
+  DI_CHECK_LAUNCH("di_branch_mix_f32");
+  return DI_OK;
+}
+
+// ++ decoder, deepinteractionplusplus_decoder.py:285-302: pred[:, 0:2] = delta + look; look' = delta + qpos;
+// keep' = image layer ? (win >= 0 [&& keep]) : keep;  rows with !keep' take `first`;  qpos' = pred[:, 0:2].
+// keep: int32 [M] cumulative mask (read unless first_layer, always written); win: this layer's winning view or NULL.
+int di_pred_finish_pp_f32(float* pred, float* qpos, float* look, const float* first, const int* win, int* keep,
+                          int first_layer, int M, int NP, cudaStream_t stream) {
+  DI_CHECK_ARG(pred && qpos && look && first && keep && M > 0 && NP >= 2 && (win || !first_layer),
+               "di_pred_finish_pp_f32: bad argument");
+  pred_finish_pp_kernel<<<di_cdiv(M, 128), 128, 0, stream>>>(pred, qpos, look, first, win, keep, first_layer, M, NP);
+  DI_CHECK_LAUNCH("di_pred_finish_pp_f32");
   return DI_OK;
 }
 

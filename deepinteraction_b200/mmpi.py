@@ -111,6 +111,44 @@ class PointRCNNBlock(nn.Module):
         _rcnn_holder(self, '_pts', c, heads, dropout)
 
 
+class TransFFN(nn.Module):
+    """Holder with mmcv 1.3.18 FFN's parameter names (`layers.0.0`, `layers.1`): Linear-ReLU-Linear + identity."""
+
+    def __init__(self, c, hidden, drop=0.):
+        super().__init__()
+        self.layers = nn.Sequential(nn.Sequential(nn.Linear(c, hidden), nn.ReLU(inplace=True), nn.Dropout(drop)),
+                                    nn.Linear(hidden, c), nn.Dropout(drop))
+
+
+def _rcnn_holder_v2(blk, sfx, c, heads, dropout):
+    """decoder_utils.py:859-882 / :1004-1026 (`ffn`, `self_ffn`, `scale`, `self_scale` carry no `_pts` suffix)."""
+    setattr(blk, 'dyconv' + sfx, DynamicConv())
+    setattr(blk, 'dyconv_pre_self_attn' + sfx, nn.MultiheadAttention(c, heads, dropout=dropout))
+    for i in (1, 2, 3):
+        setattr(blk, f'norm{i}' + sfx, nn.LayerNorm(c))
+    setattr(blk, 'self_norm' + sfx, nn.LayerNorm(c))
+    blk.ffn = TransFFN(c, 4 * c, dropout)
+    blk.self_ffn = TransFFN(c, 4 * c, dropout)
+    blk.scale = nn.Parameter(torch.ones(1) * 0.5)
+    blk.self_scale = nn.Parameter(torch.ones(1) * 0.5)
+
+
+class ImageRCNNBlockV2(nn.Module):
+    sfx, v2 = '', True
+
+    def __init__(self, c, heads, dropout):
+        super().__init__()
+        _rcnn_holder_v2(self, '', c, heads, dropout)
+
+
+class PointRCNNBlockV2(nn.Module):
+    sfx, v2 = '_pts', True
+
+    def __init__(self, c, heads, dropout):
+        super().__init__()
+        _rcnn_holder_v2(self, '_pts', c, heads, dropout)
+
+
 class TransFusionBBoxCoder:
     """Drop-in for core/bbox/coders/transfusion_bbox_coder.py:8-126: same constructor, ``decode`` and ``encode``
     (CUDA tensors; kernels di_bbox_decode_f32 / di_bbox_encode_f32).  Unlike the reference, ``decode`` does not
@@ -163,6 +201,8 @@ class DeepInteractionDecoder(nn.Module):
     """Drop-in for the reference ``DeepInteractionDecoder`` (HEADS): same constructor kwargs, state_dict
     and forward contract (``forward(pts_inputs, img_inputs, img_metas) -> [[dict]]``; side attributes
     ``query_labels`` and ``on_the_image_mask``).  Inference (eval) only."""
+    _BLOCKS = (ImageRCNNBlock, PointRCNNBlock)
+    _PRED_SRCS = 2          # prediction heads of the MMPI layers read cat([query, previous query]) (:289)
 
     def __init__(self, num_views=0, out_size_factor_img=4, num_proposals=128, auxiliary=True, hidden_channel=128,
                  num_classes=4, num_mmpi=4, num_decoder_layers=1, num_heads=8, learnable_query_pos=False,
@@ -200,10 +240,10 @@ class DeepInteractionDecoder(nn.Module):
         self.prediction_heads = nn.ModuleList(FFN(c, heads) for _ in range(num_decoder_layers))
         self.decode_head, self.pred_head = nn.ModuleList(), nn.ModuleList()
         for _ in range(num_mmpi // 2):
-            self.decode_head.append(ImageRCNNBlock(c, num_heads, dropout))
-            self.pred_head.append(FFN(2 * c, heads))
-            self.decode_head.append(PointRCNNBlock(c, num_heads, dropout))
-            self.pred_head.append(FFN(2 * c, heads))
+            self.decode_head.append(self._BLOCKS[0](c, num_heads, dropout))
+            self.pred_head.append(FFN(self._PRED_SRCS * c, heads))
+            self.decode_head.append(self._BLOCKS[1](c, num_heads, dropout))
+            self.pred_head.append(FFN(self._PRED_SRCS * c, heads))
         self.x_size = test_cfg['grid_size'][0] // test_cfg['out_size_factor']
         self.y_size = test_cfg['grid_size'][1] // test_cfg['out_size_factor']
         for p in self.decoder.parameters():          # reference :171-175
@@ -308,10 +348,17 @@ class DeepInteractionDecoder(nn.Module):
             mha = g('dyconv_pre_self_attn')
             W, b, wo, bo = self._pack_mha(mha.in_proj_weight, mha.in_proj_bias, mha.out_proj, d)
             dy = g('dyconv')
-            blocks.append(dict(image=blk.sfx == '', attn=(fold.Weight(W, device), d(b), wo, bo), norm1=lin(g('norm1')),
-                               norm2=lin(g('norm2')), norm3=lin(g('norm3')), dyn=linw(dy.dynamic_layer),
-                               dn1=lin(dy.norm1), dn2=lin(dy.norm2), dout=lin(dy.out_layer), dn3=lin(dy.norm3),
-                               ffn=linw(g('linear1')) + linw(g('linear2')), pred=self._pack_pred(ph, d)))
+            bp = dict(image=blk.sfx == '', attn=(fold.Weight(W, device), d(b), wo, bo), norm1=lin(g('norm1')),
+                      norm2=lin(g('norm2')), norm3=lin(g('norm3')), dyn=linw(dy.dynamic_layer),
+                      dn1=lin(dy.norm1), dn2=lin(dy.norm2), dout=lin(dy.out_layer), dn3=lin(dy.norm3),
+                      pred=self._pack_pred(ph, d), v2=getattr(blk, 'v2', False))
+            if bp['v2']:
+                bp.update(ffn=linw(blk.ffn.layers[0][0]) + linw(blk.ffn.layers[1]),
+                          self_ffn=linw(blk.self_ffn.layers[0][0]) + linw(blk.self_ffn.layers[1]),
+                          self_norm=lin(g('self_norm')), scale=d(fold._d(blk.scale)), self_scale=d(fold._d(blk.self_scale)))
+            else:
+                bp.update(ffn=linw(g('linear1')) + linw(g('linear2')))
+            blocks.append(bp)
         pk['blocks'] = blocks
         self._pack, self._pack_key = pk, key
         self._graphs.clear()                 # captured graphs hold pointers into the previous pack
@@ -429,7 +476,10 @@ class DeepInteractionDecoder(nn.Module):
             debug.update(query_feat1=q.clone(), first_res=first.clone())
         # MMPI layers
         prm = self._roi_params(in_hw)
-        preds, wins = [], []
+        preds, wins, keeps = [], [], []
+        if pk['blocks'] and pk['blocks'][0]['v2']:
+            look = qpos.clone()                                   # deepinteractionplusplus_decoder.py:281
+            keep = torch.empty(B * P, device=dev_, dtype=torch.int32)
         for li, bp in enumerate(pk['blocks']):
             prev = q
             # RoI reads <= one map; DynamicConv parameter generator weights 128 x 32768 (+ out_layer 6272 x 128) read once
@@ -453,11 +503,28 @@ class DeepInteractionDecoder(nn.Module):
             t = ops.rows_finish(part, bias=bp['dout'][1], gamma=bp['dn3'][0], beta=bp['dn3'][1], act=ops.ACT_RELU)
             q2 = ops.rows_finish(t, res=q1, gamma=bp['norm2'][0], beta=bp['norm2'][1])
             f1w, f1b, f2w, f2b = bp['ffn']
-            q = self._mlp([q2], f1w, f1b, ops.ACT_GELU, f2w, f2b, res=q2, ln=bp['norm3'],
-                          zero_if_neg=win if bp['image'] else None)
-            ops._MODULE[0] = ('prediction_heads', 0, 0)
-            pred = self._pred(bp['pred'], [q, prev])
-            ops.pred_finish(pred, qpos, first if bp['image'] else None, win if bp['image'] else None)
+            if bp['v2']:
+                # decoder_utils.py:971-988 / :1071-1085.  The self branch every query of a (sample, view) group receives
+                # is the one of the group's FIRST query (the reference's (1,n,C) + (n,1,C) broadcast followed by [0];
+                # oracle/mmpi_pp.py), so it is evaluated on the B*V "leader" rows only.
+                q3 = self._mlp([q2], f1w, f1b, ops.ACT_RELU, f2w, f2b, res=q2, ln=bp['norm3'])
+                Vg = V if bp['image'] else 1
+                lrow, lwin = ops.rcnn_leaders(onbits, B, P, Vg)
+                a_l = ops.mha_small_rows(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], B, P, H, onbits, lrow, lwin)
+                q1_l = self._mlp([a_l], wo, bo, res=ops.take_rows(prev, lrow), ln=bp['norm1'])
+                s1w, s1b, s2w, s2b = bp['self_ffn']
+                s_l = self._mlp([q1_l], s1w, s1b, ops.ACT_RELU, s2w, s2b, res=q1_l, ln=bp['self_norm'])
+                q = ops.branch_mix(q3, s_l, win, bp['scale'], bp['self_scale'], P, Vg, bp['image'])
+                ops._MODULE[0] = ('prediction_heads', 0, 0)
+                pred = self._pred(bp['pred'], [q])
+                ops.pred_finish_pp(pred, qpos, look, first, win if bp['image'] else None, keep, li == 0)
+                keeps.append(keep.clone())
+            else:
+                q = self._mlp([q2], f1w, f1b, ops.ACT_GELU, f2w, f2b, res=q2, ln=bp['norm3'],
+                              zero_if_neg=win if bp['image'] else None)
+                ops._MODULE[0] = ('prediction_heads', 0, 0)
+                pred = self._pred(bp['pred'], [q, prev])
+                ops.pred_finish(pred, qpos, first if bp['image'] else None, win if bp['image'] else None)
             preds.append(pred)
             if bp['image']:
                 wins.append(win)
@@ -465,7 +532,7 @@ class DeepInteractionDecoder(nn.Module):
                 debug.setdefault('layer_query', []).append(q.clone())
                 debug.setdefault('rois', []).append(rois)
         ops._MODULE[0] = None
-        return dict(preds=preds, wins=wins, qscore=qscore, dense_heatmap=dense_b, labels=labels)
+        return dict(preds=preds, wins=wins, keeps=keeps, qscore=qscore, dense_heatmap=dense_b, labels=labels)
 
     def _to_dict(self, pred, B, P):
         t = pred.view(B, P, self.NP).permute(0, 2, 1)
@@ -479,7 +546,10 @@ class DeepInteractionDecoder(nn.Module):
         r = self.forward_rows(pts_conv, new_pts, img, img_metas, debug)
         B, P = pts_conv.shape[0], self.num_proposals
         self.query_labels = r['labels'].long()
-        self.on_the_image_mask = [(w.view(B, P) != -1) for w in r['wins']]
+        if r['keeps']:                                            # ++: one cumulative mask per layer (:295-299)
+            self.on_the_image_mask = [(k.view(B, P) != 0) for k in r['keeps']]
+        else:
+            self.on_the_image_mask = [(w.view(B, P) != -1) for w in r['wins']]
         rets = [self._to_dict(p, B, P) for p in r['preds']]
         rets[0]['query_heatmap_score'] = r['qscore']
         rets[0]['dense_heatmap'] = r['dense_heatmap']
@@ -527,3 +597,12 @@ class DeepInteractionDecoder(nn.Module):
             p = t.permute(0, 2, 3, 1)
             return p if p.is_contiguous() else ops.nchw_to_nhwc(t.contiguous())
         return self.forward_nhwc(nhwc(pts_inputs[0]), nhwc(pts_inputs[1]), nhwc(img_inputs), img_metas)
+
+
+class DeepInteractionPlusPlusDecoder(DeepInteractionDecoder):
+    """Drop-in for the reference ``DeepInteractionPlusPlusDecoder`` (HEADS; models/dense_heads/
+    deepinteractionplusplus_decoder.py:19-319): V2 RCNN blocks (decoder_utils.py:844-1089), prediction heads on C
+    channels (:140, :147), look-forward centre update (:281-294), cumulative on-image mask and first-layer fallback at
+    every layer (:295-302; ``on_the_image_mask`` holds num_mmpi masks).  Same constructor kwargs and state_dict."""
+    _BLOCKS = (ImageRCNNBlockV2, PointRCNNBlockV2)
+    _PRED_SRCS = 1

@@ -515,6 +515,45 @@ def pred_finish(pred, qpos, first=None, win=None):
     _call('di_pred_finish_f32', _ptr(pred), _ptr(qpos), _ptr(first), _ptr(win), M, NP, _stream())
 
 
+def pred_finish_pp(pred, qpos, look, first, win, keep, first_layer):
+    M, NP = pred.shape
+    _call('di_pred_finish_pp_f32', _ptr(pred), _ptr(qpos), _ptr(look), _ptr(first), _ptr(win), _ptr(keep),
+          1 if first_layer else 0, M, NP, _stream())
+
+
+def rcnn_leaders(onbits, B, P, V):
+    lead_row = torch.empty(B * V, device=onbits.device, dtype=torch.int32)
+    lead_win = torch.empty(B * V, device=onbits.device, dtype=torch.int32)
+    _call('di_rcnn_leaders', _ptr(onbits), _ptr(lead_row), _ptr(lead_win), B, P, V, _stream())
+    return lead_row, lead_win
+
+
+def mha_small_rows(q, k, v, B, P, heads, onbits, rows, rwin):
+    C, R = q.shape[1], rows.shape[0]
+    out = torch.empty(R, C, device=q.device, dtype=torch.float32)
+    (pq, lq), (pk, lk), (pv, lv) = _rows(q), _rows(k), _rows(v)
+    _call('di_mha_small_rows_f32', pq, lq, pk, lk, pv, lv, _ptr(out), C, _ptr(onbits), _ptr(rows), _ptr(rwin), R, R // B, B,
+          P, heads, C // heads, _stream())
+    return out
+
+
+def take_rows(src, idx):
+    R, C = idx.shape[0], src.shape[1]
+    out = torch.empty(R, C, device=src.device, dtype=torch.float32)
+    p, ld = _rows(src)
+    _call('di_take_rows_f32', p, ld, _ptr(idx), _ptr(out), R, C, _stream())
+    return out
+
+
+def branch_mix(a, lead, win, scale, self_scale, P, V, zero_off):
+    M, C = a.shape
+    assert a.is_contiguous() and lead.is_contiguous() and lead.shape == (M // P * V, C)
+    out = torch.empty(M, C, device=a.device, dtype=torch.float32)
+    _call('di_branch_mix_f32', _ptr(a), _ptr(lead), _ptr(win), _ptr(scale), _ptr(self_scale), _ptr(out), M, C, P, V,
+          1 if zero_off else 0, _stream())
+    return out
+
+
 def rcnn_rois(pred, B, P, V, mode, params10, proj=None, aux=None):
     dev = pred.device
     rois = torch.empty(B * P, 5, device=dev, dtype=torch.float32)

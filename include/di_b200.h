@@ -254,6 +254,20 @@ int di_rows_finish_f32(const float* part, int nsplit, long long split_stride, in
 /* models/dense_heads/deepinteraction_decoder.py:265, :290-295 */
 int di_pred_finish_f32(float* pred, float* qpos, const float* first, const int* win, int M, int NP,
                        cudaStream_t stream);
+/* ++ decoder (models/dense_heads/deepinteractionplusplus_decoder.py:285-302): look-forward centre update, cumulative
+ * on-image mask `keep` (int32 [M]), first-layer fallback at every layer */
+int di_pred_finish_pp_f32(float* pred, float* qpos, float* look, const float* first, const int* win, int* keep,
+                          int first_layer, int M, int NP, cudaStream_t stream);
+/* V2 RCNN blocks (models/utils/decoder_utils.py:844-1089).  di_rcnn_leaders: first query of every (sample, view) group;
+ * di_mha_small_rows_f32: the group self-attention for a list of (query row, group) pairs; di_take_rows_f32: row
+ * gather; di_branch_mix_f32: out = main * scale + leader_self * self_scale (:987, :1085) */
+int di_rcnn_leaders(const int* onbits, int* lead_row, int* lead_win, int B, int P, int V, cudaStream_t stream);
+int di_mha_small_rows_f32(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* out, int ldo,
+                          const int* onbits, const int* rows, const int* rwin, int R, int rows_per_b, int B, int P,
+                          int heads, int head_dim, cudaStream_t stream);
+int di_take_rows_f32(const float* src, int ld, const int* idx, float* out, int R, int C, cudaStream_t stream);
+int di_branch_mix_f32(const float* a, const float* lead, const int* win, const float* scale, const float* self_scale,
+                      float* out, int M, int C, int P, int V, int zero_off, cudaStream_t stream);
 /* box decode + RoI rectangles: image mode 0 (models/utils/decoder_utils.py:660-741), BEV mode 1 (:788-819);
  * core/bbox/coders/transfusion_bbox_coder.py:59-76 */
 int di_rcnn_rois_f32(const float* pred, int NP, const float* proj, const float* aux, float* rois, int* win, int* onbits,

@@ -274,6 +274,9 @@ class ImageRCNNBlock(nn.Module):
         self.out_size_factor_img, self.test_cfg, self.bbox_coder = out_size_factor_img, test_cfg, bbox_coder
         _rcnn_params(self, '', c, heads, dropout)
 
+    def _tail(self, q_view, roi):
+        return _rcnn_tail(self, '', q_view, roi)
+
     def forward(self, query_feat, res_layer, new_lidar_feat, img_feat_flatten, img_metas, img_h, img_w):
         B = query_feat.shape[0]
         P = self.num_proposals
@@ -314,7 +317,7 @@ class ImageRCNNBlock(nn.Module):
                 fmap = img_feat_flatten[b, v].reshape(-1, img_h, img_w)
                 roi = roi_align(fmap, rect, 7, 1.0 / self.out_size_factor_img, 2)
                 q_view = prev[b][:, on].t().unsqueeze(1)                                   # (n,1,C)
-                out[b][:, on] = _rcnn_tail(self, '', q_view, roi).t()
+                out[b][:, on] = self._tail(q_view, roi).t()
                 rects_dbg.append((b, v, on.nonzero().squeeze(1), rect))
         self._dbg = rects_dbg
         return out, on_mask
@@ -327,6 +330,9 @@ class PointRCNNBlock(nn.Module):
         super().__init__()
         self.bbox_coder = bbox_coder
         _rcnn_params(self, '_pts', c, heads, dropout)
+
+    def _tail(self, q_view, roi):
+        return _rcnn_tail(self, '_pts', q_view, roi)
 
     def forward(self, query_feat, res_layer, new_lidar_feat, img_feat_flatten, img_metas, img_h, img_w):
         B = query_feat.shape[0]
@@ -343,7 +349,7 @@ class PointRCNNBlock(nn.Module):
                                 cc[..., 0].max(-1).values, cc[..., 1].max(-1).values], -1)
             roi = roi_align(new_lidar_feat[b], rect, 7, 1.0, 2)
             q_view = query_feat[b].t().unsqueeze(1)
-            out[b] = _rcnn_tail(self, '_pts', q_view, roi).t()
+            out[b] = self._tail(q_view, roi).t()
         return out, None
 
 
@@ -417,6 +423,27 @@ class DeepInteractionDecoder(nn.Module):
         top = heatmap.view(B, -1).argsort(dim=-1, descending=True)[..., :self.num_proposals]
         return heatmap, top
 
+    def _mmpi(self, query_feat, res, first_res, new_lidar_feat, img_flat, img_metas, ih, iw, aux):
+        """:279-296: the alternating image / point RCNN layers (overridden by the ++ decoder)."""
+        self.on_the_image_mask = []
+        rets = []
+        for l in range(self.num_mmpi):
+            prev = query_feat.clone()
+            query_pos = res['center'].detach().clone().permute(0, 2, 1)
+            query_feat, on = self.decode_head[l](prev, res, new_lidar_feat, img_flat, img_metas, ih, iw)
+            res = self.pred_head[l](torch.cat([query_feat, prev], 1))
+            res['center'] = res['center'] + query_pos.permute(0, 2, 1)
+            if l % 2 == 0:
+                keep = on != -1
+                self.on_the_image_mask.append(keep)
+                for key in res:
+                    m = (~keep).unsqueeze(1).expand_as(res[key])
+                    res[key] = torch.where(m, first_res[key], res[key])
+                aux.setdefault('on_view', []).append(on.clone())
+            aux['layer_query'].append(query_feat.clone())
+            rets.append(res)
+        return rets
+
     def forward(self, pts_inputs, img_inputs, img_metas, return_aux=False):
         lidar_feat, new_lidar_feat = pts_inputs
         B, C = lidar_feat.shape[:2]
@@ -443,24 +470,8 @@ class DeepInteractionDecoder(nn.Module):
         aux['query_feat1'] = query_feat.clone()
         aux['first_res'] = {k: v.clone() for k, v in first_res.items()}
         img_flat = img_inputs.view(B, self.num_views, C, -1)
-        self.on_the_image_mask = []
-        rets = []
         aux['layer_query'] = []
-        for l in range(self.num_mmpi):
-            prev = query_feat.clone()
-            query_pos = res['center'].detach().clone().permute(0, 2, 1)
-            query_feat, on = self.decode_head[l](prev, res, new_lidar_feat, img_flat, img_metas, ih, iw)
-            res = self.pred_head[l](torch.cat([query_feat, prev], 1))
-            res['center'] = res['center'] + query_pos.permute(0, 2, 1)
-            if l % 2 == 0:
-                keep = on != -1
-                self.on_the_image_mask.append(keep)
-                for key in res:
-                    m = (~keep).unsqueeze(1).expand_as(res[key])
-                    res[key] = torch.where(m, first_res[key], res[key])
-                aux.setdefault('on_view', []).append(on.clone())
-            aux['layer_query'].append(query_feat.clone())
-            rets.append(res)
+        rets = self._mmpi(query_feat, res, first_res, new_lidar_feat, img_flat, img_metas, ih, iw, aux)
         rets[0]['query_heatmap_score'] = heatmap.gather(-1, top_index[:, None, :].expand(-1, self.num_classes, -1))
         rets[0]['dense_heatmap'] = dense_heatmap_img
         if not self.auxiliary:

@@ -61,7 +61,7 @@ def load_config(path):
 
 
 def build_neck(cfg):
-    """Build cfg.model.imgpts_neck alone (e.g. the ++ config, whose decoder variant is outside this repository)."""
+    """Build cfg.model.imgpts_neck alone."""
     model = cfg['model'] if 'model' in cfg else cfg
     return NECKS.build(model['imgpts_neck'])
 

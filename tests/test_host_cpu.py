@@ -146,6 +146,34 @@ def test_plusplus_config_builds_its_neck_with_the_reference_schema():
             assert reg.get(n) is not None, n
 
 
+@pytest.mark.parametrize('cfg_path', ['/root/reference/projects/configs/nuscenes/Fusion_0075_plusplus.py',
+                                      'projects/configs/nuscenes/di_b200_plusplus_hotpath.py'])
+def test_plusplus_config_builds_its_head_with_the_reference_schema(cfg_path):
+    """`pts_bbox_head` of the ++ config (DeepInteractionPlusPlusDecoder: V2 RCNN blocks with ffn / self_ffn / self_norm /
+    scale / self_scale, prediction heads on C channels) builds through HEADS; state_dict keys and shapes equal the
+    oracle's, whose state_dict tools/make_goldens.py (G7) loads strictly into the reference class."""
+    if not os.path.isabs(cfg_path):
+        cfg_path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), cfg_path)
+    if not os.path.exists(cfg_path):
+        pytest.skip('reference tree not mounted here')
+    import projects.mmdet3d_plugin  # noqa: F401
+    from projects.mmdet3d_plugin.registry import load_config, build_hot_path, HEADS
+    import oracle.mmpi_pp as opp
+    cfg = load_config(cfg_path)
+    neck, head = build_hot_path(cfg)
+    assert type(neck).__name__ == 'FusionTransformerv4' and type(head).__name__ == 'DeepInteractionPlusPlusDecoder'
+    assert HEADS.get('DeepInteractionPlusPlusDecoder') is not None
+    hc = {k: v for k, v in cfg['model']['pts_bbox_head'].items() if k not in ('type', 'train_cfg')}
+    o = opp.DeepInteractionPlusPlusDecoder(test_cfg=cfg['model']['test_cfg']['pts'], **hc)
+    a, b = head.state_dict(), o.state_dict()
+    assert set(a) == set(b), sorted(set(a) ^ set(b))[:8]
+    for k in a:
+        assert a[k].shape == b[k].shape, k
+    head.load_state_dict(b, strict=True)
+    assert any(k.endswith('self_ffn.layers.0.0.weight') for k in a) and 'decode_head.1.self_norm_pts.weight' in a
+    assert a['pred_head.0.center.0.conv.weight'].shape[1] == 128          # C, not 2C (:140)
+
+
 def test_product_modules_refuse_cpu_and_training():
     from deepinteraction_b200 import mmri
     enc = mmri.DeepInteractionEncoder(1, 8, 8, 16).eval()

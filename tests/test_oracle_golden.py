@@ -134,6 +134,39 @@ def test_decoder_small(tag):
         assert bool((a == b).all())
 
 
+def pp_scales(m):
+    """The generator's non-default branch scales (tools/make_goldens.py G7)."""
+    with torch.no_grad():
+        for i, blk in enumerate(m.decode_head):
+            blk.scale.fill_(0.6 + 0.05 * i)
+            blk.self_scale.fill_(0.35 - 0.03 * i)
+
+
+@pytest.mark.parametrize('tag', ['decoder_pp_small', 'decoder_pp_small_aug'])
+def test_decoder_pp_small(tag):
+    """++ decoder oracle (V2 RCNN blocks incl. the literal self-branch broadcast, look-forward centres, cumulative
+    on-image mask) against outputs of the reference's own deepinteractionplusplus_decoder.py."""
+    from oracle import mmpi_pp
+    g = load(tag)
+    torch.manual_seed(g['seed'])
+    m = make_decoder(mmpi_pp.DeepInteractionPlusPlusDecoder).eval()
+    synth.randomize_norm_stats(m, g['seed'])
+    pp_scales(m)
+    assert state_checksum(m.state_dict()) == g['checksum']
+    gen = torch.Generator().manual_seed(g['seed'])
+    fr = small_frame(g['seed'], aug=g['aug'], views=2, batch=2)
+    pts_in = [torch.randn(2, 128, 36, 36, generator=gen), torch.randn(2, 128, 36, 36, generator=gen)]
+    img_in = torch.randn(4, 128, 28, 50, generator=gen)
+    with torch.no_grad():
+        out = m(pts_in, img_in, fr['img_metas'])[0][0]
+    for k, ref in g['out'].items():
+        assert rel_err(out[k], ref) < 2e-4, k
+    assert bool((m.query_labels == g['query_labels']).all())
+    assert len(m.on_the_image_mask) == len(g['on_the_image_mask']) == 4
+    for a, b in zip(m.on_the_image_mask, g['on_the_image_mask']):
+        assert bool((a == b).all())
+
+
 def test_depth_completion_numpy_matches_cv2():
     import numpy as np
     from oracle import depth_completion as dc

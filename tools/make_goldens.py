@@ -33,6 +33,7 @@ sys.path.insert(0, ROOT)
 import oracle.geometry as og          # noqa: E402
 import oracle.mmri as ommri            # noqa: E402
 import oracle.mmpi as ommpi            # noqa: E402
+from oracle.mmri_pp import FFN as ompp_ffn   # noqa: E402
 from deepinteraction_b200 import synth  # noqa: E402
 
 PLUGIN = 'projects/mmdet3d_plugin'
@@ -120,7 +121,7 @@ def install_stubs(ref):
     sm['mmcv.cnn'].build_conv_layer = build_conv_layer
     sm['mmcv.cnn'].ConvModule = ConvModule
     sm['mmcv.cnn'].kaiming_init = lambda *a, **k: None
-    sm['mmcv.cnn.bricks.transformer'].FFN = object
+    sm['mmcv.cnn.bricks.transformer'].FFN = ompp_ffn      # mmcv 1.3.18 FFN (third party): oracle.mmri_pp.FFN restates it
     sm['mmcv.runner'].force_fp32 = lambda *a, **k: (lambda f: f)
     necks, heads, coders = _Registry(), _Registry(), _Registry()
     sm['mmdet3d.models.builder'].NECKS = necks
@@ -174,6 +175,9 @@ def install_stubs(ref):
     du = _load('projects.mmdet3d_plugin.models.utils.decoder_utils', os.path.join(P, 'models/utils/decoder_utils.py'))
     dec = _load('projects.mmdet3d_plugin.models.dense_heads.deepinteraction_decoder',
                 os.path.join(P, 'models/dense_heads/deepinteraction_decoder.py'))
+    decpp = _load('projects.mmdet3d_plugin.models.dense_heads.deepinteractionplusplus_decoder',
+                  os.path.join(P, 'models/dense_heads/deepinteractionplusplus_decoder.py'))
+    dec.PlusPlus = decpp.DeepInteractionPlusPlusDecoder
     return eu, enc, du, dec
 
 
@@ -327,6 +331,34 @@ def main():
         for k in r:
             print(tag, k, tuple(r[k].shape), 'oracle vs reference', cmp(o[k], r[k]))
         print(tag, 'labels equal', bool((rm.query_labels == om.query_labels).all()),
+              'on-image', [int(m.sum()) for m in rm.on_the_image_mask])
+        save(tag, dict(seed=seed, aug=aug, checksum=state_checksum(om.state_dict()), out=r,
+                       query_labels=rm.query_labels, on_the_image_mask=rm.on_the_image_mask))
+    # --- G7: the ++ decoder (V2 RCNN blocks, look-forward centres, cumulative on-image mask) -----------------
+    from oracle import mmpi_pp as ommpi_pp
+    for tag, aug in (('decoder_pp_small', False), ('decoder_pp_small_aug', True)):
+        if only and tag not in only:
+            continue
+        seed = 1700
+        torch.manual_seed(seed)
+        om = make_decoder(ommpi_pp.DeepInteractionPlusPlusDecoder).eval()
+        synth.randomize_norm_stats(om, seed)
+        with torch.no_grad():                      # the two branch scales start equal (0.5); make them distinguishable
+            for i, blk in enumerate(om.decode_head):
+                blk.scale.fill_(0.6 + 0.05 * i)
+                blk.self_scale.fill_(0.35 - 0.03 * i)
+        rm = make_decoder(dec.PlusPlus).eval()
+        rm.load_state_dict(om.state_dict(), strict=True)
+        g = torch.Generator().manual_seed(seed)
+        fr = small_frame(seed, aug=aug, views=2, batch=2)
+        pts_in = [torch.randn(2, 128, 36, 36, generator=g), torch.randn(2, 128, 36, 36, generator=g)]
+        img_in = torch.randn(4, 128, 28, 50, generator=g)
+        r = rm(pts_in, img_in, fr['img_metas'])[0][0]
+        o = om(pts_in, img_in, fr['img_metas'])[0][0]
+        for k in r:
+            print(tag, k, tuple(r[k].shape), 'oracle vs reference', cmp(o[k], r[k]))
+        print(tag, 'labels equal', bool((rm.query_labels == om.query_labels).all()),
+              'masks equal', all(bool((a == b).all()) for a, b in zip(rm.on_the_image_mask, om.on_the_image_mask)),
               'on-image', [int(m.sum()) for m in rm.on_the_image_mask])
         save(tag, dict(seed=seed, aug=aug, checksum=state_checksum(om.state_dict()), out=r,
                        query_labels=rm.query_labels, on_the_image_mask=rm.on_the_image_mask))
