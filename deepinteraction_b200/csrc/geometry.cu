@@ -204,14 +204,27 @@ __global__ void depth_scatter_kernel(const float* __restrict__ pts, int stride, 
 
 // ------------------------------------------------------------------------------------------------
 // BEVWarp stage 2: depth completion (ip_basic fill_in_multiscale, extrapolate=False, bilateral).
-// One CTA per camera image; planes live in global scratch (L2) and are read with ld.cg so that
-// every stage sees the previous stage's stores after the block barrier.
+// One thread-block CLUSTER of DC_CL CTAs per camera image (the ~18 dependent stencil stages are bound by the per-SM
+// L2 load rate, so the pixels of an image are dealt over DC_CL SMs); planes live in global scratch (L2) and are
+// read with ld.cg, so every stage sees the previous stage's stores after the cluster barrier (release / acquire at
+// cluster scope).  Column scans and the min/max reduction are done redundantly by every CTA of the cluster.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float ldcg(const float* p) { return __ldcg(p); }
 
+constexpr int DC_CL = 8;
+
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned cluster_cta_rank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+
 template <class F>
 __device__ __forceinline__ void for_pixels(int n, F f) {
-  for (int i = threadIdx.x; i < n; i += blockDim.x) f(i);
+  for (int i = cluster_cta_rank() * blockDim.x + threadIdx.x; i < n; i += DC_CL * blockDim.x) f(i);
 }
 
 // max over a full (2r+1)^2 window, out-of-image ignored
@@ -254,11 +267,11 @@ __device__ float median5(const float* src, int h, int w, int y, int x) {
 
 __device__ __forceinline__ float invert_depth(float d) { return d > 0.1f ? 100.0f - d : d; }
 
-__global__ void __launch_bounds__(1024)
+__global__ void __cluster_dims__(DC_CL, 1, 1) __launch_bounds__(1024)
 depth_complete_kernel(const unsigned long long* __restrict__ keys, float* __restrict__ scratch, float* __restrict__ out,
                       float* __restrict__ sparse_out, int h, int w) {
   const int n = h * w;
-  const size_t img = blockIdx.x;
+  const size_t img = blockIdx.x / DC_CL;
   const unsigned long long* key = keys + img * n;
   float* A = scratch + img * 3 * n;
   float* Bp = A + n;
@@ -274,7 +287,7 @@ depth_complete_kernel(const unsigned long long* __restrict__ keys, float* __rest
     A[i] = d;
     if (sparse_out) sparse_out[img * n + i] = d;
   });
-  __syncthreads();
+  cluster_sync_all();
   // S1: per-bin cross dilations (3: far, 5: medium, 7: near), merged far -> near; B = s2
   for_pixels(n, [&](int i) {
     int y = i / w, x = i - y * w;
@@ -304,32 +317,38 @@ depth_complete_kernel(const unsigned long long* __restrict__ keys, float* __rest
     if (near_m > 0.1f) s2 = near_m;
     Bp[i] = s2;
   });
-  __syncthreads();
+  cluster_sync_all();
   // S2: 5x5 closing: C = dilate(B); A = erode(C) = s3
   for_pixels(n, [&](int i) { Cp[i] = dil_full(Bp, h, w, i / w, i % w, 2); });
-  __syncthreads();
+  cluster_sync_all();
   for_pixels(n, [&](int i) { A[i] = ero_full(Cp, h, w, i / w, i % w, 2); });
-  __syncthreads();
+  cluster_sync_all();
   // S3: median where valid; B = s4
   for_pixels(n, [&](int i) {
     float s3 = ldcg(A + i);
     Bp[i] = s3 > 0.1f ? median5(A, h, w, i / w, i % w) : s3;
   });
-  __syncthreads();
+  cluster_sync_all();
   // S4: top mask of s4
+  // first row with a valid value per column (argmax of an all-false column is 0); every CTA builds its own copy
   auto top_mask = [&](const float* src) {
-    for (int x = threadIdx.x; x < w; x += blockDim.x) {
-      int f = 0;  // argmax of an all-false column is 0
-      for (int y = 0; y < h; ++y)
-        if (ldcg(src + y * w + x) > 0.1f) {
-          f = y;
-          break;
-        }
-      first_row[x] = f;
+    for (int x = threadIdx.x; x < w; x += blockDim.x) first_row[x] = h;
+    __syncthreads();
+    // thread t scans column t % w over the rows t / w, t / w + groups, ...  (w <= blockDim.x: checked by the host)
+    const int groups = blockDim.x / w, g = threadIdx.x / w, x = threadIdx.x - g * w;
+    if (g < groups) {
+      int f = h;
+#pragma unroll 4
+      for (int y = g; y < h; y += groups)
+        if (ldcg(src + y * w + x) > 0.1f) f = min(f, y);
+      if (f < h) atomicMin(&first_row[x], f);
     }
+    __syncthreads();
+    for (int x1 = threadIdx.x; x1 < w; x1 += blockDim.x)
+      if (first_row[x1] == h) first_row[x1] = 0;
+    __syncthreads();
   };
   top_mask(Bp);
-  __syncthreads();
   // S5: fill empties under the top mask with a 9x9 dilation; A = s5
   for_pixels(n, [&](int i) {
     int y = i / w, x = i - y * w;
@@ -337,10 +356,9 @@ depth_complete_kernel(const unsigned long long* __restrict__ keys, float* __rest
     bool empty = !(s4 > 0.1f) && y >= first_row[x];
     A[i] = empty ? dil_full(Bp, h, w, y, x, 4) : s4;
   });
-  __syncthreads();
+  cluster_sync_all();
   // S6: top mask of s5
   top_mask(A);
-  __syncthreads();
   // S7: six masked 5x5 dilations, ping-pong A -> B -> A ... (ends in A)
   float* src = A;
   float* dst = Bp;
@@ -351,7 +369,7 @@ depth_complete_kernel(const unsigned long long* __restrict__ keys, float* __rest
       bool empty = (s < 0.1f) && y >= first_row[x];
       dst[i] = empty ? dil_full(src, h, w, y, x, 2) : s;
     });
-    __syncthreads();
+    cluster_sync_all();
     float* tmp = src;
     src = dst;
     dst = tmp;
@@ -363,7 +381,7 @@ depth_complete_kernel(const unsigned long long* __restrict__ keys, float* __rest
     bool valid = (s > 0.1f) && y >= first_row[x];
     Bp[i] = valid ? median5(A, h, w, y, x) : s;
   });
-  __syncthreads();
+  cluster_sync_all();
   // S9: bilateral (d=5, sigmaColor=0.5, sigmaSpace=2) of s7m, written at the pre-median mask; re-invert
   {
     float mn = INFINITY, mx = -INFINITY;
@@ -543,8 +561,8 @@ int di_depth_scatter(const float* pts, int stride, int n, const float* proj, uns
 int di_depth_complete(const unsigned long long* keys, float* scratch, float* dense, float* sparse_out, int n_img, int h,
                       int w, cudaStream_t stream) {
   DI_CHECK_ARG(keys && scratch && dense && n_img > 0 && h > 4 && w > 4, "di_depth_complete: bad argument");
-  DI_CHECK_ARG(w * (int)sizeof(int) <= 40000, "di_depth_complete: image too wide");
-  depth_complete_kernel<<<n_img, 1024, w * sizeof(int), stream>>>(keys, scratch, dense, sparse_out, h, w);
+  DI_CHECK_ARG(w <= 1024, "di_depth_complete: image too wide");
+  depth_complete_kernel<<<n_img * DC_CL, 1024, w * sizeof(int), stream>>>(keys, scratch, dense, sparse_out, h, w);
   DI_CHECK_LAUNCH("di_depth_complete");
   return DI_OK;
 }

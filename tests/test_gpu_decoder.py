@@ -400,20 +400,35 @@ def test_decoder_pp_base_shape_matches_oracle():
         dbg = {}
         out = m.forward_nhwc(nhwc(pts_in[0]), nhwc(pts_in[1]), nhwc(img_in), metas, debug=dbg)[0][0]
         top, want = dbg['top'].cpu().long(), aux['top']
-        if torch.equal(top, want):
-            break
-        # The proposal ORDER is only defined up to the fp32 rounding of the heat-map scores (they agree to ~1e-6): a
-        # differing rank must be a near tie in the oracle's own scores -- then the case is skipped for the next seed.
+        # The proposal ORDER is only defined up to the fp32 rounding of the heat-map scores (they agree to ~1e-6; with
+        # 2 x 200 ranks a swap of two neighbours is likely).  A differing rank must be a near tie in the oracle's own
+        # scores.  The decoder is equivariant to the proposal order, so the outputs are compared after undoing the
+        # swap; a near tie AT the cut (rank 200) changes the proposal set itself: next seed.
         hs = aux['heatmap'].reshape(2, -1)
-        bad = (top != want).nonzero()
-        for b, r in bad.tolist():
+        for b, r in (top != want).nonzero().tolist():
             assert abs(float(hs[b, top[b, r]] - hs[b, want[b, r]])) < 1e-5 * float(hs[b, want[b, r]]), (seed, b, r)
-        print('seed', seed, ': near tie in the top-k at ranks', bad.tolist())
+        if all(set(top[b].tolist()) == set(want[b].tolist()) for b in range(2)):
+            break
+        print('seed', seed, ': near tie at the top-k cut')
     else:
-        raise AssertionError('no seed without a near tie')
-    assert torch.equal(m.query_labels.cpu(), o.query_labels)
-    for a, b in zip(m.on_the_image_mask, o.on_the_image_mask):
-        assert torch.equal(a.cpu(), b)
+        raise AssertionError('no seed without a near tie at the cut')
+    P = 200
+    labels, masks = m.query_labels.cpu().clone(), [k.cpu().clone() for k in m.on_the_image_mask]
+    out = {k: v.cpu().clone() for k, v in out.items()}
+    for b in range(2):
+        pos = {int(v): i for i, v in enumerate(top[b])}
+        perm = torch.tensor([pos[int(v)] for v in want[b]])
+        if not torch.equal(perm, torch.arange(P)):
+            print('batch', b, 'ranks swapped:', (perm != torch.arange(P)).nonzero().flatten().tolist())
+        labels[b] = labels[b][perm]
+        for k in masks:
+            k[b] = k[b][perm]
+        for k, v in out.items():
+            if k != 'dense_heatmap':
+                v[b] = v[b][..., torch.cat([perm + c * P for c in range(v.shape[-1] // P)])]
+    assert torch.equal(labels, o.query_labels)
+    for a, b in zip(masks, o.on_the_image_mask):
+        assert torch.equal(a, b)
     _compare(out, ref[0][0], TOL)
 
 
