@@ -445,10 +445,161 @@ def run_plusplus(args):
         dist.destroy_process_group()
 
 
+def run_large(args):
+    """BASELINE.json config 5 ("large" sweep): MMRI encoder at a 256x256 BEV grid with 6 camera maps of 128x352
+    (512x1408 inputs, stride 4) and hidden width C = --channels in {128, 256, 512}; for C = 128 the MMPI decoder with 300
+    queries follows (C != 128 cannot be built: DynamicConv is hard-coded to 128 channels, decoder_utils.py:589-591).
+    Pillars are generated on the GPU from the raw points inside the forward (pts_metas carries `pts` only).  Same JSON
+    contract as the base workload; frames run one after the other (no frames in flight)."""
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device: the product path has no CPU fallback'
+    torch.cuda.set_device(local)
+    device = torch.device('cuda', local)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=device)
+    torch.set_grad_enabled(False)
+    import projects.mmdet3d_plugin  # noqa: F401
+    from projects.mmdet3d_plugin.registry import load_config, build_hot_path
+    from deepinteraction_b200 import ops, synth, graph as di_graph
+    C, B, BEV, IN_HW = args.channels, args.batch, 256, (512, 1408)
+    cfg = load_config(CFG)
+    cfg['model']['imgpts_neck']['hidden_channel'] = C
+    cfg['model']['pts_bbox_head']['num_proposals'] = 300
+    cfg['model']['test_cfg']['pts']['grid_size'] = [BEV * 8, BEV * 8, 40]
+    torch.manual_seed(SEED)
+    if C == 128:
+        neck, head = build_hot_path(cfg)
+        synth.randomize_norm_stats(head, SEED + 1)
+        head = head.to(device).eval()
+    else:
+        from projects.mmdet3d_plugin.registry import build_neck
+        neck, head = build_neck(cfg), None
+    synth.randomize_norm_stats(neck, SEED)
+    neck = neck.to(device).eval()
+    NF = 3
+    pin = lambda t: t.contiguous().pin_memory()
+
+    def mk(seed, n_points):
+        fr = synth.make_frame_batch(seed, batch=B, in_hw=IN_HW, bev_hw=(BEV, BEV), n_points=n_points)
+        return dict(img=pin(fr['img_feats']), pts=pin(fr['pts_feats']), img_metas=fr['img_metas'],
+                    cloud=[pin(p) for p in fr['pts_metas']['pts']])
+    hosts = [mk(SEED + 1000 * rank + i, int(250000 * (0.9 + 0.05 * i))) for i in range(NF)]
+    nb = lambda t: t.to(device, non_blocking=True)
+    devs = [dict(img=nb(f['img']), pts=nb(f['pts']), img_metas=f['img_metas'], cloud=[nb(p) for p in f['cloud']]) for f in hosts]
+
+    def fwd(d):
+        img, pts = neck(d['img'], d['pts'], d['img_metas'], dict(pts=d['cloud']))
+        return (img, pts[0], pts[1]) if head is None else tuple(head(pts, img, d['img_metas'])[0][0].values())
+    W, K = max(args.warmup, 3), args.steps
+    for _ in range(3):
+        for d in devs:
+            out = fwd(d)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+    for i in range(W):
+        fwd(devs[i % NF])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        barrier()
+        l0 = ops.LAUNCHES[0]
+        e0.record()
+        for i in range(K):
+            out = fwd(devs[i % NF])
+        e1.record()
+        barrier()
+        launches = ops.LAUNCHES[0] - l0
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        dset = dict(img=torch.empty_like(devs[0]['img']), pts=torch.empty_like(devs[0]['pts']))
+        outs_host = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in out]
+        h2d_b = int(np.mean([sum(t.numel() * 4 for t in [f['img'], f['pts']] + f['cloud']) for f in hosts]))
+
+        def e2e_step(i):
+            fh = hosts[i % NF]
+            dset['img'].copy_(fh['img'], non_blocking=True)
+            dset['pts'].copy_(fh['pts'], non_blocking=True)
+            o = fwd(dict(img=dset['img'], pts=dset['pts'], img_metas=fh['img_metas'], cloud=[nb(p) for p in fh['cloud']]))
+            for dst, src in zip(outs_host, o):
+                dst.copy_(src, non_blocking=True)
+        for i in range(3):
+            e2e_step(i)
+        barrier()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record()
+        for i in range(K):
+            e2e_step(i)
+        e3.record()
+        barrier()
+        ms_e2e = max_over_ranks(e2.elapsed_time(e3))
+    clocks = clk.summary()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    frames = B * world * K
+    pk = peaks()
+    di_graph.ENABLED[0] = False
+    neck._graphs.clear()
+    if head is not None:
+        head._graphs.clear()
+    ops.PROFILE[0] = []
+    for _ in range(2):
+        fwd(devs[0])
+    torch.cuda.synchronize()
+    agg = {}
+    for name, a, b, nbytes, flops, mod in ops.PROFILE[0]:
+        d = agg.setdefault(name.split(' ')[0], dict(ms=0.0, n=0, bytes=0, flops=0))
+        d['ms'] += a.elapsed_time(b)
+        d['n'] += 1
+        d['bytes'] += nbytes
+        d['flops'] += flops
+    ops.PROFILE[0] = None
+    di_graph.ENABLED[0] = True
+    tot = sum(d['ms'] for d in agg.values())
+    kernels = [dict(name=n, launches_per_step=d['n'] / 2, ms_per_step=d['ms'] / 2, share=d['ms'] / tot,
+                    avg_us=d['ms'] / d['n'] * 1e3, gbs=d['bytes'] / max(d['ms'], 1e-9) / 1e6,
+                    tflops=d['flops'] / max(d['ms'], 1e-9) / 1e9)
+               for n, d in sorted(agg.items(), key=lambda kv: -kv[1]['ms'])]
+    top = kernels[0]
+    roof = dict(bound='hbm', achieved=top['gbs'], peak=pk['hbm'], unit='GB/s', frac=top['gbs'] / pk['hbm'], kernel=top['name'],
+                traffic=None, peak_source=pk['src'], share_of_step=top['share'], avg_launch_us=top['avg_us'])
+    what = 'MMRI encoder' + (' + MMPI decoder (300 q)' if head is not None else ' (decoder needs C = 128)')
+    line = dict(metric='frames/sec %s, 256x256 BEV / 6 cams 128x352 / C=%d' % (what, C), value=frames / (ms * 1e-3),
+                unit='frames/s', n_gpus=world, steps=K, warmup=W, ms_per_step=ms / K, higher_is_better=True, scaling='weak',
+                vs_baseline=None, dtype='fp32', data='synthetic',
+                config=dict(workload='BASELINE config 5 large sweep: DeepInteraction-base modules, 256x256 BEV, 6 x 128x352 maps, '
+                                     'C=%d, bs=%d/GPU' % (C, B), global_batch=B * world,
+                            parallelism=f'dp{world} (independent frames, no data-path collective)',
+                            l2='inputs (%.0f MB/step) larger than L2; %d distinct frames cycled' % (h2d_b / 1e6, NF)),
+                clocks=clocks, e2e=dict(value=frames / (ms_e2e * 1e-3), unit='frames/s', h2d_bytes_per_step=h2d_b,
+                                        d2h_bytes_per_step=int(sum(t.numel() * t.element_size() for t in outs_host)),
+                                        ms_per_step=ms_e2e / K),
+                gpu_launches=launches, launches_per_step=launches / K, roofline=roof, cpu_baseline=None, kernels=kernels[:12])
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument('--workload', default='base', choices=['base', 'plusplus'],
-                    help='base = BASELINE.json config 2 (the headline metric); plusplus = config 4 (++ encoder)')
+    ap.add_argument('--workload', default='base', choices=['base', 'plusplus', 'large'],
+                    help='base = BASELINE.json config 2 (the headline metric); plusplus = config 4 (++ encoder); '
+                         'large = config 5 (256x256 BEV, 128x352 maps, --channels C)')
+    ap.add_argument('--channels', type=int, default=128, choices=[128, 256, 512], help='large workload: hidden width C')
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=30)
     ap.add_argument('--warmup', type=int, default=5)
@@ -470,6 +621,8 @@ def main():
         if args.batch == 1:
             args.batch = 2                       # config 4: bs=4 on 2 GPUs
         return run_plusplus(args)
+    if args.workload == 'large':
+        return run_large(args)
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))

@@ -509,14 +509,15 @@ def test_encoder_without_pillars_is_defined():
     assert rel_err(img.cpu(), r_img) < TOL and rel_err(p1.cpu(), r_p1) < TOL
 
 
-def test_encoder_hidden_256_matches_oracle():
-    """SURVEY config 5 varies the encoder width: C = 256 (window kernel with 8 channel chunks, K = 256 / 768 dense
-    layers on the tensor-core path, I2P fold at 256)."""
+@pytest.mark.parametrize('C', [256, 512])
+def test_encoder_hidden_256_512_matches_oracle(C):
+    """SURVEY config 5 varies the encoder width: C = 256 / 512 (window kernel with 8 / 16 channel chunks, K = C / 3C
+    dense layers on the tensor-core path, I2P fold at C)."""
     from deepinteraction_b200 import mmri, synth
     import oracle.mmri as om
     seed = 1720
     torch.manual_seed(seed)
-    m = om.DeepInteractionEncoder(1, 64, 64, 256).eval()
+    m = om.DeepInteractionEncoder(1, 64, 64, C).eval()
     synth.randomize_norm_stats(m, seed)
     fr = synth.make_frame_batch(seed, batch=1, num_views=2, in_hw=(128, 224), stride=4, c_img=64, c_pts=64,
                                 bev_hw=(48, 48), n_points=20000, cloud='dense')
@@ -525,11 +526,11 @@ def test_encoder_hidden_256_matches_oracle():
                            pillars_num_points=torch.from_numpy(npts))
     with torch.no_grad():
         r_img, (r_p0, r_p1) = m(fr['img_feats'], fr['pts_feats'], fr['img_metas'], fr['pts_metas'])
-    enc = mmri.DeepInteractionEncoder(1, 64, 64, 256)
+    enc = mmri.DeepInteractionEncoder(1, 64, 64, C)
     enc.load_state_dict(m.state_dict(), strict=True)
     enc = enc.to(dev()).eval()
     frd = synth.to_device(fr, dev())
     img, (p0, p1) = enc(frd['img_feats'], frd['pts_feats'], frd['img_metas'], frd['pts_metas'])
     e = (rel_err(img.cpu(), r_img), rel_err(p0.cpu(), r_p0), rel_err(p1.cpu(), r_p1))
-    print('C=256 encoder rel err img %.2e pts_conv %.2e pts %.2e' % e)
+    print('C=%d encoder rel err img %.2e pts_conv %.2e pts %.2e' % ((C,) + e))
     assert max(e) < TOL
