@@ -167,6 +167,39 @@ def test_decoder_pp_small(tag):
         assert bool((a == b).all())
 
 
+@pytest.mark.parametrize('tag', ['decoder_loss', 'decoder_pp_loss'])
+def test_loss_path(tag):
+    """Targets (Hungarian assignment, encoded boxes, weights, gaussian heat maps) and the loss dict of oracle/loss.py
+    part 1 against the outputs of the reference's own get_targets / loss / HungarianAssigner3D."""
+    import oracle.loss as ol
+    from tools.make_goldens import DEC_TRAIN_CFG, DEC_LOSSES, DEC_CODER
+    g = load(tag)
+    coder = ommpi.TransFusionBBoxCoder(**{k: v for k, v in DEC_CODER.items() if k != 'type'})
+    lh = ol.LossHead(10, 24, 4, coder, DEC_TRAIN_CFG, plusplus=tag == 'decoder_pp_loss', **DEC_LOSSES)
+    lh.query_labels, lh.on_the_image_mask = g['query_labels'], g['on_the_image_mask']
+    out = lh.loss([ol.LiDARBoxes(b) for b in g['gt_boxes']], g['gt_labels'], [[{k: v.clone() for k, v in g['preds'].items()}]])
+    for k, ref in g['losses'].items():
+        assert rel_err(out[k], ref) < 1e-6, k
+    # the goldens store get_targets' outputs (before loss() applies the on-image masks)
+    tg = lh.get_targets([ol.LiDARBoxes(b) for b in g['gt_boxes']], g['gt_labels'], [{k: v.clone() for k, v in g['preds'].items()}])
+    t = g['targets']
+    assert torch.equal(tg[0], t['labels']) and torch.equal(tg[1], t['label_weights']) and torch.equal(tg[3], t['bbox_weights'])
+    assert rel_err(tg[2], t['bbox_targets']) < 1e-6 and rel_err(tg[4], t['ious']) < 1e-6 and int(tg[5]) == t['num_pos']
+    assert torch.equal(tg[7], t['heatmap'])
+
+
+def test_rotated_iou_known_answers():
+    import oracle.loss as ol
+    a = torch.tensor([[0., 0., 0., 2., 2., 1., 0.], [0., 0., 0., 2., 2., 1., 0.7853981634], [5., 5., 0., 1., 1., 1., 0.3]])
+    b = torch.tensor([[1., 0., 0., 2., 2., 1., 0.], [0., 0., 0.5, 2., 2., 1., 0.]])
+    iou = ol.BboxOverlaps3D()(a, b)
+    assert abs(float(iou[0, 0]) - (2 * 1 * 1) / (4 + 4 - 2)) < 1e-6                   # half overlap along x
+    assert abs(float(iou[0, 1]) - (4 * 0.5) / (4 + 4 - 2)) < 1e-6                     # same footprint, half the height
+    oct_area = 8 * (2 ** 0.5 - 1)                                                     # square vs the same square turned 45 deg
+    assert abs(float(iou[1, 1]) - (oct_area * 0.5) / (8 - oct_area * 0.5)) < 1e-6
+    assert float(iou[2].abs().max()) == 0.0
+
+
 def test_depth_completion_numpy_matches_cv2():
     import numpy as np
     from oracle import depth_completion as dc

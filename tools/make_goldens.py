@@ -34,6 +34,7 @@ import oracle.geometry as og          # noqa: E402
 import oracle.mmri as ommri            # noqa: E402
 import oracle.mmpi as ommpi            # noqa: E402
 from oracle.mmri_pp import FFN as ompp_ffn   # noqa: E402
+import oracle.loss as oloss            # noqa: E402
 from deepinteraction_b200 import synth  # noqa: E402
 
 PLUGIN = 'projects/mmdet3d_plugin'
@@ -79,6 +80,8 @@ def install_stubs(ref):
               'mmdet3d', 'mmdet3d.models', 'mmdet3d.models.fusion_layers', 'mmdet3d.models.builder',
               'mmdet3d.models.utils', 'mmdet3d.core', 'mmdet3d.ops', 'mmdet3d.ops.iou3d',
               'mmdet3d.ops.iou3d.iou3d_utils', 'mmdet', 'mmdet.core', 'mmdet.core.bbox', 'mmdet.core.bbox.builder',
+              'mmdet.core.bbox.assigners', 'mmdet.core.bbox.match_costs', 'mmdet.core.bbox.match_costs.builder',
+              'mmdet.core.bbox.iou_calculators', 'projects.mmdet3d_plugin.core.bbox.assigners',
               'detectron2', 'detectron2.modeling', 'detectron2.modeling.poolers', 'detectron2.structures']:
         _mod(n)
     sm = sys.modules
@@ -126,11 +129,15 @@ def install_stubs(ref):
     necks, heads, coders = _Registry(), _Registry(), _Registry()
     sm['mmdet3d.models.builder'].NECKS = necks
     sm['mmdet3d.models.builder'].HEADS = heads
-    sm['mmdet3d.models.builder'].build_loss = lambda cfg: None
-    sm['mmdet3d.models.utils'].clip_sigmoid = None
+    # losses / target utilities of mmdet 2.14 and mmdet3d 0.17.1 (third party): restated in oracle.loss, part 2
+    sm['mmdet3d.models.builder'].build_loss = oloss.build_loss
+    sm['mmdet3d.models.utils'].clip_sigmoid = oloss.clip_sigmoid
     sm['mmdet3d.ops.iou3d.iou3d_utils'].nms_gpu = None
-    for n in ['circle_nms', 'draw_heatmap_gaussian', 'gaussian_radius', 'xywhr2xyxyr', 'PseudoSampler']:
+    for n in ['circle_nms', 'xywhr2xyxyr']:
         setattr(sm['mmdet3d.core'], n, None)
+    sm['mmdet3d.core'].draw_heatmap_gaussian = oloss.draw_heatmap_gaussian
+    sm['mmdet3d.core'].gaussian_radius = oloss.gaussian_radius
+    sm['mmdet3d.core'].PseudoSampler = oloss.PseudoSampler
 
     class LiDARInstance3DBoxes:                       # mmdet3d 0.17.1 (third party, unpinned)
         def __init__(self, tensor, box_dim=7):
@@ -143,8 +150,19 @@ def install_stubs(ref):
     sm['mmdet.core.bbox'].BaseBBoxCoder = object
     sm['mmdet.core.bbox.builder'].BBOX_CODERS = coders
     sm['mmdet.core'].build_bbox_coder = coders.build
-    for n in ['multi_apply', 'build_assigner', 'build_sampler', 'AssignResult']:
-        setattr(sm['mmdet.core'], n, None)
+    assigners, costs = _Registry(), _Registry()
+    costs.register_module()(oloss.FocalLossCost)
+    sm['mmdet.core.bbox.builder'].BBOX_ASSIGNERS = assigners
+    sm['mmdet.core.bbox.assigners'].AssignResult = oloss.AssignResult
+    sm['mmdet.core.bbox.assigners'].BaseAssigner = object
+    sm['mmdet.core.bbox.match_costs'].build_match_cost = costs.build
+    sm['mmdet.core.bbox.match_costs.builder'].MATCH_COST = costs
+    sm['mmdet.core.bbox.iou_calculators'].build_iou_calculator = \
+        lambda cfg: oloss.BboxOverlaps3D(**{k: v for k, v in cfg.items() if k != 'type'})
+    sm['mmdet.core'].multi_apply = oloss.multi_apply
+    sm['mmdet.core'].build_assigner = assigners.build
+    sm['mmdet.core'].build_sampler = None
+    sm['mmdet.core'].AssignResult = oloss.AssignResult
 
     # detectron2 ROIPooler(ROIAlignV2, one level) == torchvision roi_align(aligned=True)
     import torchvision.ops as tvo
@@ -172,6 +190,8 @@ def install_stubs(ref):
                 os.path.join(P, 'models/necks/deepinteraction_encoder.py'))
     _load('projects.mmdet3d_plugin.core.bbox.coders.transfusion_bbox_coder',
           os.path.join(P, 'core/bbox/coders/transfusion_bbox_coder.py'))
+    _load('projects.mmdet3d_plugin.core.bbox.assigners.hungarian_assigner',
+          os.path.join(P, 'core/bbox/assigners/hungarian_assigner.py'))
     du = _load('projects.mmdet3d_plugin.models.utils.decoder_utils', os.path.join(P, 'models/utils/decoder_utils.py'))
     dec = _load('projects.mmdet3d_plugin.models.dense_heads.deepinteraction_decoder',
                 os.path.join(P, 'models/dense_heads/deepinteraction_decoder.py'))
@@ -208,8 +228,46 @@ def small_frame(seed, aug=False, views=2, c_img=16, c_pts=24, bev=36, batch=1, n
     return fr
 
 
-def make_decoder(cls, views=2, proposals=24):
-    return cls(num_views=views, out_size_factor_img=4, num_proposals=proposals, auxiliary=True, hidden_channel=128,
+DEC_TRAIN_CFG = dict(dataset='nuScenes',
+                     assigner=dict(type='HungarianAssigner3D', iou_calculator=dict(type='BboxOverlaps3D', coordinate='lidar'),
+                                   cls_cost=dict(type='FocalLossCost', gamma=2, alpha=0.25, weight=0.15),
+                                   reg_cost=dict(type='BBoxBEVL1Cost', weight=0.25), iou_cost=dict(type='IoU3DCost', weight=0.25)),
+                     pos_weight=-1, gaussian_overlap=0.1, min_radius=2, grid_size=[288, 288, 40], voxel_size=[0.375, 0.375, 0.2],
+                     out_size_factor=8, code_weights=[1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 0.2, 0.2],
+                     point_cloud_range=[-54.0, -54.0, -5.0, 54.0, 54.0, 3.0])
+DEC_LOSSES = dict(loss_cls=dict(type='FocalLoss', use_sigmoid=True, gamma=2, alpha=0.25, reduction='mean', loss_weight=1.0),
+                  loss_bbox=dict(type='L1Loss', reduction='mean', loss_weight=0.25),
+                  loss_heatmap=dict(type='GaussianFocalLoss', reduction='mean', loss_weight=1.0))
+
+
+def loss_case_gt(preds, coder, seed, counts=(7, 5)):
+    """Synthetic ground truth of the loss goldens: per sample, boxes drawn at random inside the range plus three
+    jittered copies of decoded last-layer predictions (non-zero IoU entries)."""
+    g = torch.Generator().manual_seed(seed)
+    P = preds['query_heatmap_score'].shape[-1]
+    last = {k: preds[k][..., -P:] for k in ('heatmap', 'rot', 'dim', 'center', 'height', 'vel')}
+    dec = coder.decode(*(last[k].clone() for k in ('heatmap', 'rot', 'dim', 'center', 'height', 'vel')))
+    boxes, labels = [], []
+    for b, n in enumerate(counts):
+        xy = torch.rand(n, 2, generator=g) * 90 - 45
+        z = torch.rand(n, 1, generator=g) * 2 - 2.5
+        dims = torch.stack([torch.rand(n, generator=g) * 1.5 + 1.5, torch.rand(n, generator=g) * 3 + 3,
+                            torch.rand(n, generator=g) * 0.8 + 1.4], 1)
+        yaw = torch.rand(n, 1, generator=g) * 6.2 - 3.1
+        vel = torch.randn(n, 2, generator=g)
+        bx = torch.cat([xy, z, dims, yaw, vel], 1)
+        pick = torch.randperm(P, generator=g)[:3]
+        near = dec[b]['bboxes'][pick].clone()
+        near[:, :2] += torch.randn(3, 2, generator=g) * 0.3
+        near[:, 3:6] *= 1 + 0.1 * torch.randn(3, 3, generator=g)
+        near[:, 6] += 0.1 * torch.randn(3, generator=g)
+        boxes.append(torch.cat([bx, near], 0))
+        labels.append(torch.randint(0, 10, (n + 3,), generator=g))
+    return boxes, labels
+
+
+def make_decoder(cls, views=2, proposals=24, **extra):
+    return cls(**extra, num_views=views, out_size_factor_img=4, num_proposals=proposals, auxiliary=True, hidden_channel=128,
                num_classes=10, num_mmpi=4, num_heads=8, initialize_by_heatmap=True, nms_kernel_size=3,
                ffn_channel=256, dropout=0.1, bn_momentum=0.1, activation='relu',
                common_heads=dict(center=(2, 2), height=(1, 2), dim=(3, 2), rot=(2, 2), vel=(2, 2)),
@@ -362,6 +420,41 @@ def main():
               'on-image', [int(m.sum()) for m in rm.on_the_image_mask])
         save(tag, dict(seed=seed, aug=aug, checksum=state_checksum(om.state_dict()), out=r,
                        query_labels=rm.query_labels, on_the_image_mask=rm.on_the_image_mask))
+    # --- G8: loss path (targets, Hungarian assignment, gaussian heat-map targets, focal / L1 / gaussian-focal losses):
+    #     the reference's get_targets / loss / HungarianAssigner3D run UNMODIFIED on oracle.loss part 2 (third party)
+    from oracle import mmpi_pp as ommpi_pp2
+    for tag, rcls, ocls, pp in (('decoder_loss', dec.DeepInteractionDecoder, ommpi.DeepInteractionDecoder, False),
+                                ('decoder_pp_loss', dec.PlusPlus, ommpi_pp2.DeepInteractionPlusPlusDecoder, True)):
+        if only and tag not in only:
+            continue
+        seed = 1600
+        torch.manual_seed(seed)
+        om = make_decoder(ocls).eval()
+        synth.randomize_norm_stats(om, seed)
+        rm = make_decoder(rcls, train_cfg=oloss.ConfigDict(DEC_TRAIN_CFG), loss_bbox=DEC_LOSSES['loss_bbox'],
+                          loss_heatmap=DEC_LOSSES['loss_heatmap']).eval()
+        rm.load_state_dict(om.state_dict(), strict=True)
+        g = torch.Generator().manual_seed(seed)
+        fr = small_frame(seed, aug=False, views=2, batch=2)
+        pts_in = [torch.randn(2, 128, 36, 36, generator=g), torch.randn(2, 128, 36, 36, generator=g)]
+        img_in = torch.randn(4, 128, 28, 50, generator=g)
+        preds = rm(pts_in, img_in, fr['img_metas'])
+        boxes, labels = loss_case_gt(preds[0][0], om.bbox_coder, seed)
+        gt = [oloss.LiDARBoxes(b) for b in boxes]
+        saved = {k: v.clone() for k, v in preds[0][0].items()}
+        tg = rm.get_targets(gt, labels, preds[0])
+        ld = rm.loss(gt, labels, preds)
+        lh = oloss.LossHead(10, 24, 4, om.bbox_coder, DEC_TRAIN_CFG, auxiliary=True, plusplus=pp, **DEC_LOSSES)
+        lh.query_labels, lh.on_the_image_mask = rm.query_labels, rm.on_the_image_mask
+        lo = lh.loss(gt, labels, [[{k: v.clone() for k, v in saved.items()}]])
+        for k in ld:
+            print(tag, k, float(ld[k]), 'oracle vs reference', cmp(lo[k], ld[k]))
+        print(tag, 'num_pos', int(tg[5]), 'assignment equal', bool((lo['_targets']['labels'] == tg[0]).all()),
+              'heatmap targets equal', bool((lo['_targets']['heatmap'] == tg[7]).all()))
+        save(tag, dict(seed=seed, preds=saved, query_labels=rm.query_labels, on_the_image_mask=rm.on_the_image_mask,
+                       gt_boxes=boxes, gt_labels=labels, losses={k: v.clone() for k, v in ld.items()},
+                       targets=dict(labels=tg[0], label_weights=tg[1], bbox_targets=tg[2], bbox_weights=tg[3], ious=tg[4],
+                                    num_pos=int(tg[5]), matched_ious=float(tg[6]), heatmap=tg[7])))
     # --- G6: get_bboxes + bbox coder (A16): batch 1 (the reference asserts it, :631-632), nms_type None ---
     class Boxes:                                    # stands in for img_metas['box_type_3d'] (mmdet3d LiDARInstance3DBoxes)
         def __init__(self, tensor, box_dim=9):
