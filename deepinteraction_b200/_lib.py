@@ -72,6 +72,12 @@ SIGNATURES = {
     'di_rows_finish_f32': [_p, _i, _ll, _i, _p, _p, _i, _p, _p, _p, _i, _p, _i, _i, _i, _f, _p],
     'di_rows_mlp_f32': [_p, _i, _i, _p, _i, _i, _p, _p, _i, _i, _p, _p, _i, _p, _i, _p, _p, _f, _i, _p, _p, _i, _i, _p],
     'di_pred_finish_f32': [_p, _p, _p, _p, _i, _i, _p],
+    'di_match_cost_f32': [_p, _i, _p, _i, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p],
+    'di_hungarian_f32': [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p],
+    'di_loss_targets_f32': [_p, _p, _p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
+    'di_gaussian_heatmap_f32': [_p, _i, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p],
+    'di_mmpi_losses_f32': [_p, _p, _ll, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p,
+                           _p, _p, _p, _p],
     'di_pred_finish_pp_f32': [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     'di_rcnn_leaders': [_p, _p, _p, _i, _i, _i, _p],
     'di_mha_small_rows_f32': [_p, _i, _p, _i, _p, _i, _p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],

@@ -25,6 +25,7 @@ import torch
 import torch.nn as nn
 
 from . import fold, geom, ops
+from .loss import LossMixin
 from .graph import GraphCache
 from .mmri import ConvBN
 
@@ -197,10 +198,11 @@ HEAD_ORDER = ('center', 'height', 'dim', 'rot', 'vel', 'heatmap')
 _DYN_BF16 = os.environ.get('DI_B200_DYN_BF16', '0') != '0'
 
 
-class DeepInteractionDecoder(nn.Module):
+class DeepInteractionDecoder(nn.Module, LossMixin):
     """Drop-in for the reference ``DeepInteractionDecoder`` (HEADS): same constructor kwargs, state_dict
     and forward contract (``forward(pts_inputs, img_inputs, img_metas) -> [[dict]]``; side attributes
-    ``query_labels`` and ``on_the_image_mask``).  Inference (eval) only."""
+    ``query_labels`` and ``on_the_image_mask``); ``get_bboxes``, ``get_targets`` and ``loss`` (forward values,
+    deepinteraction_b200/loss.py).  The forward is inference (eval) only."""
     _BLOCKS = (ImageRCNNBlock, PointRCNNBlock)
     _PRED_SRCS = 2          # prediction heads of the MMPI layers read cat([query, previous query]) (:289)
 
@@ -262,6 +264,7 @@ class DeepInteractionDecoder(nn.Module):
         self.on_the_image_mask = []
         self._pack, self._pack_key = None, None
         self._graphs = GraphCache()
+        self._init_loss(train_cfg, loss_cls, loss_bbox, loss_heatmap)
 
     # -- packing -----------------------------------------------------------------------------------
     def _state_key(self):
@@ -606,3 +609,4 @@ class DeepInteractionPlusPlusDecoder(DeepInteractionDecoder):
     every layer (:295-302; ``on_the_image_mask`` holds num_mmpi masks).  Same constructor kwargs and state_dict."""
     _BLOCKS = (ImageRCNNBlockV2, PointRCNNBlockV2)
     _PRED_SRCS = 1
+    _PP_MASKS = True          # loss: every layer's weights are multiplied by that layer's mask (:513-514)

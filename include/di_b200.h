@@ -311,6 +311,30 @@ int di_bbox_encode_f32(const float* boxes, int nb, float* targets, int code, int
 int di_circle_nms_f32(const float* boxes, int nb, const float* scores, const int* labels, unsigned char* keep_io, int B,
                       int P, unsigned class_mask, float thresh, int post_max, cudaStream_t stream);
 
+/* ---- MMPI loss path ------------------------------------------------------------------------
+ * replaces core/bbox/assigners/hungarian_assigner.py:14-47 (match costs) + mmdet FocalLossCost + mmdet3d BboxOverlaps3D */
+int di_match_cost_f32(const float* boxes, int nb, const float* score, int K, const float* gt, const int* gt_labels,
+                      const int* n_gt, int B, int LP, int Gmax, const float* params11, float* cost, float* iou,
+                      cudaStream_t stream);
+/* hungarian_assigner.py:132-149 (scipy linear_sum_assignment on the CPU in the reference): one warp per (sample, layer) */
+int di_hungarian_f32(const float* cost, const float* iou, const int* n_gt, int B, int L, int P, int Gmax, long long* gt_inds,
+                     float* max_overlaps, cudaStream_t stream);
+/* models/dense_heads/deepinteraction_decoder.py:400-441 (+ the on-image mask products of :501-509) */
+int di_loss_targets_f32(const long long* gt_inds, const float* max_overlaps, const float* gt, const int* gt_labels, int Gmax,
+                        const unsigned char* mask, int mask_mode, int B, int L, int P, int nb, int code, int num_classes,
+                        float pos_weight, const float* coder4, long long* labels, long long* label_w, float* bbox_t,
+                        float* bbox_w, float* ious, float* num_pos, float* iou_sum, int* pos_cnt, cudaStream_t stream);
+/* deepinteraction_decoder.py:443-476 (gaussian_radius + draw_heatmap_gaussian per ground-truth box) */
+int di_gaussian_heatmap_f32(const float* gt, int nb, const int* gt_labels, const int* n_gt, int B, int Gmax, int K, int Y, int X,
+                            const float* params7, float* heat, cudaStream_t stream);
+/* deepinteraction_decoder.py:511-545: GaussianFocalLoss(clip_sigmoid(dense_heatmap)), per layer FocalLoss + weighted L1 */
+int di_mmpi_losses_f32(const float* dense_logit, const float* heat_target, long long n_heat, const float* score,
+                       const float* center, const float* height, const float* dim, const float* rot, const float* vel,
+                       const long long* labels, const long long* label_w, const float* bbox_t, const float* bbox_w,
+                       const float* num_pos, const float* iou_sum, const int* pos_cnt, int B, int K, int L, int P, int code,
+                       const float* code_w, const float* focal2, const float* gfl2, const float* weights3, double* work,
+                       float* out, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

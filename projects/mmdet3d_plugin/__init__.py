@@ -13,3 +13,5 @@ from .models.necks.deepinteraction_encoder import DeepInteractionEncoder  # noqa
 from .models.necks.fusion_transformerv4 import (FusionTransformerv4, DeepInteractionLayer, MMRI_P2I, MMRI_I2P,  # noqa: F401
                                                 MMRI_I2P_Polar)
 from .core.bbox.coders.transfusion_bbox_coder import TransFusionBBoxCoder  # noqa: F401
+from .core.bbox.assigners.hungarian_assigner import (HungarianAssigner3D, HeuristicAssigner3D, BBox3DL1Cost,  # noqa: F401
+                                                     BBoxBEVL1Cost, IoU3DCost)

@@ -50,6 +50,8 @@ HEADS = _real('mmdet3d.models.builder', 'HEADS') or Registry('head')
 BBOX_CODERS = _real('mmdet.core.bbox.builder', 'BBOX_CODERS') or Registry('bbox_coder')
 TRANSFORMER_LAYER = _real('mmcv.cnn.bricks.registry', 'TRANSFORMER_LAYER') or Registry('transformer layer')
 ATTENTION = _real('mmcv.cnn.bricks.registry', 'ATTENTION') or Registry('attention')
+BBOX_ASSIGNERS = _real('mmdet.core.bbox.builder', 'BBOX_ASSIGNERS') or Registry('bbox_assigner')
+MATCH_COST = _real('mmdet.core.bbox.match_costs.builder', 'MATCH_COST') or Registry('match cost')
 
 
 def load_config(path):
@@ -74,6 +76,7 @@ def build_hot_path(cfg):
     head_cfg = dict(model['pts_bbox_head'])
     test_cfg = model.get('test_cfg') or {}
     # folded into the cfg like MVXTwoStageDetector does (mmcv's Registry.build takes the cfg only)
-    head_cfg.update(train_cfg=None, test_cfg=test_cfg.get('pts'))
+    train_cfg = model.get('train_cfg') or {}
+    head_cfg.update(train_cfg=train_cfg.get('pts'), test_cfg=test_cfg.get('pts'))
     head = HEADS.build(head_cfg)
     return neck, head

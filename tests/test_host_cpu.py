@@ -174,6 +174,26 @@ def test_plusplus_config_builds_its_head_with_the_reference_schema(cfg_path):
     assert a['pred_head.0.center.0.conv.weight'].shape[1] == 128          # C, not 2C (:140)
 
 
+def test_assigner_and_cost_names_are_registered():
+    """HungarianAssigner3D / HeuristicAssigner3D (BBOX_ASSIGNERS) and BBox3DL1Cost / BBoxBEVL1Cost /
+    IoU3DCost (MATCH_COST) resolve, and the reference's train_cfg.pts.assigner builds with its own kwargs."""
+    import projects.mmdet3d_plugin  # noqa: F401
+    from projects.mmdet3d_plugin.registry import BBOX_ASSIGNERS, MATCH_COST
+    for n in ('HungarianAssigner3D', 'HeuristicAssigner3D'):
+        assert BBOX_ASSIGNERS.get(n) is not None, n
+    for n in ('BBox3DL1Cost', 'BBoxBEVL1Cost', 'IoU3DCost'):
+        assert MATCH_COST.get(n) is not None, n
+    a = BBOX_ASSIGNERS.build(dict(type='HungarianAssigner3D', iou_calculator=dict(type='BboxOverlaps3D', coordinate='lidar'),
+                                  cls_cost=dict(type='FocalLossCost', gamma=2, alpha=0.25, weight=0.15),
+                                  reg_cost=dict(type='BBoxBEVL1Cost', weight=0.25), iou_cost=dict(type='IoU3DCost', weight=0.25)))
+    assert (a.cls_cost.weight, a.reg_cost.weight, a.reg_cost.kind, a.iou_cost.weight) == (0.15, 0.25, 0, 0.25)
+    ref_cfg = '/root/reference/projects/configs/nuscenes/Fusion_0075_refactor.py'
+    if os.path.exists(ref_cfg):
+        from projects.mmdet3d_plugin.registry import load_config, build_hot_path
+        _, head = build_hot_path(load_config(ref_cfg))
+        assert type(head.bbox_assigner).__name__ == 'HungarianAssigner3D' and head.train_cfg['pos_weight'] == -1
+
+
 def test_product_modules_refuse_cpu_and_training():
     from deepinteraction_b200 import mmri
     enc = mmri.DeepInteractionEncoder(1, 8, 8, 16).eval()
