@@ -6,7 +6,9 @@
 //   core/bbox/coders/transfusion_bbox_coder.py:39-76      box decode
 // Queries are stored row-major [B*P, C] ("one query = one row"); feature maps are pixel-major (NHWC).
 #include "common.cuh"
+#include "tc_common.cuh"
 #include <math.h>
+
 
 namespace {
 
@@ -504,62 +506,143 @@ rows_finish_c128_kernel(const float* __restrict__ x, int ldx, const float* __res
 // :73-113, FFNs :104-109,754-757, prediction heads :498-581.  fp32 FFMA, sequential accumulation over k.
 // Weights are passed TRANSPOSED ([K, N], so that lanes read consecutive output columns).
 // ------------------------------------------------------------------------------------------------
-constexpr int MLP_R = 4;   // rows per CTA: small, so that 200 query rows already spread over 50 SMs
-__global__ void __launch_bounds__(256)
+constexpr int MLP_R = 4;        // rows per CTA: small, so that 200 query rows already spread over 50 SMs
+constexpr int MLP_NT = 512;     // threads: k-groups of column threads (16 warps hide the shared-memory / FMA latencies)
+constexpr int MLP_NS = 5;       // weight stages in shared memory (160 KB in flight: the copies are latency-bound)
+constexpr int MLP_CHUNK = 8192; // floats per stage (32 KB): KC = 8192 / N consecutive rows of the transposed weight
+
+// Weight streaming: the [K, N] transposed weights are contiguous, so KC rows are one 32 KB block; every thread copies
+// 16-byte pieces of it with cp.async into a 5-stage ring (128 KB in flight per CTA; layer 2's first chunks are under way
+// while layer 1 still computes).  Measured alternatives: dependent batches of __ldg (K / 16 round trips per layer:
+// 25-45 us per launch) and one cp.async.bulk per chunk (the copy engine delivered ~32 GB/s per SM).
+__device__ __forceinline__ void mlp_copy_chunk(float* dst, const float* src, int floats, int tid) {
+  const uint32_t d = tc::smem_u32(dst);
+  for (int i = tid * 4; i < floats; i += MLP_NT * 4)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + i * 4), "l"(src + i) : "memory");
+}
+
+__global__ void __launch_bounds__(MLP_NT)
 rows_mlp_kernel(const float* __restrict__ X0, int ld0, int K0, const float* __restrict__ X1, int ld1, int K1,
                 const float* __restrict__ W1t, const float* __restrict__ b1, int N1, int act1,
                 const float* __restrict__ W2t, const float* __restrict__ b2, int N2, const float* __restrict__ res, int ldres,
                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int act_out,
                 const int* __restrict__ zero_if_neg, float* __restrict__ Y, int ldy, int M) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(128) float sm[];
   const int K = K0 + K1;
-  float* xs = sm;                         // [R][K]
-  float* hs = xs + MLP_R * K;             // [R][N1]
-  float* ys = hs + MLP_R * N1;            // [R][N2] (only with a second layer)
+  float* wbuf = sm;                               // [MLP_NS][MLP_CHUNK]
+  float* xs = wbuf + MLP_NS * MLP_CHUNK;          // [R][K]
+  float* hs = xs + MLP_R * K;                     // [R][N1]
+  float* ys = hs + MLP_R * N1;                    // [R][N2] (only with a second layer)
   const int m0 = blockIdx.x * MLP_R, tid = threadIdx.x;
-  for (int i = tid; i < MLP_R * K; i += 256) {
+  float* red = ys + MLP_R * (W2t ? N2 : 0);       // [groups][R][N] partial sums of the narrow layers (N <= 128)
+  // job list: chunks of layer 1, then chunks of layer 2.  Chunk rows are a multiple of 4 (float4 activations).
+  auto rows_per_chunk = [](int N) { const int kc = MLP_CHUNK / N; return kc >= 4 ? (kc & ~3) : max(1, kc); };
+  const int kc1 = rows_per_chunk(N1), n1 = (K + kc1 - 1) / kc1;
+  const int kc2 = W2t ? rows_per_chunk(N2) : 1, n2 = W2t ? (N1 + kc2 - 1) / kc2 : 0;
+  const int njobs = n1 + n2;
+  auto issue = [&](int j) {                       // all threads; always commits a group (possibly an empty one)
+    if (j < njobs) {
+      float* dst = wbuf + (size_t)(j % MLP_NS) * MLP_CHUNK;
+      if (j < n1) {
+        const int k0 = j * kc1, kc = min(kc1, K - k0);
+        mlp_copy_chunk(dst, W1t + (size_t)k0 * N1, kc * N1, tid);
+      } else {
+        const int k0 = (j - n1) * kc2, kc = min(kc2, N1 - k0);
+        mlp_copy_chunk(dst, W2t + (size_t)k0 * N2, kc * N2, tid);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  for (int j = 0; j < MLP_NS - 1; ++j) issue(j);
+  for (int i = tid; i < MLP_R * K; i += MLP_NT) {
     const int r = i / K, k = i - r * K, m = m0 + r;
     float v = 0.f;
     if (m < M) v = k < K0 ? X0[(size_t)m * ld0 + k] : X1[(size_t)m * ld1 + (k - K0)];
     xs[i] = v;
   }
   __syncthreads();
-  for (int n = tid; n < N1; n += 256) {
-    float acc[MLP_R];
-    const float bb = b1 ? b1[n] : 0.f;
+  // A layer of N columns uses groups of tpg = N / 4 threads, each thread a 4-row x 4-column register tile (float4
+  // weight and activation reads: 8 shared-memory loads per 64 FMAs); the `ng` groups take disjoint k-slices of every
+  // weight chunk and their partial sums are added in group order when the layer ends.
+  float acc[MLP_R][4];
+  for (int j = 0; j < njobs; ++j) {
+    const bool l1 = j < n1;
+    const int N = l1 ? N1 : N2, Kin = l1 ? K : N1;
+    const int kc_full = l1 ? kc1 : kc2, k0 = (l1 ? j : j - n1) * kc_full, kc = min(kc_full, Kin - k0);
+    const float* in = l1 ? xs : hs;
+    const float* bias = l1 ? b1 : b2;
+    const int tpg = N >> 2, ng = min(16, MLP_NT / tpg);
+    const int grp = tid / tpg, col = (tid - grp * tpg) * 4;
+    const bool live = grp < ng;
+    if (k0 == 0) {
+      float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (bias && live && grp == 0) bb = *reinterpret_cast<const float4*>(bias + col);
 #pragma unroll
-    for (int r = 0; r < MLP_R; ++r) acc[r] = bb;
-#pragma unroll 16
-    for (int k = 0; k < K; ++k) {                       // 16 independent weight loads in flight per thread (latency-bound otherwise)
-      const float w = __ldg(W1t + (size_t)k * N1 + n);
-#pragma unroll
-      for (int r = 0; r < MLP_R; ++r) acc[r] = fmaf(xs[r * K + k], w, acc[r]);
+      for (int r = 0; r < MLP_R; ++r) { acc[r][0] = bb.x; acc[r][1] = bb.y; acc[r][2] = bb.z; acc[r][3] = bb.w; }
     }
-#pragma unroll
-    for (int r = 0; r < MLP_R; ++r) hs[r * N1 + n] = di_act(acc[r], act1);
-  }
-  __syncthreads();
-  const float* outs = hs;
-  int N = N1;
-  if (W2t) {
-    for (int n = tid; n < N2; n += 256) {
-      float acc[MLP_R];
-      const float bb = b2 ? b2[n] : 0.f;
-#pragma unroll
-      for (int r = 0; r < MLP_R; ++r) acc[r] = bb;
-#pragma unroll 16
-      for (int k = 0; k < N1; ++k) {
-        const float w = __ldg(W2t + (size_t)k * N2 + n);
-#pragma unroll
-        for (int r = 0; r < MLP_R; ++r) acc[r] = fmaf(hs[r * N1 + k], w, acc[r]);
-      }
-#pragma unroll
-      for (int r = 0; r < MLP_R; ++r) ys[r * N2 + n] = acc[r];
-    }
+    // chunk j has landed for this thread; after the barrier for all threads, and the stage consumed in iteration j - 1
+    // is free for chunk j + NS - 1 (the barrier also publishes hs when layer 2 starts)
+    asm volatile("cp.async.wait_group %0;" ::"n"(MLP_NS - 2) : "memory");
     __syncthreads();
-    outs = ys;
-    N = N2;
+    issue(j + MLP_NS - 1);
+    const float* w = wbuf + (size_t)(j % MLP_NS) * MLP_CHUNK;
+    const int slice = ((kc + 4 * ng - 1) / (4 * ng)) * 4;
+    const int ka = min(kc, grp * slice), kb = min(kc, ka + slice);
+    if (live) {
+      const bool vec = (Kin & 3) == 0 && ((k0 + ka) & 3) == 0;
+      int kk = ka;
+      if (vec) {
+#pragma unroll 2
+        for (; kk + 4 <= kb; kk += 4) {
+          float4 xv[MLP_R], wv[4];
+#pragma unroll
+          for (int r = 0; r < MLP_R; ++r) xv[r] = *reinterpret_cast<const float4*>(in + r * Kin + k0 + kk);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) wv[q] = *reinterpret_cast<const float4*>(w + (kk + q) * N + col);
+#pragma unroll
+          for (int r = 0; r < MLP_R; ++r) {
+            const float xq[4] = {xv[r].x, xv[r].y, xv[r].z, xv[r].w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              acc[r][0] = fmaf(xq[q], wv[q].x, acc[r][0]);
+              acc[r][1] = fmaf(xq[q], wv[q].y, acc[r][1]);
+              acc[r][2] = fmaf(xq[q], wv[q].z, acc[r][2]);
+              acc[r][3] = fmaf(xq[q], wv[q].w, acc[r][3]);
+            }
+          }
+        }
+      }
+      for (; kk < kb; ++kk) {
+        const float4 wv = *reinterpret_cast<const float4*>(w + kk * N + col);
+#pragma unroll
+        for (int r = 0; r < MLP_R; ++r) {
+          const float x = in[r * Kin + k0 + kk];
+          acc[r][0] = fmaf(x, wv.x, acc[r][0]);
+          acc[r][1] = fmaf(x, wv.y, acc[r][1]);
+          acc[r][2] = fmaf(x, wv.z, acc[r][2]);
+          acc[r][3] = fmaf(x, wv.w, acc[r][3]);
+        }
+      }
+    }
+    if (k0 + kc == Kin) {                            // layer finished: group sum, activation, results to shared memory
+      float* dstbuf = l1 ? hs : ys;
+      if (live) {
+#pragma unroll
+        for (int r = 0; r < MLP_R; ++r)
+          *reinterpret_cast<float4*>(red + (grp * MLP_R + r) * N + col) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+      }
+      __syncthreads();
+      for (int i = tid; i < MLP_R * N; i += MLP_NT) {
+        const int r = i / N, n = i - r * N;
+        float v = red[r * N + n];
+        for (int g = 1; g < ng; ++g) v += red[(g * MLP_R + r) * N + n];
+        dstbuf[r * N + n] = l1 ? di_act(v, act1) : v;
+      }
+    }
   }
+  __syncthreads();                                   // results of the last layer visible
+  const float* outs = W2t ? ys : hs;
+  const int N = W2t ? N2 : N1;
   // finish: warp r owns row r (N <= 512 -> up to 16 values per lane)
   const int r = tid >> 5, lane = tid & 31, m = m0 + r;
   if (r >= MLP_R || m >= M) return;
@@ -1233,7 +1316,7 @@ int di_rows_finish_f32(const float* part, int nsplit, long long split_stride, in
 
 // Query-row MLP (see rows_mlp_kernel): Y[M, N] = act_out(LN(act1([X0|X1] W1t + b1) [W2t + b2] + res)).
 // W1t [K0+K1, N1] and W2t [N1, N2] are TRANSPOSED weights (row = input channel); W2t / b1 / b2 / res / gamma may be NULL.
-// K0 + K1 <= 1024, N1, N2 <= 512.
+// K0 + K1 <= 1024, N1, N2 <= 512, K0 + K1 + N1 + N2 <= 1800.
 int di_rows_mlp_f32(const float* X0, int ld0, int K0, const float* X1, int ld1, int K1, const float* W1t, const float* b1,
                     int N1, int act1, const float* W2t, const float* b2, int N2, const float* res, int ldres,
                     const float* gamma, const float* beta, float eps, int act_out, const int* zero_if_neg, float* Y, int ldy,
@@ -1241,13 +1324,16 @@ int di_rows_mlp_f32(const float* X0, int ld0, int K0, const float* X1, int ld1, 
   DI_CHECK_ARG(X0 && W1t && Y && M > 0 && K0 > 0 && K1 >= 0 && (K1 == 0 || X1) && N1 > 0, "di_rows_mlp_f32: bad argument");
   DI_CHECK_ARG(K0 + K1 <= 1024 && N1 <= 512 && (!W2t || (N2 > 0 && N2 <= 512)), "di_rows_mlp_f32: K <= 1024, N <= 512");
   DI_CHECK_ARG((gamma == nullptr) == (beta == nullptr), "di_rows_mlp_f32: gamma and beta go together");
-  const size_t smem = sizeof(float) * MLP_R * (size_t)(K0 + K1 + N1 + (W2t ? N2 : 0));
+  DI_CHECK_ARG(N1 % 4 == 0 && (!W2t || N2 % 4 == 0) && ((uintptr_t)W1t & 15) == 0 && ((uintptr_t)W2t & 15) == 0,
+               "di_rows_mlp_f32: N1, N2 must be multiples of 4 and the weights 16-byte aligned (bulk copies)");
+  const size_t smem = sizeof(float) * ((size_t)MLP_NS * MLP_CHUNK + MLP_R * (size_t)(K0 + K1 + N1 + (W2t ? N2 : 0) + 2048));
+  DI_CHECK_ARG(smem <= 226 * 1024, "di_rows_mlp_f32: K + N1 + N2 too large for shared memory (%d)", K0 + K1 + N1 + N2);
   static bool once = false;
   if (!once) {
-    cudaFuncSetAttribute(rows_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(rows_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     once = true;
   }
-  rows_mlp_kernel<<<di_cdiv(M, MLP_R), 256, smem, stream>>>(X0, ld0, K0, X1, ld1, K1, W1t, b1, N1, act1, W2t, b2, N2, res,
+  rows_mlp_kernel<<<di_cdiv(M, MLP_R), MLP_NT, smem, stream>>>(X0, ld0, K0, X1, ld1, K1, W1t, b1, N1, act1, W2t, b2, N2, res,
                                                            ldres, gamma, beta, eps, act_out, zero_if_neg, Y, ldy, M);
   DI_CHECK_LAUNCH("di_rows_mlp_f32");
   return DI_OK;

@@ -488,7 +488,8 @@ ROWS_MLP = [os.environ.get('DI_B200_ROWS_MLP', '1') != '0']   # query-row dense 
 
 
 def can_rows_mlp(M, K, N1, N2=0):
-    return bool(ROWS_MLP[0] and M <= 2048 and K <= 1024 and N1 <= 512 and N2 <= 512)
+    return bool(ROWS_MLP[0] and M <= 2048 and K <= 1024 and N1 <= 512 and N2 <= 512 and N1 % 4 == 0 and N2 % 4 == 0 and
+                K + N1 + N2 <= 1800)
 
 
 def rows_mlp(srcs, W1, b1=None, act1=ACT_NONE, W2=None, b2=None, res=None, gamma=None, beta=None, act_out=ACT_NONE,

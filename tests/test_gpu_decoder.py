@@ -109,7 +109,7 @@ def test_cross_attention_matches_dense_softmax():
 
 
 @pytest.mark.parametrize('M,Ks,N1,N2', [(200, (128,), 384, 0), (200, (128, 128), 384, 20), (37, (2,), 128, 128),
-                                        (600, (128,), 512, 128), (5, (256,), 64, 0)])
+                                        (600, (128,), 512, 128), (5, (256,), 64, 0), (33, (128,), 128, 0), (200, (128,), 36, 12)])
 def test_rows_mlp_matches_float64(M, Ks, N1, N2):
     """Query-row MLP kernel: two chained dense layers + residual + LayerNorm + activation + row masking in one launch."""
     from deepinteraction_b200 import ops, fold
