@@ -40,6 +40,7 @@ SIGNATURES = {
     'di_lcab_window_tc_set_debug': [_i],
     'di_lcab_window_tc_debug_read': [ctypes.POINTER(ctypes.c_longlong)],
     'di_lcab_proj_f32': [_p, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p],
+    'di_lcab_forward_f32': [_p, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
     'di_lcab_proj_set_sm_limit': [_i],
     'di_set_window_ffma': [_i],
     'di_locatt_cc2k_f32': [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p],

@@ -454,4 +454,24 @@ int di_lcab_proj_f32(const float* x_t, int ld_t, const float* x_s, int ld_s, con
   return DI_OK;
 }
 
+// LocalContextAttentionBlock.forward (models/utils/encoder_utils.py:119-135) for C = 128 as ONE call: the projection chain
+// (di_lcab_proj_f32) followed by the tcgen05 window kernel (di_lcab_window_tc_f32) on `stream`.  x_t / x_s [N*H*W, 128]
+// fp32 pixel-major rows (x_s == x_t: self attention), folded weights as for di_lcab_proj_f32, qkv: workspace of
+// 3 * N*H*W * 128 32-bit words (16-byte aligned), out [N*H*W, ldo] fp32.  This is the entry SURVEY.md 8(b) calls
+// `di_lcab_forward`: module-boundary traffic = x_t (+ x_s) read once, out written once; q / k / v pass through `qkv` (L2).
+int di_lcab_window_tc_f32(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, float* out, int ldo, int N,
+                          int H, int W, int C, cudaStream_t stream);
+int di_lcab_forward_f32(const float* x_t, int ld_t, const float* x_s, int ld_s, const void* W1_hi, const void* W1_mid,
+                        const float* b1, const void* W2_hi, const void* W2_mid, const float* b2, float* qkv, float* out, int ldo,
+                        int N, int H, int W, cudaStream_t stream) {
+  DI_CHECK_ARG(qkv && out && N > 0 && H > 0 && W > 0, "di_lcab_forward_f32: bad argument");
+  const size_t M = (size_t)N * H * W;
+  float* q = qkv;
+  float* k = qkv + M * 128;
+  float* v = qkv + 2 * M * 128;
+  const int rc = di_lcab_proj_f32(x_t, ld_t, x_s, ld_s, W1_hi, W1_mid, b1, W2_hi, W2_mid, b2, q, k, v, (int)M, stream);
+  if (rc != DI_OK) return rc;
+  return di_lcab_window_tc_f32(q, 128, k, 128, v, 128, out, ldo, N, H, W, 128, stream);
+}
+
 }  // extern "C"

@@ -118,9 +118,8 @@ def lcab_forward(pk, target, source, N, H, W):
     pre = ops.can_presplit(N * H * W, C, pk['ks'])
     tc = ops.can_window_tc(N * H * W, C, pk['ks'])       # tcgen05 window kernel: planar operands (split kind 3)
     if tc and ops.LCAB_PROJ[0] and target.is_contiguous() and source.is_contiguous():
-        # all five projections in one launch, q1 / k1 stay on chip (lcab_proj.cu)
-        q, k, v = ops.lcab_proj(target, source, pk['w_self'], pk['b_self'], pk['w_2'], pk['b_2'])
-        return ops.lcab_window_tc(q, k, v, N, H, W, C)
+        # one C-ABI call: all five projections in one launch (q1 / k1 stay on chip, lcab_proj.cu), then the window kernel
+        return ops.lcab_forward_tc(target, source, pk['w_self'], pk['b_self'], pk['w_2'], pk['b_2'], N, H, W)
     if target is source:
         if pre:
             t = ops.linear_split([source], pk['w_self'], pk['b_self'], ops.ACT_RELU, 2 * C, 3 if tc else 2)    # q1 | k1 | v(split)

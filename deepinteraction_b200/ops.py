@@ -20,7 +20,8 @@ TC_CONV = [os.environ.get('DI_B200_TC_CONV', '1') != '0']
 TC_MIN_M = [int(os.environ.get('DI_B200_TC_MIN_M', '128'))]   # fewer rows: fp32 FFMA kernels of gemm.cu (measured: the tensor-core kernel is faster from 128 rows up)
 TC_BF16 = [os.environ.get('DI_B200_TC_BF16', '1') != '0']   # bf16-split operands where K % 64 == 0 (else 3xTF32)
 _TAG = ['']        # optional shape tag for the next profiled call (bench.py --shapes table)
-PROFILE = [None]  # bench.py sets PROFILE[0] = [] to record (name, start_event, end_event, bytes, flops, module) per call
+PROFILE = [None]   # bench.py sets PROFILE[0] = [] to record (name, start_event, end_event, bytes, flops, module) per call
+PROFILE_FLUSH = [None]     # optional > L2 scratch tensor zeroed before every profiled launch (bench.py)
 _MODULE = [None]  # (name, module-boundary bytes, flops) of the nn.Module whose kernels are being issued (bench.py roofline table)
 
 
@@ -57,13 +58,18 @@ def _f32(t, name='tensor'):
     return t
 
 
-def _call(name, *args, nbytes=0, flops=0):
-    """nbytes / flops: ALGORITHMIC traffic and work of the call (inputs read once, outputs written once)."""
-    LAUNCHES[0] += 1
+def _call(name, *args, nbytes=0, flops=0, launches=1):
+    """nbytes / flops: ALGORITHMIC traffic and work of the call (inputs read once, outputs written once); launches: kernels
+    the entry point issues (for bench.py's launch count)."""
+    LAUNCHES[0] += launches
     prof = PROFILE[0]
     if prof is None:
         return _lib.check(getattr(_lib.lib(), name)(*args), name)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if PROFILE_FLUSH[0] is not None:
+        # keeps the GPU busy (and evicts L2) while the host enqueues e0 / kernel / e1: the interval then is the kernel's
+        # own duration from a cold cache, like an ncu launch list -- not launch latency on an idle stream
+        PROFILE_FLUSH[0].zero_()
     e0.record()
     rc = _lib.check(getattr(_lib.lib(), name)(*args), name)
     e1.record()
@@ -203,6 +209,20 @@ def lcab_proj(x_t, x_s, w1, b1, w2, b2):
           _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), M, _stream(),
           nbytes=4 * M * 128 * (4 if x_t is x_s else 5), flops=2 * 5 * M * 128 * 128)
     return out[0], out[1], out[2]
+
+
+def lcab_forward_tc(x_t, x_s, w1, b1, w2, b2, N, H, W):
+    """LocalContextAttentionBlock for C = 128 in one C-ABI call (projection chain + tcgen05 window kernel).  The byte count
+    is the MODULE-boundary one of SURVEY.md 8(d): each distinct input map read once, the output written once."""
+    M = x_t.shape[0]
+    assert M == N * H * W and x_t.shape[1] == 128 and x_s.shape == x_t.shape
+    qkv = torch.empty(3, M, 128, device=x_t.device, dtype=torch.float32)
+    out = torch.empty(M, 128, device=x_t.device, dtype=torch.float32)
+    (pt, lt), (ps, ls) = _rows(x_t), _rows(x_s)
+    _call('di_lcab_forward_f32', pt, lt, ps, ls, _ptr(w1.bh), _ptr(w1.bm), _ptr(b1), _ptr(w2.bh), _ptr(w2.bm), _ptr(b2),
+          _ptr(qkv), _ptr(out), 128, N, H, W, _stream(),
+          nbytes=4 * M * 128 * (2 if x_t is x_s else 3), flops=2 * 5 * M * 128 * 128 + 2 * 2 * 81 * M * 128, launches=2)
+    return out
 
 
 def lcab_window_pre(q, k, v, N, H, W, C, out=None):
@@ -464,7 +484,7 @@ def cross_attn(q, kv, B, P, HW, heads, nsplit=32):
     part = torch.empty(B * heads * P * nsplit * 18, device=q.device, dtype=torch.float32)
     out = torch.empty(B * P, C, device=q.device, dtype=torch.float32)
     _call('di_cross_attn_f32', _ptr(q), _ptr(kv), _ptr(part), _ptr(out), B, P, HW, C, heads, nsplit, _stream(),
-          nbytes=4 * (kv.numel() + 2 * q.numel()), flops=4 * B * P * HW * C)
+          nbytes=4 * (kv.numel() + 2 * q.numel()), flops=4 * B * P * HW * C, launches=2)
     return out
 
 
@@ -507,7 +527,9 @@ def rows_mlp(srcs, W1, b1=None, act1=ACT_NONE, W2=None, b2=None, res=None, gamma
     pr, ldr = (None, 0) if res is None else _rows(res)
     _call('di_rows_mlp_f32', p0, l0, srcs[0].shape[1], p1, l1, K1, _ptr(W1.wt), _ptr(b1), N1, act1,
           _ptr(W2.wt) if W2 is not None else None, _ptr(b2), N2, pr, ldr, _ptr(gamma), _ptr(beta), float(eps), act_out,
-          _ptr(zero_if_neg), _ptr(out), out.shape[1], M, _stream())
+          _ptr(zero_if_neg), _ptr(out), out.shape[1], M, _stream(),
+          nbytes=4 * (W1.shape[0] * W1.shape[1] + (N2 * N1 if N2 else 0) + M * (W1.shape[1] + (N2 or N1))),
+          flops=2 * M * (W1.shape[0] * W1.shape[1] + N2 * N1))
     return out
 
 

@@ -130,6 +130,12 @@ int di_lcab_window_tc_debug_read(long long* host_buf); /* ... 6 x 256 stamps (to
 int di_lcab_proj_f32(const float* x_t, int ld_t, const float* x_s, int ld_s, const void* W1_hi, const void* W1_mid,
                      const float* b1, const void* W2_hi, const void* W2_mid, const float* b2, float* q, float* k, float* v,
                      int M, cudaStream_t stream);
+
+/* LocalContextAttentionBlock.forward for C = 128 as one call = di_lcab_proj_f32 + di_lcab_window_tc_f32 on `stream`
+ * (models/utils/encoder_utils.py:119-135; SURVEY.md 8(b) `di_lcab_forward`).  qkv: workspace of 3 * N*H*W * 128 words. */
+int di_lcab_forward_f32(const float* x_t, int ld_t, const float* x_s, int ld_s, const void* W1_hi, const void* W1_mid,
+                        const float* b1, const void* W2_hi, const void* W2_mid, const float* b2, float* qkv, float* out, int ldo,
+                        int N, int H, int W, cudaStream_t stream);
 int di_lcab_proj_set_sm_limit(int n); /* persistent grid of the kernel above uses at most n CTAs (0 = all) */
 
 /* test/diagnostic hook: 1 = always use the FFMA window kernel, 0 = tensor-core (mma.sync 3xTF32) kernel when
