@@ -662,3 +662,59 @@ def circle_nms(boxes, scores, labels, keep, class_mask, thresh, post_max=83):
     _call('di_circle_nms_f32', _ptr(boxes), nb, _ptr(scores), _ptr(labels), _ptr(k8), B, P, int(class_mask), float(thresh),
           int(post_max), _stream())
     return k8.bool()
+
+
+# ---- backward of the window attention (csrc/lcab_bwd.cu; composition in backward.py) ---------------------------------
+def win_dot(a, b, N, H, W, ks):
+    P, C = a.shape
+    out = torch.empty(P, ks * ks, device=a.device, dtype=torch.float32)
+    (pa, la), (pb, lb) = _rows(a), _rows(b)
+    _call('di_win_dot_f32', pa, la, pb, lb, _ptr(out), N, H, W, C, ks, _stream(), nbytes=4 * (2 * P * C + P * ks * ks),
+          flops=2 * P * C * ks * ks)
+    return out
+
+
+def _win_apply(name, w, b, N, H, W, ks):
+    P, C = b.shape
+    out = torch.empty(P, C, device=b.device, dtype=torch.float32)
+    pb, lb = _rows(b)
+    _call(name, _ptr(w), pb, lb, _ptr(out), C, N, H, W, C, ks, _stream(), nbytes=4 * (2 * P * C + P * ks * ks),
+          flops=2 * P * C * ks * ks)
+    return out
+
+
+def win_gather(w, b, N, H, W, ks):
+    return _win_apply('di_win_gather_f32', w, b, N, H, W, ks)
+
+
+def win_scatter(w, b, N, H, W, ks):
+    return _win_apply('di_win_scatter_f32', w, b, N, H, W, ks)
+
+
+def win_softmax(S, scale):
+    A = torch.empty_like(S)
+    _call('di_win_softmax_f32', _ptr(S), _ptr(A), S.shape[0], S.shape[1], float(scale), _stream(), nbytes=8 * S.numel())
+    return A
+
+
+def win_softmax_bwd(A, dA, scale):
+    dS = torch.empty_like(A)
+    _call('di_win_softmax_bwd_f32', _ptr(A), _ptr(dA), _ptr(dS), A.shape[0], A.shape[1], float(scale), _stream(),
+          nbytes=12 * A.numel())
+    return dS
+
+
+def relu_bwd(dy, y):
+    assert dy.is_contiguous() and y.is_contiguous() and dy.shape == y.shape
+    dx = torch.empty_like(dy)
+    _call('di_relu_bwd_f32', _ptr(dy), _ptr(y), _ptr(dx), dy.numel(), _stream(), nbytes=12 * dy.numel())
+    return dx
+
+
+def col_sum(x):
+    M, C = x.shape
+    p, ld = _rows(x)
+    work = torch.empty(256 * C, device=x.device, dtype=torch.float32)
+    out = torch.empty(C, device=x.device, dtype=torch.float32)
+    _call('di_col_sum_f32', p, ld, M, C, _ptr(work), _ptr(out), _stream(), nbytes=4 * M * C, launches=2)
+    return out

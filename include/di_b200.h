@@ -341,6 +341,24 @@ int di_mmpi_losses_f32(const float* dense_logit, const float* heat_target, long 
                        const float* code_w, const float* focal2, const float* gfl2, const float* weights3, double* work,
                        float* out, cudaStream_t stream);
 
+/* ---- backward of the window attention (SURVEY.md 8(b) `di_lcab_backward`; host composition: deepinteraction_b200/backward.py)
+ * Pixel-major maps [N*H*W, ld]; tap j = (dy + r) * ks + (dx + r) (locatt_ops/similar.cu:15-17).
+ * di_win_dot_f32     out[p, j] = a[p] . b[nbr(p, j)]          similar_forward / weighting_backward_weight (kernels.cuh:4-41, weighting.cu:83-121)
+ * di_win_gather_f32  out[p]  = sum_j w[p, j] b[nbr(p, j)]       weighting_forward / similar_backward(is_ori)   (kernels.cuh:44-80)
+ * di_win_scatter_f32 out[p'] = sum_{nbr(p,j)=p'} w[p, j] b[p]   similar_backward(!is_ori) / weighting_backward_ori (kernels.cuh:82-119) */
+int di_win_dot_f32(const float* a, int lda, const float* b, int ldb, float* out, int N, int H, int W, int C, int ks,
+                   cudaStream_t stream);
+int di_win_gather_f32(const float* w, const float* b, int ldb, float* out, int ldo, int N, int H, int W, int C, int ks,
+                      cudaStream_t stream);
+int di_win_scatter_f32(const float* w, const float* b, int ldb, float* out, int ldo, int N, int H, int W, int C, int ks,
+                       cudaStream_t stream);
+/* softmax over the ks*ks taps (encoder_utils.py:133) and its backward */
+int di_win_softmax_f32(const float* S, float* A, long long P, int KK, float scale, cudaStream_t stream);
+int di_win_softmax_bwd_f32(const float* A, const float* dA, float* dS, long long P, int KK, float scale, cudaStream_t stream);
+/* ReLU backward from the saved output; column sums of a [M, C] matrix (bias gradients; work: float [256 * C]) */
+int di_relu_bwd_f32(const float* dy, const float* y, float* dx, long long n, cudaStream_t stream);
+int di_col_sum_f32(const float* x, int ld, long long M, int C, float* work, float* out, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,107 @@
+"""Backward of LocalContextAttentionBlock on the GPU (deepinteraction_b200/backward.py + csrc/lcab_bwd.cu):
+window kernels against the reference's own CUDA extension (oracle/_ref) and the CPU oracle's autograd, the block's
+input / parameter gradients against autograd through oracle.mmri.LocalContextAttentionBlock (BatchNorm in eval mode)."""
+import os
+import sys
+
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def dev():
+    return torch.device('cuda:0')
+
+
+def rows(t):           # (N, C, H, W) -> [N*H*W, C]
+    return t.permute(0, 2, 3, 1).reshape(-1, t.shape[1]).contiguous()
+
+
+@pytest.mark.parametrize('N,C,H,W,ks', [(2, 128, 11, 14, 9), (1, 32, 7, 9, 9), (1, 256, 6, 5, 5)])
+def test_window_backward_kernels_match_reference_extension(N, C, H, W, ks):
+    """di_win_dot / gather / scatter (pixel-major) == the reference localattention functions (NCHW) they stand for."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import build_ref
+    ref = build_ref.load()
+    if ref is None:
+        pytest.skip('oracle/_ref/localattention.so not built')
+    from deepinteraction_b200 import ops
+    g = torch.Generator().manual_seed(7 + C)
+    a = torch.randn(N, C, H, W, generator=g).to(dev())
+    b = torch.randn(N, C, H, W, generator=g).to(dev())
+    w = torch.randn(N, H, W, ks * ks, generator=g).to(dev())
+    ar, br, wr = rows(a), rows(b), w.reshape(-1, ks * ks).contiguous()
+    back = lambda r: r.view(N, H, W, C).permute(0, 3, 1, 2)
+    tol = 3e-6
+    assert rel_err(ops.win_dot(ar, br, N, H, W, ks).view(N, H, W, -1), ref.similar_forward(a, b, ks, ks)) < tol
+    assert rel_err(back(ops.win_gather(wr, br, N, H, W, ks)), ref.weighting_forward(b, w, ks, ks)) < tol
+    assert rel_err(back(ops.win_gather(wr, br, N, H, W, ks)), ref.similar_backward(b, w, ks, ks, True)) < tol
+    assert rel_err(back(ops.win_scatter(wr, ar, N, H, W, ks)), ref.similar_backward(a, w, ks, ks, False)) < tol
+    assert rel_err(back(ops.win_scatter(wr, ar, N, H, W, ks)), ref.weighting_backward_ori(w, a, ks, ks)) < tol
+    assert rel_err(ops.win_dot(ar, br, N, H, W, ks).view(N, H, W, -1), ref.weighting_backward_weight(b, a, ks, ks)) < tol
+
+
+def test_softmax_relu_colsum_kernels():
+    from deepinteraction_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    S = torch.randn(500, 81, generator=g) * 3
+    dA = torch.randn(500, 81, generator=g)
+    Sg = S.clone().requires_grad_(True)
+    A_ref = torch.softmax(Sg * 0.37, -1)
+    (A_ref * dA).sum().backward()
+    A = ops.win_softmax(S.to(dev()), 0.37)
+    assert rel_err(A.cpu(), A_ref.detach()) < 2e-6
+    assert rel_err(ops.win_softmax_bwd(A, dA.to(dev()), 0.37).cpu(), Sg.grad) < 5e-6
+    y, dy = torch.randn(1001, 36, generator=g), torch.randn(1001, 36, generator=g)
+    assert torch.equal(ops.relu_bwd(dy.to(dev()), y.to(dev())).cpu(), dy * (y > 0))
+    x = torch.randn(70001, 128, generator=g)
+    assert rel_err(ops.col_sum(x.to(dev())).cpu(), x.double().sum(0).float()) < 2e-6
+
+
+@pytest.mark.parametrize('self_attn', [True, False])
+def test_lcab_backward_matches_oracle_autograd(self_attn):
+    """d target / d source / d folded weights and biases of the five Conv+BN layers vs torch autograd through the CPU oracle
+    block in eval mode; the folded-weight gradient maps to the convolution weight by the BN scale."""
+    import oracle.mmri as om
+    from deepinteraction_b200 import mmri, synth, backward
+    torch.manual_seed(31)
+    C, N, H, W = 128, 2, 12, 20
+    blk = om.LocalContextAttentionBlock(C, C, 9).eval()
+    synth.randomize_norm_stats(blk, 31)
+    g = torch.Generator().manual_seed(31)
+    xt = torch.randn(N, C, H, W, generator=g).requires_grad_(True)
+    xs = xt if self_attn else torch.randn(N, C, H, W, generator=g).requires_grad_(True)
+    G = torch.randn(N, C, H, W, generator=g)
+    with torch.enable_grad():
+        out = blk(xt, xs)
+        (out * G).sum().backward()
+    pk = mmri._pack_lcab(blk, dev())
+    t = rows(xt.detach()).to(dev())
+    s = t if self_attn else rows(xs.detach()).to(dev())
+    r = backward.lcab_backward(pk, t, s, N, H, W, rows(G).to(dev()))
+    tol = 2e-4          # bf16-split tensor-core products (1e-5 each) through a five-layer chain
+    assert rel_err(r['d_target'].cpu(), rows(xt.grad)) < tol
+    if self_attn:
+        assert r['d_source'] is None
+    else:
+        assert rel_err(r['d_source'].cpu(), rows(xs.grad)) < tol
+    layers = dict(q1=blk.query_project[0], q2=blk.query_project[1], k1=blk.key_project[0], k2=blk.key_project[1],
+                  v=blk.value_project)
+    for name, m in layers.items():
+        dW, db = r[name]
+        scale = (m.bn.weight / torch.sqrt(m.bn.running_var + m.bn.eps)).detach()
+        want_w = m.conv.weight.grad[:, :, 0, 0]                         # = dW_folded * scale (rows)
+        assert rel_err(dW.cpu() * scale[:, None], want_w) < tol, name
+        assert rel_err(db.cpu(), m.bn.bias.grad) < tol, name
+    # autograd wrapper: same input gradients through torch.autograd
+    tt = t.clone().requires_grad_(True)
+    ss = tt if self_attn else s.clone().requires_grad_(True)
+    with torch.enable_grad():
+        o = backward.LCABFunction.apply(pk, tt, ss, N, H, W)
+        assert rel_err(o.detach().cpu(), rows(out.detach())) < 2e-4
+        (o * rows(G).to(dev())).sum().backward()
+    assert rel_err(tt.grad.cpu(), rows(xt.grad)) < tol
