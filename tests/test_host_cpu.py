@@ -251,6 +251,55 @@ def test_two_rank_gloo_sharding_is_bitwise_equal_to_single_rank():
     assert ret[0][1] == 11.0 and ret[1][1] == 11.0
 
 
+def _grad_worker(rank, world, port, ret):
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        import oracle.mmri as om
+        from deepinteraction_b200.shard import GradBuckets, frame_slice
+        torch.manual_seed(5)
+        m = om.LocalContextAttentionBlock(16, 16, 9).eval()
+        g = torch.Generator().manual_seed(6)
+        x = torch.randn(4, 16, 9, 11, generator=g)
+        tgt = torch.randn(4, 16, 9, 11, generator=g)
+        # data-parallel step: every rank takes its frames, local sum-of-squares loss, bucketed all-reduce of the gradients
+        sl = frame_slice(4, world, rank)
+        with torch.enable_grad():
+            ((m(x[sl], x[sl]) - tgt[sl]) ** 2).sum().backward()
+        buckets = GradBuckets(bucket_bytes=2048)               # small buckets: several launches during the "backward"
+        grads = [p.grad for p in m.parameters() if p.grad is not None]
+        for gr in reversed(grads):                              # the order a backward pass produces them
+            buckets.add(gr)
+        buckets.finish()
+        # single-process reference over all frames (averaged over ranks, as DDP does)
+        ref = om.LocalContextAttentionBlock(16, 16, 9).eval()
+        ref.load_state_dict(m.state_dict())
+        with torch.enable_grad():
+            ((ref(x, x) - tgt) ** 2).sum().backward()
+        want = [p.grad / world for p in ref.parameters() if p.grad is not None]
+        err = max(float((a - b).abs().max() / b.abs().max().clamp_min(1e-12)) for a, b in zip(grads, want))
+        ret[rank] = (err, buckets.launched, [float(gr.sum()) for gr in grads])
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_bucketed_gradient_allreduce():
+    """the training path's one collective -- bucketed gradient all-reduce -- on 2 gloo ranks: averaged
+    gradients equal the single-process gradients of the whole batch / world, identical on both ranks, several buckets."""
+    import torch.multiprocessing as mp
+    import socket
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    ret = mp.Manager().dict()
+    mp.spawn(_grad_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert ret[0][0] < 1e-5 and ret[1][0] < 1e-5, (ret[0][0], ret[1][0])
+    assert ret[0][1] > 1 and ret[0][2] == ret[1][2]
+
+
 def test_presplit_operand_format_roundtrip():
     """fold.split_rows = host model of the window kernel's pre-split operand format (gemm_tc.cu split_block)."""
     from deepinteraction_b200 import fold
