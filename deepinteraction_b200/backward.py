@@ -88,6 +88,39 @@ def lcab_backward(pk, target, source, N, H, W, grad_out):
     return dict(d_target=d_t, d_source=d_s, **g)
 
 
+def i2p_backward(i2p_pack, pts_nhwc, img_nhwc, pts_metas, proj, V, in_hw, grad_out):
+    """Backward of the MMRI_I2P block as the product evaluates it (mmri.DeepInteractionEncoder.i2p; reference
+    encoder_utils.py:216-320): rows = pts[coors]; qk = M1 rows + c1; s = attend(qk, image samples); o = M2 s + c2;
+    out[coors] = o where a pillar saw >= 1 sample.  i2p_pack = (M1, c1, M2, c2) folded from nn.MultiheadAttention
+    (fold.i2p_fold); proj: [B, V, 12] device camera rows (mmri.Geometry.proj).  grad_out [B, Y, X, C].
+    -> dict(d_pts [B,Y,X,C], d_img [B*V,h,w,C], dM1, dc1, dM2, dc2); fold.i2p_unfold_grads maps the last four to the
+    attention module's own parameters."""
+    M1, c1, M2, c2 = i2p_pack
+    coors = pts_metas['pillar_coors']
+    pillars, npts = pts_metas['pillars'], pts_metas['pillars_num_points']
+    d_pts = torch.zeros_like(pts_nhwc)
+    d_img = torch.zeros_like(img_nhwc)
+    if coors.shape[0] == 0:
+        z = lambda t: torch.zeros_like(t.w if hasattr(t, 'w') else t)
+        return dict(d_pts=d_pts, d_img=d_img, dM1=z(M1), dc1=z(c1), dM2=z(M2), dc2=z(c2))
+    dev = pts_nhwc.device
+    T_ = lambda Wt: fold.Weight(Wt.w.detach().cpu().double().t().contiguous(), dev)
+    # forward intermediates
+    rows = ops.gather_rows(pts_nhwc, coors)
+    qk = ops.linear([rows], M1, c1)
+    s, cnt = ops.i2p_attend(qk, pillars, npts, coors, proj, img_nhwc, V, in_hw)
+    # out = scatter(M2 s + c2) at pillars with cnt > 0
+    do = ops.gather_rows_masked(grad_out.contiguous(), cnt, coors)
+    dM2, dc2 = _wgrad(do, s), ops.col_sum(do)
+    ds = ops.linear([do], T_(M2))
+    dqk = ops.i2p_attend_bwd(qk, ds, pillars, npts, coors, proj, img_nhwc, d_img, V, in_hw)
+    dM1, dc1 = _wgrad(dqk, rows), ops.col_sum(dqk)
+    drows = ops.linear([dqk], T_(M1))
+    ones = torch.ones(coors.shape[0], device=dev, dtype=torch.int32)
+    ops.scatter_rows(drows, ones, coors, d_pts)             # one pillar per BEV cell: a plain store
+    return dict(d_pts=d_pts, d_img=d_img, dM1=dM1, dc1=dc1, dM2=dM2, dc2=dc2)
+
+
 class LCABFunction(torch.autograd.Function):
     """autograd wrapper: out = LCAB(target, source) with the inference kernels, input gradients through lcab_backward.
     (Parameter gradients are returned by lcab_backward for the caller's optimiser on the folded weights.)"""

@@ -148,6 +148,180 @@ i2p_attend_kernel(const float* __restrict__ qk, const float* __restrict__ pillar
   if (lane == 0) cnt_out[p] = count;
 }
 
+// ------------------------------------------------------------------------------------------------
+// I2P backward (SURVEY.md 8(b) `di_i2p_backward`): gradient of s[p] = sum_j softmax_j(qk[p] . k_j) k_j, k_j = bilinear
+// sample of the image map at the projection of point j (encoder_utils.py:281-311; forward: i2p_attend_kernel).
+// One warp per pillar; pass A recomputes the logits l_j and t_j = ds . k_j, then a = softmax(l), D = sum a t,
+// dl_j = a_j (t_j - D); pass B re-samples k_j and emits
+//     dqk[p]  = sum_j dl_j k_j
+//     dk_j    = a_j ds[p] + dl_j qk[p]   -> scattered into d_img with the bilinear weights (atomicAdd; the sums over
+//                                           pillars are order-dependent in the last bit, as in torch's grid_sample backward)
+// ------------------------------------------------------------------------------------------------
+template <int NJ>
+__device__ __forceinline__ void bilinear_scatter(float* __restrict__ dmap, int H, int W, int C, float ix, float iy, int lane,
+                                                 const float4 (&g)[NJ]) {
+  float fx = floorf(ix), fy = floorf(iy);
+  int x0 = (int)fx, y0 = (int)fy;
+  float wx1 = ix - fx, wx0 = (fx + 1.f) - ix;
+  float wy1 = iy - fy, wy0 = (fy + 1.f) - iy;
+  float wgt[4] = {wx0 * wy0, wx1 * wy0, wx0 * wy1, wx1 * wy1};
+  if (!(ix > -2.f && ix < (float)W + 1.f && iy > -2.f && iy < (float)H + 1.f)) return;
+#pragma unroll
+  for (int cnr = 0; cnr < 4; ++cnr) {
+    int xx = x0 + (cnr & 1), yy = y0 + (cnr >> 1);
+    if (xx < 0 || xx >= W || yy < 0 || yy >= H) continue;
+    float* row = dmap + ((size_t)yy * W + xx) * C;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      int c = 4 * lane + 128 * j;
+      if (c < C) {
+        atomicAdd(row + c, g[j].x * wgt[cnr]);
+        atomicAdd(row + c + 1, g[j].y * wgt[cnr]);
+        atomicAdd(row + c + 2, g[j].z * wgt[cnr]);
+        atomicAdd(row + c + 3, g[j].w * wgt[cnr]);
+      }
+    }
+  }
+}
+
+template <int NJ>
+__global__ void __launch_bounds__(256)
+i2p_attend_bwd_kernel(const float* __restrict__ qk, const float* __restrict__ ds, const float* __restrict__ pillars,
+                      const int* __restrict__ npts, const int* __restrict__ coors, const float* __restrict__ proj,
+                      const float* __restrict__ img, float* __restrict__ d_img, float* __restrict__ dqk, int P, int T, int pdim,
+                      int V, int h, int w, int C, float H_in, float W_in, const int* __restrict__ n_dev) {
+  const int lane = threadIdx.x & 31;
+  const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n_dev) P = min(P, __ldg(n_dev));
+  if (p >= P) return;
+  const int b = coors[p * 4];
+  const int np = min(npts[p], T);
+  const int S = T * V;
+  constexpr int NS = 8;
+  float sx[NS], sy[NS], lg[NS], tv[NS];
+  bool ok[NS];
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    int i = s * 32 + lane;
+    ok[s] = false;
+    sx[s] = sy[s] = 0.f;
+    lg[s] = -INFINITY;
+    tv[s] = 0.f;
+    if (i < S) {
+      int t = i / V, v = i - t * V;
+      if (t < np) {
+        const float* pt = pillars + ((size_t)p * T + t) * pdim;
+        float cx, cy, cz;
+        project(proj + ((size_t)b * V + v) * 12, pt[0], pt[1], pt[2], cx, cy, cz);
+        const float eps = 1e-5f;
+        float zz = fmaxf(cz, eps);
+        float u = cx / zz, vv = cy / zz;
+        float nx = (u / W_in - 0.5f) * 2.f, ny = (vv / H_in - 0.5f) * 2.f;
+        ok[s] = (cz > eps) && (nx > -1.f) && (nx < 1.f) && (ny > -1.f) && (ny < 1.f);
+        sx[s] = ((nx + 1.f) * (float)w - 1.f) * 0.5f;
+        sy[s] = ((ny + 1.f) * (float)h - 1.f) * 0.5f;
+      }
+    }
+  }
+  float4 q[NJ], g[NJ], acc[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    int c = 4 * lane + 128 * j;
+    q[j] = c < C ? ldg4(qk + (size_t)p * C + c) : make_float4(0, 0, 0, 0);
+    g[j] = c < C ? ldg4(ds + (size_t)p * C + c) : make_float4(0, 0, 0, 0);
+    acc[j] = make_float4(0, 0, 0, 0);
+  }
+  // pass A: logits and t_j
+  int count = 0;
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    unsigned mask = __ballot_sync(0xffffffffu, ok[s]);
+    while (mask) {
+      int src = __ffs(mask) - 1;
+      mask &= mask - 1;
+      float ix = __shfl_sync(0xffffffffu, sx[s], src), iy = __shfl_sync(0xffffffffu, sy[s], src);
+      int v = (s * 32 + src) % V;
+      float4 kv[NJ];
+      bilinear_row<NJ>(img + (size_t)(b * V + v) * h * w * C, h, w, C, ix, iy, lane, kv);
+      float pl = 0.f, pt = 0.f;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        pl += q[j].x * kv[j].x + q[j].y * kv[j].y + q[j].z * kv[j].z + q[j].w * kv[j].w;
+        pt += g[j].x * kv[j].x + g[j].y * kv[j].y + g[j].z * kv[j].z + g[j].w * kv[j].w;
+      }
+      pl = warp_sum(pl);
+      pt = warp_sum(pt);
+      if (lane == src) { lg[s] = pl; tv[s] = pt; }
+      ++count;
+    }
+  }
+  if (count > 0) {
+    float m = -INFINITY;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) m = fmaxf(m, lg[s]);
+    m = warp_max(m);
+    float L = 0.f;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      lg[s] = ok[s] ? expf(lg[s] - m) : 0.f;          // now the un-normalised weights
+      L += lg[s];
+    }
+    L = warp_sum(L);
+    const float inv = 1.f / L;
+    float D = 0.f;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      lg[s] *= inv;                                    // a_j
+      D += lg[s] * tv[s];
+    }
+    D = warp_sum(D);
+#pragma unroll
+    for (int s = 0; s < NS; ++s) tv[s] = lg[s] * (tv[s] - D);   // dl_j
+    // pass B
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      unsigned mask = __ballot_sync(0xffffffffu, ok[s]);
+      while (mask) {
+        int src = __ffs(mask) - 1;
+        mask &= mask - 1;
+        float ix = __shfl_sync(0xffffffffu, sx[s], src), iy = __shfl_sync(0xffffffffu, sy[s], src);
+        float a = __shfl_sync(0xffffffffu, lg[s], src), dl = __shfl_sync(0xffffffffu, tv[s], src);
+        int v = (s * 32 + src) % V;
+        float4 kv[NJ], dk[NJ];
+        bilinear_row<NJ>(img + (size_t)(b * V + v) * h * w * C, h, w, C, ix, iy, lane, kv);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          acc[j].x = fmaf(dl, kv[j].x, acc[j].x);
+          acc[j].y = fmaf(dl, kv[j].y, acc[j].y);
+          acc[j].z = fmaf(dl, kv[j].z, acc[j].z);
+          acc[j].w = fmaf(dl, kv[j].w, acc[j].w);
+          dk[j] = make_float4(a * g[j].x + dl * q[j].x, a * g[j].y + dl * q[j].y, a * g[j].z + dl * q[j].z,
+                              a * g[j].w + dl * q[j].w);
+        }
+        bilinear_scatter<NJ>(d_img + (size_t)(b * V + v) * h * w * C, h, w, C, ix, iy, lane, dk);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    int c = 4 * lane + 128 * j;
+    if (c < C) *reinterpret_cast<float4*>(dqk + (size_t)p * C + c) = acc[j];
+  }
+}
+
+// rows[p,:] = cnt[p] > 0 ? map[b, y, x, :] : 0   (transpose of scatter_rows_kernel)
+__global__ void gather_rows_masked_kernel(const float* __restrict__ map, const int* __restrict__ cnt,
+                                          const int* __restrict__ coors, float* __restrict__ rows, int P, int Y, int X, int C) {
+  int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (p >= P) return;
+  const int* c4 = coors + p * 4;
+  const float* src = map + (((size_t)c4[0] * Y + c4[2]) * X + c4[3]) * C;
+  const bool on = cnt[p] > 0;
+  for (int c = lane * 4; c < C; c += 128)
+    *reinterpret_cast<float4*>(rows + (size_t)p * C + c) = on ? ldg4(src + c) : make_float4(0, 0, 0, 0);
+}
+
 // rows[p,:] = map[b, y, x, :]   (coors = [b, z, y, x])
 __global__ void gather_rows_kernel(const float* __restrict__ map, const int* __restrict__ coors, float* __restrict__ rows,
                                    int P, int Y, int X, int C, const int* __restrict__ n_dev) {
@@ -544,6 +718,35 @@ int di_i2p_attend_f32(const float* qk, const float* pillars, const int* npts, co
   else
     i2p_attend_kernel<4><<<grid, 256, 0, stream>>>(qk, pillars, npts, coors, proj, img, s_out, cnt_out, P, T, pdim, V, h, w, C, (float)H_in, (float)W_in, n_dev);
   DI_CHECK_LAUNCH("di_i2p_attend_f32");
+  return DI_OK;
+}
+
+// Backward of di_i2p_attend_f32: ds [P,C] = gradient of s_out; d_img [B*V,h,w,C] is ACCUMULATED into (zero it first);
+// dqk [P,C] written.  Same geometry arguments as the forward.
+int di_i2p_attend_bwd_f32(const float* qk, const float* ds, const float* pillars, const int* npts, const int* coors,
+                          const float* proj, const float* img, float* d_img, float* dqk, int P, int T, int pdim, int V, int h,
+                          int w, int C, int H_in, int W_in, const int* n_dev, cudaStream_t stream) {
+  DI_CHECK_ARG(qk && ds && pillars && npts && coors && proj && img && d_img && dqk, "di_i2p_attend_bwd_f32: null pointer");
+  DI_CHECK_ARG(C % 4 == 0 && C <= 512 && pdim >= 3 && T * V <= 256, "di_i2p_attend_bwd_f32: unsupported shape (C=%d T=%d V=%d)", C, T, V);
+  if (P == 0) return DI_OK;
+  dim3 grid(di_cdiv(P, 8));
+  if (C <= 128)
+    i2p_attend_bwd_kernel<1><<<grid, 256, 0, stream>>>(qk, ds, pillars, npts, coors, proj, img, d_img, dqk, P, T, pdim, V, h, w, C, (float)H_in, (float)W_in, n_dev);
+  else if (C <= 256)
+    i2p_attend_bwd_kernel<2><<<grid, 256, 0, stream>>>(qk, ds, pillars, npts, coors, proj, img, d_img, dqk, P, T, pdim, V, h, w, C, (float)H_in, (float)W_in, n_dev);
+  else
+    i2p_attend_bwd_kernel<4><<<grid, 256, 0, stream>>>(qk, ds, pillars, npts, coors, proj, img, d_img, dqk, P, T, pdim, V, h, w, C, (float)H_in, (float)W_in, n_dev);
+  DI_CHECK_LAUNCH("di_i2p_attend_bwd_f32");
+  return DI_OK;
+}
+
+// rows[p] = cnt[p] > 0 ? map[coors[p]] : 0 : the gradient that reaches the attention output of pillar p
+int di_gather_rows_masked_f32(const float* map, const int* cnt, const int* coors, float* rows, int P, int Y, int X, int C,
+                              cudaStream_t stream) {
+  DI_CHECK_ARG(map && cnt && coors && rows && P >= 0 && C % 4 == 0, "di_gather_rows_masked_f32: bad argument");
+  if (P == 0) return DI_OK;
+  gather_rows_masked_kernel<<<di_cdiv(P, 8), 256, 0, stream>>>(map, cnt, coors, rows, P, Y, X, C);
+  DI_CHECK_LAUNCH("di_gather_rows_masked_f32");
   return DI_OK;
 }
 

@@ -67,6 +67,24 @@ def i2p_fold(mha):
     return M1, c1, M2, c2
 
 
+def i2p_unfold_grads(mha, dM1, dc1, dM2, dc2):
+    """Chain rule of i2p_fold: gradients w.r.t. the folded (M1, c1, M2, c2) -> gradients of the attention module's own
+    parameters, float64 on the host: dict(Wq, Wk, Wv, bq, bk, bv, Wo, bo).  (bk does not influence the output: it adds
+    the same constant to every logit of a pillar.)"""
+    E = mha.embed_dim
+    if mha._qkv_same_embed_dim:
+        Wq, Wk, Wv = _d(mha.in_proj_weight).chunk(3, 0)
+    else:
+        Wq, Wk, Wv = _d(mha.q_proj_weight), _d(mha.k_proj_weight), _d(mha.v_proj_weight)
+    bq, bk, bv = _d(mha.in_proj_bias).chunk(3, 0)
+    Wo = _d(mha.out_proj.weight)
+    s = 1.0 / math.sqrt(E)
+    dM1, dc1, dM2, dc2 = (t.detach().cpu().double() for t in (dM1, dc1, dM2, dc2))
+    # M1 = s Wk^T Wq, c1 = s Wk^T bq, M2 = Wo Wv, c2 = Wo bv + bo
+    return dict(Wq=s * Wk @ dM1, bq=s * Wk @ dc1, Wk=s * (Wq @ dM1.T + torch.outer(bq, dc1)), bk=torch.zeros_like(bk),
+                Wv=Wo.T @ dM2, Wo=dM2 @ Wv.T + torch.outer(dc2, bv), bv=Wo.T @ dc2, bo=dc2)
+
+
 def dev(t, device):
     return t.to(torch.float32).contiguous().to(device)
 

@@ -718,3 +718,24 @@ def col_sum(x):
     out = torch.empty(C, device=x.device, dtype=torch.float32)
     _call('di_col_sum_f32', p, ld, M, C, _ptr(work), _ptr(out), _stream(), nbytes=4 * M * C, launches=2)
     return out
+
+
+def i2p_attend_bwd(qk, ds, pillars, npts, coors, proj, img_nhwc, d_img, V, in_hw):
+    """Gradient of i2p_attend: -> dqk [P, C]; d_img (same shape as img_nhwc) is accumulated into."""
+    P, C = qk.shape
+    _, T, pdim = pillars.shape
+    BV, h, w, Ci = img_nhwc.shape
+    assert Ci == C and d_img.shape == img_nhwc.shape and d_img.is_contiguous() and ds.is_contiguous()
+    dqk = torch.empty(P, C, device=qk.device, dtype=torch.float32)
+    _call('di_i2p_attend_bwd_f32', _ptr(qk), _ptr(ds), _ptr(pillars), _ptr(npts), _ptr(coors), _ptr(proj), _ptr(img_nhwc),
+          _ptr(d_img), _ptr(dqk), P, T, pdim, V, h, w, C, in_hw[0], in_hw[1], None, _stream(),
+          nbytes=4 * (3 * P * C + pillars.numel() + 2 * img_nhwc.numel()))
+    return dqk
+
+
+def gather_rows_masked(map_nhwc, cnt, coors):
+    B, Y, X, C = map_nhwc.shape
+    P = coors.shape[0]
+    rows = torch.empty(P, C, device=map_nhwc.device, dtype=torch.float32)
+    _call('di_gather_rows_masked_f32', _ptr(map_nhwc), _ptr(cnt), _ptr(coors), _ptr(rows), P, Y, X, C, _stream())
+    return rows

@@ -359,6 +359,14 @@ int di_win_softmax_bwd_f32(const float* A, const float* dA, float* dS, long long
 int di_relu_bwd_f32(const float* dy, const float* y, float* dx, long long n, cudaStream_t stream);
 int di_col_sum_f32(const float* x, int ld, long long M, int C, float* work, float* out, cudaStream_t stream);
 
+/* ---- I2P backward (SURVEY.md 8(b) `di_i2p_backward`; host composition: deepinteraction_b200/backward.py i2p_backward)
+ * gradient of di_i2p_attend_f32 (models/utils/encoder_utils.py:281-311): ds [P,C] -> dqk [P,C], d_img += (atomic) */
+int di_i2p_attend_bwd_f32(const float* qk, const float* ds, const float* pillars, const int* npts, const int* coors,
+                          const float* proj, const float* img, float* d_img, float* dqk, int P, int T, int pdim, int V, int h,
+                          int w, int C, int H_in, int W_in, const int* n_dev, cudaStream_t stream);
+int di_gather_rows_masked_f32(const float* map, const int* cnt, const int* coors, float* rows, int P, int Y, int X, int C,
+                              cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -105,3 +105,46 @@ def test_lcab_backward_matches_oracle_autograd(self_attn):
         assert rel_err(o.detach().cpu(), rows(out.detach())) < 2e-4
         (o * rows(G).to(dev())).sum().backward()
     assert rel_err(tt.grad.cpu(), rows(xt.grad)) < tol
+
+
+@pytest.mark.parametrize('aug', [False, True])
+def test_i2p_backward_matches_oracle_autograd(aug):
+    """MMRI_I2P (BASELINE config 1 shapes: 32x32 BEV, C = 64, one 64x64 camera map, batch 2): gradients w.r.t. the BEV map, the
+    image map and the attention module's own parameters vs torch autograd through the CPU oracle."""
+    import oracle.mmri as om
+    from deepinteraction_b200 import mmri, synth, fold, geom, backward
+    from test_gpu_encoder import _cfg1_frame
+    seed = 1100
+    torch.manual_seed(seed)
+    m = om.MMRI_I2P(64, 64, 0.1).eval()
+    synth.randomize_norm_stats(m, seed)
+    fr = _cfg1_frame(seed, aug)
+    g = torch.Generator().manual_seed(seed)
+    pts = fr['pts_feats'].clone().requires_grad_(True)                  # (B, C, Y, X)
+    img = fr['img_feats'].clone().requires_grad_(True)                  # (B*V, C, h, w), V = 1
+    B = pts.shape[0]
+    G = torch.randn(pts.shape, generator=g)
+    with torch.enable_grad():
+        out = m(pts, img.view(B, 1, *img.shape[1:]), fr['img_metas'], fr['pts_metas'])
+        (out * G).sum().backward()
+    d = dev()
+    mha = m.learnedAlign
+    M1, c1, M2, c2 = fold.i2p_fold(mha)
+    pack = (fold.Weight(M1, d), fold.dev(c1, d), fold.Weight(M2, d), fold.dev(c2, d))
+    enc = mmri.DeepInteractionEncoder(1, 64, 64, 64)
+    pm = enc._canon_pts_metas(fr['pts_metas'], d)
+    proj, _ = geom.camera_rows(fr['img_metas'], d)
+    nhwc = lambda t: t.detach().permute(0, 2, 3, 1).contiguous().to(d)
+    r = backward.i2p_backward(pack, nhwc(pts), nhwc(img), pm, proj, 1, (256, 256), nhwc(G))
+    tol = 1e-4
+    assert rel_err(r['d_pts'].permute(0, 3, 1, 2).cpu(), pts.grad) < tol
+    assert rel_err(r['d_img'].permute(0, 3, 1, 2).cpu(), img.grad) < tol
+    assert float(pts.grad.abs().max()) > 0 and float(img.grad.abs().max()) > 0
+    pg = fold.i2p_unfold_grads(mha, r['dM1'], r['dc1'], r['dM2'], r['dc2'])
+    Wq_g, Wk_g, Wv_g = (mha.in_proj_weight.grad.chunk(3, 0) if mha._qkv_same_embed_dim else
+                        (mha.q_proj_weight.grad, mha.k_proj_weight.grad, mha.v_proj_weight.grad))
+    bq_g, bk_g, bv_g = mha.in_proj_bias.grad.chunk(3, 0)
+    for name, want in (('Wq', Wq_g), ('Wk', Wk_g), ('Wv', Wv_g), ('bq', bq_g), ('bv', bv_g),
+                       ('Wo', mha.out_proj.weight.grad), ('bo', mha.out_proj.bias.grad)):
+        assert rel_err(pg[name].float(), want) < tol, name
+    assert float(bk_g.abs().max()) < 1e-4 * float(bq_g.abs().max() + 1e-12)          # the key bias has no influence
