@@ -864,17 +864,44 @@ def main():
         try:
             with Deadline(150):
                 o_neck, o_head = build_oracle(neck.state_dict(), head.state_dict())
-                frc = dict(img_feats=fr_host['img_feats'], pts_feats=fr_host['pts_feats'],
-                           img_metas=fr_host['img_metas'], pts_metas=fr_host['pts_metas'])
+                # the check frame of the workload definition (250 000 draws, seed SEED + rank), not one of the cycled ones
+                fr_chk = host_frame(args.batch, args.cloud, SEED + rank)
+                frc = dict(img_feats=fr_chk['img_feats'], pts_feats=fr_chk['pts_feats'],
+                           img_metas=fr_chk['img_metas'], pts_metas=fr_chk['pts_metas'])
                 t0 = time.perf_counter()
                 ref_out = forward(o_neck, o_head, frc)
                 dt = time.perf_counter() - t0
-            err = {k: float((out[k].float().cpu() - ref_out[k]).abs().max() / ref_out[k].abs().max().clamp_min(1e-12))
-                   for k in ref_out}
+            # The ORDER of the proposals is defined only up to the fp32 rounding of the heat-map scores (top-k over 324 000
+            # values that agree to ~1e-6 between the two implementations: neighbouring ranks can swap).  The decoder is
+            # equivariant to that order, so the proposals are matched by their heat-map score vectors before comparing.
+            got = {k: v.float().cpu().clone() for k, v in forward(neck, head, h2d(fr_chk, device)).items()}   # the SAME frame
+            labels = head.query_labels.cpu().clone()
+            P_ = got['query_heatmap_score'].shape[-1]
+            moved, unmatched = 0, 0
+            errs, lab_ok = {k: 0.0 for k in ref_out}, True
+            for b in range(got['query_heatmap_score'].shape[0]):
+                dist = torch.cdist(ref_out['query_heatmap_score'][b].t().double(), got['query_heatmap_score'][b].t().double())
+                perm = dist.argmin(1)
+                ok = dist.min(1).values <= 1e-5                      # a near tie AT the cut swaps one proposal for another:
+                unmatched += int((~ok).sum())                        # those columns are counted, not compared
+                moved += int((perm != torch.arange(P_))[ok].sum())
+                lab_ok = lab_ok and bool(torch.equal(labels[b][perm][ok], o_head.query_labels[b][ok]))
+                for k, r in ref_out.items():
+                    if k == 'dense_heatmap':
+                        errs[k] = max(errs[k], float((got[k][b] - r[b]).abs().max() / r[b].abs().max().clamp_min(1e-12)))
+                        continue
+                    L_ = r.shape[-1] // P_
+                    cols = torch.cat([perm + c * P_ for c in range(L_)])
+                    keep = ok.repeat(L_)
+                    d_ = (got[k][b][..., cols] - r[b])[..., keep]
+                    errs[k] = max(errs[k], float(d_.abs().max() / r[b].abs().max().clamp_min(1e-12)))
             cpu = dict(value=args.batch / dt, unit='frames/s', cores=cores, kind='port',
                        sample='1 full frame of the same workload (oracle = reference PyTorch math, fp32)',
-                       max_rel_err_vs_gpu=max(err.values()),
-                       labels_equal=bool(torch.equal(head.query_labels.cpu(), o_head.query_labels)))
+                       max_rel_err_vs_gpu=max(errs.values()), labels_equal=lab_ok,
+                       proposals_reordered=moved, proposals_unmatched=unmatched,
+                       note='proposal ORDER / the membership at the top-k cut depend on fp32 rounding of heat-map scores that '
+                            'agree to ~1e-6 between the two implementations; proposals are matched by their score vectors, '
+                            'unmatched ones (near tie at the cut) are counted and excluded from max_rel_err')
         except TimeoutError:
             cpu = dict(value=None, unit='frames/s', cores=cores, kind='port',
                        sample='1 full frame did not finish within 150 s on this host')

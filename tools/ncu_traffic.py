@@ -15,7 +15,8 @@ ENTRY = [('lcab_window_tc_kernel', 'di_lcab_window_tc_f32'), ('lcab_proj_kernel'
          ('lcab_window_pre_kernel', 'di_lcab_window_pre_f32'), ('msdeform_kernel', 'di_msdeform_f32'),
          ('i2p_attend_kernel', 'di_i2p_attend_f32'), ('bev_sample_kernel', 'di_bev_sample_f32'),
          ('cross_attn', 'di_cross_attn_f32'), ('dynconv_kernel', 'di_dynconv_f32'), ('seq_attn_kernel', 'di_seq_attn_f32'),
-         ('gemm_tc_kernel_v3', 'gemm_tc_kernel_v3 (di_linear_tc*/di_conv3x3_tc*)')]
+         ('gemm_tc_kernel_v3', 'gemm_tc_kernel_v3 (di_linear_tc*/di_conv3x3_tc*)'), ('rows_mlp_kernel', 'di_rows_mlp_f32'),
+         ('depth_complete_kernel', 'di_depth_complete')]
 
 
 def main(rep, out):
@@ -31,6 +32,8 @@ def main(rep, out):
             continue
         acc[name].append(float(r[ir].replace(',', '')) * scale[units[ir]] + float(r[iw].replace(',', '')) * scale[units[iw]])
     res = {k: sum(v) / len(v) for k, v in acc.items()}
+    if 'di_lcab_proj_f32' in res and 'di_lcab_window_tc_f32' in res:      # the one-call module = both kernels
+        res['di_lcab_forward_f32'] = res['di_lcab_proj_f32'] + res['di_lcab_window_tc_f32']
     res['_source'] = dict(report=rep, launches={k: len(v) for k, v in acc.items()},
                           metric='dram__bytes_read.sum + dram__bytes_write.sum per launch (ncu --set full, --clock-control none)')
     json.dump(res, open(out, 'w'), indent=1)
