@@ -881,6 +881,8 @@ def main():
             errs, lab_ok = {k: 0.0 for k in ref_out}, True
             for b in range(got['query_heatmap_score'].shape[0]):
                 dist = torch.cdist(ref_out['query_heatmap_score'][b].t().double(), got['query_heatmap_score'][b].t().double())
+                # a BEV cell can be proposed for two classes (same score vector): the class label completes the key
+                dist = dist + 1e3 * (o_head.query_labels[b][:, None] != labels[b][None, :]).double()
                 perm = dist.argmin(1)
                 ok = dist.min(1).values <= 1e-5                      # a near tie AT the cut swaps one proposal for another:
                 unmatched += int((~ok).sum())                        # those columns are counted, not compared
