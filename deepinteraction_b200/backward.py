@@ -16,6 +16,18 @@ import torch
 from . import fold, ops
 
 
+class _precise:
+    """Gradient products run on the 3xTF32 split (error ~1e-7 per product) rather than the bf16 split of the inference
+    path (~1e-5): the backward chains a dozen products per layer."""
+
+    def __enter__(self):
+        self.saved = ops.TC_BF16[0]
+        ops.TC_BF16[0] = False
+
+    def __exit__(self, *a):
+        ops.TC_BF16[0] = self.saved
+
+
 def _bw_pack(pk):
     """Transposed weights for the dX products, built once per pack."""
     if '_bw' in pk:
@@ -45,6 +57,11 @@ def lcab_backward(pk, target, source, N, H, W, grad_out):
     """target / source / grad_out: [N*H*W, C] fp32 pixel-major rows (same tensor object for target and source = self
     attention).  -> dict(d_target, d_source (None for self attention: summed into d_target), and per layer name in
     (q1, q2, k1, k2, v) a pair (dW_folded [C, C], db_folded [C]))."""
+    with _precise():
+        return _lcab_backward(pk, target, source, N, H, W, grad_out)
+
+
+def _lcab_backward(pk, target, source, N, H, W, grad_out):
     C, ks = pk['C'], pk['ks']
     M = N * H * W
     bw = _bw_pack(pk)
@@ -95,6 +112,11 @@ def i2p_backward(i2p_pack, pts_nhwc, img_nhwc, pts_metas, proj, V, in_hw, grad_o
     (fold.i2p_fold); proj: [B, V, 12] device camera rows (mmri.Geometry.proj).  grad_out [B, Y, X, C].
     -> dict(d_pts [B,Y,X,C], d_img [B*V,h,w,C], dM1, dc1, dM2, dc2); fold.i2p_unfold_grads maps the last four to the
     attention module's own parameters."""
+    with _precise():
+        return _i2p_backward(i2p_pack, pts_nhwc, img_nhwc, pts_metas, proj, V, in_hw, grad_out)
+
+
+def _i2p_backward(i2p_pack, pts_nhwc, img_nhwc, pts_metas, proj, V, in_hw, grad_out):
     M1, c1, M2, c2 = i2p_pack
     coors = pts_metas['pillar_coors']
     pillars, npts = pts_metas['pillars'], pts_metas['pillars_num_points']
@@ -119,6 +141,105 @@ def i2p_backward(i2p_pack, pts_nhwc, img_nhwc, pts_metas, proj, V, in_hw, grad_o
     ones = torch.ones(coors.shape[0], device=dev, dtype=torch.int32)
     ops.scatter_rows(drows, ones, coors, d_pts)             # one pillar per BEV cell: a plain store
     return dict(d_pts=d_pts, d_img=d_img, dM1=dM1, dc1=dc1, dM2=dM2, dc2=dc2)
+
+
+def _t_weight(W, device):
+    return fold.Weight(W.w.detach().cpu().double().t().contiguous(), device)
+
+
+def _conv3x3_transposed(w_packed, cin, device):
+    """Packed forward weight [Cout, (ky*3+kx)*Cin + ci] -> packed weight of the input-gradient convolution
+    [Cin, (ky*3+kx)*Cout + co] with the taps flipped (d x = conv3x3(d y, W^T flipped))."""
+    w = w_packed.w.detach().cpu().double()
+    cout = w.shape[0]
+    w4 = w.view(cout, 3, 3, cin)                                   # co, ky, kx, ci
+    wt = w4.flip(1, 2).permute(3, 1, 2, 0).reshape(cin, 9 * cout)   # ci, ky', kx', co
+    return fold.Weight(wt.contiguous(), device)
+
+
+def encoder_backward(enc, img_feats, pts_feats, img_metas, pts_metas, d_img, d_pts_conv, d_pts):
+    """Backward of DeepInteractionEncoder.forward (base model, hidden width 128, BatchNorm in eval mode = the folded
+    weights of the forward; reference deepinteraction_encoder.py:8-85).  img_feats (B*V, Ci, h, w), pts_feats
+    (B, Cp, Y, X): the module's NCHW inputs on the GPU; pts_metas with pillars; d_img [B*V, h, w, C], d_pts_conv / d_pts
+    [B, Y, X, C]: gradients of the three outputs (pixel-major; None = zero).
+    -> dict(d_img_feats [B*V, h, w, Ci], d_pts_feats [B, Y, X, Cp] (pixel-major), layers = per encoder layer the folded
+    parameter gradients: i2p (dM1, dc1, dM2, dc2), p_iml / p2i / i_iml (lcab_backward dicts), p_fuse / i_fuse (dW [C, 3C], db)).
+    The forward is re-run eagerly with its intermediates kept; weight gradients of the two 3x3 shared convolutions are not
+    produced (input gradients are)."""
+    with _precise():
+        return _encoder_backward(enc, img_feats, pts_feats, img_metas, pts_metas, d_img, d_pts_conv, d_pts)
+
+
+def _encoder_backward(enc, img_feats, pts_feats, img_metas, pts_metas, d_img, d_pts_conv, d_pts):
+    from . import mmri
+    pk = enc.pack()
+    dev = img_feats.device
+    C = enc.hidden_channel
+    BV, Ci, h, w = img_feats.shape
+    B, Cp, Y, X = pts_feats.shape
+    V = BV // B
+    pm = enc._canon_pts_metas(pts_metas, dev)
+    pm['pts'] = [p.to(dev) for p in pts_metas['pts']]
+    g = mmri.Geometry(img_metas, pm, (h, w), (Y, X), dev)
+    g.wait()
+    # ---- forward with saved intermediates
+    img = ops.conv3x3(img_feats.contiguous(), *pk['shared_conv_img'], cout=C, x_nhwc=False)
+    pts = ops.conv3x3(pts_feats.contiguous(), *pk['shared_conv_pts'], cout=C, x_nhwc=False)
+    saved = []
+    for lp in pk['layers']:
+        img_r, pts_r = img.view(-1, C), pts.view(-1, C)
+        i2p = enc.i2p(lp, pts, img, pm, g)
+        p2p = mmri.lcab_forward(lp['p_iml'], pts_r, pts_r, B, Y, X)
+        new_pts = ops.linear([i2p.view(-1, C), p2p, pts_r], *lp['p_fuse']).view(B, Y, X, C)
+        warped = ops.bev_sample(pts, g.grid, V)
+        p2i = mmri.lcab_forward(lp['p2i'], img_r, warped.view(-1, C), BV, h, w)
+        i2i = mmri.lcab_forward(lp['i_iml'], img_r, img_r, BV, h, w)
+        new_img = ops.linear([p2i, i2i, img_r], *lp['i_fuse']).view(BV, h, w, C)
+        saved.append(dict(img=img, pts=pts, i2p=i2p, p2p=p2p, warped=warped, p2i=p2i, i2i=i2i))
+        img, pts = new_img, new_pts
+    # ---- backward
+    one = torch.ones(1, device=dev)
+    add = lambda a, b: b if a is None else (a if b is None else ops.axpy(a.contiguous(), b.contiguous(), one))
+    zeros_i = lambda: torch.zeros(BV * h * w, C, device=dev)
+    zeros_p = lambda: torch.zeros(B * Y * X, C, device=dev)
+    gi = d_img.reshape(-1, C).contiguous() if d_img is not None else zeros_i()
+    gp = d_pts.reshape(-1, C).contiguous() if d_pts is not None else zeros_p()
+    layer_grads = []
+    for lp, sv in zip(reversed(pk['layers']), reversed(saved)):
+        img_r, pts_r = sv['img'].view(-1, C), sv['pts'].view(-1, C)
+        lg = {}
+        # fuse convolutions: new = Wf [a | b | c] + bf
+        wi, wp = lp['i_fuse'][0], lp['p_fuse'][0]
+        di3 = ops.linear([gi], _t_weight(wi, dev))                     # [M_i, 3C] = d p2i | d i2i | d img (direct)
+        dp3 = ops.linear([gp], _t_weight(wp, dev))                     # [M_p, 3C] = d i2p | d p2p | d pts (direct)
+        lg['i_fuse'] = (torch.cat([_wgrad(gi, sv['p2i']), _wgrad(gi, sv['i2i']), _wgrad(gi, img_r.contiguous())], 1), ops.col_sum(gi))
+        lg['p_fuse'] = (torch.cat([_wgrad(gp, sv['i2p'].view(-1, C)), _wgrad(gp, sv['p2p']), _wgrad(gp, pts_r.contiguous())], 1),
+                        ops.col_sum(gp))
+        d_p2i, d_i2i, d_img_dir = (di3[:, k * C:(k + 1) * C].contiguous() for k in range(3))
+        d_i2p, d_p2p, d_pts_dir = (dp3[:, k * C:(k + 1) * C].contiguous() for k in range(3))
+        # image side
+        r_ii = lcab_backward(lp['i_iml'], img_r, img_r, BV, h, w, d_i2i)
+        r_pi = lcab_backward(lp['p2i'], img_r, sv['warped'].view(-1, C), BV, h, w, d_p2i)
+        r_ip = i2p_backward(lp['i2p'], sv['pts'], sv['img'], pm, g.proj, V, g.in_hw, d_i2p.view(B, Y, X, C))
+        r_pp = lcab_backward(lp['p_iml'], pts_r, pts_r, B, Y, X, d_p2p)
+        new_gi = add(add(add(d_img_dir, r_ii['d_target']), r_pi['d_target']), r_ip['d_img'].view(-1, C))
+        d_bev = ops.bev_sample_bwd(r_pi['d_source'].view(BV, h, w, C).contiguous(), g.grid, V, (B, Y, X, C))
+        new_gp = add(add(add(d_pts_dir, r_pp['d_target']), r_ip['d_pts'].view(-1, C)), d_bev.view(-1, C))
+        lg.update(i_iml={k: v for k, v in r_ii.items() if not k.startswith('d_')},
+                  p2i={k: v for k, v in r_pi.items() if not k.startswith('d_')},
+                  p_iml={k: v for k, v in r_pp.items() if not k.startswith('d_')},
+                  i2p=(r_ip['dM1'], r_ip['dc1'], r_ip['dM2'], r_ip['dc2']))
+        layer_grads.append(lg)
+        gi, gp = new_gi, new_gp
+    layer_grads.reverse()
+    if d_pts_conv is not None:
+        gp = add(gp, d_pts_conv.reshape(-1, C).contiguous())
+    # shared 3x3 convolutions: input gradients = convolution of the output gradient with the transposed, flipped kernels
+    wti = _conv3x3_transposed(pk['shared_conv_img'][0], Ci, dev)
+    wtp = _conv3x3_transposed(pk['shared_conv_pts'][0], Cp, dev)
+    d_img_feats = ops.conv3x3(gi.view(BV, h, w, C), wti, None, cout=Ci, x_nhwc=True)
+    d_pts_feats = ops.conv3x3(gp.view(B, Y, X, C), wtp, None, cout=Cp, x_nhwc=True)
+    return dict(d_img_feats=d_img_feats, d_pts_feats=d_pts_feats, layers=layer_grads)
 
 
 class LCABFunction(torch.autograd.Function):

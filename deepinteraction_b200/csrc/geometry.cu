@@ -676,6 +676,25 @@ bev_sample_kernel(const float* __restrict__ bev, const float2* __restrict__ grid
   }
 }
 
+// transpose of bev_sample_kernel: d_bev[b] += bilinear scatter of d_out[bv, y, x, :] at grid[bv, y, x]
+template <int NJ>
+__global__ void __launch_bounds__(256)
+bev_sample_bwd_kernel(const float* __restrict__ d_out, const float2* __restrict__ grid, float* __restrict__ d_bev, int V, int hw,
+                      int Yb, int Xb, int C, int total) {
+  int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (i >= total) return;
+  int b = i / (V * hw);
+  float2 g = grid[i];
+  float4 v[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    int c = 4 * lane + 128 * j;
+    v[j] = c < C ? ldg4(d_out + (size_t)i * C + c) : make_float4(0, 0, 0, 0);
+  }
+  bilinear_scatter<NJ>(d_bev + (size_t)b * Yb * Xb * C, Yb, Xb, C, g.x, g.y, lane, v);
+}
+
 }  // namespace
 
 extern "C" {
@@ -796,6 +815,23 @@ int di_bev_sample_f32(const float* bev, const float* grid_xy, float* out, int B,
   else
     bev_sample_kernel<4><<<grid, 256, 0, stream>>>(bev, g, out, V, hw, Yb, Xb, C, total);
   DI_CHECK_LAUNCH("di_bev_sample_f32");
+  return DI_OK;
+}
+
+// Backward of di_bev_sample_f32 w.r.t. the BEV map: d_bev [B,Yb,Xb,C] += scatter of d_out [B*V,hw,C] (atomicAdd; zero it first)
+int di_bev_sample_bwd_f32(const float* d_out, const float* grid_xy, float* d_bev, int B, int V, int hw, int Yb, int Xb, int C,
+                          cudaStream_t stream) {
+  DI_CHECK_ARG(d_out && grid_xy && d_bev && C % 4 == 0 && C <= 512, "di_bev_sample_bwd_f32: bad argument");
+  int total = B * V * hw;
+  dim3 grid(di_cdiv(total, 8));
+  const float2* g = reinterpret_cast<const float2*>(grid_xy);
+  if (C <= 128)
+    bev_sample_bwd_kernel<1><<<grid, 256, 0, stream>>>(d_out, g, d_bev, V, hw, Yb, Xb, C, total);
+  else if (C <= 256)
+    bev_sample_bwd_kernel<2><<<grid, 256, 0, stream>>>(d_out, g, d_bev, V, hw, Yb, Xb, C, total);
+  else
+    bev_sample_bwd_kernel<4><<<grid, 256, 0, stream>>>(d_out, g, d_bev, V, hw, Yb, Xb, C, total);
+  DI_CHECK_LAUNCH("di_bev_sample_bwd_f32");
   return DI_OK;
 }
 

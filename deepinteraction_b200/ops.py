@@ -739,3 +739,14 @@ def gather_rows_masked(map_nhwc, cnt, coors):
     rows = torch.empty(P, C, device=map_nhwc.device, dtype=torch.float32)
     _call('di_gather_rows_masked_f32', _ptr(map_nhwc), _ptr(cnt), _ptr(coors), _ptr(rows), P, Y, X, C, _stream())
     return rows
+
+
+def bev_sample_bwd(d_out, grid, V, bev_shape):
+    """Gradient of bev_sample w.r.t. the BEV map: d_out [B*V, h, w, C] -> [B, Yb, Xb, C]."""
+    B, Yb, Xb, C = bev_shape
+    n_img, h, w, _ = grid.shape
+    d_bev = torch.zeros(B, Yb, Xb, C, device=d_out.device, dtype=torch.float32)
+    assert d_out.is_contiguous()
+    _call('di_bev_sample_bwd_f32', _ptr(d_out), _ptr(grid), _ptr(d_bev), B, V, h * w, Yb, Xb, C, _stream(),
+          nbytes=4 * (d_bev.numel() + grid.numel() + d_out.numel()))
+    return d_bev

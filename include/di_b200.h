@@ -364,6 +364,9 @@ int di_col_sum_f32(const float* x, int ld, long long M, int C, float* work, floa
 int di_i2p_attend_bwd_f32(const float* qk, const float* ds, const float* pillars, const int* npts, const int* coors,
                           const float* proj, const float* img, float* d_img, float* dqk, int P, int T, int pdim, int V, int h,
                           int w, int C, int H_in, int W_in, const int* n_dev, cudaStream_t stream);
+/* backward of di_bev_sample_f32 w.r.t. the BEV map (encoder_utils.py:193-195 grid_sample): d_bev += bilinear scatter */
+int di_bev_sample_bwd_f32(const float* d_out, const float* grid_xy, float* d_bev, int B, int V, int hw, int Yb, int Xb, int C,
+                          cudaStream_t stream);
 int di_gather_rows_masked_f32(const float* map, const int* cnt, const int* coors, float* rows, int P, int Y, int X, int C,
                               cudaStream_t stream);
 

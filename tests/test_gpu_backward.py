@@ -148,3 +148,45 @@ def test_i2p_backward_matches_oracle_autograd(aug):
                        ('Wo', mha.out_proj.weight.grad), ('bo', mha.out_proj.bias.grad)):
         assert rel_err(pg[name].float(), want) < tol, name
     assert float(bk_g.abs().max()) < 1e-4 * float(bq_g.abs().max() + 1e-12)          # the key bias has no influence
+
+
+def test_encoder_backward_matches_oracle_autograd():
+    """Whole base encoder (2 layers: I2P, BEVWarp sampling + P2I, both self-attention blocks, fuse convolutions, 3x3 shared
+    convolutions) with BatchNorm in eval mode: gradients of a random linear functional of the three outputs w.r.t. the two input
+    feature maps, and a few folded parameter gradients, vs torch autograd through the CPU oracle."""
+    import oracle.mmri as om
+    from deepinteraction_b200 import mmri, synth, backward
+    from tools.make_goldens import small_frame
+    seed = 1560
+    torch.manual_seed(seed)
+    m = om.DeepInteractionEncoder(2, 64, 64, 128).eval()
+    synth.randomize_norm_stats(m, seed)
+    fr = small_frame(seed, aug=True, views=2, c_img=64, c_pts=64, bev=36, batch=1)
+    g = torch.Generator().manual_seed(seed)
+    xi = fr['img_feats'].clone().requires_grad_(True)
+    xp = fr['pts_feats'].clone().requires_grad_(True)
+    with torch.enable_grad():
+        o_img, (o_pc, o_p) = m(xi, xp, fr['img_metas'], fr['pts_metas'])
+        G_img, G_pc, G_p = (torch.randn(t.shape, generator=g) for t in (o_img, o_pc, o_p))
+        ((o_img * G_img).sum() + (o_pc * G_pc).sum() + (o_p * G_p).sum()).backward()
+    enc = mmri.DeepInteractionEncoder(2, 64, 64, 128)
+    enc.load_state_dict(m.state_dict(), strict=True)
+    enc = enc.to(dev()).eval()
+    d = dev()
+    nhwc = lambda t: t.detach().permute(0, 2, 3, 1).contiguous().to(d)
+    pm = {k: (v.to(d) if torch.is_tensor(v) else [p.to(d) for p in v]) for k, v in fr['pts_metas'].items()}
+    r = backward.encoder_backward(enc, fr['img_feats'].to(d), fr['pts_feats'].to(d), fr['img_metas'], pm, nhwc(G_img), nhwc(G_pc),
+                                  nhwc(G_p))
+    tol = 1e-3          # the forward intermediates carry the inference path's bf16-split rounding (1e-5 per layer)
+    e_i = rel_err(r['d_img_feats'].permute(0, 3, 1, 2).cpu(), xi.grad)
+    e_p = rel_err(r['d_pts_feats'].permute(0, 3, 1, 2).cpu(), xp.grad)
+    print('encoder backward: d img_feats %.2e, d pts_feats %.2e' % (e_i, e_p))
+    assert e_i < tol and e_p < tol
+    # parameter gradients of the last layer: value_project of I_IML (conv weight via the BN scale) and the I2P output bias
+    blk = m.fusion_blocks[1]
+    vp = blk.I_IML.value_project
+    scale = (vp.bn.weight / torch.sqrt(vp.bn.running_var + vp.bn.eps)).detach()
+    dW, db = r['layers'][1]['i_iml']['v']
+    assert rel_err(dW.cpu() * scale[:, None], vp.conv.weight.grad[:, :, 0, 0]) < tol
+    assert rel_err(db.cpu(), vp.bn.bias.grad) < tol
+    assert rel_err(r['layers'][1]['i2p'][3].cpu(), blk.I2P_block.learnedAlign.out_proj.bias.grad) < tol
