@@ -466,8 +466,13 @@ class DeepInteractionDecoder(nn.Module, LossMixin):
         q = self._mlp([a], wo, bo, res=q, ln=pk['norm1'])
         qc = self._mlp([q, qpe], *pk['cross_q'])
         w_kv, b_kv, ckv = pk['cross_kv']
-        kv = ops.linear([pts_conv.view(B * HW, C)], w_kv, b_kv, res=ckv, res_mod=HW)
-        a = ops.cross_attn(qc, kv, B, P, HW, H)
+        if ops.can_xattn_tc(P, C, H, B * HW):
+            # K / V projection with a planar bf16 hi|mid epilogue, then the tcgen05 attention kernel (xattn_tc.cu)
+            kv = ops.linear_split_tc([pts_conv.view(B * HW, C)], w_kv, b_kv, ckv, HW, 0, 3)
+            a = ops.xattn_tc(ops.planar_split(qc), kv, B, P, HW, H)
+        else:
+            kv = ops.linear([pts_conv.view(B * HW, C)], w_kv, b_kv, res=ckv, res_mod=HW)
+            a = ops.cross_attn(qc, kv, B, P, HW, H)
         q = self._mlp([a], *pk['cross_out'], res=q, ln=pk['norm2'])
         f1w, f1b, f2w, f2b = pk['ffn']
         q = self._mlp([q], f1w, f1b, ops.ACT_RELU, f2w, f2b, res=q, ln=pk['norm3'])
