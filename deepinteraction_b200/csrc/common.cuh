@@ -32,6 +32,21 @@ void di_set_error(const char* fmt, ...);
 
 static inline int di_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (call site, device): one process may drive several GPUs
+struct DiSmemOnce {
+  bool done[64];
+};
+template <class Kern>
+static inline bool di_smem_once(DiSmemOnce& st, Kern kernel, int bytes) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
+  if (!st.done[dev]) {
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return false;
+    st.done[dev] = true;
+  }
+  return true;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -1328,10 +1328,10 @@ int di_rows_mlp_f32(const float* X0, int ld0, int K0, const float* X1, int ld1, 
                "di_rows_mlp_f32: N1, N2 must be multiples of 4 and the weights 16-byte aligned (bulk copies)");
   const size_t smem = sizeof(float) * ((size_t)MLP_NS * MLP_CHUNK + MLP_R * (size_t)(K0 + K1 + N1 + (W2t ? N2 : 0) + 2048));
   DI_CHECK_ARG(smem <= 226 * 1024, "di_rows_mlp_f32: K + N1 + N2 too large for shared memory (%d)", K0 + K1 + N1 + N2);
-  static bool once = false;
-  if (!once) {
-    cudaFuncSetAttribute(rows_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-    once = true;
+  static DiSmemOnce once{};
+  if (!di_smem_once(once, rows_mlp_kernel, 226 * 1024)) {
+    di_set_error("di_rows_mlp_f32: cannot reserve shared memory");
+    return DI_ERR_LAUNCH;
   }
   rows_mlp_kernel<<<di_cdiv(M, MLP_R), MLP_NT, smem, stream>>>(X0, ld0, K0, X1, ld1, K1, W1t, b1, N1, act1, W2t, b2, N2, res,
                                                            ldres, gamma, beta, eps, act_out, zero_if_neg, Y, ldy, M);
@@ -1380,10 +1380,10 @@ int di_dynconv_f32(const float* roi, const float* params, const float* g1, const
                    const float* b2, float* out, int n, float eps, cudaStream_t stream) {
   DI_CHECK_ARG(roi && params && g1 && b1 && g2 && b2 && out && n > 0, "di_dynconv_f32: bad argument");
   const int smem = 2 * DR * DC * (int)sizeof(float);
-  static bool once = false;
-  if (!once) {
-    cudaFuncSetAttribute(dynconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    once = true;
+  static DiSmemOnce once{};
+  if (!di_smem_once(once, dynconv_kernel, smem)) {
+    di_set_error("di_dynconv_f32: cannot reserve shared memory");
+    return DI_ERR_LAUNCH;
   }
   dynconv_kernel<<<n, 256, smem, stream>>>(roi, params, g1, b1, g2, b2, out, eps);
   DI_CHECK_LAUNCH("di_dynconv_f32");

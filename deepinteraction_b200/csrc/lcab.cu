@@ -842,10 +842,10 @@ int di_lcab_window_pre_f32(const float* q, int ldq, const float* k, int ldk, con
   DI_CHECK_ARG(((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)out) % 16 == 0, "di_lcab_window_pre_f32: pointers must be 16-byte aligned");
   dim3 mgrid(di_cdiv(W, MQ_COLS), di_cdiv(H, MQ_ROWS), N);
   size_t smem = 2ull * BSTAGE_WORDS * sizeof(float);
-  static bool once = false;
-  if (!once) {
-    cudaFuncSetAttribute(lcab_window_pre_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    once = true;
+  static DiSmemOnce once{};
+  if (!di_smem_once(once, lcab_window_pre_kernel, (int)smem)) {
+    di_set_error("di_lcab_window_pre_f32: cannot reserve shared memory");
+    return DI_ERR_LAUNCH;
   }
   lcab_window_pre_kernel<<<mgrid, 256, smem, stream>>>(q, ldq, k, ldk, v, ldv, out, ldo, H, W, C, 1.0f / sqrtf((float)C));
   DI_CHECK_LAUNCH("di_lcab_window_pre_f32");
@@ -865,35 +865,35 @@ int di_lcab_window_f32(const float* q, int ldq, const float* k, int ldk, const f
   if (ksize == 9 && C % MCH == 0 && g_force_ffma_window == 0) {
     dim3 mgrid(di_cdiv(W, MQ_COLS), di_cdiv(H, MQ_ROWS), N);
     size_t smem = (2ull * BSTAGE_WORDS + VPK_WORDS) * sizeof(float);
-    static bool once_bf = false;
-    if (!once_bf) {
-      cudaFuncSetAttribute(lcab_window_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      once_bf = true;
+    static DiSmemOnce once_bf{};
+    if (!di_smem_once(once_bf, lcab_window_bf16_kernel, (int)smem)) {
+      di_set_error("di_lcab_window_f32: cannot reserve shared memory");
+      return DI_ERR_LAUNCH;
     }
     lcab_window_bf16_kernel<<<mgrid, 256, smem, stream>>>(q, ldq, k, ldk, v, ldv, out, ldo, H, W, C, scale);
   } else if (ksize == 9 && C % MCH == 0 && g_force_ffma_window == 2) {
     dim3 mgrid(di_cdiv(W, MQ_COLS), di_cdiv(H, MQ_ROWS), N);
     size_t smem = 2ull * MSTAGE_FLOATS * sizeof(float);
-    static bool once_mma = false;
-    if (!once_mma) {
-      cudaFuncSetAttribute(lcab_window_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      once_mma = true;
+    static DiSmemOnce once_mma{};
+    if (!di_smem_once(once_mma, lcab_window_mma_kernel, (int)smem)) {
+      di_set_error("di_lcab_window_f32: cannot reserve shared memory");
+      return DI_ERR_LAUNCH;
     }
     lcab_window_mma_kernel<<<mgrid, 256, smem, stream>>>(q, ldq, k, ldk, v, ldv, out, ldo, H, W, C, scale);
   } else if (ksize == 9) {
     size_t smem = 2ull * (TQ + 8) * (TQ + 8) * PSTR * sizeof(float);
-    static bool once9 = false;
-    if (!once9) {
-      cudaFuncSetAttribute(lcab_window_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      once9 = true;
+    static DiSmemOnce once9{};
+    if (!di_smem_once(once9, lcab_window_kernel<9>, (int)smem)) {
+      di_set_error("di_lcab_window_f32: cannot reserve shared memory");
+      return DI_ERR_LAUNCH;
     }
     lcab_window_kernel<9><<<grid, TQ * TQ, smem, stream>>>(q, ldq, k, ldk, v, ldv, out, ldo, H, W, C, scale);
   } else if (ksize == 3) {
     size_t smem = 2ull * (TQ + 2) * (TQ + 2) * PSTR * sizeof(float);
-    static bool once3 = false;
-    if (!once3) {
-      cudaFuncSetAttribute(lcab_window_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      once3 = true;
+    static DiSmemOnce once3{};
+    if (!di_smem_once(once3, lcab_window_kernel<3>, (int)smem)) {
+      di_set_error("di_lcab_window_f32: cannot reserve shared memory");
+      return DI_ERR_LAUNCH;
     }
     lcab_window_kernel<3><<<grid, TQ * TQ, smem, stream>>>(q, ldq, k, ldk, v, ldv, out, ldo, H, W, C, scale);
   } else {

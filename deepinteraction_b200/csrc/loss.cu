@@ -445,10 +445,10 @@ int di_hungarian_f32(const float* cost, const float* iou, const int* n_gt, int B
   const int nmax = P > Gmax ? P : Gmax;
   const int smem = nmax * (3 * (int)sizeof(double) + 5 * (int)sizeof(int));
   DI_CHECK_ARG(smem <= 200 * 1024, "di_hungarian_f32: problem too large (P=%d, G=%d)", P, Gmax);
-  static bool once = false;
-  if (!once) {
-    cudaFuncSetAttribute(hungarian_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    once = true;
+  static DiSmemOnce once{};
+  if (!di_smem_once(once, hungarian_kernel, 200 * 1024)) {
+    di_set_error("di_hungarian_f32: cannot reserve shared memory");
+    return DI_ERR_LAUNCH;
   }
   hungarian_kernel<<<B * L, 32, smem, stream>>>(cost, iou, n_gt, P, L, Gmax, gt_inds, max_overlaps);
   DI_CHECK_LAUNCH("di_hungarian_f32");

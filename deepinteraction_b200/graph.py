@@ -36,6 +36,7 @@ class GraphCache:
         self.entries = collections.OrderedDict()
         self.seen = collections.OrderedDict()
         self.max_entries = max_entries
+        self._capture_streams = {}             # consumer stream id -> the stream its graphs are captured on
 
     def clear(self):
         self.entries.clear()
@@ -105,7 +106,14 @@ class GraphCache:
         torch.cuda.synchronize(dev)
         g = torch.cuda.CUDAGraph()
         n0 = ops.LAUNCHES[0]
-        with torch.cuda.graph(g):
+        # Capture on a stream that belongs to THIS cache and THIS consumer stream.  torch.cuda.graph() would otherwise capture
+        # every graph of the process on one shared side stream, and the per-(device, stream) tile-scheduler rings of the
+        # persistent tensor-core kernels (tc::sched_slot, gemm_tc.cu) are keyed by the stream seen at launch = capture time:
+        # graphs replayed concurrently on different pipeline streams would then share scheduler slots.
+        cap = self._capture_streams.get(cur.cuda_stream)
+        if cap is None:
+            cap = self._capture_streams[cur.cuda_stream] = torch.cuda.Stream(device=dev)
+        with torch.cuda.graph(g, stream=cap):
             out = fn(s_in, s_c, s_st)
         launches = ops.LAUNCHES[0] - n0
         ent = (g, s_in, s_c, pinned, out, launches, [0, None, None], s_st)

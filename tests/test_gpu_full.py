@@ -46,6 +46,40 @@ def test_config2_base_full_frame_matches_oracle():
     assert max(errs.values()) < TOL, errs
 
 
+def test_pipeline_depth3_distinct_base_frames_equal_sequential():
+    """FramePipeline(depth=3) at the BASE shapes with six different frames (different point / pillar counts) submitted
+    round-robin for several rounds: every output equals, bit for bit, the one-frame-at-a-time result.  Guards the
+    per-(device, stream) tile-scheduler slots of the persistent tensor-core kernels and the geometry side streams."""
+    sys.path.insert(0, ROOT)
+    import bench
+    from deepinteraction_b200 import synth
+    from deepinteraction_b200.pipeline import FramePipeline
+    torch.set_grad_enabled(False)
+    neck, head = bench.build_models(dev())
+    frames = [synth.to_device(synth.make_frame_batch(bench.SEED + 40 + i, batch=1, cloud='lidar',
+                                                     n_points=int(250000 * (0.88 + 0.04 * i))), dev()) for i in range(6)]
+    refs = []
+    for fr in frames:
+        img, pts = neck(fr['img_feats'], fr['pts_feats'], fr['img_metas'], fr['pts_metas'])
+        refs.append({k: v.clone() for k, v in head(pts, img, fr['img_metas'])[0][0].items()})
+    torch.cuda.synchronize()
+    pipe = FramePipeline(neck, head, depth=3, device=dev())
+    try:
+        for rnd in range(4):
+            got = []
+            for i, fr in enumerate(frames):
+                out, ev, s = pipe.submit(fr, stream_index=i % 3)
+                with torch.cuda.stream(s):
+                    got.append({k: v.clone() for k, v in out.items()})
+            pipe.join()
+            torch.cuda.synchronize()
+            bad = [(rnd, i, k, float((g_[k] - r[k]).abs().max())) for i, (g_, r) in enumerate(zip(got, refs)) for k in r
+                   if not torch.equal(g_[k], r[k])]
+            assert not bad, bad[:8]
+    finally:
+        pipe.close() if hasattr(pipe, 'close') else None
+
+
 def test_config5_decoder_300_queries_256_bev():
     """Decoder at config 5's sizes: 256x256 BEV, 6 x (128,128,352) image maps, 300 queries."""
     from test_gpu_decoder import _build, _compare
