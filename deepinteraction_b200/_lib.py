@@ -24,10 +24,9 @@ SIGNATURES = {
     'di_linear_tc_f32': [_p, _i, _i, _p, _i, _i, _p, _i, _i, _p, _p, _p, _p, _i, _i, _p, _i, _i, _i, _i, _p],
     'di_linear_tcb_f32': [_p, _i, _i, _p, _i, _i, _p, _i, _i, _p, _p, _p, _p, _i, _i, _p, _i, _i, _i, _i, _p],
     'di_linear_tcb_split_f32': [_p, _i, _i, _p, _i, _i, _p, _i, _i, _p, _p, _p, _p, _i, _i, _p, _i, _i, _i, _i, _i, _i, _p],
-    'di_linear_tc_split_f32': [_p, _i, _i, _p, _i, _i, _p, _i, _i, _p, _p, _p, _p, _i, _i, _p, _i, _i, _i, _i, _i, _i, _p],
-    'di_planar_split_f32': [_p, _i, _p, _i, _p],
+    'di_attn_planes_f32': [_p, _i, _p, _i, _p, _i, _p, _p, _ll, _p],
     'di_xattn_tc_splits': [_i, _i],
-    'di_xattn_tc_f32': [_p, _p, _p, _i, _p, _p, _i, _i, _i, _i, _p],
+    'di_xattn_tc_f32': [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
     'di_conv3x3_tc_f32': [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     'di_conv3x3_tcb_f32': [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     'di_conv3x3_tc_nchw_f32': [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],

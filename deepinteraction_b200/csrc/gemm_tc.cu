@@ -1031,14 +1031,4 @@ int di_conv3x3_tcb_nchw_f32(const float* x, const void* w_hi, const void* w_mid,
   return conv3x3_tc_impl("di_conv3x3_tcb_nchw_f32", 1, 1, x, w_hi, w_mid, bias, y, N, Cin, H, W, Cout, act, stream);
 }
 
-// di_linear_tc_f32 (3xTF32) with the pre-split output formats of di_linear_tcb_split_f32: the K / V projection of the
-// decoder's cross attention keeps the precise product and still emits planar operands for di_xattn_tc_f32.
-int di_linear_tc_split_f32(const float* A0, int lda0, int K0, const float* A1, int lda1, int K1, const float* A2, int lda2,
-                           int K2, const float* W_hi, const float* W_lo, const float* bias, const float* res, int ldres,
-                           int res_mod, float* C, int ldc, int M, int N, int act, int split_col0, int split_kind,
-                           cudaStream_t stream) {
-  return linear_tc_impl("di_linear_tc_split_f32", 0, A0, lda0, K0, A1, lda1, K1, A2, lda2, K2, W_hi, W_lo, bias, res, ldres,
-                        res_mod, C, ldc, M, N, act, split_col0, split_kind, stream);
-}
-
 }  // extern "C"

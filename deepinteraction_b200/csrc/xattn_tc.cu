@@ -2,15 +2,15 @@
 //
 // Reference: TransformerDecoderLayer / multi_head_attention_forward, models/utils/decoder_utils.py:101-103, 466-493:
 // P = 200 object queries x HW = 32 400 BEV keys, 8 heads of 16 channels, softmax over all keys.  The K / V projection
-// (with the folded key positional term) is a 3xTF32 GEMM whose epilogue writes K and V as PLANAR bf16 hi|mid operands
-// (gemm_tc.cu split kind 3: per 128 channels 64 words of bf16 hi pairs, then 64 words of mid pairs); the projected,
-// pre-scaled queries are converted to the same format by di_planar_split_f32.  A TMA box {64 channels, rows} of such a
-// map is a 128B-swizzled tcgen05 operand tile whose 32-byte k-slices are the heads.
+// (with the folded key positional term) stays a 3xTF32 GEMM; di_attn_planes_f32 then writes the operands as bf16 PLANES:
+// K and the pre-scaled queries as hi | mid | lo (x = hi + mid + lo to 24 mantissa bits: the logits go through exp, and a
+// two-plane product -- 3 * 2^-18 relative -- moved the decoder outputs by up to 3e-3), V as hi | mid.  A TMA box
+// {64 channels, rows} of a plane is a 128B-swizzled tcgen05 operand tile whose 32-byte k-slices are the heads.
 //
 // CTA = (batch, query tile of 128, channel box of 64 = 4 heads, key split).  Per key tile of 64 keys:
 //   S_h[128 q x 64 keys] = Q_h K_h^T    h = 0..3: one k-step (16 channels) per head, SS-mode tcgen05.mma kind::f16,
-//                                       error-compensated split product Q_mid K_hi + Q_hi K_mid + Q_hi K_hi -> TMEM
-//                                       columns [64 h, 64 h + 64)
+//                                       six-term split product (lo hi, hi lo, mid mid, mid hi, hi mid, hi hi: error
+//                                       ~2^-26) -> TMEM columns [64 h, 64 h + 64)
 //   P_h = exp(S_h - m)                  8 softmax warps (two per TMEM lane quarter, two heads each), thread = query:
 //                                       running maximum m and sum l per head in registers (online softmax), P written
 //                                       IN PLACE over S as bf16 hi | mid words (the A operand of the second product)
@@ -28,10 +28,10 @@ using namespace tc;
 
 constexpr int XT_KEYS = 64;                          // keys per tile
 constexpr int XT_BOX = XT_KEYS * 128;                // one K / V box: 64 rows x 128 B
-constexpr int XT_STAGE = 4 * XT_BOX;                 // K hi | K mid | V hi | V mid
+constexpr int XT_STAGE = 5 * XT_BOX;                 // K hi | K mid | K lo | V hi | V mid
 constexpr int XT_RING = 4;
 constexpr int XT_QBOX = 128 * 128;                   // 128 queries x 128 B
-constexpr int XT_Q_OFF = 0, XT_RING_OFF = 2 * XT_QBOX, XT_BAR_OFF = XT_RING_OFF + XT_RING * XT_STAGE;
+constexpr int XT_Q_OFF = 0, XT_RING_OFF = 3 * XT_QBOX, XT_BAR_OFF = XT_RING_OFF + XT_RING * XT_STAGE;
 constexpr int XT_SMEM = XT_BAR_OFF + 256;
 constexpr int XT_THREADS = 10 * 32;                  // producer, MMA issuer, 8 softmax warps
 static_assert(XT_SMEM <= 232448, "xattn kernel exceeds the shared-memory limit");
@@ -121,19 +121,20 @@ xattn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
     // ---------------- TMA producer ----------------
     if (lane == 0) {
       const int q0 = b * p.P + mt * 128;
-      mbar_expect_tx(q_full, 2 * XT_QBOX);
-      tma_load_2d(base + XT_Q_OFF, &mapQ, q_full, 64 * box, q0);                    // hi
-      tma_load_2d(base + XT_Q_OFF + XT_QBOX, &mapQ, q_full, 128 + 64 * box, q0);    // mid
+      mbar_expect_tx(q_full, 3 * XT_QBOX);
+#pragma unroll
+      for (int pl = 0; pl < 3; ++pl)                                                 // hi, mid, lo planes
+        tma_load_2d(base + XT_Q_OFF + pl * XT_QBOX, &mapQ, q_full, 128 * pl + 64 * box, q0);
       for (int i = 0; i < ntiles; ++i) {
         const int s = i % XT_RING;
         if (i >= XT_RING) mbar_wait(empty(s), ((i / XT_RING) - 1) & 1);
         const uint32_t st = base + XT_RING_OFF + s * XT_STAGE;
         const int row = b * p.HW + k_begin + i * XT_KEYS;
         mbar_expect_tx(full(s), XT_STAGE);
-        tma_load_2d(st, &mapK, full(s), 64 * box, row);
-        tma_load_2d(st + XT_BOX, &mapK, full(s), 128 + 64 * box, row);
-        tma_load_2d(st + 2 * XT_BOX, &mapV, full(s), 64 * box, row);
-        tma_load_2d(st + 3 * XT_BOX, &mapV, full(s), 128 + 64 * box, row);
+#pragma unroll
+        for (int pl = 0; pl < 3; ++pl) tma_load_2d(st + pl * XT_BOX, &mapK, full(s), 128 * pl + 64 * box, row);
+        tma_load_2d(st + 3 * XT_BOX, &mapV, full(s), 64 * box, row);
+        tma_load_2d(st + 4 * XT_BOX, &mapV, full(s), 128 + 64 * box, row);
       }
     }
   } else if (warp == 1) {
@@ -148,10 +149,15 @@ xattn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
       if (elect_one()) {
 #pragma unroll
         for (int hh = 0; hh < 4; ++hh) {
-          const uint64_t q_hi = umma_desc(qb + hh * 32), q_mid = umma_desc(qb + XT_QBOX + hh * 32);
-          const uint64_t k_hi = umma_desc(kb + hh * 32), k_mid = umma_desc(kb + XT_BOX + hh * 32);
+          const uint64_t q_hi = umma_desc(qb + hh * 32), q_mid = umma_desc(qb + XT_QBOX + hh * 32),
+                         q_lo = umma_desc(qb + 2 * XT_QBOX + hh * 32);
+          const uint64_t k_hi = umma_desc(kb + hh * 32), k_mid = umma_desc(kb + XT_BOX + hh * 32),
+                         k_lo = umma_desc(kb + 2 * XT_BOX + hh * 32);
           const uint32_t d = tmem_base + (uint32_t)(64 * hh);
-          x_umma_ss(d, q_mid, k_hi, XIDESC_S, 0);
+          x_umma_ss(d, q_lo, k_hi, XIDESC_S, 0);              // smallest terms first
+          x_umma_ss(d, q_hi, k_lo, XIDESC_S, 1);
+          x_umma_ss(d, q_mid, k_mid, XIDESC_S, 1);
+          x_umma_ss(d, q_mid, k_hi, XIDESC_S, 1);
           x_umma_ss(d, q_hi, k_mid, XIDESC_S, 1);
           x_umma_ss(d, q_hi, k_hi, XIDESC_S, 1);
         }
@@ -162,7 +168,7 @@ xattn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
       if (i > 0) mbar_wait(o_empty, (i - 1) & 1);           // the previous tile's O columns have been read
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t vb = kb + 2 * XT_BOX;
+        const uint32_t vb = kb + 3 * XT_BOX;
 #pragma unroll
         for (int hh = 0; hh < 4; ++hh) {
           const uint32_t d = tmem_base + 256u + (uint32_t)(64 * hh);
@@ -305,21 +311,47 @@ xattn_combine_kernel(const float* __restrict__ part, float* __restrict__ out, in
   if (lane < 16) out[(size_t)(b * P + qi) * C + head * 16 + lane] = mine;
 }
 
-// fp32 rows -> planar bf16 hi | mid words (the operand format of the tcgen05 attention kernels), 128 channels
-__global__ void planar_split_kernel(const float* __restrict__ x, int ld, uint32_t* __restrict__ out, int M) {
+// bf16 planes of fp32 rows: hi = bf16(x), mid = bf16(x - hi), lo = bf16(x - hi - mid); a plane holds 128 channels as 64
+// words of packed pairs (lower channel in the low half)
+__device__ __forceinline__ void split3(float a, float b, uint32_t& hi, uint32_t& mid, uint32_t& lo) {
+  hi = pack_bf16x2(a, b);
+  const float ra = a - __uint_as_float(hi << 16), rb = b - __uint_as_float(hi & 0xFFFF0000u);
+  mid = pack_bf16x2(ra, rb);
+  lo = pack_bf16x2(ra - __uint_as_float(mid << 16), rb - __uint_as_float(mid & 0xFFFF0000u));
+}
+// q rows [M, ld] -> [M, 192 words]: hi | mid | lo
+__global__ void planes3_kernel(const float* __restrict__ x, int ld, uint32_t* __restrict__ out, int M) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;       // (row, word)
   if (i >= M * 64) return;
   const int r = i >> 6, wd = i & 63;
-  const float a = x[(size_t)r * ld + 2 * wd], b = x[(size_t)r * ld + 2 * wd + 1];
-  const uint32_t hi = pack_bf16x2(a, b);
-  out[(size_t)r * 128 + wd] = hi;
-  out[(size_t)r * 128 + 64 + wd] = pack_bf16x2(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xFFFF0000u));
+  uint32_t hi, mid, lo;
+  split3(x[(size_t)r * ld + 2 * wd], x[(size_t)r * ld + 2 * wd + 1], hi, mid, lo);
+  uint32_t* o = out + (size_t)r * 192;
+  o[wd] = hi; o[64 + wd] = mid; o[128 + wd] = lo;
+}
+// kv rows [M, ld >= 256] (K = columns 0..127, V = 128..255) -> kplanes [M, 192 words] hi | mid | lo, vplanes [M, 128 words] hi | mid
+__global__ void kv_planes_kernel(const float* __restrict__ kv, int ld, uint32_t* __restrict__ kp, uint32_t* __restrict__ vp,
+                                 long long M) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (row, word of 128)
+  if (i >= M * 128) return;
+  const long long r = i >> 7;
+  const int wd = (int)(i & 127);
+  const float2 v = *reinterpret_cast<const float2*>(kv + (size_t)r * ld + 2 * wd);
+  uint32_t hi, mid, lo;
+  split3(v.x, v.y, hi, mid, lo);
+  if (wd < 64) {
+    uint32_t* o = kp + (size_t)r * 192;
+    o[wd] = hi; o[64 + wd] = mid; o[128 + wd] = lo;
+  } else {
+    uint32_t* o = vp + (size_t)r * 128;
+    o[wd - 64] = hi; o[wd] = mid;
+  }
 }
 
 bool make_rows_map(CUtensorMap* m, const void* ptr, long long rows, int ld_words, int box_rows) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
-  cuuint64_t dims[2] = {256, (cuuint64_t)rows};
+  cuuint64_t dims[2] = {(cuuint64_t)ld_words * 2, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld_words * 4};
   cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
@@ -334,11 +366,17 @@ bool g_xt_attr[64];
 
 extern "C" {
 
-// x [M, ld] fp32 (128 channels) -> out [M, 128] words: 64 words of bf16 hi pairs | 64 words of bf16 mid pairs per row
-int di_planar_split_f32(const float* x, int ld, void* out, int M, cudaStream_t stream) {
-  DI_CHECK_ARG(x && out && M > 0 && ld >= 128, "di_planar_split_f32: bad argument");
-  planar_split_kernel<<<di_cdiv((long long)M * 64, 256), 256, 0, stream>>>(x, ld, reinterpret_cast<uint32_t*>(out), M);
-  DI_CHECK_LAUNCH("di_planar_split_f32");
+// Operand planes of the tcgen05 cross attention.  q [M, ld] fp32 (128 channels, pre-scaled) -> qplanes [M, 192 words]
+// (bf16 hi | mid | lo); kv [Mk, ld_kv >= 256] fp32 (K | V) -> kplanes [Mk, 192 words], vplanes [Mk, 128 words] (hi | mid).
+int di_attn_planes_f32(const float* q, int ld_q, void* qplanes, int M, const float* kv, int ld_kv, void* kplanes,
+                       void* vplanes, long long Mk, cudaStream_t stream) {
+  DI_CHECK_ARG((q == nullptr || (qplanes && M > 0 && ld_q >= 128)) && (kv == nullptr || (kplanes && vplanes && Mk > 0 && ld_kv >= 256 &&
+               ld_kv % 2 == 0 && ((uintptr_t)kv & 7) == 0)), "di_attn_planes_f32: bad argument");
+  if (q) planes3_kernel<<<di_cdiv((long long)M * 64, 256), 256, 0, stream>>>(q, ld_q, reinterpret_cast<uint32_t*>(qplanes), M);
+  if (kv)
+    kv_planes_kernel<<<di_cdiv(Mk * 128, 256), 256, 0, stream>>>(kv, ld_kv, reinterpret_cast<uint32_t*>(kplanes),
+                                                                 reinterpret_cast<uint32_t*>(vplanes), Mk);
+  DI_CHECK_LAUNCH("di_attn_planes_f32");
   return DI_OK;
 }
 
@@ -353,17 +391,16 @@ int di_xattn_tc_splits(int B, int HW) {
   return n;
 }
 
-// q [B*P, 128 words] planar (pre-scaled queries), k / v: planar rows with a stride of ld_kv words ([B*HW] rows; K and V of
-// one GEMM output: v = k + 128 words), part: workspace (di_xattn_tc_splits), out [B*P, 128] fp32.  8 heads x 16 channels.
-int di_xattn_tc_f32(const void* q, const void* k, const void* v, int ld_kv, float* part, float* out, int B, int P, int HW,
-                    int heads, cudaStream_t stream) {
+// q [B*P, 192 words], k [B*HW, 192 words], v [B*HW, 128 words]: the planes of di_attn_planes_f32; part: workspace
+// (di_xattn_tc_splits), out [B*P, 128] fp32.  8 heads x 16 channels.
+int di_xattn_tc_f32(const void* q, const void* k, const void* v, float* part, float* out, int B, int P, int HW, int heads,
+                    cudaStream_t stream) {
   DI_CHECK_ARG(q && k && v && part && out && B > 0 && P > 0 && HW > 0, "di_xattn_tc_f32: bad argument");
   if (heads != 8 || P > 256) {
     di_set_error("di_xattn_tc_f32: supported configuration is 8 heads x 16 channels, P <= 256 (got heads=%d P=%d)", heads, P);
     return DI_ERR_UNSUPPORTED;
   }
-  DI_CHECK_ARG(ld_kv % 4 == 0 && ld_kv >= 128 && (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v) & 15) == 0,
-               "di_xattn_tc_f32: strides / alignment");
+  DI_CHECK_ARG((((uintptr_t)q | (uintptr_t)k | (uintptr_t)v) & 15) == 0, "di_xattn_tc_f32: operands must be 16-byte aligned");
   int devid = 0;
   cudaGetDevice(&devid);
   if (devid < 0 || devid >= 64) {
@@ -378,8 +415,8 @@ int di_xattn_tc_f32(const void* q, const void* k, const void* v, int ld_kv, floa
     g_xt_attr[devid] = true;
   }
   CUtensorMap mq, mk, mv;
-  if (!(make_rows_map(&mq, q, (long long)B * P, 128, 128) && make_rows_map(&mk, k, (long long)B * HW, ld_kv, XT_KEYS) &&
-        make_rows_map(&mv, v, (long long)B * HW, ld_kv, XT_KEYS))) {
+  if (!(make_rows_map(&mq, q, (long long)B * P, 192, 128) && make_rows_map(&mk, k, (long long)B * HW, 192, XT_KEYS) &&
+        make_rows_map(&mv, v, (long long)B * HW, 128, XT_KEYS))) {
     di_set_error("di_xattn_tc_f32: cuTensorMapEncodeTiled failed");
     return DI_ERR_LAUNCH;
   }

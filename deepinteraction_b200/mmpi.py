@@ -466,12 +466,10 @@ class DeepInteractionDecoder(nn.Module, LossMixin):
         q = self._mlp([a], wo, bo, res=q, ln=pk['norm1'])
         qc = self._mlp([q, qpe], *pk['cross_q'])
         w_kv, b_kv, ckv = pk['cross_kv']
+        kv = ops.linear([pts_conv.view(B * HW, C)], w_kv, b_kv, res=ckv, res_mod=HW)
         if ops.can_xattn_tc(P, C, H, B * HW):
-            # K / V projection with a planar bf16 hi|mid epilogue, then the tcgen05 attention kernel (xattn_tc.cu)
-            kv = ops.linear_split_tc([pts_conv.view(B * HW, C)], w_kv, b_kv, ckv, HW, 0, 3)
-            a = ops.xattn_tc(ops.planar_split(qc), kv, B, P, HW, H)
+            a = ops.xattn_tc(qc, kv, B, P, HW, H)                   # tcgen05 attention kernel (xattn_tc.cu)
         else:
-            kv = ops.linear([pts_conv.view(B * HW, C)], w_kv, b_kv, res=ckv, res_mod=HW)
             a = ops.cross_attn(qc, kv, B, P, HW, H)
         q = self._mlp([a], *pk['cross_out'], res=q, ln=pk['norm2'])
         f1w, f1b, f2w, f2b = pk['ffn']

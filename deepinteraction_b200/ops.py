@@ -753,53 +753,27 @@ def bev_sample_bwd(d_out, grid, V, bev_shape):
 
 
 # ---- tcgen05 query x BEV cross attention (csrc/xattn_tc.cu) ----------------------------------------------------------
-XATTN_TC = [os.environ.get('DI_B200_XATTN_TC', '0') != '0']   # off until verified on the GPU
+XATTN_TC = [os.environ.get('DI_B200_XATTN_TC', '1') != '0']   # tcgen05 query x BEV cross attention (xattn_tc.cu)
 
 
 def can_xattn_tc(P, C, heads, M_keys):
     return bool(XATTN_TC[0] and USE_TC[0] and C == 128 and heads == 8 and P <= 256 and M_keys >= TC_MIN_M[0])
 
 
-def planar_split(x):
-    """[M, 128] fp32 rows -> [M, 128] words: 64 words of bf16 hi pairs | 64 words of bf16 mid pairs."""
-    M = x.shape[0]
-    assert x.shape[1] == 128
-    out = torch.empty(M, 128, device=x.device, dtype=torch.float32)
-    p, ld = _rows(x)
-    _call('di_planar_split_f32', p, ld, _ptr(out), M, _stream(), nbytes=8 * x.numel())
-    return out
-
-
-def linear_split_tc(srcs, W, bias, res, res_mod, split_col0, split_kind):
-    """3xTF32 dense layer whose output columns >= split_col0 are written pre-split (kind 3: planar bf16 hi|mid)."""
-    srcs = list(srcs)
-    M, N = srcs[0].shape[0], W.shape[0]
-    assert isinstance(W, Weight) and all(s.shape[1] % 32 == 0 for s in srcs) and N % 128 == 0 and split_col0 % 128 == 0
-    a = []
-    for s in srcs:
-        _f32(s)
-        p, ld = _rows(s)
-        a += [p, ld, s.shape[1]]
-    while len(a) < 9:
-        a += [None, 0, 0]
-    out = torch.empty(M, N, device=W.w.device, dtype=torch.float32)
-    K = sum(s.shape[1] for s in srcs)
-    pr, ldr = (None, 0) if res is None else _rows(res)
-    if PROFILE[0] is not None:
-        _TAG[0] = ' M%d N%d K%d split' % (M, N, K)
-    _call('di_linear_tc_split_f32', *a, _ptr(W.hi), _ptr(W.lo), _ptr(bias), pr, ldr, res_mod, _ptr(out), N, M, N, ACT_NONE,
-          split_col0, split_kind, _stream(), nbytes=4 * (M * K + N * K + M * N + (0 if res is None else res.numel())),
-          flops=2 * M * N * K)
-    return out
-
-
-def xattn_tc(q_planar, kv_planar, B, P, HW, heads):
-    """q_planar [B*P, 128 words], kv_planar [B*HW, 256 words] (K planar | V planar) -> [B*P, 128] fp32."""
-    assert q_planar.is_contiguous() and kv_planar.is_contiguous() and kv_planar.shape == (B * HW, 256)
+def xattn_tc(q, kv, B, P, HW, heads):
+    """q [B*P, 128] fp32 (pre-scaled queries), kv [B*HW, 256] fp32 (K | V) -> softmax(q k^T) v per head, [B*P, 128] fp32:
+    operand planes (di_attn_planes_f32) + the tcgen05 attention kernel + the split merge."""
+    assert kv.is_contiguous() and kv.shape == (B * HW, 256) and q.shape == (B * P, 128)
+    dev_ = q.device
+    qp = torch.empty(B * P, 192, device=dev_, dtype=torch.float32)
+    kp = torch.empty(B * HW, 192, device=dev_, dtype=torch.float32)
+    vp = torch.empty(B * HW, 128, device=dev_, dtype=torch.float32)
+    pq, lq = _rows(q)
+    _call('di_attn_planes_f32', pq, lq, _ptr(qp), B * P, _ptr(kv), 256, _ptr(kp), _ptr(vp), B * HW, _stream(),
+          nbytes=4 * (kv.numel() + kp.numel() + vp.numel()), launches=2)
     nsplit = _lib.lib().di_xattn_tc_splits(B, HW)
-    part = torch.empty(B * heads * nsplit * 18 * P, device=q_planar.device, dtype=torch.float32)
-    out = torch.empty(B * P, 128, device=q_planar.device, dtype=torch.float32)
-    _call('di_xattn_tc_f32', _ptr(q_planar), _ptr(kv_planar), ctypes.c_void_p(kv_planar.data_ptr() + 512), 256, _ptr(part),
-          _ptr(out), B, P, HW, heads, _stream(), nbytes=4 * (kv_planar.numel() + 2 * q_planar.numel()),
-          flops=4 * B * P * HW * 128, launches=2)
+    part = torch.empty(B * heads * nsplit * 18 * P, device=dev_, dtype=torch.float32)
+    out = torch.empty(B * P, 128, device=dev_, dtype=torch.float32)
+    _call('di_xattn_tc_f32', _ptr(qp), _ptr(kp), _ptr(vp), _ptr(part), _ptr(out), B, P, HW, heads, _stream(),
+          nbytes=4 * (kp.numel() + vp.numel() + 2 * q.numel()), flops=4 * B * P * HW * 128, launches=2)
     return out

@@ -81,11 +81,6 @@ int di_linear_tcb_split_f32(const float* A0, int lda0, int K0, const float* A1, 
                             int lda2, int K2, const void* W_hi, const void* W_mid, const float* bias, const float* res,
                             int ldres, int res_mod, float* C, int ldc, int M, int N, int act, int split_col0,
                             int split_kind, cudaStream_t stream);
-/* the same output formats on the 3xTF32 product (K / V projection of the decoder's cross attention) */
-int di_linear_tc_split_f32(const float* A0, int lda0, int K0, const float* A1, int lda1, int K1, const float* A2, int lda2,
-                           int K2, const float* W_hi, const float* W_lo, const float* bias, const float* res, int ldres,
-                           int res_mod, float* C, int ldc, int M, int N, int act, int split_col0, int split_kind,
-                           cudaStream_t stream);
 int di_conv3x3_tc_f32(const float* x, const float* w_hi, const float* w_lo, const float* bias, float* y, int N, int Cin,
                       int H, int W, int Cout, int act, cudaStream_t stream);
 int di_conv3x3_tcb_f32(const float* x, const void* w_hi, const void* w_mid, const float* bias, float* y, int N, int Cin,
@@ -376,14 +371,15 @@ int di_gather_rows_masked_f32(const float* map, const int* cnt, const int* coors
                               cudaStream_t stream);
 
 /* ---- query x BEV cross attention on tcgen05 (models/utils/decoder_utils.py:101-103, 466-493; xattn_tc.cu)
- * q [B*P, 128 words] / k, v [B*HW rows, stride ld_kv words]: planar bf16 hi|mid operands (di_planar_split_f32 /
- * di_linear_tc_split_f32 kind 3; v = k + 128 words when both come from one [.., 256] GEMM output); queries pre-scaled by
- * head_dim^-0.5; part: float workspace of B * heads * di_xattn_tc_splits(B, HW) * 18 * P; out [B*P, 128] fp32.
- * 8 heads x 16 channels, P <= 256 (returns -3 otherwise: use di_cross_attn_f32). */
-int di_planar_split_f32(const float* x, int ld, void* out, int M, cudaStream_t stream);
+ * di_attn_planes_f32: fp32 rows -> bf16 operand planes (queries, pre-scaled by head_dim^-0.5, and keys: hi | mid | lo = 192
+ * words per row; values: hi | mid = 128 words); either input may be NULL.  di_xattn_tc_f32: part = float workspace of
+ * B * heads * di_xattn_tc_splits(B, HW) * 18 * P; out [B*P, 128] fp32.  8 heads x 16 channels, P <= 256 (returns -3
+ * otherwise: use di_cross_attn_f32). */
+int di_attn_planes_f32(const float* q, int ld_q, void* qplanes, int M, const float* kv, int ld_kv, void* kplanes,
+                       void* vplanes, long long Mk, cudaStream_t stream);
 int di_xattn_tc_splits(int B, int HW);
-int di_xattn_tc_f32(const void* q, const void* k, const void* v, int ld_kv, float* part, float* out, int B, int P, int HW,
-                    int heads, cudaStream_t stream);
+int di_xattn_tc_f32(const void* q, const void* k, const void* v, float* part, float* out, int B, int P, int HW, int heads,
+                    cudaStream_t stream);
 
 #ifdef __cplusplus
 }
