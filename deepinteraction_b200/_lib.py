@@ -86,6 +86,7 @@ SIGNATURES = {
     'di_win_softmax_bwd_f32': [_p, _p, _p, _ll, _i, _f, _p],
     'di_relu_bwd_f32': [_p, _p, _p, _ll, _p],
     'di_col_sum_f32': [_p, _i, _ll, _i, _p, _p, _p],
+    'di_shift_map_f32': [_p, _p, _i, _i, _i, _i, _i, _i, _p],
     'di_match_cost_f32': [_p, _i, _p, _i, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p],
     'di_hungarian_f32': [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p],
     'di_loss_targets_f32': [_p, _p, _p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],

@@ -164,8 +164,7 @@ def encoder_backward(enc, img_feats, pts_feats, img_metas, pts_metas, d_img, d_p
     [B, Y, X, C]: gradients of the three outputs (pixel-major; None = zero).
     -> dict(d_img_feats [B*V, h, w, Ci], d_pts_feats [B, Y, X, Cp] (pixel-major), layers = per encoder layer the folded
     parameter gradients: i2p (dM1, dc1, dM2, dc2), p_iml / p2i / i_iml (lcab_backward dicts), p_fuse / i_fuse (dW [C, 3C], db)).
-    The forward is re-run eagerly with its intermediates kept; weight gradients of the two 3x3 shared convolutions are not
-    produced (input gradients are)."""
+    shared_conv = dict(img / pts -> (dW [C, Cin, 3, 3], db)).  The forward is re-run eagerly with its intermediates kept."""
     with _precise():
         return _encoder_backward(enc, img_feats, pts_feats, img_metas, pts_metas, d_img, d_pts_conv, d_pts)
 
@@ -239,7 +238,20 @@ def _encoder_backward(enc, img_feats, pts_feats, img_metas, pts_metas, d_img, d_
     wtp = _conv3x3_transposed(pk['shared_conv_pts'][0], Cp, dev)
     d_img_feats = ops.conv3x3(gi.view(BV, h, w, C), wti, None, cout=Ci, x_nhwc=True)
     d_pts_feats = ops.conv3x3(gp.view(B, Y, X, C), wtp, None, cout=Cp, x_nhwc=True)
-    return dict(d_img_feats=d_img_feats, d_pts_feats=d_pts_feats, layers=layer_grads)
+
+    def conv_wgrad(x_nchw, g_rows, n, hh, ww):
+        """dW [Cout, Cin, 3, 3] and db of a 3x3 convolution: per tap a split-K product of the output gradient with the shifted
+        input (dW[co, ci, ky, kx] = sum_p dY[p, co] X[p + (ky - 1, kx - 1), ci])."""
+        x_nhwc = ops.nchw_to_nhwc(x_nchw.contiguous())
+        cin = x_nhwc.shape[-1]
+        dw = torch.empty(C, cin, 3, 3, device=dev)
+        for ky in range(3):
+            for kx in range(3):
+                xs = ops.shift_map(x_nhwc, ky - 1, kx - 1).view(-1, cin)
+                dw[:, :, ky, kx] = _wgrad(g_rows, xs)
+        return dw, ops.col_sum(g_rows)
+    shared = dict(img=conv_wgrad(img_feats, gi, BV, h, w), pts=conv_wgrad(pts_feats, gp, B, Y, X))
+    return dict(d_img_feats=d_img_feats, d_pts_feats=d_pts_feats, layers=layer_grads, shared_conv=shared)
 
 
 class LCABFunction(torch.autograd.Function):

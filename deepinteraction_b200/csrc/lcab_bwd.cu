@@ -173,6 +173,19 @@ __global__ void col_sum_final_kernel(const float* __restrict__ part, int nblk, i
   out[c] = (float)s;
 }
 
+// out[n, y, x, :] = in[n, y + dy, x + dx, :] (zero outside the map): the shifted copies behind the weight gradient of a
+// 3x3 convolution (dW[co, tap, ci] = sum_p dY[p, co] X[p + tap, ci])
+__global__ void shift_map_kernel(const float4* __restrict__ in, float4* __restrict__ out, int N, int H, int W, int C4, int dy,
+                                 int dx) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N * H * W * C4) return;
+  const int c = (int)(i % C4);
+  const long long p = i / C4;
+  const int x = (int)(p % W), y = (int)((p / W) % H), n = (int)(p / ((long long)W * H));
+  const int yy = y + dy, xx = x + dx;
+  out[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? in[(((long long)n * H + yy) * W + xx) * C4 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
 template <int VEC>
 int launch_dot(const float* a, int lda, const float* b, int ldb, float* out, int N, int H, int W, int C, int ks, cudaStream_t st) {
   win_dot_kernel<VEC><<<di_cdiv((long long)N * H * W, 8), 256, 0, st>>>(a, lda, b, ldb, out, N, H, W, C, ks);
@@ -248,6 +261,17 @@ int di_relu_bwd_f32(const float* dy, const float* y, float* dx, long long n, cud
   DI_CHECK_ARG(dy && y && dx && n > 0 && ((((uintptr_t)dy | (uintptr_t)y | (uintptr_t)dx) & 15) == 0), "di_relu_bwd_f32: bad argument");
   relu_bwd_kernel<<<di_cdiv(di_cdiv(n, 4), 256), 256, 0, stream>>>(dy, y, dx, n);
   DI_CHECK_LAUNCH("di_relu_bwd_f32");
+  return DI_OK;
+}
+
+// out [N, H, W, C] = in shifted by (dy, dx) with zero fill (pixel-major maps, C % 4 == 0)
+int di_shift_map_f32(const float* in, float* out, int N, int H, int W, int C, int dy, int dx, cudaStream_t stream) {
+  DI_CHECK_ARG(in && out && N > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0 && ((((uintptr_t)in | (uintptr_t)out) & 15) == 0),
+               "di_shift_map_f32: bad argument");
+  const long long n4 = (long long)N * H * W * (C / 4);
+  shift_map_kernel<<<di_cdiv(n4, 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out), N,
+                                                        H, W, C / 4, dy, dx);
+  DI_CHECK_LAUNCH("di_shift_map_f32");
   return DI_OK;
 }
 

@@ -711,6 +711,15 @@ def relu_bwd(dy, y):
     return dx
 
 
+def shift_map(x_nhwc, dy, dx):
+    """out[n, y, x] = in[n, y + dy, x + dx] (zeros outside)."""
+    N, H, W, C = x_nhwc.shape
+    assert x_nhwc.is_contiguous()
+    out = torch.empty_like(x_nhwc)
+    _call('di_shift_map_f32', _ptr(x_nhwc), _ptr(out), N, H, W, C, dy, dx, _stream(), nbytes=8 * x_nhwc.numel())
+    return out
+
+
 def col_sum(x):
     M, C = x.shape
     p, ld = _rows(x)

@@ -358,6 +358,8 @@ int di_win_softmax_bwd_f32(const float* A, const float* dA, float* dS, long long
 /* ReLU backward from the saved output; column sums of a [M, C] matrix (bias gradients; work: float [256 * C]) */
 int di_relu_bwd_f32(const float* dy, const float* y, float* dx, long long n, cudaStream_t stream);
 int di_col_sum_f32(const float* x, int ld, long long M, int C, float* work, float* out, cudaStream_t stream);
+/* zero-filled shift of a pixel-major map (weight gradient of the 3x3 shared convolutions) */
+int di_shift_map_f32(const float* in, float* out, int N, int H, int W, int C, int dy, int dx, cudaStream_t stream);
 
 /* ---- I2P backward (SURVEY.md 8(b) `di_i2p_backward`; host composition: deepinteraction_b200/backward.py i2p_backward)
  * gradient of di_i2p_attend_f32 (models/utils/encoder_utils.py:281-311): ds [P,C] -> dqk [P,C], d_img += (atomic) */

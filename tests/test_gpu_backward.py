@@ -190,3 +190,8 @@ def test_encoder_backward_matches_oracle_autograd():
     assert rel_err(dW.cpu() * scale[:, None], vp.conv.weight.grad[:, :, 0, 0]) < tol
     assert rel_err(db.cpu(), vp.bn.bias.grad) < tol
     assert rel_err(r['layers'][1]['i2p'][3].cpu(), blk.I2P_block.learnedAlign.out_proj.bias.grad) < tol
+    # the two 3x3 shared convolutions (weights and biases)
+    for name, conv in (('img', m.shared_conv_img), ('pts', m.shared_conv_pts)):
+        dW, db = r['shared_conv'][name]
+        assert rel_err(dW.cpu(), conv.weight.grad) < tol, name
+        assert rel_err(db.cpu(), conv.bias.grad) < tol, name
