@@ -933,7 +933,8 @@ roi_align_kernel(const float* __restrict__ maps, const float* __restrict__ rois,
 // ------------------------------------------------------------------------------------------------
 constexpr int DC = 128, DR = 49;
 
-__global__ void __launch_bounds__(256)
+constexpr int DYN_T = 512;       // 16 warps: rows ty, ty + 16, ... per thread (the product loop is latency-bound at 8 warps)
+__global__ void __launch_bounds__(DYN_T)
 dynconv_kernel(const float* __restrict__ roi, const float* __restrict__ params, const float* __restrict__ g1,
                const float* __restrict__ b1, const float* __restrict__ g2, const float* __restrict__ b2,
                float* __restrict__ out, float eps) {
@@ -941,30 +942,57 @@ dynconv_kernel(const float* __restrict__ roi, const float* __restrict__ params, 
   float(*F)[DC] = reinterpret_cast<float(*)[DC]>(dyn_smem);
   float(*T)[DC] = reinterpret_cast<float(*)[DC]>(dyn_smem + DR * DC);
   const int qn = blockIdx.x, t = threadIdx.x;
+  // the query's two 128 x 128 parameter matrices (128 KB, written by the generator GEMM just before) are pulled into
+  // shared memory with cp.async while the RoI tile loads: reading them with dependent __ldg batches inside the product
+  // loop left the kernel latency-bound (57 us for 26 MB)
+  float* PS = dyn_smem + 2 * DR * DC;                    // [2][DC][DC]
+  {
+    const float* psrc = params + (size_t)qn * 2 * DC * DC;
+    for (int l = 0; l < 2; ++l) {
+      for (int i = t * 4; i < DC * DC; i += DYN_T * 4)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tc::smem_u32(PS + l * DC * DC + i)), "l"(psrc + l * DC * DC + i)
+                     : "memory");
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+  }
   const float* src = roi + (size_t)qn * DR * DC;
   for (int i = t; i < DR * DC / 4; i += blockDim.x)
     reinterpret_cast<float4*>(&F[0][0])[i] = ldg4(src + i * 4);
+  asm volatile("cp.async.wait_group 1;" ::: "memory");
   __syncthreads();
-  const int d = t & (DC - 1), half = t >> 7;  // rows half, half+2, ...
-  constexpr int NR = (DR + 1) / 2;            // 25
+  // register tile: thread = 4 output columns (4 tx .. 4 tx + 3) x the rows ty, ty + 16, ... (4 rows); per 4 input channels
+  // 4 parameter loads (float4) and 4 broadcast activation loads feed 64 FMAs (the one-column mapping spent one
+  // 16-byte shared-memory load per 4 FMAs and was bound by the shared-memory pipe).  Accumulation order over c unchanged.
+  const int tx = t & 31, ty = t >> 5;
+  constexpr int NW = DYN_T / 32;
+  constexpr int NR = (DR + NW - 1) / NW;      // 4
   for (int layer = 0; layer < 2; ++layer) {
-    const float* Pm = params + (size_t)qn * 2 * DC * DC + (size_t)layer * DC * DC;  // [c][d]
+    if (layer == 1) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+    }
+    const float* Pm = PS + layer * DC * DC;               // [c][d] in shared memory
     float(*X)[DC] = layer == 0 ? F : T;
-    float acc[NR];
+    float4 acc[NR];
 #pragma unroll
-    for (int i = 0; i < NR; ++i) acc[i] = 0.f;
+    for (int i = 0; i < NR; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
     for (int c = 0; c < DC; c += 4) {
-      float p0 = __ldg(Pm + (size_t)(c + 0) * DC + d), p1 = __ldg(Pm + (size_t)(c + 1) * DC + d);
-      float p2 = __ldg(Pm + (size_t)(c + 2) * DC + d), p3 = __ldg(Pm + (size_t)(c + 3) * DC + d);
+      const float4 p0 = *reinterpret_cast<const float4*>(Pm + (c + 0) * DC + 4 * tx), p1 = *reinterpret_cast<const float4*>(Pm + (c + 1) * DC + 4 * tx);
+      const float4 p2 = *reinterpret_cast<const float4*>(Pm + (c + 2) * DC + 4 * tx), p3 = *reinterpret_cast<const float4*>(Pm + (c + 3) * DC + 4 * tx);
 #pragma unroll
       for (int i = 0; i < NR; ++i) {
-        int r = half + 2 * i;
+        const int r = ty + NW * i;
         if (r < DR) {
-          float4 x = *reinterpret_cast<const float4*>(&X[r][c]);
-          acc[i] = fmaf(x.x, p0, acc[i]);
-          acc[i] = fmaf(x.y, p1, acc[i]);
-          acc[i] = fmaf(x.z, p2, acc[i]);
-          acc[i] = fmaf(x.w, p3, acc[i]);
+          const float4 x = *reinterpret_cast<const float4*>(&X[r][c]);
+          acc[i].x = fmaf(x.x, p0.x, acc[i].x); acc[i].y = fmaf(x.x, p0.y, acc[i].y);
+          acc[i].z = fmaf(x.x, p0.z, acc[i].z); acc[i].w = fmaf(x.x, p0.w, acc[i].w);
+          acc[i].x = fmaf(x.y, p1.x, acc[i].x); acc[i].y = fmaf(x.y, p1.y, acc[i].y);
+          acc[i].z = fmaf(x.y, p1.z, acc[i].z); acc[i].w = fmaf(x.y, p1.w, acc[i].w);
+          acc[i].x = fmaf(x.z, p2.x, acc[i].x); acc[i].y = fmaf(x.z, p2.y, acc[i].y);
+          acc[i].z = fmaf(x.z, p2.z, acc[i].z); acc[i].w = fmaf(x.z, p2.w, acc[i].w);
+          acc[i].x = fmaf(x.w, p3.x, acc[i].x); acc[i].y = fmaf(x.w, p3.y, acc[i].y);
+          acc[i].z = fmaf(x.w, p3.z, acc[i].z); acc[i].w = fmaf(x.w, p3.w, acc[i].w);
         }
       }
     }
@@ -972,8 +1000,8 @@ dynconv_kernel(const float* __restrict__ roi, const float* __restrict__ params, 
     float(*Y)[DC] = layer == 0 ? T : F;
 #pragma unroll
     for (int i = 0; i < NR; ++i) {
-      int r = half + 2 * i;
-      if (r < DR) Y[r][d] = acc[i];
+      const int r = ty + NW * i;
+      if (r < DR) *reinterpret_cast<float4*>(&Y[r][4 * tx]) = acc[i];
     }
     __syncthreads();
     // LayerNorm over d + ReLU, one warp per row
@@ -1378,14 +1406,15 @@ int di_roi_align_f32(const float* maps, const float* rois, float* out, int n, in
 // roi [n,49,128]; params [n, 2*128*128]; out [n, 49*128]
 int di_dynconv_f32(const float* roi, const float* params, const float* g1, const float* b1, const float* g2,
                    const float* b2, float* out, int n, float eps, cudaStream_t stream) {
-  DI_CHECK_ARG(roi && params && g1 && b1 && g2 && b2 && out && n > 0, "di_dynconv_f32: bad argument");
-  const int smem = 2 * DR * DC * (int)sizeof(float);
+  DI_CHECK_ARG(roi && params && g1 && b1 && g2 && b2 && out && n > 0 && (((uintptr_t)params | (uintptr_t)roi) & 15) == 0,
+               "di_dynconv_f32: bad argument");
+  const int smem = (2 * DR * DC + 2 * DC * DC) * (int)sizeof(float);
   static DiSmemOnce once{};
   if (!di_smem_once(once, dynconv_kernel, smem)) {
     di_set_error("di_dynconv_f32: cannot reserve shared memory");
     return DI_ERR_LAUNCH;
   }
-  dynconv_kernel<<<n, 256, smem, stream>>>(roi, params, g1, b1, g2, b2, out, eps);
+  dynconv_kernel<<<n, DYN_T, smem, stream>>>(roi, params, g1, b1, g2, b2, out, eps);
   DI_CHECK_LAUNCH("di_dynconv_f32");
   return DI_OK;
 }
