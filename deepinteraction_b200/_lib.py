@@ -88,6 +88,7 @@ SIGNATURES = {
     'di_col_sum_f32': [_p, _i, _ll, _i, _p, _p, _p],
     'di_shift_map_f32': [_p, _p, _i, _i, _i, _i, _i, _i, _p],
     'di_match_cost_f32': [_p, _i, _p, _i, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p],
+    'di_heuristic_assign_f32': [_p, _i, _i, _p, _p, _i, _p, _f, _p, _p, _p, _p, _p],
     'di_hungarian_f32': [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p],
     'di_loss_targets_f32': [_p, _p, _p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     'di_gaussian_heatmap_f32': [_p, _i, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p],

@@ -417,6 +417,46 @@ __global__ void loss_finish_kernel(const double* __restrict__ hpart, const doubl
   out[1 + 2 * L] = (float)(m / (double)B);
 }
 
+// HeuristicAssigner3D.assign (hungarian_assigner.py:60-91): every ground-truth box claims its nearest prediction (BEV centre
+// distance, + dist_thre when the query's class differs); a prediction claimed twice keeps the nearer box (ties: the earlier
+// box, the reference's strict `<`).  One CTA; P, G small.
+__global__ void __launch_bounds__(256)
+heuristic_assign_kernel(const float* __restrict__ boxes, int nb, int P, const float* __restrict__ gt, const int* __restrict__ gt_labels,
+                        int G, const int* __restrict__ query_labels, float dist_thre, long long* __restrict__ gt_inds,
+                        float* __restrict__ overlaps, float* __restrict__ labels, int* __restrict__ nearest, float* __restrict__ ndist) {
+  for (int i = threadIdx.x; i < P; i += blockDim.x) { gt_inds[i] = 0; overlaps[i] = 0.f; labels[i] = -1.f; }
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    const float gx = gt[(size_t)g * nb], gy = gt[(size_t)g * nb + 1];
+    float best = INFINITY;
+    int arg = 0;
+    for (int i = 0; i < P; ++i) {
+      const float dx = boxes[(size_t)i * nb] - gx, dy = boxes[(size_t)i * nb + 1] - gy;
+      float d = sqrtf(dx * dx + dy * dy);
+      if (query_labels && query_labels[i] != gt_labels[g]) d += dist_thre;
+      if (d < best) { best = d; arg = i; }           // torch.min: first minimum
+    }
+    nearest[g] = arg;
+    ndist[g] = best;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int g = 0; g < G; ++g) {
+      const int i = nearest[g];
+      const float d = ndist[g];
+      if (d <= dist_thre && (gt_inds[i] == 0 || d < overlaps[i])) {   // overlaps[] holds the claimed distance for now
+        overlaps[i] = d;
+        gt_inds[i] = g + 1;
+        labels[i] = (float)gt_labels[g];
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    const long long gi = gt_inds[i];
+    overlaps[i] = gi > 0 ? iou3d(gt + (size_t)(gi - 1) * nb, boxes + (size_t)i * nb) : 0.f;
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -435,6 +475,19 @@ int di_match_cost_f32(const float* boxes, int nb, const float* score, int K, con
   dim3 grid(di_cdiv(LP, 128), Gmax, B);
   match_cost_kernel<<<grid, 128, 0, stream>>>(boxes, nb, score, K, gt, gt_labels, n_gt, Gmax, LP, cp, cost, iou);
   DI_CHECK_LAUNCH("di_match_cost_f32");
+  return DI_OK;
+}
+
+// boxes [P, nb] predictions, gt [G, nb], gt_labels [G] int32, query_labels [P] int32 or NULL; work: int32 [G] + float [G];
+// -> gt_inds [P] int64 (0 = unassigned, g + 1), max_overlaps [P] (3-D IoU of the matched pairs), labels [P] float (-1 unassigned)
+int di_heuristic_assign_f32(const float* boxes, int nb, int P, const float* gt, const int* gt_labels, int G,
+                            const int* query_labels, float dist_thre, long long* gt_inds, float* max_overlaps, float* labels,
+                            void* work, cudaStream_t stream) {
+  DI_CHECK_ARG(boxes && gt && gt_labels && gt_inds && max_overlaps && labels && work && P > 0 && G > 0 && nb >= 7,
+               "di_heuristic_assign_f32: bad argument");
+  heuristic_assign_kernel<<<1, 256, 0, stream>>>(boxes, nb, P, gt, gt_labels, G, query_labels, dist_thre, gt_inds, max_overlaps,
+                                               labels, reinterpret_cast<int*>(work), reinterpret_cast<float*>(work) + G);
+  DI_CHECK_LAUNCH("di_heuristic_assign_f32");
   return DI_OK;
 }
 

@@ -126,13 +126,27 @@ class HungarianAssigner3D:
 
 
 class HeuristicAssigner3D:
-    """Constructor-compatible holder for hungarian_assigner.py:50-91 (not used by the reference configs)."""
+    """Drop-in for hungarian_assigner.py:50-91 (di_heuristic_assign_f32): every ground-truth box claims its nearest prediction
+    (BEV distance, same-class constraint when query_labels is given); returns (gt_inds int64, max_overlaps, labels float) --
+    the fields of mmdet's AssignResult."""
 
     def __init__(self, dist_thre=100, iou_calculator=dict(type='BboxOverlaps3D')):
         self.dist_thre = dist_thre
 
-    def assign(self, *a, **k):
-        raise NotImplementedError('HeuristicAssigner3D.assign is not provided (both reference configs use HungarianAssigner3D)')
+    def assign(self, bboxes, gt_bboxes, gt_bboxes_ignore=None, gt_labels=None, query_labels=None):
+        P, G, dev = bboxes.shape[0], gt_bboxes.shape[0], bboxes.device
+        gt_inds = torch.zeros(P, device=dev, dtype=torch.int64)
+        overlaps = torch.zeros(P, device=dev, dtype=torch.float32)
+        labels = torch.full((P,), -1.0, device=dev, dtype=torch.float32)
+        if P == 0 or G == 0:
+            return gt_inds, overlaps, labels
+        b, g = bboxes.contiguous().float(), gt_bboxes.to(dev).contiguous().float()
+        gl = gt_labels.to(dev, torch.int32).contiguous()
+        ql = None if query_labels is None else query_labels.to(dev, torch.int32).contiguous()
+        work = torch.empty(2 * G, device=dev, dtype=torch.int32)
+        ops._call('di_heuristic_assign_f32', ops._ptr(b), b.shape[1], P, ops._ptr(g), ops._ptr(gl), G, ops._ptr(ql),
+                  float(self.dist_thre), ops._ptr(gt_inds), ops._ptr(overlaps), ops._ptr(labels), ops._ptr(work), ops._stream())
+        return gt_inds, overlaps, labels
 
 
 ASSIGNERS = dict(HungarianAssigner3D=HungarianAssigner3D, HeuristicAssigner3D=HeuristicAssigner3D)

@@ -325,6 +325,10 @@ int di_match_cost_f32(const float* boxes, int nb, const float* score, int K, con
 /* hungarian_assigner.py:132-149 (scipy linear_sum_assignment on the CPU in the reference): one warp per (sample, layer) */
 int di_hungarian_f32(const float* cost, const float* iou, const int* n_gt, int B, int L, int P, int Gmax, long long* gt_inds,
                      float* max_overlaps, cudaStream_t stream);
+/* HeuristicAssigner3D.assign (hungarian_assigner.py:60-91); work: int32 [G] + float [G] */
+int di_heuristic_assign_f32(const float* boxes, int nb, int P, const float* gt, const int* gt_labels, int G,
+                            const int* query_labels, float dist_thre, long long* gt_inds, float* max_overlaps, float* labels,
+                            void* work, cudaStream_t stream);
 /* models/dense_heads/deepinteraction_decoder.py:400-441 (+ the on-image mask products of :501-509) */
 int di_loss_targets_f32(const long long* gt_inds, const float* max_overlaps, const float* gt, const int* gt_labels, int Gmax,
                         const unsigned char* mask, int mask_mode, int B, int L, int P, int nb, int code, int num_classes,

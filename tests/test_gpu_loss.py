@@ -58,6 +58,25 @@ def test_match_cost_and_iou_match_oracle():
     assert torch.equal(gi.cpu(), r.gt_inds) and torch.equal(lab.cpu(), r.labels)
 
 
+@pytest.mark.parametrize('with_labels', [False, True])
+def test_heuristic_assigner_matches_oracle(with_labels):
+    import oracle.loss as ol
+    from deepinteraction_b200 import loss as L
+    g = torch.Generator().manual_seed(13)
+    P, G = 120, 25
+    pred = _random_boxes(P, g, 30.0)
+    gt = torch.cat([_random_boxes(G - 6, g, 30.0), pred[:6] + 0.3 * torch.randn(6, 9, generator=g)], 0)
+    gt[:, 3:6] = gt[:, 3:6].abs() + 0.5
+    gt[3, :2] = gt[2, :2] + 0.01                       # two boxes compete for one prediction
+    gl = torch.randint(0, 4, (G,), generator=g)
+    ql = torch.randint(0, 4, (P,), generator=g) if with_labels else None
+    ref = ol.HeuristicAssigner3D(dist_thre=20).assign(pred, gt, None, gl, ql)
+    gi, ov, lab = L.HeuristicAssigner3D(dist_thre=20).assign(pred.to(dev()), gt.to(dev()), None, gl.to(dev()),
+                                                              None if ql is None else ql.to(dev()))
+    assert torch.equal(gi.cpu(), ref.gt_inds) and torch.equal(lab.cpu(), ref.labels.float())
+    assert float((ov.cpu() - ref.max_overlaps).abs().max()) < 2e-6 and int((gi > 0).sum()) > 5
+
+
 @pytest.mark.parametrize('P,Gs', [(200, (37, 0, 1)), (24, (24, 30, 5)), (300, (120, 299, 300)), (7, (3, 7, 12))])
 def test_hungarian_matches_scipy(P, Gs):
     """Rectangular assignment problems of every orientation (fewer / as many / more ground-truth boxes than proposals, one,
