@@ -615,7 +615,7 @@ def main():
                     help='plusplus workload: run DeepInteractionPlusPlusDecoder after the ++ encoder (default: encoder only, '
                          'as BASELINE.json config 4 is quoted)')
     ap.add_argument('--profile-steps', type=int, default=3)
-    ap.add_argument('--inflight', type=int, default=3, help='independent frames in flight per GPU (CUDA streams)')
+    ap.add_argument('--inflight', type=int, default=5, help='independent frames in flight per GPU (CUDA streams)')
     ap.add_argument('--frames', type=int, default=9, help='distinct synthetic frames (different point / pillar counts) cycled '
                     'through the timed regions, each in its own device buffers')
     args = ap.parse_args()

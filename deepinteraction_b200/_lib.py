@@ -87,6 +87,10 @@ SIGNATURES = {
     'di_relu_bwd_f32': [_p, _p, _p, _ll, _p],
     'di_col_sum_f32': [_p, _i, _ll, _i, _p, _p, _p],
     'di_shift_map_f32': [_p, _p, _i, _i, _i, _i, _i, _i, _p],
+    # bn_train.cu
+    'di_bn_stats_f32': [_p, _ll, _i, _p, _p, _p, _p, _p, _f, _p],
+    'di_bn_apply_f32': [_p, _ll, _i, _p, _p, _p, _p, _f, _i, _p, _p],
+    'di_bn_bwd_f32': [_p, _p, _p, _ll, _i, _p, _p, _p, _f, _p, _p, _p, _p, _p],
     'di_match_cost_f32': [_p, _i, _p, _i, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p],
     'di_heuristic_assign_f32': [_p, _i, _i, _p, _p, _i, _p, _f, _p, _p, _p, _p, _p],
     'di_hungarian_f32': [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p],

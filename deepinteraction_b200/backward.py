@@ -157,6 +157,19 @@ def _conv3x3_transposed(w_packed, cin, device):
     return fold.Weight(wt.contiguous(), device)
 
 
+def conv3x3_wgrad(x_nchw, g_rows, cout):
+    """dW [Cout, Cin, 3, 3] and db of a 3x3 convolution: per tap a split-K product of the output gradient with the shifted
+    input (dW[co, ci, ky, kx] = sum_p dY[p, co] X[p + (ky - 1, kx - 1), ci])."""
+    x_nhwc = ops.nchw_to_nhwc(x_nchw.contiguous())
+    cin = x_nhwc.shape[-1]
+    dw = torch.empty(cout, cin, 3, 3, device=x_nchw.device)
+    for ky in range(3):
+        for kx in range(3):
+            xs = ops.shift_map(x_nhwc, ky - 1, kx - 1).view(-1, cin)
+            dw[:, :, ky, kx] = _wgrad(g_rows, xs)
+    return dw, ops.col_sum(g_rows)
+
+
 def encoder_backward(enc, img_feats, pts_feats, img_metas, pts_metas, d_img, d_pts_conv, d_pts):
     """Backward of DeepInteractionEncoder.forward (base model, hidden width 128, BatchNorm in eval mode = the folded
     weights of the forward; reference deepinteraction_encoder.py:8-85).  img_feats (B*V, Ci, h, w), pts_feats
@@ -239,18 +252,7 @@ def _encoder_backward(enc, img_feats, pts_feats, img_metas, pts_metas, d_img, d_
     d_img_feats = ops.conv3x3(gi.view(BV, h, w, C), wti, None, cout=Ci, x_nhwc=True)
     d_pts_feats = ops.conv3x3(gp.view(B, Y, X, C), wtp, None, cout=Cp, x_nhwc=True)
 
-    def conv_wgrad(x_nchw, g_rows, n, hh, ww):
-        """dW [Cout, Cin, 3, 3] and db of a 3x3 convolution: per tap a split-K product of the output gradient with the shifted
-        input (dW[co, ci, ky, kx] = sum_p dY[p, co] X[p + (ky - 1, kx - 1), ci])."""
-        x_nhwc = ops.nchw_to_nhwc(x_nchw.contiguous())
-        cin = x_nhwc.shape[-1]
-        dw = torch.empty(C, cin, 3, 3, device=dev)
-        for ky in range(3):
-            for kx in range(3):
-                xs = ops.shift_map(x_nhwc, ky - 1, kx - 1).view(-1, cin)
-                dw[:, :, ky, kx] = _wgrad(g_rows, xs)
-        return dw, ops.col_sum(g_rows)
-    shared = dict(img=conv_wgrad(img_feats, gi, BV, h, w), pts=conv_wgrad(pts_feats, gp, B, Y, X))
+    shared = dict(img=conv3x3_wgrad(img_feats, gi, C), pts=conv3x3_wgrad(pts_feats, gp, C))
     return dict(d_img_feats=d_img_feats, d_pts_feats=d_pts_feats, layers=layer_grads, shared_conv=shared)
 
 

@@ -729,6 +729,41 @@ def col_sum(x):
     return out
 
 
+# ---- train-mode BatchNorm over rows (csrc/bn_train.cu; composition in train.py) ----------------------------------------
+def bn_stats(y, run_mean=None, run_var=None, momentum=0.1):
+    """y [M, C] -> (mean [C], biased var [C]); running statistics updated in place when given."""
+    M, C = y.shape
+    assert y.is_contiguous()
+    work = torch.empty(592 * C * 3, device=y.device, dtype=torch.float32)
+    mean = torch.empty(C, device=y.device, dtype=torch.float32)
+    var = torch.empty(C, device=y.device, dtype=torch.float32)
+    _call('di_bn_stats_f32', _ptr(y), M, C, _ptr(work), _ptr(mean), _ptr(var), _ptr(run_mean), _ptr(run_var), float(momentum),
+          _stream(), nbytes=4 * M * C, launches=2)
+    return mean, var
+
+
+def bn_apply(y, mean, var, gamma, beta, eps, relu):
+    M, C = y.shape
+    assert y.is_contiguous()
+    z = torch.empty_like(y)
+    _call('di_bn_apply_f32', _ptr(y), M, C, _ptr(mean), _ptr(var), _ptr(gamma), _ptr(beta), float(eps), int(relu), _ptr(z),
+          _stream(), nbytes=8 * M * C)
+    return z
+
+
+def bn_bwd(dz, z, y, mean, var, gamma, eps):
+    """-> (dy [M, C], dgamma [C], dbeta [C]); z = the saved output when the layer ends in ReLU, else None."""
+    M, C = y.shape
+    assert y.is_contiguous() and dz.is_contiguous() and (z is None or z.is_contiguous())
+    work = torch.empty(592 * C * 2, device=y.device, dtype=torch.float32)
+    dy = torch.empty_like(y)
+    dg = torch.empty(C, device=y.device, dtype=torch.float32)
+    db = torch.empty(C, device=y.device, dtype=torch.float32)
+    _call('di_bn_bwd_f32', _ptr(dz), _ptr(z), _ptr(y), M, C, _ptr(mean), _ptr(var), _ptr(gamma), float(eps), _ptr(work), _ptr(dy),
+          _ptr(dg), _ptr(db), _stream(), nbytes=4 * M * C * 7, launches=3)
+    return dy, dg, db
+
+
 def i2p_attend_bwd(qk, ds, pillars, npts, coors, proj, img_nhwc, d_img, V, in_hw):
     """Gradient of i2p_attend: -> dqk [P, C]; d_img (same shape as img_nhwc) is accumulated into."""
     P, C = qk.shape

@@ -365,6 +365,20 @@ int di_col_sum_f32(const float* x, int ld, long long M, int C, float* work, floa
 /* zero-filled shift of a pixel-major map (weight gradient of the 3x3 shared convolutions) */
 int di_shift_map_f32(const float* in, float* out, int N, int H, int W, int C, int dy, int dx, cudaStream_t stream);
 
+/* ---- train-mode BatchNorm over pixel-major rows (csrc/bn_train.cu) -------------------------------------------------------
+ * models/utils/encoder_utils.py:11-34 (ConvBNReLU with nn.BatchNorm2d in training mode; every norm of the encoder follows a
+ * 1x1 convolution, so its input is a [M = N*H*W, C] row matrix).  di_bn_stats_f32: batch mean / biased variance, optional
+ * in-place update of the running statistics (momentum, unbiased variance); work: float [592 * C * 3].
+ * di_bn_apply_f32: z = act((y - mean) / sqrt(var + eps) * gamma + beta), gamma / beta NULL = affine=False.
+ * di_bn_bwd_f32: dz, saved z (NULL = no ReLU), saved y -> dy, dgamma, dbeta incl. the gradient through the batch
+ * statistics; work: float [592 * C * 2]. */
+int di_bn_stats_f32(const float* y, long long M, int C, float* work, float* mean, float* var, float* run_mean, float* run_var,
+                    float momentum, cudaStream_t stream);
+int di_bn_apply_f32(const float* y, long long M, int C, const float* mean, const float* var, const float* gamma, const float* beta,
+                    float eps, int relu, float* z, cudaStream_t stream);
+int di_bn_bwd_f32(const float* dz, const float* z, const float* y, long long M, int C, const float* mean, const float* var,
+                  const float* gamma, float eps, float* work, float* dy, float* dgamma, float* dbeta, cudaStream_t stream);
+
 /* ---- I2P backward (SURVEY.md 8(b) `di_i2p_backward`; host composition: deepinteraction_b200/backward.py i2p_backward)
  * gradient of di_i2p_attend_f32 (models/utils/encoder_utils.py:281-311): ds [P,C] -> dqk [P,C], d_img += (atomic) */
 int di_i2p_attend_bwd_f32(const float* qk, const float* ds, const float* pillars, const int* npts, const int* coors,

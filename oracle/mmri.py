@@ -88,6 +88,8 @@ class LocalContextAttentionBlock(nn.Module):
 
     def forward(self, target, source, chunk=1):
         outs = []
+        if self.training:
+            chunk = target.shape[0]                     # batch statistics are over the whole call, as in the reference
         for i in range(0, target.shape[0], chunk):      # chunking only bounds CPU memory
             q = self.query_project(target[i:i + chunk])
             k = self.key_project(source[i:i + chunk])
