@@ -1,9 +1,12 @@
 #!/usr/bin/env python
 """Partial BASELINE config 3: forward + backward of the base MMRI ENCODER at the base shapes (6 x (256,112,200) camera maps,
-(512,180,180) BEV map, ~250k points), BatchNorm in eval mode, synthetic loss = sum of squared differences to fixed random
-targets on the three encoder outputs, parameter gradients all-reduced over the ranks with shard.GradBuckets (NCCL).  The
-decoder's backward, train-mode BatchNorm and the optimiser step are not built, so this is NOT the
-config-3 metric; it measures what exists: the encoder's training-side kernels and the path's one collective.
+(512,180,180) BEV map, ~250k points), synthetic loss = sum of squared differences to fixed random targets on the three
+encoder outputs, parameter gradients all-reduced over the ranks with shard.GradBuckets (NCCL).
+--bn eval: BatchNorm folded (backward.encoder_backward; gradients of the folded weights).
+--bn train: BatchNorm with batch statistics (train.encoder_train_step; gradients of the module's own parameters), followed by
+a torch.optim.AdamW step on the encoder's parameters (the reference's optimiser, configs/nuscenes/Fusion_0075_refactor.py).
+The decoder's backward and the I2P attention dropout are not built, so this is NOT the config-3 metric;
+it measures what exists: the encoder's training-side kernels and the path's one collective.
 
     python tools/train_encoder_step.py [--steps 5]                                    # 1 GPU
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 tools/train_encoder_step.py
@@ -36,6 +39,7 @@ def flat_grads(r):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--bn', default='eval', choices=['eval', 'train'])
     args = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (('RANK', 0), ('WORLD_SIZE', 1), ('LOCAL_RANK', 0)))
     torch.cuda.set_device(local)
@@ -65,6 +69,28 @@ def main():
             buckets.add(t)
         buckets.finish()
         return gl, buckets.launched
+    if args.bn == 'train':
+        from deepinteraction_b200 import train
+        neck.train()
+        params = dict(neck.named_parameters())
+        opt = torch.optim.AdamW(neck.parameters(), lr=1e-4, weight_decay=0.01)
+
+        def grad_fn(*outs):
+            zero = [torch.zeros_like(t) for t in outs]
+            return [ops.axpy(ops.axpy(z, t.contiguous(), two), tg, mtwo) for z, t, tg in zip(zero, outs, targets)]
+
+        def step():                                                      # noqa: F811
+            r = train.encoder_train_step(neck, fr['img_feats'], fr['pts_feats'], fr['img_metas'], fr['pts_metas'], grad_fn)
+            buckets = GradBuckets()
+            names = sorted(r['grads'])
+            gl = [r['grads'][n].contiguous() for n in names]
+            for t in gl:
+                buckets.add(t)
+            buckets.finish()
+            for n, t in zip(names, gl):
+                params[n].grad = t.view_as(params[n])
+            opt.step()
+            return gl, buckets.launched
     gl, launched = step()
     torch.cuda.synchronize()
     if world > 1:
@@ -82,8 +108,8 @@ def main():
         ms = float(t.item())
     if rank == 0:
         nbytes = sum(t.numel() * 4 for t in gl)
-        print(json.dumps(dict(metric='frames/sec MMRI encoder forward + backward + gradient all-reduce (partial config 3: eval-mode '
-                                     'BatchNorm, no decoder backward, no optimiser)', value=world * 1000.0 / ms, unit='frames/s',
+        print(json.dumps(dict(metric='frames/sec MMRI encoder forward + backward + gradient all-reduce%s (partial config 3: %s-mode '
+                                     'BatchNorm, no decoder backward)' % (' + AdamW step' if args.bn == 'train' else '', args.bn), value=world * 1000.0 / ms, unit='frames/s',
                               n_gpus=world, steps=args.steps, ms_per_step=ms, gradient_tensors=len(gl), gradient_bytes=nbytes,
                               allreduce_buckets=launched, finite=bool(all(torch.isfinite(t).all() for t in gl)))), flush=True)
     if world > 1:
