@@ -126,7 +126,7 @@ def _i2p_backward(i2p_pack, pts_nhwc, img_nhwc, pts_metas, proj, V, in_hw, grad_
         z = lambda t: torch.zeros_like(t.w if hasattr(t, 'w') else t)
         return dict(d_pts=d_pts, d_img=d_img, dM1=z(M1), dc1=z(c1), dM2=z(M2), dc2=z(c2))
     dev = pts_nhwc.device
-    T_ = lambda Wt: fold.Weight(Wt.w.detach().cpu().double().t().contiguous(), dev)
+    T_ = lambda Wt: fold.Weight(Wt.w.detach().t().contiguous(), dev, lazy=True)
     # forward intermediates
     rows = ops.gather_rows(pts_nhwc, coors)
     qk = ops.linear([rows], M1, c1)
@@ -144,17 +144,17 @@ def _i2p_backward(i2p_pack, pts_nhwc, img_nhwc, pts_metas, proj, V, in_hw, grad_
 
 
 def _t_weight(W, device):
-    return fold.Weight(W.w.detach().cpu().double().t().contiguous(), device)
+    return fold.Weight(W.w.detach().t().contiguous(), device, lazy=True)
 
 
 def _conv3x3_transposed(w_packed, cin, device):
     """Packed forward weight [Cout, (ky*3+kx)*Cin + ci] -> packed weight of the input-gradient convolution
     [Cin, (ky*3+kx)*Cout + co] with the taps flipped (d x = conv3x3(d y, W^T flipped))."""
-    w = w_packed.w.detach().cpu().double()
+    w = w_packed.w.detach()                                        # stays on the device: no host round trip
     cout = w.shape[0]
     w4 = w.view(cout, 3, 3, cin)                                   # co, ky, kx, ci
     wt = w4.flip(1, 2).permute(3, 1, 2, 0).reshape(cin, 9 * cout)   # ci, ky', kx', co
-    return fold.Weight(wt.contiguous(), device)
+    return fold.Weight(wt.contiguous(), device, lazy=True)
 
 
 def conv3x3_wgrad(x_nchw, g_rows, cout):

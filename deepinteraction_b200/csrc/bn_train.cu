@@ -10,41 +10,83 @@ namespace {
 constexpr int BN_BLOCKS = 592;   // 4 x 148 row blocks
 
 __device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+inline int bn_blocks(long long M) { return (int)(M < BN_BLOCKS ? M : BN_BLOCKS); }
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-// per row block and channel: n, mean, M2 (sum of squared deviations from the block mean; second pass re-reads the block from L1/L2)
+// Thread layout of the two column-reduction kernels: 256 threads = 32 float4 channel lanes (a 128-channel tile, blockIdx.y)
+// x 8 row lanes; a block owns a contiguous row chunk (blockIdx.x), every load is an independent 16-byte one.
+constexpr int BN_RL = 8;
+
+__device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
+// per row block and channel: n, mean, M2 (sum of squared deviations from the block mean).  One pass with the sums shifted by
+// the block's first row (a sample of the column, so |mean - pivot| ~ the spread and s2 - s1^2 / n does not cancel).
 __global__ void __launch_bounds__(256)
 bn_stats_part_kernel(const float* __restrict__ y, long long M, int C, float* __restrict__ part) {
-  const int c = blockIdx.y * 256 + threadIdx.x;
-  if (c >= C) return;
+  __shared__ float4 sh1[BN_RL][32], sh2[BN_RL][32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.y * 128 + tx * 4;
   const long long rows = (M + gridDim.x - 1) / gridDim.x, m0 = blockIdx.x * rows, m1 = min(M, m0 + rows);
-  float s = 0.f;
-  for (long long m = m0; m < m1; ++m) s += y[m * C + c];
-  const float n = (float)max(0LL, m1 - m0), mu = n > 0.f ? s / n : 0.f;
-  float q = 0.f;
-  for (long long m = m0; m < m1; ++m) {
-    const float d = y[m * C + c] - mu;
-    q = fmaf(d, d, q);
+  const bool on = c < C && m0 < m1;
+  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1, p = s1;
+  if (on) {
+    p = ld4(y + m0 * C + c);
+#pragma unroll 4
+    for (long long m = m0 + ty; m < m1; m += BN_RL) {
+      const float4 v = ld4(y + m * C + c);
+      const float dx = v.x - p.x, dy = v.y - p.y, dz = v.z - p.z, dw = v.w - p.w;
+      s1.x += dx; s1.y += dy; s1.z += dz; s1.w += dw;
+      s2.x = fmaf(dx, dx, s2.x); s2.y = fmaf(dy, dy, s2.y); s2.z = fmaf(dz, dz, s2.z); s2.w = fmaf(dw, dw, s2.w);
+    }
   }
-  float* o = part + ((size_t)blockIdx.x * C + c) * 3;
-  o[0] = n; o[1] = mu; o[2] = q;
+  sh1[ty][tx] = s1;
+  sh2[ty][tx] = s2;
+  __syncthreads();
+  if (ty != 0 || c >= C) return;
+  for (int r = 1; r < BN_RL; ++r) { s1 = f4_add(s1, sh1[r][tx]); s2 = f4_add(s2, sh2[r][tx]); }
+  const float n = (float)max(0LL, m1 - m0), inv = n > 0.f ? 1.f / n : 0.f;
+  const float a1[4] = {s1.x, s1.y, s1.z, s1.w}, a2[4] = {s2.x, s2.y, s2.z, s2.w}, pv[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float* o = part + ((size_t)blockIdx.x * C + c + k) * 3;
+    o[0] = n; o[1] = pv[k] + a1[k] * inv; o[2] = fmaxf(a2[k] - a1[k] * a1[k] * inv, 0.f);
+  }
 }
 
-// Chan's pairwise combination in double, fixed block order; optional running-statistics update (unbiased variance, momentum)
-__global__ void bn_stats_final_kernel(const float* __restrict__ part, int nblk, int C, long long M, float* __restrict__ mean,
-                                      float* __restrict__ var, float* __restrict__ run_mean, float* __restrict__ run_var,
-                                      float momentum) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// Chan's pairwise combination in double, one warp per channel: lane l folds blocks l, l + 32, ... in order, then a fixed
+// shuffle tree merges the 32 partial (n, mean, M2) triples -> deterministic.  Optional running-statistics update (unbiased
+// variance, momentum).
+__device__ __forceinline__ void chan_merge(double& n, double& mu, double& m2, double nb, double mub, double m2b) {
+  if (nb <= 0.0) return;
+  const double nn = n + nb, d = mub - mu;
+  mu += d * nb / nn;
+  m2 += m2b + d * d * n * nb / nn;
+  n = nn;
+}
+__global__ void __launch_bounds__(256)
+bn_stats_final_kernel(const float* __restrict__ part, int nblk, int C, long long M, float* __restrict__ mean,
+                      float* __restrict__ var, float* __restrict__ run_mean, float* __restrict__ run_var, float momentum) {
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (c >= C) return;
   double n = 0.0, mu = 0.0, m2 = 0.0;
-  for (int b = 0; b < nblk; ++b) {
+  for (int b = lane; b < nblk; b += 32) {
     const float* p = part + ((size_t)b * C + c) * 3;
-    const double nb = p[0];
-    if (nb <= 0.0) continue;
-    const double d = (double)p[1] - mu, nn = n + nb;
-    mu += d * nb / nn;
-    m2 += (double)p[2] + d * d * n * nb / nn;
-    n = nn;
+    chan_merge(n, mu, m2, (double)p[0], (double)p[1], (double)p[2]);
   }
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double nb = __shfl_xor_sync(0xffffffffu, n, o), mub = __shfl_xor_sync(0xffffffffu, mu, o),
+                 m2b = __shfl_xor_sync(0xffffffffu, m2, o);
+    // both partners must compute the same merged triple: order the pair by lane so the arithmetic is identical
+    if (lane & o) {
+      double n2 = nb, mu2 = mub, m22 = m2b;
+      chan_merge(n2, mu2, m22, n, mu, m2);
+      n = n2; mu = mu2; m2 = m22;
+    } else {
+      chan_merge(n, mu, m2, nb, mub, m2b);
+    }
+  }
+  if (lane != 0) return;
   mean[c] = (float)mu;
   var[c] = (float)(m2 / (double)M);
   if (run_mean) {
@@ -75,28 +117,54 @@ bn_apply_kernel(const float* __restrict__ y, long long n4, int C4, const float* 
 __global__ void __launch_bounds__(256)
 bn_bwd_part_kernel(const float* __restrict__ dz, const float* __restrict__ z, const float* __restrict__ y, long long M, int C,
                    const float* __restrict__ mean, const float* __restrict__ var, float eps, float* __restrict__ part) {
-  const int c = blockIdx.y * 256 + threadIdx.x;
-  if (c >= C) return;
+  __shared__ float4 sh1[BN_RL][32], sh2[BN_RL][32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.y * 128 + tx * 4;
   const long long rows = (M + gridDim.x - 1) / gridDim.x, m0 = blockIdx.x * rows, m1 = min(M, m0 + rows);
-  const float mu = mean[c], rstd = 1.f / sqrtf(var[c] + eps);
-  float s1 = 0.f, s2 = 0.f;
-  for (long long m = m0; m < m1; ++m) {
-    float g = dz[m * C + c];
-    if (z && !(z[m * C + c] > 0.f)) g = 0.f;
-    s1 += g;
-    s2 = fmaf(g, (y[m * C + c] - mu) * rstd, s2);
+  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+  if (c < C) {
+    const float4 mu = ld4(mean + c), va = ld4(var + c);
+    const float4 rs = make_float4(1.f / sqrtf(va.x + eps), 1.f / sqrtf(va.y + eps), 1.f / sqrtf(va.z + eps), 1.f / sqrtf(va.w + eps));
+#pragma unroll 4
+    for (long long m = m0 + ty; m < m1; m += BN_RL) {
+      float4 g = ld4(dz + m * C + c);
+      const float4 v = ld4(y + m * C + c);
+      if (z) {
+        const float4 zz = ld4(z + m * C + c);
+        g.x = zz.x > 0.f ? g.x : 0.f; g.y = zz.y > 0.f ? g.y : 0.f; g.z = zz.z > 0.f ? g.z : 0.f; g.w = zz.w > 0.f ? g.w : 0.f;
+      }
+      s1.x += g.x; s1.y += g.y; s1.z += g.z; s1.w += g.w;
+      s2.x = fmaf(g.x, (v.x - mu.x) * rs.x, s2.x); s2.y = fmaf(g.y, (v.y - mu.y) * rs.y, s2.y);
+      s2.z = fmaf(g.z, (v.z - mu.z) * rs.z, s2.z); s2.w = fmaf(g.w, (v.w - mu.w) * rs.w, s2.w);
+    }
   }
-  part[((size_t)blockIdx.x * C + c) * 2] = s1;
-  part[((size_t)blockIdx.x * C + c) * 2 + 1] = s2;
+  sh1[ty][tx] = s1;
+  sh2[ty][tx] = s2;
+  __syncthreads();
+  if (ty != 0 || c >= C) return;
+  for (int r = 1; r < BN_RL; ++r) { s1 = f4_add(s1, sh1[r][tx]); s2 = f4_add(s2, sh2[r][tx]); }
+  const float a1[4] = {s1.x, s1.y, s1.z, s1.w}, a2[4] = {s2.x, s2.y, s2.z, s2.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    part[((size_t)blockIdx.x * C + c + k) * 2] = a1[k];
+    part[((size_t)blockIdx.x * C + c + k) * 2 + 1] = a2[k];
+  }
 }
-__global__ void bn_bwd_final_kernel(const float* __restrict__ part, int nblk, int C, float* __restrict__ s1, float* __restrict__ s2) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256)
+bn_bwd_final_kernel(const float* __restrict__ part, int nblk, int C, float* __restrict__ s1, float* __restrict__ s2) {
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;     // one warp per channel, fixed order
   if (c >= C) return;
   double a = 0.0, b = 0.0;
-  for (int k = 0; k < nblk; ++k) {
+  for (int k = lane; k < nblk; k += 32) {
     a += (double)part[((size_t)k * C + c) * 2];
     b += (double)part[((size_t)k * C + c) * 2 + 1];
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_down_sync(0xffffffffu, a, o);
+    b += __shfl_down_sync(0xffffffffu, b, o);
+  }
+  if (lane != 0) return;
   s1[c] = (float)a;     // = d beta
   s2[c] = (float)b;     // = d gamma
 }
@@ -125,21 +193,20 @@ bn_bwd_apply_kernel(const float* __restrict__ dz, const float* __restrict__ z, c
   *reinterpret_cast<float4*>(dy + i * 4) = o;
 }
 
-inline int bn_blocks(long long M) { return (int)(M < BN_BLOCKS ? M : BN_BLOCKS); }
-inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
-
 }  // namespace
 
 extern "C" {
 
 // y [M, C] contiguous rows -> mean [C], var [C] (biased, as the normalisation uses); run_mean / run_var (optional) updated
-// in place with `momentum` and the unbiased variance (torch.nn.BatchNorm2d training semantics).  work: float [592 * C * 3]
+// in place with `momentum` and the unbiased variance (torch.nn.BatchNorm2d training semantics).  C % 4 == 0.
+// work: float [592 * C * 3]
 int di_bn_stats_f32(const float* y, long long M, int C, float* work, float* mean, float* var, float* run_mean, float* run_var,
                     float momentum, cudaStream_t stream) {
-  DI_CHECK_ARG(y && work && mean && var && M > 0 && C > 0 && (!run_mean == !run_var), "di_bn_stats_f32: bad argument");
+  DI_CHECK_ARG(y && work && mean && var && M > 0 && C > 0 && C % 4 == 0 && al16(y) && (!run_mean == !run_var),
+               "di_bn_stats_f32: bad argument");
   const int nblk = bn_blocks(M);
-  bn_stats_part_kernel<<<dim3(nblk, di_cdiv(C, 256)), 256, 0, stream>>>(y, M, C, work);
-  bn_stats_final_kernel<<<di_cdiv(C, 128), 128, 0, stream>>>(work, nblk, C, M, mean, var, run_mean, run_var, momentum);
+  bn_stats_part_kernel<<<dim3(nblk, di_cdiv(C, 128)), 256, 0, stream>>>(y, M, C, work);
+  bn_stats_final_kernel<<<di_cdiv(C, 8), 256, 0, stream>>>(work, nblk, C, M, mean, var, run_mean, run_var, momentum);
   DI_CHECK_LAUNCH("di_bn_stats_f32");
   return DI_OK;
 }
@@ -163,8 +230,8 @@ int di_bn_bwd_f32(const float* dz, const float* z, const float* y, long long M, 
                    al16(y) && al16(dy) && al16(mean) && al16(var) && al16(gamma) && al16(dgamma) && al16(dbeta),
                "di_bn_bwd_f32: bad argument");
   const int nblk = bn_blocks(M);
-  bn_bwd_part_kernel<<<dim3(nblk, di_cdiv(C, 256)), 256, 0, stream>>>(dz, z, y, M, C, mean, var, eps, work);
-  bn_bwd_final_kernel<<<di_cdiv(C, 128), 128, 0, stream>>>(work, nblk, C, dbeta, dgamma);
+  bn_bwd_part_kernel<<<dim3(nblk, di_cdiv(C, 128)), 256, 0, stream>>>(dz, z, y, M, C, mean, var, eps, work);
+  bn_bwd_final_kernel<<<di_cdiv(C, 8), 256, 0, stream>>>(work, nblk, C, dbeta, dgamma);
   const long long n4 = M * (C / 4);
   bn_bwd_apply_kernel<<<(unsigned)di_cdiv(n4, 256), 256, 0, stream>>>(dz, z, y, n4, C / 4, mean, var, gamma, eps, dbeta, dgamma,
                                                                      1.f / (float)M, dy);

@@ -11,8 +11,22 @@ import math
 import torch
 
 
+ON_DEVICE = [False]     # train.py: fold on the parameters' device (no host round trip, hence no stream synchronisation)
+
+
 def _d(t):
-    return t.detach().double().cpu()
+    t = t.detach().double()
+    return t if ON_DEVICE[0] else t.cpu()
+
+
+class on_device:
+    """Context: the folding helpers of this module keep their float64 intermediates on the parameters' device."""
+
+    def __enter__(self):
+        self.saved, ON_DEVICE[0] = ON_DEVICE[0], True
+
+    def __exit__(self, *a):
+        ON_DEVICE[0] = self.saved
 
 
 def conv_bn(conv, bn=None):
@@ -79,7 +93,7 @@ def i2p_unfold_grads(mha, dM1, dc1, dM2, dc2):
     bq, bk, bv = _d(mha.in_proj_bias).chunk(3, 0)
     Wo = _d(mha.out_proj.weight)
     s = 1.0 / math.sqrt(E)
-    dM1, dc1, dM2, dc2 = (t.detach().cpu().double() for t in (dM1, dc1, dM2, dc2))
+    dM1, dc1, dM2, dc2 = (_d(t) for t in (dM1, dc1, dM2, dc2))
     # M1 = s Wk^T Wq, c1 = s Wk^T bq, M2 = Wo Wv, c2 = Wo bv + bo
     return dict(Wq=s * Wk @ dM1, bq=s * Wk @ dc1, Wk=s * (Wq @ dM1.T + torch.outer(bq, dc1)), bk=torch.zeros_like(bk),
                 Wv=Wo.T @ dM2, Wo=dM2 @ Wv.T + torch.outer(dc2, bv), bv=Wo.T @ dc2, bo=dc2)
@@ -136,14 +150,29 @@ class Weight:
     """A dense-layer weight [N, K] kept in the forms the kernels consume: plain fp32 (FFMA path), the TF32 hi/lo
     split and the bf16 hi/mid split (tcgen05 paths)."""
 
-    def __init__(self, w, device):
+    def __init__(self, w, device, lazy=False):
+        """lazy: build the two splits on first use (training: weights change every step and only one split is read)."""
         self.w = dev(w, device)
-        hi, lo = split_tf32(w.to(torch.float32))
-        self.hi, self.lo = hi.to(device), lo.to(device)
-        bh, bm = split_bf16(w)
-        self.bh, self.bm = bh.to(device), bm.to(device)
         self.shape = self.w.shape
-        self._wt = None
+        self._wt = self._tf32 = self._bf16 = None
+        if not lazy:
+            self._tf32 = tuple(t.to(device) for t in split_tf32(w.to(torch.float32)))
+            self._bf16 = tuple(t.to(device) for t in split_bf16(w))
+
+    def _get_tf32(self):
+        if self._tf32 is None:
+            self._tf32 = split_tf32(self.w)
+        return self._tf32
+
+    def _get_bf16(self):
+        if self._bf16 is None:
+            self._bf16 = split_bf16(self.w)
+        return self._bf16
+
+    hi = property(lambda self: self._get_tf32()[0])
+    lo = property(lambda self: self._get_tf32()[1])
+    bh = property(lambda self: self._get_bf16()[0])
+    bm = property(lambda self: self._get_bf16()[1])
 
     @property
     def wt(self):

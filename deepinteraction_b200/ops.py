@@ -106,6 +106,8 @@ def linear(srcs, W, bias=None, act=ACT_NONE, out=None, res=None, res_mod=0, spli
     if splits > 1:
         assert res is None and bias is None and act == ACT_NONE
         part = torch.empty(splits, M, N, device=W.device, dtype=torch.float32) if out is None else out
+        if PROFILE[0] is not None:
+            _TAG[0] = ' M%d N%d K%d s%d' % (M, N, K, splits)
         n = _call('di_linear_f32', *a, _ptr(W), None, None, 0, 0, _ptr(part), N, M, N, ACT_NONE, splits, M * N,
                   _stream(), nbytes=4 * (M * K + N * K + splits * M * N), flops=2 * M * N * K)
         return part[:n]

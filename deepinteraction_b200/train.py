@@ -35,7 +35,7 @@ class ConvBNTrain:
         conv, bn = self.cb.conv, self.cb.bn
         dev = conv.weight.device
         w = conv.weight.detach().reshape(conv.weight.shape[0], -1)
-        W = fold.Weight(w, dev)
+        W = fold.Weight(w, dev, lazy=True)
         y = ops.linear(srcs, W)
         mean, var = ops.bn_stats(y, bn.running_mean, bn.running_var, bn.momentum)
         if bn.num_batches_tracked is not None:
@@ -54,7 +54,7 @@ class ConvBNTrain:
         grads[id(conv.weight)] = dw.view_as(conv.weight)
         if bn.weight is not None:
             grads[id(bn.weight)], grads[id(bn.bias)] = dg, db
-        return ops.linear([dy], fold.Weight(w.t().contiguous(), w.device))
+        return ops.linear([dy], fold.Weight(w.t().contiguous(), w.device, lazy=True))
 
 
 class LCABTrain:
@@ -128,7 +128,7 @@ def encoder_train_step(enc, img_feats, pts_feats, img_metas, pts_metas, grad_fn,
     per-layer branch outputs ('fwd') and their gradients ('bwd') as pixel-major rows.
     -> dict(outputs=(img, pts_conv, pts), d_img_feats [B*V,h,w,Ci], d_pts_feats [B,Y,X,Cp],
             grads={parameter name: gradient} for every parameter of `enc` the output depends on)."""
-    with bw._precise(), torch.no_grad():
+    with bw._precise(), torch.no_grad(), fold.on_device():
         return _encoder_train_step(enc, img_feats, pts_feats, img_metas, pts_metas, grad_fn, debug)
 
 
@@ -143,7 +143,7 @@ def _encoder_train_step(enc, img_feats, pts_feats, img_metas, pts_metas, grad_fn
     pm['pts'] = [p.to(dev) for p in pts_metas['pts']]
     g = mmri.Geometry(img_metas, pm, (h, w), (Y, X), dev)
     g.wait()
-    Wt = lambda t: fold.Weight(t, dev)
+    Wt = lambda t: fold.Weight(t, dev, lazy=True)
     d = lambda t: fold.dev(t, dev)
     conv_pack = lambda conv: (Wt(fold.pack_conv3x3(conv.weight.detach())), d(conv.bias.detach()))
     pk_img, pk_pts = conv_pack(enc.shared_conv_img), conv_pack(enc.shared_conv_pts)

@@ -40,6 +40,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--bn', default='eval', choices=['eval', 'train'])
+    ap.add_argument('--profile', action='store_true', help='after the timed steps: one more step with per-entry-point device times')
     args = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (('RANK', 0), ('WORLD_SIZE', 1), ('LOCAL_RANK', 0)))
     torch.cuda.set_device(local)
@@ -112,6 +113,32 @@ def main():
                                      'BatchNorm, no decoder backward)' % (' + AdamW step' if args.bn == 'train' else '', args.bn), value=world * 1000.0 / ms, unit='frames/s',
                               n_gpus=world, steps=args.steps, ms_per_step=ms, gradient_tensors=len(gl), gradient_bytes=nbytes,
                               allreduce_buckets=launched, finite=bool(all(torch.isfinite(t).all() for t in gl)))), flush=True)
+    if args.profile and rank == 0:
+        import collections
+        import time
+        ops.PROFILE[0] = []
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        step()
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) * 1e3
+        rec, ops.PROFILE[0] = ops.PROFILE[0], None
+        agg = collections.defaultdict(lambda: [0, 0.0])
+        for name, e0, e1, *_ in rec:
+            a_ = agg[name.split(' ')[0]]
+            a_[0] += 1
+            a_[1] += e0.elapsed_time(e1)
+        tot = sum(v[1] for v in agg.values())
+        print('profiled step: wall %.1f ms, %d libdi_b200 calls, sum of their device times %.1f ms' % (wall, len(rec), tot))
+        for name, (n, ms_) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:22]:
+            print('  %-28s %4d calls %8.2f ms  %5.1f%%' % (name, n, ms_, 100 * ms_ / tot))
+        tags = collections.defaultdict(lambda: [0, 0.0])
+        for name, e0, e1, *_ in rec:
+            if name.startswith('di_linear_f32'):
+                tags[name][0] += 1
+                tags[name][1] += e0.elapsed_time(e1)
+        for name, (n, ms_) in sorted(tags.items(), key=lambda kv: -kv[1][1])[:8]:
+            print('    %-44s %4d calls %8.2f ms' % (name, n, ms_))
     if world > 1:
         dist.destroy_process_group()
 
