@@ -11,44 +11,62 @@
 //     dS       = A * (dA - sum_j A dA) * scale                  di_win_softmax_bwd_f32
 //     dq[p]    = sum_j dS[p, j] k[nbr(p, j)]                    di_win_gather_f32(dS, k)
 //     dk[p']   = sum_{nbr(p, j) = p'} dS[p, j] q[p]             di_win_scatter_f32(dS, q)
-// One warp per pixel, lanes over channels (float4), the kH*kW taps in a loop; tap j = (dy + r) * kW + (dx + r), the
+// One warp per 4 x-adjacent pixels, lanes over channels (float4), the kH*kW taps in a loop; tap j = (dy + r) * kW + (dx + r), the
 // reference's order (similar.cu:15-17).  fp32 throughout.  These are the training-side counterparts of the fused
 // forward kernels; they are not fused (the [P, 81] tensors go through memory) -- first correct, measured version.
 #include "common.cuh"
 
 namespace {
 
+// A warp owns WPX pixels adjacent in x: their windows overlap in (ks - 1) of ks columns, so every neighbour row is loaded once
+// per warp and used for up to WPX taps (3x fewer L2 -> SM bytes than one pixel per warp at ks = 9).  The per-pixel
+// arithmetic and its order are those of the one-pixel form.
+constexpr int WPX = 4;
+
 // out[p, j] = a[p] . b[nbr(p, j)]
 template <int VEC>
 __global__ void __launch_bounds__(256)
 win_dot_kernel(const float* __restrict__ a, int lda, const float* __restrict__ b, int ldb, float* __restrict__ out, int N, int H,
                int W, int C, int ks) {
-  const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (wid >= N * H * W) return;
-  const int n = wid / (H * W), yx = wid - n * H * W, y = yx / W, x = yx - y * W, r = ks >> 1, KK = ks * ks;
-  float4 av[VEC];
+  const int gpr = (W + WPX - 1) / WPX;
+  const int gid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (gid >= N * H * gpr) return;
+  const int row = gid / gpr, x0 = (gid - row * gpr) * WPX, n = row / H, y = row - n * H, r = ks >> 1, KK = ks * ks;
+  const int npx = min(WPX, W - x0);
+  float4 av[WPX][VEC];
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) {
-    const int c = (i * 32 + lane) * 4;
-    av[i] = c < C ? ldg4(a + (size_t)wid * lda + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  float* o = out + (size_t)wid * KK;
-  for (int j = 0; j < KK; ++j) {
-    const int yy = y + j / ks - r, xx = x + j % ks - r;
-    float s = 0.f;
-    if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-      const float* bp = b + ((size_t)(n * H + yy) * W + xx) * ldb;
+  for (int i = 0; i < WPX; ++i)
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        const int c = (i * 32 + lane) * 4;
-        if (c < C) {
-          const float4 bv = ldg4(bp + c);
-          s += av[i].x * bv.x + av[i].y * bv.y + av[i].z * bv.z + av[i].w * bv.w;
-        }
-      }
-      s = warp_sum(s);
+    for (int v = 0; v < VEC; ++v) {
+      const int c = (v * 32 + lane) * 4;
+      av[i][v] = (i < npx && c < C) ? ldg4(a + ((size_t)row * W + x0 + i) * lda + c) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    if (lane == 0) o[j] = s;
+  float* o = out + ((size_t)row * W + x0) * KK;
+  for (int dy = -r; dy <= r; ++dy) {
+    const int yy = y + dy;
+    const bool rowok = yy >= 0 && yy < H;
+    for (int cx = -r; cx <= r + WPX - 1; ++cx) {
+      const int xx = x0 + cx;
+      const bool ok = rowok && xx >= 0 && xx < W;                 // warp-uniform
+      float4 bv[VEC];
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        const int c = (v * 32 + lane) * 4;
+        bv[v] = (ok && c < C) ? ldg4(b + ((size_t)(n * H + yy) * W + xx) * ldb + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < WPX; ++i) {
+        const int dx = cx - i;
+        if (dx < -r || dx > r || i >= npx) continue;
+        float s = 0.f;
+        if (ok) {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) s += av[i][v].x * bv[v].x + av[i][v].y * bv[v].y + av[i][v].z * bv[v].z + av[i][v].w * bv[v].w;
+          s = warp_sum(s);
+        }
+        if (lane == 0) o[(size_t)i * KK + (dy + r) * ks + dx + r] = s;
+      }
+    }
   }
 }
 
@@ -57,36 +75,53 @@ template <int VEC, bool SCATTER>
 __global__ void __launch_bounds__(256)
 win_apply_kernel(const float* __restrict__ w, const float* __restrict__ b, int ldb, float* __restrict__ out, int ldo, int N,
                  int H, int W, int C, int ks) {
-  const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (wid >= N * H * W) return;
-  const int n = wid / (H * W), yx = wid - n * H * W, y = yx / W, x = yx - y * W, r = ks >> 1, KK = ks * ks;
-  float4 acc[VEC];
+  const int gpr = (W + WPX - 1) / WPX;
+  const int gid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (gid >= N * H * gpr) return;
+  const int row = gid / gpr, x0 = (gid - row * gpr) * WPX, n = row / H, y = row - n * H, r = ks >> 1, KK = ks * ks;
+  const int npx = min(WPX, W - x0);
+  float4 acc[WPX][VEC];
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int j = 0; j < KK; ++j) {
-    const int dy = j / ks - r, dx = j % ks - r;
-    const int yy = SCATTER ? y - dy : y + dy, xx = SCATTER ? x - dx : x + dx;
-    if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-    const size_t src = (size_t)(n * H + yy) * W + xx;
-    const float wt = SCATTER ? __ldg(w + src * KK + j) : __ldg(w + (size_t)wid * KK + j);
-    const float* bp = b + src * ldb;
+  for (int i = 0; i < WPX; ++i)
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      const int c = (i * 32 + lane) * 4;
-      if (c < C) {
-        const float4 bv = ldg4(bp + c);
-        acc[i].x = fmaf(wt, bv.x, acc[i].x);
-        acc[i].y = fmaf(wt, bv.y, acc[i].y);
-        acc[i].z = fmaf(wt, bv.z, acc[i].z);
-        acc[i].w = fmaf(wt, bv.w, acc[i].w);
+    for (int v = 0; v < VEC; ++v) acc[i][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int dy = -r; dy <= r; ++dy) {                              // tap row, in the reference's order
+    const int yy = SCATTER ? y - dy : y + dy;
+    if (yy < 0 || yy >= H) continue;
+    for (int u = 0; u < ks + WPX - 1; ++u) {
+      const int cx = SCATTER ? r + WPX - 1 - u : u - r;            // source column relative to x0; tap dx ascends with u
+      const int xx = x0 + cx;
+      if (xx < 0 || xx >= W) continue;
+      const size_t src = (size_t)(n * H + yy) * W + xx;
+      float4 bv[VEC];
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        const int c = (v * 32 + lane) * 4;
+        bv[v] = c < C ? ldg4(b + src * ldb + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < WPX; ++i) {
+        const int dx = SCATTER ? i - cx : cx - i;
+        if (dx < -r || dx > r || i >= npx) continue;
+        const int j = (dy + r) * ks + dx + r;
+        const float wt = SCATTER ? __ldg(w + src * KK + j) : __ldg(w + ((size_t)row * W + x0 + i) * KK + j);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          acc[i][v].x = fmaf(wt, bv[v].x, acc[i][v].x);
+          acc[i][v].y = fmaf(wt, bv[v].y, acc[i][v].y);
+          acc[i][v].z = fmaf(wt, bv[v].z, acc[i][v].z);
+          acc[i][v].w = fmaf(wt, bv[v].w, acc[i][v].w);
+        }
       }
     }
   }
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) {
-    const int c = (i * 32 + lane) * 4;
-    if (c < C) *reinterpret_cast<float4*>(out + (size_t)wid * ldo + c) = acc[i];
-  }
+  for (int i = 0; i < WPX; ++i)
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      const int c = (v * 32 + lane) * 4;
+      if (i < npx && c < C) *reinterpret_cast<float4*>(out + ((size_t)row * W + x0 + i) * ldo + c) = acc[i][v];
+    }
 }
 
 // rows of KK <= 128 values: A = softmax(S * scale) (forward, in place allowed)
@@ -188,12 +223,12 @@ __global__ void shift_map_kernel(const float4* __restrict__ in, float4* __restri
 
 template <int VEC>
 int launch_dot(const float* a, int lda, const float* b, int ldb, float* out, int N, int H, int W, int C, int ks, cudaStream_t st) {
-  win_dot_kernel<VEC><<<di_cdiv((long long)N * H * W, 8), 256, 0, st>>>(a, lda, b, ldb, out, N, H, W, C, ks);
+  win_dot_kernel<VEC><<<di_cdiv((long long)N * H * di_cdiv(W, WPX), 8), 256, 0, st>>>(a, lda, b, ldb, out, N, H, W, C, ks);
   return 0;
 }
 template <int VEC, bool SC>
 int launch_apply(const float* w, const float* b, int ldb, float* out, int ldo, int N, int H, int W, int C, int ks, cudaStream_t st) {
-  win_apply_kernel<VEC, SC><<<di_cdiv((long long)N * H * W, 8), 256, 0, st>>>(w, b, ldb, out, ldo, N, H, W, C, ks);
+  win_apply_kernel<VEC, SC><<<di_cdiv((long long)N * H * di_cdiv(W, WPX), 8), 256, 0, st>>>(w, b, ldb, out, ldo, N, H, W, C, ks);
   return 0;
 }
 
