@@ -54,18 +54,25 @@ win_dot_kernel(const float* __restrict__ a, int lda, const float* __restrict__ b
         const int c = (v * 32 + lane) * 4;
         bv[v] = (ok && c < C) ? ldg4(b + ((size_t)(n * H + yy) * W + xx) * ldb + c) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
+      // the WPX dot products of this neighbour row, reduced together: two exchange steps fold 4 values per lane into 1
+      // (lanes with bits 4:3 = i keep pixel i), three more finish the sum -- 6 shuffles instead of 4 x 5
+      float s[WPX];
 #pragma unroll
       for (int i = 0; i < WPX; ++i) {
-        const int dx = cx - i;
-        if (dx < -r || dx > r || i >= npx) continue;
-        float s = 0.f;
-        if (ok) {
+        s[i] = 0.f;
 #pragma unroll
-          for (int v = 0; v < VEC; ++v) s += av[i][v].x * bv[v].x + av[i][v].y * bv[v].y + av[i][v].z * bv[v].z + av[i][v].w * bv[v].w;
-          s = warp_sum(s);
-        }
-        if (lane == 0) o[(size_t)i * KK + (dy + r) * ks + dx + r] = s;
+        for (int v = 0; v < VEC; ++v) s[i] += av[i][v].x * bv[v].x + av[i][v].y * bv[v].y + av[i][v].z * bv[v].z + av[i][v].w * bv[v].w;
       }
+      const bool up16 = lane & 16, up8 = lane & 8;
+      const float k0 = up16 ? s[2] : s[0], k1 = up16 ? s[3] : s[1];          // kept pair
+      const float g0 = up16 ? s[0] : s[2], g1 = up16 ? s[1] : s[3];          // given to the partner half
+      const float t0 = k0 + __shfl_xor_sync(0xffffffffu, g0, 16), t1 = k1 + __shfl_xor_sync(0xffffffffu, g1, 16);
+      float t = (up8 ? t1 : t0) + __shfl_xor_sync(0xffffffffu, up8 ? t0 : t1, 8);
+      t += __shfl_xor_sync(0xffffffffu, t, 4);
+      t += __shfl_xor_sync(0xffffffffu, t, 2);
+      t += __shfl_xor_sync(0xffffffffu, t, 1);
+      const int i = lane >> 3, dx = cx - i;                                  // lanes 0, 8, 16, 24 write pixels 0..3
+      if ((lane & 7) == 0 && i < npx && dx >= -r && dx <= r) o[(size_t)i * KK + (dy + r) * ks + dx + r] = ok ? t : 0.f;
     }
   }
 }
