@@ -55,6 +55,71 @@ def test_i2p_attention_fold_equals_multihead_attention():
     assert rel_err(out, ref) < 1e-5
 
 
+def test_i2p_unfold_grads_is_the_chain_rule_of_the_fold():
+    """fold.i2p_unfold_grads maps gradients w.r.t. the folded (M1, c1, M2, c2) back to nn.MultiheadAttention's own parameters:
+    compared with autograd through the module itself (the training step relies on it, train.py)."""
+    from deepinteraction_b200 import fold
+    torch.manual_seed(2)
+    C = 16
+    mha = torch.nn.MultiheadAttention(C, 1, kdim=C, vdim=C, batch_first=True).double()
+    with torch.no_grad():
+        mha.in_proj_bias.normal_(0, 0.1)
+        mha.out_proj.bias.normal_(0, 0.1)
+    q, kv, G = torch.randn(9, 1, C).double(), torch.randn(9, 6, C).double(), torch.randn(9, C).double()
+    (mha(q, kv, kv)[0][:, 0] * G).sum().backward()
+    M1, c1, M2, c2 = (t.clone().requires_grad_(True) for t in fold.i2p_fold(mha))
+    qk = q[:, 0] @ M1.t() + c1
+    s_ = torch.einsum('pk,pkc->pc', torch.einsum('pc,pkc->pk', qk, kv).softmax(-1), kv)
+    ((s_ @ M2.t() + c2) * G).sum().backward()
+    u = fold.i2p_unfold_grads(mha, M1.grad, c1.grad, M2.grad, c2.grad)
+    W = torch.cat([u['Wq'], u['Wk'], u['Wv']], 0)
+    b = torch.cat([u['bq'], u['bk'], u['bv']], 0)
+    assert rel_err(W, mha.in_proj_weight.grad) < 1e-10 and rel_err(b, mha.in_proj_bias.grad) < 1e-10
+    assert rel_err(u['Wo'], mha.out_proj.weight.grad) < 1e-10 and rel_err(u['bo'], mha.out_proj.bias.grad) < 1e-10
+    with fold.on_device():                     # the device-resident variant computes the same thing (CPU tensors here)
+        u2 = fold.i2p_unfold_grads(mha, M1.grad, c1.grad, M2.grad, c2.grad)
+    assert all(torch.equal(u[k], u2[k]) for k in u)
+
+
+def test_lazy_weight_equals_eager_weight():
+    from deepinteraction_b200 import fold
+    w = torch.randn(24, 40, generator=torch.Generator().manual_seed(3))
+    a, b = fold.Weight(w, 'cpu'), fold.Weight(w, 'cpu', lazy=True)
+    assert b._tf32 is None and b._bf16 is None
+    for k in ('w', 'hi', 'lo', 'bh', 'bm', 'wt'):
+        assert torch.equal(getattr(a, k), getattr(b, k)), k
+    assert torch.equal(a.hi + a.lo, w) and a.shape == b.shape == (24, 40)
+
+
+def test_train_mode_batchnorm_formulas():
+    """The closed forms csrc/bn_train.cu implements (shifted one-pass block moments merged with Chan's formula; dy = gamma rstd
+    (g - mean(g) - xhat mean(g xhat))) against torch.nn.functional.batch_norm + autograd, in float64 on the host."""
+    import torch.nn.functional as F
+    g_ = torch.Generator().manual_seed(4)
+    M, C, eps = 203, 5, 1e-5
+    y = (torch.randn(M, C, generator=g_) * 0.3 + torch.tensor([100.0, -3.0, 0.0, 7.0, 0.5])).double()
+    parts = []
+    for m0 in range(0, M, 37):                                    # row blocks as the kernel forms them
+        blk = y[m0:m0 + 37]
+        d = blk - blk[0]
+        s1, s2, n = d.sum(0), (d * d).sum(0), blk.shape[0]
+        parts.append((n, blk[0] + s1 / n, s2 - s1 * s1 / n))
+    n, mu, m2 = 0, torch.zeros(C).double(), torch.zeros(C).double()
+    for nb, mub, m2b in parts:
+        d = mub - mu
+        mu, m2, n = mu + d * nb / (n + nb), m2 + m2b + d * d * n * nb / (n + nb), n + nb
+    assert rel_err(mu, y.mean(0)) < 1e-12 and rel_err(m2 / M, y.var(0, unbiased=False)) < 1e-10
+    gamma, beta, dz = torch.rand(C).double() + 0.5, torch.randn(C).double(), torch.randn(M, C, generator=g_).double()
+    yr, gr = y.clone().requires_grad_(True), gamma.clone().requires_grad_(True)
+    z = F.relu(F.batch_norm(yr, None, None, gr, beta, True, 0.1, eps))
+    (z * dz).sum().backward()
+    rstd = 1 / torch.sqrt(m2 / M + eps)
+    xhat = (y - mu) * rstd
+    g = dz * (z.detach() > 0)
+    dy = gamma * rstd * (g - g.mean(0) - xhat * (g * xhat).mean(0))
+    assert rel_err(dy, yr.grad) < 1e-9 and rel_err((g * xhat).sum(0), gr.grad) < 1e-10
+
+
 def test_aug_affine_matches_apply_3d_transformation():
     from oracle.geometry import apply_3d_transformation
     from deepinteraction_b200 import geom, synth
