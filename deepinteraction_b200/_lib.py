@@ -77,6 +77,9 @@ SIGNATURES = {
     'di_rows_mlp_f32': [_p, _i, _i, _p, _i, _i, _p, _p, _i, _i, _p, _p, _i, _p, _i, _p, _p, _f, _i, _p, _p, _i, _i, _p],
     'di_pred_finish_f32': [_p, _p, _p, _p, _i, _i, _p],
     'di_i2p_attend_bwd_f32': [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p],
+    'di_i2p_attend_dropout_f32': [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _f, ctypes.c_uint, _p],
+    'di_i2p_attend_bwd_dropout_f32': [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _f, ctypes.c_uint, _p],
+    'di_i2p_dropout_mask_f32': [_p, _i, _i, _f, ctypes.c_uint, _p],
     'di_bev_sample_bwd_f32': [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     'di_gather_rows_masked_f32': [_p, _p, _p, _p, _i, _i, _i, _i, _p],
     'di_win_dot_f32': [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _p],

@@ -105,18 +105,18 @@ def _lcab_backward(pk, target, source, N, H, W, grad_out):
     return dict(d_target=d_t, d_source=d_s, **g)
 
 
-def i2p_backward(i2p_pack, pts_nhwc, img_nhwc, pts_metas, proj, V, in_hw, grad_out):
+def i2p_backward(i2p_pack, pts_nhwc, img_nhwc, pts_metas, proj, V, in_hw, grad_out, dropout=None):
     """Backward of the MMRI_I2P block as the product evaluates it (mmri.DeepInteractionEncoder.i2p; reference
     encoder_utils.py:216-320): rows = pts[coors]; qk = M1 rows + c1; s = attend(qk, image samples); o = M2 s + c2;
     out[coors] = o where a pillar saw >= 1 sample.  i2p_pack = (M1, c1, M2, c2) folded from nn.MultiheadAttention
     (fold.i2p_fold); proj: [B, V, 12] device camera rows (mmri.Geometry.proj).  grad_out [B, Y, X, C].
     -> dict(d_pts [B,Y,X,C], d_img [B*V,h,w,C], dM1, dc1, dM2, dc2); fold.i2p_unfold_grads maps the last four to the
-    attention module's own parameters."""
+    attention module's own parameters.  dropout = (p, seed): the training-mode attention dropout the forward used."""
     with _precise():
-        return _i2p_backward(i2p_pack, pts_nhwc, img_nhwc, pts_metas, proj, V, in_hw, grad_out)
+        return _i2p_backward(i2p_pack, pts_nhwc, img_nhwc, pts_metas, proj, V, in_hw, grad_out, dropout)
 
 
-def _i2p_backward(i2p_pack, pts_nhwc, img_nhwc, pts_metas, proj, V, in_hw, grad_out):
+def _i2p_backward(i2p_pack, pts_nhwc, img_nhwc, pts_metas, proj, V, in_hw, grad_out, dropout=None):
     M1, c1, M2, c2 = i2p_pack
     coors = pts_metas['pillar_coors']
     pillars, npts = pts_metas['pillars'], pts_metas['pillars_num_points']
@@ -130,12 +130,12 @@ def _i2p_backward(i2p_pack, pts_nhwc, img_nhwc, pts_metas, proj, V, in_hw, grad_
     # forward intermediates
     rows = ops.gather_rows(pts_nhwc, coors)
     qk = ops.linear([rows], M1, c1)
-    s, cnt = ops.i2p_attend(qk, pillars, npts, coors, proj, img_nhwc, V, in_hw)
+    s, cnt = ops.i2p_attend(qk, pillars, npts, coors, proj, img_nhwc, V, in_hw, dropout=dropout)
     # out = scatter(M2 s + c2) at pillars with cnt > 0
     do = ops.gather_rows_masked(grad_out.contiguous(), cnt, coors)
     dM2, dc2 = _wgrad(do, s), ops.col_sum(do)
     ds = ops.linear([do], T_(M2))
-    dqk = ops.i2p_attend_bwd(qk, ds, pillars, npts, coors, proj, img_nhwc, d_img, V, in_hw)
+    dqk = ops.i2p_attend_bwd(qk, ds, pillars, npts, coors, proj, img_nhwc, d_img, V, in_hw, dropout)
     dM1, dc1 = _wgrad(dqk, rows), ops.col_sum(dqk)
     drows = ops.linear([dqk], T_(M1))
     ones = torch.ones(coors.shape[0], device=dev, dtype=torch.int32)

@@ -60,12 +60,22 @@ __device__ __forceinline__ void bilinear_row(const float* __restrict__ map, int 
 // ------------------------------------------------------------------------------------------------
 // I2P: one warp per pillar.
 // ------------------------------------------------------------------------------------------------
-template <int NJ>
-__global__ void __launch_bounds__(256)
-i2p_attend_kernel(const float* __restrict__ qk, const float* __restrict__ pillars, const int* __restrict__ npts,
-                  const int* __restrict__ coors, const float* __restrict__ proj, const float* __restrict__ img,
-                  float* __restrict__ s_out, int* __restrict__ cnt_out, int P, int T, int pdim, int V, int h, int w,
-                  int C, float H_in, float W_in, const int* __restrict__ n_dev) {
+// Attention dropout of nn.MultiheadAttention in training mode (encoder_utils.py:223, dropout = 0.1 in the reference config):
+// the softmax weights are multiplied by keep / (1 - p) AFTER normalisation.  keep is a counter-based hash of (seed, pillar,
+// key index), so the backward regenerates the same mask without storing it.  Returns 0 or 1 / (1 - p).
+__device__ __forceinline__ float i2p_keep_scale(unsigned seed, int p, int key, float pdrop) {
+  unsigned x = seed ^ (0x9E3779B9u * (unsigned)(p + 1));
+  x ^= (unsigned)key * 0x85EBCA6Bu + 0xC2B2AE35u;
+  x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+  return (float)(x >> 8) * (1.f / 16777216.f) >= pdrop ? 1.f / (1.f - pdrop) : 0.f;
+}
+
+template <int NJ, bool DROP>
+__device__ __forceinline__ void
+i2p_attend_body(const float* __restrict__ qk, const float* __restrict__ pillars, const int* __restrict__ npts,
+                const int* __restrict__ coors, const float* __restrict__ proj, const float* __restrict__ img,
+                float* __restrict__ s_out, int* __restrict__ cnt_out, int P, int T, int pdim, int V, int h, int w,
+                int C, float H_in, float W_in, const int* __restrict__ n_dev, float pdrop, unsigned seed) {
   const int lane = threadIdx.x & 31;
   const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (n_dev) P = min(P, __ldg(n_dev));          // capacity-sized arrays: the live count sits in device memory
@@ -126,6 +136,7 @@ i2p_attend_kernel(const float* __restrict__ qk, const float* __restrict__ pillar
       float corr = expf(mrun - mnew);
       float pw = expf(logit - mnew);
       lrun = lrun * corr + pw;
+      if (DROP) pw *= i2p_keep_scale(seed, p, s * 32 + src, pdrop);      // the normaliser keeps the dropped keys
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
         acc[j].x = acc[j].x * corr + pw * kv[j].x;
@@ -146,6 +157,29 @@ i2p_attend_kernel(const float* __restrict__ qk, const float* __restrict__ pillar
           make_float4(acc[j].x * inv, acc[j].y * inv, acc[j].z * inv, acc[j].w * inv);
   }
   if (lane == 0) cnt_out[p] = count;
+}
+
+template <int NJ>
+__global__ void __launch_bounds__(256)
+i2p_attend_kernel(const float* __restrict__ qk, const float* __restrict__ pillars, const int* __restrict__ npts,
+                  const int* __restrict__ coors, const float* __restrict__ proj, const float* __restrict__ img,
+                  float* __restrict__ s_out, int* __restrict__ cnt_out, int P, int T, int pdim, int V, int h, int w,
+                  int C, float H_in, float W_in, const int* __restrict__ n_dev) {
+  i2p_attend_body<NJ, false>(qk, pillars, npts, coors, proj, img, s_out, cnt_out, P, T, pdim, V, h, w, C, H_in, W_in, n_dev, 0.f, 0u);
+}
+template <int NJ>
+__global__ void __launch_bounds__(256)
+i2p_attend_drop_kernel(const float* __restrict__ qk, const float* __restrict__ pillars, const int* __restrict__ npts,
+                       const int* __restrict__ coors, const float* __restrict__ proj, const float* __restrict__ img,
+                       float* __restrict__ s_out, int* __restrict__ cnt_out, int P, int T, int pdim, int V, int h, int w,
+                       int C, float H_in, float W_in, const int* __restrict__ n_dev, float pdrop, unsigned seed) {
+  i2p_attend_body<NJ, true>(qk, pillars, npts, coors, proj, img, s_out, cnt_out, P, T, pdim, V, h, w, C, H_in, W_in, n_dev, pdrop, seed);
+}
+
+// mask[p, key] = 0 or 1 / (1 - p): the factors the two kernels above / below apply (tests, debugging)
+__global__ void i2p_dropout_mask_kernel(float* __restrict__ mask, int P, int S, float pdrop, unsigned seed) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < P * S) mask[i] = i2p_keep_scale(seed, i / S, i % S, pdrop);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -183,12 +217,12 @@ __device__ __forceinline__ void bilinear_scatter(float* __restrict__ dmap, int H
   }
 }
 
-template <int NJ>
-__global__ void __launch_bounds__(256)
-i2p_attend_bwd_kernel(const float* __restrict__ qk, const float* __restrict__ ds, const float* __restrict__ pillars,
-                      const int* __restrict__ npts, const int* __restrict__ coors, const float* __restrict__ proj,
-                      const float* __restrict__ img, float* __restrict__ d_img, float* __restrict__ dqk, int P, int T, int pdim,
-                      int V, int h, int w, int C, float H_in, float W_in, const int* __restrict__ n_dev) {
+template <int NJ, bool DROP>
+__device__ __forceinline__ void
+i2p_attend_bwd_body(const float* __restrict__ qk, const float* __restrict__ ds, const float* __restrict__ pillars,
+                    const int* __restrict__ npts, const int* __restrict__ coors, const float* __restrict__ proj,
+                    const float* __restrict__ img, float* __restrict__ d_img, float* __restrict__ dqk, int P, int T, int pdim,
+                    int V, int h, int w, int C, float H_in, float W_in, const int* __restrict__ n_dev, float pdrop, unsigned seed) {
   const int lane = threadIdx.x & 31;
   const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (n_dev) P = min(P, __ldg(n_dev));
@@ -271,6 +305,7 @@ i2p_attend_bwd_kernel(const float* __restrict__ qk, const float* __restrict__ ds
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
       lg[s] *= inv;                                    // a_j
+      if (DROP) tv[s] *= i2p_keep_scale(seed, p, s * 32 + lane, pdrop);    // s = sum a_j m_j k_j: t_j -> m_j t_j
       D += lg[s] * tv[s];
     }
     D = warp_sum(D);
@@ -285,6 +320,7 @@ i2p_attend_bwd_kernel(const float* __restrict__ qk, const float* __restrict__ ds
         mask &= mask - 1;
         float ix = __shfl_sync(0xffffffffu, sx[s], src), iy = __shfl_sync(0xffffffffu, sy[s], src);
         float a = __shfl_sync(0xffffffffu, lg[s], src), dl = __shfl_sync(0xffffffffu, tv[s], src);
+        if (DROP) a *= i2p_keep_scale(seed, p, s * 32 + src, pdrop);       // the direct path carries a_j m_j
         int v = (s * 32 + src) % V;
         float4 kv[NJ], dk[NJ];
         bilinear_row<NJ>(img + (size_t)(b * V + v) * h * w * C, h, w, C, ix, iy, lane, kv);
@@ -306,6 +342,24 @@ i2p_attend_bwd_kernel(const float* __restrict__ qk, const float* __restrict__ ds
     int c = 4 * lane + 128 * j;
     if (c < C) *reinterpret_cast<float4*>(dqk + (size_t)p * C + c) = acc[j];
   }
+}
+
+template <int NJ>
+__global__ void __launch_bounds__(256)
+i2p_attend_bwd_kernel(const float* __restrict__ qk, const float* __restrict__ ds, const float* __restrict__ pillars,
+                      const int* __restrict__ npts, const int* __restrict__ coors, const float* __restrict__ proj,
+                      const float* __restrict__ img, float* __restrict__ d_img, float* __restrict__ dqk, int P, int T, int pdim,
+                      int V, int h, int w, int C, float H_in, float W_in, const int* __restrict__ n_dev) {
+  i2p_attend_bwd_body<NJ, false>(qk, ds, pillars, npts, coors, proj, img, d_img, dqk, P, T, pdim, V, h, w, C, H_in, W_in, n_dev, 0.f, 0u);
+}
+template <int NJ>
+__global__ void __launch_bounds__(256)
+i2p_attend_bwd_drop_kernel(const float* __restrict__ qk, const float* __restrict__ ds, const float* __restrict__ pillars,
+                           const int* __restrict__ npts, const int* __restrict__ coors, const float* __restrict__ proj,
+                           const float* __restrict__ img, float* __restrict__ d_img, float* __restrict__ dqk, int P, int T,
+                           int pdim, int V, int h, int w, int C, float H_in, float W_in, const int* __restrict__ n_dev, float pdrop,
+                           unsigned seed) {
+  i2p_attend_bwd_body<NJ, true>(qk, ds, pillars, npts, coors, proj, img, d_img, dqk, P, T, pdim, V, h, w, C, H_in, W_in, n_dev, pdrop, seed);
 }
 
 // rows[p,:] = cnt[p] > 0 ? map[b, y, x, :] : 0   (transpose of scatter_rows_kernel)
@@ -755,6 +809,53 @@ int di_i2p_attend_bwd_f32(const float* qk, const float* ds, const float* pillars
   else
     i2p_attend_bwd_kernel<4><<<grid, 256, 0, stream>>>(qk, ds, pillars, npts, coors, proj, img, d_img, dqk, P, T, pdim, V, h, w, C, (float)H_in, (float)W_in, n_dev);
   DI_CHECK_LAUNCH("di_i2p_attend_bwd_f32");
+  return DI_OK;
+}
+
+// Training-mode variants with attention dropout (pdrop in [0, 1), mask = hash(seed, pillar, key); see i2p_keep_scale).
+int di_i2p_attend_dropout_f32(const float* qk, const float* pillars, const int* npts, const int* coors, const float* proj,
+                              const float* img, float* s_out, int* cnt_out, int P, int T, int pdim, int V, int h, int w, int C,
+                              int H_in, int W_in, const int* n_dev, float pdrop, unsigned int seed, cudaStream_t stream) {
+  DI_CHECK_ARG(qk && pillars && npts && coors && proj && img && s_out && cnt_out, "di_i2p_attend_dropout_f32: null pointer");
+  DI_CHECK_ARG(C % 4 == 0 && C <= 512 && pdim >= 3 && T * V <= 256 && pdrop >= 0.f && pdrop < 1.f,
+               "di_i2p_attend_dropout_f32: unsupported shape or rate (C=%d T=%d V=%d)", C, T, V);
+  if (P == 0) return DI_OK;
+  dim3 grid(di_cdiv(P, 8));
+  if (C <= 128)
+    i2p_attend_drop_kernel<1><<<grid, 256, 0, stream>>>(qk, pillars, npts, coors, proj, img, s_out, cnt_out, P, T, pdim, V, h, w, C, (float)H_in, (float)W_in, n_dev, pdrop, seed);
+  else if (C <= 256)
+    i2p_attend_drop_kernel<2><<<grid, 256, 0, stream>>>(qk, pillars, npts, coors, proj, img, s_out, cnt_out, P, T, pdim, V, h, w, C, (float)H_in, (float)W_in, n_dev, pdrop, seed);
+  else
+    i2p_attend_drop_kernel<4><<<grid, 256, 0, stream>>>(qk, pillars, npts, coors, proj, img, s_out, cnt_out, P, T, pdim, V, h, w, C, (float)H_in, (float)W_in, n_dev, pdrop, seed);
+  DI_CHECK_LAUNCH("di_i2p_attend_dropout_f32");
+  return DI_OK;
+}
+
+int di_i2p_attend_bwd_dropout_f32(const float* qk, const float* ds, const float* pillars, const int* npts, const int* coors,
+                                  const float* proj, const float* img, float* d_img, float* dqk, int P, int T, int pdim, int V,
+                                  int h, int w, int C, int H_in, int W_in, const int* n_dev, float pdrop, unsigned int seed,
+                                  cudaStream_t stream) {
+  DI_CHECK_ARG(qk && ds && pillars && npts && coors && proj && img && d_img && dqk, "di_i2p_attend_bwd_dropout_f32: null pointer");
+  DI_CHECK_ARG(C % 4 == 0 && C <= 512 && pdim >= 3 && T * V <= 256 && pdrop >= 0.f && pdrop < 1.f,
+               "di_i2p_attend_bwd_dropout_f32: unsupported shape or rate (C=%d T=%d V=%d)", C, T, V);
+  if (P == 0) return DI_OK;
+  dim3 grid(di_cdiv(P, 8));
+  if (C <= 128)
+    i2p_attend_bwd_drop_kernel<1><<<grid, 256, 0, stream>>>(qk, ds, pillars, npts, coors, proj, img, d_img, dqk, P, T, pdim, V, h, w, C, (float)H_in, (float)W_in, n_dev, pdrop, seed);
+  else if (C <= 256)
+    i2p_attend_bwd_drop_kernel<2><<<grid, 256, 0, stream>>>(qk, ds, pillars, npts, coors, proj, img, d_img, dqk, P, T, pdim, V, h, w, C, (float)H_in, (float)W_in, n_dev, pdrop, seed);
+  else
+    i2p_attend_bwd_drop_kernel<4><<<grid, 256, 0, stream>>>(qk, ds, pillars, npts, coors, proj, img, d_img, dqk, P, T, pdim, V, h, w, C, (float)H_in, (float)W_in, n_dev, pdrop, seed);
+  DI_CHECK_LAUNCH("di_i2p_attend_bwd_dropout_f32");
+  return DI_OK;
+}
+
+// mask [P, S = T*V]: the factor (0 or 1 / (1 - pdrop)) the two entry points above apply to key `key` of pillar p
+int di_i2p_dropout_mask_f32(float* mask, int P, int S, float pdrop, unsigned int seed, cudaStream_t stream) {
+  DI_CHECK_ARG(mask && P >= 0 && S > 0 && pdrop >= 0.f && pdrop < 1.f, "di_i2p_dropout_mask_f32: bad argument");
+  if (P == 0) return DI_OK;
+  i2p_dropout_mask_kernel<<<di_cdiv((long long)P * S, 256), 256, 0, stream>>>(mask, P, S, pdrop, seed);
+  DI_CHECK_LAUNCH("di_i2p_dropout_mask_f32");
   return DI_OK;
 }
 

@@ -252,8 +252,9 @@ class DeepInteractionEncoder(nn.Module):
         return pk
 
     # -- forward -----------------------------------------------------------------------------------
-    def i2p(self, lp, pts_nhwc, img_nhwc, pts_metas, g, n_dev=None):
-        """n_dev: device int32 [1] with the live pillar count when the pillar arrays are capacity buffers."""
+    def i2p(self, lp, pts_nhwc, img_nhwc, pts_metas, g, n_dev=None, dropout=None):
+        """n_dev: device int32 [1] with the live pillar count when the pillar arrays are capacity buffers.  dropout = (p, seed):
+        training-mode attention dropout (train.py only)."""
         B, Y, X, C = pts_nhwc.shape
         coors = pts_metas['pillar_coors']
         out = torch.zeros_like(pts_nhwc)
@@ -263,7 +264,7 @@ class DeepInteractionEncoder(nn.Module):
         rows = ops.gather_rows(pts_nhwc, coors, n_dev)
         qk = ops.linear([rows], M1, c1)
         s, cnt = ops.i2p_attend(qk, pts_metas['pillars'], pts_metas['pillars_num_points'], coors, g.proj, img_nhwc,
-                                g.V, g.in_hw, n_dev)
+                                g.V, g.in_hw, n_dev, dropout)
         o = ops.linear([s], M2, c2)
         return ops.scatter_rows(o, cnt, coors, out, n_dev)
 

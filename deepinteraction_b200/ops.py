@@ -384,7 +384,8 @@ def axpy(a, b, scale):
     return out
 
 
-def i2p_attend(qk, pillars, npts, coors, proj, img_nhwc, V, in_hw, n_dev=None):
+def i2p_attend(qk, pillars, npts, coors, proj, img_nhwc, V, in_hw, n_dev=None, dropout=None):
+    """dropout = (p, seed): training-mode attention dropout (mask = hash(seed, pillar, key), see i2p_dropout_mask)."""
     P, C = qk.shape
     _, T, pdim = pillars.shape
     BV, h, w, Ci = img_nhwc.shape
@@ -393,10 +394,22 @@ def i2p_attend(qk, pillars, npts, coors, proj, img_nhwc, V, in_hw, n_dev=None):
     cnt = torch.empty(P, device=qk.device, dtype=torch.int32)
     if n_dev is not None:
         s.zero_()                       # rows beyond the live count feed a dense layer: keep them finite
+    nb = 4 * (2 * P * C + pillars.numel() + img_nhwc.numel())
+    if dropout is not None and dropout[0] > 0:
+        _call('di_i2p_attend_dropout_f32', _ptr(qk), _ptr(pillars), _ptr(npts), _ptr(coors), _ptr(proj), _ptr(img_nhwc), _ptr(s),
+              _ptr(cnt), P, T, pdim, V, h, w, C, in_hw[0], in_hw[1], _ptr(n_dev), float(dropout[0]), int(dropout[1]) & 0xFFFFFFFF,
+              _stream(), nbytes=nb)
+        return s, cnt
     _call('di_i2p_attend_f32', _ptr(qk), _ptr(pillars), _ptr(npts), _ptr(coors), _ptr(proj), _ptr(img_nhwc), _ptr(s),
-          _ptr(cnt), P, T, pdim, V, h, w, C, in_hw[0], in_hw[1], _ptr(n_dev), _stream(),
-          nbytes=4 * (2 * P * C + pillars.numel() + img_nhwc.numel()), flops=0)
+          _ptr(cnt), P, T, pdim, V, h, w, C, in_hw[0], in_hw[1], _ptr(n_dev), _stream(), nbytes=nb, flops=0)
     return s, cnt
+
+
+def i2p_dropout_mask(P, S, pdrop, seed, device):
+    """[P, S] factors (0 or 1 / (1 - pdrop)) that i2p_attend / i2p_attend_bwd apply with dropout = (pdrop, seed)."""
+    mask = torch.empty(P, S, device=device, dtype=torch.float32)
+    _call('di_i2p_dropout_mask_f32', _ptr(mask), P, S, float(pdrop), int(seed) & 0xFFFFFFFF, _stream())
+    return mask
 
 
 def depth_scatter(pts, proj_b, keys_b, in_hw, n_dev=None):
@@ -766,16 +779,21 @@ def bn_bwd(dz, z, y, mean, var, gamma, eps):
     return dy, dg, db
 
 
-def i2p_attend_bwd(qk, ds, pillars, npts, coors, proj, img_nhwc, d_img, V, in_hw):
+def i2p_attend_bwd(qk, ds, pillars, npts, coors, proj, img_nhwc, d_img, V, in_hw, dropout=None):
     """Gradient of i2p_attend: -> dqk [P, C]; d_img (same shape as img_nhwc) is accumulated into."""
     P, C = qk.shape
     _, T, pdim = pillars.shape
     BV, h, w, Ci = img_nhwc.shape
     assert Ci == C and d_img.shape == img_nhwc.shape and d_img.is_contiguous() and ds.is_contiguous()
     dqk = torch.empty(P, C, device=qk.device, dtype=torch.float32)
+    nb = 4 * (3 * P * C + pillars.numel() + 2 * img_nhwc.numel())
+    if dropout is not None and dropout[0] > 0:
+        _call('di_i2p_attend_bwd_dropout_f32', _ptr(qk), _ptr(ds), _ptr(pillars), _ptr(npts), _ptr(coors), _ptr(proj),
+              _ptr(img_nhwc), _ptr(d_img), _ptr(dqk), P, T, pdim, V, h, w, C, in_hw[0], in_hw[1], None, float(dropout[0]),
+              int(dropout[1]) & 0xFFFFFFFF, _stream(), nbytes=nb)
+        return dqk
     _call('di_i2p_attend_bwd_f32', _ptr(qk), _ptr(ds), _ptr(pillars), _ptr(npts), _ptr(coors), _ptr(proj), _ptr(img_nhwc),
-          _ptr(d_img), _ptr(dqk), P, T, pdim, V, h, w, C, in_hw[0], in_hw[1], None, _stream(),
-          nbytes=4 * (3 * P * C + pillars.numel() + 2 * img_nhwc.numel()))
+          _ptr(d_img), _ptr(dqk), P, T, pdim, V, h, w, C, in_hw[0], in_hw[1], None, _stream(), nbytes=nb)
     return dqk
 
 

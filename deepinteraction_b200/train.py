@@ -12,8 +12,11 @@ di_bn_bwd_f32 + the weight / input products.  The window attention runs in the u
 the [P, 81] weights kept for the backward; I2P, BEVWarp sampling and the 3x3 shared convolutions have no norm and
 reuse backward.py.
 
-Not covered: the attention dropout of MMRI_I2P (encoder_utils.py:223, p = 0.1 in the reference config) -- the step is
-the p = 0 one; the decoder's backward; the optimiser.  First-version kernels: every intermediate is materialised.
+The attention dropout of MMRI_I2P (encoder_utils.py:223, p = 0.1 in the reference config) is applied when a
+`dropout_seed` is given: the mask is a counter-based hash regenerated in the backward (di_i2p_attend_dropout_f32); it is
+not torch's Philox stream, so a step equals the reference's in distribution, and exactly when the same mask is used
+(tests/test_gpu_backward.py injects it into the oracle).  Not covered: the decoder's backward.  First-version kernels:
+every intermediate is materialised.
 """
 import torch
 
@@ -118,21 +121,23 @@ def _add(a, b):
     return ops.axpy(a.contiguous(), b.contiguous(), torch.ones(1, device=a.device))
 
 
-def encoder_train_step(enc, img_feats, pts_feats, img_metas, pts_metas, grad_fn, debug=None):
+def encoder_train_step(enc, img_feats, pts_feats, img_metas, pts_metas, grad_fn, debug=None, dropout_seed=None):
     """One training-mode forward + backward of DeepInteractionEncoder (base model).
 
     enc: mmri.DeepInteractionEncoder on the GPU (the parameter holder; its BatchNorm running statistics are updated as
     torch's training mode does).  img_feats (B*V, Ci, h, w), pts_feats (B, Cp, Y, X): NCHW inputs on the GPU.
     grad_fn(img [B*V,h,w,C], pts_conv [B,Y,X,C], pts [B,Y,X,C]) -> (d_img, d_pts_conv, d_pts), same shapes (None = zero):
     the gradient of the loss w.r.t. the three outputs (pixel-major), e.g. from the decoder.  debug: dict that receives the
-    per-layer branch outputs ('fwd') and their gradients ('bwd') as pixel-major rows.
+    per-layer branch outputs ('fwd') and their gradients ('bwd') as pixel-major rows.  dropout_seed: None = no attention
+    dropout in MMRI_I2P (deterministic step); an integer (e.g. the iteration number) = dropout with the module's rate
+    (`learnedAlign.dropout`, 0.1 in the reference config) and a mask derived from (seed, layer, pillar, key).
     -> dict(outputs=(img, pts_conv, pts), d_img_feats [B*V,h,w,Ci], d_pts_feats [B,Y,X,Cp],
             grads={parameter name: gradient} for every parameter of `enc` the output depends on)."""
     with bw._precise(), torch.no_grad(), fold.on_device():
-        return _encoder_train_step(enc, img_feats, pts_feats, img_metas, pts_metas, grad_fn, debug)
+        return _encoder_train_step(enc, img_feats, pts_feats, img_metas, pts_metas, grad_fn, debug, dropout_seed)
 
 
-def _encoder_train_step(enc, img_feats, pts_feats, img_metas, pts_metas, grad_fn, debug=None):
+def _encoder_train_step(enc, img_feats, pts_feats, img_metas, pts_metas, grad_fn, debug=None, dropout_seed=None):
     from . import mmri
     dev = img_feats.device
     C = enc.hidden_channel
@@ -159,7 +164,8 @@ def _encoder_train_step(enc, img_feats, pts_feats, img_metas, pts_metas, grad_fn
         M1, c1, M2, c2 = fold.i2p_fold(mha)
         L['i2p'] = (Wt(M1), d(c1), Wt(M2), d(c2))
         img_r, pts_r = img.view(-1, C), pts.view(-1, C)
-        i2p = enc.i2p(L, pts, img, pm, g)
+        L['drop'] = None if dropout_seed is None else (float(mha.dropout), int(dropout_seed) * 131 + len(layers))
+        i2p = enc.i2p(L, pts, img, pm, g, dropout=L['drop'])
         p2p = L['p_iml'].forward(pts_r, pts_r, B, Y, X)
         new_pts = L['p_fuse'].forward(i2p.view(-1, C), p2p, pts_r).view(B, Y, X, C)
         warped = ops.bev_sample(pts, g.grid, V)
@@ -182,7 +188,7 @@ def _encoder_train_step(enc, img_feats, pts_feats, img_metas, pts_metas, grad_fn
         d_i2p, d_p2p, d_pts_dir = L['p_fuse'].backward(gp, grads)
         t_ii, s_ii = L['i_iml'].backward(d_i2i, grads)
         t_pi, s_pi = L['p2i'].backward(d_p2i, grads)
-        r_ip = bw._i2p_backward(L['i2p'], L['pts'], L['img'], pm, g.proj, V, g.in_hw, d_i2p.view(B, Y, X, C))
+        r_ip = bw._i2p_backward(L['i2p'], L['pts'], L['img'], pm, g.proj, V, g.in_hw, d_i2p.view(B, Y, X, C), L['drop'])
         t_pp, s_pp = L['p_iml'].backward(d_p2p, grads)
         gi = _add(_add(_add(_add(d_img_dir, t_ii), s_ii), t_pi), r_ip['d_img'].view(-1, C))
         d_bev = ops.bev_sample_bwd(s_pi.view(BV, h, w, C).contiguous(), g.grid, V, (B, Y, X, C))

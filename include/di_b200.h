@@ -384,6 +384,17 @@ int di_bn_bwd_f32(const float* dz, const float* z, const float* y, long long M, 
 int di_i2p_attend_bwd_f32(const float* qk, const float* ds, const float* pillars, const int* npts, const int* coors,
                           const float* proj, const float* img, float* d_img, float* dqk, int P, int T, int pdim, int V, int h,
                           int w, int C, int H_in, int W_in, const int* n_dev, cudaStream_t stream);
+/* Training-mode variants with the attention dropout of nn.MultiheadAttention (encoder_utils.py:223; the softmax weights times
+ * keep / (1 - pdrop), keep = counter-based hash of (seed, pillar, key index), regenerated in the backward);
+ * di_i2p_dropout_mask_f32 writes those factors [P, S = T*V] (tests). */
+int di_i2p_attend_dropout_f32(const float* qk, const float* pillars, const int* npts, const int* coors, const float* proj,
+                              const float* img, float* s_out, int* cnt_out, int P, int T, int pdim, int V, int h, int w, int C,
+                              int H_in, int W_in, const int* n_dev, float pdrop, unsigned int seed, cudaStream_t stream);
+int di_i2p_attend_bwd_dropout_f32(const float* qk, const float* ds, const float* pillars, const int* npts, const int* coors,
+                                  const float* proj, const float* img, float* d_img, float* dqk, int P, int T, int pdim, int V,
+                                  int h, int w, int C, int H_in, int W_in, const int* n_dev, float pdrop, unsigned int seed,
+                                  cudaStream_t stream);
+int di_i2p_dropout_mask_f32(float* mask, int P, int S, float pdrop, unsigned int seed, cudaStream_t stream);
 /* backward of di_bev_sample_f32 w.r.t. the BEV map (encoder_utils.py:193-195 grid_sample): d_bev += bilinear scatter */
 int di_bev_sample_bwd_f32(const float* d_out, const float* grid_xy, float* d_bev, int B, int V, int hw, int Yb, int Xb, int C,
                           cudaStream_t stream);

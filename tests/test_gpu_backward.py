@@ -369,3 +369,85 @@ def test_encoder_train_step_matches_oracle_autograd():
             bad.append((name, e, e32))
     print('train step: %d parameter tensors, worst %s %.2e (fp32 autograd %.2e)' % (len(r['grads']), worst[1], worst[0], worst[2]))
     assert not bad, bad
+
+
+def _dropout_calls(coors, valid, chunk=2048):
+    """Row sets (global pillar indices) in the order oracle.mmri.MMRI_I2P calls the attention: per batch sample, valid pillars,
+    chunks of `chunk`."""
+    out = []
+    for b in range(int(coors[:, 0].max()) + 1):
+        idx = ((coors[:, 0] == b) & valid).nonzero().squeeze(1)
+        out += [idx[s:s + chunk] for s in range(0, idx.numel(), chunk)]
+    return out
+
+
+def test_i2p_attention_dropout_matches_oracle_with_the_same_mask(monkeypatch):
+    """Training-mode attention dropout of MMRI_I2P (nn.MultiheadAttention(dropout=p), encoder_utils.py:223): the product draws its
+    mask from a counter-based hash, torch from Philox, so the mask the kernels use (di_i2p_dropout_mask_f32) is injected into the
+    oracle's F.dropout; output and all gradients must then agree with autograd, and the keep rate must be 1 - p."""
+    import torch.nn.functional as F
+    import oracle.mmri as om
+    from deepinteraction_b200 import mmri, synth, fold, geom, backward, ops
+    from test_gpu_encoder import _cfg1_frame
+    seed, pdrop, dseed = 1100, 0.3, 20240917
+    torch.manual_seed(seed)
+    m = om.MMRI_I2P(64, 64, pdrop)
+    synth.randomize_norm_stats(m, seed)
+    m.train()
+    fr = _cfg1_frame(seed, True)
+    g = torch.Generator().manual_seed(seed)
+    pts = fr['pts_feats'].clone().requires_grad_(True)
+    img = fr['img_feats'].clone().requires_grad_(True)
+    B = pts.shape[0]
+    G = torch.randn(pts.shape, generator=g)
+    d = dev()
+    mha = m.learnedAlign
+    M1, c1, M2, c2 = fold.i2p_fold(mha)
+    pack = (fold.Weight(M1, d), fold.dev(c1, d), fold.Weight(M2, d), fold.dev(c2, d))
+    enc = mmri.DeepInteractionEncoder(1, 64, 64, 64)
+    pm = enc._canon_pts_metas(fr['pts_metas'], d)
+    proj, _ = geom.camera_rows(fr['img_metas'], d)
+    nhwc = lambda t: t.detach().permute(0, 2, 3, 1).contiguous().to(d)
+    P, T = pm['pillars'].shape[:2]
+    # ours: forward (through the module-level helper) and backward with dropout = (p, seed)
+    geo = type('G', (), dict(proj=proj, V=1, in_hw=(256, 256)))()
+    with backward._precise():
+        out = enc.i2p(dict(i2p=pack), nhwc(pts), nhwc(img), pm, geo, dropout=(pdrop, dseed))
+    r = backward.i2p_backward(pack, nhwc(pts), nhwc(img), pm, proj, 1, (256, 256), nhwc(G), dropout=(pdrop, dseed))
+    mask = ops.i2p_dropout_mask(P, T * 1, pdrop, dseed, d).cpu()
+    vals = mask.unique().tolist()
+    print('mask values', vals, 'keep rate %.4f' % float((mask > 0).float().mean()))
+    assert len(vals) == 2 and vals[0] == 0.0 and abs(vals[1] - 1.0 / (1.0 - pdrop)) < 1e-6
+    assert abs(float((mask > 0).float().mean()) - (1 - pdrop)) < 0.01
+    # the p = 0 variant of the dropout entry point is the plain kernel
+    rows = ops.gather_rows(nhwc(pts), pm['pillar_coors'])
+    qk = ops.linear([rows], pack[0], pack[1])
+    args = (qk, pm['pillars'], pm['pillars_num_points'], pm['pillar_coors'], proj, nhwc(img), 1, (256, 256))
+    s0, cnt = ops.i2p_attend(*args)
+    s1, _ = ops.i2p_attend(*args, dropout=(1e-30, 5))
+    print('p -> 0 variant vs plain kernel: %.2e' % rel_err(s1, s0))
+    assert rel_err(s1, s0) < 1e-6
+    # oracle with the same mask
+    calls = _dropout_calls(pm['pillar_coors'].cpu().long(), cnt.cpu() > 0)
+
+    def fake_dropout(x, p=0.5, training=True, inplace=False):
+        rows_ = calls.pop(0)
+        assert abs(p - pdrop) < 1e-12 and training and x.shape[0] == rows_.numel(), (p, x.shape, rows_.numel())
+        return x * mask[rows_].view(x.shape).to(x.dtype)
+    monkeypatch.setattr(F, 'dropout', fake_dropout)
+    with torch.enable_grad():
+        ref = m(pts, img.view(B, 1, *img.shape[1:]), fr['img_metas'], fr['pts_metas'])
+        (ref * G).sum().backward()
+    assert not calls
+    tol = 1e-4
+    e_out = rel_err(out.permute(0, 3, 1, 2).cpu(), ref.detach())
+    e_pts, e_img = rel_err(r['d_pts'].permute(0, 3, 1, 2).cpu(), pts.grad), rel_err(r['d_img'].permute(0, 3, 1, 2).cpu(), img.grad)
+    print('dropout step vs oracle with the same mask: out %.2e, d_pts %.2e, d_img %.2e' % (e_out, e_pts, e_img))
+    assert e_out < tol and e_pts < tol and e_img < tol
+    pg = fold.i2p_unfold_grads(mha, r['dM1'], r['dc1'], r['dM2'], r['dc2'])
+    Wq_g, Wk_g, Wv_g = (mha.in_proj_weight.grad.chunk(3, 0) if mha._qkv_same_embed_dim else
+                        (mha.q_proj_weight.grad, mha.k_proj_weight.grad, mha.v_proj_weight.grad))
+    bq_g, _, bv_g = mha.in_proj_bias.grad.chunk(3, 0)
+    for name, want in (('Wq', Wq_g), ('Wk', Wk_g), ('Wv', Wv_g), ('bq', bq_g), ('bv', bv_g),
+                       ('Wo', mha.out_proj.weight.grad), ('bo', mha.out_proj.bias.grad)):
+        assert rel_err(pg[name].float(), want) < tol, name
