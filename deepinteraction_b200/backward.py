@@ -126,7 +126,8 @@ def _i2p_backward(i2p_pack, pts_nhwc, img_nhwc, pts_metas, proj, V, in_hw, grad_
         z = lambda t: torch.zeros_like(t.w if hasattr(t, 'w') else t)
         return dict(d_pts=d_pts, d_img=d_img, dM1=z(M1), dc1=z(c1), dM2=z(M2), dc2=z(c2))
     dev = pts_nhwc.device
-    T_ = lambda Wt: fold.Weight(Wt.w.detach().t().contiguous(), dev, lazy=True)
+    # a plain tensor (the [C, C + 4] output weight of the dropout form) stays on the FFMA path
+    T_ = lambda Wt: (fold.Weight(Wt.w.detach().t().contiguous(), dev, lazy=True) if hasattr(Wt, 'w') else Wt.detach().t().contiguous())
     # forward intermediates
     rows = ops.gather_rows(pts_nhwc, coors)
     qk = ops.linear([rows], M1, c1)

@@ -114,7 +114,7 @@ i2p_attend_body(const float* __restrict__ qk, const float* __restrict__ pillars,
     q[j] = c < C ? ldg4(qk + (size_t)p * C + c) : make_float4(0, 0, 0, 0);
     acc[j] = make_float4(0, 0, 0, 0);
   }
-  float mrun = -INFINITY, lrun = 0.f;
+  float mrun = -INFINITY, lrun = 0.f, rrun = 0.f;
   int count = 0;
 #pragma unroll
   for (int s = 0; s < NS; ++s) {
@@ -136,7 +136,10 @@ i2p_attend_body(const float* __restrict__ qk, const float* __restrict__ pillars,
       float corr = expf(mrun - mnew);
       float pw = expf(logit - mnew);
       lrun = lrun * corr + pw;
-      if (DROP) pw *= i2p_keep_scale(seed, p, s * 32 + src, pdrop);      // the normaliser keeps the dropped keys
+      if (DROP) {
+        pw *= i2p_keep_scale(seed, p, s * 32 + src, pdrop);               // the normaliser keeps the dropped keys
+        rrun = rrun * corr + pw;
+      }
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
         acc[j].x = acc[j].x * corr + pw * kv[j].x;
@@ -149,13 +152,17 @@ i2p_attend_body(const float* __restrict__ qk, const float* __restrict__ pillars,
     }
   }
   float inv = count > 0 ? 1.f / lrun : 0.f;
+  // DROP: rows of C + 4 floats; column C carries rho = sum_j a_j m_j (the weights no longer sum to 1, and the value bias of
+  // nn.MultiheadAttention is weighted by that sum: out = W_o W_v s + rho W_o b_v + b_o), columns C+1..C+3 are 0
+  const int ld = DROP ? C + 4 : C;
 #pragma unroll
   for (int j = 0; j < NJ; ++j) {
     int c = 4 * lane + 128 * j;
     if (c < C)
-      *reinterpret_cast<float4*>(s_out + (size_t)p * C + c) =
+      *reinterpret_cast<float4*>(s_out + (size_t)p * ld + c) =
           make_float4(acc[j].x * inv, acc[j].y * inv, acc[j].z * inv, acc[j].w * inv);
   }
+  if (DROP && lane == 0) *reinterpret_cast<float4*>(s_out + (size_t)p * ld + C) = make_float4(rrun * inv, 0.f, 0.f, 0.f);
   if (lane == 0) cnt_out[p] = count;
 }
 
@@ -261,9 +268,10 @@ i2p_attend_bwd_body(const float* __restrict__ qk, const float* __restrict__ ds, 
   for (int j = 0; j < NJ; ++j) {
     int c = 4 * lane + 128 * j;
     q[j] = c < C ? ldg4(qk + (size_t)p * C + c) : make_float4(0, 0, 0, 0);
-    g[j] = c < C ? ldg4(ds + (size_t)p * C + c) : make_float4(0, 0, 0, 0);
+    g[j] = c < C ? ldg4(ds + (size_t)p * (DROP ? C + 4 : C) + c) : make_float4(0, 0, 0, 0);
     acc[j] = make_float4(0, 0, 0, 0);
   }
+  const float drho = DROP ? __ldg(ds + (size_t)p * (C + 4) + C) : 0.f;     // gradient of rho (column C of the forward's rows)
   // pass A: logits and t_j
   int count = 0;
 #pragma unroll
@@ -305,7 +313,7 @@ i2p_attend_bwd_body(const float* __restrict__ qk, const float* __restrict__ ds, 
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
       lg[s] *= inv;                                    // a_j
-      if (DROP) tv[s] *= i2p_keep_scale(seed, p, s * 32 + lane, pdrop);    // s = sum a_j m_j k_j: t_j -> m_j t_j
+      if (DROP) tv[s] = (tv[s] + drho) * i2p_keep_scale(seed, p, s * 32 + lane, pdrop);   // [s, rho] = sum a_j m_j [k_j, 1]
       D += lg[s] * tv[s];
     }
     D = warp_sum(D);
@@ -813,6 +821,7 @@ int di_i2p_attend_bwd_f32(const float* qk, const float* ds, const float* pillars
 }
 
 // Training-mode variants with attention dropout (pdrop in [0, 1), mask = hash(seed, pillar, key); see i2p_keep_scale).
+// s_out (forward) and ds (backward) are [P, C + 4] here: column C = rho = sum_j a_j m_j resp. its gradient, C+1..C+3 = 0.
 int di_i2p_attend_dropout_f32(const float* qk, const float* pillars, const int* npts, const int* coors, const float* proj,
                               const float* img, float* s_out, int* cnt_out, int P, int T, int pdim, int V, int h, int w, int C,
                               int H_in, int W_in, const int* n_dev, float pdrop, unsigned int seed, cudaStream_t stream) {

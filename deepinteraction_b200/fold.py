@@ -62,9 +62,11 @@ def fuse_pair(out_proj, integration):
     return torch.cat([W2a @ W1, W2b], 1), W2a @ b1 + b2
 
 
-def i2p_fold(mha):
+def i2p_fold(mha, split_bias=False):
     """nn.MultiheadAttention (1 head) -> M1 [Ck, Cq], c1, M2 [Cq, Ck], c2 with
-    qk = M1 q + c1;  out = M2 (sum_j a_j k_j) + c2."""
+    qk = M1 q + c1;  out = M2 (sum_j a_j k_j) + c2.
+    split_bias (attention dropout, weights a_j m_j that no longer sum to 1): -> M1, c1, M2x [Cq, Ck + 4], b_o with
+    out = M2x [s, rho, 0, 0, 0] + b_o, s = sum_j a_j m_j k_j, rho = sum_j a_j m_j, M2x = [W_o W_v | W_o b_v | 0 0 0]."""
     E = mha.embed_dim
     assert mha.num_heads == 1
     if mha._qkv_same_embed_dim:
@@ -77,6 +79,8 @@ def i2p_fold(mha):
     M1 = Wk.T @ Wq * s
     c1 = Wk.T @ bq * s
     M2 = Wo @ Wv
+    if split_bias:
+        return M1, c1, torch.cat([M2, (Wo @ bv)[:, None], torch.zeros_like(M2[:, :3])], 1), bo
     c2 = Wo @ bv + bo
     return M1, c1, M2, c2
 
@@ -94,9 +98,13 @@ def i2p_unfold_grads(mha, dM1, dc1, dM2, dc2):
     Wo = _d(mha.out_proj.weight)
     s = 1.0 / math.sqrt(E)
     dM1, dc1, dM2, dc2 = (_d(t) for t in (dM1, dc1, dM2, dc2))
+    dbo = dc2
+    Ck = Wv.shape[1]
+    if dM2.shape[1] == Ck + 4:                 # i2p_fold(split_bias=True): column Ck is d(W_o b_v), dc2 is d b_o alone
+        dM2, dc2 = dM2[:, :Ck], dM2[:, Ck]
     # M1 = s Wk^T Wq, c1 = s Wk^T bq, M2 = Wo Wv, c2 = Wo bv + bo
     return dict(Wq=s * Wk @ dM1, bq=s * Wk @ dc1, Wk=s * (Wq @ dM1.T + torch.outer(bq, dc1)), bk=torch.zeros_like(bk),
-                Wv=Wo.T @ dM2, Wo=dM2 @ Wv.T + torch.outer(dc2, bv), bv=Wo.T @ dc2, bo=dc2)
+                Wv=Wo.T @ dM2, Wo=dM2 @ Wv.T + torch.outer(dc2, bv), bv=Wo.T @ dc2, bo=dbo)
 
 
 def dev(t, device):

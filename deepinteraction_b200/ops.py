@@ -385,7 +385,8 @@ def axpy(a, b, scale):
 
 
 def i2p_attend(qk, pillars, npts, coors, proj, img_nhwc, V, in_hw, n_dev=None, dropout=None):
-    """dropout = (p, seed): training-mode attention dropout (mask = hash(seed, pillar, key), see i2p_dropout_mask)."""
+    """dropout = (p, seed): training-mode attention dropout (mask = hash(seed, pillar, key), see i2p_dropout_mask); s is then
+    [P, C + 4] with rho = sum_j a_j m_j in column C (fold.i2p_fold(split_bias=True) gives the matching [C, C + 4] weight)."""
     P, C = qk.shape
     _, T, pdim = pillars.shape
     BV, h, w, Ci = img_nhwc.shape
@@ -396,6 +397,7 @@ def i2p_attend(qk, pillars, npts, coors, proj, img_nhwc, V, in_hw, n_dev=None, d
         s.zero_()                       # rows beyond the live count feed a dense layer: keep them finite
     nb = 4 * (2 * P * C + pillars.numel() + img_nhwc.numel())
     if dropout is not None and dropout[0] > 0:
+        s = torch.empty(P, C + 4, device=qk.device, dtype=torch.float32)
         _call('di_i2p_attend_dropout_f32', _ptr(qk), _ptr(pillars), _ptr(npts), _ptr(coors), _ptr(proj), _ptr(img_nhwc), _ptr(s),
               _ptr(cnt), P, T, pdim, V, h, w, C, in_hw[0], in_hw[1], _ptr(n_dev), float(dropout[0]), int(dropout[1]) & 0xFFFFFFFF,
               _stream(), nbytes=nb)
@@ -788,6 +790,7 @@ def i2p_attend_bwd(qk, ds, pillars, npts, coors, proj, img_nhwc, d_img, V, in_hw
     dqk = torch.empty(P, C, device=qk.device, dtype=torch.float32)
     nb = 4 * (3 * P * C + pillars.numel() + 2 * img_nhwc.numel())
     if dropout is not None and dropout[0] > 0:
+        assert ds.shape == (P, C + 4), ds.shape
         _call('di_i2p_attend_bwd_dropout_f32', _ptr(qk), _ptr(ds), _ptr(pillars), _ptr(npts), _ptr(coors), _ptr(proj),
               _ptr(img_nhwc), _ptr(d_img), _ptr(dqk), P, T, pdim, V, h, w, C, in_hw[0], in_hw[1], None, float(dropout[0]),
               int(dropout[1]) & 0xFFFFFFFF, _stream(), nbytes=nb)

@@ -386,7 +386,8 @@ int di_i2p_attend_bwd_f32(const float* qk, const float* ds, const float* pillars
                           int w, int C, int H_in, int W_in, const int* n_dev, cudaStream_t stream);
 /* Training-mode variants with the attention dropout of nn.MultiheadAttention (encoder_utils.py:223; the softmax weights times
  * keep / (1 - pdrop), keep = counter-based hash of (seed, pillar, key index), regenerated in the backward);
- * di_i2p_dropout_mask_f32 writes those factors [P, S = T*V] (tests). */
+ * s_out / ds are [P, C + 4]: column C carries rho = sum_j a_j m_j (the weights no longer sum to 1 and the value bias of the
+ * attention is weighted by that sum) resp. its gradient.  di_i2p_dropout_mask_f32 writes the factors [P, S = T*V] (tests). */
 int di_i2p_attend_dropout_f32(const float* qk, const float* pillars, const int* npts, const int* coors, const float* proj,
                               const float* img, float* s_out, int* cnt_out, int P, int T, int pdim, int V, int h, int w, int C,
                               int H_in, int W_in, const int* n_dev, float pdrop, unsigned int seed, cudaStream_t stream);

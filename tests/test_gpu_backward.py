@@ -402,8 +402,9 @@ def test_i2p_attention_dropout_matches_oracle_with_the_same_mask(monkeypatch):
     G = torch.randn(pts.shape, generator=g)
     d = dev()
     mha = m.learnedAlign
-    M1, c1, M2, c2 = fold.i2p_fold(mha)
-    pack = (fold.Weight(M1, d), fold.dev(c1, d), fold.Weight(M2, d), fold.dev(c2, d))
+    # dropout form of the fold: out = M2x [s, rho, 0, 0, 0] + b_o with rho = sum_j a_j m_j (the value bias is weighted by it)
+    M1, c1, M2x, bo = fold.i2p_fold(mha, split_bias=True)
+    pack = (fold.Weight(M1, d), fold.dev(c1, d), fold.dev(M2x, d), fold.dev(bo, d))
     enc = mmri.DeepInteractionEncoder(1, 64, 64, 64)
     pm = enc._canon_pts_metas(fr['pts_metas'], d)
     proj, _ = geom.camera_rows(fr['img_metas'], d)
@@ -425,8 +426,10 @@ def test_i2p_attention_dropout_matches_oracle_with_the_same_mask(monkeypatch):
     args = (qk, pm['pillars'], pm['pillars_num_points'], pm['pillar_coors'], proj, nhwc(img), 1, (256, 256))
     s0, cnt = ops.i2p_attend(*args)
     s1, _ = ops.i2p_attend(*args, dropout=(1e-30, 5))
-    print('p -> 0 variant vs plain kernel: %.2e' % rel_err(s1, s0))
-    assert rel_err(s1, s0) < 1e-6
+    rho = s1[:, 64]
+    print('p -> 0 variant vs plain kernel: %.2e, rho in [%.7f, %.7f]' % (rel_err(s1[:, :64], s0), float(rho[cnt > 0].min()), float(rho.max())))
+    assert s1.shape == (P, 68) and rel_err(s1[:, :64], s0) < 1e-6 and float(s1[:, 65:].abs().max()) == 0.0
+    assert float((rho[cnt > 0] - 1).abs().max()) < 1e-6 and float(rho[cnt == 0].abs().max()) == 0.0
     # oracle with the same mask
     calls = _dropout_calls(pm['pillar_coors'].cpu().long(), cnt.cpu() > 0)
 

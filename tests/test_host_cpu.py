@@ -81,6 +81,37 @@ def test_i2p_unfold_grads_is_the_chain_rule_of_the_fold():
     assert all(torch.equal(u[k], u2[k]) for k in u)
 
 
+def test_i2p_fold_with_attention_dropout(monkeypatch):
+    """Dropout multiplies the softmax weights by m_j / (1 - p) AFTER normalisation, so they no longer sum to 1 and the value
+    bias is weighted by rho = sum_j a_j m_j: fold.i2p_fold(split_bias=True) / i2p_unfold_grads against nn.MultiheadAttention in
+    training mode with the same mask injected into F.dropout (forward and every parameter gradient, float64)."""
+    import torch.nn.functional as F
+    from deepinteraction_b200 import fold
+    torch.manual_seed(5)
+    C, P, S, pd = 16, 9, 6, 0.3
+    mha = torch.nn.MultiheadAttention(C, 1, dropout=pd, kdim=C, vdim=C, batch_first=True).double().train()
+    with torch.no_grad():
+        mha.in_proj_bias.normal_(0, 0.3)
+        mha.out_proj.bias.normal_(0, 0.3)
+    q, kv, G = torch.randn(P, 1, C).double(), torch.randn(P, S, C).double(), torch.randn(P, C).double()
+    mask = (torch.rand(P, S) >= pd).double() / (1 - pd)
+    monkeypatch.setattr(F, 'dropout', lambda x, p=0.5, training=True, inplace=False: x * mask.view(x.shape))
+    ref = mha(q, kv, kv)[0][:, 0]
+    (ref * G).sum().backward()
+    monkeypatch.undo()
+    M1, c1, M2x, bo = (t.clone().requires_grad_(True) for t in fold.i2p_fold(mha, split_bias=True))
+    assert M2x.shape == (C, C + 4)
+    a = torch.einsum('pc,pkc->pk', q[:, 0] @ M1.t() + c1, kv).softmax(-1) * mask
+    s_ext = torch.cat([torch.einsum('pk,pkc->pc', a, kv), a.sum(1, keepdim=True), torch.zeros(P, 3).double()], 1)
+    out = s_ext @ M2x.t() + bo
+    assert rel_err(out.detach(), ref.detach()) < 1e-12
+    (out * G).sum().backward()
+    u = fold.i2p_unfold_grads(mha, M1.grad, c1.grad, M2x.grad, bo.grad)
+    W, b = torch.cat([u['Wq'], u['Wk'], u['Wv']], 0), torch.cat([u['bq'], u['bk'], u['bv']], 0)
+    assert rel_err(W, mha.in_proj_weight.grad) < 1e-10 and rel_err(b, mha.in_proj_bias.grad) < 1e-10
+    assert rel_err(u['Wo'], mha.out_proj.weight.grad) < 1e-10 and rel_err(u['bo'], mha.out_proj.bias.grad) < 1e-10
+
+
 def test_lazy_weight_equals_eager_weight():
     from deepinteraction_b200 import fold
     w = torch.randn(24, 40, generator=torch.Generator().manual_seed(3))
