@@ -161,14 +161,15 @@ def _encoder_train_step(enc, img_feats, pts_feats, img_metas, pts_metas, grad_fn
         L = dict(p_iml=LCABTrain(blk.P_IML), p2i=LCABTrain(blk.P2I_block.Local), i_iml=LCABTrain(blk.I_IML),
                  p_fuse=FuseTrain(blk.P_out_proj, blk.P_integration), i_fuse=FuseTrain(blk.I_out_proj, blk.I_integration))
         mha = blk.I2P_block.learnedAlign
-        if dropout_seed is None:
+        use_drop = dropout_seed is not None and float(mha.dropout) > 0
+        if not use_drop:
             M1, c1, M2, c2 = fold.i2p_fold(mha)
             L['i2p'] = (Wt(M1), d(c1), Wt(M2), d(c2))
         else:                                   # dropout form: [C, C + 4] output weight (FFMA path), bias = b_o alone
             M1, c1, M2x, bo = fold.i2p_fold(mha, split_bias=True)
             L['i2p'] = (Wt(M1), d(c1), d(M2x), d(bo))
         img_r, pts_r = img.view(-1, C), pts.view(-1, C)
-        L['drop'] = None if dropout_seed is None else (float(mha.dropout), int(dropout_seed) * 131 + len(layers))
+        L['drop'] = (float(mha.dropout), int(dropout_seed) * 131 + len(layers)) if use_drop else None
         i2p = enc.i2p(L, pts, img, pm, g, dropout=L['drop'])
         p2p = L['p_iml'].forward(pts_r, pts_r, B, Y, X)
         new_pts = L['p_fuse'].forward(i2p.view(-1, C), p2p, pts_r).view(B, Y, X, C)

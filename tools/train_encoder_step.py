@@ -5,7 +5,7 @@ encoder outputs, parameter gradients all-reduced over the ranks with shard.GradB
 --bn eval: BatchNorm folded (backward.encoder_backward; gradients of the folded weights).
 --bn train: BatchNorm with batch statistics (train.encoder_train_step; gradients of the module's own parameters), followed by
 a torch.optim.AdamW step on the encoder's parameters (the reference's optimiser, configs/nuscenes/Fusion_0075_refactor.py).
-The decoder's backward and the I2P attention dropout are not built (DESIGN.md section 1), so this is NOT the config-3 metric;
+--dropout adds the MMRI_I2P attention dropout.  The decoder's backward is not built (DESIGN.md section 1), so this is NOT the config-3 metric;
 it measures what exists: the encoder's training-side kernels and the path's one collective.
 
     python tools/train_encoder_step.py [--steps 5]                                    # 1 GPU
@@ -40,6 +40,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--bn', default='eval', choices=['eval', 'train'])
+    ap.add_argument('--dropout', action='store_true', help='--bn train: MMRI_I2P attention dropout (module rate, seed = step number)')
     ap.add_argument('--profile', action='store_true', help='after the timed steps: one more step with per-entry-point device times')
     args = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (('RANK', 0), ('WORLD_SIZE', 1), ('LOCAL_RANK', 0)))
@@ -80,8 +81,12 @@ def main():
             zero = [torch.zeros_like(t) for t in outs]
             return [ops.axpy(ops.axpy(z, t.contiguous(), two), tg, mtwo) for z, t, tg in zip(zero, outs, targets)]
 
+        it = [0]
+
         def step():                                                      # noqa: F811
-            r = train.encoder_train_step(neck, fr['img_feats'], fr['pts_feats'], fr['img_metas'], fr['pts_metas'], grad_fn)
+            it[0] += 1
+            r = train.encoder_train_step(neck, fr['img_feats'], fr['pts_feats'], fr['img_metas'], fr['pts_metas'], grad_fn,
+                                         dropout_seed=it[0] if args.dropout else None)
             buckets = GradBuckets()
             names = sorted(r['grads'])
             gl = [r['grads'][n].contiguous() for n in names]
