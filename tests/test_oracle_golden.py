@@ -91,6 +91,63 @@ def test_encoder_c128():
     assert rel_err(img, g['img']) < TOL and rel_err(p0, g['pts_conv']) < TOL and rel_err(p1, g['pts']) < TOL
 
 
+def _train_step(m, inputs, cots, call):
+    with torch.enable_grad():
+        xs = [x.clone().requires_grad_(True) for x in inputs]
+        outs = call(m, xs)
+        sum((o * c).sum() for o, c in zip(outs, cots)).backward()
+    return [o.detach() for o in outs], [x.grad for x in xs]
+
+
+def test_lcab_training_mode_matches_reference_golden():
+    """TRAINING mode (BatchNorm batch statistics over the whole call, the reference's autograd Functions around the window
+    ops): output, input / parameter gradients and the running statistics after the step equal the reference module's
+    (tools/make_goldens.py G9).  This pins the oracle that the product's training step is compared with on the GPU."""
+    g = load('lcab_train')
+    torch.manual_seed(g['seed'])
+    m = ommri.LocalContextAttentionBlock(32, 32, 9)
+    synth.randomize_norm_stats(m, g['seed'])
+    assert state_checksum(m.state_dict()) == g['checksum']
+    m.train()
+    gen = torch.Generator().manual_seed(g['seed'])
+    tgt, src, cot = (torch.randn(2, 32, 9, 12, generator=gen) for _ in range(3))
+    src[:, :, :2] = 0.0
+    outs, d_in = _train_step(m, [tgt, src], [cot], lambda mm, xs: [mm(xs[0], xs[1])])
+    assert rel_err(outs[0], g['outs'][0]) < 1e-6
+    assert all(rel_err(a, b) < 1e-6 for a, b in zip(d_in, g['d_in']))
+    for n, p in m.named_parameters():
+        assert rel_err(p.grad, g['grads'][n]) < 1e-5, n
+    for n, b in m.named_buffers():
+        assert rel_err(b.float(), g['buffers'][n].float()) < 1e-6, n
+
+
+def test_encoder_training_mode_matches_reference_golden():
+    """Whole base encoder in TRAINING mode (batch of 2, augmented frame, I2P attention dropout set to 0): outputs, running
+    statistics, input gradients and every parameter gradient vs the reference's own encoder."""
+    g = load('encoder_train')
+    torch.manual_seed(g['seed'])
+    m = ommri.DeepInteractionEncoder(2, 16, 24, 32)
+    synth.randomize_norm_stats(m, g['seed'])
+    assert state_checksum(m.state_dict()) == g['checksum']
+    m.train()
+    for blk in m.fusion_blocks:
+        blk.I2P_block.learnedAlign.dropout = 0.0
+    fr = small_frame(g['seed'], aug=True, views=2, batch=2)
+    gen = torch.Generator().manual_seed(g['seed'])
+    cots = [torch.randn(o.shape, generator=gen) for o in g['outs']]
+    call = lambda mm, xs: (lambda r: [r[0], r[1][0], r[1][1]])(mm(xs[0], xs[1], fr['img_metas'], fr['pts_metas']))
+    outs, d_in = _train_step(m, [fr['img_feats'], fr['pts_feats']], cots, call)
+    assert all(rel_err(a, b) < TOL for a, b in zip(outs, g['outs']))
+    assert all(rel_err(a, b) < 1e-4 for a, b in zip(d_in, g['d_in']))
+    for n, p in m.named_parameters():
+        if n.endswith('out_proj.bn.bias'):          # analytically zero (cancelled by the next layer's batch mean): rounding noise
+            assert float(p.grad.abs().max()) < 1e-3 and float(g['grads'][n].abs().max()) < 1e-3, n
+            continue
+        assert rel_err(p.grad, g['grads'][n]) < 1e-3, n
+    for n, b in m.named_buffers():
+        assert rel_err(b.float(), g['buffers'][n].float()) < 1e-5, n
+
+
 @pytest.mark.parametrize('tag', ['encoder_pp_small', 'encoder_pp_nopolar'])
 def test_encoder_plusplus(tag):
     """++ ("deformable") encoder, BASELINE config 4: oracle/mmri_pp.py vs the golden produced by the reference's own

@@ -90,9 +90,25 @@ def install_stubs(ref):
         lambda pcd, coords_type, img_meta, reverse=False: og.apply_3d_transformation(pcd, img_meta, reverse)
 
     # locatt_ops has no CPU path: semantics of kernels.cuh:4-80 via the oracle's shifted-MAC ops
+    # The three backward entry points (kernels.cuh:44-119, bound in similar.cu:43-92 / weighting.cu:44-121) are the vector-Jacobian
+    # products of the two forward ops, which are bilinear -- evaluated through autograd of the oracle's ops.  (The oracle's ops
+    # and the product's backward kernels are pinned to the reference's own CUDA extension in tests/test_gpu_backward.py.)
+    def _vjp(fn, wrt_like, cot):
+        with torch.enable_grad():
+            x = torch.zeros_like(wrt_like).requires_grad_(True)
+            return torch.autograd.grad(fn(x), x, cot)[0]
+
     class _LA:
         similar_forward = staticmethod(lambda q, k, kh, kw: ommri.window_similarity(q, k, kh))
         weighting_forward = staticmethod(lambda v, w, kh, kw: ommri.window_weighting(v, w, kh))
+        # similar_backward(x, grad, kH, kW, is_ori): is_ori -> x is x_loc, returns d x_ori; else x is x_ori, returns d x_loc
+        similar_backward = staticmethod(lambda x, g, kh, kw, is_ori: (
+            _vjp(lambda q: ommri.window_similarity(q, x, kh), x, g) if is_ori
+            else _vjp(lambda k: ommri.window_similarity(x, k, kh), x, g)))
+        # weighting_backward_ori(x_weight, grad): d v;  weighting_backward_weight(x_ori = v, grad): d weight
+        weighting_backward_ori = staticmethod(lambda w, g, kh, kw: _vjp(lambda v: ommri.window_weighting(v, w, kh), g, g))
+        weighting_backward_weight = staticmethod(lambda v, g, kh, kw: _vjp(
+            lambda w: ommri.window_weighting(v, w, kh), torch.zeros(v.shape[0], v.shape[2], v.shape[3], kh * kw, dtype=v.dtype), g))
     ops = sm['projects.mmdet3d_plugin.models.utils.ops']
     ops.locatt_ops = types.SimpleNamespace(localattention=_LA)
 
@@ -371,6 +387,65 @@ def main():
         print('encoder_c128 oracle vs reference', cmp(o_img, r_img), cmp(o_p0, r_p0), cmp(o_p1, r_p1))
         save('encoder_c128', dict(seed=seed, aug=True, checksum=state_checksum(om.state_dict()), img=r_img, pts_conv=r_p0,
                                   pts=r_p1))
+
+    # --- G9: TRAINING mode of the reference modules (BatchNorm batch statistics, the autograd wiring of the window Functions;
+    # I2P attention dropout set to 0 so the step is deterministic): outputs, running statistics after the step, input and
+    # parameter gradients of a fixed linear functional.  Pins the oracle's .train() behaviour (tests/test_oracle_golden.py),
+    # which is what the product's training step is compared with on the GPU.
+    def train_step(m, inputs, cots, call):
+        """-> outputs, grads of sum(out * cot) w.r.t. inputs and parameters, state after the step"""
+        with torch.enable_grad():
+            xs = [x.clone().requires_grad_(True) for x in inputs]
+            outs = call(m, xs)
+            sum((o * c).sum() for o, c in zip(outs, cots)).backward()
+        return dict(outs=[o.detach() for o in outs], d_in=[x.grad for x in xs],
+                    grads={n: p.grad.clone() for n, p in m.named_parameters()},
+                    buffers={n: b.clone() for n, b in m.named_buffers()})
+
+    if not only or 'lcab_train' in only:
+        seed = 1810
+        torch.manual_seed(seed)
+        om = ommri.LocalContextAttentionBlock(32, 32, 9)
+        synth.randomize_norm_stats(om, seed)
+        rm = eu.LocalContextAttentionBlock(32, 32, 9)
+        rm.load_state_dict(om.state_dict(), strict=True)
+        ck = state_checksum(om.state_dict())
+        om.train(), rm.train()
+        g = torch.Generator().manual_seed(seed)
+        tgt, src, cot = (torch.randn(2, 32, 9, 12, generator=g) for _ in range(3))
+        src[:, :, :2] = 0.0
+        call = lambda m, xs: [m(xs[0], xs[1])]
+        r, o = train_step(rm, [tgt, src], [cot], call), train_step(om, [tgt, src], [cot], call)
+        print('lcab_train oracle vs reference: out', cmp(o['outs'][0], r['outs'][0]), 'd_in',
+              [cmp(a, b) for a, b in zip(o['d_in'], r['d_in'])], 'worst param grad',
+              max(cmp(o['grads'][n], r['grads'][n]) for n in r['grads']))
+        save('lcab_train', dict(seed=seed, checksum=ck, **r))          # inputs / cotangent: regenerated from the seed
+
+    if not only or 'encoder_train' in only:
+        seed = 1820
+        torch.manual_seed(seed)
+        om = ommri.DeepInteractionEncoder(2, 16, 24, 32)
+        synth.randomize_norm_stats(om, seed)
+        rm = enc.DeepInteractionEncoder(num_layers=2, in_channels_img=16, in_channels_pts=24, hidden_channel=32)
+        rm.load_state_dict(om.state_dict(), strict=True)
+        ck = state_checksum(om.state_dict())
+        for m in (om, rm):
+            m.train()
+            for blk in m.fusion_blocks:
+                blk.I2P_block.learnedAlign.dropout = 0.0
+        fr = small_frame(seed, aug=True, views=2, batch=2)
+        g = torch.Generator().manual_seed(seed)
+        call = lambda m, xs: (lambda r_: [r_[0], r_[1][0], r_[1][1]])(m(xs[0], xs[1], fr['img_metas'], fr['pts_metas']))
+        with torch.no_grad():
+            shapes = [t.shape for t in call(ommri.DeepInteractionEncoder(2, 16, 24, 32).eval(), [fr['img_feats'], fr['pts_feats']])]
+        cots = [torch.randn(sh, generator=g) for sh in shapes]
+        r = train_step(rm, [fr['img_feats'], fr['pts_feats']], cots, call)
+        o = train_step(om, [fr['img_feats'], fr['pts_feats']], cots, call)
+        print('encoder_train oracle vs reference: outs', [cmp(a, b) for a, b in zip(o['outs'], r['outs'])], 'd_in',
+              [cmp(a, b) for a, b in zip(o['d_in'], r['d_in'])], 'worst param grad',
+              max((cmp(o['grads'][n], r['grads'][n]), n) for n in r['grads'] if not n.endswith('out_proj.bn.bias')),
+              'worst running stat', max(cmp(o['buffers'][n].float(), r['buffers'][n].float()) for n in r['buffers']))
+        save('encoder_train', dict(seed=seed, checksum=ck, **r))       # frame / cotangents: regenerated from the seed
 
     # --- G5: decoder (hidden 128 is hard-coded in DynamicConv) ----------------------------------------
     for tag, aug in (('decoder_small', False), ('decoder_small_aug', True)):
