@@ -1,6 +1,8 @@
-"""Backward of LocalContextAttentionBlock on the GPU (deepinteraction_b200/backward.py + csrc/lcab_bwd.cu):
-window kernels against the reference's own CUDA extension (oracle/_ref) and the CPU oracle's autograd, the block's
-input / parameter gradients against autograd through oracle.mmri.LocalContextAttentionBlock (BatchNorm in eval mode)."""
+"""Training side on the GPU (deepinteraction_b200/{backward,train}.py + csrc/{lcab_bwd,bn_train}.cu, the I2P kernels of
+geometry.cu): window kernels against the reference's own CUDA extension (oracle/_ref) and the CPU oracle's autograd; input /
+parameter gradients of the attention blocks and of the whole encoder against autograd through the oracle with BatchNorm in
+eval mode (folded weights) and in training mode (batch statistics; the oracle's .train() behaviour is itself pinned to the
+reference by tests/golden/{lcab,encoder}_train.pt); the I2P attention dropout with the product's mask injected into the oracle."""
 import os
 import sys
 
