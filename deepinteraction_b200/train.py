@@ -115,13 +115,29 @@ class FuseTrain:
         return d1[:, :C].contiguous(), d1[:, C:].contiguous(), d2[:, C:].contiguous()
 
 
+class GradSink(dict):
+    """Gradient store that reports every parameter gradient the moment the backward produces it (last layer first), e.g. to
+    shard.GradBuckets.add -- so the all-reduce of full buckets overlaps the rest of the backward (the reference
+    gets this from MMDistributedDataParallel).  on_grad(name, tensor): tensor is the contiguous gradient kept in this dict; an
+    in-place update of it (the averaged result) is what encoder_train_step returns."""
+
+    def __init__(self, names, on_grad):
+        super().__init__()
+        self.names, self.on_grad = names, on_grad
+
+    def __setitem__(self, key, grad):
+        grad = grad.contiguous()
+        super().__setitem__(key, grad)
+        self.on_grad(self.names[key], grad)
+
+
 def _add(a, b):
     if a is None or b is None:
         return b if a is None else a
     return ops.axpy(a.contiguous(), b.contiguous(), torch.ones(1, device=a.device))
 
 
-def encoder_train_step(enc, img_feats, pts_feats, img_metas, pts_metas, grad_fn, debug=None, dropout_seed=None):
+def encoder_train_step(enc, img_feats, pts_feats, img_metas, pts_metas, grad_fn, debug=None, dropout_seed=None, on_grad=None):
     """One training-mode forward + backward of DeepInteractionEncoder (base model).
 
     enc: mmri.DeepInteractionEncoder on the GPU (the parameter holder; its BatchNorm running statistics are updated as
@@ -131,13 +147,15 @@ def encoder_train_step(enc, img_feats, pts_feats, img_metas, pts_metas, grad_fn,
     per-layer branch outputs ('fwd') and their gradients ('bwd') as pixel-major rows.  dropout_seed: None = no attention
     dropout in MMRI_I2P (deterministic step); an integer (e.g. the iteration number) = dropout with the module's rate
     (`learnedAlign.dropout`, 0.1 in the reference config) and a mask derived from (seed, layer, pillar, key).
+    on_grad(name, tensor): called for every parameter gradient as soon as the backward has it (GradSink), e.g.
+    `lambda n, t: buckets.add(t)` to overlap the bucketed all-reduce with the backward.
     -> dict(outputs=(img, pts_conv, pts), d_img_feats [B*V,h,w,Ci], d_pts_feats [B,Y,X,Cp],
             grads={parameter name: gradient} for every parameter of `enc` the output depends on)."""
     with bw._precise(), torch.no_grad(), fold.on_device():
-        return _encoder_train_step(enc, img_feats, pts_feats, img_metas, pts_metas, grad_fn, debug, dropout_seed)
+        return _encoder_train_step(enc, img_feats, pts_feats, img_metas, pts_metas, grad_fn, debug, dropout_seed, on_grad)
 
 
-def _encoder_train_step(enc, img_feats, pts_feats, img_metas, pts_metas, grad_fn, debug=None, dropout_seed=None):
+def _encoder_train_step(enc, img_feats, pts_feats, img_metas, pts_metas, grad_fn, debug=None, dropout_seed=None, on_grad=None):
     from . import mmri
     dev = img_feats.device
     C = enc.hidden_channel
@@ -185,7 +203,8 @@ def _encoder_train_step(enc, img_feats, pts_feats, img_metas, pts_metas, grad_fn
     outputs = (img, pts_conv, pts)
     d_img, d_pts_conv, d_pts = grad_fn(*outputs)
     # ---- backward
-    grads = {}
+    names = {id(p): n for n, p in enc.named_parameters()}
+    grads = {} if on_grad is None else GradSink(names, on_grad)
     gi = d_img.reshape(-1, C).contiguous() if d_img is not None else torch.zeros(BV * h * w, C, device=dev)
     gp = d_pts.reshape(-1, C).contiguous() if d_pts is not None else torch.zeros(B * Y * X, C, device=dev)
     for L in reversed(layers):
@@ -217,6 +236,5 @@ def _encoder_train_step(enc, img_feats, pts_feats, img_metas, pts_metas, grad_fn
     d_pts_feats = ops.conv3x3(gp.view(B, Y, X, C), wtp, None, cout=Cp, x_nhwc=True)
     for conv, x, gr in ((enc.shared_conv_img, img_feats, gi), (enc.shared_conv_pts, pts_feats, gp)):
         grads[id(conv.weight)], grads[id(conv.bias)] = bw.conv3x3_wgrad(x, gr, C)
-    names = {id(p): n for n, p in enc.named_parameters()}
     return dict(outputs=outputs, d_img_feats=d_img_feats, d_pts_feats=d_pts_feats,
                 grads={names[k]: v for k, v in grads.items()})

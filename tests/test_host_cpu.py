@@ -112,6 +112,25 @@ def test_i2p_fold_with_attention_dropout(monkeypatch):
     assert rel_err(u['Wo'], mha.out_proj.weight.grad) < 1e-10 and rel_err(u['bo'], mha.out_proj.bias.grad) < 1e-10
 
 
+def test_grad_sink_reports_gradients_in_backward_order_to_the_buckets():
+    """train.GradSink hands every parameter gradient to the callback when it is produced (so shard.GradBuckets can launch full
+    buckets during the backward) and keeps the contiguous tensor the buckets later overwrite with the averaged result."""
+    from deepinteraction_b200.shard import GradBuckets
+    from deepinteraction_b200.train import GradSink
+    ps = [torch.nn.Parameter(torch.zeros(3, 2)), torch.nn.Parameter(torch.zeros(5)), torch.nn.Parameter(torch.zeros(2, 2))]
+    names = {id(p): 'p%d' % i for i, p in enumerate(ps)}
+    buckets, order = GradBuckets(bucket_bytes=32), []
+    sink = GradSink(names, lambda n, t: (order.append(n), buckets.add(t)))
+    sink[id(ps[2])] = torch.full((2, 2), 2.0)
+    sink[id(ps[0])] = torch.arange(6.0).view(2, 3).t()              # a non-contiguous gradient is stored contiguous
+    assert buckets.launched == 1                                    # 16 + 24 bytes >= 32: launched before the last gradient exists
+    sink[id(ps[1])] = torch.ones(5)
+    buckets.finish()
+    assert order == ['p2', 'p0', 'p1'] and buckets.launched == 2
+    assert all(t.is_contiguous() for t in sink.values())
+    assert torch.equal(sink[id(ps[0])], torch.arange(6.0).view(2, 3).t()) and torch.equal(sink[id(ps[1])], torch.ones(5))
+
+
 def test_lazy_weight_equals_eager_weight():
     from deepinteraction_b200 import fold
     w = torch.randn(24, 40, generator=torch.Generator().manual_seed(3))

@@ -85,15 +85,12 @@ def main():
 
         def step():                                                      # noqa: F811
             it[0] += 1
+            buckets = GradBuckets()                 # buckets fill in backward order and are all-reduced while the backward continues
             r = train.encoder_train_step(neck, fr['img_feats'], fr['pts_feats'], fr['img_metas'], fr['pts_metas'], grad_fn,
-                                         dropout_seed=it[0] if args.dropout else None)
-            buckets = GradBuckets()
-            names = sorted(r['grads'])
-            gl = [r['grads'][n].contiguous() for n in names]
-            for t in gl:
-                buckets.add(t)
+                                         dropout_seed=it[0] if args.dropout else None, on_grad=lambda n, t: buckets.add(t))
             buckets.finish()
-            for n, t in zip(names, gl):
+            gl = list(r['grads'].values())
+            for n, t in r['grads'].items():
                 params[n].grad = t.view_as(params[n])
             opt.step()
             return gl, buckets.launched
