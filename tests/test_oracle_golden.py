@@ -245,6 +245,18 @@ def test_loss_path(tag):
     assert torch.equal(tg[7], t['heatmap'])
 
 
+def test_heuristic_assigner_matches_reference_golden():
+    """HeuristicAssigner3D (hungarian_assigner.py:50-91) run unmodified by tools/make_goldens.py (G10): assigned indices and labels
+    bit-equal, matched IoUs to 1e-6 -- with and without the same-class constraint, incl. two boxes competing for one prediction."""
+    import oracle.loss as ol
+    g = load('heuristic_assign')
+    for name, q in (('plain', None), ('same_class', g['query_labels'])):
+        r = ol.HeuristicAssigner3D(dist_thre=g['dist_thre']).assign(g['pred'], g['gt'], None, g['gt_labels'], q)
+        want = g['cases'][name]
+        assert torch.equal(r.gt_inds, want['gt_inds']) and torch.equal(r.labels, want['labels']), name
+        assert float((r.max_overlaps - want['max_overlaps']).abs().max()) < 1e-6 and int((r.gt_inds > 0).sum()) > 20, name
+
+
 def test_rotated_iou_known_answers():
     import oracle.loss as ol
     a = torch.tensor([[0., 0., 0., 2., 2., 1., 0.], [0., 0., 0., 2., 2., 1., 0.7853981634], [5., 5., 0., 1., 1., 1., 0.3]])

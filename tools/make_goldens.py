@@ -447,6 +447,30 @@ def main():
               'worst running stat', max(cmp(o['buffers'][n].float(), r['buffers'][n].float()) for n in r['buffers']))
         save('encoder_train', dict(seed=seed, checksum=ck, **r))       # frame / cotangents: regenerated from the seed
 
+    # --- G10: HeuristicAssigner3D (hungarian_assigner.py:50-91) run unmodified (its IoU calculator is the restated BboxOverlaps3D) ---
+    if not only or 'heuristic_assign' in only:
+        ha = sys.modules['projects.mmdet3d_plugin.core.bbox.assigners.hungarian_assigner']
+        g = torch.Generator().manual_seed(1900)
+
+        def boxes(n, spread):
+            xy = torch.rand(n, 2, generator=g) * 2 * spread - spread
+            z = torch.rand(n, 1, generator=g) * 2 - 2.5
+            dims = torch.stack([torch.rand(n, generator=g) * 2 + 1, torch.rand(n, generator=g) * 4 + 2, torch.rand(n, generator=g) + 1.2], 1)
+            return torch.cat([xy, z, dims, torch.rand(n, 1, generator=g) * 6.2 - 3.1, torch.randn(n, 2, generator=g)], 1)
+        pred = boxes(150, 30.0)
+        gt = torch.cat([boxes(22, 30.0), pred[:8] + 0.3 * torch.randn(8, 9, generator=g)], 0)
+        gt[:, 3:6] = gt[:, 3:6].abs() + 0.5
+        gt[5, :2] = gt[4, :2] + 0.01                        # two boxes compete for one prediction
+        gl, ql = torch.randint(0, 4, (30,), generator=g), torch.randint(0, 4, (150,), generator=g)
+        cases = {}
+        for name, q in (('plain', None), ('same_class', ql)):
+            r = ha.HeuristicAssigner3D(dist_thre=20).assign(pred, gt, None, gl, q)
+            o = oloss.HeuristicAssigner3D(dist_thre=20).assign(pred, gt, None, gl, q)
+            print('heuristic_assign', name, 'matched', int((r.gt_inds > 0).sum()), 'oracle == reference',
+                  bool(torch.equal(o.gt_inds, r.gt_inds) and torch.equal(o.labels, r.labels)), cmp(o.max_overlaps, r.max_overlaps))
+            cases[name] = dict(gt_inds=r.gt_inds, max_overlaps=r.max_overlaps, labels=r.labels)
+        save('heuristic_assign', dict(pred=pred, gt=gt, gt_labels=gl, query_labels=ql, dist_thre=20, cases=cases))
+
     # --- G5: decoder (hidden 128 is hard-coded in DynamicConv) ----------------------------------------
     for tag, aug in (('decoder_small', False), ('decoder_small_aug', True)):
         seed = 1600
