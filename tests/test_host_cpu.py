@@ -384,10 +384,13 @@ def _grad_worker(rank, world, port, ret):
         with torch.enable_grad():
             ((m(x[sl], x[sl]) - tgt[sl]) ** 2).sum().backward()
         buckets = GradBuckets(bucket_bytes=2048)               # small buckets: several launches during the "backward"
-        grads = [p.grad for p in m.parameters() if p.grad is not None]
-        for gr in reversed(grads):                              # the order a backward pass produces them
-            buckets.add(gr)
+        from deepinteraction_b200.train import GradSink          # the training step's gradient store feeds the buckets
+        params = [p for p in m.parameters() if p.grad is not None]
+        sink = GradSink({id(p): str(i) for i, p in enumerate(params)}, lambda n, t: buckets.add(t))
+        for p in reversed(params):                              # the order a backward pass produces them
+            sink[id(p)] = p.grad
         buckets.finish()
+        grads = [sink[id(p)] for p in params]                   # overwritten in place with the rank average
         # single-process reference over all frames (averaged over ranks, as DDP does)
         ref = om.LocalContextAttentionBlock(16, 16, 9).eval()
         ref.load_state_dict(m.state_dict())
